@@ -1,0 +1,209 @@
+"""ORACLE / TEST INFRASTRUCTURE ONLY.
+
+Generates tests/golden/*.pt by running the UNMODIFIED reference Python (imported from /root/reference/src through
+oracle/ref_harness.py) on CPU.  Run in the build container only:
+
+    python -m oracle.gen_golden [--only filters|regressor|loop|midu]
+
+The reference ships no tests/fixtures, so these vectors are the pin for the standalone oracle
+(oracle/oracle.py) and, through it, for the CUDA path.  Inputs are regenerated from seeds at test time; only outputs
+and small inputs are stored.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import tempfile
+import time
+
+import torch
+
+from . import oracle as O
+from . import ref_harness
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _ref_clf(r, sd):
+    tmp = tempfile.mkdtemp()
+    path = os.path.join(tmp, "va_pred_all")
+    torch.save(sd, path)
+    return r.ValenceArousalLoss(path, torch.device("cpu"), 1, is_minimized=True, requires_grad=True)
+
+
+def filter_cases():
+    """(name, trans list, x vector) cases exercising every branch of the default 8 filters + the 6 'next' ones."""
+    cases = []
+    d = O.DEFAULT_FILTERS
+    lay = O.param_layout(d)
+    x_id = O.init_x0(d)
+    cases.append(("identity", d, x_id.clone()))
+    g = torch.Generator().manual_seed(7)
+    x = x_id + 0.15 * torch.randn(41, generator=g)
+    x[lay['blur'][0]] = 1.3
+    x[lay['sharp'][0]] = 0.7
+    x[lay['scale'][0]:lay['scale'][0] + 4] = torch.tensor([1.2, 1.1, 9.0, 14.0])
+    cases.append(("perturbed", d, x.clone()))
+    x = x_id + 0.3 * torch.randn(41, generator=g)
+    x[lay['blur'][0]] = 3.0
+    x[lay['sharp'][0]] = 1.8          # clamped-blend branch
+    x[lay['contrast'][0]] = 1.6
+    x[lay['exposure'][0]] = 0.8       # saturating exposure -> many ties at 1.0 in rgb_to_hsv
+    x[lay['scale'][0]:lay['scale'][0] + 4] = torch.tensor([1.5, 1.0, 30.0, 5.0])
+    cases.append(("strong", d, x.clone()))
+    x = x_id.clone()
+    x[lay['contrast'][0]] = -0.2      # :291 host branch -> python float 0.0
+    x[lay['sharp'][0]] = 1.0          # blend returns input2
+    x[lay['saturation'][0]] = 0.0
+    x[lay['scale'][0]:lay['scale'][0] + 4] = torch.tensor([0.7, 0.9, -3.0, 500.0])   # clamps active
+    cases.append(("branches", d, x.clone()))
+    # single filters, non default ('next' row): bw needs a 1-d param in the reference -> skipped there
+    for name, val in (("gamma", 1.4), ("bright", 0.2), ("hue", 0.6), ("wb", 0.5)):
+        cases.append((f"single_{name}", [name, "contrast"], torch.tensor([val, 1.0])))
+    return cases
+
+
+def gen_filters(r):
+    out = {}
+    for h, w in ((40, 48), (33, 57)):
+        im = O.synthetic_image(5, h, w)[None]
+        for name, trans, x in filter_cases():
+            p_t, _ = r.optimize_image_param.init_params(trans)
+            xv = x.clone().requires_grad_(True)
+            imv = im.clone().requires_grad_(True)
+            px = r.optimize_image_param.get_params_from_vector(xv, 1, p_t, im.size(2))
+            outs = r.image_transformations.apply_params(imv, px)
+            gen = torch.Generator().manual_seed(11)
+            gout = torch.randn(outs[-1].shape, generator=gen)
+            gx, gim = torch.autograd.grad((outs[-1] * gout).sum(), [xv, imv], allow_unused=True)
+            out[f"{name}_{h}x{w}"] = dict(trans=list(trans), x=x.clone(), h=h, w=w, image_index=5,
+                                         stages=[o.detach().clone() for o in (outs if name in ('perturbed', 'strong') else outs[-1:])],
+                                         gout_seed=11,
+                                         grad_x=gx.detach().clone() if gx is not None else torch.zeros_like(x),
+                                         grad_im=gim.detach().clone())
+    # per-filter chains (each filter alone, with its own gradient) for per-kernel parity
+    im = O.synthetic_image(6, 36, 44)[None]
+    singles = {}
+    for name, vals in (("exposure", [0.0, 0.4, -0.7]), ("saturation", [1.0, 0.0, 1.7, 0.4]),
+                       ("contrast", [1.0, 0.5, 1.8]), ("sharp", [0.0, 0.5, 1.0, 2.5]),
+                       ("blur", [1e-4, 0.5, 2.0, 6.0])):
+        for v in vals:
+            trans = [name] if name == "contrast" else [name, "contrast"]
+            x = torch.tensor([v] if name == "contrast" else [v, 1.0])
+            p_t, _ = r.optimize_image_param.init_params(trans)
+            xv = x.clone().requires_grad_(True)
+            imv = im.clone().requires_grad_(True)
+            px = r.optimize_image_param.get_params_from_vector(xv, 1, p_t, im.size(2))
+            o1 = r.image_transformations.apply_params(imv, {name: px[name]})[-1]
+            gen = torch.Generator().manual_seed(13)
+            gout = torch.randn(o1.shape, generator=gen)
+            gx, gim = torch.autograd.grad((o1 * gout).sum(), [xv, imv], allow_unused=True)
+            singles[f"{name}_{v}"] = dict(name=name, value=v, out=o1.detach().clone(),
+                                          grad_p=(gx[0].clone() if gx is not None else torch.tensor(0.0)),
+                                          grad_im=gim.detach().clone())
+    out["singles"] = dict(image_index=6, h=36, w=44, gout_seed=13, cases=singles)
+    torch.save(out, os.path.join(GOLDEN_DIR, "filters.pt"))
+    print("filters.pt:", len(out), "entries")
+
+
+def gen_regressor(r):
+    sd = O.make_regressor_state_dict()
+    clf = _ref_clf(r, sd)
+    out = {"weights_probe": {k: sd[k].flatten()[:4].clone() for k in
+                             ("conv1.weight", "layer3.2.conv2.weight", "layer4.2.bn3.bias", "fc.weight")}}
+    for tag, (h, w) in {"up256": (256, 256), "down512": (512, 512), "same480": (480, 480),
+                        "rect300x400": (300, 400)}.items():
+        img = O.synthetic_image(3, h, w)[None].requires_grad_(True)
+        torch.manual_seed(4242)
+        loss = 0.15 * clf(img, target=torch.tensor([[0.9, 0.4]]))
+        g, = torch.autograd.grad(loss, img)
+        torch.manual_seed(4242)
+        oh, ow = O.resize_output_size(h, w, 480)
+        offs = O.draw_crop_offsets(1, 1, oh, ow)
+        out[tag] = dict(h=h, w=w, image_index=3, offsets=offs[0], pred=clf.fake_loss_metric.detach().clone(),
+                        loss=loss.detach().clone(), grad_abs_sum=g.abs().sum(), grad_max=g.abs().max(),
+                        grad_ds=g[0, :, ::8, ::8].clone(), grad_patch=g[0, :, :32, :32].clone(),
+                        target=torch.tensor([[0.9, 0.4]]), weight_clf=0.15)
+        print(tag, out[tag]["pred"], float(loss), float(g.abs().max()))
+    torch.save(out, os.path.join(GOLDEN_DIR, "regressor.pt"))
+
+
+def gen_loop(r, h=256, w=256, num_steps=50, tag="c1", image_index=0):
+    """BASELINE.json configs[0]: one synthetic 256x256 image, random-init regressor, 50 steps, CPU."""
+    sd = O.make_regressor_state_dict()
+    clf = _ref_clf(r, sd)
+    image = O.synthetic_image(image_index, h, w)[None]
+    torch.manual_seed(2000 + image_index)
+    obj = {"clf": clf, "dis": None, "weight_clf": 0.15, "weight_dis": 0.0, "weight_recon": 0.0, "alpha": 0.1}
+    x0, obj = r.optimize_image_param.initialize_parametric(image, obj)
+    obj["target"] = r.optimize_image.get_condition_from_alpha(obj["alpha"], obj["clf"], image)
+    del obj["alpha"]
+    losses, preds, xs = [], [], []
+    orig = r.optimize_image_param.objective_function_parametric
+
+    def wrapped(x, **kw):
+        xs.append(x.detach().clone())
+        l = orig(x, **kw)
+        losses.append(float(l))
+        preds.append(clf.fake_loss_metric.detach().clone()[0])
+        return l
+
+    t0 = time.perf_counter()
+    best_x = r.optimize_image.optimization(x0, obj, wrapped, learning_rate=0.05, num_steps=num_steps)
+    dt = time.perf_counter() - t0
+    with torch.no_grad():
+        px = r.optimize_image_param.get_params_from_vector(best_x, 1, obj["params"], image.size(2))
+        edited = r.image_transformations.apply_params(image, px)[-1]
+    torch.manual_seed(2000 + image_index)
+    offs = O.draw_crop_offsets(1 + num_steps, 1, 480, 480)
+    out = dict(h=h, w=w, num_steps=num_steps, image_index=image_index, alpha=0.1, learning_rate=0.05, weight_clf=0.15,
+               target=obj["target"].clone(), losses=torch.tensor(losses), preds=torch.stack(preds),
+               xs=torch.stack(xs), best_x=best_x.clone(), edited=edited.clone(), offsets=offs,
+               ref_seconds=dt, ref_threads=torch.get_num_threads())
+    torch.save(out, os.path.join(GOLDEN_DIR, f"loop_{tag}.pt"))
+    print(f"loop_{tag}.pt: {num_steps} steps in {dt:.1f}s; loss {losses[0]:.6f} -> {min(losses):.6f}")
+
+
+def gen_midu(r):
+    import importlib
+    ref_harness.install()
+    Midu = importlib.import_module("guidance_classifier.MiduClassifier").MiduClassifier
+    scores = importlib.import_module("guidance_classifier.guidance_scores")
+    out = {}
+    for is_sdxl, hw in ((False, 8), (True, 32)):
+        torch.manual_seed(0)
+        m = Midu._create_midu_classifier("cpu", 2, is_sdxl)
+        g = torch.Generator().manual_seed(3000)
+        feat = torch.randn(2, 1280, hw, hw, generator=g).requires_grad_(True)
+        pred = m(feat)
+        loss = scores.valence_arousal_score(pred, "cpu", True, None)
+        gf, = torch.autograd.grad(loss, feat)
+        out["sdxl" if is_sdxl else "sd"] = dict(seed=0, feat_seed=3000, hw=hw, pred=pred.detach().clone(),
+                                                  loss=loss.detach().clone(), grad_abs_sum=gf.abs().sum(),
+                                                  grad_slice=gf[:, ::64, ::2, ::2].clone())
+    torch.save(out, os.path.join(GOLDEN_DIR, "midu.pt"))
+    print("midu.pt written")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    args = ap.parse_args()
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    r = ref_harness.ref()
+    todo = [args.only] if args.only else ["filters", "midu", "regressor", "loop"]
+    if "filters" in todo:
+        gen_filters(r)
+    if "midu" in todo:
+        gen_midu(r)
+    if "regressor" in todo:
+        gen_regressor(r)
+    if "loop" in todo:
+        gen_loop(r)
+    if "loop512" in todo:
+        gen_loop(r, 512, 512, 10, "c2_10steps", image_index=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,17 @@
+// Error plumbing + version for the C ABI (include/rgie.h).
+#include "common.cuh"
+#include "rgie.h"
+
+namespace rgie {
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(const std::string& msg) {
+  g_last_error = msg;
+  return RGIE_ERR;
+}
+}  // namespace rgie
+
+extern "C" {
+int rgie_version(void) { return RGIE_ABI_VERSION; }
+const char* rgie_last_error(void) { return rgie::g_last_error.c_str(); }
+}

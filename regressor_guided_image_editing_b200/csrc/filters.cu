@@ -1,0 +1,887 @@
+// Parametric photo-filter kernels (forward + backward) for the default 8-filter chain of the reference
+// (src/baselines/image_transformations/image_transformations.py:7-66, img_trans_torch_diff.py, kornia 0.8.2 calls).
+//
+// Layout: images NCHW fp32 contiguous [B,3,H,W] in [0,1]; every filter is followed by clamp(0,1) exactly as
+// apply_params does (:60).  Parameters are the EFFECTIVE per-image values (after the reference's own clamps, which live
+// in the host mirror / the param-transform kernel): `p` points at image 0's values, `p_stride` floats between images
+// (0 = shared by the batch).  Backward kernels produce d(in) and per-image d(param) through a deterministic two-stage
+// reduction (warp shuffle -> block partials in `ws` -> fixed-order finalize), no atomics.
+//
+// All kernels are HBM-bound elementwise/stencil passes: float4-vectorised over pixels when H*W % 4 == 0.
+#include "common.cuh"
+#include "rgie.h"
+
+namespace rgie {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxBlk = 128;       // blocks per image along x (partials per image)
+constexpr float kTwoPi = 6.283185307179586f;
+
+__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
+__device__ __forceinline__ bool in01(float v) { return v >= 0.f && v <= 1.f; }   // torch clamp backward: inclusive
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-reduce NP per-thread accumulators, thread 0 writes them to dst[0..NP)
+template <int NP>
+__device__ __forceinline__ void block_reduce_store(float* acc, float* dst) {
+  __shared__ float red[kThreads / 32][NP > 0 ? NP : 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    float v = warp_sum(acc[i]);
+    if (lane == 0) red[warp][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NP) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) s += red[w][threadIdx.x];
+    dst[threadIdx.x] = s;
+  }
+}
+
+// finalize: out[b*stride + i] = sum_k partial[(b*nblk + k)*NP + i]
+__global__ void finalize_partials(const float* __restrict__ partial, int nblk, int NP, float* __restrict__ out, int stride) {
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < NP; i += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < nblk; ++k) s += partial[((long)b * nblk + k) * NP + i];
+    out[(long)b * stride + i] = s;
+  }
+}
+
+__global__ void copy_strided_kernel(const float* __restrict__ src, int src_stride, float* __restrict__ dst,
+                                    int dst_stride, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[(long)i * dst_stride] = src[(long)i * src_stride];
+}
+
+struct LaunchShape {
+  int nblk;    // blocks per image
+  int chunk;   // pixels per block (multiple of 4)
+};
+LaunchShape shape_for(int HW) {
+  LaunchShape s;
+  s.nblk = ceil_div(HW, 2048);
+  if (s.nblk > kMaxBlk) s.nblk = kMaxBlk;
+  if (s.nblk < 1) s.nblk = 1;
+  s.chunk = ceil_div(ceil_div(HW, s.nblk), 4) * 4;
+  return s;
+}
+
+// ===============================================================================================================
+// Pointwise ops (one RGB pixel in, one RGB pixel out)
+// ===============================================================================================================
+struct ExposureOp {            // F1: img_trans_torch_diff.py:60-64
+  static constexpr int NP = 1;
+  const float* p; int stride; float s;
+  __device__ void load(int b) { s = expf(__fmul_rn(p[(long)b * stride], logf(2.0f))); }
+  __device__ void fwd(const float* x, float* y) const {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) y[c] = clamp01(__fmul_rn(x[c], s));
+  }
+  __device__ void bwd(const float* x, const float* g, float* gx, float* gp) const {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float pre = __fmul_rn(x[c], s);
+      float gg = in01(pre) ? g[c] : 0.f;
+      gx[c] = gg * s;
+      gp[0] += gg * x[c] * s * 0.6931471805599453f;
+    }
+  }
+};
+
+struct SaturationOp {          // F2: kornia.enhance.adjust_saturation (rgb_to_hsv -> s*=f, clamp -> hsv_to_rgb)
+  static constexpr int NP = 1;
+  const float* p; int stride; float F;
+  __device__ void load(int b) { F = p[(long)b * stride]; }
+
+  struct Mid { float M, mn, delta, dc, hnum, hsel, s, v, s2pre, s2, f; int a, imin, hi; };
+
+  __device__ void forward_mid(const float* x, Mid& m, float* y) const {
+    const float r = x[0], g = x[1], b = x[2];
+    m.a = (r >= g && r >= b) ? 0 : (g >= b ? 1 : 2);              // first max (torch CPU tie rule)
+    m.imin = (r <= g && r <= b) ? 0 : (g <= b ? 1 : 2);           // first min
+    m.M = fmaxf(r, fmaxf(g, b));
+    m.mn = fminf(r, fminf(g, b));
+    m.delta = m.M - m.mn;
+    m.v = m.M;
+    m.s = m.delta / (m.M + 1e-8f);
+    m.dc = (m.delta == 0.f) ? 1.f : m.delta;
+    const float rc = m.M - r, gc = m.M - g, bc = m.M - b;
+    m.hnum = (m.a == 0) ? (bc - gc) : (m.a == 1 ? __fadd_rn(rc - bc, __fmul_rn(2.0f, m.dc))
+                                                 : __fadd_rn(gc - rc, __fmul_rn(4.0f, m.dc)));
+    m.hsel = m.hnum / m.dc;
+    float hm = fmodf(m.hsel / 6.0f, 1.0f);
+    if (hm != 0.f && hm < 0.f) hm += 1.0f;
+    const float h = __fmul_rn(kTwoPi, hm);
+    m.s2pre = __fmul_rn(m.s, F);
+    m.s2 = clamp01(m.s2pre);
+    // hsv_to_rgb
+    const float hn = h / kTwoPi;
+    const float h6 = __fmul_rn(hn, 6.0f);
+    float fl = floorf(h6);
+    float him = fmodf(fl, 6.0f);
+    if (him != 0.f && him < 0.f) him += 6.0f;
+    float h6m = fmodf(h6, 6.0f);
+    if (h6m != 0.f && h6m < 0.f) h6m += 6.0f;
+    m.f = h6m - him;
+    m.hi = (int)him;
+    const float v = m.v, s2 = m.s2, f = m.f;
+    const float pp = __fmul_rn(v, 1.0f - s2);
+    const float qq = __fmul_rn(v, 1.0f - __fmul_rn(f, s2));
+    const float tt = __fmul_rn(v, 1.0f - __fmul_rn(1.0f - f, s2));
+    switch (m.hi) {
+      case 0: y[0] = v; y[1] = tt; y[2] = pp; break;
+      case 1: y[0] = qq; y[1] = v; y[2] = pp; break;
+      case 2: y[0] = pp; y[1] = v; y[2] = tt; break;
+      case 3: y[0] = pp; y[1] = qq; y[2] = v; break;
+      case 4: y[0] = tt; y[1] = pp; y[2] = v; break;
+      default: y[0] = v; y[1] = pp; y[2] = qq; break;
+    }
+  }
+  __device__ void fwd(const float* x, float* y) const {
+    Mid m;
+    forward_mid(x, m, y);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) y[c] = clamp01(y[c]);
+  }
+  __device__ void bwd(const float* x, const float* g, float* gx, float* gp) const {
+    Mid m;
+    float y[3];
+    forward_mid(x, m, y);
+    float go[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) go[c] = in01(y[c]) ? g[c] : 0.f;
+    float g_v = 0.f, g_p = 0.f, g_q = 0.f, g_t = 0.f;
+    switch (m.hi) {
+      case 0: g_v = go[0]; g_t = go[1]; g_p = go[2]; break;
+      case 1: g_q = go[0]; g_v = go[1]; g_p = go[2]; break;
+      case 2: g_p = go[0]; g_v = go[1]; g_t = go[2]; break;
+      case 3: g_p = go[0]; g_q = go[1]; g_v = go[2]; break;
+      case 4: g_t = go[0]; g_p = go[1]; g_v = go[2]; break;
+      default: g_v = go[0]; g_p = go[1]; g_q = go[2]; break;
+    }
+    const float v = m.v, s2 = m.s2, f = m.f;
+    float gv = g_v + g_p * (1.0f - s2) + g_q * (1.0f - f * s2) + g_t * (1.0f - (1.0f - f) * s2);
+    float gs2 = -v * (g_p + f * g_q + (1.0f - f) * g_t);
+    float gf = v * s2 * (g_t - g_q);
+    // f <- h6 <- hn <- h <- hmod <- hsel   (floor / integer parts carry no gradient)
+    float ghsel = (((gf * 6.0f) / kTwoPi) * kTwoPi) / 6.0f;
+    float gpre = in01(m.s2pre) ? gs2 : 0.f;
+    float gs = gpre * F;
+    gp[0] += gpre * m.s;
+    float ghnum = ghsel / m.dc;
+    float gdc = -ghsel * m.hsel / m.dc;
+    float grc = 0.f, ggc = 0.f, gbc = 0.f;
+    if (m.a == 0) { gbc += ghnum; ggc -= ghnum; }
+    else if (m.a == 1) { grc += ghnum; gbc -= ghnum; gdc += 2.0f * ghnum; }
+    else { ggc += ghnum; grc -= ghnum; gdc += 4.0f * ghnum; }
+    float gM = grc + ggc + gbc;
+    gx[0] = -grc; gx[1] = -ggc; gx[2] = -gbc;
+    float gdelta = (m.delta != 0.f) ? gdc : 0.f;
+    const float Me = m.M + 1e-8f;
+    gdelta += gs / Me;
+    gM += -gs * m.s / Me;
+    gM += gv;
+    gM += gdelta;
+    const float gmn = -gdelta;
+    gx[m.a] += gM;
+    gx[m.imin] += gmn;
+  }
+};
+
+template <int NCURVE>          // F3 (tone: NCURVE=1, shared by RGB) / F4 (color: NCURVE=3): img_trans_torch_diff.py:6-19
+struct CurveOp {
+  static constexpr int NP = 8 * NCURVE;
+  const float* p; int stride; float w[NP];
+  __device__ void load(int b) {
+#pragma unroll
+    for (int i = 0; i < NP; ++i) w[i] = p[(long)b * stride + i];
+  }
+  __device__ void fwd(const float* x, float* y) const {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* wc = w + (NCURVE == 3 ? 8 * c : 0);
+      float tot = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        tot = __fadd_rn(tot, __fmul_rn(fminf(fmaxf(x[c] - 0.125f * i, 0.f), 0.125f), wc[i]));
+      y[c] = clamp01(fminf(tot, 1.0f));
+    }
+  }
+  __device__ void bwd(const float* x, const float* g, float* gx, float* gp) const {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* wc = w + (NCURVE == 3 ? 8 * c : 0);
+      float* gpc = gp + (NCURVE == 3 ? 8 * c : 0);
+      float tot = 0.f, seg[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        seg[i] = fminf(fmaxf(x[c] - 0.125f * i, 0.f), 0.125f);
+        tot = __fadd_rn(tot, __fmul_rn(seg[i], wc[i]));
+      }
+      const float gg = in01(tot) ? g[c] : 0.f;    // clamp(max=1) then clamp(0,1): passes iff 0 <= tot <= 1
+      float dx = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        gpc[i] += gg * seg[i];
+        const float u = x[c] - 0.125f * i;
+        if (u >= 0.f && u <= 0.125f) dx += wc[i];
+      }
+      gx[c] = gg * dx;
+    }
+  }
+};
+
+struct ContrastOp {            // F5: kornia adjust_contrast_with_mean_subtraction (mean computed by gray_mean_kernel)
+  static constexpr int NP = 2;                  // [0]: sum g*(x-mu) = d/df ; [1]: sum g = G (mean path)
+  const float* p; int stride; const float* mu_all; float f, mu;
+  __device__ void load(int b) { f = p[(long)b * stride]; mu = mu_all[b]; }
+  __device__ void fwd(const float* x, float* y) const {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) y[c] = clamp01(__fadd_rn(__fmul_rn(x[c], f), __fmul_rn(mu, 1.0f - f)));
+  }
+  // first backward pass: masked gradient gm (written in place of gx), reductions for df and the mean path
+  __device__ void bwd(const float* x, const float* g, float* gx, float* gp) const {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float pre = __fadd_rn(__fmul_rn(x[c], f), __fmul_rn(mu, 1.0f - f));
+      const float gg = in01(pre) ? g[c] : 0.f;
+      gx[c] = gg * f;
+      gp[0] += gg * (x[c] - mu);
+      gp[1] += gg;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+template <class Op, int VEC, bool BWD>
+__global__ void __launch_bounds__(kThreads) pointwise_kernel(const float* __restrict__ in, const float* __restrict__ gout,
+                                                            float* __restrict__ out, Op op, float* __restrict__ partial,
+                                                            int HW, int chunk) {
+  const int b = blockIdx.y;
+  op.load(b);
+  const long base = (long)b * 3 * HW;
+  const int p0 = blockIdx.x * chunk;
+  const int p1 = min(p0 + chunk, HW);
+  float acc[Op::NP > 0 ? Op::NP : 1];
+#pragma unroll
+  for (int i = 0; i < Op::NP; ++i) acc[i] = 0.f;
+  for (int px = p0 + threadIdx.x * VEC; px < p1; px += kThreads * VEC) {
+    float x[3][VEC], g[3][VEC], y[3][VEC];
+    if (VEC == 4) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float4 v = *reinterpret_cast<const float4*>(in + base + (long)c * HW + px);
+        x[c][0] = v.x; x[c][1] = v.y; x[c][2] = v.z; x[c][3] = v.w;
+        if (BWD) {
+          float4 gv = *reinterpret_cast<const float4*>(gout + base + (long)c * HW + px);
+          g[c][0] = gv.x; g[c][1] = gv.y; g[c][2] = gv.z; g[c][3] = gv.w;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        x[c][0] = in[base + (long)c * HW + px];
+        if (BWD) g[c][0] = gout[base + (long)c * HW + px];
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float xi[3] = {x[0][v], x[1][v], x[2][v]}, yo[3];
+      if (BWD) {
+        float gi[3] = {g[0][v], g[1][v], g[2][v]};
+        op.bwd(xi, gi, yo, acc);
+      } else {
+        op.fwd(xi, yo);
+      }
+      y[0][v] = yo[0]; y[1][v] = yo[1]; y[2][v] = yo[2];
+    }
+    if (VEC == 4) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        *reinterpret_cast<float4*>(out + base + (long)c * HW + px) = make_float4(y[c][0], y[c][1], y[c][2], y[c][3]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) out[base + (long)c * HW + px] = y[c][0];
+    }
+  }
+  if (BWD && Op::NP > 0) block_reduce_store<Op::NP>(acc, partial + ((long)b * gridDim.x + blockIdx.x) * Op::NP);
+}
+
+template <class Op, bool BWD>
+int launch_pointwise(const float* in, const float* gout, float* out, Op op, float* partial, int B, int HW,
+                     cudaStream_t st) {
+  LaunchShape s = shape_for(HW);
+  dim3 grid(s.nblk, B);
+  if (HW % 4 == 0) pointwise_kernel<Op, 4, BWD><<<grid, kThreads, 0, st>>>(in, gout, out, op, partial, HW, s.chunk);
+  else pointwise_kernel<Op, 1, BWD><<<grid, kThreads, 0, st>>>(in, gout, out, op, partial, HW, s.chunk);
+  RGIE_LAUNCH_OK();
+  return 0;
+}
+
+// gray mean (contrast): partial sums of 0.299r + 0.587g + 0.114b
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) gray_sum_kernel(const float* __restrict__ in, float* __restrict__ partial,
+                                                           int HW, int chunk) {
+  const int b = blockIdx.y;
+  const long base = (long)b * 3 * HW;
+  const int p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, HW);
+  float acc[1] = {0.f};
+  for (int px = p0 + threadIdx.x * VEC; px < p1; px += kThreads * VEC) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const float r = in[base + px + v], g = in[base + HW + px + v], bl = in[base + 2L * HW + px + v];
+      acc[0] += __fadd_rn(__fadd_rn(__fmul_rn(0.299f, r), __fmul_rn(0.587f, g)), __fmul_rn(0.114f, bl));
+    }
+  }
+  block_reduce_store<1>(acc, partial + (long)b * gridDim.x + blockIdx.x);
+}
+__global__ void gray_mean_finalize(const float* __restrict__ partial, int nblk, float inv_hw, float* __restrict__ mu) {
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int k = 0; k < nblk; ++k) s += partial[(long)b * nblk + k];
+    mu[b] = s * inv_hw;
+  }
+}
+
+// contrast backward, second pass: gin = gm (already g*mask*f) + w_c * (1-f) * G / HW
+__global__ void __launch_bounds__(kThreads) contrast_bwd_mean_kernel(float* __restrict__ gin, const float* __restrict__ p,
+                                                                    int stride, const float* __restrict__ sums,
+                                                                    int sum_stride, int HW) {
+  const int b = blockIdx.y;
+  const float f = p[(long)b * stride];
+  const float G = sums[(long)b * sum_stride + 1];
+  const float k = (1.0f - f) * G / (float)HW;
+  const float wc[3] = {0.299f, 0.587f, 0.114f};
+  const long base = (long)b * 3 * HW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * HW; i += gridDim.x * blockDim.x) gin[base + i] += wc[i / HW] * k;
+}
+
+// ===============================================================================================================
+// F6 sharpness: kornia.enhance.sharpness -- 3x3 [[1,1,1],[1,5,1],[1,1,1]]/13 'valid' smoothing, border keeps input,
+//               _blend_one(degenerate, input, factor) with its ==0 / ==1 / (0,1) / else branches
+// ===============================================================================================================
+__device__ __forceinline__ float sharp_conv(const float* __restrict__ pl, int y, int x, int W) {
+  const float k1 = 1.0f / 13.0f, k5 = 5.0f / 13.0f;
+  const float* r0 = pl + (long)(y - 1) * W + x;
+  const float* r1 = r0 + W;
+  const float* r2 = r1 + W;
+  float s = 0.f;
+  s = fmaf(k1, r0[-1], s); s = fmaf(k1, r0[0], s); s = fmaf(k1, r0[1], s);
+  s = fmaf(k1, r1[-1], s); s = fmaf(k5, r1[0], s); s = fmaf(k1, r1[1], s);
+  s = fmaf(k1, r2[-1], s); s = fmaf(k1, r2[0], s); s = fmaf(k1, r2[1], s);
+  return s;
+}
+
+// mode: 0 -> factor==0 (result), 1 -> factor==1 (input), 2 -> 0<f<1 (no inner clamp), 3 -> clamp
+__device__ __forceinline__ int sharp_mode(float f) { return f == 0.f ? 0 : (f == 1.f ? 1 : ((f > 0.f && f < 1.f) ? 2 : 3)); }
+
+__global__ void __launch_bounds__(kThreads) sharp_fwd_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                            const float* __restrict__ p, int stride, int H, int W) {
+  const int b = blockIdx.z, c = blockIdx.y;
+  const float f = p[(long)b * stride];
+  const int mode = sharp_mode(f);
+  const float* pl = in + ((long)b * 3 + c) * H * W;
+  float* po = out + ((long)b * 3 + c) * H * W;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+    const int y = i / W, x = i - y * W;
+    const float xin = pl[i];
+    float result = xin;
+    if (y >= 1 && y < H - 1 && x >= 1 && x < W - 1) result = clamp01(sharp_conv(pl, y, x, W));
+    float o;
+    if (mode == 0) o = result;
+    else if (mode == 1) o = xin;
+    else {
+      o = __fadd_rn(result, __fmul_rn(xin - result, f));
+      if (mode == 3) o = clamp01(o);
+    }
+    po[i] = clamp01(o);
+  }
+}
+
+// backward pass A: gdeg (gradient w.r.t. the clamped 3x3 smoothing, zero on the border) and the direct d(in) term;
+// partial sums of d(factor)
+__global__ void __launch_bounds__(kThreads) sharp_bwd_a_kernel(const float* __restrict__ in, const float* __restrict__ gout,
+                                                              float* __restrict__ gdeg, float* __restrict__ gin,
+                                                              const float* __restrict__ p, int stride,
+                                                              float* __restrict__ partial, int H, int W) {
+  const int b = blockIdx.z, c = blockIdx.y;
+  const float f = p[(long)b * stride];
+  const int mode = sharp_mode(f);
+  const long off = ((long)b * 3 + c) * H * W;
+  const float* pl = in + off;
+  float acc[1] = {0.f};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+    const int y = i / W, x = i - y * W;
+    const float xin = pl[i];
+    const bool interior = y >= 1 && y < H - 1 && x >= 1 && x < W - 1;
+    float conv = 0.f, result = xin;
+    if (interior) { conv = sharp_conv(pl, y, x, W); result = clamp01(conv); }
+    float g = gout[off + i];
+    float g_res = 0.f, g_x = 0.f;
+    if (mode == 0) { g = in01(result) ? g : 0.f; g_res = g; }
+    else if (mode == 1) { g = in01(xin) ? g : 0.f; g_x = g; }
+    else {
+      const float o = __fadd_rn(result, __fmul_rn(xin - result, f));
+      g = in01(o) ? g : 0.f;       // inner clamp (mode 3) and outer clamp have the same range
+      g_res = g - g * f;
+      g_x = g * f;
+      acc[0] += g * (xin - result);
+    }
+    if (interior) gdeg[off + i] = in01(conv) ? g_res : 0.f;
+    else { gdeg[off + i] = 0.f; g_x += g_res; }
+    gin[off + i] = g_x;
+  }
+  block_reduce_store<1>(acc, partial + ((long)b * 3 + c) * gridDim.x + blockIdx.x);
+}
+// backward pass B: gin += 3x3 correlation of gdeg (symmetric kernel => transpose == same kernel), zero outside
+__global__ void __launch_bounds__(kThreads) sharp_bwd_b_kernel(const float* __restrict__ gdeg, float* __restrict__ gin,
+                                                              int H, int W) {
+  const int b = blockIdx.z, c = blockIdx.y;
+  const long off = ((long)b * 3 + c) * H * W;
+  const float k1 = 1.0f / 13.0f, k5 = 5.0f / 13.0f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+    const int y = i / W, x = i - y * W;
+    float s = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= W) continue;
+        s = fmaf((dy == 0 && dx == 0) ? k5 : k1, gdeg[off + (long)yy * W + xx], s);
+      }
+    }
+    gin[off + i] += s;
+  }
+}
+
+// ===============================================================================================================
+// F7 gaussian blur: kornia.filters.gaussian_blur2d((25,25), sigma, 'reflect', separable) + clamp
+// ===============================================================================================================
+constexpr int kTaps = 25, kRad = 12;
+
+// per-image 1-D kernel w and its sigma-derivative dw; returns true when the kernel is an exact delta (sigma tiny)
+__device__ __forceinline__ bool gauss_weights(float sigma, float* w, float* dw) {
+  float e[kTaps], de[kTaps], Z = 0.f, dZ = 0.f;
+  const float s2 = sigma * sigma;
+#pragma unroll
+  for (int k = 0; k < kTaps; ++k) {
+    const float x = (float)(k - kRad);
+    e[k] = expf(-(x * x) / (2.0f * s2));
+    de[k] = e[k] * (x * x) / (s2 * sigma);
+    Z += e[k];
+    dZ += de[k];
+  }
+  bool delta = true;
+#pragma unroll
+  for (int k = 0; k < kTaps; ++k) {
+    w[k] = e[k] / Z;
+    if (dw) dw[k] = (de[k] - w[k] * dZ) / Z;
+    if (k != kRad && w[k] != 0.f) delta = false;
+  }
+  return delta && w[kRad] == 1.0f;
+}
+__device__ __forceinline__ int reflect(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * (n - 1) - i : i); }
+
+// horizontal pass: t = H_w(in) and (optionally) td = H_dw(in)
+__global__ void __launch_bounds__(kThreads) blur_h_kernel(const float* __restrict__ in, float* __restrict__ t,
+                                                         float* __restrict__ td, const float* __restrict__ p, int stride,
+                                                         int H, int W) {
+  __shared__ float w[kTaps], dw[kTaps];
+  __shared__ int is_delta;
+  const int b = blockIdx.z, c = blockIdx.y;
+  if (threadIdx.x == 0) {
+    float lw[kTaps], ldw[kTaps];
+    is_delta = gauss_weights(p[(long)b * stride], lw, ldw);
+    for (int k = 0; k < kTaps; ++k) { w[k] = lw[k]; dw[k] = ldw[k]; }
+  }
+  __syncthreads();
+  const long off = ((long)b * 3 + c) * H * W;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+    if (is_delta) { t[off + i] = in[off + i]; if (td) td[off + i] = 0.f; continue; }
+    const int y = i / W, x = i - y * W;
+    const float* row = in + off + (long)y * W;
+    float s = 0.f, sd = 0.f;
+#pragma unroll
+    for (int k = 0; k < kTaps; ++k) {
+      const float v = row[reflect(x + k - kRad, W)];
+      s = fmaf(w[k], v, s);
+      sd = fmaf(dw[k], v, sd);
+    }
+    t[off + i] = s;
+    if (td) td[off + i] = sd;
+  }
+}
+// vertical pass (forward): out = clamp(V_w(t))
+__global__ void __launch_bounds__(kThreads) blur_v_kernel(const float* __restrict__ t, float* __restrict__ out,
+                                                         const float* __restrict__ p, int stride, int H, int W) {
+  __shared__ float w[kTaps];
+  __shared__ int is_delta;
+  const int b = blockIdx.z, c = blockIdx.y;
+  if (threadIdx.x == 0) {
+    float lw[kTaps];
+    is_delta = gauss_weights(p[(long)b * stride], lw, nullptr);
+    for (int k = 0; k < kTaps; ++k) w[k] = lw[k];
+  }
+  __syncthreads();
+  const long off = ((long)b * 3 + c) * H * W;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+    if (is_delta) { out[off + i] = clamp01(t[off + i]); continue; }
+    const int y = i / W, x = i - y * W;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kTaps; ++k) s = fmaf(w[k], t[off + (long)reflect(y + k - kRad, H) * W + x], s);
+    out[off + i] = clamp01(s);
+  }
+}
+// backward vertical: pre = V_w(t) -> mask; gm = g*mask; acc += gm * V_dw(t); writes gm (masked gradient)
+__global__ void __launch_bounds__(kThreads) blur_bwd_mask_kernel(const float* __restrict__ t, const float* __restrict__ gout,
+                                                                float* __restrict__ gm, const float* __restrict__ p,
+                                                                int stride, float* __restrict__ partial, int H, int W) {
+  __shared__ float w[kTaps], dw[kTaps];
+  __shared__ int is_delta;
+  const int b = blockIdx.z, c = blockIdx.y;
+  if (threadIdx.x == 0) {
+    float lw[kTaps], ldw[kTaps];
+    is_delta = gauss_weights(p[(long)b * stride], lw, ldw);
+    for (int k = 0; k < kTaps; ++k) { w[k] = lw[k]; dw[k] = ldw[k]; }
+  }
+  __syncthreads();
+  const long off = ((long)b * 3 + c) * H * W;
+  float acc[1] = {0.f};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+    if (is_delta) { gm[off + i] = in01(t[off + i]) ? gout[off + i] : 0.f; continue; }
+    const int y = i / W, x = i - y * W;
+    float s = 0.f, sd = 0.f;
+#pragma unroll
+    for (int k = 0; k < kTaps; ++k) {
+      const float v = t[off + (long)reflect(y + k - kRad, H) * W + x];
+      s = fmaf(w[k], v, s);
+      sd = fmaf(dw[k], v, sd);
+    }
+    const float g = in01(s) ? gout[off + i] : 0.f;
+    gm[off + i] = g;
+    acc[0] += g * sd;
+  }
+  block_reduce_store<1>(acc, partial + ((long)b * 3 + c) * gridDim.x + blockIdx.x);
+}
+// transpose of a reflect-padded 25-tap correlation along one axis (AXIS 0 = vertical, 1 = horizontal):
+//   z[u] = sum_k w[k] * g[u - k + 12] on the padded domain (g = 0 outside), out[i] = z[i] + z[-i] + z[2(n-1)-i]
+// optional: acc += out * other  (second d(sigma) term)
+template <int AXIS>
+__global__ void __launch_bounds__(kThreads) blur_bwd_t_kernel(const float* __restrict__ g, float* __restrict__ out,
+                                                             const float* __restrict__ other, const float* __restrict__ p,
+                                                             int stride, float* __restrict__ partial, int H, int W) {
+  __shared__ float w[kTaps];
+  __shared__ int is_delta;
+  const int b = blockIdx.z, c = blockIdx.y;
+  if (threadIdx.x == 0) {
+    float lw[kTaps];
+    is_delta = gauss_weights(p[(long)b * stride], lw, nullptr);
+    for (int k = 0; k < kTaps; ++k) w[k] = lw[k];
+  }
+  __syncthreads();
+  const long off = ((long)b * 3 + c) * H * W;
+  const int n = AXIS == 0 ? H : W;
+  float acc[1] = {0.f};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+    if (is_delta) { out[off + i] = g[off + i]; continue; }
+    const int y = i / W, x = i - y * W;
+    const int pos = AXIS == 0 ? y : x;
+    float s = 0.f;
+    int us[3] = {pos, -pos, 2 * (n - 1) - pos};
+    bool ok[3] = {true, pos >= 1 && pos <= kRad, pos <= n - 2 && pos >= n - 1 - kRad};
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      if (!ok[q]) continue;
+#pragma unroll
+      for (int k = 0; k < kTaps; ++k) {
+        const int src = us[q] - k + kRad;
+        if (src < 0 || src >= n) continue;
+        const float v = AXIS == 0 ? g[off + (long)src * W + x] : g[off + (long)y * W + src];
+        s = fmaf(w[k], v, s);
+      }
+    }
+    out[off + i] = s;
+    if (other) acc[0] += s * other[off + i];
+  }
+  if (other) block_reduce_store<1>(acc, partial + ((long)b * 3 + c) * gridDim.x + blockIdx.x);
+}
+
+// ===============================================================================================================
+// F8 scale: kornia.geometry.transform.scale -> warp_affine -> affine_grid/grid_sample (bilinear, zeros, align_corners)
+//   p = (sx, sy, cx, cy);  M = [[sx,0,(1-sx)cx],[0,sy,(1-sx)cy]]  (kornia reuses alpha=M00 for both translations)
+// ===============================================================================================================
+struct WarpCoef { float inv_sx, inv_sy, t02, t12; };
+__device__ __forceinline__ WarpCoef warp_coef(const float* p, int H, int W) {
+  const float sx = p[0], sy = p[1], cx = p[2], cy = p[3];
+  const float a = 2.0f / (float)(W - 1), b = 2.0f / (float)(H - 1);
+  const float tx = (1.0f - sx) * cx, ty = (1.0f - sx) * cy;
+  WarpCoef k;
+  k.inv_sx = 1.0f / sx;
+  k.inv_sy = 1.0f / sy;
+  k.t02 = -(sx + a * tx - 1.0f) / sx;
+  k.t12 = -(sy + b * ty - 1.0f) / sy;
+  return k;
+}
+__device__ __forceinline__ float lin_coord(int i, int n) {       // torch.linspace(-1, 1, n)[i]
+  const float step = 2.0f / (float)(n - 1);
+  return (i < n / 2) ? (-1.0f + step * (float)i) : (1.0f - step * (float)(n - 1 - i));
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(kThreads) scale_kernel(const float* __restrict__ in, const float* __restrict__ gout,
+                                                        float* __restrict__ out, float* __restrict__ gin,
+                                                        const float* __restrict__ p, int stride,
+                                                        float* __restrict__ partial, int H, int W) {
+  const int b = blockIdx.y;
+  const float* pb = p + (long)b * stride;
+  const WarpCoef k = warp_coef(pb, H, W);
+  const float sx = pb[0], sy = pb[1], cx = pb[2], cy = pb[3];
+  const float a = 2.0f / (float)(W - 1), bb = 2.0f / (float)(H - 1);
+  const long base = (long)b * 3 * H * W;
+  const int HW = H * W;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    const int y = i / W, x = i - y * W;
+    const float xn = lin_coord(x, W), yn = lin_coord(y, H);
+    const float gxn = xn * k.inv_sx + k.t02, gyn = yn * k.inv_sy + k.t12;
+    const float ix = ((gxn + 1.0f) * 0.5f) * (float)(W - 1), iy = ((gyn + 1.0f) * 0.5f) * (float)(H - 1);
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
+    const float wx1 = ix - fx0, wx0 = 1.0f - wx1, wy1 = iy - fy0, wy0 = 1.0f - wy1;
+    const bool vx0 = x0 >= 0 && x0 < W, vx1 = x1 >= 0 && x1 < W, vy0 = y0 >= 0 && y0 < H, vy1 = y1 >= 0 && y1 < H;
+    float gix = 0.f, giy = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* pl = in + base + (long)c * HW;
+      const float v00 = (vy0 && vx0) ? pl[(long)y0 * W + x0] : 0.f;
+      const float v01 = (vy0 && vx1) ? pl[(long)y0 * W + x1] : 0.f;
+      const float v10 = (vy1 && vx0) ? pl[(long)y1 * W + x0] : 0.f;
+      const float v11 = (vy1 && vx1) ? pl[(long)y1 * W + x1] : 0.f;
+      const float o = v00 * (wx0 * wy0) + v01 * (wx1 * wy0) + v10 * (wx0 * wy1) + v11 * (wx1 * wy1);
+      if (!BWD) {
+        out[base + (long)c * HW + i] = clamp01(o);
+      } else {
+        const float g = in01(o) ? gout[base + (long)c * HW + i] : 0.f;
+        float* gp = gin + base + (long)c * HW;
+        if (vy0 && vx0) atomicAdd(gp + (long)y0 * W + x0, g * wx0 * wy0);
+        if (vy0 && vx1) atomicAdd(gp + (long)y0 * W + x1, g * wx1 * wy0);
+        if (vy1 && vx0) atomicAdd(gp + (long)y1 * W + x0, g * wx0 * wy1);
+        if (vy1 && vx1) atomicAdd(gp + (long)y1 * W + x1, g * wx1 * wy1);
+        gix += g * ((v01 - v00) * wy0 + (v11 - v10) * wy1);
+        giy += g * ((v10 - v00) * wx0 + (v11 - v01) * wx1);
+      }
+    }
+    if (BWD) {
+      const float ggx = gix * 0.5f * (float)(W - 1), ggy = giy * 0.5f * (float)(H - 1);   // d/d(grid x), d/d(grid y)
+      acc[0] += ggx * ((-xn + a * cx - 1.0f) / (sx * sx)) + ggy * (bb * cy / sy);         // d/dsx
+      acc[1] += ggy * ((-yn + bb * (1.0f - sx) * cy - 1.0f) / (sy * sy));                  // d/dsy
+      acc[2] += ggx * (-a * (1.0f - sx) / sx);                                             // d/dcx
+      acc[3] += ggy * (-bb * (1.0f - sx) / sy);                                            // d/dcy
+    }
+  }
+  if (BWD) block_reduce_store<4>(acc, partial + ((long)b * gridDim.x + blockIdx.x) * 4);
+}
+
+int plane_blocks(int HW) { int n = ceil_div(HW, kThreads * 4); return n > 64 ? 64 : (n < 1 ? 1 : n); }
+
+}  // namespace
+}  // namespace rgie
+
+using namespace rgie;
+
+// =================================================================================================================
+// C ABI
+// =================================================================================================================
+extern "C" {
+
+long rgie_filter_ws_floats(int B, int H, int W) {
+  // worst case over all filters: partials (B * kMaxBlk * 24) + three full-size temporaries (blur backward)
+  return (long)B * kMaxBlk * 24 + 3L * B * 3 * H * W + 64;
+}
+
+int rgie_filter_param_count(int kind) {
+  switch (kind) {
+    case RGIE_F_EXPOSURE: case RGIE_F_SATURATION: case RGIE_F_CONTRAST: case RGIE_F_SHARP: case RGIE_F_BLUR: return 1;
+    case RGIE_F_TONE: return 8;
+    case RGIE_F_COLOR: return 24;
+    case RGIE_F_SCALE: return 4;
+  }
+  return -1;
+}
+
+int rgie_filter_fwd(int kind, const float* in, float* out, const float* p, int p_stride, int B, int H, int W,
+                    float* ws, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HW = H * W;
+  RGIE_CHECK(B > 0 && H > 0 && W > 0, "rgie_filter_fwd: bad shape");
+  switch (kind) {
+    case RGIE_F_EXPOSURE: { ExposureOp op{p, p_stride, 0.f}; return launch_pointwise<ExposureOp, false>(in, nullptr, out, op, nullptr, B, HW, st); }
+    case RGIE_F_SATURATION: { SaturationOp op{p, p_stride, 0.f}; return launch_pointwise<SaturationOp, false>(in, nullptr, out, op, nullptr, B, HW, st); }
+    case RGIE_F_TONE: { CurveOp<1> op; op.p = p; op.stride = p_stride; return launch_pointwise<CurveOp<1>, false>(in, nullptr, out, op, nullptr, B, HW, st); }
+    case RGIE_F_COLOR: { CurveOp<3> op; op.p = p; op.stride = p_stride; return launch_pointwise<CurveOp<3>, false>(in, nullptr, out, op, nullptr, B, HW, st); }
+    case RGIE_F_CONTRAST: {
+      RGIE_CHECK(ws != nullptr, "rgie_filter_fwd(contrast): workspace required");
+      LaunchShape s = shape_for(HW);
+      float* partial = ws;                 // [B, nblk]
+      float* mu = ws + (long)B * kMaxBlk;  // [B]
+      dim3 grid(s.nblk, B);
+      if (HW % 4 == 0) gray_sum_kernel<4><<<grid, kThreads, 0, st>>>(in, partial, HW, s.chunk);
+      else gray_sum_kernel<1><<<grid, kThreads, 0, st>>>(in, partial, HW, s.chunk);
+      RGIE_LAUNCH_OK();
+      gray_mean_finalize<<<B, 32, 0, st>>>(partial, s.nblk, 1.0f / (float)HW, mu);
+      RGIE_LAUNCH_OK();
+      ContrastOp op{p, p_stride, mu, 0.f, 0.f};
+      return launch_pointwise<ContrastOp, false>(in, nullptr, out, op, nullptr, B, HW, st);
+    }
+    case RGIE_F_SHARP: {
+      RGIE_CHECK(H >= 3 && W >= 3, "sharp: image too small");
+      dim3 grid(plane_blocks(HW), 3, B);
+      sharp_fwd_kernel<<<grid, kThreads, 0, st>>>(in, out, p, p_stride, H, W);
+      RGIE_LAUNCH_OK();
+      return 0;
+    }
+    case RGIE_F_BLUR: {
+      RGIE_CHECK(ws != nullptr, "rgie_filter_fwd(blur): workspace required");
+      RGIE_CHECK(H > kRad && W > kRad, "blur: reflect padding needs H,W > 12");
+      float* t = ws;
+      dim3 grid(plane_blocks(HW), 3, B);
+      blur_h_kernel<<<grid, kThreads, 0, st>>>(in, t, nullptr, p, p_stride, H, W);
+      RGIE_LAUNCH_OK();
+      blur_v_kernel<<<grid, kThreads, 0, st>>>(t, out, p, p_stride, H, W);
+      RGIE_LAUNCH_OK();
+      return 0;
+    }
+    case RGIE_F_SCALE: {
+      RGIE_CHECK(H >= 2 && W >= 2, "scale: image too small");
+      dim3 grid(plane_blocks(HW), B);
+      scale_kernel<false><<<grid, kThreads, 0, st>>>(in, nullptr, out, nullptr, p, p_stride, nullptr, H, W);
+      RGIE_LAUNCH_OK();
+      return 0;
+    }
+  }
+  return fail("rgie_filter_fwd: unknown filter kind");
+}
+
+int rgie_filter_bwd(int kind, const float* in, const float* gout, float* gin, const float* p, int p_stride,
+                    float* gp, int gp_stride, int B, int H, int W, float* ws, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HW = H * W;
+  RGIE_CHECK(B > 0 && H > 0 && W > 0 && ws != nullptr, "rgie_filter_bwd: bad arguments");
+  LaunchShape s = shape_for(HW);
+  float* partial = ws;
+  switch (kind) {
+    case RGIE_F_EXPOSURE: {
+      ExposureOp op{p, p_stride, 0.f};
+      if (int rc = launch_pointwise<ExposureOp, true>(in, gout, gin, op, partial, B, HW, st)) return rc;
+      finalize_partials<<<B, 32, 0, st>>>(partial, s.nblk, 1, gp, gp_stride);
+      break;
+    }
+    case RGIE_F_SATURATION: {
+      SaturationOp op{p, p_stride, 0.f};
+      if (int rc = launch_pointwise<SaturationOp, true>(in, gout, gin, op, partial, B, HW, st)) return rc;
+      finalize_partials<<<B, 32, 0, st>>>(partial, s.nblk, 1, gp, gp_stride);
+      break;
+    }
+    case RGIE_F_TONE: {
+      CurveOp<1> op; op.p = p; op.stride = p_stride;
+      if (int rc = launch_pointwise<CurveOp<1>, true>(in, gout, gin, op, partial, B, HW, st)) return rc;
+      finalize_partials<<<B, 32, 0, st>>>(partial, s.nblk, 8, gp, gp_stride);
+      break;
+    }
+    case RGIE_F_COLOR: {
+      CurveOp<3> op; op.p = p; op.stride = p_stride;
+      if (int rc = launch_pointwise<CurveOp<3>, true>(in, gout, gin, op, partial, B, HW, st)) return rc;
+      finalize_partials<<<B, 32, 0, st>>>(partial, s.nblk, 24, gp, gp_stride);
+      break;
+    }
+    case RGIE_F_CONTRAST: {
+      // mean is recomputed (cheap) so that backward does not depend on forward-call state
+      float* mu = ws + (long)B * kMaxBlk * 2;
+      float* sums = mu + B;      // [B,2]
+      dim3 grid(s.nblk, B);
+      if (HW % 4 == 0) gray_sum_kernel<4><<<grid, kThreads, 0, st>>>(in, partial, HW, s.chunk);
+      else gray_sum_kernel<1><<<grid, kThreads, 0, st>>>(in, partial, HW, s.chunk);
+      RGIE_LAUNCH_OK();
+      gray_mean_finalize<<<B, 32, 0, st>>>(partial, s.nblk, 1.0f / (float)HW, mu);
+      RGIE_LAUNCH_OK();
+      ContrastOp op{p, p_stride, mu, 0.f, 0.f};
+      if (int rc = launch_pointwise<ContrastOp, true>(in, gout, gin, op, partial, B, HW, st)) return rc;
+      finalize_partials<<<B, 32, 0, st>>>(partial, s.nblk, 2, sums, 2);
+      RGIE_LAUNCH_OK();
+      dim3 g2(plane_blocks(3 * HW), B);
+      contrast_bwd_mean_kernel<<<g2, kThreads, 0, st>>>(gin, p, p_stride, sums, 2, HW);
+      RGIE_LAUNCH_OK();
+      copy_strided_kernel<<<ceil_div(B, 128), 128, 0, st>>>(sums, 2, gp, gp_stride, B);   // sums[b,0] -> gp[b]
+      break;
+    }
+    case RGIE_F_SHARP: {
+      RGIE_CHECK(H >= 3 && W >= 3, "sharp: image too small");
+      const int nb = plane_blocks(HW);
+      float* gdeg = ws + (long)B * kMaxBlk * 24;
+      dim3 grid(nb, 3, B);
+      sharp_bwd_a_kernel<<<grid, kThreads, 0, st>>>(in, gout, gdeg, gin, p, p_stride, partial, H, W);
+      RGIE_LAUNCH_OK();
+      sharp_bwd_b_kernel<<<grid, kThreads, 0, st>>>(gdeg, gin, H, W);
+      RGIE_LAUNCH_OK();
+      finalize_partials<<<B, 32, 0, st>>>(partial, 3 * nb, 1, gp, gp_stride);
+      break;
+    }
+    case RGIE_F_BLUR: {
+      RGIE_CHECK(H > kRad && W > kRad, "blur: reflect padding needs H,W > 12");
+      const int nb = plane_blocks(HW);
+      const long plane = (long)B * 3 * HW;
+      float* part2 = ws + (long)B * kMaxBlk * 12;
+      float* t = ws + (long)B * kMaxBlk * 24;
+      float* td = t + plane;
+      float* gm = td + plane;
+      dim3 grid(nb, 3, B);
+      blur_h_kernel<<<grid, kThreads, 0, st>>>(in, t, td, p, p_stride, H, W);
+      RGIE_LAUNCH_OK();
+      blur_bwd_mask_kernel<<<grid, kThreads, 0, st>>>(t, gout, gm, p, p_stride, partial, H, W);
+      RGIE_LAUNCH_OK();
+      // t is dead now: reuse it for V^T gm
+      blur_bwd_t_kernel<0><<<grid, kThreads, 0, st>>>(gm, t, td, p, p_stride, part2, H, W);
+      RGIE_LAUNCH_OK();
+      blur_bwd_t_kernel<1><<<grid, kThreads, 0, st>>>(t, gin, nullptr, p, p_stride, nullptr, H, W);
+      RGIE_LAUNCH_OK();
+      // d(sigma) = sum(partial) + sum(part2): both live in one contiguous [B, 2*3*nb] view when nb == kMaxBlk*12/(3*nb)...
+      // keep it simple: finalize each into a 2-float scratch then add
+      float* two = gm;   // gm is dead after blur_bwd_t_kernel<0>; [B,2]
+      finalize_partials<<<B, 32, 0, st>>>(partial, 3 * nb, 1, two, 2);
+      finalize_partials<<<B, 32, 0, st>>>(part2, 3 * nb, 1, two + 1, 2);
+      RGIE_LAUNCH_OK();
+      finalize_partials<<<B, 32, 0, st>>>(two, 2, 1, gp, gp_stride);
+      break;
+    }
+    case RGIE_F_SCALE: {
+      RGIE_CHECK(H >= 2 && W >= 2, "scale: image too small");
+      const int nb = plane_blocks(HW);
+      RGIE_CUDA_OK(cudaMemsetAsync(gin, 0, sizeof(float) * (size_t)B * 3 * HW, st));
+      dim3 grid(nb, B);
+      scale_kernel<true><<<grid, kThreads, 0, st>>>(in, gout, nullptr, gin, p, p_stride, partial, H, W);
+      RGIE_LAUNCH_OK();
+      finalize_partials<<<B, 32, 0, st>>>(partial, nb, 4, gp, gp_stride);
+      break;
+    }
+    default:
+      return fail("rgie_filter_bwd: unknown filter kind");
+  }
+  RGIE_LAUNCH_OK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,798 @@
+// Valence/arousal regressor: torchvision resnet50 (eval, BatchNorm folded) on 10 random crops per image, forward and
+// input-gradient backward.  Reference: src/baselines/models/EmotionPredictionModel.py:10-54 (load_model_eval),
+// utilities/ReplicateAndCrop.py:30-45, torchvision.models.resnet50.
+//
+// Every convolution is lowered to the row-shifted GEMM of common.cuh (3x3 = nine row-shifted operand loads over a
+// zero-padded flat pixel layout; stride-2 convs read a 2x2 phase-split layout so they are row shifts too; conv1 7x7/2
+// becomes 4 vertical taps over a space-to-depth + 4-horizontal-tap packed input with 64 channels).  Backward keeps only
+// the post-ReLU activations (for the ReLU masks) and the max-pool argmax; weight gradients are never computed.
+#include <string.h>
+#include <string>
+#include <vector>
+#include "common.cuh"
+#include "gemm_sm100.cuh"
+#include "rgie.h"
+
+namespace rgie {
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------
+// small kernels around the GEMMs (templated on the activation type T: float = parity mode, bf16 = throughput mode)
+// ---------------------------------------------------------------------------------------------------------------
+
+// crop + normalise + 2x2 space-to-depth + 4 horizontal taps -> ZZ[n, i, j, bi*16 + (pr*2+pc)*3 + c]
+template <typename T>
+__global__ void __launch_bounds__(256) pack_crops_kernel(const float* __restrict__ img, const int* __restrict__ offsets,
+                                                        const int* __restrict__ step_ptr, long off_step_stride,
+                                                        T* __restrict__ zz, Geom g, int reps, int Hr, int Wr,
+                                                        int normalize, long total) {
+  const int* offs = offsets + (step_ptr ? (long)(*step_ptr) * off_step_stride : 0);
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int bi = (int)(idx & 3);
+    long q = idx >> 2;
+    const int j = (int)(q % g.W); q /= g.W;
+    const int i = (int)(q % g.H);
+    const int n = (int)(q / g.H);
+    const int b = n / reps;
+    const int top = offs[2 * n], left = offs[2 * n + 1];
+    const int jj = j + bi - 2;
+    T vals[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) vals[k] = from_f<T>(0.f);
+    if (jj >= 0 && jj < g.W) {
+#pragma unroll
+      for (int pr = 0; pr < 2; ++pr)
+#pragma unroll
+        for (int pc = 0; pc < 2; ++pc)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float v = img[(((long)b * 3 + c) * Hr + (top + 2 * i + pr)) * Wr + (left + 2 * jj + pc)];
+            if (normalize) v = (v - 0.5f) / 0.5f;
+            vals[(pr * 2 + pc) * 3 + c] = from_f<T>(v);
+          }
+    }
+    T* dst = zz + geom_row(g, 0, n, i, j) * 64 + bi * 16;
+    if (sizeof(T) == 2) {
+      const uint4* s = reinterpret_cast<const uint4*>(vals);
+      reinterpret_cast<uint4*>(dst)[0] = s[0];
+      reinterpret_cast<uint4*>(dst)[1] = s[1];
+    } else {
+      const float4* s = reinterpret_cast<const float4*>(vals);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) reinterpret_cast<float4*>(dst)[k] = s[k];
+    }
+  }
+}
+
+// 3x3 stride-2 pad-1 max pool over plain NHWC [N,Hi,Hi,C] -> padded layout g (Ho = Hi/2), argmax code 0..8 (first max)
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                         uint8_t* __restrict__ arg, Geom g, int Hi, int C, long total) {
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    long q = idx / C;
+    const int j = (int)(q % g.W); q /= g.W;
+    const int i = (int)(q % g.H);
+    const int n = (int)(q / g.H);
+    float best = -INFINITY;
+    int code = 0;
+    bool first = true;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int y = 2 * i - 1 + dy;
+      if (y < 0 || y >= Hi) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int x = 2 * j - 1 + dx;
+        if (x < 0 || x >= Hi) continue;
+        const float v = to_f<T>(in[(((long)n * Hi + y) * Hi + x) * C + c]);
+        if (first || v > best) { best = v; code = dy * 3 + dx; first = false; }
+      }
+    }
+    out[geom_row(g, 0, n, i, j) * C + c] = from_f<T>(best);
+    arg[idx] = (uint8_t)code;
+  }
+}
+// backward of the pool + the stem ReLU mask: dC1[n,y,x,c] (layout gd) = (C1 > 0) * sum_{windows whose argmax is (y,x)} dP
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ dP, const uint8_t* __restrict__ arg,
+                                                         const T* __restrict__ c1, T* __restrict__ dC1, Geom gp, Geom gd,
+                                                         int Hi, int C, long total) {
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    long q = idx / C;
+    const int x = (int)(q % Hi); q /= Hi;
+    const int y = (int)(q % Hi);
+    const int n = (int)(q / Hi);
+    float s = 0.f;
+    if (to_f<T>(c1[idx]) > 0.f) {
+      // windows i with 2i-1 <= y <= 2i+1  <=>  i in [ceil((y-1)/2), floor((y+1)/2)]
+      const int i0 = y >> 1, i1 = (y + 1) >> 1;     // y even: i0=i1=y/2 ; y odd: i0=(y-1)/2, i1=(y+1)/2
+      const int j0 = x >> 1, j1 = (x + 1) >> 1;
+      for (int i = i0; i <= i1; ++i) {
+        if (i >= gp.H) continue;
+        const int dy = y - (2 * i - 1);
+        for (int j = j0; j <= j1; ++j) {
+          if (j >= gp.W) continue;
+          const int dx = x - (2 * j - 1);
+          const long pidx = (((long)n * gp.H + i) * gp.W + j) * C + c;
+          if (arg[pidx] == dy * 3 + dx) s += to_f<T>(dP[geom_row(gp, 0, n, i, j) * C + c]);
+        }
+      }
+    }
+    dC1[geom_row(gd, 0, n, y, x) * C + c] = from_f<T>(s);
+  }
+}
+
+// global average pool over the valid window of layout g + fully connected layer
+template <typename T>
+__global__ void __launch_bounds__(256) avgpool_fc_kernel(const T* __restrict__ x, Geom g, int C, const float* __restrict__ wfc,
+                                                        const float* __restrict__ bfc, int K, float* __restrict__ feat,
+                                                        float* __restrict__ logits) {
+  __shared__ float red[8][8];
+  const int n = blockIdx.x;
+  float part[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) part[k] = 0.f;
+  const float inv = 1.0f / (float)(g.H * g.W);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int i = 0; i < g.H; ++i)
+      for (int j = 0; j < g.W; ++j) s += to_f<T>(x[geom_row(g, 0, n, i, j) * C + c]);
+    s *= inv;
+    feat[(long)n * C + c] = s;
+    for (int k = 0; k < K; ++k) part[k] = fmaf(s, wfc[(long)k * C + c], part[k]);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = 0; k < K; ++k) {
+    float v = part[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    float s = bfc[threadIdx.x];
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    logits[(long)n * K + threadIdx.x] = s;
+  }
+}
+// d(layer4 out)[n,i,j,c] = (out > 0) * (sum_k dlogits[n,k] * wfc[k,c]) / (H*W)
+template <typename T>
+__global__ void __launch_bounds__(256) avgpool_fc_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ wfc,
+                                                            int K, const T* __restrict__ x, T* __restrict__ dx, Geom g, int C) {
+  const int n = blockIdx.x;
+  const float inv = 1.0f / (float)(g.H * g.W);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float d = 0.f;
+    for (int k = 0; k < K; ++k) d = fmaf(dlogits[(long)n * K + k], wfc[(long)k * C + c], d);
+    d *= inv;
+    for (int i = 0; i < g.H; ++i)
+      for (int j = 0; j < g.W; ++j) {
+        const long r = geom_row(g, 0, n, i, j) * C + c;
+        dx[r] = from_f<T>(to_f<T>(x[r]) > 0.f ? d : 0.f);
+      }
+  }
+}
+
+// dimg[b,c,Y,X] = nscale * sum_r dZ[(b*reps+r), (Y-top)>>1, (X-left)>>1, ((Y-top)&1)*2+((X-left)&1))*3 + c]
+__global__ void __launch_bounds__(256) crop_grad_gather_kernel(const float* __restrict__ dz, const int* __restrict__ offsets,
+                                                              const int* __restrict__ step_ptr, long off_step_stride,
+                                                              float* __restrict__ dimg, int B, int reps, int Hr, int Wr,
+                                                              int crop, float nscale) {
+  const int* offs = offsets + (step_ptr ? (long)(*step_ptr) * off_step_stride : 0);
+  const int Ho = crop / 2;
+  const long total = (long)B * Hr * Wr;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int X = (int)(idx % Wr);
+    long q = idx / Wr;
+    const int Y = (int)(q % Hr);
+    const int b = (int)(q / Hr);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int r = 0; r < reps; ++r) {
+      const int n = b * reps + r;
+      const int y = Y - offs[2 * n], x = X - offs[2 * n + 1];
+      if (y < 0 || y >= crop || x < 0 || x >= crop) continue;
+      const float* p = dz + (((long)n * Ho + (y >> 1)) * Ho + (x >> 1)) * 16 + ((y & 1) * 2 + (x & 1)) * 3;
+      s0 += p[0]; s1 += p[1]; s2 += p[2];
+    }
+    const long plane = (long)Hr * Wr;
+    float* o = dimg + (long)b * 3 * plane + (long)Y * Wr + X;
+    o[0] = s0 * nscale; o[plane] = s1 * nscale; o[2 * plane] = s2 * nscale;
+  }
+}
+
+// activation (any layout) -> NCHW fp32, for parity taps
+template <typename T>
+__global__ void tap_kernel(const T* __restrict__ x, Geom g, int C, int full_h, int full_w, float* __restrict__ out, long total) {
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % full_w);
+    long q = idx / full_w;
+    const int i = (int)(q % full_h); q /= full_h;
+    const int c = (int)(q % C);
+    const int n = (int)(q / C);
+    long row;
+    if (g.planes == 4) row = geom_row(g, (i & 1) * 2 + (j & 1), n, i >> 1, j >> 1);
+    else row = geom_row(g, 0, n, i, j);
+    out[idx] = to_f<T>(x[row * C + c]);
+  }
+}
+
+int grid_for(long total) {
+  long g = (total + 255) / 256;
+  const long cap = 148L * 32;
+  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+}  // namespace
+}  // namespace rgie
+
+using namespace rgie;
+
+// =================================================================================================================
+// plan
+// =================================================================================================================
+struct ConvW {        // host fp32 folded weights
+  const float* w; const float* b; int co, ci, k;
+};
+
+struct Block {
+  int stage, ci, cm, co;
+  bool ds, last, stride2;
+  ConvW c1, c2, c3, dsw;
+  // device weights (T) / biases (fp32)
+  void *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *wds = nullptr;           // forward
+  void *w1t = nullptr, *w2t[4] = {nullptr, nullptr, nullptr, nullptr}, *w3t = nullptr, *wdst = nullptr;   // dgrad
+  int w2t_taps[4] = {0, 0, 0, 0};
+  long w2t_off[4][kMaxTaps];
+  float *b1 = nullptr, *b2 = nullptr, *b3 = nullptr, *bds = nullptr;
+  // activations
+  void *h1 = nullptr, *h2 = nullptr, *out = nullptr;
+  Geom gx, gs, gout;    // layout of X / of the stage / of OUT
+  const void* x = nullptr;
+};
+
+struct GemmOp {
+  GemmDesc d;
+  GemmPlanSm100 plan;
+};
+
+struct RgieRegressor {
+  int precision = 0, dtype = 0, esz = 4;     // dtype 0 fp32 / 1 bf16
+  int N = 0, crop = 0, K = 0;
+  int H0 = 0;
+  int Hs[5] = {0, 0, 0, 0, 0};
+  Geom gZZ, gDY, gS[5], gPh[5];
+  std::vector<Block> blocks;
+  std::vector<void*> allocs;
+  long ws_bytes = 0;
+  // stem
+  void *wc1 = nullptr, *wc1t = nullptr; float* bc1 = nullptr;
+  void *zz = nullptr, *c1 = nullptr, *p1 = nullptr; uint8_t* arg = nullptr;
+  float *wfc = nullptr, *bfc = nullptr, *feat = nullptr;
+  // gradients
+  void* dOut[5][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  void *dH2[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *dH1[5] = {nullptr, nullptr, nullptr, nullptr, nullptr},
+       *gds[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *dsbuf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  void* dC1 = nullptr; float* dZ = nullptr;
+  std::vector<GemmOp> fwd_ops, bwd_ops;
+  // call state
+  const int* offsets = nullptr; const int* step_ptr = nullptr; long off_stride = 0;
+  int B = 0, reps = 0, Hr = 0, Wr = 0, normalize = 1;
+  void* final_dout = nullptr;   // where the tail backward writes d(layer4 out)
+};
+
+namespace {
+
+int dev_alloc(RgieRegressor* R, void** p, size_t bytes, bool zero) {
+  if (bytes == 0) bytes = 16;
+  RGIE_CUDA_OK(cudaMalloc(p, bytes));
+  if (zero) RGIE_CUDA_OK(cudaMemset(*p, 0, bytes));
+  R->allocs.push_back(*p);
+  R->ws_bytes += (long)bytes;
+  return 0;
+}
+
+// upload a host fp32 matrix as T (fp32 or bf16)
+int upload(RgieRegressor* R, const std::vector<float>& h, void** dptr) {
+  if (int rc = dev_alloc(R, dptr, h.size() * R->esz, false)) return rc;
+  if (R->dtype == 0) {
+    RGIE_CUDA_OK(cudaMemcpy(*dptr, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+  } else {
+    std::vector<__nv_bfloat16> hb(h.size());
+    for (size_t i = 0; i < h.size(); ++i) hb[i] = __float2bfloat16(h[i]);
+    RGIE_CUDA_OK(cudaMemcpy(*dptr, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+int upload_f32(RgieRegressor* R, const float* h, size_t n, float** dptr) {
+  if (int rc = dev_alloc(R, (void**)dptr, n * 4, false)) return rc;
+  RGIE_CUDA_OK(cudaMemcpy(*dptr, h, n * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// phase decomposition of a stride-2 pad-1 3x3 tap offset d = r-1 in {-1,0,1}: plane parity and plane-row shift
+inline void s2_phase(int d, int& par, int& shift) { par = d & 1; shift = (d - par) / 2; }
+
+GemmDesc base_desc() {
+  GemmDesc d;
+  memset(&d, 0, sizeof(d));
+  return d;
+}
+
+int add_op(RgieRegressor* R, std::vector<GemmOp>& ops, const GemmDesc& d) {
+  GemmOp op;
+  op.d = d;
+  if (R->precision == RGIE_PREC_BF16) {
+    if (int rc = build_gemm_sm100(d, &op.plan)) return rc;
+  }
+  ops.push_back(op);
+  return 0;
+}
+
+int run_op(RgieRegressor* R, const GemmOp& op, cudaStream_t st) {
+  if (R->precision == RGIE_PREC_BF16) return run_gemm_sm100(op.plan, st);
+  return launch_gemm_simt(op.d, R->dtype, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+void rgie_regressor_destroy(RgieRegressor* R) {
+  if (!R) return;
+  for (void* p : R->allocs) cudaFree(p);
+  delete R;
+}
+
+long rgie_regressor_workspace_bytes(const RgieRegressor* R) { return R ? R->ws_bytes : 0; }
+
+int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_classes, int crop_size, int max_crops,
+                          int precision, RgieRegressor** out) {
+  RGIE_CHECK(out != nullptr && h_tensors != nullptr, "rgie_regressor_create: null argument");
+  RGIE_CHECK(n_tensors == 2 + 2 * (3 * 16 + 4) + 2, "rgie_regressor_create: expected 108 tensors");
+  RGIE_CHECK(crop_size % 32 == 0 && crop_size >= 64, "rgie_regressor_create: crop_size must be a multiple of 32");
+  RGIE_CHECK(num_classes >= 1 && num_classes <= 8, "rgie_regressor_create: num_classes must be in 1..8");
+  RGIE_CHECK(max_crops >= 1, "rgie_regressor_create: max_crops");
+  RGIE_CHECK(precision >= 0 && precision <= 2, "rgie_regressor_create: precision");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("rgie_regressor_create: no CUDA device (there is no CPU fallback)");
+
+  RgieRegressor* R = new RgieRegressor();
+  struct Guard { RgieRegressor* r; bool ok = false; ~Guard() { if (!ok) rgie_regressor_destroy(r); } } guard{R};
+  R->precision = precision;
+  R->dtype = precision == RGIE_PREC_FP32 ? 0 : 1;
+  R->esz = R->dtype == 0 ? 4 : 2;
+  const int N = R->N = max_crops;
+  R->crop = crop_size;
+  R->K = num_classes;
+  const int H0 = R->H0 = crop_size / 2;
+  for (int s = 1; s <= 4; ++s) R->Hs[s] = H0 >> s;
+  R->gZZ = make_geom(1, N, H0, H0, 2, 1, 0, 0);
+  R->gDY = make_geom(1, N, H0, H0, 1, 2, 1, 2);
+  for (int s = 1; s <= 4; ++s) {
+    R->gS[s] = make_geom(1, N, R->Hs[s], R->Hs[s], 1, 1, 1, 1);
+    R->gPh[s] = make_geom(4, N, R->Hs[s], R->Hs[s], 1, 1, 1, 1);
+  }
+  const int esz = R->esz;
+
+  // ---- parse tensors
+  int ti = 0;
+  ConvW conv1{h_tensors[0], h_tensors[1], 64, 3, 7};
+  ti = 2;
+  const int nblk[5] = {0, 3, 4, 6, 3};
+  int cin = 64;
+  for (int s = 1; s <= 4; ++s) {
+    const int cm = 64 << (s - 1), co = 4 * cm;
+    for (int b = 0; b < nblk[s]; ++b) {
+      Block k;
+      k.stage = s; k.ci = cin; k.cm = cm; k.co = co;
+      k.ds = (b == 0); k.last = (b == nblk[s] - 1); k.stride2 = (b == 0 && s > 1);
+      k.c1 = ConvW{h_tensors[ti], h_tensors[ti + 1], cm, cin, 1};
+      k.c2 = ConvW{h_tensors[ti + 2], h_tensors[ti + 3], cm, cm, 3};
+      k.c3 = ConvW{h_tensors[ti + 4], h_tensors[ti + 5], co, cm, 1};
+      ti += 6;
+      if (k.ds) { k.dsw = ConvW{h_tensors[ti], h_tensors[ti + 1], co, cin, 1}; ti += 2; }
+      R->blocks.push_back(k);
+      cin = co;
+    }
+  }
+  const float* h_wfc = h_tensors[ti];
+  const float* h_bfc = h_tensors[ti + 1];
+  for (int i = 0; i < n_tensors; ++i) RGIE_CHECK(h_tensors[i] != nullptr, "rgie_regressor_create: null tensor");
+
+  // ---- stem weights: conv1 as 4 vertical taps over the packed input (64 channels = 4 horizontal taps x 16)
+  {
+    std::vector<float> w((size_t)64 * 256, 0.f), wt((size_t)16 * 1024, 0.f);
+    for (int k = 0; k < 64; ++k)
+      for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 7; ++r)
+          for (int s = 0; s < 7; ++s) {
+            const int dr = r - 3, dc = s - 3;
+            const int pr = dr & 1, pc = dc & 1;
+            const int a = (dr - pr) / 2, b = (dc - pc) / 2;      // in {-2,..,1}
+            const int ai = a + 2, bi = b + 2, q = (pr * 2 + pc) * 3 + c;
+            const float v = conv1.w[((k * 3 + c) * 7 + r) * 7 + s];
+            w[(size_t)k * 256 + ai * 64 + bi * 16 + q] = v;
+            wt[(size_t)q * 1024 + (ai * 4 + bi) * 64 + k] = v;
+          }
+    if (int rc = upload(R, w, &R->wc1)) return rc;
+    if (int rc = upload(R, wt, &R->wc1t)) return rc;
+    if (int rc = upload_f32(R, conv1.b, 64, &R->bc1)) return rc;
+  }
+  if (int rc = upload_f32(R, h_wfc, (size_t)num_classes * 2048, &R->wfc)) return rc;
+  if (int rc = upload_f32(R, h_bfc, num_classes, &R->bfc)) return rc;
+
+  // ---- stem buffers
+  if (int rc = dev_alloc(R, &R->zz, (size_t)R->gZZ.rows() * 64 * esz, true)) return rc;
+  if (int rc = dev_alloc(R, &R->c1, (size_t)N * H0 * H0 * 64 * esz, true)) return rc;
+  if (int rc = dev_alloc(R, &R->p1, (size_t)R->gS[1].rows() * 64 * esz, true)) return rc;
+  if (int rc = dev_alloc(R, (void**)&R->arg, (size_t)N * R->Hs[1] * R->Hs[1] * 64, true)) return rc;
+  if (int rc = dev_alloc(R, (void**)&R->feat, (size_t)N * 2048 * 4, true)) return rc;
+  if (int rc = dev_alloc(R, &R->dC1, (size_t)R->gDY.rows() * 64 * esz, true)) return rc;
+  if (int rc = dev_alloc(R, (void**)&R->dZ, (size_t)N * H0 * H0 * 16 * 4, true)) return rc;
+
+  // ---- per-stage gradient scratch
+  for (int s = 1; s <= 4; ++s) {
+    const int cm = 64 << (s - 1), co = 4 * cm;
+    const int ci_max = s == 1 ? 64 : 2 * cm;           // input channels of the stage's ds block
+    const long rows = R->gS[s].rows();
+    for (int p = 0; p < 2; ++p)
+      if (int rc = dev_alloc(R, &R->dOut[s][p], (size_t)rows * co * esz, true)) return rc;
+    if (int rc = dev_alloc(R, &R->dH2[s], (size_t)rows * cm * esz, true)) return rc;
+    if (int rc = dev_alloc(R, &R->dH1[s], (size_t)(s > 1 ? 4 : 1) * rows * cm * esz, true)) return rc;
+    if (int rc = dev_alloc(R, &R->gds[s], (size_t)rows * ci_max * esz, true)) return rc;
+    if (int rc = dev_alloc(R, &R->dsbuf[s], (size_t)rows * co * esz, true)) return rc;
+  }
+
+  // ---- forward GEMM 0: conv1
+  {
+    GemmDesc d = base_desc();
+    d.A = R->zz; d.a_rows = R->gZZ.rows(); d.Cin = 64;
+    d.Wt = R->wc1; d.n_pad = 64; d.ntaps = 4;
+    for (int a = 0; a < 4; ++a) d.row_off[a] = (long)(a - 2) * R->gZZ.P;
+    d.m_begin = 0; d.m_end = R->gZZ.rows(); d.Cout = 64;
+    d.src = R->gZZ; d.dst_kind = DST_TO_PLAIN; d.dst = R->gZZ;
+    d.D = R->c1; d.ldd = 64; d.bias = R->bc1; d.relu = 1;
+    if (int rc = add_op(R, R->fwd_ops, d)) return rc;
+  }
+
+  // ---- blocks: weights, buffers, forward ops
+  const void* x = R->p1;
+  for (size_t bi = 0; bi < R->blocks.size(); ++bi) {
+    Block& k = R->blocks[bi];
+    const int s = k.stage;
+    k.gs = R->gS[s];
+    k.gx = k.stride2 ? R->gPh[s] : R->gS[s];
+    k.gout = (k.last && s < 4) ? R->gPh[s + 1] : R->gS[s];
+    k.x = x;
+    const Geom& gs = k.gs;
+    const long Mp = gs.rows();
+    // weights
+    {
+      std::vector<float> w1((size_t)k.cm * k.ci), w1t((size_t)k.ci * k.cm);
+      for (int n = 0; n < k.cm; ++n)
+        for (int c = 0; c < k.ci; ++c) { w1[(size_t)n * k.ci + c] = k.c1.w[(size_t)n * k.ci + c]; w1t[(size_t)c * k.cm + n] = k.c1.w[(size_t)n * k.ci + c]; }
+      if (int rc = upload(R, w1, &k.w1)) return rc;
+      if (int rc = upload(R, w1t, &k.w1t)) return rc;
+      std::vector<float> w3((size_t)k.co * k.cm), w3t((size_t)k.cm * k.co);
+      for (int n = 0; n < k.co; ++n)
+        for (int c = 0; c < k.cm; ++c) { w3[(size_t)n * k.cm + c] = k.c3.w[(size_t)n * k.cm + c]; w3t[(size_t)c * k.co + n] = k.c3.w[(size_t)n * k.cm + c]; }
+      if (int rc = upload(R, w3, &k.w3)) return rc;
+      if (int rc = upload(R, w3t, &k.w3t)) return rc;
+      // 3x3: forward [cm, 9*cm] (t = r*3+s); dgrad: stride 1 -> one matrix [cm, 9*cm]; stride 2 -> one per input phase
+      std::vector<float> w2((size_t)k.cm * 9 * k.cm);
+      for (int n = 0; n < k.cm; ++n)
+        for (int c = 0; c < k.cm; ++c)
+          for (int t = 0; t < 9; ++t) w2[(size_t)n * 9 * k.cm + (size_t)t * k.cm + c] = k.c2.w[((size_t)n * k.cm + c) * 9 + t];
+      if (int rc = upload(R, w2, &k.w2)) return rc;
+      if (!k.stride2) {
+        std::vector<float> w2t((size_t)k.cm * 9 * k.cm);
+        for (int n = 0; n < k.cm; ++n)
+          for (int c = 0; c < k.cm; ++c)
+            for (int t = 0; t < 9; ++t) w2t[(size_t)c * 9 * k.cm + (size_t)t * k.cm + n] = k.c2.w[((size_t)n * k.cm + c) * 9 + t];
+        if (int rc = upload(R, w2t, &k.w2t[0])) return rc;
+        k.w2t_taps[0] = 9;
+        for (int t = 0; t < 9; ++t) k.w2t_off[0][t] = -((long)(t / 3 - 1) * gs.P + (t % 3 - 1));
+      } else {
+        for (int ph = 0; ph < 4; ++ph) {
+          const int pr = ph >> 1, pc = ph & 1;
+          std::vector<int> taps;
+          for (int t = 0; t < 9; ++t) {
+            int par_r, sh_r, par_c, sh_c;
+            s2_phase(t / 3 - 1, par_r, sh_r);
+            s2_phase(t % 3 - 1, par_c, sh_c);
+            if (par_r == pr && par_c == pc) {
+              k.w2t_off[ph][taps.size()] = -((long)sh_r * gs.P + sh_c) - (long)ph * Mp;
+              taps.push_back(t);
+            }
+          }
+          k.w2t_taps[ph] = (int)taps.size();
+          std::vector<float> w2t((size_t)k.cm * taps.size() * k.cm);
+          for (int n = 0; n < k.cm; ++n)
+            for (int c = 0; c < k.cm; ++c)
+              for (size_t tt = 0; tt < taps.size(); ++tt)
+                w2t[(size_t)c * taps.size() * k.cm + tt * k.cm + n] = k.c2.w[((size_t)n * k.cm + c) * 9 + taps[tt]];
+          if (int rc = upload(R, w2t, &k.w2t[ph])) return rc;
+        }
+      }
+      if (k.ds) {
+        std::vector<float> wd((size_t)k.co * k.ci), wdt((size_t)k.ci * k.co);
+        for (int n = 0; n < k.co; ++n)
+          for (int c = 0; c < k.ci; ++c) { wd[(size_t)n * k.ci + c] = k.dsw.w[(size_t)n * k.ci + c]; wdt[(size_t)c * k.co + n] = k.dsw.w[(size_t)n * k.ci + c]; }
+        if (int rc = upload(R, wd, &k.wds)) return rc;
+        if (int rc = upload(R, wdt, &k.wdst)) return rc;
+        if (int rc = upload_f32(R, k.dsw.b, k.co, &k.bds)) return rc;
+      }
+      if (int rc = upload_f32(R, k.c1.b, k.cm, &k.b1)) return rc;
+      if (int rc = upload_f32(R, k.c2.b, k.cm, &k.b2)) return rc;
+      if (int rc = upload_f32(R, k.c3.b, k.co, &k.b3)) return rc;
+    }
+    // activations
+    if (int rc = dev_alloc(R, &k.h1, (size_t)k.gx.rows() * k.cm * esz, true)) return rc;
+    if (int rc = dev_alloc(R, &k.h2, (size_t)Mp * k.cm * esz, true)) return rc;
+    if (int rc = dev_alloc(R, &k.out, (size_t)k.gout.rows() * k.co * esz, true)) return rc;
+
+    // c1
+    {
+      GemmDesc d = base_desc();
+      d.A = k.x; d.a_rows = k.gx.rows(); d.Cin = k.ci; d.Wt = k.w1; d.n_pad = k.cm; d.ntaps = 1; d.row_off[0] = 0;
+      d.m_begin = 0; d.m_end = k.gx.rows(); d.Cout = k.cm;
+      d.src = k.gx; d.dst_kind = DST_SAME; d.dst = k.gx; d.D = k.h1; d.ldd = k.cm; d.bias = k.b1; d.relu = 1;
+      if (int rc = add_op(R, R->fwd_ops, d)) return rc;
+    }
+    // c2
+    {
+      GemmDesc d = base_desc();
+      d.A = k.h1; d.a_rows = k.gx.rows(); d.Cin = k.cm; d.Wt = k.w2; d.n_pad = k.cm; d.ntaps = 9;
+      for (int t = 0; t < 9; ++t) {
+        if (!k.stride2) d.row_off[t] = (long)(t / 3 - 1) * gs.P + (t % 3 - 1);
+        else {
+          int par_r, sh_r, par_c, sh_c;
+          s2_phase(t / 3 - 1, par_r, sh_r);
+          s2_phase(t % 3 - 1, par_c, sh_c);
+          d.row_off[t] = (long)(par_r * 2 + par_c) * Mp + (long)sh_r * gs.P + sh_c;
+        }
+      }
+      d.m_begin = 0; d.m_end = Mp; d.Cout = k.cm;
+      d.src = gs; d.dst_kind = DST_SAME; d.dst = gs; d.D = k.h2; d.ldd = k.cm; d.bias = k.b2; d.relu = 1;
+      if (int rc = add_op(R, R->fwd_ops, d)) return rc;
+    }
+    // downsample branch
+    if (k.ds) {
+      GemmDesc d = base_desc();
+      d.A = k.x; d.a_rows = k.gx.rows(); d.Cin = k.ci; d.Wt = k.wds; d.n_pad = k.co; d.ntaps = 1; d.row_off[0] = 0;
+      d.m_begin = 0; d.m_end = Mp; d.Cout = k.co;
+      d.src = gs; d.dst_kind = DST_SAME; d.dst = gs; d.D = R->dsbuf[s]; d.ldd = k.co; d.bias = k.bds; d.relu = 0;
+      if (int rc = add_op(R, R->fwd_ops, d)) return rc;
+    }
+    // c3 + residual + relu
+    {
+      GemmDesc d = base_desc();
+      d.A = k.h2; d.a_rows = Mp; d.Cin = k.cm; d.Wt = k.w3; d.n_pad = k.co; d.ntaps = 1; d.row_off[0] = 0;
+      d.m_begin = 0; d.m_end = Mp; d.Cout = k.co;
+      d.src = gs; d.dst_kind = (k.last && s < 4) ? DST_TO_PHASE : DST_SAME; d.dst = k.gout;
+      d.D = k.out; d.ldd = k.co; d.bias = k.b3; d.relu = 1;
+      d.res = k.ds ? R->dsbuf[s] : k.x; d.ld_res = k.co; d.res_rows = Mp;
+      if (int rc = add_op(R, R->fwd_ops, d)) return rc;
+    }
+    x = k.out;
+  }
+
+  // ---- backward ops (built in execution order: last block first)
+  int pp[5] = {0, 0, 0, 0, 0};     // ping-pong index of the CURRENT dOut per stage
+  R->final_dout = R->dOut[4][0];
+  for (int bi = (int)R->blocks.size() - 1; bi >= 0; --bi) {
+    Block& k = R->blocks[bi];
+    const int s = k.stage;
+    const Geom& gs = k.gs;
+    const long Mp = gs.rows();
+    void* dout = R->dOut[s][pp[s]];
+    // c3 dgrad
+    {
+      GemmDesc d = base_desc();
+      d.A = dout; d.a_rows = Mp; d.Cin = k.co; d.Wt = k.w3t; d.n_pad = k.cm; d.ntaps = 1; d.row_off[0] = 0;
+      d.m_begin = 0; d.m_end = Mp; d.Cout = k.cm;
+      d.src = gs; d.dst_kind = DST_SAME; d.dst = gs; d.D = R->dH2[s]; d.ldd = k.cm;
+      d.mask = k.h2; d.ld_mask = k.cm;
+      if (int rc = add_op(R, R->bwd_ops, d)) return rc;
+    }
+    // c2 dgrad
+    if (!k.stride2) {
+      GemmDesc d = base_desc();
+      d.A = R->dH2[s]; d.a_rows = Mp; d.Cin = k.cm; d.Wt = k.w2t[0]; d.n_pad = k.cm; d.ntaps = 9;
+      for (int t = 0; t < 9; ++t) d.row_off[t] = k.w2t_off[0][t];
+      d.m_begin = 0; d.m_end = Mp; d.Cout = k.cm;
+      d.src = gs; d.dst_kind = DST_SAME; d.dst = gs; d.D = R->dH1[s]; d.ldd = k.cm;
+      d.mask = k.h1; d.ld_mask = k.cm;
+      if (int rc = add_op(R, R->bwd_ops, d)) return rc;
+    } else {
+      for (int ph = 0; ph < 4; ++ph) {
+        GemmDesc d = base_desc();
+        d.A = R->dH2[s]; d.a_rows = Mp; d.Cin = k.cm; d.Wt = k.w2t[ph]; d.n_pad = k.cm; d.ntaps = k.w2t_taps[ph];
+        for (int t = 0; t < d.ntaps; ++t) d.row_off[t] = k.w2t_off[ph][t];
+        d.m_begin = (long)ph * Mp; d.m_end = (long)(ph + 1) * Mp; d.Cout = k.cm;
+        d.src = k.gx; d.dst_kind = DST_SAME; d.dst = k.gx; d.D = R->dH1[s]; d.ldd = k.cm;
+        d.mask = k.h1; d.ld_mask = k.cm;
+        if (int rc = add_op(R, R->bwd_ops, d)) return rc;
+      }
+    }
+    // downsample dgrad
+    if (k.ds) {
+      GemmDesc d = base_desc();
+      d.A = dout; d.a_rows = Mp; d.Cin = k.co; d.Wt = k.wdst; d.n_pad = k.ci; d.ntaps = 1; d.row_off[0] = 0;
+      d.m_begin = 0; d.m_end = Mp; d.Cout = k.ci;
+      d.src = gs; d.dst_kind = DST_SAME; d.dst = gs; d.D = R->gds[s]; d.ldd = k.ci;
+      if (int rc = add_op(R, R->bwd_ops, d)) return rc;
+    }
+    // c1 dgrad (+ skip / downsample gradient, * ReLU mask of the block input)
+    {
+      GemmDesc d = base_desc();
+      d.A = R->dH1[s]; d.a_rows = k.gx.rows(); d.Cin = k.cm; d.Wt = k.w1t; d.n_pad = k.ci; d.ntaps = 1; d.row_off[0] = 0;
+      d.m_begin = 0; d.m_end = k.gx.rows(); d.Cout = k.ci;
+      d.src = k.gx;
+      if (k.ds) { d.res = R->gds[s]; d.ld_res = k.ci; d.res_rows = Mp; }
+      else { d.res = dout; d.ld_res = k.ci; d.res_rows = Mp; }
+      if (bi == 0) {
+        d.mask = nullptr;                      // block input = max-pool output (no ReLU of its own)
+        d.dst_kind = DST_SAME; d.dst = gs; d.D = R->dOut[1][pp[1] ^ 1];   // = d(pool out)
+        pp[1] ^= 1;
+      } else if (k.stride2) {
+        d.mask = k.x; d.ld_mask = k.ci;
+        d.dst_kind = DST_FROM_PHASE; d.dst = R->gS[s - 1]; d.D = R->dOut[s - 1][pp[s - 1]];
+      } else {
+        d.mask = k.x; d.ld_mask = k.ci;
+        d.dst_kind = DST_SAME; d.dst = gs; d.D = R->dOut[s][pp[s] ^ 1];
+        pp[s] ^= 1;
+      }
+      d.ldd = k.ci;
+      if (int rc = add_op(R, R->bwd_ops, d)) return rc;
+    }
+  }
+  // conv1 dgrad: dZ[m, q] = sum_{a,b} dC1[m - (a*P + b)] . Wt
+  {
+    GemmDesc d = base_desc();
+    d.A = R->dC1; d.a_rows = R->gDY.rows(); d.Cin = 64; d.Wt = R->wc1t; d.n_pad = 16; d.ntaps = 16;
+    for (int a = 0; a < 4; ++a)
+      for (int b = 0; b < 4; ++b) d.row_off[a * 4 + b] = -((long)(a - 2) * R->gDY.P + (b - 2));
+    d.m_begin = 0; d.m_end = R->gDY.rows(); d.Cout = 16;
+    d.src = R->gDY; d.dst_kind = DST_TO_PLAIN; d.dst = R->gDY; d.D = R->dZ; d.ldd = 16; d.d_fp32 = 1;
+    if (int rc = add_op(R, R->bwd_ops, d)) return rc;
+  }
+  RGIE_CUDA_OK(cudaDeviceSynchronize());
+  guard.ok = true;
+  *out = R;
+  return 0;
+}
+
+int rgie_regressor_forward_ex(RgieRegressor* R, const float* img, int B, int Hr, int Wr, const int* offsets,
+                              const int* step_ptr, long off_step_stride, int reps, int normalize, float* logits,
+                              void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  RGIE_CHECK(R && img && offsets && logits, "rgie_regressor_forward: null argument");
+  RGIE_CHECK(B * reps == R->N, "rgie_regressor_forward: B*reps must equal the max_crops the handle was created with");
+  RGIE_CHECK(Hr >= R->crop && Wr >= R->crop, "rgie_regressor_forward: image smaller than the crop");
+  R->offsets = offsets; R->step_ptr = step_ptr; R->off_stride = off_step_stride;
+  R->B = B; R->reps = reps; R->Hr = Hr; R->Wr = Wr; R->normalize = normalize;
+  const int N = R->N, H0 = R->H0, H1 = R->Hs[1];
+  const long tot_pack = (long)N * H0 * H0 * 4;
+  const long tot_pool = (long)N * H1 * H1 * 64;
+  if (R->dtype == 0) {
+    pack_crops_kernel<float><<<grid_for(tot_pack), 256, 0, st>>>(img, offsets, step_ptr, off_step_stride, (float*)R->zz,
+                                                               R->gZZ, reps, Hr, Wr, normalize, tot_pack);
+  } else {
+    pack_crops_kernel<__nv_bfloat16><<<grid_for(tot_pack), 256, 0, st>>>(img, offsets, step_ptr, off_step_stride,
+                                                                       (__nv_bfloat16*)R->zz, R->gZZ, reps, Hr, Wr,
+                                                                       normalize, tot_pack);
+  }
+  RGIE_LAUNCH_OK();
+  if (int rc = run_op(R, R->fwd_ops[0], st)) return rc;
+  if (R->dtype == 0)
+    maxpool_fwd_kernel<float><<<grid_for(tot_pool), 256, 0, st>>>((const float*)R->c1, (float*)R->p1, R->arg, R->gS[1], H0, 64, tot_pool);
+  else
+    maxpool_fwd_kernel<__nv_bfloat16><<<grid_for(tot_pool), 256, 0, st>>>((const __nv_bfloat16*)R->c1, (__nv_bfloat16*)R->p1, R->arg, R->gS[1], H0, 64, tot_pool);
+  RGIE_LAUNCH_OK();
+  for (size_t i = 1; i < R->fwd_ops.size(); ++i)
+    if (int rc = run_op(R, R->fwd_ops[i], st)) return rc;
+  const Block& last = R->blocks.back();
+  if (R->dtype == 0)
+    avgpool_fc_kernel<float><<<N, 256, 0, st>>>((const float*)last.out, R->gS[4], 2048, R->wfc, R->bfc, R->K, R->feat, logits);
+  else
+    avgpool_fc_kernel<__nv_bfloat16><<<N, 256, 0, st>>>((const __nv_bfloat16*)last.out, R->gS[4], 2048, R->wfc, R->bfc, R->K, R->feat, logits);
+  RGIE_LAUNCH_OK();
+  return 0;
+}
+
+int rgie_regressor_forward(RgieRegressor* R, const float* img, int B, int Hr, int Wr, const int* offsets, int reps,
+                           int normalize, float* logits, void* stream) {
+  return rgie_regressor_forward_ex(R, img, B, Hr, Wr, offsets, nullptr, 0, reps, normalize, logits, stream);
+}
+
+int rgie_regressor_backward(RgieRegressor* R, const float* dlogits, float* dimg, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  RGIE_CHECK(R && dlogits && dimg, "rgie_regressor_backward: null argument");
+  RGIE_CHECK(R->offsets != nullptr, "rgie_regressor_backward: call rgie_regressor_forward first");
+  const int N = R->N, H0 = R->H0;
+  const Block& last = R->blocks.back();
+  if (R->dtype == 0)
+    avgpool_fc_bwd_kernel<float><<<N, 256, 0, st>>>(dlogits, R->wfc, R->K, (const float*)last.out, (float*)R->final_dout, R->gS[4], 2048);
+  else
+    avgpool_fc_bwd_kernel<__nv_bfloat16><<<N, 256, 0, st>>>(dlogits, R->wfc, R->K, (const __nv_bfloat16*)last.out, (__nv_bfloat16*)R->final_dout, R->gS[4], 2048);
+  RGIE_LAUNCH_OK();
+  const size_t nb = R->bwd_ops.size();
+  for (size_t i = 0; i + 1 < nb; ++i)
+    if (int rc = run_op(R, R->bwd_ops[i], st)) return rc;
+  // d(pool out) is the destination of the last block op (layer1.0 c1 dgrad)
+  const void* dP = R->bwd_ops[nb - 2].d.D;
+  const long tot = (long)N * H0 * H0 * 64;
+  if (R->dtype == 0)
+    maxpool_bwd_kernel<float><<<grid_for(tot), 256, 0, st>>>((const float*)dP, R->arg, (const float*)R->c1, (float*)R->dC1, R->gS[1], R->gDY, H0, 64, tot);
+  else
+    maxpool_bwd_kernel<__nv_bfloat16><<<grid_for(tot), 256, 0, st>>>((const __nv_bfloat16*)dP, R->arg, (const __nv_bfloat16*)R->c1, (__nv_bfloat16*)R->dC1, R->gS[1], R->gDY, H0, 64, tot);
+  RGIE_LAUNCH_OK();
+  if (int rc = run_op(R, R->bwd_ops[nb - 1], st)) return rc;
+  const long totg = (long)R->B * R->Hr * R->Wr;
+  crop_grad_gather_kernel<<<grid_for(totg), 256, 0, st>>>(R->dZ, R->offsets, R->step_ptr, R->off_stride, dimg, R->B, R->reps,
+                                                          R->Hr, R->Wr, R->crop, R->normalize ? 2.0f : 1.0f);
+  RGIE_LAUNCH_OK();
+  return 0;
+}
+
+int rgie_regressor_tap(RgieRegressor* R, const char* name, float* out, long capacity, long* n_out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  RGIE_CHECK(R && name && out && n_out, "rgie_regressor_tap: null argument");
+  const void* buf = nullptr;
+  Geom g; int C = 0, fh = 0, fw = 0;
+  std::string nm(name);
+  if (nm == "feat") {
+    long n = (long)R->N * 2048;
+    RGIE_CHECK(n <= capacity, "rgie_regressor_tap: capacity");
+    RGIE_CUDA_OK(cudaMemcpyAsync(out, R->feat, n * 4, cudaMemcpyDeviceToDevice, st));
+    *n_out = n;
+    return 0;
+  }
+  if (nm == "stem") { buf = R->c1; g = make_geom(1, R->N, R->H0, R->H0, 0, 0, 0, 0); C = 64; fh = fw = R->H0; }
+  else if (nm == "pool") { buf = R->p1; g = R->gS[1]; C = 64; fh = fw = R->Hs[1]; }
+  else {
+    // "layer{s}.{i}" [".c1" | ".c2"]
+    int s = 0, i = 0; char tail[8] = {0};
+    int got = sscanf(name, "layer%d.%d.%7s", &s, &i, tail);
+    RGIE_CHECK(got >= 2 && s >= 1 && s <= 4, "rgie_regressor_tap: unknown name");
+    const int nblk[5] = {0, 3, 4, 6, 3};
+    RGIE_CHECK(i >= 0 && i < nblk[s], "rgie_regressor_tap: block index");
+    int bi = i;
+    for (int q = 1; q < s; ++q) bi += nblk[q];
+    const Block& k = R->blocks[bi];
+    if (got == 2) { buf = k.out; g = k.gout; C = k.co; }
+    else if (!strcmp(tail, "c1")) { buf = k.h1; g = k.gx; C = k.cm; }
+    else if (!strcmp(tail, "c2")) { buf = k.h2; g = k.gs; C = k.cm; }
+    else return fail("rgie_regressor_tap: unknown suffix");
+    fh = fw = g.planes == 4 ? 2 * g.H : g.H;
+  }
+  const long total = (long)R->N * C * fh * fw;
+  RGIE_CHECK(total <= capacity, "rgie_regressor_tap: capacity");
+  if (R->dtype == 0) tap_kernel<float><<<grid_for(total), 256, 0, st>>>((const float*)buf, g, C, fh, fw, out, total);
+  else tap_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, st>>>((const __nv_bfloat16*)buf, g, C, fh, fw, out, total);
+  RGIE_LAUNCH_OK();
+  *n_out = total;
+  return 0;
+}
+
+int rgie_gemm_selftest(int backend, const void* A, long a_rows, int Cin, const void* W, int n_pad, int ntaps,
+                       const long* h_row_off, long m_begin, long m_end, int Cout, const float* bias, const void* res,
+                       int relu, void* D, int d_fp32, void* stream) {
+  RGIE_CHECK(ntaps >= 1 && ntaps <= kMaxTaps, "rgie_gemm_selftest: ntaps");
+  GemmDesc d;
+  memset(&d, 0, sizeof(d));
+  d.A = A; d.a_rows = a_rows; d.Cin = Cin; d.Wt = W; d.n_pad = n_pad; d.ntaps = ntaps;
+  for (int t = 0; t < ntaps; ++t) d.row_off[t] = h_row_off[t];
+  d.m_begin = m_begin; d.m_end = m_end; d.Cout = Cout;
+  // trivial geometry: one "image" of (m_end) x 1 pixels, nothing is padding
+  d.src = make_geom(1, 1, (int)m_end, 1, 0, 0, 0, 0);
+  d.dst_kind = DST_SAME; d.dst = d.src;
+  d.D = D; d.ldd = Cout; d.d_fp32 = d_fp32; d.bias = bias;
+  d.res = res; d.ld_res = Cout; d.res_rows = m_end; d.relu = relu;
+  if (backend == 1) return launch_gemm_sm100(d, (cudaStream_t)stream);
+  return launch_gemm_simt(d, 1, (cudaStream_t)stream);
+}
+
+}  // extern "C"

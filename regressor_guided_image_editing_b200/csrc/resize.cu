@@ -1,0 +1,199 @@
+// Antialiased bilinear resize (ATen _upsample_bilinear2d_aa, align_corners=False) and its transpose.
+// Reference call site: torchvision transforms.Resize(480, antialias=True) inside load_model_eval
+// (src/baselines/models/EmotionPredictionModel.py:36-37).
+//
+// Separable: horizontal pass into `tmp` [planes, in_h, out_w], then vertical pass.  Tap tables (per output index:
+// first source index, tap count, normalised fp32 weights; and the CSR transpose for backward) are built once on the
+// host with the same float arithmetic as ATen's `_compute_indices_weights_aa` and live in the handle.
+#include <math.h>
+#include <vector>
+#include "common.cuh"
+#include "rgie.h"
+
+namespace rgie {
+
+struct AxisTable {
+  int in_size = 0, out_size = 0, kmax = 0, tmax = 0;
+  int* xmin = nullptr;      // [out]
+  int* xsize = nullptr;     // [out]
+  float* w = nullptr;       // [out, kmax]
+  int* t_start = nullptr;   // [in + 1]  CSR over inputs
+  int* t_out = nullptr;     // [nnz] output index
+  float* t_w = nullptr;     // [nnz] weight
+};
+
+static int build_axis(int in_size, int out_size, AxisTable* t) {
+  t->in_size = in_size;
+  t->out_size = out_size;
+  const float scale = (float)((double)in_size / (double)out_size);
+  const float support = scale >= 1.0f ? scale : 1.0f;
+  const float invscale = scale >= 1.0f ? 1.0f / scale : 1.0f;
+  const int kmax = (int)ceilf(support) * 2 + 1;
+  t->kmax = kmax;
+  std::vector<int> xmin(out_size), xsize(out_size);
+  std::vector<float> w((size_t)out_size * kmax, 0.f);
+  std::vector<std::vector<std::pair<int, float>>> tr(in_size);
+  for (int i = 0; i < out_size; ++i) {
+    const float center = scale * ((float)i + 0.5f);
+    int lo = (int)(center - support + 0.5f);
+    if (lo < 0) lo = 0;
+    int hi = (int)(center + support + 0.5f);
+    if (hi > in_size) hi = in_size;
+    xmin[i] = lo;
+    xsize[i] = hi - lo;
+    float tot = 0.f;
+    for (int j = 0; j < hi - lo; ++j) {
+      const float arg = ((float)(j + lo) - center + 0.5f) * invscale;
+      const float v = fabsf(arg) < 1.0f ? 1.0f - fabsf(arg) : 0.f;
+      w[(size_t)i * kmax + j] = v;
+      tot += v;
+    }
+    for (int j = 0; j < hi - lo; ++j) {
+      if (tot != 0.f) w[(size_t)i * kmax + j] /= tot;
+      tr[lo + j].push_back({i, w[(size_t)i * kmax + j]});
+    }
+  }
+  std::vector<int> ts(in_size + 1, 0), to;
+  std::vector<float> tw;
+  int tmax = 0;
+  for (int s = 0; s < in_size; ++s) {
+    ts[s] = (int)to.size();
+    for (auto& e : tr[s]) { to.push_back(e.first); tw.push_back(e.second); }
+    if ((int)tr[s].size() > tmax) tmax = (int)tr[s].size();
+  }
+  ts[in_size] = (int)to.size();
+  t->tmax = tmax;
+  if (to.empty()) { to.push_back(0); tw.push_back(0.f); }
+  RGIE_CUDA_OK(cudaMalloc(&t->xmin, sizeof(int) * out_size));
+  RGIE_CUDA_OK(cudaMalloc(&t->xsize, sizeof(int) * out_size));
+  RGIE_CUDA_OK(cudaMalloc(&t->w, sizeof(float) * w.size()));
+  RGIE_CUDA_OK(cudaMalloc(&t->t_start, sizeof(int) * ts.size()));
+  RGIE_CUDA_OK(cudaMalloc(&t->t_out, sizeof(int) * to.size()));
+  RGIE_CUDA_OK(cudaMalloc(&t->t_w, sizeof(float) * tw.size()));
+  RGIE_CUDA_OK(cudaMemcpy(t->xmin, xmin.data(), sizeof(int) * out_size, cudaMemcpyHostToDevice));
+  RGIE_CUDA_OK(cudaMemcpy(t->xsize, xsize.data(), sizeof(int) * out_size, cudaMemcpyHostToDevice));
+  RGIE_CUDA_OK(cudaMemcpy(t->w, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
+  RGIE_CUDA_OK(cudaMemcpy(t->t_start, ts.data(), sizeof(int) * ts.size(), cudaMemcpyHostToDevice));
+  RGIE_CUDA_OK(cudaMemcpy(t->t_out, to.data(), sizeof(int) * to.size(), cudaMemcpyHostToDevice));
+  RGIE_CUDA_OK(cudaMemcpy(t->t_w, tw.data(), sizeof(float) * tw.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+static void free_axis(AxisTable* t) {
+  cudaFree(t->xmin); cudaFree(t->xsize); cudaFree(t->w); cudaFree(t->t_start); cudaFree(t->t_out); cudaFree(t->t_w);
+}
+
+// out[plane, y, xo] = sum_j w[xo, j] * in[plane, y, xmin[xo] + j]        (AXIS 1: along x, rows = in_h)
+// out[plane, yo, x] = sum_j w[yo, j] * in[plane, ymin[yo] + j, x]        (AXIS 0: along y, cols = width)
+template <int AXIS>
+__global__ void __launch_bounds__(256) resample_fwd_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                          const int* __restrict__ xmin, const int* __restrict__ xsize,
+                                                          const float* __restrict__ w, int kmax, int in_size, int out_size,
+                                                          int other, long total) {
+  // AXIS 1: in [planes, other, in_size] -> out [planes, other, out_size]
+  // AXIS 0: in [planes, in_size, other] -> out [planes, out_size, other]
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long plane;
+    int o, r;
+    if (AXIS == 1) { o = (int)(i % out_size); long q = i / out_size; r = (int)(q % other); plane = q / other; }
+    else { r = (int)(i % other); long q = i / other; o = (int)(q % out_size); plane = q / out_size; }
+    const int lo = xmin[o], n = xsize[o];
+    const float* wk = w + (long)o * kmax;
+    float s = 0.f;
+    if (AXIS == 1) {
+      const float* src = in + (plane * other + r) * (long)in_size + lo;
+      for (int j = 0; j < n; ++j) s = fmaf(wk[j], src[j], s);
+    } else {
+      const float* src = in + (plane * in_size + lo) * (long)other + r;
+      for (int j = 0; j < n; ++j) s = fmaf(wk[j], src[(long)j * other], s);
+    }
+    out[i] = s;
+  }
+}
+// transpose: gin[plane, .., s] = sum_e t_w[e] * gout[plane, .., t_out[e]]
+template <int AXIS>
+__global__ void __launch_bounds__(256) resample_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin,
+                                                          const int* __restrict__ t_start, const int* __restrict__ t_out,
+                                                          const float* __restrict__ t_w, int in_size, int out_size,
+                                                          int other, long total) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long plane;
+    int s_idx, r;
+    if (AXIS == 1) { s_idx = (int)(i % in_size); long q = i / in_size; r = (int)(q % other); plane = q / other; }
+    else { r = (int)(i % other); long q = i / other; s_idx = (int)(q % in_size); plane = q / in_size; }
+    float s = 0.f;
+    const int e0 = t_start[s_idx], e1 = t_start[s_idx + 1];
+    if (AXIS == 1) {
+      const float* src = gout + (plane * other + r) * (long)out_size;
+      for (int e = e0; e < e1; ++e) s = fmaf(t_w[e], src[t_out[e]], s);
+    } else {
+      const float* src = gout + plane * (long)out_size * other + r;
+      for (int e = e0; e < e1; ++e) s = fmaf(t_w[e], src[(long)t_out[e] * other], s);
+    }
+    gin[i] = s;
+  }
+}
+
+static int grid_for(long total) {
+  long g = (total + 255) / 256;
+  long cap = 148L * 16;
+  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+}  // namespace rgie
+
+using namespace rgie;
+
+struct RgieResize {
+  AxisTable ax_w, ax_h;
+  int in_h, in_w, out_h, out_w;
+};
+
+extern "C" {
+
+int rgie_resize_create(int in_h, int in_w, int out_h, int out_w, RgieResize** out) {
+  RGIE_CHECK(in_h > 0 && in_w > 0 && out_h > 0 && out_w > 0 && out != nullptr, "rgie_resize_create: bad shape");
+  RgieResize* r = new RgieResize();
+  r->in_h = in_h; r->in_w = in_w; r->out_h = out_h; r->out_w = out_w;
+  if (int rc = build_axis(in_w, out_w, &r->ax_w)) { delete r; return rc; }
+  if (int rc = build_axis(in_h, out_h, &r->ax_h)) { delete r; return rc; }
+  *out = r;
+  return 0;
+}
+
+void rgie_resize_destroy(RgieResize* r) {
+  if (!r) return;
+  free_axis(&r->ax_w);
+  free_axis(&r->ax_h);
+  delete r;
+}
+
+int rgie_resize_fwd(const RgieResize* r, const float* in, float* out, int planes, float* tmp, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  RGIE_CHECK(r && in && out && tmp && planes > 0, "rgie_resize_fwd: bad arguments");
+  long t1 = (long)planes * r->in_h * r->out_w;
+  resample_fwd_kernel<1><<<grid_for(t1), 256, 0, st>>>(in, tmp, r->ax_w.xmin, r->ax_w.xsize, r->ax_w.w, r->ax_w.kmax,
+                                                       r->in_w, r->out_w, r->in_h, t1);
+  RGIE_LAUNCH_OK();
+  long t2 = (long)planes * r->out_h * r->out_w;
+  resample_fwd_kernel<0><<<grid_for(t2), 256, 0, st>>>(tmp, out, r->ax_h.xmin, r->ax_h.xsize, r->ax_h.w, r->ax_h.kmax,
+                                                       r->in_h, r->out_h, r->out_w, t2);
+  RGIE_LAUNCH_OK();
+  return 0;
+}
+
+int rgie_resize_bwd(const RgieResize* r, const float* gout, float* gin, int planes, float* tmp, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  RGIE_CHECK(r && gout && gin && tmp && planes > 0, "rgie_resize_bwd: bad arguments");
+  // transpose of (vertical o horizontal) = horizontal^T o vertical^T ; tmp: [planes, in_h, out_w]
+  long t1 = (long)planes * r->in_h * r->out_w;
+  resample_bwd_kernel<0><<<grid_for(t1), 256, 0, st>>>(gout, tmp, r->ax_h.t_start, r->ax_h.t_out, r->ax_h.t_w, r->in_h,
+                                                       r->out_h, r->out_w, t1);
+  RGIE_LAUNCH_OK();
+  long t2 = (long)planes * r->in_h * r->in_w;
+  resample_bwd_kernel<1><<<grid_for(t2), 256, 0, st>>>(tmp, gin, r->ax_w.t_start, r->ax_w.t_out, r->ax_w.t_w, r->in_w,
+                                                       r->out_w, r->in_h, t2);
+  RGIE_LAUNCH_OK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,122 @@
+"""GPU: the 8 default filter kernels (forward + backward) against the CPU oracle and the reference-generated goldens."""
+import os
+
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _mirror():
+    from regressor_guided_image_editing_b200.baselines.image_transformations import image_transformations as IT
+    return IT
+
+
+def _oracle_single(name, im, p):
+    return torch.clamp(O.apply_one(name, im, p), 0.0, 1.0)
+
+
+def _param_tensor(name, val):
+    if name == "tone":
+        return torch.tensor(val, dtype=torch.float32).view(1, 1, 8, 1)
+    if name == "color":
+        return torch.tensor(val, dtype=torch.float32).view(1, 3, 8, 1)
+    if name == "scale":
+        return torch.tensor(val, dtype=torch.float32).view(1, 4)
+    return torch.tensor(val, dtype=torch.float32)
+
+
+g7 = torch.Generator().manual_seed(7)
+SINGLE_CASES = [
+    ("exposure", 0.0), ("exposure", 0.45), ("exposure", -0.8),
+    ("saturation", 1.0), ("saturation", 0.0), ("saturation", 1.7), ("saturation", 0.35),
+    ("tone", [1.0] * 8), ("tone", (1.0 + 0.3 * torch.randn(8, generator=g7)).tolist()),
+    ("color", [1.0] * 24), ("color", (1.0 + 0.3 * torch.randn(24, generator=g7)).tolist()),
+    ("contrast", 1.0), ("contrast", 0.5), ("contrast", 1.8), ("contrast", 0.0),
+    ("sharp", 0.0), ("sharp", 0.5), ("sharp", 1.0), ("sharp", 2.5),
+    ("blur", 1e-4), ("blur", 0.5), ("blur", 2.0), ("blur", 6.0),
+    ("scale", [1.0, 1.0, 0.0, 0.0]), ("scale", [1.2, 1.1, 9.0, 14.0]), ("scale", [1.5, 1.0, 30.0, 5.0]),
+    ("scale", [1.05, 1.3, 0.0, 40.0]),
+]
+
+
+@pytest.mark.parametrize("hw", [(36, 44), (33, 57), (128, 96)])
+@pytest.mark.parametrize("name,val", SINGLE_CASES, ids=[f"{n}-{i}" for i, (n, _) in enumerate(SINGLE_CASES)])
+def test_single_filter_vs_oracle(name, val, hw):
+    IT = _mirror()
+    h, w = hw
+    im = O.synthetic_image(6, h, w)[None]
+    # make clamps / ties bite: push some pixels to the ends of the range
+    im = torch.clamp(im * 1.25 - 0.1, 0.0, 1.0)
+    p = _param_tensor(name, val)
+    gout = torch.randn(im.shape, generator=torch.Generator().manual_seed(13))
+
+    im_c, p_c = im.clone().requires_grad_(True), p.clone().requires_grad_(True)
+    out_c = _oracle_single(name, im_c, p_c)
+    gi_c, gp_c = torch.autograd.grad((out_c * gout).sum(), [im_c, p_c], allow_unused=True)
+    gp_c = torch.zeros_like(p) if gp_c is None else gp_c
+
+    im_g, p_g = im.to(DEV).requires_grad_(True), p.to(DEV).requires_grad_(True)
+    out_g = IT._DISPATCH[name](im_g, p_g)
+    gi_g, gp_g = torch.autograd.grad((out_g * gout.to(DEV)).sum(), [im_g, p_g], allow_unused=True)
+    gp_g = torch.zeros_like(p_g) if gp_g is None else gp_g
+
+    fwd_tol = 2e-4 if name == "scale" else 2e-6     # bilinear sampling positions differ at the 1e-5 px level
+    err = (out_g.cpu() - out_c).abs().max().item()
+    assert err <= fwd_tol, f"{name} forward max-abs {err}"
+    # image gradient: robust relative-L1 criterion (isolated pixels sit exactly on clamp / tie boundaries)
+    gden = gi_c.abs().mean().item() + 1e-12
+    gerr = (gi_g.cpu() - gi_c).abs().mean().item() / gden
+    gtol = 2e-3 if name == "scale" else 1e-4
+    assert gerr <= gtol, f"{name} d(image) relative L1 {gerr}"
+    pden = gp_c.abs().max().item() + 1e-6 * gout.numel() ** 0.5
+    perr = (gp_g.cpu() - gp_c).abs().max().item() / pden
+    ptol = 5e-3 if name == "scale" else 5e-4
+    assert perr <= ptol, f"{name} d(param) {gp_g.cpu().flatten()[:4]} vs {gp_c.flatten()[:4]} rel {perr}"
+
+
+def test_identity_known_answer():
+    """run_img_trans.py SAME preset / init_params start values: exposure, tone, color, contrast, scale leave the image
+    unchanged; blur at 1e-4 is a delta; sharp at 0 returns the 3x3-smoothed image."""
+    IT = _mirror()
+    im = O.synthetic_image(2, 64, 80)[None].to(DEV)
+    x0 = O.init_x0()
+    p = O.get_params_from_vector(x0, O.DEFAULT_FILTERS, 64)
+    for name in ("exposure", "tone", "color", "contrast", "blur"):
+        out = IT._DISPATCH[name](im, p[name].to(DEV) if isinstance(p[name], torch.Tensor) else p[name])
+        assert (out - im).abs().max().item() <= 1e-6, name
+    out = IT.apply_scale(im, p["scale"].to(DEV))
+    assert (out - im).abs().max().item() <= 1e-4
+    out = IT.apply_saturation(im, p["saturation"].to(DEV))
+    assert (out - im).abs().max().item() <= 2e-6
+
+
+def test_chain_vs_golden(golden_dir):
+    """apply_params on the reference-generated goldens (tests/golden/filters.pt, made by oracle/gen_golden.py)."""
+    IT = _mirror()
+    gold = torch.load(os.path.join(golden_dir, "filters.pt"))
+    checked = 0
+    for key, g in gold.items():
+        if key == "singles" or any(t not in IT._DISPATCH for t in g["trans"]):
+            continue
+        im = O.synthetic_image(g["image_index"], g["h"], g["w"])[None].to(DEV).requires_grad_(True)
+        x = g["x"].to(DEV).requires_grad_(True)
+        params = O.get_params_from_vector(x, g["trans"], g["h"])
+        outs = IT.apply_params(im, params)
+        ref = g["stages"][-1]
+        err = (outs[-1].detach().cpu() - ref).abs().max().item()
+        assert err <= 5e-4, f"{key}: forward max-abs {err}"
+        gout = torch.randn(ref.shape, generator=torch.Generator().manual_seed(g["gout_seed"])).to(DEV)
+        gx, gim = torch.autograd.grad((outs[-1] * gout).sum(), [x, im], allow_unused=True)
+        den = g["grad_x"].abs().max().item() + 1e-3
+        rel = (gx.cpu() - g["grad_x"]).abs().max().item() / den
+        assert rel <= 2e-2, f"{key}: d(x) rel {rel}\n{gx.cpu()}\n{g['grad_x']}"
+        gden = g["grad_im"].abs().mean().item() + 1e-12
+        grel = (gim.cpu() - g["grad_im"]).abs().mean().item() / gden
+        assert grel <= 2e-2, f"{key}: d(image) rel-L1 {grel}"
+        checked += 1
+    assert checked >= 8

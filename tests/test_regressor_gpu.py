@@ -1,0 +1,153 @@
+"""GPU: native resnet50 regressor (forward + input-gradient backward) against the CPU oracle.
+
+fp32 mode (CUDA-core GEMMs) is the parity mode: activations, logits and d(image) must match the oracle to fp32
+round-off.  bf16 mode (tcgen05/TMEM/TMA GEMMs) is checked against the bf16 CUDA-core cross-check (same storage
+precision, different accumulation order) and, loosely, against the fp32 oracle.
+"""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+TAPS = ["stem", "pool", "layer1.0.c1", "layer1.0.c2", "layer1.0", "layer1.2", "layer2.0.c1", "layer2.0.c2", "layer2.0",
+        "layer2.3", "layer3.0", "layer3.5", "layer4.0.c2", "layer4.0", "layer4.2"]
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return O.make_regressor_state_dict()
+
+
+def _inputs(reps, hr=480, wr=480, seed=5):
+    img = O.synthetic_image(seed, hr, wr)[None]
+    g = torch.Generator().manual_seed(99)
+    offs = torch.stack([torch.randint(0, hr - 448 + 1, (1, reps), generator=g),
+                        torch.randint(0, wr - 448 + 1, (1, reps), generator=g)], -1).int()
+    return img, offs
+
+
+def _oracle(sd, img, offs, dlogits):
+    img = img.clone().requires_grad_(True)
+    crops = O.replicate_and_crop(img, offs, 448, True)
+    taps = {}
+    logits = O.resnet50_forward(crops, sd, taps)
+    g, = torch.autograd.grad((logits * dlogits).sum(), img)
+    return logits.detach(), {k: v.detach() for k, v in taps.items()}, g
+
+
+def _native(sd, img, offs, dlogits, precision, want_taps=True):
+    from regressor_guided_image_editing_b200 import ops
+    reps = offs.shape[1]
+    reg = ops.Regressor(sd, max_crops=reps, precision=precision)
+    img_d, offs_d = img.to(DEV).contiguous(), offs.to(DEV).contiguous()
+    logits = reg.forward(img_d, offs_d, normalize=True)
+    taps = {}
+    if want_taps:
+        shapes = {"stem": (64, 224), "pool": (64, 112)}
+        for name in TAPS:
+            if name in shapes:
+                c, h = shapes[name]
+            else:
+                s = int(name[5])
+                cm = 64 << (s - 1)
+                h = 224 >> s
+                if name.endswith(".c1"):
+                    c = cm
+                    h = h * 2 if (name[7] == "0" and s > 1) else h
+                elif name.endswith(".c2"):
+                    c = cm
+                else:
+                    c = 4 * cm
+            taps[name] = reg.tap(name, (reps, c, h, h)).cpu()
+    dimg = torch.empty_like(img_d)
+    reg.backward(dlogits.to(DEV).contiguous(), dimg)
+    torch.cuda.synchronize()
+    return logits.cpu(), taps, dimg.cpu()
+
+
+def test_fp32_mode_matches_oracle(sd):
+    reps = 2
+    img, offs = _inputs(reps)
+    dlogits = torch.randn(reps, 4, generator=torch.Generator().manual_seed(3))
+    lo, to, go = _oracle(sd, img, offs, dlogits)
+    ln, tn, gn = _native(sd, img, offs, dlogits, "fp32")
+    for name in TAPS:
+        ref = to[name]
+        err = (tn[name] - ref).abs().max().item()
+        scale = ref.abs().max().item()
+        print(f"{name:14s} max-abs err {err:.3e} (max |ref| {scale:.3f})")
+        assert err <= 2e-4 * max(scale, 1.0), f"{name}: {err}"
+    lerr = (ln - lo).abs().max().item()
+    print("logits", ln.flatten()[:4], lo.flatten()[:4], lerr)
+    assert lerr <= 2e-4 * max(lo.abs().max().item(), 1.0)
+    gerr = (gn - go).abs().max().item() / go.abs().max().item()
+    grel = (gn - go).abs().mean().item() / go.abs().mean().item()
+    print(f"d(image): max-rel {gerr:.3e} mean-rel {grel:.3e}")
+    assert gerr <= 5e-3 and grel <= 1e-3
+
+
+def test_bf16_tcgen05_matches_bf16_simt_and_oracle(sd):
+    reps = 2
+    img, offs = _inputs(reps, seed=6)
+    dlogits = torch.randn(reps, 4, generator=torch.Generator().manual_seed(4))
+    lo, to, go = _oracle(sd, img, offs, dlogits)
+    ls, ts, gs = _native(sd, img, offs, dlogits, "bf16_simt")
+    lt, tt, gt = _native(sd, img, offs, dlogits, "bf16")
+    for name in TAPS:
+        ref = to[name]
+        scale = max(ref.abs().max().item(), 1.0)
+        e_ts = (tt[name] - ts[name]).abs().max().item() / scale
+        e_to = (tt[name] - ref).abs().max().item() / scale
+        print(f"{name:14s} tcgen05 vs simt-bf16 {e_ts:.3e}   tcgen05 vs fp32 oracle {e_to:.3e}")
+        assert e_ts <= 3e-2, f"{name}: tcgen05 vs CUDA-core bf16 {e_ts}"
+        assert e_to <= 6e-2, f"{name}: tcgen05 vs oracle {e_to}"
+    print("logits tcgen05", lt.flatten()[:4], "simt", ls.flatten()[:4], "oracle", lo.flatten()[:4])
+    assert (lt - lo).abs().max().item() <= 5e-2 * max(lo.abs().max().item(), 1.0)
+    assert (lt - ls).abs().max().item() <= 2e-2 * max(lo.abs().max().item(), 1.0)
+    cos = F.cosine_similarity(gt.flatten(), go.flatten(), dim=0).item()
+    cos_s = F.cosine_similarity(gt.flatten(), gs.flatten(), dim=0).item()
+    print(f"d(image) cosine: tcgen05 vs oracle {cos:.5f}, tcgen05 vs simt-bf16 {cos_s:.5f}; "
+          f"norm ratio {gt.norm().item() / go.norm().item():.4f}")
+    assert cos >= 0.98 and cos_s >= 0.99
+    assert abs(gt.norm().item() / go.norm().item() - 1.0) <= 0.05
+
+
+def test_regressor_golden(sd, golden_dir):
+    """Reference-generated golden (ValenceArousalLoss forward + backward on CPU) through the native fp32 path."""
+    from regressor_guided_image_editing_b200 import ops
+    gold = torch.load(os.path.join(golden_dir, "regressor.pt"))
+    for k, v in gold["weights_probe"].items():
+        assert torch.equal(sd[k].flatten()[:4], v), "seeded state_dict differs from the one the golden was made with"
+    for tag in ("up256", "down512", "same480", "rect300x400"):
+        g = gold[tag]
+        img = O.synthetic_image(g["image_index"], g["h"], g["w"])[None].to(DEV).contiguous()
+        oh, ow = ops.resize_output_size(g["h"], g["w"], 480)
+        rs = ops.Resize(g["h"], g["w"], oh, ow)
+        x = rs.fwd(img)
+        reg = ops.Regressor(sd, max_crops=10, precision="fp32")
+        offs = g["offsets"].to(DEV).contiguous()
+        logits = reg.forward(x, offs, normalize=True)
+        preds = torch.empty(1, 4, device=DEV)
+        loss = torch.empty(1, device=DEV)
+        dlogits = torch.empty_like(logits)
+        ops.va_head(logits, 1, 10, True, g["target"].to(DEV), 0.5, 0.0, 3, g["weight_clf"], preds, loss, dlogits)
+        dx = torch.empty_like(x)
+        reg.backward(dlogits, dx)
+        dimg = rs.bwd(dx)
+        torch.cuda.synchronize()
+        perr = (preds.cpu()[:, :2] - g["pred"]).abs().max().item()
+        lerr = abs(loss.item() - g["loss"].item())
+        print(tag, "pred", preds.cpu()[0, :2].tolist(), g["pred"][0].tolist(), "loss", loss.item(), g["loss"].item())
+        assert perr <= 2e-5 and lerr <= 1e-6
+        gd = dimg.cpu()[0, :, ::8, ::8]
+        gerr = (gd - g["grad_ds"]).abs().max().item() / g["grad_max"].item()
+        serr = abs(dimg.abs().sum().item() - g["grad_abs_sum"].item()) / g["grad_abs_sum"].item()
+        print(tag, f"grad: max-rel {gerr:.3e}, abs-sum rel {serr:.3e}")
+        assert gerr <= 2e-2 and serr <= 5e-3
+        del reg
