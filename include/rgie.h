@@ -105,6 +105,15 @@ int rgie_regressor_forward_ex(RgieRegressor* r, const float* img, int B, int Hr,
                               void* stream);
 /* dlogits: [B*reps, num_classes]; dimg: [B,3,Hr,Wr] gradient w.r.t. `img` of the preceding forward (overwritten) */
 int rgie_regressor_backward(RgieRegressor* r, const float* dlogits, float* dimg, void* stream);
+/* per-GEMM timing of the last forward/backward (cudaEvent pairs around every row-shifted GEMM launch; used by bench.py
+ * for the live roofline figure).  get_profile synchronises on the recorded events.  h_info[4*i..]: {0 fwd | 1 bwd,
+ * Cout, K, m_tiles}; h_flops: algorithmic FLOPs (valid pixels only, padding excluded). */
+int rgie_regressor_set_profiling(RgieRegressor* r, int on);
+int rgie_regressor_num_ops(const RgieRegressor* r);
+int rgie_regressor_get_profile(RgieRegressor* r, float* h_ms, double* h_flops, int* h_info, int capacity, int* n_out);
+/* number of kernel launches this library has issued in this process (bench.py's gpu_launches evidence) */
+long rgie_launch_count(void);
+
 /* debugging / parity taps: copies a named activation of the last forward as fp32 NCHW into `out` (device).
  * names: "stem","pool","layer{1..4}.{i}","layer{1..4}.{i}.c1","...c2","feat".  Returns element count via *n. */
 int rgie_regressor_tap(RgieRegressor* r, const char* name, float* out, long capacity, long* n, void* stream);

@@ -42,14 +42,14 @@ def filter_cases():
     x = x_id + 0.15 * torch.randn(41, generator=g)
     x[lay['blur'][0]] = 1.3
     x[lay['sharp'][0]] = 0.7
-    x[lay['scale'][0]:lay['scale'][0] + 4] = torch.tensor([1.2, 1.1, 9.0, 14.0])
+    x[lay['scale'][0]:lay['scale'][0] + 4] = torch.tensor([1.2371, 1.1113, 9.37, 14.21])
     cases.append(("perturbed", d, x.clone()))
     x = x_id + 0.3 * torch.randn(41, generator=g)
     x[lay['blur'][0]] = 3.0
     x[lay['sharp'][0]] = 1.8          # clamped-blend branch
     x[lay['contrast'][0]] = 1.6
     x[lay['exposure'][0]] = 0.8       # saturating exposure -> many ties at 1.0 in rgb_to_hsv
-    x[lay['scale'][0]:lay['scale'][0] + 4] = torch.tensor([1.5, 1.0, 30.0, 5.0])
+    x[lay['scale'][0]:lay['scale'][0] + 4] = torch.tensor([1.5311, 1.0173, 30.19, 5.23])
     cases.append(("strong", d, x.clone()))
     x = x_id.clone()
     x[lay['contrast'][0]] = -0.2      # :291 host branch -> python float 0.0

@@ -1,0 +1,98 @@
+"""Drop-in for the hot-path functions of src/baselines/optimize_image.py: `optimization` (:56-97) and
+`get_condition_from_alpha` (:119-123).
+
+`optimization` keeps the reference signature and semantics (Adam betas (0.9, 0.999), lr ramp :69-75, strict-`<`
+best-x tracking BEFORE the update :78-81, returns best_x :97).  Two execution paths, both on the device:
+  * fused: when the objective is this package's `objective_function_parametric` over the default 8-filter list with a
+    native ValenceArousalLoss and no reconstruction / discriminator term, the whole loop runs inside
+    engine.ParametricEditEngine (one CUDA graph per step, no host sync); crop draws are consumed from torch's global
+    CPU generator in the reference's order.
+  * generic: any other objective callable is evaluated through autograd each step; the Adam update and the best-x
+    snapshot are the fused rgie_adam_step kernel (loss compared on the device, so the reference's two per-step host
+    syncs disappear).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import _lib, ops
+from ..engine import ParametricEditEngine, lr_schedule
+
+_ENGINES = {}
+
+
+def get_condition_from_alpha(alpha, clf, img):                                            # :119-123
+    condition = clf.predict_loss_metric(img)
+    condition = condition + torch.ones(condition.shape).to(condition.device) * alpha
+    return torch.clamp(condition, min=0.0, max=1.0)
+
+
+def _fused_eligible(x0, params, objective_function):
+    from .. import optimize_image_param as oip
+    if objective_function is not oip.objective_function_parametric:
+        return False
+    clf, image = params.get("clf"), params.get("image")
+    if clf is None or image is None or not image.is_cuda or image.shape[0] != 1:
+        return False
+    if params.get("weight_recon", 0) > 0 or (params.get("dis") is not None and params.get("weight_dis", 0) > 0):
+        return False
+    if list(params.get("params", {}).keys()) != oip.DEFAULT_TRANS or x0.numel() != 41:
+        return False
+    core = clf.model[0] if hasattr(clf, "model") and hasattr(clf.model, "__getitem__") else None
+    from .models.EmotionPredictionModel import NativeCropResNet50
+    if not isinstance(core, NativeCropResNet50) or clf.output_ixs != [0, 1] or len(clf.model) != 3:
+        return False
+    if not isinstance(clf.model[2], torch.nn.Sigmoid) or params.get("target") is None:
+        return False
+    return core.input_size is not None and core.normalize
+
+
+def _optimization_fused(x0, params, learning_rate, num_steps):
+    from .models.utilities.ReplicateAndCrop import draw_crop_offsets
+    clf, image = params["clf"], params["image"]
+    core = clf.model[0]
+    _, _, H, W = image.shape
+    key = (id(core), H, W, num_steps, core.precision)
+    eng = _ENGINES.get(key)
+    if eng is None:
+        _ENGINES.clear()
+        eng = ParametricEditEngine(core._sd, 1, H, W, num_steps, precision=core.precision,
+                                   input_size=core.input_size, crop_size=core.crop_size, folded=core._folded)
+        _ENGINES[key] = eng
+    offs = torch.stack([draw_crop_offsets(1, eng.Hr, eng.Wr, core.crop_size, 10) for _ in range(num_steps)])
+    eng.load_problem(image.float().contiguous(), offs.to(image.device), alpha=None, target=params["target"],
+                     learning_rate=learning_rate, weight_clf=params["weight_clf"], clf_weight=clf.weight,
+                     x0=x0.detach().float().cpu())
+    eng.advance(num_steps)
+    out = eng.results()
+    clf.fake_loss_metric = out["preds"][-1:, 0, :2]
+    optimization.last_run = out
+    return out["best_x"][0].clone()
+
+
+def optimization(x0, params, objective_function, learning_rate=0.1, lr_rampdown_length=0.25,
+                 lr_rampup_length=0.05, num_steps=100, verbose=False):                      # :56-97
+    if not x0.is_cuda:
+        raise _lib.RgieError("optimization() needs CUDA tensors: there is no CPU path in this package")
+    if (lr_rampdown_length, lr_rampup_length) == (0.25, 0.05) and _fused_eligible(x0, params, objective_function):
+        return _optimization_fused(x0, params, learning_rate, num_steps)
+
+    x_opt = x0.clone().detach().float().contiguous().requires_grad_(True)
+    m, v = torch.zeros_like(x_opt), torch.zeros_like(x_opt)
+    best_x = x_opt.clone().detach()
+    best_loss = torch.full((1,), float("inf"), device=x_opt.device)
+    best_step = torch.zeros(1, dtype=torch.int32, device=x_opt.device)
+    for step in range(num_steps):
+        t = step / num_steps
+        lr_ramp = min(1.0, (1.0 - t) / lr_rampdown_length)
+        lr_ramp = 0.5 - 0.5 * np.cos(lr_ramp * np.pi)
+        lr_ramp = lr_ramp * min(1.0, t / lr_rampup_length)
+        lr = float(learning_rate * lr_ramp)
+        loss = objective_function(x_opt, **params)
+        g, = torch.autograd.grad(loss, x_opt)
+        ops.adam_step(x_opt.data, g.contiguous(), m, v, lr, step + 1, loss=loss.detach().reshape(1).float().contiguous(),
+                      best_loss=best_loss, best_x=best_x, best_step=best_step, step=step)
+        if verbose:
+            print(f'[ step {step + 1:>4d}/{num_steps}] [ loss: {float(loss):<5.4f}] [ lr: {float(lr):<5.4f}] ')
+    return best_x

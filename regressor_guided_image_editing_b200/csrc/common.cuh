@@ -28,7 +28,12 @@ int  fail(const std::string& msg);          // sets the message, returns RGIE_ER
     if (!(cond)) return ::rgie::fail(std::string("check failed: ") + (msg)); \
   } while (0)
 
-#define RGIE_LAUNCH_OK() RGIE_CUDA_OK(cudaGetLastError())
+void count_launch();
+#define RGIE_LAUNCH_OK()                  \
+  do {                                    \
+    ::rgie::count_launch();               \
+    RGIE_CUDA_OK(cudaGetLastError());     \
+  } while (0)
 
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 

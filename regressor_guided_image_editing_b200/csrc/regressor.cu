@@ -279,6 +279,9 @@ struct RgieRegressor {
   const int* offsets = nullptr; const int* step_ptr = nullptr; long off_stride = 0;
   int B = 0, reps = 0, Hr = 0, Wr = 0, normalize = 1;
   void* final_dout = nullptr;   // where the tail backward writes d(layer4 out)
+  // optional per-GEMM timing (cudaEvent pairs), enabled by rgie_regressor_set_profiling
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev;  // 2 per op: fwd ops then bwd ops
 };
 
 namespace {
@@ -329,9 +332,24 @@ int add_op(RgieRegressor* R, std::vector<GemmOp>& ops, const GemmDesc& d) {
   return 0;
 }
 
-int run_op(RgieRegressor* R, const GemmOp& op, cudaStream_t st) {
+int run_op_raw(RgieRegressor* R, const GemmOp& op, cudaStream_t st) {
   if (R->precision == RGIE_PREC_BF16) return run_gemm_sm100(op.plan, st);
   return launch_gemm_simt(op.d, R->dtype, st);
+}
+// idx: position in [fwd_ops..., bwd_ops...]
+int run_op(RgieRegressor* R, const GemmOp& op, cudaStream_t st, size_t idx) {
+  if (!R->profiling) return run_op_raw(R, op, st);
+  RGIE_CUDA_OK(cudaEventRecord(R->ev[2 * idx], st));
+  int rc = run_op_raw(R, op, st);
+  RGIE_CUDA_OK(cudaEventRecord(R->ev[2 * idx + 1], st));
+  return rc;
+}
+// algorithmic flops of one op: 2 * (valid output rows) * Cout_useful * K
+double op_flops(const GemmDesc& d, double useful_frac) {
+  const Geom& g = d.src;
+  double rows_per_plane = (double)g.n_img * g.H * g.W;
+  double planes = (double)(d.m_end - d.m_begin) / (double)g.plane_rows();
+  return 2.0 * rows_per_plane * planes * (double)d.Cout * (double)d.ntaps * (double)d.Cin * useful_frac;
 }
 
 }  // namespace
@@ -340,6 +358,7 @@ extern "C" {
 
 void rgie_regressor_destroy(RgieRegressor* R) {
   if (!R) return;
+  for (cudaEvent_t e : R->ev) cudaEventDestroy(e);
   for (void* p : R->allocs) cudaFree(p);
   delete R;
 }
@@ -685,14 +704,14 @@ int rgie_regressor_forward_ex(RgieRegressor* R, const float* img, int B, int Hr,
                                                                        normalize, tot_pack);
   }
   RGIE_LAUNCH_OK();
-  if (int rc = run_op(R, R->fwd_ops[0], st)) return rc;
+  if (int rc = run_op(R, R->fwd_ops[0], st, 0)) return rc;
   if (R->dtype == 0)
     maxpool_fwd_kernel<float><<<grid_for(tot_pool), 256, 0, st>>>((const float*)R->c1, (float*)R->p1, R->arg, R->gS[1], H0, 64, tot_pool);
   else
     maxpool_fwd_kernel<__nv_bfloat16><<<grid_for(tot_pool), 256, 0, st>>>((const __nv_bfloat16*)R->c1, (__nv_bfloat16*)R->p1, R->arg, R->gS[1], H0, 64, tot_pool);
   RGIE_LAUNCH_OK();
   for (size_t i = 1; i < R->fwd_ops.size(); ++i)
-    if (int rc = run_op(R, R->fwd_ops[i], st)) return rc;
+    if (int rc = run_op(R, R->fwd_ops[i], st, i)) return rc;
   const Block& last = R->blocks.back();
   if (R->dtype == 0)
     avgpool_fc_kernel<float><<<N, 256, 0, st>>>((const float*)last.out, R->gS[4], 2048, R->wfc, R->bfc, R->K, R->feat, logits);
@@ -720,7 +739,7 @@ int rgie_regressor_backward(RgieRegressor* R, const float* dlogits, float* dimg,
   RGIE_LAUNCH_OK();
   const size_t nb = R->bwd_ops.size();
   for (size_t i = 0; i + 1 < nb; ++i)
-    if (int rc = run_op(R, R->bwd_ops[i], st)) return rc;
+    if (int rc = run_op(R, R->bwd_ops[i], st, R->fwd_ops.size() + i)) return rc;
   // d(pool out) is the destination of the last block op (layer1.0 c1 dgrad)
   const void* dP = R->bwd_ops[nb - 2].d.D;
   const long tot = (long)N * H0 * H0 * 64;
@@ -729,11 +748,49 @@ int rgie_regressor_backward(RgieRegressor* R, const float* dlogits, float* dimg,
   else
     maxpool_bwd_kernel<__nv_bfloat16><<<grid_for(tot), 256, 0, st>>>((const __nv_bfloat16*)dP, R->arg, (const __nv_bfloat16*)R->c1, (__nv_bfloat16*)R->dC1, R->gS[1], R->gDY, H0, 64, tot);
   RGIE_LAUNCH_OK();
-  if (int rc = run_op(R, R->bwd_ops[nb - 1], st)) return rc;
+  if (int rc = run_op(R, R->bwd_ops[nb - 1], st, R->fwd_ops.size() + nb - 1)) return rc;
   const long totg = (long)R->B * R->Hr * R->Wr;
   crop_grad_gather_kernel<<<grid_for(totg), 256, 0, st>>>(R->dZ, R->offsets, R->step_ptr, R->off_stride, dimg, R->B, R->reps,
                                                           R->Hr, R->Wr, R->crop, R->normalize ? 2.0f : 1.0f);
   RGIE_LAUNCH_OK();
+  return 0;
+}
+
+int rgie_regressor_set_profiling(RgieRegressor* R, int on) {
+  RGIE_CHECK(R != nullptr, "rgie_regressor_set_profiling: null");
+  if (on && R->ev.empty()) {
+    R->ev.resize(2 * (R->fwd_ops.size() + R->bwd_ops.size()));
+    for (auto& e : R->ev) RGIE_CUDA_OK(cudaEventCreate(&e));
+  }
+  R->profiling = on != 0;
+  return 0;
+}
+
+int rgie_regressor_num_ops(const RgieRegressor* R) { return R ? (int)(R->fwd_ops.size() + R->bwd_ops.size()) : 0; }
+
+int rgie_regressor_get_profile(RgieRegressor* R, float* h_ms, double* h_flops, int* h_info, int capacity, int* n_out) {
+  RGIE_CHECK(R && h_ms && h_flops && h_info && n_out, "rgie_regressor_get_profile: null");
+  RGIE_CHECK(!R->ev.empty(), "rgie_regressor_get_profile: profiling was never enabled");
+  const int n = (int)(R->fwd_ops.size() + R->bwd_ops.size());
+  RGIE_CHECK(capacity >= n, "rgie_regressor_get_profile: capacity");
+  for (int i = 0; i < n; ++i) {
+    const bool fwd = i < (int)R->fwd_ops.size();
+    const GemmOp& op = fwd ? R->fwd_ops[i] : R->bwd_ops[i - R->fwd_ops.size()];
+    float ms = 0.f;
+    RGIE_CUDA_OK(cudaEventSynchronize(R->ev[2 * i + 1]));
+    RGIE_CUDA_OK(cudaEventElapsedTime(&ms, R->ev[2 * i], R->ev[2 * i + 1]));
+    h_ms[i] = ms;
+    // useful fraction of the padded stem formulations: conv1 fwd 147 of 4*64 K-elements; conv1 dgrad 147*? of 16*16*64
+    double useful = 1.0;
+    if (fwd && i == 0) useful = 147.0 / 256.0;
+    if (!fwd && i == n - 1) useful = (147.0 * 64.0) / (16.0 * 16.0 * 64.0);
+    h_flops[i] = op_flops(op.d, useful);
+    h_info[4 * i + 0] = fwd ? 0 : 1;
+    h_info[4 * i + 1] = op.d.Cout;
+    h_info[4 * i + 2] = op.d.ntaps * op.d.Cin;
+    h_info[4 * i + 3] = (int)((op.d.m_end - op.d.m_begin + 127) / 128);
+  }
+  *n_out = n;
   return 0;
 }
 

@@ -39,8 +39,11 @@ SINGLE_CASES = [
     ("contrast", 1.0), ("contrast", 0.5), ("contrast", 1.8), ("contrast", 0.0),
     ("sharp", 0.0), ("sharp", 0.5), ("sharp", 1.0), ("sharp", 2.5),
     ("blur", 1e-4), ("blur", 0.5), ("blur", 2.0), ("blur", 6.0),
-    ("scale", [1.0, 1.0, 0.0, 0.0]), ("scale", [1.2, 1.1, 9.0, 14.0]), ("scale", [1.5, 1.0, 30.0, 5.0]),
-    ("scale", [1.05, 1.3, 0.0, 40.0]),
+    # generic (non-"nice") values: with e.g. sx=1.5, cx=30 a third of the sample points land exactly on pixel centres,
+    # where bilinear sampling has a kink and the side the reference takes is decided by float round-off of
+    # torch.linspace (platform dependent); identity is checked separately (forward + d(image) only)
+    ("scale", [1.0, 1.0, 0.0, 0.0]), ("scale", [1.2371, 1.1113, 9.37, 14.21]), ("scale", [1.5311, 1.0173, 30.19, 5.23]),
+    ("scale", [1.0537, 1.3071, 0.0, 40.43]),
 ]
 
 
@@ -76,6 +79,8 @@ def test_single_filter_vs_oracle(name, val, hw):
     pden = gp_c.abs().max().item() + 1e-6 * gout.numel() ** 0.5
     perr = (gp_g.cpu() - gp_c).abs().max().item() / pden
     ptol = 5e-3 if name == "scale" else 5e-4
+    if name == "scale" and list(val) == [1.0, 1.0, 0.0, 0.0]:
+        return            # d(param) at exact identity is a kink (see SINGLE_CASES comment)
     assert perr <= ptol, f"{name} d(param) {gp_g.cpu().flatten()[:4]} vs {gp_c.flatten()[:4]} rel {perr}"
 
 
@@ -112,8 +117,12 @@ def test_chain_vs_golden(golden_dir):
         assert err <= 5e-4, f"{key}: forward max-abs {err}"
         gout = torch.randn(ref.shape, generator=torch.Generator().manual_seed(g["gout_seed"])).to(DEV)
         gx, gim = torch.autograd.grad((outs[-1] * gout).sum(), [x, im], allow_unused=True)
-        den = g["grad_x"].abs().max().item() + 1e-3
-        rel = (gx.cpu() - g["grad_x"]).abs().max().item() / den
+        gx_c, gx_r = gx.cpu().clone(), g["grad_x"].clone()
+        if key.startswith(("identity", "branches")) and "scale" in g["trans"]:
+            lay = O.param_layout(g["trans"])["scale"]
+            gx_c[lay[0]:lay[0] + 4] = 0; gx_r[lay[0]:lay[0] + 4] = 0      # scale at exact identity: kink, side = round-off
+        den = gx_r.abs().max().item() + 1e-3
+        rel = (gx_c - gx_r).abs().max().item() / den
         assert rel <= 2e-2, f"{key}: d(x) rel {rel}\n{gx.cpu()}\n{g['grad_x']}"
         gden = g["grad_im"].abs().mean().item() + 1e-12
         grel = (gim.cpu() - g["grad_im"]).abs().mean().item() / gden
