@@ -641,10 +641,22 @@ __device__ __forceinline__ float lin_coord(int i, int n) {       // torch.linspa
   return (i < n / 2) ? (-1.0f + step * (float)i) : (1.0f - step * (float)(n - 1 - i));
 }
 
+struct SampleCoord { int i0; float w1; };
+__device__ __forceinline__ SampleCoord sample_coord(int i, int n, float inv_s, float t) {
+  const float gn = lin_coord(i, n) * inv_s + t;
+  const float ix = ((gn + 1.0f) * 0.5f) * (float)(n - 1);
+  const float f = floorf(ix);
+  SampleCoord c;
+  c.i0 = (int)f;
+  c.w1 = ix - f;
+  return c;
+}
+
+// forward (BWD=false): out = clamp(bilinear(in)).  backward pass A (BWD=true): gm = g * [0 <= bilinear(in) <= 1] written
+// to `out`, plus the per-block partial sums of d(sx, sy, cx, cy).
 template <bool BWD>
 __global__ void __launch_bounds__(kThreads) scale_kernel(const float* __restrict__ in, const float* __restrict__ gout,
-                                                        float* __restrict__ out, float* __restrict__ gin,
-                                                        const float* __restrict__ p, int stride,
+                                                        float* __restrict__ out, const float* __restrict__ p, int stride,
                                                         float* __restrict__ partial, int H, int W) {
   const int b = blockIdx.y;
   const float* pb = p + (long)b * stride;
@@ -656,12 +668,9 @@ __global__ void __launch_bounds__(kThreads) scale_kernel(const float* __restrict
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
     const int y = i / W, x = i - y * W;
-    const float xn = lin_coord(x, W), yn = lin_coord(y, H);
-    const float gxn = xn * k.inv_sx + k.t02, gyn = yn * k.inv_sy + k.t12;
-    const float ix = ((gxn + 1.0f) * 0.5f) * (float)(W - 1), iy = ((gyn + 1.0f) * 0.5f) * (float)(H - 1);
-    const float fx0 = floorf(ix), fy0 = floorf(iy);
-    const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
-    const float wx1 = ix - fx0, wx0 = 1.0f - wx1, wy1 = iy - fy0, wy0 = 1.0f - wy1;
+    const SampleCoord sxc = sample_coord(x, W, k.inv_sx, k.t02), syc = sample_coord(y, H, k.inv_sy, k.t12);
+    const int x0 = sxc.i0, y0 = syc.i0, x1 = x0 + 1, y1 = y0 + 1;
+    const float wx1 = sxc.w1, wx0 = 1.0f - wx1, wy1 = syc.w1, wy0 = 1.0f - wy1;
     const bool vx0 = x0 >= 0 && x0 < W, vx1 = x1 >= 0 && x1 < W, vy0 = y0 >= 0 && y0 < H, vy1 = y1 >= 0 && y1 < H;
     float gix = 0.f, giy = 0.f;
 #pragma unroll
@@ -676,16 +685,13 @@ __global__ void __launch_bounds__(kThreads) scale_kernel(const float* __restrict
         out[base + (long)c * HW + i] = clamp01(o);
       } else {
         const float g = in01(o) ? gout[base + (long)c * HW + i] : 0.f;
-        float* gp = gin + base + (long)c * HW;
-        if (vy0 && vx0) atomicAdd(gp + (long)y0 * W + x0, g * wx0 * wy0);
-        if (vy0 && vx1) atomicAdd(gp + (long)y0 * W + x1, g * wx1 * wy0);
-        if (vy1 && vx0) atomicAdd(gp + (long)y1 * W + x0, g * wx0 * wy1);
-        if (vy1 && vx1) atomicAdd(gp + (long)y1 * W + x1, g * wx1 * wy1);
+        out[base + (long)c * HW + i] = g;
         gix += g * ((v01 - v00) * wy0 + (v11 - v10) * wy1);
         giy += g * ((v10 - v00) * wx0 + (v11 - v01) * wx1);
       }
     }
     if (BWD) {
+      const float xn = lin_coord(x, W), yn = lin_coord(y, H);
       const float ggx = gix * 0.5f * (float)(W - 1), ggy = giy * 0.5f * (float)(H - 1);   // d/d(grid x), d/d(grid y)
       acc[0] += ggx * ((-xn + a * cx - 1.0f) / (sx * sx)) + ggy * (bb * cy / sy);         // d/dsx
       acc[1] += ggy * ((-yn + bb * (1.0f - sx) * cy - 1.0f) / (sy * sy));                  // d/dsy
@@ -694,6 +700,51 @@ __global__ void __launch_bounds__(kThreads) scale_kernel(const float* __restrict
     }
   }
   if (BWD) block_reduce_store<4>(acc, partial + ((long)b * gridDim.x + blockIdx.x) * 4);
+}
+
+// backward pass B: d(in)[v,u] = sum over the destination pixels whose bilinear footprint contains (v,u) -- a gather, so
+// the result is deterministic (no atomics).  The warp is separable and monotone: the candidate destination columns /
+// rows of a source column / row form a contiguous range found by inverting the affine coordinate map.
+__global__ void __launch_bounds__(kThreads) scale_bwd_gather_kernel(const float* __restrict__ gm, float* __restrict__ gin,
+                                                                   const float* __restrict__ p, int stride, int H, int W) {
+  const int b = blockIdx.y;
+  const WarpCoef k = warp_coef(p + (long)b * stride, H, W);
+  const long base = (long)b * 3 * H * W;
+  const int HW = H * W;
+  // ix(x) ~= c0x + slope_x * x  (exact values are recomputed per candidate with sample_coord)
+  const float gx0 = lin_coord(0, W) * k.inv_sx + k.t02, gx1 = lin_coord(W - 1, W) * k.inv_sx + k.t02;
+  const float c0x = ((gx0 + 1.0f) * 0.5f) * (float)(W - 1);
+  const float slx = (((gx1 + 1.0f) * 0.5f) * (float)(W - 1) - c0x) / (float)(W - 1);
+  const float gy0 = lin_coord(0, H) * k.inv_sy + k.t12, gy1 = lin_coord(H - 1, H) * k.inv_sy + k.t12;
+  const float c0y = ((gy0 + 1.0f) * 0.5f) * (float)(H - 1);
+  const float sly = (((gy1 + 1.0f) * 0.5f) * (float)(H - 1) - c0y) / (float)(H - 1);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    const int v = i / W, u = i - v * W;
+    int xlo = (int)floorf(((float)(u - 1) - c0x) / slx) - 1, xhi = (int)ceilf(((float)(u + 1) - c0x) / slx) + 1;
+    int ylo = (int)floorf(((float)(v - 1) - c0y) / sly) - 1, yhi = (int)ceilf(((float)(v + 1) - c0y) / sly) + 1;
+    xlo = max(xlo, 0); xhi = min(xhi, W - 1); ylo = max(ylo, 0); yhi = min(yhi, H - 1);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int y = ylo; y <= yhi; ++y) {
+      const SampleCoord cy = sample_coord(y, H, k.inv_sy, k.t12);
+      float wy;
+      if (cy.i0 == v) wy = 1.0f - cy.w1;
+      else if (cy.i0 + 1 == v) wy = cy.w1;
+      else continue;
+      for (int x = xlo; x <= xhi; ++x) {
+        const SampleCoord cx = sample_coord(x, W, k.inv_sx, k.t02);
+        float wx;
+        if (cx.i0 == u) wx = 1.0f - cx.w1;
+        else if (cx.i0 + 1 == u) wx = cx.w1;
+        else continue;
+        const float w = wx * wy;
+        const long o = base + (long)y * W + x;
+        s0 = fmaf(w, gm[o], s0);
+        s1 = fmaf(w, gm[o + HW], s1);
+        s2 = fmaf(w, gm[o + 2L * HW], s2);
+      }
+    }
+    gin[base + i] = s0; gin[base + HW + i] = s1; gin[base + 2L * HW + i] = s2;
+  }
 }
 
 int plane_blocks(int HW) { int n = ceil_div(HW, kThreads * 4); return n > 64 ? 64 : (n < 1 ? 1 : n); }
@@ -768,7 +819,7 @@ int rgie_filter_fwd(int kind, const float* in, float* out, const float* p, int p
     case RGIE_F_SCALE: {
       RGIE_CHECK(H >= 2 && W >= 2, "scale: image too small");
       dim3 grid(plane_blocks(HW), B);
-      scale_kernel<false><<<grid, kThreads, 0, st>>>(in, nullptr, out, nullptr, p, p_stride, nullptr, H, W);
+      scale_kernel<false><<<grid, kThreads, 0, st>>>(in, nullptr, out, p, p_stride, nullptr, H, W);
       RGIE_LAUNCH_OK();
       return 0;
     }
@@ -870,9 +921,11 @@ int rgie_filter_bwd(int kind, const float* in, const float* gout, float* gin, co
     case RGIE_F_SCALE: {
       RGIE_CHECK(H >= 2 && W >= 2, "scale: image too small");
       const int nb = plane_blocks(HW);
-      RGIE_CUDA_OK(cudaMemsetAsync(gin, 0, sizeof(float) * (size_t)B * 3 * HW, st));
+      float* gm = ws + (long)B * kMaxBlk * 24;
       dim3 grid(nb, B);
-      scale_kernel<true><<<grid, kThreads, 0, st>>>(in, gout, nullptr, gin, p, p_stride, partial, H, W);
+      scale_kernel<true><<<grid, kThreads, 0, st>>>(in, gout, gm, p, p_stride, partial, H, W);
+      RGIE_LAUNCH_OK();
+      scale_bwd_gather_kernel<<<grid, kThreads, 0, st>>>(gm, gin, p, p_stride, H, W);
       RGIE_LAUNCH_OK();
       finalize_partials<<<B, 32, 0, st>>>(partial, nb, 4, gp, gp_stride);
       break;

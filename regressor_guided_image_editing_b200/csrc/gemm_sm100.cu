@@ -2,10 +2,11 @@
 //
 //   D[map(m), n] = epi( sum_t sum_c A[m + row_off[t], c] * Wt[n, t*Cin + c] )          bf16 x bf16 -> fp32 (TMEM)
 //
-// One persistent CTA per SM, 192 threads:
+// One persistent CTA per SM, 320 threads:
 //   warp 0      : TMA producer   (cp.async.bulk.tensor.2d, 128B swizzle, zero fill for out-of-range rows = conv padding)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (cta_group::1, M=128, N=BN, K=16 per instruction)
-//   warps 2..5  : epilogue       (tcgen05.ld 32x32b -> bias / residual / ReLU / ReLU-mask -> row-remapped 16B stores)
+//   warps 2..9  : epilogue       (tcgen05.ld 32x32b -> bias / residual / ReLU / ReLU-mask -> row-remapped 16B stores;
+//                                 residual/mask operands prefetched one chunk ahead)
 // Pipelines: STAGES-deep smem ring (full/empty mbarriers) between TMA and MMA; 2 TMEM accumulator buffers
 // (tmem_full/tmem_empty) between MMA and epilogue so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
@@ -18,7 +19,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;                 // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;          // TMA warp + MMA warp + 8 epilogue warps
+constexpr int MAX_BIAS = 2048;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -121,7 +123,8 @@ struct SmemLayout {
   static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
   static constexpr int BAR_OFF = B_OFF + STAGES * B_STAGE_BYTES;   // full[S], empty[S], tfull[2], tempty[2]
   static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * STAGES + 4) * 8;
-  static constexpr int TOTAL = TMEM_PTR_OFF + 16;
+  static constexpr int BIAS_OFF = TMEM_PTR_OFF + 16;                // whole bias vector (<= MAX_BIAS floats)
+  static constexpr int TOTAL = BIAS_OFF + MAX_BIAS * 4;
   static constexpr int DYN_BYTES = TOTAL + 1024;   // + slack for manual 1024 B alignment
 };
 
@@ -157,7 +160,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);     // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), 8);     // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -165,6 +168,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_base + L::TMEM_PTR_OFF),
                  "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (d.bias != nullptr) {
+    float* sb = reinterpret_cast<float*>(smem + L::BIAS_OFF);
+    for (int i = threadIdx.x; i < d.Cout; i += NUM_THREADS) sb[i] = d.bias[i];
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -221,11 +228,21 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue (4 warps, one TMEM lane = one output row per thread) =====================
-    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    // ===================== epilogue (8 warps; one TMEM lane = one output row per thread) =====================
+    // warps 2..9: lane quarter q = warp & 3 (hardware restriction on tcgen05.ld), column half = (warp - 2) >> 2.
+    // The residual / ReLU-mask operands of a chunk are fetched one chunk ahead (and, for the first chunk of a tile,
+    // before waiting for the accumulator) so their HBM latency overlaps the TMEM read + math of the previous chunk.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
+    constexpr int NCH = BN / CH;                     // chunks per tile
+    constexpr int CPW = NCH >= 2 ? NCH / 2 : 1;      // chunks per warp
+    const int c_begin = NCH >= 2 ? half * CPW : 0;
+    const bool active = NCH >= 2 || half == 0;
     const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(d.res);
     const __nv_bfloat16* mask = reinterpret_cast<const __nv_bfloat16*>(d.mask);
+    const float* sbias = reinterpret_cast<const float*>(smem + L::BIAS_OFF);
+    const bool has_bias = d.bias != nullptr;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int mt = tile / num_n_tiles, nt = tile - mt * num_n_tiles;
@@ -234,69 +251,86 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const long m = d.m_begin + (long)mt * BM + row;
       long dest = -1;
       if (m < d.m_end) dest = map_row(d.src, d.dst_kind, d.dst, m);
-      const bool use_res = res != nullptr && m < d.res_rows;
+      const bool live = active && dest >= 0;
+      const bool use_res = live && res != nullptr && m < d.res_rows;
+      const bool use_mask = live && mask != nullptr;
+      const uint4* res_p = reinterpret_cast<const uint4*>(res + m * d.ld_res + nt * BN);
+      const uint4* mask_p = reinterpret_cast<const uint4*>(mask + m * d.ld_mask + nt * BN);
+      uint4 rcur[CH / 8], kcur[CH / 8], rnxt[CH / 8], knxt[CH / 8];
+      auto fetch = [&](int c, uint4* rr, uint4* kk) {
+#pragma unroll
+        for (int j = 0; j < CH / 8; ++j) {
+          if (use_res) rr[j] = __ldg(res_p + c * (CH / 8) + j);
+          if (use_mask) kk[j] = __ldg(mask_p + c * (CH / 8) + j);
+        }
+      };
+      fetch(c_begin, rcur, kcur);
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int c = 0; c < BN / CH; ++c) {
-        uint32_t r[CH];
-        tmem_ld<CH>(taddr + (uint32_t)(c * CH), r);
-        tmem_ld_wait();
-        const int n0 = nt * BN + c * CH;
-        if (dest >= 0 && n0 < d.Cout) {
-          float v[CH];
+      if (active) {
 #pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
-          if (d.bias) {
-            const float4* b4 = reinterpret_cast<const float4*>(d.bias + n0);
+        for (int ci = 0; ci < CPW; ++ci) {
+          const int c = c_begin + ci;
+          if (ci + 1 < CPW) fetch(c + 1, rnxt, knxt);
+          uint32_t r[CH];
+          tmem_ld<CH>(taddr + (uint32_t)(c * CH), r);
+          tmem_ld_wait();
+          const int n0 = nt * BN + c * CH;
+          if (live) {
+            float v[CH];
 #pragma unroll
-            for (int j = 0; j < CH / 4; ++j) {
-              float4 b = __ldg(b4 + j);
-              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-            }
-          }
-          if (use_res) {
-            const uint4* p = reinterpret_cast<const uint4*>(res + m * d.ld_res + n0);
+            for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
+            if (has_bias) {
+              const float4* b4 = reinterpret_cast<const float4*>(sbias + n0);
 #pragma unroll
-            for (int j = 0; j < CH / 8; ++j) {
-              uint4 u = __ldg(p + j);
-              v[8 * j + 0] += bf16_lo(u.x); v[8 * j + 1] += bf16_hi(u.x);
-              v[8 * j + 2] += bf16_lo(u.y); v[8 * j + 3] += bf16_hi(u.y);
-              v[8 * j + 4] += bf16_lo(u.z); v[8 * j + 5] += bf16_hi(u.z);
-              v[8 * j + 6] += bf16_lo(u.w); v[8 * j + 7] += bf16_hi(u.w);
-            }
-          }
-          if (d.relu) {
-#pragma unroll
-            for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (mask) {
-            const uint4* p = reinterpret_cast<const uint4*>(mask + m * d.ld_mask + n0);
-#pragma unroll
-            for (int j = 0; j < CH / 8; ++j) {
-              uint4 u = __ldg(p + j);
-              // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-              uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                uint32_t lo = w[e] & 0xFFFFu, hi = w[e] >> 16;
-                if (!(lo != 0 && lo < 0x8000u)) v[8 * j + 2 * e] = 0.f;
-                if (!(hi != 0 && hi < 0x8000u)) v[8 * j + 2 * e + 1] = 0.f;
+              for (int j = 0; j < CH / 4; ++j) {
+                const float4 b = b4[j];
+                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
               }
             }
-          }
-          if (d.d_fp32) {
-            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(d.D) + dest * d.ldd + n0);
+            if (use_res) {
 #pragma unroll
-            for (int j = 0; j < CH / 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.D) + dest * d.ldd + n0);
+              for (int j = 0; j < CH / 8; ++j) {
+                const uint4 u = rcur[j];
+                v[8 * j + 0] += bf16_lo(u.x); v[8 * j + 1] += bf16_hi(u.x);
+                v[8 * j + 2] += bf16_lo(u.y); v[8 * j + 3] += bf16_hi(u.y);
+                v[8 * j + 4] += bf16_lo(u.z); v[8 * j + 5] += bf16_hi(u.z);
+                v[8 * j + 6] += bf16_lo(u.w); v[8 * j + 7] += bf16_hi(u.w);
+              }
+            }
+            if (d.relu) {
 #pragma unroll
-            for (int j = 0; j < CH / 8; ++j)
-              o[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+              for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (use_mask) {
+#pragma unroll
+              for (int j = 0; j < CH / 8; ++j) {
+                const uint4 u = kcur[j];
+                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const uint32_t lo = w[e] & 0xFFFFu, hi = w[e] >> 16;
+                  if (!(lo != 0 && lo < 0x8000u)) v[8 * j + 2 * e] = 0.f;
+                  if (!(hi != 0 && hi < 0x8000u)) v[8 * j + 2 * e + 1] = 0.f;
+                }
+              }
+            }
+            if (d.d_fp32) {
+              float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(d.D) + dest * d.ldd + n0);
+#pragma unroll
+              for (int j = 0; j < CH / 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+              uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.D) + dest * d.ldd + n0);
+#pragma unroll
+              for (int j = 0; j < CH / 8; ++j)
+                o[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                  pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+            }
           }
+#pragma unroll
+          for (int j = 0; j < CH / 8; ++j) { rcur[j] = rnxt[j]; kcur[j] = knxt[j]; }
         }
       }
       tcgen05_fence_before();
@@ -376,7 +410,7 @@ int gemm_sm100_num_sms() {
 int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
   RGIE_CHECK(d.Cin % BK == 0, "gemm_sm100: Cin must be a multiple of 64");
   RGIE_CHECK(d.ntaps >= 1 && d.ntaps <= kMaxTaps, "gemm_sm100: ntaps out of range");
-  RGIE_CHECK(d.Cout % 16 == 0, "gemm_sm100: Cout must be a multiple of 16");
+  RGIE_CHECK(d.Cout % 16 == 0 && d.Cout <= MAX_BIAS, "gemm_sm100: Cout must be a multiple of 16 and <= 2048");
   RGIE_CHECK(d.a_rows < (1L << 31), "gemm_sm100: too many A rows for a TMA coordinate");
   int bn = d.Cout >= 256 ? 256 : (d.Cout >= 128 ? 128 : (d.Cout >= 64 ? 64 : 16));
   RGIE_CHECK(d.Cout % bn == 0 && d.n_pad % bn == 0, "gemm_sm100: Cout/n_pad must be a multiple of the N tile");

@@ -64,18 +64,48 @@ __global__ void __launch_bounds__(256) pack_crops_kernel(const float* __restrict
   }
 }
 
-// 3x3 stride-2 pad-1 max pool over plain NHWC [N,Hi,Hi,C] -> padded layout g (Ho = Hi/2), argmax code 0..8 (first max)
+// 16-byte vector of activations: 8 bf16 or 4 fp32
+template <typename T> struct Vec16 { static constexpr int N = 16 / sizeof(T); };
+template <typename T>
+__device__ __forceinline__ void vec_load(const T* p, float* v) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  if (sizeof(T) == 2) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { v[2 * e] = __uint_as_float(w[e] << 16); v[2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u); }
+  } else {
+    v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void vec_store(T* p, const float* v) {
+  uint4 u;
+  if (sizeof(T) == 2) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]),
+                   c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+  } else {
+    u.x = __float_as_uint(v[0]); u.y = __float_as_uint(v[1]); u.z = __float_as_uint(v[2]); u.w = __float_as_uint(v[3]);
+  }
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// 3x3 stride-2 pad-1 max pool over plain NHWC [N,Hi,Hi,C] -> padded layout g (Ho = Hi/2), argmax code 0..8 (first max).
+// One thread = one output pixel x 16 bytes of channels.
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const T* __restrict__ in, T* __restrict__ out,
                                                          uint8_t* __restrict__ arg, Geom g, int Hi, int C, long total) {
+  constexpr int V = Vec16<T>::N;
+  const int cv = C / V;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % C);
-    long q = idx / C;
+    const int c = (int)(idx % cv) * V;
+    long q = idx / cv;
     const int j = (int)(q % g.W); q /= g.W;
     const int i = (int)(q % g.H);
     const int n = (int)(q / g.H);
-    float best = -INFINITY;
-    int code = 0;
+    float best[V];
+    int code[V];
     bool first = true;
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
@@ -85,12 +115,24 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const T* __restrict__ 
       for (int dx = 0; dx < 3; ++dx) {
         const int x = 2 * j - 1 + dx;
         if (x < 0 || x >= Hi) continue;
-        const float v = to_f<T>(in[(((long)n * Hi + y) * Hi + x) * C + c]);
-        if (first || v > best) { best = v; code = dy * 3 + dx; first = false; }
+        float v[V];
+        vec_load<T>(in + (((long)n * Hi + y) * Hi + x) * C + c, v);
+#pragma unroll
+        for (int e = 0; e < V; ++e)
+          if (first || v[e] > best[e]) { best[e] = v[e]; code[e] = dy * 3 + dx; }
+        first = false;
       }
     }
-    out[geom_row(g, 0, n, i, j) * C + c] = from_f<T>(best);
-    arg[idx] = (uint8_t)code;
+    vec_store<T>(out + geom_row(g, 0, n, i, j) * C + c, best);
+    uint8_t* a = arg + (((long)n * g.H + i) * g.W + j) * C + c;
+    if (V == 8) {
+      uint2 pk;
+      pk.x = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
+      pk.y = code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24);
+      *reinterpret_cast<uint2*>(a) = pk;
+    } else {
+      *reinterpret_cast<uint32_t*>(a) = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
+    }
   }
 }
 // backward of the pool + the stem ReLU mask: dC1[n,y,x,c] (layout gd) = (C1 > 0) * sum_{windows whose argmax is (y,x)} dP
@@ -98,29 +140,40 @@ template <typename T>
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ dP, const uint8_t* __restrict__ arg,
                                                          const T* __restrict__ c1, T* __restrict__ dC1, Geom gp, Geom gd,
                                                          int Hi, int C, long total) {
+  constexpr int V = Vec16<T>::N;
+  const int cv = C / V;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % C);
-    long q = idx / C;
+    const int c = (int)(idx % cv) * V;
+    long q = idx / cv;
     const int x = (int)(q % Hi); q /= Hi;
     const int y = (int)(q % Hi);
     const int n = (int)(q / Hi);
-    float s = 0.f;
-    if (to_f<T>(c1[idx]) > 0.f) {
-      // windows i with 2i-1 <= y <= 2i+1  <=>  i in [ceil((y-1)/2), floor((y+1)/2)]
-      const int i0 = y >> 1, i1 = (y + 1) >> 1;     // y even: i0=i1=y/2 ; y odd: i0=(y-1)/2, i1=(y+1)/2
-      const int j0 = x >> 1, j1 = (x + 1) >> 1;
-      for (int i = i0; i <= i1; ++i) {
-        if (i >= gp.H) continue;
-        const int dy = y - (2 * i - 1);
-        for (int j = j0; j <= j1; ++j) {
-          if (j >= gp.W) continue;
-          const int dx = x - (2 * j - 1);
-          const long pidx = (((long)n * gp.H + i) * gp.W + j) * C + c;
-          if (arg[pidx] == dy * 3 + dx) s += to_f<T>(dP[geom_row(gp, 0, n, i, j) * C + c]);
-        }
+    float act[V], s[V];
+    vec_load<T>(c1 + (((long)n * Hi + y) * Hi + x) * C + c, act);
+#pragma unroll
+    for (int e = 0; e < V; ++e) s[e] = 0.f;
+    // windows i with 2i-1 <= y <= 2i+1  <=>  i in [y>>1, (y+1)>>1]
+    const int i0 = y >> 1, i1 = (y + 1) >> 1, j0 = x >> 1, j1 = (x + 1) >> 1;
+    for (int i = i0; i <= i1; ++i) {
+      if (i >= gp.H) continue;
+      const int dy = y - (2 * i - 1);
+      for (int j = j0; j <= j1; ++j) {
+        if (j >= gp.W) continue;
+        const int code = dy * 3 + (x - (2 * j - 1));
+        const uint8_t* a = arg + (((long)n * gp.H + i) * gp.W + j) * C + c;
+        uint32_t codes[2];
+        if (V == 8) { const uint2 pk = *reinterpret_cast<const uint2*>(a); codes[0] = pk.x; codes[1] = pk.y; }
+        else { codes[0] = *reinterpret_cast<const uint32_t*>(a); codes[1] = 0; }
+        float g[V];
+        vec_load<T>(dP + geom_row(gp, 0, n, i, j) * C + c, g);
+#pragma unroll
+        for (int e = 0; e < V; ++e)
+          if (((codes[e >> 2] >> (8 * (e & 3))) & 0xFF) == (uint32_t)code) s[e] += g[e];
       }
     }
-    dC1[geom_row(gd, 0, n, y, x) * C + c] = from_f<T>(s);
+#pragma unroll
+    for (int e = 0; e < V; ++e) s[e] = act[e] > 0.f ? s[e] : 0.f;
+    vec_store<T>(dC1 + geom_row(gd, 0, n, y, x) * C + c, s);
   }
 }
 
@@ -694,7 +747,7 @@ int rgie_regressor_forward_ex(RgieRegressor* R, const float* img, int B, int Hr,
   R->B = B; R->reps = reps; R->Hr = Hr; R->Wr = Wr; R->normalize = normalize;
   const int N = R->N, H0 = R->H0, H1 = R->Hs[1];
   const long tot_pack = (long)N * H0 * H0 * 4;
-  const long tot_pool = (long)N * H1 * H1 * 64;
+  const long tot_pool = (long)N * H1 * H1 * (64 / (16 / R->esz));
   if (R->dtype == 0) {
     pack_crops_kernel<float><<<grid_for(tot_pack), 256, 0, st>>>(img, offsets, step_ptr, off_step_stride, (float*)R->zz,
                                                                R->gZZ, reps, Hr, Wr, normalize, tot_pack);
@@ -742,7 +795,7 @@ int rgie_regressor_backward(RgieRegressor* R, const float* dlogits, float* dimg,
     if (int rc = run_op(R, R->bwd_ops[i], st, R->fwd_ops.size() + i)) return rc;
   // d(pool out) is the destination of the last block op (layer1.0 c1 dgrad)
   const void* dP = R->bwd_ops[nb - 2].d.D;
-  const long tot = (long)N * H0 * H0 * 64;
+  const long tot = (long)N * H0 * H0 * (64 / (16 / R->esz));
   if (R->dtype == 0)
     maxpool_bwd_kernel<float><<<grid_for(tot), 256, 0, st>>>((const float*)dP, R->arg, (const float*)R->c1, (float*)R->dC1, R->gS[1], R->gDY, H0, 64, tot);
   else

@@ -80,6 +80,7 @@ class ParametricEditEngine:
         self.rs_tmp = torch.empty(B * 3 * height * self.Wr, **f32)
         self.ws = torch.empty(self.lib.rgie_filter_ws_floats(B, height, width), **f32)
         self.loss_log = torch.zeros(num_steps, B, **f32); self.pred_log = torch.zeros(num_steps, B, self.nc, **f32)
+        self.x_log = torch.zeros(num_steps, B, NP, **f32)        # x BEFORE each step (what the objective was evaluated at)
         self.sched = torch.zeros(num_steps, 2, **f32)
         self.counter = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.offsets = torch.zeros(num_steps, B, reps, 2, dtype=torch.int32, device=self.dev)
@@ -114,6 +115,7 @@ class ParametricEditEngine:
         B, mb, reps, nc = self.B, self.mb, self.reps, self.nc
         n_launch = 0
         check(lib.rgie_params_default_fwd(ptr(self.x), ptr(self.p), B, float(self.H), st), "params_fwd")
+        check(lib.rgie_record(ptr(self.x), ptr(self.x_log), ptr(self.counter), B * self.NP, st), "record")
         self._filters_fwd(self.p)
         src = self._regressor_fwd(self.stage[-1], self.offsets, self.counter, 0)
         dsrc = self.gA if self.resize.identity else self.dresized
@@ -232,7 +234,7 @@ class ParametricEditEngine:
         check(lib.rgie_params_default_fwd(ptr(self.best_x), ptr(pbest), self.B, float(self.H), st), "params_fwd")
         self._filters_fwd(pbest)
         return dict(best_x=self.best_x.clone(), x_last=self.x.clone(), losses=self.loss_log.clone(),
-                    preds=self.pred_log.clone(), target=self.target.clone(), pred0=self.pred0.clone(),
+                    preds=self.pred_log.clone(), xs=self.x_log.clone(), target=self.target.clone(), pred0=self.pred0.clone(),
                     best_loss=self.best_loss.clone(), best_step=self.best_step.clone(),
                     edited=self.stage[-1].clone())
 

@@ -1,0 +1,105 @@
+"""GPU: MiDU guidance head (forward + d/d(feature)) and the regressor-guidance step against the oracle and the
+reference-generated golden (tests/golden/midu.pt), plus the six guidance lines of the SD pipeline
+(pipelines/InversionResamplingStableDiffusionPipeline.py:126-142) run through a seeded test-double UNet."""
+import os
+import types
+
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+class _FakeScheduler:
+    def scale_model_input(self, latents, t):
+        return latents
+
+
+class _FakeUNet(nn.Module):
+    """Seeded stand-in for the diffusers UNet: latents [B,4,64,64] -> mid_block feature [B,1280,8,8]."""
+
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(11)
+        self.down = nn.Sequential(nn.Conv2d(4, 32, 3, stride=2, padding=1), nn.SiLU(),
+                                  nn.Conv2d(32, 64, 3, stride=2, padding=1), nn.SiLU(),
+                                  nn.Conv2d(64, 128, 3, stride=2, padding=1), nn.SiLU())
+        self.mid_block = nn.Conv2d(128, 1280, 1)
+
+    def forward(self, latents, t, encoder_hidden_states=None, **kw):
+        return self.mid_block(self.down(latents))
+
+
+def _pipe(device):
+    unet = _FakeUNet().to(device)
+    return types.SimpleNamespace(unet=unet, scheduler=_FakeScheduler())
+
+
+def test_head_matches_reference_golden(golden_dir):
+    from regressor_guided_image_editing_b200.guidance_classifier.ValenceArousalMidu import ValenceArousalMidu
+    from regressor_guided_image_editing_b200.guidance_classifier.guidance_scores import valence_arousal_score
+    g = torch.load(os.path.join(golden_dir, "midu.pt"))["sd"]
+    clf = ValenceArousalMidu(_pipe(DEV), DEV, precision="fp32")
+    clf.model.load_state_dict(O.make_midu_head_state_dict(g["seed"]))
+    feat = torch.randn(2, 1280, g["hw"], g["hw"], generator=torch.Generator().manual_seed(g["feat_seed"]))
+    f = feat.to(DEV).requires_grad_(True)
+    pred = clf.head(f)
+    loss = valence_arousal_score(pred, DEV, True, None)
+    gf, = torch.autograd.grad(loss, f)
+    assert (pred.detach().cpu() - g["pred"]).abs().max().item() <= 2e-5
+    assert abs(loss.item() - g["loss"].item()) <= 1e-5
+    gs = gf.cpu()[:, ::64, ::2, ::2]
+    assert (gs - g["grad_slice"]).abs().max().item() <= 1e-3 * g["grad_slice"].abs().max().item() + 1e-7
+    assert abs(gf.abs().sum().item() - g["grad_abs_sum"].item()) <= 2e-3 * g["grad_abs_sum"].item()
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 2e-2)])
+def test_head_vs_oracle(precision, tol):
+    from regressor_guided_image_editing_b200.guidance_classifier.ValenceArousalMidu import ValenceArousalMidu
+    sd = O.make_midu_head_state_dict(3)
+    B = 32
+    feat = torch.randn(B, 1280, 8, 8, generator=torch.Generator().manual_seed(5))
+    fc = feat.clone().requires_grad_(True)
+    pc = O.midu_head_forward(fc, sd)
+    lc = O.valence_arousal_score(pc, True, None)
+    gc, = torch.autograd.grad(lc, fc)
+    clf = ValenceArousalMidu(_pipe(DEV), DEV, precision=precision)
+    clf.model.load_state_dict(sd)
+    f = feat.to(DEV).requires_grad_(True)
+    pn = clf.head(f)
+    ln = clf._calculate_score(f, clf.head, DEV, True, None)
+    gn, = torch.autograd.grad(ln, f)
+    scale = pc.abs().max().item()
+    assert (pn.detach().cpu() - pc.detach()).abs().max().item() <= tol * max(scale, 1.0)
+    cos = torch.nn.functional.cosine_similarity(gn.cpu().flatten(), gc.flatten(), dim=0).item()
+    assert cos >= (0.9999 if precision == "fp32" else 0.99), cos
+    assert abs(gn.norm().item() / gc.norm().item() - 1) <= (1e-3 if precision == "fp32" else 3e-2)
+
+
+def test_guidance_step_through_test_double_unet():
+    """The guidance lines :126-142 with the native head + native normalised update vs the same lines in torch on CPU."""
+    from regressor_guided_image_editing_b200 import ops
+    from regressor_guided_image_editing_b200.guidance_classifier.ValenceArousalMidu import ValenceArousalMidu
+    sd = O.make_midu_head_state_dict(0)
+    lat0 = torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(3000))
+    # CPU restatement
+    pipe_c = _pipe("cpu")
+    lc = lat0.clone().requires_grad_(True)
+    feat = pipe_c.unet(lc, 0)
+    loss_c = O.valence_arousal_score(O.midu_head_forward(feat.float(), sd), True, None)
+    g_c, = torch.autograd.grad(loss_c, lc)
+    new_c = O.guidance_update(lc, g_c, 0.2, True)
+    # native
+    pipe_g = _pipe(DEV)
+    clf = ValenceArousalMidu(pipe_g, DEV, precision="fp32")
+    clf.model.load_state_dict(sd)
+    lg = lat0.to(DEV).clone().detach().requires_grad_()
+    loss_g = clf(lg, 0, None)
+    g_g = torch.autograd.grad(loss_g, lg)[0]
+    new_g = ops.guidance_update(lg.detach().clone(), g_g.contiguous(), 0.2, True)
+    assert abs(loss_g.item() - loss_c.item()) <= 1e-4 * max(abs(loss_c.item()), 1.0)
+    assert (new_g.cpu() - new_c).abs().max().item() <= 1e-4
