@@ -49,6 +49,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+// L2 prefetch of one tensor-map box (no smem destination, no barrier): used for the epilogue's residual / mask tiles
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"((uint64_t)map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -131,6 +135,7 @@ struct SmemLayout {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmK,
                   const GemmDesc d, const int num_m_tiles, const int num_n_tiles) {
   using L = SmemLayout<BN, STAGES>;
   constexpr int CH = BN >= 32 ? 32 : 16;            // epilogue column chunk
@@ -186,6 +191,15 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile / num_n_tiles, nt = tile - mt * num_n_tiles;
         const long m0 = d.m_begin + (long)mt * BM;
+        // the epilogue of this tile will read res/mask rows [m0, m0+128) x [nt*BN, +BN): pull them into L2 now
+        if (d.res != nullptr && m0 < d.res_rows) {
+#pragma unroll
+          for (int j = 0; j < (BN + 63) / 64; ++j) tma_prefetch_2d(&tmR, nt * BN + j * 64, (int)m0);
+        }
+        if (d.mask != nullptr) {
+#pragma unroll
+          for (int j = 0; j < (BN + 63) / 64; ++j) tma_prefetch_2d(&tmK, nt * BN + j * 64, (int)m0);
+        }
         int tap = 0, cb = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
@@ -388,8 +402,8 @@ int run_impl(const GemmPlanSm100& p, cudaStream_t st) {
                                       L::DYN_BYTES));
     attr_set = true;
   }
-  gemm_sm100_kernel<BN, STAGES><<<p.grid, NUM_THREADS, L::DYN_BYTES, st>>>(p.tmA, p.tmB, p.d, p.num_m_tiles,
-                                                                           p.num_n_tiles);
+  gemm_sm100_kernel<BN, STAGES><<<p.grid, NUM_THREADS, L::DYN_BYTES, st>>>(p.tmA, p.tmB, p.tmR, p.tmK, p.d,
+                                                                           p.num_m_tiles, p.num_n_tiles);
   RGIE_LAUNCH_OK();
   return 0;
 }
@@ -426,7 +440,16 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
   if (p->grid < 1) p->grid = 1;
   int rc = make_map_2d(&p->tmA, d.A, (uint64_t)d.Cin, (uint64_t)d.a_rows, BK, BM);
   if (rc) return rc;
-  return make_map_2d(&p->tmB, d.Wt, (uint64_t)d.ntaps * d.Cin, (uint64_t)d.n_pad, BK, (uint32_t)bn);
+  rc = make_map_2d(&p->tmB, d.Wt, (uint64_t)d.ntaps * d.Cin, (uint64_t)d.n_pad, BK, (uint32_t)bn);
+  if (rc) return rc;
+  // prefetch-only maps of the epilogue operands (valid placeholders when absent: never dereferenced by the kernel)
+  const uint32_t pf_cols = d.Cout >= 64 ? 64u : (uint32_t)d.Cout;
+  if (d.res != nullptr) rc = make_map_2d(&p->tmR, d.res, (uint64_t)d.ld_res, (uint64_t)(d.res_rows > 0 ? d.res_rows : 1), pf_cols, BM);
+  else p->tmR = p->tmA;
+  if (rc) return rc;
+  if (d.mask != nullptr) rc = make_map_2d(&p->tmK, d.mask, (uint64_t)d.ld_mask, (uint64_t)d.m_end, pf_cols, BM);
+  else p->tmK = p->tmA;
+  return rc;
 }
 
 int run_gemm_sm100(const GemmPlanSm100& p, cudaStream_t st) {

@@ -59,6 +59,16 @@ def _check_against_golden(out, gold, tol_loss, tol_pred, tol_x, tag):
     print(f"{tag} per-step |dloss|:", [f"{v:.1e}" for v in dl.tolist()])
     print(f"{tag} per-step |dpred|:", [f"{v:.1e}" for v in dp.tolist()])
     print(f"{tag} per-step |dx|   :", [f"{v:.1e}" for v in dx.tolist()])
+    dlast = (out["xs"][-1, 0] - gold["xs"][-1]).abs()
+    top = torch.topk(dlast, 6)
+    print(f"{tag} largest parameter drifts at the last step (index: |d|, mine, golden):",
+          [(int(i), round(float(v), 4), round(float(out["xs"][-1, 0, i]), 4), round(float(gold["xs"][-1, i]), 4))
+           for v, i in zip(top.values, top.indices)])
+    # image-space effect of the parameter drift: edit with my last x and with the golden's last x (same native filters)
+    ed_a = _edit_with(None, out["xs"][-1, 0], gold["h"], gold["w"], gold["image_index"])
+    ed_b = _edit_with(None, gold["xs"][-1], gold["h"], gold["w"], gold["image_index"])
+    print(f"{tag} edited(x_mine[-1]) vs edited(x_golden[-1]): max-abs {(ed_a - ed_b).abs().max().item():.3e} "
+          f"mean-abs {(ed_a - ed_b).abs().mean().item():.3e}")
     assert dl.max().item() <= tol_loss, f"{tag}: per-step loss drifted ({dl.max().item():.3e})"
     assert dp.max().item() <= tol_pred, f"{tag}: per-step prediction drifted ({dp.max().item():.3e})"
     assert dx.max().item() <= tol_x, f"{tag}: parameter trajectory drifted ({dx.max().item():.3e})"
