@@ -5,7 +5,8 @@
 // One persistent CTA per SM, 320 threads:
 //   warp 0      : TMA producer   (cp.async.bulk.tensor.2d, 128B swizzle, zero fill for out-of-range rows = conv padding)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (cta_group::1, M=128, N=BN, K=16 per instruction)
-//   warps 2..9  : epilogue       (tcgen05.ld 32x32b -> bias / residual / ReLU / ReLU-mask -> row-remapped 16B stores;
+//   warps 2..9  : epilogue       (tcgen05.ld 32x32b -> warp-private swizzled smem transpose -> bias / residual / ReLU /
+//                                 ReLU-mask in a row-coalesced distribution -> row-remapped, fully coalesced stores;
 //                                 residual/mask operands prefetched one chunk ahead)
 // Pipelines: STAGES-deep smem ring (full/empty mbarriers) between TMA and MMA; 2 TMEM accumulator buffers
 // (tmem_full/tmem_empty) between MMA and epilogue so the epilogue of tile i overlaps the MMAs of tile i+1.
@@ -48,10 +49,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(bar) : "memory");
-}
-// L2 prefetch of one tensor-map box (no smem destination, no barrier): used for the epilogue's residual / mask tiles
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"((uint64_t)map), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -127,15 +124,14 @@ struct SmemLayout {
   static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
   static constexpr int BAR_OFF = B_OFF + STAGES * B_STAGE_BYTES;   // full[S], empty[S], tfull[2], tempty[2]
   static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * STAGES + 4) * 8;
-  static constexpr int BIAS_OFF = TMEM_PTR_OFF + 16;                // whole bias vector (<= MAX_BIAS floats)
-  static constexpr int TOTAL = BIAS_OFF + MAX_BIAS * 4;
+  static constexpr int STAGE_OFF = (TMEM_PTR_OFF + 16 + 127) / 128 * 128;   // 8 warps x [32 rows x CH fp32] staging
+  static constexpr int TOTAL = STAGE_OFF + 8 * 32 * (BN >= 32 ? 32 : 16) * 4;
   static constexpr int DYN_BYTES = TOTAL + 1024;   // + slack for manual 1024 B alignment
 };
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmK,
                   const GemmDesc d, const int num_m_tiles, const int num_n_tiles) {
   using L = SmemLayout<BN, STAGES>;
   constexpr int CH = BN >= 32 ? 32 : 16;            // epilogue column chunk
@@ -174,10 +170,6 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                  "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (d.bias != nullptr) {
-    float* sb = reinterpret_cast<float*>(smem + L::BIAS_OFF);
-    for (int i = threadIdx.x; i < d.Cout; i += NUM_THREADS) sb[i] = d.bias[i];
-  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -191,15 +183,6 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile / num_n_tiles, nt = tile - mt * num_n_tiles;
         const long m0 = d.m_begin + (long)mt * BM;
-        // the epilogue of this tile will read res/mask rows [m0, m0+128) x [nt*BN, +BN): pull them into L2 now
-        if (d.res != nullptr && m0 < d.res_rows) {
-#pragma unroll
-          for (int j = 0; j < (BN + 63) / 64; ++j) tma_prefetch_2d(&tmR, nt * BN + j * 64, (int)m0);
-        }
-        if (d.mask != nullptr) {
-#pragma unroll
-          for (int j = 0; j < (BN + 63) / 64; ++j) tma_prefetch_2d(&tmK, nt * BN + j * 64, (int)m0);
-        }
         int tap = 0, cb = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
@@ -242,40 +225,49 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue (8 warps; one TMEM lane = one output row per thread) =====================
-    // warps 2..9: lane quarter q = warp & 3 (hardware restriction on tcgen05.ld), column half = (warp - 2) >> 2.
-    // The residual / ReLU-mask operands of a chunk are fetched one chunk ahead (and, for the first chunk of a tile,
-    // before waiting for the accumulator) so their HBM latency overlaps the TMEM read + math of the previous chunk.
+    // ===================== epilogue (8 warps) =====================
+    // warps 2..9: TMEM lane quarter q = warp & 3 (hardware restriction on tcgen05.ld), column half = (warp - 2) >> 2.
+    // tcgen05.ld hands every thread one accumulator ROW; storing it that way makes each warp-wide 16 B store hit 32
+    // different rows (32 half-filled sectors per request).  So every 32-column chunk is transposed through a
+    // warp-private, XOR-swizzled fp32 staging tile in shared memory, after which LPR = 4 lanes own one row and each
+    // lane owns 8 consecutive columns: residual / mask loads and output stores then move 8 rows x 64 contiguous bytes
+    // per warp instruction (full sectors), and the bias / residual / ReLU / mask math is done in that distribution.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int row = q * 32 + lane;
     constexpr int NCH = BN / CH;                     // chunks per tile
     constexpr int CPW = NCH >= 2 ? NCH / 2 : 1;      // chunks per warp
+    constexpr int LPR = CH / 8;                      // lanes per row in the coalesced distribution (4 or 2)
+    constexpr int RPP = 32 / LPR;                    // rows per pass (8 or 16)
+    constexpr int NQ = CH / 4;                       // 16-byte fp32 quads per staged row (8 or 4)
     const int c_begin = NCH >= 2 ? half * CPW : 0;
     const bool active = NCH >= 2 || half == 0;
     const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(d.res);
     const __nv_bfloat16* mask = reinterpret_cast<const __nv_bfloat16*>(d.mask);
-    const float* sbias = reinterpret_cast<const float*>(smem + L::BIAS_OFF);
-    const bool has_bias = d.bias != nullptr;
+    float4* stage4 = reinterpret_cast<float4*>(smem + L::STAGE_OFF + (warp - 2) * (32 * CH * 4));
+    const int lr = lane / LPR;                       // row within a pass
+    const int lc = lane % LPR;                       // 8-column group within the chunk
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int mt = tile / num_n_tiles, nt = tile - mt * num_n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const long m = d.m_begin + (long)mt * BM + row;
-      long dest = -1;
-      if (m < d.m_end) dest = map_row(d.src, d.dst_kind, d.dst, m);
-      const bool live = active && dest >= 0;
-      const bool use_res = live && res != nullptr && m < d.res_rows;
-      const bool use_mask = live && mask != nullptr;
-      const uint4* res_p = reinterpret_cast<const uint4*>(res + m * d.ld_res + nt * BN);
-      const uint4* mask_p = reinterpret_cast<const uint4*>(mask + m * d.ld_mask + nt * BN);
-      uint4 rcur[CH / 8], kcur[CH / 8], rnxt[CH / 8], knxt[CH / 8];
-      auto fetch = [&](int c, uint4* rr, uint4* kk) {
+      const long m_base = d.m_begin + (long)mt * BM + q * 32;
+      // rows this lane owns in the coalesced distribution: R_k = lr + k*RPP
+      long mrow[LPR], dest[LPR];
 #pragma unroll
-        for (int j = 0; j < CH / 8; ++j) {
-          if (use_res) rr[j] = __ldg(res_p + c * (CH / 8) + j);
-          if (use_mask) kk[j] = __ldg(mask_p + c * (CH / 8) + j);
+      for (int k = 0; k < LPR; ++k) {
+        mrow[k] = m_base + lr + k * RPP;
+        dest[k] = (active && mrow[k] < d.m_end) ? map_row(d.src, d.dst_kind, d.dst, mrow[k]) : -1;
+      }
+      uint4 rcur[LPR], kcur[LPR], rnxt[LPR], knxt[LPR];
+      auto fetch = [&](int c, uint4* rr, uint4* kk) {
+        const int n = nt * BN + c * CH + lc * 8;
+#pragma unroll
+        for (int k = 0; k < LPR; ++k) {
+          if (dest[k] >= 0) {
+            if (res != nullptr && mrow[k] < d.res_rows) rr[k] = __ldg(reinterpret_cast<const uint4*>(res + mrow[k] * d.ld_res + n));
+            if (mask != nullptr) kk[k] = __ldg(reinterpret_cast<const uint4*>(mask + mrow[k] * d.ld_mask + n));
+          }
         }
       };
       fetch(c_begin, rcur, kcur);
@@ -290,61 +282,64 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           uint32_t r[CH];
           tmem_ld<CH>(taddr + (uint32_t)(c * CH), r);
           tmem_ld_wait();
-          const int n0 = nt * BN + c * CH;
-          if (live) {
-            float v[CH];
+          // stage: thread = row `lane`, quad j at swizzled position j ^ (lane & (NQ-1))
 #pragma unroll
-            for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
-            if (has_bias) {
-              const float4* b4 = reinterpret_cast<const float4*>(sbias + n0);
+          for (int j = 0; j < NQ; ++j)
+            stage4[lane * NQ + (j ^ (lane & (NQ - 1)))] =
+                make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                            __uint_as_float(r[4 * j + 3]));
+          __syncwarp();
+          const int n0 = nt * BN + c * CH + lc * 8;
+          float bias8[8];
+          if (d.bias != nullptr) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(d.bias + n0));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(d.bias + n0 + 4));
+            bias8[0] = b0.x; bias8[1] = b0.y; bias8[2] = b0.z; bias8[3] = b0.w;
+            bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
+          } else {
 #pragma unroll
-              for (int j = 0; j < CH / 4; ++j) {
-                const float4 b = b4[j];
-                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-              }
-            }
-            if (use_res) {
+            for (int e = 0; e < 8; ++e) bias8[e] = 0.f;
+          }
 #pragma unroll
-              for (int j = 0; j < CH / 8; ++j) {
-                const uint4 u = rcur[j];
-                v[8 * j + 0] += bf16_lo(u.x); v[8 * j + 1] += bf16_hi(u.x);
-                v[8 * j + 2] += bf16_lo(u.y); v[8 * j + 3] += bf16_hi(u.y);
-                v[8 * j + 4] += bf16_lo(u.z); v[8 * j + 5] += bf16_hi(u.z);
-                v[8 * j + 6] += bf16_lo(u.w); v[8 * j + 7] += bf16_hi(u.w);
-              }
+          for (int k = 0; k < LPR; ++k) {
+            const int R = lr + k * RPP;
+            const float4 a0 = stage4[R * NQ + ((2 * lc) ^ (R & (NQ - 1)))];
+            const float4 a1 = stage4[R * NQ + ((2 * lc + 1) ^ (R & (NQ - 1)))];
+            if (dest[k] < 0) continue;
+            float v[8] = {a0.x + bias8[0], a0.y + bias8[1], a0.z + bias8[2], a0.w + bias8[3],
+                          a1.x + bias8[4], a1.y + bias8[5], a1.z + bias8[6], a1.w + bias8[7]};
+            if (res != nullptr && mrow[k] < d.res_rows) {
+              const uint4 u = rcur[k];
+              v[0] += bf16_lo(u.x); v[1] += bf16_hi(u.x); v[2] += bf16_lo(u.y); v[3] += bf16_hi(u.y);
+              v[4] += bf16_lo(u.z); v[5] += bf16_hi(u.z); v[6] += bf16_lo(u.w); v[7] += bf16_hi(u.w);
             }
             if (d.relu) {
 #pragma unroll
-              for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
+              for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
             }
-            if (use_mask) {
+            if (mask != nullptr) {
+              const uint4 u = kcur[k];
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};     // bf16 > 0  <=>  sign clear and magnitude non-zero
 #pragma unroll
-              for (int j = 0; j < CH / 8; ++j) {
-                const uint4 u = kcur[j];
-                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const uint32_t lo = w[e] & 0xFFFFu, hi = w[e] >> 16;
-                  if (!(lo != 0 && lo < 0x8000u)) v[8 * j + 2 * e] = 0.f;
-                  if (!(hi != 0 && hi < 0x8000u)) v[8 * j + 2 * e + 1] = 0.f;
-                }
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t lo = w[e] & 0xFFFFu, hi = w[e] >> 16;
+                if (!(lo != 0 && lo < 0x8000u)) v[2 * e] = 0.f;
+                if (!(hi != 0 && hi < 0x8000u)) v[2 * e + 1] = 0.f;
               }
             }
             if (d.d_fp32) {
-              float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(d.D) + dest * d.ldd + n0);
-#pragma unroll
-              for (int j = 0; j < CH / 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(d.D) + dest[k] * d.ldd + n0);
+              o[0] = make_float4(v[0], v[1], v[2], v[3]);
+              o[1] = make_float4(v[4], v[5], v[6], v[7]);
             } else {
-              uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.D) + dest * d.ldd + n0);
-#pragma unroll
-              for (int j = 0; j < CH / 8; ++j)
-                o[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                  pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.D) + dest[k] * d.ldd + n0) =
+                  make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                             pack_bf16x2(v[6], v[7]));
             }
           }
+          __syncwarp();
 #pragma unroll
-          for (int j = 0; j < CH / 8; ++j) { rcur[j] = rnxt[j]; kcur[j] = knxt[j]; }
+          for (int k = 0; k < LPR; ++k) { rcur[k] = rnxt[k]; kcur[k] = knxt[k]; }
         }
       }
       tcgen05_fence_before();
@@ -402,8 +397,8 @@ int run_impl(const GemmPlanSm100& p, cudaStream_t st) {
                                       L::DYN_BYTES));
     attr_set = true;
   }
-  gemm_sm100_kernel<BN, STAGES><<<p.grid, NUM_THREADS, L::DYN_BYTES, st>>>(p.tmA, p.tmB, p.tmR, p.tmK, p.d,
-                                                                           p.num_m_tiles, p.num_n_tiles);
+  gemm_sm100_kernel<BN, STAGES><<<p.grid, NUM_THREADS, L::DYN_BYTES, st>>>(p.tmA, p.tmB, p.d, p.num_m_tiles,
+                                                                           p.num_n_tiles);
   RGIE_LAUNCH_OK();
   return 0;
 }
@@ -440,16 +435,7 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
   if (p->grid < 1) p->grid = 1;
   int rc = make_map_2d(&p->tmA, d.A, (uint64_t)d.Cin, (uint64_t)d.a_rows, BK, BM);
   if (rc) return rc;
-  rc = make_map_2d(&p->tmB, d.Wt, (uint64_t)d.ntaps * d.Cin, (uint64_t)d.n_pad, BK, (uint32_t)bn);
-  if (rc) return rc;
-  // prefetch-only maps of the epilogue operands (valid placeholders when absent: never dereferenced by the kernel)
-  const uint32_t pf_cols = d.Cout >= 64 ? 64u : (uint32_t)d.Cout;
-  if (d.res != nullptr) rc = make_map_2d(&p->tmR, d.res, (uint64_t)d.ld_res, (uint64_t)(d.res_rows > 0 ? d.res_rows : 1), pf_cols, BM);
-  else p->tmR = p->tmA;
-  if (rc) return rc;
-  if (d.mask != nullptr) rc = make_map_2d(&p->tmK, d.mask, (uint64_t)d.ld_mask, (uint64_t)d.m_end, pf_cols, BM);
-  else p->tmK = p->tmA;
-  return rc;
+  return make_map_2d(&p->tmB, d.Wt, (uint64_t)d.ntaps * d.Cin, (uint64_t)d.n_pad, BK, (uint32_t)bn);
 }
 
 int run_gemm_sm100(const GemmPlanSm100& p, cudaStream_t st) {

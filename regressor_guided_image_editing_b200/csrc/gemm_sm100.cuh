@@ -6,7 +6,7 @@ namespace rgie {
 
 struct GemmPlanSm100 {
   GemmDesc d;
-  CUtensorMap tmA, tmB, tmR, tmK;   // operands + prefetch-only maps of the epilogue's residual / mask
+  CUtensorMap tmA, tmB;
   int bn;
   int num_m_tiles, num_n_tiles;
   int grid;
