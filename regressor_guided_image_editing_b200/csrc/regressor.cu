@@ -177,24 +177,51 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ 
   }
 }
 
-// global average pool over the valid window of layout g + fully connected layer
+// global average pool over the valid window of layout g: grid (N, C / (32*V)), 256 threads = 32 channel vectors x 8 pixel
+// groups; 16-byte channel vectors, coalesced over channels
 template <typename T>
-__global__ void __launch_bounds__(256) avgpool_fc_kernel(const T* __restrict__ x, Geom g, int C, const float* __restrict__ wfc,
-                                                        const float* __restrict__ bfc, int K, float* __restrict__ feat,
-                                                        float* __restrict__ logits) {
+__global__ void __launch_bounds__(256) avgpool_kernel(const T* __restrict__ x, Geom g, int C, float* __restrict__ feat) {
+  constexpr int V = Vec16<T>::N;
+  __shared__ float red[8][32 * V];
+  const int n = blockIdx.x;
+  const int cv = threadIdx.x & 31, pg = threadIdx.x >> 5;
+  const int c = (blockIdx.y * 32 + cv) * V;
+  float s[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) s[e] = 0.f;
+  const int npx = g.H * g.W;
+  for (int p = pg; p < npx; p += 8) {
+    const int i = p / g.W, j = p - i * g.W;
+    float v[V];
+    vec_load<T>(x + geom_row(g, 0, n, i, j) * C + c, v);
+#pragma unroll
+    for (int e = 0; e < V; ++e) s[e] += v[e];
+  }
+#pragma unroll
+  for (int e = 0; e < V; ++e) red[pg][cv * V + e] = s[e];
+  __syncthreads();
+  if (pg == 0) {
+    const float inv = 1.0f / (float)npx;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      float t = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t += red[q][cv * V + e];
+      feat[(long)n * C + c + e] = t * inv;
+    }
+  }
+}
+// logits[n,k] = b[k] + sum_c feat[n,c] * w[k,c]
+__global__ void __launch_bounds__(256) fc_kernel(const float* __restrict__ feat, int C, const float* __restrict__ wfc,
+                                                const float* __restrict__ bfc, int K, float* __restrict__ logits) {
   __shared__ float red[8][8];
   const int n = blockIdx.x;
   float part[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) part[k] = 0.f;
-  const float inv = 1.0f / (float)(g.H * g.W);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int i = 0; i < g.H; ++i)
-      for (int j = 0; j < g.W; ++j) s += to_f<T>(x[geom_row(g, 0, n, i, j) * C + c]);
-    s *= inv;
-    feat[(long)n * C + c] = s;
-    for (int k = 0; k < K; ++k) part[k] = fmaf(s, wfc[(long)k * C + c], part[k]);
+    const float f = feat[(long)n * C + c];
+    for (int k = 0; k < K; ++k) part[k] = fmaf(f, wfc[(long)k * C + c], part[k]);
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int k = 0; k < K; ++k) {
@@ -204,26 +231,39 @@ __global__ void __launch_bounds__(256) avgpool_fc_kernel(const T* __restrict__ x
   }
   __syncthreads();
   if (threadIdx.x < K) {
-    float s = bfc[threadIdx.x];
-    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-    logits[(long)n * K + threadIdx.x] = s;
+    float t = bfc[threadIdx.x];
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    logits[(long)n * K + threadIdx.x] = t;
   }
 }
-// d(layer4 out)[n,i,j,c] = (out > 0) * (sum_k dlogits[n,k] * wfc[k,c]) / (H*W)
-template <typename T>
-__global__ void __launch_bounds__(256) avgpool_fc_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ wfc,
-                                                            int K, const T* __restrict__ x, T* __restrict__ dx, Geom g, int C) {
+// dfeat[n,c] = (sum_k dlogits[n,k] * w[k,c]) / (H*W)
+__global__ void __launch_bounds__(256) fc_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ wfc, int K,
+                                                    int C, float inv, float* __restrict__ dfeat) {
   const int n = blockIdx.x;
-  const float inv = 1.0f / (float)(g.H * g.W);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float d = 0.f;
     for (int k = 0; k < K; ++k) d = fmaf(dlogits[(long)n * K + k], wfc[(long)k * C + c], d);
-    d *= inv;
-    for (int i = 0; i < g.H; ++i)
-      for (int j = 0; j < g.W; ++j) {
-        const long r = geom_row(g, 0, n, i, j) * C + c;
-        dx[r] = from_f<T>(to_f<T>(x[r]) > 0.f ? d : 0.f);
-      }
+    dfeat[(long)n * C + c] = d * inv;
+  }
+}
+// d(layer4 out)[n,i,j,c] = (out > 0) ? dfeat[n,c] : 0    (one thread = one pixel x 16 bytes of channels)
+template <typename T>
+__global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restrict__ dfeat, const T* __restrict__ x,
+                                                         T* __restrict__ dx, Geom g, int C, long total) {
+  constexpr int V = Vec16<T>::N;
+  const int cvn = C / V;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cvn) * V;
+    long q = idx / cvn;
+    const int j = (int)(q % g.W); q /= g.W;
+    const int i = (int)(q % g.H);
+    const int n = (int)(q / g.H);
+    const long r = geom_row(g, 0, n, i, j) * C + c;
+    float v[V], o[V];
+    vec_load<T>(x + r, v);
+#pragma unroll
+    for (int e = 0; e < V; ++e) o[e] = v[e] > 0.f ? dfeat[(long)n * C + c + e] : 0.f;
+    vec_store<T>(dx + r, o);
   }
 }
 
@@ -321,7 +361,7 @@ struct RgieRegressor {
   // stem
   void *wc1 = nullptr, *wc1t = nullptr; float* bc1 = nullptr;
   void *zz = nullptr, *c1 = nullptr, *p1 = nullptr; uint8_t* arg = nullptr;
-  float *wfc = nullptr, *bfc = nullptr, *feat = nullptr;
+  float *wfc = nullptr, *bfc = nullptr, *feat = nullptr, *dfeat = nullptr;
   // gradients
   void* dOut[5][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
   void *dH2[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *dH1[5] = {nullptr, nullptr, nullptr, nullptr, nullptr},
@@ -500,6 +540,7 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
   if (int rc = dev_alloc(R, &R->p1, (size_t)R->gS[1].rows() * 64 * esz, true)) return rc;
   if (int rc = dev_alloc(R, (void**)&R->arg, (size_t)N * R->Hs[1] * R->Hs[1] * 64, true)) return rc;
   if (int rc = dev_alloc(R, (void**)&R->feat, (size_t)N * 2048 * 4, true)) return rc;
+  if (int rc = dev_alloc(R, (void**)&R->dfeat, (size_t)N * 2048 * 4, true)) return rc;
   if (int rc = dev_alloc(R, &R->dC1, (size_t)R->gDY.rows() * 64 * esz, true)) return rc;
   if (int rc = dev_alloc(R, (void**)&R->dZ, (size_t)N * H0 * H0 * 16 * 4, true)) return rc;
 
@@ -767,9 +808,11 @@ int rgie_regressor_forward_ex(RgieRegressor* R, const float* img, int B, int Hr,
     if (int rc = run_op(R, R->fwd_ops[i], st, i)) return rc;
   const Block& last = R->blocks.back();
   if (R->dtype == 0)
-    avgpool_fc_kernel<float><<<N, 256, 0, st>>>((const float*)last.out, R->gS[4], 2048, R->wfc, R->bfc, R->K, R->feat, logits);
+    avgpool_kernel<float><<<dim3(N, 2048 / (32 * 4)), 256, 0, st>>>((const float*)last.out, R->gS[4], 2048, R->feat);
   else
-    avgpool_fc_kernel<__nv_bfloat16><<<N, 256, 0, st>>>((const __nv_bfloat16*)last.out, R->gS[4], 2048, R->wfc, R->bfc, R->K, R->feat, logits);
+    avgpool_kernel<__nv_bfloat16><<<dim3(N, 2048 / (32 * 8)), 256, 0, st>>>((const __nv_bfloat16*)last.out, R->gS[4], 2048, R->feat);
+  RGIE_LAUNCH_OK();
+  fc_kernel<<<N, 256, 0, st>>>(R->feat, 2048, R->wfc, R->bfc, R->K, logits);
   RGIE_LAUNCH_OK();
   return 0;
 }
@@ -785,11 +828,17 @@ int rgie_regressor_backward(RgieRegressor* R, const float* dlogits, float* dimg,
   RGIE_CHECK(R->offsets != nullptr, "rgie_regressor_backward: call rgie_regressor_forward first");
   const int N = R->N, H0 = R->H0;
   const Block& last = R->blocks.back();
-  if (R->dtype == 0)
-    avgpool_fc_bwd_kernel<float><<<N, 256, 0, st>>>(dlogits, R->wfc, R->K, (const float*)last.out, (float*)R->final_dout, R->gS[4], 2048);
-  else
-    avgpool_fc_bwd_kernel<__nv_bfloat16><<<N, 256, 0, st>>>(dlogits, R->wfc, R->K, (const __nv_bfloat16*)last.out, (__nv_bfloat16*)R->final_dout, R->gS[4], 2048);
+  const int H4 = R->Hs[4];
+  fc_bwd_kernel<<<N, 256, 0, st>>>(dlogits, R->wfc, R->K, 2048, 1.0f / (float)(H4 * H4), R->dfeat);
   RGIE_LAUNCH_OK();
+  {
+    const long tot4 = (long)N * H4 * H4 * (2048 / (16 / R->esz));
+    if (R->dtype == 0)
+      avgpool_bwd_kernel<float><<<grid_for(tot4), 256, 0, st>>>(R->dfeat, (const float*)last.out, (float*)R->final_dout, R->gS[4], 2048, tot4);
+    else
+      avgpool_bwd_kernel<__nv_bfloat16><<<grid_for(tot4), 256, 0, st>>>(R->dfeat, (const __nv_bfloat16*)last.out, (__nv_bfloat16*)R->final_dout, R->gS[4], 2048, tot4);
+    RGIE_LAUNCH_OK();
+  }
   const size_t nb = R->bwd_ops.size();
   for (size_t i = 0; i + 1 < nb; ++i)
     if (int rc = run_op(R, R->bwd_ops[i], st, R->fwd_ops.size() + i)) return rc;
