@@ -9,6 +9,7 @@
 //                                 residual/mask operands prefetched one chunk ahead)
 // Pipelines: STAGES-deep smem ring (full/empty mbarriers) between TMA and MMA; 2 TMEM accumulator buffers
 // (tmem_full/tmem_empty) between MMA and epilogue so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <stdlib.h>
 #include "common.cuh"
 #include "gemm_sm100.cuh"
 
@@ -127,47 +128,70 @@ __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u 
 
 __host__ __device__ constexpr int tmem_cols(int bn) { return 2 * bn <= 32 ? 32 : (2 * bn <= 64 ? 64 : (2 * bn <= 128 ? 128 : (2 * bn <= 256 ? 256 : 512))); }
 
-template <int BN, int STAGES>
+// Shared-memory plan: an A ring of SA "slabs" (136 rows x 128 B, so that up to kMaxGroupW consecutive row-shifted taps
+// can be served from ONE load through matrix descriptors whose start address is shifted by whole rows) and a B ring of SB
+// weight tiles.  Slab slots are padded to a multiple of 1024 B (swizzle-128B atom alignment).
+constexpr int SLAB_ROWS = BM + 8;
+constexpr int A_SLAB_BYTES = SLAB_ROWS * BK * 2;                    // 17408
+constexpr int A_SLOT_BYTES = (A_SLAB_BYTES + 1023) / 1024 * 1024;    // 18432
+constexpr int kMaxGroupW = 8;
+
+template <int BN, int SA, int SB>
 struct SmemLayout {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int A_OFF = 0;
-  static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
-  static constexpr int BAR_OFF = B_OFF + STAGES * B_STAGE_BYTES;   // full[S], empty[S], tfull[2], tempty[2]
-  static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * STAGES + 4) * 8;
+  static constexpr int B_OFF = SA * A_SLOT_BYTES;
+  static constexpr int BAR_OFF = B_OFF + SB * B_STAGE_BYTES;   // a_full[SA], a_empty[SA], b_full[SB], b_empty[SB], tfull[2], tempty[2]
+  static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * SA + 2 * SB + 4) * 8;
   static constexpr int BIAS_OFF = TMEM_PTR_OFF + 16;                // whole bias vector (<= MAX_BIAS floats)
   static constexpr int TOTAL = BIAS_OFF + MAX_BIAS * 4;
   static constexpr int DYN_BYTES = TOTAL + 1024;   // + slack for manual 1024 B alignment
 };
 
-template <int BN, int STAGES>
+// taps grouped into runs of consecutive row offsets (host side, build_gemm_sm100)
+struct TapGroups {
+  int n;
+  int w[kMaxTaps];        // taps in the group (row offsets off, off+1, ..., off+w-1)
+  int tap0[kMaxTaps];     // index of the group's first tap (= its column block in the weight matrix)
+  long off[kMaxTaps];
+};
+
+template <int BN, int SA, int SB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const GemmDesc d, const int num_m_tiles, const int num_n_tiles) {
-  using L = SmemLayout<BN, STAGES>;
+gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                  const __grid_constant__ CUtensorMap tmB, const GemmDesc d, const TapGroups tg, const int num_m_tiles,
+                  const int num_n_tiles, const int use_base_offset) {
+  using L = SmemLayout<BN, SA, SB>;
   constexpr int CH = BN >= 32 ? 32 : 16;            // epilogue column chunk
   constexpr uint32_t TMEM_COLS = tmem_cols(BN);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_base + L::BAR_OFF;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  auto afull_bar = [&](int s) { return bar_base + 8u * s; };
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (SA + s); };
+  auto bfull_bar = [&](int s) { return bar_base + 8u * (2 * SA + s); };
+  auto bempty_bar = [&](int s) { return bar_base + 8u * (2 * SA + SB + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SB + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SB + 2 + a); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_PTR_OFF);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = num_m_tiles * num_n_tiles;
   const int kb_per_tap = d.Cin / BK;
-  const int num_kb = d.ntaps * kb_per_tap;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA2) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+    for (int s = 0; s < SA; ++s) {
+      mbar_init(afull_bar(s), 1);
+      mbar_init(aempty_bar(s), 1);
+    }
+    for (int s = 0; s < SB; ++s) {
+      mbar_init(bfull_bar(s), 1);
+      mbar_init(bempty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -192,20 +216,28 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile / num_n_tiles, nt = tile - mt * num_n_tiles;
         const long m0 = d.m_begin + (long)mt * BM;
-        int tap = 0, cb = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_expect_tx(full_bar(stage), A_STAGE_BYTES + L::B_STAGE_BYTES);
-          tma_load_2d(smem_base + L::A_OFF + stage * A_STAGE_BYTES, &tmA, cb * BK, (int)(m0 + d.row_off[tap]),
-                      full_bar(stage));
-          tma_load_2d(smem_base + L::B_OFF + stage * L::B_STAGE_BYTES, &tmB, kb * BK, nt * BN, full_bar(stage));
-          if (++cb == kb_per_tap) { cb = 0; ++tap; }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        for (int g = 0; g < tg.n; ++g) {
+          const int w = tg.w[g];
+          for (int cb = 0; cb < kb_per_tap; ++cb) {
+            // one A slab serves the w row-shifted taps of this group
+            mbar_wait(aempty_bar(sa), pa ^ 1);
+            mbar_expect_tx(afull_bar(sa), w > 1 ? A_SLAB_BYTES : A_STAGE_BYTES);
+            tma_load_2d(smem_base + L::A_OFF + sa * A_SLOT_BYTES, w > 1 ? &tmA2 : &tmA, cb * BK, (int)(m0 + tg.off[g]),
+                        afull_bar(sa));
+            if (++sa == SA) { sa = 0; pa ^= 1; }
+            for (int j = 0; j < w; ++j) {
+              mbar_wait(bempty_bar(sb), pb ^ 1);
+              mbar_expect_tx(bfull_bar(sb), L::B_STAGE_BYTES);
+              tma_load_2d(smem_base + L::B_OFF + sb * L::B_STAGE_BYTES, &tmB, ((tg.tap0[g] + j) * kb_per_tap + cb) * BK,
+                          nt * BN, bfull_bar(sb));
+              if (++sb == SB) { sb = 0; pb ^= 1; }
+            }
+          }
         }
       }
     }
@@ -213,8 +245,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
@@ -222,18 +254,32 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tcgen05_fence_after();
-          const uint64_t adesc = make_smem_desc(smem_base + L::A_OFF + stage * A_STAGE_BYTES);
-          const uint64_t bdesc = make_smem_desc(smem_base + L::B_OFF + stage * L::B_STAGE_BYTES);
+        uint32_t accum = 0;
+        for (int g = 0; g < tg.n; ++g) {
+          const int w = tg.w[g];
+          for (int cb = 0; cb < kb_per_tap; ++cb) {
+            mbar_wait(afull_bar(sa), pa);
+            const uint32_t a_addr = smem_base + L::A_OFF + sa * A_SLOT_BYTES;
+            for (int j = 0; j < w; ++j) {
+              mbar_wait(bfull_bar(sb), pb);
+              tcgen05_fence_after();
+              // tap j of the group reads slab rows [j, j+128): start address + j rows; the descriptor's base-offset field
+              // carries the swizzle phase of the shifted start ((addr >> 7) & 7 = j & 7, slots are 1024 B aligned)
+              uint64_t adesc = make_smem_desc(a_addr + (uint32_t)(j * 128));
+              if (use_base_offset) adesc |= (uint64_t)(j & 7) << 49;
+              const uint64_t bdesc = make_smem_desc(smem_base + L::B_OFF + sb * L::B_STAGE_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr>>4) start field
-            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k) {
+                // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr>>4) start field
+                umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accum);
+                accum = 1u;
+              }
+              umma_commit(bempty_bar(sb));        // frees the weight tile once these MMAs have read it
+              if (++sb == SB) { sb = 0; pb ^= 1; }
+            }
+            umma_commit(aempty_bar(sa));          // frees the slab after the group's last tap
+            if (++sa == SA) { sa = 0; pa ^= 1; }
           }
-          umma_commit(empty_bar(stage));          // frees the smem slot once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(tfull_bar(acc));              // accumulator complete -> epilogue
       }
@@ -380,17 +426,21 @@ int make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t row
   return 0;
 }
 
-template <int BN, int STAGES>
+template <int BN, int SA, int SB>
 int run_impl(const GemmPlanSm100& p, cudaStream_t st) {
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, SA, SB>;
+  static_assert(L::DYN_BYTES <= 232448, "shared memory plan exceeds 227 KB");
   static bool attr_set = false;
   if (!attr_set) {
-    RGIE_CUDA_OK(cudaFuncSetAttribute(gemm_sm100_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RGIE_CUDA_OK(cudaFuncSetAttribute(gemm_sm100_kernel<BN, SA, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       L::DYN_BYTES));
     attr_set = true;
   }
-  gemm_sm100_kernel<BN, STAGES><<<p.grid, NUM_THREADS, L::DYN_BYTES, st>>>(p.tmA, p.tmB, p.d, p.num_m_tiles,
-                                                                           p.num_n_tiles);
+  TapGroups tg;
+  tg.n = p.n_groups;
+  for (int g = 0; g < p.n_groups; ++g) { tg.w[g] = p.group_w[g]; tg.tap0[g] = p.group_tap0[g]; tg.off[g] = p.group_off[g]; }
+  gemm_sm100_kernel<BN, SA, SB><<<p.grid, NUM_THREADS, L::DYN_BYTES, st>>>(p.tmA, p.tmA2, p.tmB, p.d, tg, p.num_m_tiles,
+                                                                           p.num_n_tiles, p.use_base_offset);
   RGIE_LAUNCH_OK();
   return 0;
 }
@@ -426,7 +476,26 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
   int sms = gemm_sm100_num_sms();
   p->grid = (int)(tiles < sms ? tiles : sms);
   if (p->grid < 1) p->grid = 1;
+  // group consecutive row offsets (3x3 taps of one kernel row, the 4 horizontal taps of the stem's input gradient)
+  const char* env_slab = getenv("RGIE_GEMM_SLAB");
+  const char* env_bo = getenv("RGIE_GEMM_BASE_OFFSET");
+  const bool slab = env_slab ? atoi(env_slab) != 0 : true;
+  p->use_base_offset = env_bo ? atoi(env_bo) : 1;
+  p->n_groups = 0;
+  for (int t = 0; t < d.ntaps; ++t) {
+    const int g = p->n_groups - 1;
+    if (slab && g >= 0 && p->group_w[g] < kMaxGroupW && d.row_off[t] == p->group_off[g] + p->group_w[g]) {
+      p->group_w[g]++;
+    } else {
+      p->group_off[p->n_groups] = d.row_off[t];
+      p->group_w[p->n_groups] = 1;
+      p->group_tap0[p->n_groups] = t;
+      p->n_groups++;
+    }
+  }
   int rc = make_map_2d(&p->tmA, d.A, (uint64_t)d.Cin, (uint64_t)d.a_rows, BK, BM);
+  if (rc) return rc;
+  rc = make_map_2d(&p->tmA2, d.A, (uint64_t)d.Cin, (uint64_t)d.a_rows, BK, SLAB_ROWS);
   if (rc) return rc;
   return make_map_2d(&p->tmB, d.Wt, (uint64_t)d.ntaps * d.Cin, (uint64_t)d.n_pad, BK, (uint32_t)bn);
 }
@@ -434,10 +503,10 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
 int run_gemm_sm100(const GemmPlanSm100& p, cudaStream_t st) {
   if (p.d.m_end <= p.d.m_begin) return 0;
   switch (p.bn) {
-    case 256: return run_impl<256, 4>(p, st);
-    case 128: return run_impl<128, 6>(p, st);
-    case 64: return run_impl<64, 8>(p, st);
-    case 16: return run_impl<16, 8>(p, st);
+    case 256: return run_impl<256, 3, 4>(p, st);
+    case 128: return run_impl<128, 4, 6>(p, st);
+    case 64: return run_impl<64, 4, 8>(p, st);
+    case 16: return run_impl<16, 4, 8>(p, st);
   }
   return fail("gemm_sm100: unsupported N tile");
 }

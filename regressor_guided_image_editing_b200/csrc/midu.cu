@@ -194,7 +194,8 @@ void pack3x3(const float* w, int co, int ci, std::vector<float>& f, std::vector<
       for (int k = 0; k < 9; ++k) {
         const float v = w[((size_t)n * ci + c) * 9 + k];
         f[(size_t)n * 9 * ci + (size_t)k * ci + c] = v;
-        t[(size_t)c * 9 * co + (size_t)k * co + n] = v;
+        const int kk = (k / 3) * 3 + (2 - k % 3);          // dgrad tap slot: taps of a kernel row reversed (ascending offsets)
+        t[(size_t)c * 9 * co + (size_t)kk * co + n] = v;
       }
 }
 int midu_run(RgieMiduHead* M, int i, cudaStream_t st) {
@@ -257,8 +258,11 @@ int rgie_midu_create(const float* const* h_tensors, int n_tensors, int n_out, in
     memset(&d, 0, sizeof(d));
     d.A = A; d.a_rows = g.rows(); d.Cin = ci; d.Wt = W; d.n_pad = co; d.ntaps = 9;
     for (int k = 0; k < 9; ++k) {
-      long off = (long)(k / 3 - 1) * g.P + (k % 3 - 1);
-      d.row_off[k] = transpose ? -off : off;
+      if (!transpose) d.row_off[k] = (long)(k / 3 - 1) * g.P + (k % 3 - 1);
+      else {
+        const int t = (k / 3) * 3 + (2 - k % 3);             // slot k holds kernel tap t (see pack3x3)
+        d.row_off[k] = -((long)(t / 3 - 1) * g.P + (t % 3 - 1));
+      }
     }
     d.m_begin = 0; d.m_end = g.rows(); d.Cout = co;
     d.src = g; d.dst_kind = DST_SAME; d.dst = g; d.D = D; d.ldd = co; d.d_fp32 = d_fp32;

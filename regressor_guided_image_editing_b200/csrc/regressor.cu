@@ -92,18 +92,16 @@ __device__ __forceinline__ void vec_store(T* p, const float* v) {
 }
 
 // 3x3 stride-2 pad-1 max pool over plain NHWC [N,Hi,Hi,C] -> padded layout g (Ho = Hi/2), argmax code 0..8 (first max).
-// One thread = one output pixel x 16 bytes of channels.
+// grid = (N * Ho) output rows; a thread = one output pixel x 16 bytes of channels (no 64-bit div/mod in the loop).
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const T* __restrict__ in, T* __restrict__ out,
-                                                         uint8_t* __restrict__ arg, Geom g, int Hi, int C, long total) {
+                                                         uint8_t* __restrict__ arg, Geom g, int Hi, int C) {
   constexpr int V = Vec16<T>::N;
-  const int cv = C / V;
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % cv) * V;
-    long q = idx / cv;
-    const int j = (int)(q % g.W); q /= g.W;
-    const int i = (int)(q % g.H);
-    const int n = (int)(q / g.H);
+  const int cvn = C / V;
+  const int n = blockIdx.x / g.H, i = blockIdx.x - n * g.H;
+  const T* in_n = in + (long)n * Hi * Hi * C;
+  for (int t = threadIdx.x; t < g.W * cvn; t += blockDim.x) {
+    const int j = t / cvn, c = (t - j * cvn) * V;
     float best[V];
     int code[V];
     bool first = true;
@@ -116,7 +114,7 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const T* __restrict__ 
         const int x = 2 * j - 1 + dx;
         if (x < 0 || x >= Hi) continue;
         float v[V];
-        vec_load<T>(in + (((long)n * Hi + y) * Hi + x) * C + c, v);
+        vec_load<T>(in_n + ((long)y * Hi + x) * C + c, v);
 #pragma unroll
         for (int e = 0; e < V; ++e)
           if (first || v[e] > best[e]) { best[e] = v[e]; code[e] = dy * 3 + dx; }
@@ -136,24 +134,22 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const T* __restrict__ 
   }
 }
 // backward of the pool + the stem ReLU mask: dC1[n,y,x,c] (layout gd) = (C1 > 0) * sum_{windows whose argmax is (y,x)} dP
+// grid = (N * Hi) input rows
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ dP, const uint8_t* __restrict__ arg,
                                                          const T* __restrict__ c1, T* __restrict__ dC1, Geom gp, Geom gd,
-                                                         int Hi, int C, long total) {
+                                                         int Hi, int C) {
   constexpr int V = Vec16<T>::N;
-  const int cv = C / V;
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % cv) * V;
-    long q = idx / cv;
-    const int x = (int)(q % Hi); q /= Hi;
-    const int y = (int)(q % Hi);
-    const int n = (int)(q / Hi);
+  const int cvn = C / V;
+  const int n = blockIdx.x / Hi, y = blockIdx.x - n * Hi;
+  const int i0 = y >> 1, i1 = (y + 1) >> 1;        // windows i with 2i-1 <= y <= 2i+1
+  for (int t = threadIdx.x; t < Hi * cvn; t += blockDim.x) {
+    const int x = t / cvn, c = (t - x * cvn) * V;
     float act[V], s[V];
     vec_load<T>(c1 + (((long)n * Hi + y) * Hi + x) * C + c, act);
 #pragma unroll
     for (int e = 0; e < V; ++e) s[e] = 0.f;
-    // windows i with 2i-1 <= y <= 2i+1  <=>  i in [y>>1, (y+1)>>1]
-    const int i0 = y >> 1, i1 = (y + 1) >> 1, j0 = x >> 1, j1 = (x + 1) >> 1;
+    const int j0 = x >> 1, j1 = (x + 1) >> 1;
     for (int i = i0; i <= i1; ++i) {
       if (i >= gp.H) continue;
       const int dy = y - (2 * i - 1);
@@ -164,11 +160,11 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ 
         uint32_t codes[2];
         if (V == 8) { const uint2 pk = *reinterpret_cast<const uint2*>(a); codes[0] = pk.x; codes[1] = pk.y; }
         else { codes[0] = *reinterpret_cast<const uint32_t*>(a); codes[1] = 0; }
-        float g[V];
-        vec_load<T>(dP + geom_row(gp, 0, n, i, j) * C + c, g);
+        float gr[V];
+        vec_load<T>(dP + geom_row(gp, 0, n, i, j) * C + c, gr);
 #pragma unroll
         for (int e = 0; e < V; ++e)
-          if (((codes[e >> 2] >> (8 * (e & 3))) & 0xFF) == (uint32_t)code) s[e] += g[e];
+          if (((codes[e >> 2] >> (8 * (e & 3))) & 0xFF) == (uint32_t)code) s[e] += gr[e];
       }
     }
 #pragma unroll
@@ -525,7 +521,7 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
             const int ai = a + 2, bi = b + 2, q = (pr * 2 + pc) * 3 + c;
             const float v = conv1.w[((k * 3 + c) * 7 + r) * 7 + s];
             w[(size_t)k * 256 + ai * 64 + bi * 16 + q] = v;
-            wt[(size_t)q * 1024 + (ai * 4 + bi) * 64 + k] = v;
+            wt[(size_t)q * 1024 + (ai * 4 + (3 - bi)) * 64 + k] = v;     // tap order j = 3 - bi: row offsets ascend
           }
     if (int rc = upload(R, w, &R->wc1)) return rc;
     if (int rc = upload(R, wt, &R->wc1t)) return rc;
@@ -599,13 +595,21 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
           for (int t = 0; t < 9; ++t) w2[(size_t)n * 9 * k.cm + (size_t)t * k.cm + c] = k.c2.w[((size_t)n * k.cm + c) * 9 + t];
       if (int rc = upload(R, w2, &k.w2)) return rc;
       if (!k.stride2) {
+        // tap slot tt = r*3 + j holds kernel tap (r, s = 2-j): the row offsets -((r-1)P + (s-1)) then ascend with j, so the
+        // GEMM serves the three taps of a kernel row from one operand slab
         std::vector<float> w2t((size_t)k.cm * 9 * k.cm);
         for (int n = 0; n < k.cm; ++n)
           for (int c = 0; c < k.cm; ++c)
-            for (int t = 0; t < 9; ++t) w2t[(size_t)c * 9 * k.cm + (size_t)t * k.cm + n] = k.c2.w[((size_t)n * k.cm + c) * 9 + t];
+            for (int tt = 0; tt < 9; ++tt) {
+              const int t = (tt / 3) * 3 + (2 - tt % 3);
+              w2t[(size_t)c * 9 * k.cm + (size_t)tt * k.cm + n] = k.c2.w[((size_t)n * k.cm + c) * 9 + t];
+            }
         if (int rc = upload(R, w2t, &k.w2t[0])) return rc;
         k.w2t_taps[0] = 9;
-        for (int t = 0; t < 9; ++t) k.w2t_off[0][t] = -((long)(t / 3 - 1) * gs.P + (t % 3 - 1));
+        for (int tt = 0; tt < 9; ++tt) {
+          const int t = (tt / 3) * 3 + (2 - tt % 3);
+          k.w2t_off[0][tt] = -((long)(t / 3 - 1) * gs.P + (t % 3 - 1));
+        }
       } else {
         for (int ph = 0; ph < 4; ++ph) {
           const int pr = ph >> 1, pc = ph & 1;
@@ -766,7 +770,7 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
     GemmDesc d = base_desc();
     d.A = R->dC1; d.a_rows = R->gDY.rows(); d.Cin = 64; d.Wt = R->wc1t; d.n_pad = 16; d.ntaps = 16;
     for (int a = 0; a < 4; ++a)
-      for (int b = 0; b < 4; ++b) d.row_off[a * 4 + b] = -((long)(a - 2) * R->gDY.P + (b - 2));
+      for (int j = 0; j < 4; ++j) d.row_off[a * 4 + j] = -((long)(a - 2) * R->gDY.P + ((3 - j) - 2));   // ascending in j
     d.m_begin = 0; d.m_end = R->gDY.rows(); d.Cout = 16;
     d.src = R->gDY; d.dst_kind = DST_TO_PLAIN; d.dst = R->gDY; d.D = R->dZ; d.ldd = 16; d.d_fp32 = 1;
     if (int rc = add_op(R, R->bwd_ops, d)) return rc;
@@ -788,7 +792,6 @@ int rgie_regressor_forward_ex(RgieRegressor* R, const float* img, int B, int Hr,
   R->B = B; R->reps = reps; R->Hr = Hr; R->Wr = Wr; R->normalize = normalize;
   const int N = R->N, H0 = R->H0, H1 = R->Hs[1];
   const long tot_pack = (long)N * H0 * H0 * 4;
-  const long tot_pool = (long)N * H1 * H1 * (64 / (16 / R->esz));
   if (R->dtype == 0) {
     pack_crops_kernel<float><<<grid_for(tot_pack), 256, 0, st>>>(img, offsets, step_ptr, off_step_stride, (float*)R->zz,
                                                                R->gZZ, reps, Hr, Wr, normalize, tot_pack);
@@ -800,9 +803,9 @@ int rgie_regressor_forward_ex(RgieRegressor* R, const float* img, int B, int Hr,
   RGIE_LAUNCH_OK();
   if (int rc = run_op(R, R->fwd_ops[0], st, 0)) return rc;
   if (R->dtype == 0)
-    maxpool_fwd_kernel<float><<<grid_for(tot_pool), 256, 0, st>>>((const float*)R->c1, (float*)R->p1, R->arg, R->gS[1], H0, 64, tot_pool);
+    maxpool_fwd_kernel<float><<<N * H1, 256, 0, st>>>((const float*)R->c1, (float*)R->p1, R->arg, R->gS[1], H0, 64);
   else
-    maxpool_fwd_kernel<__nv_bfloat16><<<grid_for(tot_pool), 256, 0, st>>>((const __nv_bfloat16*)R->c1, (__nv_bfloat16*)R->p1, R->arg, R->gS[1], H0, 64, tot_pool);
+    maxpool_fwd_kernel<__nv_bfloat16><<<N * H1, 256, 0, st>>>((const __nv_bfloat16*)R->c1, (__nv_bfloat16*)R->p1, R->arg, R->gS[1], H0, 64);
   RGIE_LAUNCH_OK();
   for (size_t i = 1; i < R->fwd_ops.size(); ++i)
     if (int rc = run_op(R, R->fwd_ops[i], st, i)) return rc;
@@ -844,11 +847,10 @@ int rgie_regressor_backward(RgieRegressor* R, const float* dlogits, float* dimg,
     if (int rc = run_op(R, R->bwd_ops[i], st, R->fwd_ops.size() + i)) return rc;
   // d(pool out) is the destination of the last block op (layer1.0 c1 dgrad)
   const void* dP = R->bwd_ops[nb - 2].d.D;
-  const long tot = (long)N * H0 * H0 * (64 / (16 / R->esz));
   if (R->dtype == 0)
-    maxpool_bwd_kernel<float><<<grid_for(tot), 256, 0, st>>>((const float*)dP, R->arg, (const float*)R->c1, (float*)R->dC1, R->gS[1], R->gDY, H0, 64, tot);
+    maxpool_bwd_kernel<float><<<N * H0, 256, 0, st>>>((const float*)dP, R->arg, (const float*)R->c1, (float*)R->dC1, R->gS[1], R->gDY, H0, 64);
   else
-    maxpool_bwd_kernel<__nv_bfloat16><<<grid_for(tot), 256, 0, st>>>((const __nv_bfloat16*)dP, R->arg, (const __nv_bfloat16*)R->c1, (__nv_bfloat16*)R->dC1, R->gS[1], R->gDY, H0, 64, tot);
+    maxpool_bwd_kernel<__nv_bfloat16><<<N * H0, 256, 0, st>>>((const __nv_bfloat16*)dP, R->arg, (const __nv_bfloat16*)R->c1, (__nv_bfloat16*)R->dC1, R->gS[1], R->gDY, H0, 64);
   RGIE_LAUNCH_OK();
   if (int rc = run_op(R, R->bwd_ops[nb - 1], st, R->fwd_ops.size() + nb - 1)) return rc;
   const long totg = (long)R->B * R->Hr * R->Wr;

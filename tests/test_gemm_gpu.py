@@ -52,6 +52,11 @@ CASES = [
     (6000, 256, 1024, [0], 0, 0, True, True, True, False),
     (9000, 128, 128, [3000 + d for d in (-59, -58, 0, 1)], 3000, -3000, False, False, False, False),
     (2500, 512, 2048, [0], 0, 0, True, False, True, False),
+    # runs of consecutive row offsets -> served from one operand slab through row-shifted matrix descriptors
+    (5000, 64, 16, [a * 227 + b for a in range(-2, 2) for b in range(-1, 3)], 0, 0, False, False, False, True),
+    (7000, 64, 64, [-115, -114, -113, -1, 0, 1, 113, 114, 115], 0, 0, True, False, True, False),
+    (3000, 128, 128, [-3, -2, -1, 0, 1, 2, 3, 4], 0, 0, False, False, False, True),
+    (4000, 256, 256, [-58 - 1, -58, -58 + 1, -1, 0, 1, 58 - 1, 58, 58 + 1], 0, 0, True, True, True, False),
 ]
 
 
