@@ -480,7 +480,7 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
   const char* env_slab = getenv("RGIE_GEMM_SLAB");
   const char* env_bo = getenv("RGIE_GEMM_BASE_OFFSET");
   const bool slab = env_slab ? atoi(env_slab) != 0 : true;
-  p->use_base_offset = env_bo ? atoi(env_bo) : 1;
+  p->use_base_offset = env_bo ? atoi(env_bo) : 0;   // measured on B200: the 128B swizzle is applied to absolute smem address bits, so a row-shifted start needs NO base offset (setting it corrupts the result)
   p->n_groups = 0;
   for (int t = 0; t < d.ntaps; ++t) {
     const int g = p->n_groups - 1;
