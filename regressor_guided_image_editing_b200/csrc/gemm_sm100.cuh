@@ -6,11 +6,7 @@ namespace rgie {
 
 struct GemmPlanSm100 {
   GemmDesc d;
-  CUtensorMap tmA, tmA2, tmB;      // A as 128-row tiles / 136-row slabs, weights
-  int n_groups;                     // runs of consecutive row offsets (one A slab load serves the whole run)
-  int group_w[kMaxTaps], group_tap0[kMaxTaps];
-  long group_off[kMaxTaps];
-  int use_base_offset;
+  CUtensorMap tmA, tmB;
   int bn;
   int num_m_tiles, num_n_tiles;
   int grid;
