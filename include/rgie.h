@@ -178,6 +178,13 @@ int rgie_midu_backward(RgieMiduHead* h, const float* dpred, float* dfeat, void* 
 int rgie_gemm_selftest(int backend, const void* A, long a_rows, int Cin, const void* W, int n_pad, int ntaps,
                        const long* h_row_off, long m_begin, long m_end, int Cout, const float* bias, const void* res,
                        int relu, void* D, int d_fp32, void* stream);
+/* extended form: optional second operand A2 [a2_rows, Cin2] whose contraction is concatenated along K
+ * (W is then [n_pad, ntaps*Cin + Cin2]), optional ReLU mask as 1 bit per element (mask_bits[m, Cout/32]) and optional
+ * sign-bit output (D_bits[m, Cout/32], bit set where the stored value is > 0). */
+int rgie_gemm_selftest_ex(int backend, const void* A, long a_rows, int Cin, const void* A2, long a2_rows, int Cin2,
+                          const void* W, int n_pad, int ntaps, const long* h_row_off, long m_begin, long m_end, int Cout,
+                          const float* bias, const void* res, const unsigned* mask_bits, int relu, void* D, int d_fp32,
+                          unsigned* D_bits, void* stream);
 
 #ifdef __cplusplus
 }

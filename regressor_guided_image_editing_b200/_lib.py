@@ -62,6 +62,8 @@ SIGNATURES = {
     "rgie_midu_forward": (_i, [_vp, _vp, _i, _vp, _vp]),
     "rgie_midu_backward": (_i, [_vp, _vp, _vp, _vp]),
     "rgie_gemm_selftest": (_i, [_i, _vp, _l, _i, _vp, _i, _i, C.POINTER(_l), _l, _l, _i, _vp, _vp, _i, _vp, _i, _vp]),
+    "rgie_gemm_selftest_ex": (_i, [_i, _vp, _l, _i, _vp, _l, _i, _vp, _i, _i, C.POINTER(_l), _l, _l, _i, _vp, _vp, _vp, _i,
+                                   _vp, _i, _vp, _vp]),
 }
 
 _lib = None

@@ -100,7 +100,11 @@ __host__ __device__ inline long map_row(const Geom& src, int kind, const Geom& d
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// The universal "row-shifted GEMM":  D[map(m), n] = epi( sum_t sum_c A[m + row_off[t], c] * Wt[n, t*Cin + c] )
+// The universal "row-shifted GEMM":
+//   D[map(m), n] = epi( sum_t sum_c A[m + row_off[t], c] * Wt[n, t*Cin + c]  +  sum_c A2[m, c] * Wt[n, ntaps*Cin + c] )
+// The optional second operand A2 (rows >= a2_rows contribute nothing) concatenates a second contraction along K: it
+// fuses the 1x1 downsample branch of a bottleneck into its conv3 (forward) / conv1 input gradient (backward), so the
+// branch output is never written to or re-read from HBM.
 // Both backends (tcgen05 in gemm_sm100.cu, CUDA-core fp32/bf16 in gemm_simt.cu) consume this descriptor.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kMaxTaps = 16;
@@ -110,6 +114,7 @@ struct GemmDesc {
   const void* A;      long a_rows;  int Cin;     // A: [a_rows, Cin] row-major
   const void* Wt;     int  n_pad;                 // Wt: [n_pad, ntaps*Cin] row-major (K-major), n_pad >= Cout
   int ntaps;          long row_off[kMaxTaps];
+  const void* A2;     long a2_rows; int Cin2;    // optional second operand [a2_rows, Cin2] (row offset 0), or null
   long m_begin, m_end;                            // rows enumerated (tiles start at m_begin)
   int Cout;
   // epilogue
@@ -118,8 +123,16 @@ struct GemmDesc {
   const float* bias;                               // [Cout] or null
   const void* res;    int ld_res;    long res_rows; // + res[m, n] for m < res_rows (same dtype as A)
   const void* mask;   int ld_mask;                 // * (mask[m, n] > 0)          (same dtype as A)
+  const uint32_t* mask_bits; int ld_mb;            // * bit n of row m (1 bit per element, ld in 32-bit words); alternative to mask
+  uint32_t* D_bits;   int ld_db;                   // also emit (stored value > 0) as 1 bit per element at row map(m) (tcgen05 backend)
   int relu;
 };
+
+// 1-bit-per-element masks (sign bits of an activation): word w (32 channels) of pixel row m.  Blocked by 32 rows so that
+// the 32 lanes of a warp (32 consecutive rows, same word) touch one contiguous 128-byte segment.
+// An array for `rows` rows of `words` words holds bits_words(rows, words) 32-bit words.
+__host__ __device__ inline long bits_index(long m, int w, int words) { return ((m >> 5) * words + w) * 32 + (m & 31); }
+__host__ __device__ inline long bits_words(long rows, int words) { return ((rows + 31) / 32) * 32 * (long)words; }
 
 // element helpers
 template <typename T> __device__ __forceinline__ float to_f(T v);

@@ -1,14 +1,17 @@
 // tcgen05 / TMEM / TMA backend of the row-shifted GEMM (common.cuh: GemmDesc) -- sm_100a only.
 //
-//   D[map(m), n] = epi( sum_t sum_c A[m + row_off[t], c] * Wt[n, t*Cin + c] )          bf16 x bf16 -> fp32 (TMEM)
+//   D[map(m), n] = epi( sum_t sum_c A[m + row_off[t], c] * Wt[n, t*Cin + c] + sum_c A2[m, c] * Wt[n, ntaps*Cin + c] )
+//                                                                                     bf16 x bf16 -> fp32 (TMEM)
 //
 // One persistent CTA per SM, 320 threads:
 //   warp 0      : TMA producer   (cp.async.bulk.tensor.2d, 128B swizzle, zero fill for out-of-range rows = conv padding)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (cta_group::1, M=128, N=BN, K=16 per instruction)
-//   warps 2..9  : epilogue       (tcgen05.ld 32x32b -> bias / residual / ReLU / ReLU-mask -> row-remapped 16B stores;
-//                                 residual/mask operands prefetched one chunk ahead)
+//   warps 2..9  : epilogue       (tcgen05.ld 32x32b -> bias / residual / ReLU / ReLU-mask -> row-remapped 32B stores
+//                                 + 1 sign bit per stored element).  The residual operand is prefetched a whole tile ahead
+//                                 in registers (its HBM latency is never exposed); ReLU masks are 1 bit per element.
 // Pipelines: STAGES-deep smem ring (full/empty mbarriers) between TMA and MMA; 2 TMEM accumulator buffers
 // (tmem_full/tmem_empty) between MMA and epilogue so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <stdlib.h>
 #include "common.cuh"
 #include "gemm_sm100.cuh"
 
@@ -137,13 +140,18 @@ struct SmemLayout {
   static constexpr int BIAS_OFF = TMEM_PTR_OFF + 16;                // whole bias vector (<= MAX_BIAS floats)
   static constexpr int TOTAL = BIAS_OFF + MAX_BIAS * 4;
   static constexpr int DYN_BYTES = TOTAL + 1024;   // + slack for manual 1024 B alignment
+  static_assert(DYN_BYTES <= 232448, "shared memory plan exceeds 227 KB");
 };
 
 // ===================== epilogue role (8 warps; one TMEM lane = one output row per thread) =====================
 // warps 2..9: lane quarter q = warp & 3 (hardware restriction on tcgen05.ld), column half = (warp - 2) >> 2.
-// The residual / ReLU-mask operands of a chunk are fetched one chunk ahead (and, for the first chunk of a tile, before
-// waiting for the accumulator) so their HBM latency overlaps the TMEM read + math of the previous chunk.  All global
-// accesses are 256-bit (one full 32 B sector per thread per instruction).
+// A thread walks the 32-column chunks of its row / column half, tile after tile.  Operands it has to read:
+//   residual (bf16 [m, n])   one register buffer per chunk position; the buffer is refilled with the SAME chunk of the
+//                            NEXT tile right after it has been consumed, so a whole tile's worth of residual (256 B per
+//                            thread, 64 KB per SM) is always in flight and its HBM latency is never exposed
+//   ReLU mask as bits        one 32-bit word per chunk, loaded one tile ahead (blocked layout: bits_index)
+//   ReLU mask as activations loaded at use (MiDU head only; the regressor uses bits)
+// All global accesses of activations are 256-bit (one full 32 B sector per thread per instruction).
 template <int BN>
 __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sbias, const uint32_t tmem_base,
                                               const uint32_t tfull0, const uint32_t tempty0, const int warp, const int lane,
@@ -160,7 +168,39 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
   const bool active = NCH >= 2 || half == 0;
   const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(d.res);
   const __nv_bfloat16* mask = reinterpret_cast<const __nv_bfloat16*>(d.mask);
-    const bool has_bias = d.bias != nullptr;
+  const uint32_t* mbits = d.mask_bits;
+  const bool has_bias = d.bias != nullptr;
+  const long res_lim = d.res_rows < d.m_end ? d.res_rows : d.m_end;
+
+  // operands of the NEXT tile (prefetched while the current one is processed)
+  uint32_t rbuf[CPW][CH / 2];                      // residual: CH bf16 per chunk
+  uint32_t bits_nxt[CPW];
+  const __nv_bfloat16* nres = nullptr;             // residual row of the tile being prefetched (null: nothing to read)
+  auto locate = [&](int tile) {
+    nres = nullptr;
+#pragma unroll
+    for (int i = 0; i < CPW; ++i) bits_nxt[i] = 0u;
+    if (tile < num_tiles && active) {
+      const int mt = tile / num_n_tiles, nt = tile - mt * num_n_tiles;
+      const long m = d.m_begin + (long)mt * BM + row;
+      if (res != nullptr && m < res_lim) nres = res + m * d.ld_res + nt * BN + c_begin * CH;
+      if (mbits != nullptr && m < d.m_end) {
+        const int w0 = (nt * BN) / 32 + c_begin;
+#pragma unroll
+        for (int i = 0; i < CPW; ++i) bits_nxt[i] = __ldg(mbits + bits_index(m, w0 + i, d.ld_mb));
+      }
+    }
+  };
+  auto res_fetch = [&](int ci) {
+    if (nres != nullptr) {
+#pragma unroll
+      for (int j = 0; j < CH / 16; ++j) ldg256(nres + ci * CH + j * 16, rbuf[ci] + 8 * j);
+    }
+  };
+  locate(blockIdx.x);
+#pragma unroll
+  for (int ci = 0; ci < CPW; ++ci) res_fetch(ci);
+
   int it = 0;
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
     const int mt = tile / num_n_tiles, nt = tile - mt * num_n_tiles;
@@ -172,17 +212,11 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
     const bool live = active && dest >= 0;
     const bool use_res = live && res != nullptr && m < d.res_rows;
     const bool use_mask = live && mask != nullptr;
-    const __nv_bfloat16* res_p = res + m * d.ld_res + nt * BN;
     const __nv_bfloat16* mask_p = mask + m * d.ld_mask + nt * BN;
-    uint32_t rcur[CH / 2], kcur[CH / 2], rnxt[CH / 2], knxt[CH / 2];     // CH bf16 = CH/2 words = CH/16 x 256 bit
-    auto fetch = [&](int c, uint32_t* rr, uint32_t* kk) {
+    uint32_t bits_cur[CPW], bits_out[CPW];
 #pragma unroll
-      for (int j = 0; j < CH / 16; ++j) {
-        if (use_res) ldg256(res_p + c * CH + j * 16, rr + 8 * j);
-        if (use_mask) ldg256(mask_p + c * CH + j * 16, kk + 8 * j);
-      }
-    };
-    fetch(c_begin, rcur, kcur);
+    for (int i = 0; i < CPW; ++i) { bits_cur[i] = bits_nxt[i]; bits_out[i] = 0u; }
+    locate(tile + gridDim.x);                      // pointers / mask words of the next tile
     mbar_wait(tfull_bar(acc), acc_phase);
     tcgen05_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
@@ -190,15 +224,19 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
 #pragma unroll
       for (int ci = 0; ci < CPW; ++ci) {
         const int c = c_begin + ci;
-        if (ci + 1 < CPW) fetch(c + 1, rnxt, knxt);
         uint32_t r[CH];
         tmem_ld<CH>(taddr + (uint32_t)(c * CH), r);
         tmem_ld_wait();
         const int n0 = nt * BN + c * CH;
-        if (live) {
-          float v[CH];
+        float v[CH];
 #pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
+        for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
+        if (use_res) {
+#pragma unroll
+          for (int j = 0; j < CH / 2; ++j) { v[2 * j] += bf16_lo(rbuf[ci][j]); v[2 * j + 1] += bf16_hi(rbuf[ci][j]); }
+        }
+        res_fetch(ci);                             // refill this buffer with the same chunk of the next tile
+        if (live) {
           if (has_bias) {
             const float4* b4 = reinterpret_cast<const float4*>(sbias + n0);
 #pragma unroll
@@ -207,27 +245,40 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
               v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
             }
           }
-          if (use_res) {
-#pragma unroll
-            for (int j = 0; j < CH / 2; ++j) { v[2 * j] += bf16_lo(rcur[j]); v[2 * j + 1] += bf16_hi(rcur[j]); }
-          }
           if (d.relu) {
 #pragma unroll
             for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
           }
           if (use_mask) {
 #pragma unroll
-            for (int j = 0; j < CH / 2; ++j) {
-              // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-              const uint32_t lo = kcur[j] & 0xFFFFu, hi = kcur[j] >> 16;
-              if (!(lo != 0 && lo < 0x8000u)) v[2 * j] = 0.f;
-              if (!(hi != 0 && hi < 0x8000u)) v[2 * j + 1] = 0.f;
+            for (int jj = 0; jj < CH / 16; ++jj) {
+              uint32_t k8[8];
+              ldg256(mask_p + c * CH + jj * 16, k8);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                const uint32_t lo = k8[j] & 0xFFFFu, hi = k8[j] >> 16;
+                if (!(lo != 0 && lo < 0x8000u)) v[jj * 16 + 2 * j] = 0.f;
+                if (!(hi != 0 && hi < 0x8000u)) v[jj * 16 + 2 * j + 1] = 0.f;
+              }
             }
+          }
+          if (mbits != nullptr) {
+            const uint32_t w = bits_cur[ci];
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (!((w >> j) & 1u)) v[j] = 0.f;
           }
           if (d.d_fp32) {
             float* o = reinterpret_cast<float*>(d.D) + dest * d.ldd + n0;
 #pragma unroll
             for (int j = 0; j < CH / 8; ++j) stg256(o + 8 * j, reinterpret_cast<const uint32_t*>(v) + 8 * j);
+            if (d.D_bits != nullptr) {
+              uint32_t w = 0u;
+#pragma unroll
+              for (int j = 0; j < CH; ++j) w |= (v[j] > 0.f ? 1u : 0u) << j;
+              bits_out[ci] = w;
+            }
           } else {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(d.D) + dest * d.ldd + n0;
             uint32_t pk[CH / 2];
@@ -235,10 +286,24 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
             for (int j = 0; j < CH / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
 #pragma unroll
             for (int j = 0; j < CH / 16; ++j) stg256(o + 16 * j, pk + 8 * j);
+            if (d.D_bits != nullptr) {
+              // sign bits of the STORED bf16 values (what a later (activation > 0) test would see): as signed 16-bit
+              // integers, bf16 > 0  <=>  halfword > 0
+              uint32_t w = 0u;
+#pragma unroll
+              for (int j = 0; j < CH / 2; ++j) {
+                const uint32_t g = __vcmpgts2(pk[j], 0u) & 0x00010001u;      // bit 0 / bit 16
+                w |= ((g | (g >> 15)) & 3u) << (2 * j);
+              }
+              bits_out[ci] = w;
+            }
           }
         }
+      }
+      if (live && d.D_bits != nullptr) {
+        const int w0 = (nt * BN) / 32 + c_begin;
 #pragma unroll
-        for (int j = 0; j < CH / 2; ++j) { rcur[j] = rnxt[j]; kcur[j] = knxt[j]; }
+        for (int i = 0; i < CPW; ++i) d.D_bits[bits_index(dest, w0 + i, d.ld_db)] = bits_out[i];
       }
     }
     tcgen05_fence_before();
@@ -249,10 +314,9 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const GemmDesc d, const int num_m_tiles, const int num_n_tiles) {
+gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                  const __grid_constant__ CUtensorMap tmB, const GemmDesc d, const int num_m_tiles, const int num_n_tiles) {
   using L = SmemLayout<BN, STAGES>;
-  constexpr int CH = BN >= 32 ? 32 : 16;            // epilogue column chunk
   constexpr uint32_t TMEM_COLS = tmem_cols(BN);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -268,10 +332,12 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int lane = threadIdx.x & 31;
   const int num_tiles = num_m_tiles * num_n_tiles;
   const int kb_per_tap = d.Cin / BK;
-  const int num_kb = d.ntaps * kb_per_tap;
+  const int num_kb = d.ntaps * kb_per_tap;                       // k-blocks of the row-shifted taps
+  const int num_kb2 = d.A2 != nullptr ? d.Cin2 / BK : 0;         // k-blocks of the second operand (tiles below a2_rows)
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA2) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
@@ -315,6 +381,15 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (++cb == kb_per_tap) { cb = 0; ++tap; }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (m0 < d.a2_rows) {
+          for (int kb = 0; kb < num_kb2; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            mbar_expect_tx(full_bar(stage), A_STAGE_BYTES + L::B_STAGE_BYTES);
+            tma_load_2d(smem_base + L::A_OFF + stage * A_STAGE_BYTES, &tmA2, kb * BK, (int)m0, full_bar(stage));
+            tma_load_2d(smem_base + L::B_OFF + stage * L::B_STAGE_BYTES, &tmB, (num_kb + kb) * BK, nt * BN, full_bar(stage));
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -327,10 +402,12 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
+        const long m0 = d.m_begin + (long)(tile / num_n_tiles) * BM;
+        const int kb_total = num_kb + (m0 < d.a2_rows ? num_kb2 : 0);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
           const uint64_t adesc = make_smem_desc(smem_base + L::A_OFF + stage * A_STAGE_BYTES);
@@ -400,8 +477,8 @@ int run_impl(const GemmPlanSm100& p, cudaStream_t st) {
                                       L::DYN_BYTES));
     attr_set = true;
   }
-  gemm_sm100_kernel<BN, STAGES><<<p.grid, NUM_THREADS, L::DYN_BYTES, st>>>(p.tmA, p.tmB, p.d, p.num_m_tiles,
-                                                                           p.num_n_tiles);
+  gemm_sm100_kernel<BN, STAGES><<<p.grid, NUM_THREADS, L::DYN_BYTES, st>>>(p.tmA, p.tmA2, p.tmB, p.d, p.num_m_tiles,
+                                                                                p.num_n_tiles);
   RGIE_LAUNCH_OK();
   return 0;
 }
@@ -426,6 +503,8 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
   RGIE_CHECK(d.a_rows < (1L << 31), "gemm_sm100: too many A rows for a TMA coordinate");
   int bn = d.Cout >= 256 ? 256 : (d.Cout >= 128 ? 128 : (d.Cout >= 64 ? 64 : 16));
   RGIE_CHECK(d.Cout % bn == 0 && d.n_pad % bn == 0, "gemm_sm100: Cout/n_pad must be a multiple of the N tile");
+  RGIE_CHECK(d.A2 == nullptr || (d.Cin2 % BK == 0 && d.a2_rows < (1L << 31)), "gemm_sm100: second operand: Cin2 % 64, rows");
+  RGIE_CHECK((d.mask_bits == nullptr && d.D_bits == nullptr) || bn >= 64, "gemm_sm100: bit masks need Cout >= 64");
   RGIE_CHECK(d.ldd % 16 == 0 && (d.res == nullptr || d.ld_res % 16 == 0) && (d.mask == nullptr || d.ld_mask % 16 == 0),
              "gemm_sm100: leading dimensions must be multiples of 16 elements (32-byte accesses)");
   p->d = d;
@@ -439,7 +518,10 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
   if (p->grid < 1) p->grid = 1;
   int rc = make_map_2d(&p->tmA, d.A, (uint64_t)d.Cin, (uint64_t)d.a_rows, BK, BM);
   if (rc) return rc;
-  return make_map_2d(&p->tmB, d.Wt, (uint64_t)d.ntaps * d.Cin, (uint64_t)d.n_pad, BK, (uint32_t)bn);
+  if (d.A2 != nullptr) rc = make_map_2d(&p->tmA2, d.A2, (uint64_t)d.Cin2, (uint64_t)d.a2_rows, BK, BM);
+  else p->tmA2 = p->tmA;
+  if (rc) return rc;
+  return make_map_2d(&p->tmB, d.Wt, (uint64_t)d.ntaps * d.Cin + (d.A2 ? d.Cin2 : 0), (uint64_t)d.n_pad, BK, (uint32_t)bn);
 }
 
 int run_gemm_sm100(const GemmPlanSm100& p, cudaStream_t st) {

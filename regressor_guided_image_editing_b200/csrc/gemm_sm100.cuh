@@ -6,7 +6,7 @@ namespace rgie {
 
 struct GemmPlanSm100 {
   GemmDesc d;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmA2, tmB;      // A, optional second operand, weights
   int bn;
   int num_m_tiles, num_n_tiles;
   int grid;

@@ -91,7 +91,9 @@ __device__ __forceinline__ void vec_store(T* p, const float* v) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
-// 3x3 stride-2 pad-1 max pool over plain NHWC [N,Hi,Hi,C] -> padded layout g (Ho = Hi/2), argmax code 0..8 (first max).
+// 3x3 stride-2 pad-1 max pool over plain NHWC [N,Hi,Hi,C] -> padded layout g (Ho = Hi/2).  Per element one byte:
+// argmax code 0..8 (first max) | 0x10 when the maximum is > 0 (the pool input is the stem's post-ReLU activation, so
+// the backward pass never has to re-read it for the ReLU mask).
 // grid = (N * Ho) output rows; a thread = one output pixel x 16 bytes of channels (no 64-bit div/mod in the loop).
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const T* __restrict__ in, T* __restrict__ out,
@@ -122,6 +124,8 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const T* __restrict__ 
       }
     }
     vec_store<T>(out + geom_row(g, 0, n, i, j) * C + c, best);
+#pragma unroll
+    for (int e = 0; e < V; ++e) code[e] |= best[e] > 0.f ? 0x10 : 0;
     uint8_t* a = arg + (((long)n * g.H + i) * g.W + j) * C + c;
     if (V == 8) {
       uint2 pk;
@@ -133,43 +137,53 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const T* __restrict__ 
     }
   }
 }
-// backward of the pool + the stem ReLU mask: dC1[n,y,x,c] (layout gd) = (C1 > 0) * sum_{windows whose argmax is (y,x)} dP
-// grid = (N * Hi) input rows
+// backward of the pool fused with the stem ReLU mask: dC1[n,y,x,c] (layout gd) = sum over the windows whose argmax is
+// (y,x) AND whose maximum is positive of dP.  grid = (N * Ho) rows of 2x2 input quads; a thread = one quad (a,b) x 16 bytes
+// of channels: pixel (2a+ry, 2b+rx) can only be the argmax of windows (a..a+1, b..b+1), so four window reads (argmax byte
+// + gradient) produce the four outputs -- the stem activation itself is not read.
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ dP, const uint8_t* __restrict__ arg,
-                                                         const T* __restrict__ c1, T* __restrict__ dC1, Geom gp, Geom gd,
-                                                         int Hi, int C) {
+                                                         T* __restrict__ dC1, Geom gp, Geom gd, int C) {
   constexpr int V = Vec16<T>::N;
   const int cvn = C / V;
-  const int n = blockIdx.x / Hi, y = blockIdx.x - n * Hi;
-  const int i0 = y >> 1, i1 = (y + 1) >> 1;        // windows i with 2i-1 <= y <= 2i+1
-  for (int t = threadIdx.x; t < Hi * cvn; t += blockDim.x) {
-    const int x = t / cvn, c = (t - x * cvn) * V;
-    float act[V], s[V];
-    vec_load<T>(c1 + (((long)n * Hi + y) * Hi + x) * C + c, act);
+  const int n = blockIdx.x / gp.H, a = blockIdx.x - n * gp.H;
+  for (int t = threadIdx.x; t < gp.W * cvn; t += blockDim.x) {
+    const int b = t / cvn, c = (t - b * cvn) * V;
+    float s[2][2][V];
 #pragma unroll
-    for (int e = 0; e < V; ++e) s[e] = 0.f;
-    const int j0 = x >> 1, j1 = (x + 1) >> 1;
-    for (int i = i0; i <= i1; ++i) {
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int e = 0; e < V; ++e) s[q >> 1][q & 1][e] = 0.f;
+#pragma unroll
+    for (int wi = 0; wi < 2; ++wi) {
+      const int i = a + wi;
       if (i >= gp.H) continue;
-      const int dy = y - (2 * i - 1);
-      for (int j = j0; j <= j1; ++j) {
+#pragma unroll
+      for (int wj = 0; wj < 2; ++wj) {
+        const int j = b + wj;
         if (j >= gp.W) continue;
-        const int code = dy * 3 + (x - (2 * j - 1));
-        const uint8_t* a = arg + (((long)n * gp.H + i) * gp.W + j) * C + c;
+        const uint8_t* ap = arg + (((long)n * gp.H + i) * gp.W + j) * C + c;
         uint32_t codes[2];
-        if (V == 8) { const uint2 pk = *reinterpret_cast<const uint2*>(a); codes[0] = pk.x; codes[1] = pk.y; }
-        else { codes[0] = *reinterpret_cast<const uint32_t*>(a); codes[1] = 0; }
+        if (V == 8) { const uint2 pk = *reinterpret_cast<const uint2*>(ap); codes[0] = pk.x; codes[1] = pk.y; }
+        else { codes[0] = *reinterpret_cast<const uint32_t*>(ap); codes[1] = 0; }
         float gr[V];
         vec_load<T>(dP + geom_row(gp, 0, n, i, j) * C + c, gr);
+        // window (i,j) covers input rows 2i-1..2i+1: quad row ry maps to dy = ry+1 (wi = 0) or ry-1 (wi = 1, ry = 1 only)
 #pragma unroll
-        for (int e = 0; e < V; ++e)
-          if (((codes[e >> 2] >> (8 * (e & 3))) & 0xFF) == (uint32_t)code) s[e] += gr[e];
+        for (int ry = wi; ry < 2; ++ry)
+#pragma unroll
+          for (int rx = wj; rx < 2; ++rx) {
+            const uint32_t want = 0x10u | (uint32_t)((wi ? 0 : ry + 1) * 3 + (wj ? 0 : rx + 1));
+#pragma unroll
+            for (int e = 0; e < V; ++e)
+              if (((codes[e >> 2] >> (8 * (e & 3))) & 0xFF) == want) s[ry][rx][e] += gr[e];
+          }
       }
     }
 #pragma unroll
-    for (int e = 0; e < V; ++e) s[e] = act[e] > 0.f ? s[e] : 0.f;
-    vec_store<T>(dC1 + geom_row(gd, 0, n, y, x) * C + c, s);
+    for (int ry = 0; ry < 2; ++ry)
+#pragma unroll
+      for (int rx = 0; rx < 2; ++rx) vec_store<T>(dC1 + geom_row(gd, 0, n, 2 * a + ry, 2 * b + rx) * C + c, s[ry][rx]);
   }
 }
 
@@ -334,10 +348,12 @@ struct Block {
   int w2t_taps[4] = {0, 0, 0, 0};
   long w2t_off[4][kMaxTaps];
   float *b1 = nullptr, *b2 = nullptr, *b3 = nullptr, *bds = nullptr;
-  // activations
+  // activations (+ their sign bits, 1 bit per element, bf16 modes only: the ReLU masks of the backward pass)
   void *h1 = nullptr, *h2 = nullptr, *out = nullptr;
+  uint32_t *h1_bits = nullptr, *h2_bits = nullptr, *out_bits = nullptr;
   Geom gx, gs, gout;    // layout of X / of the stage / of OUT
   const void* x = nullptr;
+  const uint32_t* x_bits = nullptr;
 };
 
 struct GemmOp {
@@ -360,8 +376,7 @@ struct RgieRegressor {
   float *wfc = nullptr, *bfc = nullptr, *feat = nullptr, *dfeat = nullptr;
   // gradients
   void* dOut[5][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
-  void *dH2[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *dH1[5] = {nullptr, nullptr, nullptr, nullptr, nullptr},
-       *gds[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *dsbuf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  void *dH2[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *dH1[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   void* dC1 = nullptr; float* dZ = nullptr;
   std::vector<GemmOp> fwd_ops, bwd_ops;
   // call state
@@ -438,7 +453,18 @@ double op_flops(const GemmDesc& d, double useful_frac) {
   const Geom& g = d.src;
   double rows_per_plane = (double)g.n_img * g.H * g.W;
   double planes = (double)(d.m_end - d.m_begin) / (double)g.plane_rows();
-  return 2.0 * rows_per_plane * planes * (double)d.Cout * (double)d.ntaps * (double)d.Cin * useful_frac;
+  double f = 2.0 * rows_per_plane * planes * (double)d.Cout * (double)d.ntaps * (double)d.Cin * useful_frac;
+  if (d.A2 != nullptr) f += 2.0 * rows_per_plane * (double)d.Cout * (double)d.Cin2;   // second operand: one plane of rows
+  return f;
+}
+
+// set the ReLU mask of a backward op: sign bits in the bf16 modes, the activation itself in fp32 parity mode
+void set_mask(const RgieRegressor* R, GemmDesc& d, const void* act, const uint32_t* bits, int channels) {
+  if (R->dtype == 1) { d.mask = nullptr; d.mask_bits = bits; d.ld_mb = channels / 32; }
+  else { d.mask = act; d.ld_mask = channels; }
+}
+void set_out_bits(const RgieRegressor* R, GemmDesc& d, uint32_t* bits, int channels) {
+  if (R->dtype == 1) { d.D_bits = bits; d.ld_db = channels / 32; }
 }
 
 }  // namespace
@@ -543,14 +569,11 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
   // ---- per-stage gradient scratch
   for (int s = 1; s <= 4; ++s) {
     const int cm = 64 << (s - 1), co = 4 * cm;
-    const int ci_max = s == 1 ? 64 : 2 * cm;           // input channels of the stage's ds block
     const long rows = R->gS[s].rows();
     for (int p = 0; p < 2; ++p)
       if (int rc = dev_alloc(R, &R->dOut[s][p], (size_t)rows * co * esz, true)) return rc;
     if (int rc = dev_alloc(R, &R->dH2[s], (size_t)rows * cm * esz, true)) return rc;
     if (int rc = dev_alloc(R, &R->dH1[s], (size_t)(s > 1 ? 4 : 1) * rows * cm * esz, true)) return rc;
-    if (int rc = dev_alloc(R, &R->gds[s], (size_t)rows * ci_max * esz, true)) return rc;
-    if (int rc = dev_alloc(R, &R->dsbuf[s], (size_t)rows * co * esz, true)) return rc;
   }
 
   // ---- forward GEMM 0: conv1
@@ -567,6 +590,7 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
 
   // ---- blocks: weights, buffers, forward ops
   const void* x = R->p1;
+  const uint32_t* x_bits = nullptr;
   for (size_t bi = 0; bi < R->blocks.size(); ++bi) {
     Block& k = R->blocks[bi];
     const int s = k.stage;
@@ -633,12 +657,23 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
         }
       }
       if (k.ds) {
-        std::vector<float> wd((size_t)k.co * k.ci), wdt((size_t)k.ci * k.co);
-        for (int n = 0; n < k.co; ++n)
-          for (int c = 0; c < k.ci; ++c) { wd[(size_t)n * k.ci + c] = k.dsw.w[(size_t)n * k.ci + c]; wdt[(size_t)c * k.co + n] = k.dsw.w[(size_t)n * k.ci + c]; }
+        // the downsample branch rides in the same GEMMs as a second operand (K-concatenation):
+        //   forward  out = relu([h2 | x_ds] . [W3 | Wds]^T + b3 + bds)        -> wds  = [co, cm + ci]
+        //   backward dX  = mask * ([dH1 | dOut] . [W1^T | Wds^T]^T)           -> wdst = [ci, cm + co]
+        const int kf = k.cm + k.ci, kb = k.cm + k.co;
+        std::vector<float> wd((size_t)k.co * kf), wdt((size_t)k.ci * kb), bsum(k.co);
+        for (int n = 0; n < k.co; ++n) {
+          for (int c = 0; c < k.cm; ++c) wd[(size_t)n * kf + c] = k.c3.w[(size_t)n * k.cm + c];
+          for (int c = 0; c < k.ci; ++c) wd[(size_t)n * kf + k.cm + c] = k.dsw.w[(size_t)n * k.ci + c];
+          bsum[n] = k.c3.b[n] + k.dsw.b[n];
+        }
+        for (int c = 0; c < k.ci; ++c) {
+          for (int n = 0; n < k.cm; ++n) wdt[(size_t)c * kb + n] = k.c1.w[(size_t)n * k.ci + c];
+          for (int n = 0; n < k.co; ++n) wdt[(size_t)c * kb + k.cm + n] = k.dsw.w[(size_t)n * k.ci + c];
+        }
         if (int rc = upload(R, wd, &k.wds)) return rc;
         if (int rc = upload(R, wdt, &k.wdst)) return rc;
-        if (int rc = upload_f32(R, k.dsw.b, k.co, &k.bds)) return rc;
+        if (int rc = upload_f32(R, bsum.data(), k.co, &k.bds)) return rc;
       }
       if (int rc = upload_f32(R, k.c1.b, k.cm, &k.b1)) return rc;
       if (int rc = upload_f32(R, k.c2.b, k.cm, &k.b2)) return rc;
@@ -648,6 +683,11 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
     if (int rc = dev_alloc(R, &k.h1, (size_t)k.gx.rows() * k.cm * esz, true)) return rc;
     if (int rc = dev_alloc(R, &k.h2, (size_t)Mp * k.cm * esz, true)) return rc;
     if (int rc = dev_alloc(R, &k.out, (size_t)k.gout.rows() * k.co * esz, true)) return rc;
+    if (R->dtype == 1) {
+      if (int rc = dev_alloc(R, (void**)&k.h1_bits, (size_t)bits_words(k.gx.rows(), k.cm / 32) * 4, true)) return rc;
+      if (int rc = dev_alloc(R, (void**)&k.h2_bits, (size_t)bits_words(Mp, k.cm / 32) * 4, true)) return rc;
+      if (int rc = dev_alloc(R, (void**)&k.out_bits, (size_t)bits_words(k.gout.rows(), k.co / 32) * 4, true)) return rc;
+    }
 
     // c1
     {
@@ -655,6 +695,7 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
       d.A = k.x; d.a_rows = k.gx.rows(); d.Cin = k.ci; d.Wt = k.w1; d.n_pad = k.cm; d.ntaps = 1; d.row_off[0] = 0;
       d.m_begin = 0; d.m_end = k.gx.rows(); d.Cout = k.cm;
       d.src = k.gx; d.dst_kind = DST_SAME; d.dst = k.gx; d.D = k.h1; d.ldd = k.cm; d.bias = k.b1; d.relu = 1;
+      set_out_bits(R, d, k.h1_bits, k.cm);
       if (int rc = add_op(R, R->fwd_ops, d)) return rc;
     }
     // c2
@@ -672,26 +713,27 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
       }
       d.m_begin = 0; d.m_end = Mp; d.Cout = k.cm;
       d.src = gs; d.dst_kind = DST_SAME; d.dst = gs; d.D = k.h2; d.ldd = k.cm; d.bias = k.b2; d.relu = 1;
+      set_out_bits(R, d, k.h2_bits, k.cm);
       if (int rc = add_op(R, R->fwd_ops, d)) return rc;
     }
-    // downsample branch
-    if (k.ds) {
-      GemmDesc d = base_desc();
-      d.A = k.x; d.a_rows = k.gx.rows(); d.Cin = k.ci; d.Wt = k.wds; d.n_pad = k.co; d.ntaps = 1; d.row_off[0] = 0;
-      d.m_begin = 0; d.m_end = Mp; d.Cout = k.co;
-      d.src = gs; d.dst_kind = DST_SAME; d.dst = gs; d.D = R->dsbuf[s]; d.ldd = k.co; d.bias = k.bds; d.relu = 0;
-      if (int rc = add_op(R, R->fwd_ops, d)) return rc;
-    }
-    // c3 + residual + relu
+    // c3 + residual (identity skip: epilogue operand; downsample branch: second GEMM operand) + relu
     {
       GemmDesc d = base_desc();
-      d.A = k.h2; d.a_rows = Mp; d.Cin = k.cm; d.Wt = k.w3; d.n_pad = k.co; d.ntaps = 1; d.row_off[0] = 0;
+      d.A = k.h2; d.a_rows = Mp; d.Cin = k.cm; d.n_pad = k.co; d.ntaps = 1; d.row_off[0] = 0;
       d.m_begin = 0; d.m_end = Mp; d.Cout = k.co;
       d.src = gs; d.dst_kind = (k.last && s < 4) ? DST_TO_PHASE : DST_SAME; d.dst = k.gout;
-      d.D = k.out; d.ldd = k.co; d.bias = k.b3; d.relu = 1;
-      d.res = k.ds ? R->dsbuf[s] : k.x; d.ld_res = k.co; d.res_rows = Mp;
+      d.D = k.out; d.ldd = k.co; d.relu = 1;
+      if (k.ds) {
+        // 1x1 (stride-2: phase plane (0,0) of the phase-split input = rows [0, Mp)) downsample conv on the block input
+        d.Wt = k.wds; d.bias = k.bds; d.A2 = k.x; d.a2_rows = Mp; d.Cin2 = k.ci;
+      } else {
+        d.Wt = k.w3; d.bias = k.b3; d.res = k.x; d.ld_res = k.co; d.res_rows = Mp;
+      }
+      set_out_bits(R, d, k.out_bits, k.co);
       if (int rc = add_op(R, R->fwd_ops, d)) return rc;
     }
+    k.x_bits = x_bits;
+    x_bits = k.out_bits;
     x = k.out;
   }
 
@@ -710,7 +752,7 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
       d.A = dout; d.a_rows = Mp; d.Cin = k.co; d.Wt = k.w3t; d.n_pad = k.cm; d.ntaps = 1; d.row_off[0] = 0;
       d.m_begin = 0; d.m_end = Mp; d.Cout = k.cm;
       d.src = gs; d.dst_kind = DST_SAME; d.dst = gs; d.D = R->dH2[s]; d.ldd = k.cm;
-      d.mask = k.h2; d.ld_mask = k.cm;
+      set_mask(R, d, k.h2, k.h2_bits, k.cm);
       if (int rc = add_op(R, R->bwd_ops, d)) return rc;
     }
     // c2 dgrad
@@ -720,7 +762,7 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
       for (int t = 0; t < 9; ++t) d.row_off[t] = k.w2t_off[0][t];
       d.m_begin = 0; d.m_end = Mp; d.Cout = k.cm;
       d.src = gs; d.dst_kind = DST_SAME; d.dst = gs; d.D = R->dH1[s]; d.ldd = k.cm;
-      d.mask = k.h1; d.ld_mask = k.cm;
+      set_mask(R, d, k.h1, k.h1_bits, k.cm);
       if (int rc = add_op(R, R->bwd_ops, d)) return rc;
     } else {
       for (int ph = 0; ph < 4; ++ph) {
@@ -729,35 +771,28 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
         for (int t = 0; t < d.ntaps; ++t) d.row_off[t] = k.w2t_off[ph][t];
         d.m_begin = (long)ph * Mp; d.m_end = (long)(ph + 1) * Mp; d.Cout = k.cm;
         d.src = k.gx; d.dst_kind = DST_SAME; d.dst = k.gx; d.D = R->dH1[s]; d.ldd = k.cm;
-        d.mask = k.h1; d.ld_mask = k.cm;
+        set_mask(R, d, k.h1, k.h1_bits, k.cm);
         if (int rc = add_op(R, R->bwd_ops, d)) return rc;
       }
     }
-    // downsample dgrad
-    if (k.ds) {
-      GemmDesc d = base_desc();
-      d.A = dout; d.a_rows = Mp; d.Cin = k.co; d.Wt = k.wdst; d.n_pad = k.ci; d.ntaps = 1; d.row_off[0] = 0;
-      d.m_begin = 0; d.m_end = Mp; d.Cout = k.ci;
-      d.src = gs; d.dst_kind = DST_SAME; d.dst = gs; d.D = R->gds[s]; d.ldd = k.ci;
-      if (int rc = add_op(R, R->bwd_ops, d)) return rc;
-    }
-    // c1 dgrad (+ skip / downsample gradient, * ReLU mask of the block input)
+    // c1 dgrad (+ skip gradient as epilogue operand / downsample-branch gradient as second GEMM operand,
+    //           * ReLU mask of the block input)
     {
       GemmDesc d = base_desc();
-      d.A = R->dH1[s]; d.a_rows = k.gx.rows(); d.Cin = k.cm; d.Wt = k.w1t; d.n_pad = k.ci; d.ntaps = 1; d.row_off[0] = 0;
+      d.A = R->dH1[s]; d.a_rows = k.gx.rows(); d.Cin = k.cm; d.n_pad = k.ci; d.ntaps = 1; d.row_off[0] = 0;
       d.m_begin = 0; d.m_end = k.gx.rows(); d.Cout = k.ci;
       d.src = k.gx;
-      if (k.ds) { d.res = R->gds[s]; d.ld_res = k.ci; d.res_rows = Mp; }
-      else { d.res = dout; d.ld_res = k.ci; d.res_rows = Mp; }
+      if (k.ds) { d.Wt = k.wdst; d.A2 = dout; d.a2_rows = Mp; d.Cin2 = k.co; }
+      else { d.Wt = k.w1t; d.res = dout; d.ld_res = k.ci; d.res_rows = Mp; }
       if (bi == 0) {
-        d.mask = nullptr;                      // block input = max-pool output (no ReLU of its own)
+        // block input = max-pool output (no ReLU of its own)
         d.dst_kind = DST_SAME; d.dst = gs; d.D = R->dOut[1][pp[1] ^ 1];   // = d(pool out)
         pp[1] ^= 1;
       } else if (k.stride2) {
-        d.mask = k.x; d.ld_mask = k.ci;
+        set_mask(R, d, k.x, k.x_bits, k.ci);
         d.dst_kind = DST_FROM_PHASE; d.dst = R->gS[s - 1]; d.D = R->dOut[s - 1][pp[s - 1]];
       } else {
-        d.mask = k.x; d.ld_mask = k.ci;
+        set_mask(R, d, k.x, k.x_bits, k.ci);
         d.dst_kind = DST_SAME; d.dst = gs; d.D = R->dOut[s][pp[s] ^ 1];
         pp[s] ^= 1;
       }
@@ -829,7 +864,7 @@ int rgie_regressor_backward(RgieRegressor* R, const float* dlogits, float* dimg,
   cudaStream_t st = (cudaStream_t)stream;
   RGIE_CHECK(R && dlogits && dimg, "rgie_regressor_backward: null argument");
   RGIE_CHECK(R->offsets != nullptr, "rgie_regressor_backward: call rgie_regressor_forward first");
-  const int N = R->N, H0 = R->H0;
+  const int N = R->N;
   const Block& last = R->blocks.back();
   const int H4 = R->Hs[4];
   fc_bwd_kernel<<<N, 256, 0, st>>>(dlogits, R->wfc, R->K, 2048, 1.0f / (float)(H4 * H4), R->dfeat);
@@ -848,9 +883,9 @@ int rgie_regressor_backward(RgieRegressor* R, const float* dlogits, float* dimg,
   // d(pool out) is the destination of the last block op (layer1.0 c1 dgrad)
   const void* dP = R->bwd_ops[nb - 2].d.D;
   if (R->dtype == 0)
-    maxpool_bwd_kernel<float><<<N * H0, 256, 0, st>>>((const float*)dP, R->arg, (const float*)R->c1, (float*)R->dC1, R->gS[1], R->gDY, H0, 64);
+    maxpool_bwd_kernel<float><<<N * R->Hs[1], 256, 0, st>>>((const float*)dP, R->arg, (float*)R->dC1, R->gS[1], R->gDY, 64);
   else
-    maxpool_bwd_kernel<__nv_bfloat16><<<N * H0, 256, 0, st>>>((const __nv_bfloat16*)dP, R->arg, (const __nv_bfloat16*)R->c1, (__nv_bfloat16*)R->dC1, R->gS[1], R->gDY, H0, 64);
+    maxpool_bwd_kernel<__nv_bfloat16><<<N * R->Hs[1], 256, 0, st>>>((const __nv_bfloat16*)dP, R->arg, (__nv_bfloat16*)R->dC1, R->gS[1], R->gDY, 64);
   RGIE_LAUNCH_OK();
   if (int rc = run_op(R, R->bwd_ops[nb - 1], st, R->fwd_ops.size() + nb - 1)) return rc;
   const long totg = (long)R->B * R->Hr * R->Wr;
@@ -891,7 +926,7 @@ int rgie_regressor_get_profile(RgieRegressor* R, float* h_ms, double* h_flops, i
     h_flops[i] = op_flops(op.d, useful);
     h_info[4 * i + 0] = fwd ? 0 : 1;
     h_info[4 * i + 1] = op.d.Cout;
-    h_info[4 * i + 2] = op.d.ntaps * op.d.Cin;
+    h_info[4 * i + 2] = op.d.ntaps * op.d.Cin + (op.d.A2 ? op.d.Cin2 : 0);
     h_info[4 * i + 3] = (int)((op.d.m_end - op.d.m_begin + 127) / 128);
   }
   *n_out = n;
@@ -938,13 +973,15 @@ int rgie_regressor_tap(RgieRegressor* R, const char* name, float* out, long capa
   return 0;
 }
 
-int rgie_gemm_selftest(int backend, const void* A, long a_rows, int Cin, const void* W, int n_pad, int ntaps,
-                       const long* h_row_off, long m_begin, long m_end, int Cout, const float* bias, const void* res,
-                       int relu, void* D, int d_fp32, void* stream) {
+int rgie_gemm_selftest_ex(int backend, const void* A, long a_rows, int Cin, const void* A2, long a2_rows, int Cin2,
+                          const void* W, int n_pad, int ntaps, const long* h_row_off, long m_begin, long m_end, int Cout,
+                          const float* bias, const void* res, const unsigned* mask_bits, int relu, void* D, int d_fp32,
+                          unsigned* D_bits, void* stream) {
   RGIE_CHECK(ntaps >= 1 && ntaps <= kMaxTaps, "rgie_gemm_selftest: ntaps");
   GemmDesc d;
   memset(&d, 0, sizeof(d));
   d.A = A; d.a_rows = a_rows; d.Cin = Cin; d.Wt = W; d.n_pad = n_pad; d.ntaps = ntaps;
+  d.A2 = A2; d.a2_rows = a2_rows; d.Cin2 = Cin2;
   for (int t = 0; t < ntaps; ++t) d.row_off[t] = h_row_off[t];
   d.m_begin = m_begin; d.m_end = m_end; d.Cout = Cout;
   // trivial geometry: one "image" of (m_end) x 1 pixels, nothing is padding
@@ -952,8 +989,16 @@ int rgie_gemm_selftest(int backend, const void* A, long a_rows, int Cin, const v
   d.dst_kind = DST_SAME; d.dst = d.src;
   d.D = D; d.ldd = Cout; d.d_fp32 = d_fp32; d.bias = bias;
   d.res = res; d.ld_res = Cout; d.res_rows = m_end; d.relu = relu;
+  d.mask_bits = mask_bits; d.ld_mb = Cout / 32; d.D_bits = D_bits; d.ld_db = Cout / 32;
   if (backend == 1) return launch_gemm_sm100(d, (cudaStream_t)stream);
   return launch_gemm_simt(d, 1, (cudaStream_t)stream);
+}
+
+int rgie_gemm_selftest(int backend, const void* A, long a_rows, int Cin, const void* W, int n_pad, int ntaps,
+                       const long* h_row_off, long m_begin, long m_end, int Cout, const float* bias, const void* res,
+                       int relu, void* D, int d_fp32, void* stream) {
+  return rgie_gemm_selftest_ex(backend, A, a_rows, Cin, nullptr, 0, 0, W, n_pad, ntaps, h_row_off, m_begin, m_end, Cout, bias,
+                               res, nullptr, relu, D, d_fp32, nullptr, stream);
 }
 
 }  // extern "C"

@@ -79,3 +79,83 @@ def test_tcgen05_vs_reference(case):
     print(f"max|simt-ref|={err_simt:.3e} max|tcgen05-ref|={err_tc:.3e} max|ref|={ref.abs().max().item():.3f}")
     assert err_simt < tol, f"CUDA-core backend off by {err_simt}"
     assert err_tc < tol, f"tcgen05 backend off by {err_tc}"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# second operand (K-concatenated downsample branch), 1-bit ReLU masks, sign-bit outputs, residual ring
+# ---------------------------------------------------------------------------------------------------------------
+def _run_ex(backend, A, A2, a2_rows, W, offs, m_end, Cin, Cin2, Cout, bias, res, mask_bits, relu, want_bits):
+    from regressor_guided_image_editing_b200 import _lib
+    from regressor_guided_image_editing_b200._lib import ptr, stream_ptr, check
+    lib = _lib.load()
+    D = torch.zeros(m_end, Cout, device=A.device, dtype=torch.bfloat16)
+    Db = torch.zeros((m_end + 31) // 32 * 32 * (Cout // 32), device=A.device, dtype=torch.int32) if want_bits else None
+    offs_c = (C.c_long * len(offs))(*offs)
+    check(lib.rgie_gemm_selftest_ex(backend, ptr(A), A.shape[0], Cin, ptr(A2), a2_rows, Cin2, ptr(W), W.shape[0], len(offs),
+                                    offs_c, 0, m_end, Cout, ptr(bias), ptr(res), ptr(mask_bits), int(relu), ptr(D), 0,
+                                    ptr(Db), stream_ptr(A.device)), "gemm_selftest_ex")
+    torch.cuda.synchronize()
+    return D.float(), Db
+
+
+def _blocked_index(rows, words, dev):
+    """common.cuh: bits_index(m, w, words) = ((m >> 5) * words + w) * 32 + (m & 31)."""
+    m = torch.arange(rows, device=dev)[:, None]
+    w = torch.arange(words, device=dev)[None, :]
+    return ((m >> 5) * words + w) * 32 + (m & 31)
+
+
+def _unpack_bits(flat, rows, ncols):
+    words = flat.to(torch.int64)[_blocked_index(rows, ncols // 32, flat.device)] & 0xFFFFFFFF
+    sh = torch.arange(32, device=flat.device)
+    return ((words[:, :, None] >> sh) & 1).reshape(rows, -1).bool()
+
+
+def _pack_bits(keep):
+    rows, ncols = keep.shape
+    sh = torch.arange(32, device=keep.device, dtype=torch.int64)
+    words = (keep.reshape(rows, ncols // 32, 32).to(torch.int64) << sh).sum(-1)
+    words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
+    flat = torch.zeros((rows + 31) // 32 * 32 * (ncols // 32), device=keep.device, dtype=torch.int32)
+    flat[_blocked_index(rows, ncols // 32, keep.device).flatten()] = words.flatten()
+    return flat.contiguous()
+
+
+EX_CASES = [
+    # (rows, Cin, Cin2, a2_rows, Cout, offs, res, mask, out_bits)
+    (9000, 64, 64, 9000, 256, [0], False, False, True),          # layer1.0 conv3 + downsample
+    (5000, 128, 256, 1250, 256, [0], False, True, False),        # stride-2 conv1 dgrad: A2 covers plane 0 only
+    (4096, 512, 1024, 4000, 2048, [0], False, False, True),
+    (7000, 64, 0, 0, 256, [0], True, True, True),                # residual ring + bits, single k-block tiles
+    (40000, 256, 0, 0, 1024, [0], True, False, True),            # residual ring, many tiles per CTA
+    (3000, 64, 0, 0, 64, [-59, -58, -57, -1, 0, 1, 57, 58, 59], False, True, True),
+    (6000, 512, 0, 0, 128, [0], False, True, True),
+]
+
+
+@pytest.mark.parametrize("case", EX_CASES, ids=[f"r{c[0]}_k{c[1]}+{c[2]}_n{c[4]}_t{len(c[5])}" for c in EX_CASES])
+def test_second_operand_and_bit_masks(case):
+    rows, Cin, Cin2, a2_rows, Cout, offs, use_res, use_mask, want_bits = case
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(7 * rows + Cin + Cout)
+    K = len(offs) * Cin + Cin2
+    A = (torch.randn(rows, Cin, generator=g) * 0.5).to(dev).bfloat16().contiguous()
+    A2 = (torch.randn(max(a2_rows, 1), max(Cin2, 1), generator=g) * 0.5).to(dev).bfloat16().contiguous() if Cin2 else None
+    W = (torch.randn(Cout, K, generator=g) / K ** 0.5).to(dev).bfloat16().contiguous()
+    bias = (torch.randn(Cout, generator=g) * 0.1).to(dev)
+    res = torch.randn(rows, Cout, generator=g).to(dev).bfloat16().contiguous() if use_res else None
+    keep = (torch.rand(rows, Cout, generator=g) > 0.4).to(dev) if use_mask else None
+    mbits = _pack_bits(keep) if use_mask else None
+    ref = _ref(A, W[:, :len(offs) * Cin].contiguous(), offs, 0, rows, Cin, bias, res, False)
+    if Cin2:
+        ref[:a2_rows] += A2.float()[:a2_rows] @ W.float()[:, len(offs) * Cin:].T
+    ref = ref.relu()
+    if use_mask:
+        ref = ref * keep
+    for backend in (0, 1):
+        out, bits = _run_ex(backend, A, A2, a2_rows, W, offs, rows, Cin, Cin2, Cout, bias, res, mbits, True, want_bits)
+        err = (out - ref).abs().max().item()
+        assert err < 2e-2, f"backend {backend} off by {err}"
+        if want_bits:
+            got = _unpack_bits(bits, rows, Cout)
+            assert torch.equal(got, out > 0), f"backend {backend}: sign bits differ from the stored values"

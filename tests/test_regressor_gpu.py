@@ -150,6 +150,9 @@ def test_regressor_golden(sd, golden_dir):
         gd = dimg.cpu()[0, :, ::8, ::8]
         gerr = (gd - g["grad_ds"]).abs().max().item() / g["grad_max"].item()
         serr = abs(dimg.abs().sum().item() - g["grad_abs_sum"].item()) / g["grad_abs_sum"].item()
-        print(tag, f"grad: max-rel {gerr:.3e}, abs-sum rel {serr:.3e}")
-        assert gerr <= 2e-2 and serr <= 5e-3
+        merr = (gd - g["grad_ds"]).abs().mean().item() / g["grad_ds"].abs().mean().item()
+        print(tag, f"grad: max-rel {gerr:.3e}, mean-rel {merr:.3e}, abs-sum rel {serr:.3e}")
+        # isolated pixels sit on ReLU / max-pool kinks whose side is decided by fp32 round-off (accumulation order):
+        # the max over the sampled pixels is bounded loosely, the mean and the |.|-sum tightly
+        assert gerr <= 5e-2 and merr <= 2e-3 and serr <= 5e-3
         del reg
