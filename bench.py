@@ -222,7 +222,8 @@ def main():
         lib.rgie_regressor_set_profiling(eng.reg._h, 1)
         nops = lib.rgie_regressor_num_ops(eng.reg._h)
         tot_ms, tot_fl, table = 0.0, 0.0, None
-        reps_prof = 2
+        reps_prof = int(os.environ.get("RGIE_PROF_REPS", "4"))
+        per_rep = []
         for r in range(reps_prof):
             eng.counter.fill_(min(done, eng.steps - 1))
             eng._step()
@@ -232,9 +233,12 @@ def main():
             # the profile holds the LAST micro-batch of the step; all micro-batches are identical in shape
             tot_ms += sum(ms_a) * (B // eng.mb)
             tot_fl += sum(fl_a) * (B // eng.mb)
-            table = [{"dir": "fwd" if info[4 * i] == 0 else "bwd", "N": info[4 * i + 1], "K": info[4 * i + 2],
-                      "m_tiles": info[4 * i + 3], "ms": ms_a[i], "tflops": fl_a[i] / max(ms_a[i], 1e-9) / 1e9}
-                     for i in range(n.value)]
+            per_rep.append(list(ms_a))
+        med = [sorted(x)[len(x) // 2] for x in zip(*per_rep)]
+        mn = [min(x) for x in zip(*per_rep)]
+        table = [{"dir": "fwd" if info[4 * i] == 0 else "bwd", "N": info[4 * i + 1], "K": info[4 * i + 2],
+                  "m_tiles": info[4 * i + 3], "ms": med[i], "ms_min": mn[i], "tflops": fl_a[i] / max(med[i], 1e-9) / 1e9}
+                 for i in range(n.value)]
         lib.rgie_regressor_set_profiling(eng.reg._h, 0)
         gemm_ms_per_step = tot_ms / reps_prof
         peaks, which = _peaks()

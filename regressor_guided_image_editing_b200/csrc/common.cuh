@@ -44,6 +44,32 @@ static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 // creation and the epilogues never write pad rows), which is what turns a 3x3 convolution into nine row-shifted
 // GEMM operand loads.  planes == 4 is the 2x2 phase split (space-to-depth by parity) used around stride-2 convs.
 // ---------------------------------------------------------------------------------------------------------------
+// Division of a non-negative 31-bit integer by a runtime constant: q = umulhi(n, mul) >> shift with
+// mul = ceil(2^(31 + ceil(log2 d)) / d) < 2^32 (exact for every n < 2^31); d == 1 is flagged by mul == 0.
+// The epilogue decodes one pixel row per thread per tile; 64-bit hardware-emulated divisions there cost more
+// instructions than the rest of the epilogue.
+struct FastDiv {
+  uint32_t d, mul, shift;
+  __host__ __device__ uint32_t div(uint32_t n) const {
+#ifdef __CUDA_ARCH__
+    return mul ? (__umulhi(n, mul) >> shift) : n;
+#else
+    return mul ? (uint32_t)(((uint64_t)n * mul) >> 32) >> shift : n;
+#endif
+  }
+};
+static inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d; f.mul = 0; f.shift = 0;
+  if (d <= 1) return f;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;                    // ceil(log2 d) >= 1
+  const unsigned __int128 one = 1;
+  f.mul = (uint32_t)(((one << (31 + l)) + d - 1) / d);
+  f.shift = l - 1;
+  return f;
+}
+
 struct Geom {
   int planes;   // 1 or 4
   int n_img;
@@ -51,6 +77,7 @@ struct Geom {
   int pad_t, pad_l;
   int P;        // pitch in pixels
   int S;        // pixel rows per image per plane
+  FastDiv fd_plane, fd_S, fd_P;   // dividers by plane_rows(), S, P (plane_rows() < 2^31)
   __host__ __device__ long plane_rows() const { return (long)n_img * S; }
   __host__ __device__ long rows() const { return (long)planes * n_img * S; }
 };
@@ -60,6 +87,9 @@ static inline Geom make_geom(int planes, int n_img, int H, int W, int pad_t, int
   g.planes = planes; g.n_img = n_img; g.H = H; g.W = W; g.pad_t = pad_t; g.pad_l = pad_l;
   g.P = W + pad_l + pad_r;
   g.S = g.P * (H + pad_t + pad_b);
+  g.fd_plane = make_fastdiv((uint32_t)g.plane_rows());
+  g.fd_S = make_fastdiv((uint32_t)g.S);
+  g.fd_P = make_fastdiv((uint32_t)g.P);
   return g;
 }
 
@@ -72,15 +102,16 @@ enum DstKind : int {
 
 // decode row m of geometry g; returns false for pad rows
 __host__ __device__ inline bool geom_decode(const Geom& g, long m, int& plane, int& n, int& i, int& j) {
-  long pr = g.plane_rows();
-  plane = (int)(m / pr);
-  long mm = m - (long)plane * pr;
-  n = (int)(mm / g.S);
-  int rem = (int)(mm - (long)n * g.S);
-  int ri = rem / g.P;
+  // all row indices are < 2^31 (checked where the tensors are created)
+  const uint32_t mu = (uint32_t)m;
+  plane = g.planes == 1 ? 0 : (int)g.fd_plane.div(mu);
+  const uint32_t mm = mu - (uint32_t)plane * (uint32_t)g.plane_rows();
+  n = (int)g.fd_S.div(mm);
+  int rem = (int)(mm - (uint32_t)n * (uint32_t)g.S);
+  int ri = (int)g.fd_P.div((uint32_t)rem);
   i = ri - g.pad_t;
   j = rem - ri * g.P - g.pad_l;
-  return plane < g.planes && i >= 0 && i < g.H && j >= 0 && j < g.W;
+  return plane < g.planes && n < g.n_img && i >= 0 && i < g.H && j >= 0 && j < g.W;
 }
 
 __host__ __device__ inline long geom_row(const Geom& g, int plane, int n, int i, int j) {

@@ -22,7 +22,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;                 // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int NUM_THREADS = 320;          // TMA warp + MMA warp + 8 epilogue warps
+__host__ __device__ constexpr int num_threads(int new_warps) { return 64 + 32 * new_warps; }   // TMA warp + MMA warp + NEW epilogue warps
 constexpr int MAX_BIAS = 2048;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -51,6 +51,24 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+// TMA store (shared -> global, bulk async-group completion) and the fences / named barriers the store epilogue needs
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"((uint64_t)map), "r"(c0),
+               "r"(c1), "r"(src) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint32_t* r) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+__device__ __forceinline__ void lds128(uint32_t addr, uint32_t* r) {
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -125,47 +143,236 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t* r) {
   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
                "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
+// v AND (bit j of w ? all-ones : 0): signed 1-bit field extract gives 0 / -1 in one instruction
+__device__ __forceinline__ float keep_if_bit(float v, uint32_t w, int j) {
+  int m;
+  asm("bfe.s32 %0, %1, %2, 1;" : "=r"(m) : "r"(w), "r"(j));
+  return __uint_as_float(__float_as_uint(v) & (uint32_t)m);
+}
+// w = (w << 1) | (x > 0) for a NON-NEGATIVE float x (post-ReLU): x > 0 <=> bit pattern i >= 1 <=> sign bit of
+// i + 0x7FFFFFFF.  Pushing elements CH-1 .. 0 leaves the bit of element j at position j.  Exact, including x == 0
+// (about 1e-8 of all fp32 accumulators are exactly zero; measured by tests/test_gemm_gpu.py).
+__device__ __forceinline__ uint32_t push_positive_bit(uint32_t w, float x_nonneg) {
+  return __funnelshift_l(__float_as_uint(x_nonneg) + 0x7FFFFFFFu, w, 1);
+}
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
 __host__ __device__ constexpr int tmem_cols(int bn) { return 2 * bn <= 32 ? 32 : (2 * bn <= 64 ? 64 : (2 * bn <= 128 ? 128 : (2 * bn <= 256 ? 256 : 512))); }
 
-template <int BN, int STAGES>
+// EPI selects the epilogue: 0 = row-per-thread global accesses (any destination mapping, fp32 or bf16 output);
+// 1 = output tile staged in shared memory and written by TMA stores (DST_SAME bf16 outputs: every global write is a
+// full-line bulk transfer instead of 32 scattered sectors per warp instruction); 2 or 4 = 1 + the residual operand arrives
+// by TMA loads issued EPI chunks ahead (4 = a whole tile ahead).  Staging boxes are 128 rows x 32 columns (64-byte rows,
+// SWIZZLE_64B): per column half two output boxes and EPI residual boxes of 8 KB.
+constexpr int EPI_BOX_BYTES = BM * 32 * 2;
+template <int BN, int STAGES, int EPI>
 struct SmemLayout {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
-  static constexpr int BAR_OFF = B_OFF + STAGES * B_STAGE_BYTES;   // full[S], empty[S], tfull[2], tempty[2]
-  static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * STAGES + 4) * 8;
+  static constexpr int OB_OFF = B_OFF + STAGES * B_STAGE_BYTES;                 // [half][2] output boxes
+  static constexpr int RB_OFF = OB_OFF + (EPI >= 1 ? 4 * EPI_BOX_BYTES : 0);    // [half][EPI] residual boxes
+  static constexpr int BAR_OFF = RB_OFF + (EPI >= 2 ? 2 * EPI * EPI_BOX_BYTES : 0);   // full[S], empty[S], tfull[2], tempty[2], rfull[8]
+  static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * STAGES + 12) * 8;
   static constexpr int BIAS_OFF = TMEM_PTR_OFF + 16;                // whole bias vector (<= MAX_BIAS floats)
   static constexpr int TOTAL = BIAS_OFF + MAX_BIAS * 4;
   static constexpr int DYN_BYTES = TOTAL + 1024;   // + slack for manual 1024 B alignment
   static_assert(DYN_BYTES <= 232448, "shared memory plan exceeds 227 KB");
 };
 
-// ===================== epilogue role (8 warps; one TMEM lane = one output row per thread) =====================
-// warps 2..9: lane quarter q = warp & 3 (hardware restriction on tcgen05.ld), column half = (warp - 2) >> 2.
-// A thread walks the 32-column chunks of its row / column half, tile after tile.  Operands it has to read:
-//   residual (bf16 [m, n])   one register buffer per chunk position; the buffer is refilled with the SAME chunk of the
-//                            NEXT tile right after it has been consumed, so a whole tile's worth of residual (256 B per
-//                            thread, 64 KB per SM) is always in flight and its HBM latency is never exposed
-//   ReLU mask as bits        one 32-bit word per chunk, loaded one tile ahead (blocked layout: bits_index)
-//   ReLU mask as activations loaded at use (MiDU head only; the regressor uses bits)
-// All global accesses of activations are 256-bit (one full 32 B sector per thread per instruction).
-template <int BN>
-__device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sbias, const uint32_t tmem_base,
-                                              const uint32_t tfull0, const uint32_t tempty0, const int warp, const int lane,
-                                              const int num_tiles, const int num_n_tiles) {
-  constexpr int CH = BN >= 32 ? 32 : 16;
+// ===================== store epilogue (EPI 1 / 2): BN == 256, DST_SAME, bf16 output =====================
+// The 8 epilogue warps form two groups of 4 (column halves of 128); a group walks its 32-column chunks, tile after tile.
+// Per chunk: tcgen05.ld -> (+bias, +residual from the TMA-loaded box, ReLU, bit mask; pad rows and rows >= m_end forced
+// to 0) -> bf16 -> st.shared into a swizzled 128x32 box -> one named barrier -> the group leader issues the TMA store of
+// that box and the TMA load of the residual box the group will need one tile later.  Pad rows receive zeros (they are
+// zero by construction), rows >= m_end are clipped by the tensor map.
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_store_role(const GemmDesc& d, const CUtensorMap* tmD, const CUtensorMap* tmR,
+                                                    const float* sbias, const uint32_t ob_smem, const uint32_t rb_smem,
+                                                    const uint32_t rfull0, const uint32_t tmem_base, const uint32_t tfull0,
+                                                    const uint32_t tempty0, const int warp, const int lane,
+                                                    const int num_tiles, const int num_n_tiles, const FastDiv fd_nt) {
+  constexpr int CH = 32;
+  constexpr int CPW = BN / 64;                     // chunks per group per tile
+  static_assert(CPW == 4, "the store epilogue is instantiated for BN = 256");
   auto tfull_bar = [&](int a) { return tfull0 + 8u * a; };
   auto tempty_bar = [&](int a) { return tempty0 + 8u * a; };
   const int q = warp & 3;
   const int half = (warp - 2) >> 2;
   const int row = q * 32 + lane;
+  const int c_begin = half * CPW;
+  const bool leader = (warp == 2 + 4 * half) && lane == 0;
+  constexpr int NRB = EPI >= 2 ? EPI : 1;          // residual boxes per group (power of two)
+  const bool has_res = EPI >= 2 && d.res != nullptr;
+  const bool has_bias = d.bias != nullptr;
+  const uint32_t* mbits = d.mask_bits;
+  // this thread's 64-byte row inside a box: 16-byte piece j lives at piece (j ^ ((row >> 1) & 3))  (SWIZZLE_64B)
+  const uint32_t row_off = (uint32_t)row * 64u;
+  const uint32_t swz = (uint32_t)((row >> 1) & 3);
+  auto ob_addr = [&](int b) { return ob_smem + (uint32_t)((half * 2 + b) * EPI_BOX_BYTES); };
+  auto rb_addr = [&](int b) { return rb_smem + (uint32_t)((half * NRB + b) * EPI_BOX_BYTES); };
+  auto rfull_bar = [&](int b) { return rfull0 + 8u * (half * NRB + b); };
+
+  // residual boxes: chunk sequence s = it * CPW + ci uses box s % NRB and is loaded NRB chunks ahead
+  int p_tile = blockIdx.x, p_ci = 0, p_s = 0;
+  auto res_issue = [&]() {        // leader only
+    if (p_tile < num_tiles) {
+      const int mt = (int)fd_nt.div((uint32_t)p_tile), nt = p_tile - mt * num_n_tiles;
+      const int b = p_s & (NRB - 1);
+      mbar_expect_tx(rfull_bar(b), EPI_BOX_BYTES);
+      tma_load_2d(rb_addr(b), tmR, nt * BN + (c_begin + p_ci) * CH, (int)(d.m_begin + (long)mt * BM), rfull_bar(b));
+    }
+    ++p_s;
+    if (++p_ci == CPW) { p_ci = 0; p_tile += gridDim.x; }
+  };
+  if (has_res && leader) {
+#pragma unroll
+    for (int i = 0; i < NRB; ++i) res_issue();
+  }
+
+  uint32_t bits_nxt[CPW];
+  auto bits_fetch = [&](int tile) {
+#pragma unroll
+    for (int i = 0; i < CPW; ++i) bits_nxt[i] = 0u;
+    if (mbits != nullptr && tile < num_tiles) {
+      const int mt = (int)fd_nt.div((uint32_t)tile), nt = tile - mt * num_n_tiles;
+      const long m = d.m_begin + (long)mt * BM + row;
+      if (m < d.m_end) {
+        const int w0 = (nt * BN) / 32 + c_begin;
+#pragma unroll
+        for (int i = 0; i < CPW; ++i) bits_nxt[i] = __ldg(mbits + bits_index(m, w0 + i, d.ld_mb));
+      }
+    }
+  };
+  bits_fetch(blockIdx.x);
+
+  int it = 0, s = 0;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    const int mt = (int)fd_nt.div((uint32_t)tile), nt = tile - mt * num_n_tiles;
+    const int acc = it & 1;
+    const uint32_t acc_phase = (it >> 1) & 1;
+    const long m0 = d.m_begin + (long)mt * BM;
+    const long m = m0 + row;
+    long dest = -1;
+    if (m < d.m_end) dest = map_row(d.src, d.dst_kind, d.dst, m);
+    const bool live = dest >= 0;
+    const bool use_res = has_res && live && m < d.res_rows;
+    uint32_t bits_cur[CPW], bits_out[CPW];
+#pragma unroll
+    for (int i = 0; i < CPW; ++i) { bits_cur[i] = bits_nxt[i]; bits_out[i] = 0u; }
+    bits_fetch(tile + gridDim.x);
+    mbar_wait(tfull_bar(acc), acc_phase);
+    tcgen05_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+    uint32_t racc[2][CH];
+    tmem_ld<CH>(taddr + (uint32_t)(c_begin * CH), racc[0]);
+#pragma unroll
+    for (int ci = 0; ci < CPW; ++ci, ++s) {
+      const int c = c_begin + ci;
+      const int b = s & 1;
+      tmem_ld_wait();
+      if (ci + 1 < CPW) tmem_ld<CH>(taddr + (uint32_t)((c + 1) * CH), racc[(ci + 1) & 1]);   // in flight during this chunk
+      const uint32_t* r = racc[ci & 1];
+      const int n0 = nt * BN + c * CH;
+      float v[CH];
+#pragma unroll
+      for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
+      if (has_res) {
+        const int rb = s & (NRB - 1);
+        mbar_wait(rfull_bar(rb), (uint32_t)((s / NRB) & 1));
+        if (use_res) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t w4[4];
+            lds128(rb_addr(rb) + row_off + (((uint32_t)j ^ swz) << 4), w4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { v[8 * j + 2 * e] += bf16_lo(w4[e]); v[8 * j + 2 * e + 1] += bf16_hi(w4[e]); }
+          }
+        }
+      }
+      if (has_bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(sbias + n0);
+#pragma unroll
+        for (int j = 0; j < CH / 4; ++j) {
+          const float4 bb = b4[j];
+          v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+        }
+      }
+      uint32_t keep = live ? 0xFFFFFFFFu : 0u;     // pad rows / rows >= m_end store zeros
+      if (mbits != nullptr) keep &= bits_cur[ci];
+      if (d.relu) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
+        if (d.D_bits != nullptr) {
+          uint32_t w = 0u;
+#pragma unroll
+          for (int j = CH - 1; j >= 0; --j) w = push_positive_bit(w, v[j]);
+          bits_out[ci] = w & keep;
+        }
+      } else if (d.D_bits != nullptr) {
+        uint32_t w = 0u;
+#pragma unroll
+        for (int j = 0; j < CH; ++j) w |= (v[j] > 0.f ? 1u : 0u) << j;
+        bits_out[ci] = w & keep;
+      }
+      if (keep != 0xFFFFFFFFu) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] = keep_if_bit(v[j], keep, j);
+      }
+      uint32_t pk[CH / 2];
+#pragma unroll
+      for (int j = 0; j < CH / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+      // box b was handed to the TMA store two chunks ago; the barrier of the previous chunk (after the leader's
+      // wait_group.read) guarantees that store has finished reading it
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sts128(ob_addr(b) + row_off + (((uint32_t)j ^ swz) << 4), pk + 4 * j);
+      fence_async_smem();
+      if (leader) bulk_wait_read0();               // the store of the previous chunk (other box) has read its box
+      named_bar_sync(1 + half, 128);
+      if (leader) {
+        tma_store_2d(tmD, ob_addr(b), n0, (int)m0);
+        bulk_commit();
+        if (has_res) res_issue();                  // this chunk's residual box is free again: fetch the chunk NRB steps ahead
+      }
+    }
+    if (live && d.D_bits != nullptr) {
+      const int w0 = (nt * BN) / 32 + c_begin;
+#pragma unroll
+      for (int i = 0; i < CPW; ++i) d.D_bits[bits_index(dest, w0 + i, d.ld_db)] = bits_out[i];
+    }
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty_bar(acc));
+  }
+  if (leader) bulk_wait0();
+}
+
+// ===================== epilogue role (8 warps; one TMEM lane = one output row per thread) =====================
+// warps 2..9: lane quarter q = warp & 3 (hardware restriction on tcgen05.ld), column half = (warp - 2) >> 2.
+// A thread walks the 32-column chunks of its row / column half, tile after tile.  Operands it has to read:
+//   residual (bf16 [m, n])   two register buffers; a buffer is refilled with the chunk two positions ahead (crossing
+//                            into the next tile) right after it has been consumed, so the loads never wait for a tile
+//                            boundary
+//   accumulator (TMEM)       tcgen05.ld of chunk c+1 is in flight while chunk c is processed
+//   ReLU mask as bits        one 32-bit word per chunk, loaded one tile ahead (blocked layout: bits_index)
+//   ReLU mask as activations loaded at use (MiDU head only; the regressor uses bits)
+// All global accesses of activations are 256-bit (one full 32 B sector per thread per instruction).
+template <int BN, int NEW>
+__device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sbias, const uint32_t tmem_base,
+                                              const uint32_t tfull0, const uint32_t tempty0, const int warp, const int lane,
+                                              const int num_tiles, const int num_n_tiles, const FastDiv fd_nt) {
+  constexpr int NSPLIT = NEW / 4;                  // column parts: 4 warps (one per TMEM lane quarter) share a part
+  constexpr int CH = BN >= 32 ? 32 : 16;
+  auto tfull_bar = [&](int a) { return tfull0 + 8u * a; };
+  auto tempty_bar = [&](int a) { return tempty0 + 8u * a; };
+  const int q = warp & 3;
+  const int part = (warp - 2) >> 2;
+  const int row = q * 32 + lane;
   constexpr int NCH = BN / CH;                     // chunks per tile
-  constexpr int CPW = NCH >= 2 ? NCH / 2 : 1;      // chunks per warp
-  const int c_begin = NCH >= 2 ? half * CPW : 0;
-  const bool active = NCH >= 2 || half == 0;
+  constexpr int CPW = NCH >= NSPLIT ? NCH / NSPLIT : 1;      // chunks per warp
+  const int c_begin = part * CPW;
+  const bool active = c_begin < NCH;
   const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(d.res);
   const __nv_bfloat16* mask = reinterpret_cast<const __nv_bfloat16*>(d.mask);
   const uint32_t* mbits = d.mask_bits;
@@ -173,15 +380,18 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
   const long res_lim = d.res_rows < d.m_end ? d.res_rows : d.m_end;
 
   // operands of the NEXT tile (prefetched while the current one is processed)
-  uint32_t rbuf[CPW][CH / 2];                      // residual: CH bf16 per chunk
+  constexpr int NB = CPW >= 2 ? 2 : 1;             // residual buffers (chunk ci lives in buffer ci % NB; CPW is 1 or even)
+  uint32_t rbuf[NB][CH / 2];                       // residual: CH bf16 per chunk
   uint32_t bits_nxt[CPW];
-  const __nv_bfloat16* nres = nullptr;             // residual row of the tile being prefetched (null: nothing to read)
+  const __nv_bfloat16* nres = nullptr;             // residual row of the next tile (null: nothing to read)
+  const __nv_bfloat16* cres = nullptr;             // residual row of the current tile
   auto locate = [&](int tile) {
+    cres = nres;
     nres = nullptr;
 #pragma unroll
     for (int i = 0; i < CPW; ++i) bits_nxt[i] = 0u;
     if (tile < num_tiles && active) {
-      const int mt = tile / num_n_tiles, nt = tile - mt * num_n_tiles;
+      const int mt = (int)fd_nt.div((uint32_t)tile), nt = tile - mt * num_n_tiles;
       const long m = d.m_begin + (long)mt * BM + row;
       if (res != nullptr && m < res_lim) nres = res + m * d.ld_res + nt * BN + c_begin * CH;
       if (mbits != nullptr && m < d.m_end) {
@@ -191,19 +401,26 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
       }
     }
   };
-  auto res_fetch = [&](int ci) {
-    if (nres != nullptr) {
+  // fetch chunk position cj (>= CPW: chunk cj - CPW of the next tile) into its buffer
+  auto res_fetch = [&](int cj) {
+    const __nv_bfloat16* p = cj < CPW ? cres : nres;
+    const int cc = cj < CPW ? cj : cj - CPW;
+    if (p != nullptr) {
 #pragma unroll
-      for (int j = 0; j < CH / 16; ++j) ldg256(nres + ci * CH + j * 16, rbuf[ci] + 8 * j);
+      for (int j = 0; j < CH / 16; ++j) ldg256(p + cc * CH + j * 16, rbuf[cj % NB] + 8 * j);
     }
   };
-  locate(blockIdx.x);
+  locate(blockIdx.x);      // nres = first tile
+  {
+    const __nv_bfloat16* first = nres;
+    cres = first;
 #pragma unroll
-  for (int ci = 0; ci < CPW; ++ci) res_fetch(ci);
+    for (int cj = 0; cj < NB; ++cj) res_fetch(cj);
+  }
 
   int it = 0;
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-    const int mt = tile / num_n_tiles, nt = tile - mt * num_n_tiles;
+    const int mt = (int)fd_nt.div((uint32_t)tile), nt = tile - mt * num_n_tiles;
     const int acc = it & 1;
     const uint32_t acc_phase = (it >> 1) & 1;
     const long m = d.m_begin + (long)mt * BM + row;
@@ -216,26 +433,28 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
     uint32_t bits_cur[CPW], bits_out[CPW];
 #pragma unroll
     for (int i = 0; i < CPW; ++i) { bits_cur[i] = bits_nxt[i]; bits_out[i] = 0u; }
-    locate(tile + gridDim.x);                      // pointers / mask words of the next tile
+    locate(tile + gridDim.x);                      // cres = this tile, nres / mask words = next tile
     mbar_wait(tfull_bar(acc), acc_phase);
     tcgen05_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
     if (active) {
+      uint32_t racc[2][CH];
+      tmem_ld<CH>(taddr + (uint32_t)(c_begin * CH), racc[0]);
 #pragma unroll
       for (int ci = 0; ci < CPW; ++ci) {
         const int c = c_begin + ci;
-        uint32_t r[CH];
-        tmem_ld<CH>(taddr + (uint32_t)(c * CH), r);
         tmem_ld_wait();
+        if (ci + 1 < CPW) tmem_ld<CH>(taddr + (uint32_t)((c + 1) * CH), racc[(ci + 1) & 1]);
+        const uint32_t* r = racc[ci & 1];
         const int n0 = nt * BN + c * CH;
         float v[CH];
 #pragma unroll
         for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
         if (use_res) {
 #pragma unroll
-          for (int j = 0; j < CH / 2; ++j) { v[2 * j] += bf16_lo(rbuf[ci][j]); v[2 * j + 1] += bf16_hi(rbuf[ci][j]); }
+          for (int j = 0; j < CH / 2; ++j) { v[2 * j] += bf16_lo(rbuf[ci % NB][j]); v[2 * j + 1] += bf16_hi(rbuf[ci % NB][j]); }
         }
-        res_fetch(ci);                             // refill this buffer with the same chunk of the next tile
+        res_fetch(ci + NB);                        // refill this buffer with the chunk NB positions ahead
         if (live) {
           if (has_bias) {
             const float4* b4 = reinterpret_cast<const float4*>(sbias + n0);
@@ -248,6 +467,17 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
           if (d.relu) {
 #pragma unroll
             for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
+            if (d.D_bits != nullptr) {
+              uint32_t w = 0u;
+#pragma unroll
+              for (int j = CH - 1; j >= 0; --j) w = push_positive_bit(w, v[j]);
+              bits_out[ci] = w;
+            }
+          } else if (d.D_bits != nullptr) {
+            uint32_t w = 0u;
+#pragma unroll
+            for (int j = 0; j < CH; ++j) w |= (v[j] > 0.f ? 1u : 0u) << j;
+            bits_out[ci] = w;
           }
           if (use_mask) {
 #pragma unroll
@@ -258,27 +488,21 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
               for (int j = 0; j < 8; ++j) {
                 // bf16 > 0  <=>  sign bit clear and magnitude non-zero
                 const uint32_t lo = k8[j] & 0xFFFFu, hi = k8[j] >> 16;
-                if (!(lo != 0 && lo < 0x8000u)) v[jj * 16 + 2 * j] = 0.f;
-                if (!(hi != 0 && hi < 0x8000u)) v[jj * 16 + 2 * j + 1] = 0.f;
+                if (!(lo != 0 && lo < 0x8000u)) { v[jj * 16 + 2 * j] = 0.f; bits_out[ci] &= ~(1u << (jj * 16 + 2 * j)); }
+                if (!(hi != 0 && hi < 0x8000u)) { v[jj * 16 + 2 * j + 1] = 0.f; bits_out[ci] &= ~(1u << (jj * 16 + 2 * j + 1)); }
               }
             }
           }
           if (mbits != nullptr) {
             const uint32_t w = bits_cur[ci];
+            bits_out[ci] &= w;
 #pragma unroll
-            for (int j = 0; j < CH; ++j)
-              if (!((w >> j) & 1u)) v[j] = 0.f;
+            for (int j = 0; j < CH; ++j) v[j] = keep_if_bit(v[j], w, j);
           }
           if (d.d_fp32) {
             float* o = reinterpret_cast<float*>(d.D) + dest * d.ldd + n0;
 #pragma unroll
             for (int j = 0; j < CH / 8; ++j) stg256(o + 8 * j, reinterpret_cast<const uint32_t*>(v) + 8 * j);
-            if (d.D_bits != nullptr) {
-              uint32_t w = 0u;
-#pragma unroll
-              for (int j = 0; j < CH; ++j) w |= (v[j] > 0.f ? 1u : 0u) << j;
-              bits_out[ci] = w;
-            }
           } else {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(d.D) + dest * d.ldd + n0;
             uint32_t pk[CH / 2];
@@ -286,17 +510,6 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
             for (int j = 0; j < CH / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
 #pragma unroll
             for (int j = 0; j < CH / 16; ++j) stg256(o + 16 * j, pk + 8 * j);
-            if (d.D_bits != nullptr) {
-              // sign bits of the STORED bf16 values (what a later (activation > 0) test would see): as signed 16-bit
-              // integers, bf16 > 0  <=>  halfword > 0
-              uint32_t w = 0u;
-#pragma unroll
-              for (int j = 0; j < CH / 2; ++j) {
-                const uint32_t g = __vcmpgts2(pk[j], 0u) & 0x00010001u;      // bit 0 / bit 16
-                w |= ((g | (g >> 15)) & 3u) << (2 * j);
-              }
-              bits_out[ci] = w;
-            }
           }
         }
       }
@@ -312,11 +525,13 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
   }
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BN, int STAGES, int EPI, int NEW>
+__global__ void __launch_bounds__(num_threads(NEW), 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                  const __grid_constant__ CUtensorMap tmB, const GemmDesc d, const int num_m_tiles, const int num_n_tiles) {
-  using L = SmemLayout<BN, STAGES>;
+                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
+                  const __grid_constant__ CUtensorMap tmR, const GemmDesc d, const int num_m_tiles, const int num_n_tiles,
+                  const FastDiv fd_nt) {
+  using L = SmemLayout<BN, STAGES, EPI>;
   constexpr uint32_t TMEM_COLS = tmem_cols(BN);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -326,6 +541,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  auto rfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 4 + a); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_PTR_OFF);
 
   const int warp = threadIdx.x >> 5;
@@ -345,7 +561,12 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);     // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), NEW);   // one arrive per epilogue warp
+    }
+    for (int a = 0; a < 8; ++a) mbar_init(rfull_bar(a), 1);
+    if (EPI >= 1) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmD) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmR) : "memory");
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -356,7 +577,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   if (d.bias != nullptr) {
     float* sb = reinterpret_cast<float*>(smem + L::BIAS_OFF);
-    for (int i = threadIdx.x; i < d.Cout; i += NUM_THREADS) sb[i] = d.bias[i];
+    for (int i = threadIdx.x; i < d.Cout; i += num_threads(NEW)) sb[i] = d.bias[i];
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -369,7 +590,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / num_n_tiles, nt = tile - mt * num_n_tiles;
+        const int mt = (int)fd_nt.div((uint32_t)tile), nt = tile - mt * num_n_tiles;
         const long m0 = d.m_begin + (long)mt * BM;
         int tap = 0, cb = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -402,7 +623,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        const long m0 = d.m_begin + (long)(tile / num_n_tiles) * BM;
+        const long m0 = d.m_begin + (long)fd_nt.div((uint32_t)tile) * BM;
         const int kb_total = num_kb + (m0 < d.a2_rows ? num_kb2 : 0);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tcgen05_fence_after();
@@ -423,9 +644,14 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         umma_commit(tfull_bar(acc));              // accumulator complete -> epilogue
       }
     }
+  } else if constexpr (EPI >= 1) {
+    static_assert(EPI == 0 || NEW == 8, "the store epilogue runs with 8 epilogue warps");
+    epilogue_store_role<BN, EPI>(d, &tmD, &tmR, reinterpret_cast<const float*>(smem + L::BIAS_OFF), smem_base + L::OB_OFF,
+                                 smem_base + L::RB_OFF, rfull_bar(0), tmem_base, tfull_bar(0), tempty_bar(0), warp, lane,
+                                 num_tiles, num_n_tiles, fd_nt);
   } else {
-    epilogue_role<BN>(d, reinterpret_cast<const float*>(smem + L::BIAS_OFF), tmem_base, tfull_bar(0), tempty_bar(0), warp, lane,
-                      num_tiles, num_n_tiles);
+    epilogue_role<BN, NEW>(d, reinterpret_cast<const float*>(smem + L::BIAS_OFF), tmem_base, tfull_bar(0), tempty_bar(0), warp,
+                           lane, num_tiles, num_n_tiles, fd_nt);
   }
 
   // ===================== teardown =====================
@@ -454,7 +680,8 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-int make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows) {
+int make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows,
+                CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_encodeTiled enc = get_encode_fn();
   RGIE_CHECK(enc != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
   cuuint64_t gdim[2] = {inner, rows};
@@ -462,23 +689,24 @@ int make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t row
   cuuint32_t box[2] = {box_inner, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
   return 0;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI, int NEW>
 int run_impl(const GemmPlanSm100& p, cudaStream_t st) {
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, STAGES, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
-    RGIE_CUDA_OK(cudaFuncSetAttribute(gemm_sm100_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RGIE_CUDA_OK(cudaFuncSetAttribute(gemm_sm100_kernel<BN, STAGES, EPI, NEW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       L::DYN_BYTES));
     attr_set = true;
   }
-  gemm_sm100_kernel<BN, STAGES><<<p.grid, NUM_THREADS, L::DYN_BYTES, st>>>(p.tmA, p.tmA2, p.tmB, p.d, p.num_m_tiles,
-                                                                                p.num_n_tiles);
+  gemm_sm100_kernel<BN, STAGES, EPI, NEW><<<p.grid, num_threads(NEW), L::DYN_BYTES, st>>>(p.tmA, p.tmA2, p.tmB, p.tmD, p.tmR,
+                                                                                          p.d, p.num_m_tiles, p.num_n_tiles,
+                                                                                          make_fastdiv((uint32_t)p.num_n_tiles));
   RGIE_LAUNCH_OK();
   return 0;
 }
@@ -516,7 +744,32 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
   int sms = gemm_sm100_num_sms();
   p->grid = (int)(tiles < sms ? tiles : sms);
   if (p->grid < 1) p->grid = 1;
-  int rc = make_map_2d(&p->tmA, d.A, (uint64_t)d.Cin, (uint64_t)d.a_rows, BK, BM);
+  // epilogue variant (measured per shape class on B200, profiles/README.md): the TMA-store epilogue wins where the epilogue
+  // reads a residual AND a bit mask (conv1 input gradients of the identity blocks); everywhere else the row-per-thread
+  // epilogue is as fast or faster.  RGIE_GEMM_EPI = 0 / 1 / 2 / 4 forces a variant for A/B experiments.
+  static const int env_epi = getenv("RGIE_GEMM_EPI") ? atoi(getenv("RGIE_GEMM_EPI")) : -1;
+  const int ktot = d.ntaps * d.Cin + (d.A2 ? d.Cin2 : 0);
+  p->epi = env_epi == -16 ? -16 : 0;
+  if (bn == 256 && d.dst_kind == DST_SAME && !d.d_fp32 && d.mask == nullptr && env_epi != 0 && env_epi != -16) {
+    if (d.res != nullptr) {
+      if (env_epi == 2 || env_epi == 4) p->epi = env_epi;
+      else if (env_epi < 0 && d.mask_bits != nullptr) p->epi = 2;
+    } else if (env_epi >= 1 && ktot <= 768) {
+      p->epi = 1;
+    }
+  }
+  p->tmD = p->tmA; p->tmR = p->tmA;
+  int rc = 0;
+  if (p->epi >= 1) {
+    rc = make_map_2d(&p->tmD, d.D, (uint64_t)d.ldd, (uint64_t)d.m_end, 32, BM, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
+  if (p->epi >= 2) {
+    const long rr = d.res_rows < d.m_end ? d.res_rows : d.m_end;
+    rc = make_map_2d(&p->tmR, d.res, (uint64_t)d.ld_res, (uint64_t)rr, 32, BM, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
+  rc = make_map_2d(&p->tmA, d.A, (uint64_t)d.Cin, (uint64_t)d.a_rows, BK, BM);
   if (rc) return rc;
   if (d.A2 != nullptr) rc = make_map_2d(&p->tmA2, d.A2, (uint64_t)d.Cin2, (uint64_t)d.a2_rows, BK, BM);
   else p->tmA2 = p->tmA;
@@ -527,10 +780,17 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
 int run_gemm_sm100(const GemmPlanSm100& p, cudaStream_t st) {
   if (p.d.m_end <= p.d.m_begin) return 0;
   switch (p.bn) {
-    case 256: return run_impl<256, 4>(p, st);
-    case 128: return run_impl<128, 6>(p, st);
-    case 64: return run_impl<64, 8>(p, st);
-    case 16: return run_impl<16, 8>(p, st);
+    case 256:
+      switch (p.epi) {
+        case 4: return run_impl<256, 2, 4, 8>(p, st);
+        case 2: return run_impl<256, 3, 2, 8>(p, st);
+        case 1: return run_impl<256, 3, 1, 8>(p, st);
+        case -16: return run_impl<256, 4, 0, 16>(p, st);
+        default: return run_impl<256, 4, 0, 8>(p, st);
+      }
+    case 128: return run_impl<128, 6, 0, 8>(p, st);
+    case 64: return run_impl<64, 8, 0, 8>(p, st);
+    case 16: return run_impl<16, 8, 0, 8>(p, st);
   }
   return fail("gemm_sm100: unsupported N tile");
 }

@@ -7,6 +7,8 @@ namespace rgie {
 struct GemmPlanSm100 {
   GemmDesc d;
   CUtensorMap tmA, tmA2, tmB;      // A, optional second operand, weights
+  CUtensorMap tmD, tmR;            // output / residual boxes of the TMA-store epilogue (epi >= 1 / >= 2)
+  int epi;                          // epilogue variant (gemm_sm100.cu: SmemLayout)
   int bn;
   int num_m_tiles, num_n_tiles;
   int grid;
