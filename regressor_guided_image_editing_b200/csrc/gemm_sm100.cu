@@ -158,7 +158,9 @@ __device__ __forceinline__ uint32_t push_positive_bit(uint32_t w, float x_nonneg
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
-__host__ __device__ constexpr int tmem_cols(int bn) { return 2 * bn <= 32 ? 32 : (2 * bn <= 64 ? 64 : (2 * bn <= 128 ? 128 : (2 * bn <= 256 ? 256 : 512))); }
+__host__ __device__ constexpr int tmem_cols(int bn, int nacc = 2) {
+  return nacc * bn <= 32 ? 32 : (nacc * bn <= 64 ? 64 : (nacc * bn <= 128 ? 128 : (nacc * bn <= 256 ? 256 : 512)));
+}
 
 // EPI selects the epilogue: 0 = row-per-thread global accesses (any destination mapping, fp32 or bf16 output);
 // 1 = output tile staged in shared memory and written by TMA stores (DST_SAME bf16 outputs: every global write is a
@@ -179,6 +181,14 @@ struct SmemLayout {
   static constexpr int TOTAL = BIAS_OFF + MAX_BIAS * 4;
   static constexpr int DYN_BYTES = TOTAL + 1024;   // + slack for manual 1024 B alignment
   static_assert(DYN_BYTES <= 232448, "shared memory plan exceeds 227 KB");
+};
+
+// Tile -> pixel-row mapping of the epilogue.  Flat tiles (enabled == 0): tile mt covers rows m_begin + mt*128 + r.
+// Patch tiles (gemm_patch_kernel): tile mt = (ht, wt) covers the 16 x 8 pixel patch at line ht*16, column wt*8 of the
+// [lines, P] pixel grid; accumulator row r is pixel (r >> 3, r & 7) of the patch.
+struct PatchMap {
+  int enabled, P, WT;
+  FastDiv fd_wt;
 };
 
 // ===================== store epilogue (EPI 1 / 2): BN == 256, DST_SAME, bf16 output =====================
@@ -358,10 +368,15 @@ __device__ __forceinline__ void epilogue_store_role(const GemmDesc& d, const CUt
 //   ReLU mask as bits        one 32-bit word per chunk, loaded one tile ahead (blocked layout: bits_index)
 //   ReLU mask as activations loaded at use (MiDU head only; the regressor uses bits)
 // All global accesses of activations are 256-bit (one full 32 B sector per thread per instruction).
-template <int BN, int NEW>
+// TSPLIT = false: the NEW/4 warp groups split the COLUMNS of every tile (2 accumulator buffers).
+// TSPLIT = true : the warp groups take alternate TILES (all columns; NACC accumulator buffers, one arrive group per
+//                 buffer): with narrow N tiles the epilogue of a tile is a latency chain, not a throughput problem, so
+//                 two tiles in flight halve its cost.
+template <int BN, int NEW, bool TSPLIT = false, int NACC = 2>
 __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sbias, const uint32_t tmem_base,
                                               const uint32_t tfull0, const uint32_t tempty0, const int warp, const int lane,
-                                              const int num_tiles, const int num_n_tiles, const FastDiv fd_nt) {
+                                              const int num_tiles, const int num_n_tiles, const FastDiv fd_nt,
+                                              const PatchMap pm) {
   constexpr int NSPLIT = NEW / 4;                  // column parts: 4 warps (one per TMEM lane quarter) share a part
   constexpr int CH = BN >= 32 ? 32 : 16;
   auto tfull_bar = [&](int a) { return tfull0 + 8u * a; };
@@ -370,14 +385,25 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
   const int part = (warp - 2) >> 2;
   const int row = q * 32 + lane;
   constexpr int NCH = BN / CH;                     // chunks per tile
-  constexpr int CPW = NCH >= NSPLIT ? NCH / NSPLIT : 1;      // chunks per warp
-  const int c_begin = part * CPW;
+  constexpr int CSPLIT = TSPLIT ? 1 : NSPLIT;      // column parts
+  constexpr int TSTEP = TSPLIT ? NSPLIT : 1;       // tile stride between the tiles of one warp group
+  constexpr int CPW = NCH >= CSPLIT ? NCH / CSPLIT : 1;      // chunks per warp
+  const int c_begin = TSPLIT ? 0 : part * CPW;
   const bool active = c_begin < NCH;
+  const int tile0 = blockIdx.x + (TSPLIT ? part * (int)gridDim.x : 0);
+  const int tile_step = TSTEP * (int)gridDim.x;
   const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(d.res);
   const __nv_bfloat16* mask = reinterpret_cast<const __nv_bfloat16*>(d.mask);
   const uint32_t* mbits = d.mask_bits;
   const bool has_bias = d.bias != nullptr;
   const long res_lim = d.res_rows < d.m_end ? d.res_rows : d.m_end;
+  // pixel row of this thread in m-tile mt (d.m_end = not a row)
+  auto row_m = [&](int mt) -> long {
+    if (!pm.enabled) return d.m_begin + (long)mt * BM + row;
+    const int ht = (int)pm.fd_wt.div((uint32_t)mt), wt = mt - ht * pm.WT;
+    const int w = wt * 8 + (row & 7);
+    return w < pm.P ? (long)(ht * 16 + (row >> 3)) * pm.P + w : d.m_end;
+  };
 
   // operands of the NEXT tile (prefetched while the current one is processed)
   constexpr int NB = CPW >= 2 ? 2 : 1;             // residual buffers (chunk ci lives in buffer ci % NB; CPW is 1 or even)
@@ -392,7 +418,7 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
     for (int i = 0; i < CPW; ++i) bits_nxt[i] = 0u;
     if (tile < num_tiles && active) {
       const int mt = (int)fd_nt.div((uint32_t)tile), nt = tile - mt * num_n_tiles;
-      const long m = d.m_begin + (long)mt * BM + row;
+      const long m = row_m(mt);
       if (res != nullptr && m < res_lim) nres = res + m * d.ld_res + nt * BN + c_begin * CH;
       if (mbits != nullptr && m < d.m_end) {
         const int w0 = (nt * BN) / 32 + c_begin;
@@ -410,7 +436,7 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
       for (int j = 0; j < CH / 16; ++j) ldg256(p + cc * CH + j * 16, rbuf[cj % NB] + 8 * j);
     }
   };
-  locate(blockIdx.x);      // nres = first tile
+  locate(tile0);           // nres = first tile
   {
     const __nv_bfloat16* first = nres;
     cres = first;
@@ -418,12 +444,12 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
     for (int cj = 0; cj < NB; ++cj) res_fetch(cj);
   }
 
-  int it = 0;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+  int it = TSPLIT ? part : 0;                      // index of the tile in this CTA's sequence
+  for (int tile = tile0; tile < num_tiles; tile += tile_step, it += TSTEP) {
     const int mt = (int)fd_nt.div((uint32_t)tile), nt = tile - mt * num_n_tiles;
-    const int acc = it & 1;
-    const uint32_t acc_phase = (it >> 1) & 1;
-    const long m = d.m_begin + (long)mt * BM + row;
+    const int acc = it % NACC;
+    const uint32_t acc_phase = (it / NACC) & 1;
+    const long m = row_m(mt);
     long dest = -1;
     if (m < d.m_end) dest = map_row(d.src, d.dst_kind, d.dst, m);
     const bool live = active && dest >= 0;
@@ -433,7 +459,7 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
     uint32_t bits_cur[CPW], bits_out[CPW];
 #pragma unroll
     for (int i = 0; i < CPW; ++i) { bits_cur[i] = bits_nxt[i]; bits_out[i] = 0u; }
-    locate(tile + gridDim.x);                      // cres = this tile, nres / mask words = next tile
+    locate(tile + tile_step);                      // cres = this tile, nres / mask words = next tile
     mbar_wait(tfull_bar(acc), acc_phase);
     tcgen05_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
@@ -651,10 +677,169 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                  num_tiles, num_n_tiles, fd_nt);
   } else {
     epilogue_role<BN, NEW>(d, reinterpret_cast<const float*>(smem + L::BIAS_OFF), tmem_base, tfull_bar(0), tempty_bar(0), warp,
-                           lane, num_tiles, num_n_tiles, fd_nt);
+                           lane, num_tiles, num_n_tiles, fd_nt, PatchMap{0, 0, 0, FastDiv{1, 0, 0}});
   }
 
   // ===================== teardown =====================
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ===============================================================================================================
+// Patch-tile variant for the small-channel multi-tap convolutions (Cin = 64, Cout <= 64: conv1 forward / input
+// gradient, the 3x3 convs of layer1).  With flat 128-row tiles every tap re-loads its own 16 KB operand tile, and these
+// layers run at the L2->SM bandwidth ceiling (~42 B/clk/SM) instead of the tensor or HBM roofline.  Here
+//   * an output tile is a 16 x 8 pixel patch; for each horizontal tap dx ONE box of (16 + ny - 1) x 8 pixel rows is
+//     loaded (3-D TMA map [C, P, lines]; out-of-range columns / lines are zero-filled = conv padding) and serves all
+//     ny vertical taps: vertical tap yi is the same box read through a matrix descriptor that starts yi * 8 rows
+//     (= yi * 1024 B, a whole swizzle atom) further down;
+//   * the whole weight matrix (<= 72 KB) is loaded once per CTA and stays resident in shared memory.
+// Operand traffic per tile drops from ntaps * (16 KB + BN * 128 B) to nx * (18..19 KB).
+// ===============================================================================================================
+constexpr int PATCH_SLAB_H = 19;                               // 16 + up to 3 halo lines
+constexpr int PATCH_SLAB_BYTES = PATCH_SLAB_H * 8 * 128;       // 19456 (a multiple of 1024)
+constexpr int PATCH_SLABS = 6;
+constexpr int PATCH_W_BYTES = 72 * 1024;                       // resident weights: ntaps * BN * 128 B <= 72 KB
+struct PatchSmem {
+  static constexpr int A_OFF = 0;
+  static constexpr int W_OFF = PATCH_SLABS * PATCH_SLAB_BYTES;
+  static constexpr int BAR_OFF = W_OFF + PATCH_W_BYTES;        // afull[S], aempty[S], tfull[2], tempty[2], wfull
+  static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * PATCH_SLABS + 10) * 8;  // afull, aempty, tfull[4], tempty[4], wfull (+1: keeps BIAS_OFF 16-byte aligned)
+  static constexpr int BIAS_OFF = TMEM_PTR_OFF + 16;
+  static constexpr int TOTAL = BIAS_OFF + 64 * 4;
+  static constexpr int DYN_BYTES = TOTAL + 1024;
+};
+static_assert(PatchSmem::DYN_BYTES <= 232448, "patch kernel shared memory plan exceeds 227 KB");
+
+struct PatchTaps {
+  int ny, nx, dy0, dx0;          // taps (dy0 + yi, dx0 + xi)
+  int tap[4][4];                 // index of tap (yi, xi) in the weight matrix (column block), -1 = absent
+};
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(num_threads(8), 1)
+gemm_patch_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmB, const GemmDesc d,
+                  const PatchTaps tp, const PatchMap pm, const int num_tiles, const int dbg) {
+  using L = PatchSmem;
+  constexpr int NACC = 4;                         // accumulator buffers: two tiles in the epilogue, two in the tensor pipe
+  constexpr uint32_t TMEM_COLS = tmem_cols(BN, NACC);
+  constexpr int W_TAP_BYTES = BN * BK * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_base + L::BAR_OFF;
+  auto afull_bar = [&](int s) { return bar_base + 8u * s; };
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (PATCH_SLABS + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * PATCH_SLABS + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * PATCH_SLABS + NACC + a); };
+  const uint32_t wfull_bar = bar_base + 8u * (2 * PATCH_SLABS + 2 * NACC);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_PTR_OFF);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t slab_bytes = (uint32_t)((16 + tp.ny - 1) * 8 * 128);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA3) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+    for (int s = 0; s < PATCH_SLABS; ++s) {
+      mbar_init(afull_bar(s), 1);
+      mbar_init(aempty_bar(s), 1);
+    }
+    for (int a = 0; a < NACC; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);     // the 4 warps of the group that owns the tile
+    }
+    mbar_init(wfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_base + L::TMEM_PTR_OFF),
+                 "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (d.bias != nullptr) {
+    float* sb = reinterpret_cast<float*>(smem + L::BIAS_OFF);
+    for (int i = threadIdx.x; i < d.Cout; i += num_threads(8)) sb[i] = d.bias[i];
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer: resident weights once, then one box per (tile, horizontal tap) =====================
+    if (lane == 0) {
+      mbar_expect_tx(wfull_bar, (uint32_t)(d.ntaps * W_TAP_BYTES));
+      for (int t = 0; t < d.ntaps; ++t)
+        tma_load_2d(smem_base + L::W_OFF + t * W_TAP_BYTES, &tmB, t * BK, 0, wfull_bar);
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int ht = (int)pm.fd_wt.div((uint32_t)tile), wt = tile - ht * pm.WT;
+        for (int xi = 0; xi < tp.nx; ++xi) {
+          mbar_wait(aempty_bar(slot), phase ^ 1);
+          if (dbg & 2) { mbar_arrive(afull_bar(slot)); }
+          else {
+          mbar_expect_tx(afull_bar(slot), slab_bytes);
+          tma_load_3d(smem_base + L::A_OFF + slot * PATCH_SLAB_BYTES, &tmA3, 0, wt * 8 + tp.dx0 + xi, ht * 16 + tp.dy0,
+                      afull_bar(slot));
+          }
+          if (++slot == PATCH_SLABS) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      mbar_wait(wfull_bar, 0);
+      int slot = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it % NACC;
+        const uint32_t acc_phase = (it / NACC) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        uint32_t accum = 0u;
+        for (int xi = 0; xi < tp.nx; ++xi) {
+          mbar_wait(afull_bar(slot), phase);
+          tcgen05_fence_after();
+          const uint32_t slab = smem_base + L::A_OFF + slot * PATCH_SLAB_BYTES;
+          for (int yi = 0; yi < tp.ny; ++yi) {
+            const int t = tp.tap[yi][xi];
+            if (t < 0 || ((dbg & 1) && (xi | yi))) continue;
+            // vertical tap yi: the same box, yi pixel lines (= yi swizzle atoms of 8 rows x 128 B) further down
+            const uint64_t adesc = make_smem_desc(slab + (uint32_t)(yi * 1024));
+            const uint64_t bdesc = make_smem_desc(smem_base + L::W_OFF + t * W_TAP_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accum);
+              accum = 1u;
+            }
+          }
+          umma_commit(aempty_bar(slot));
+          if (++slot == PATCH_SLABS) { slot = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    epilogue_role<BN, 8, true, NACC>(d, reinterpret_cast<const float*>(smem + L::BIAS_OFF), tmem_base, tfull_bar(0),
+                                     tempty_bar(0), warp, lane, num_tiles, 1, FastDiv{1, 0, 0}, pm);
+  }
+
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -692,6 +877,40 @@ int make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t row
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+  return 0;
+}
+
+// A as [C = 64, P, lines] with a box of 8 pixels x box_lines lines (one 128-byte row per pixel, SWIZZLE_128B)
+int make_map_3d(CUtensorMap* map, const void* base, uint64_t P, uint64_t lines, uint32_t box_lines) {
+  PFN_encodeTiled enc = get_encode_fn();
+  RGIE_CHECK(enc != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
+  cuuint64_t gdim[3] = {64, P, lines};
+  cuuint64_t gstride[2] = {64 * 2, P * 64 * 2};
+  cuuint32_t box[3] = {64, 8, box_lines};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (3-D) failed with CUresult " + std::to_string((int)r));
+  return 0;
+}
+
+template <int BN>
+int run_patch(const GemmPlanSm100& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    RGIE_CUDA_OK(cudaFuncSetAttribute(gemm_patch_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, PatchSmem::DYN_BYTES));
+    attr_set = true;
+  }
+  PatchTaps tp;
+  tp.ny = p.patch_ny; tp.nx = p.patch_nx; tp.dy0 = p.patch_dy0; tp.dx0 = p.patch_dx0;
+  for (int y = 0; y < 4; ++y)
+    for (int x = 0; x < 4; ++x) tp.tap[y][x] = p.patch_tap[y][x];
+  PatchMap pm;
+  pm.enabled = 1; pm.P = p.d.src.P; pm.WT = p.patch_wt; pm.fd_wt = make_fastdiv((uint32_t)p.patch_wt);
+  static const int dbg = getenv("RGIE_PATCH_DEBUG") ? atoi(getenv("RGIE_PATCH_DEBUG")) : 0;
+  gemm_patch_kernel<BN><<<p.grid, num_threads(8), PatchSmem::DYN_BYTES, st>>>(p.tmA, p.tmB, p.d, tp, pm, p.num_m_tiles, dbg);
+  RGIE_LAUNCH_OK();
   return 0;
 }
 
@@ -737,6 +956,51 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
              "gemm_sm100: leading dimensions must be multiples of 16 elements (32-byte accesses)");
   p->d = d;
   p->bn = bn;
+  p->patch = 0;
+  // ---- patch-tile variant: Cin = 64, one N tile, single-plane source whose rows are whole pixel lines, taps on a
+  //      (dy, dx) grid of at most 4 x 4 with |dx| well below the pitch
+  //      MEASURED SLOWER than the flat kernel on B200 (3x3 layer1: 0.70 vs 0.52 ms, conv1 dgrad 4.2 vs 3.7 ms per 320 crops;
+  //      profiles/README.md): operand traffic was not the limiter of these layers.  Kept behind RGIE_GEMM_PATCH=1.
+  static const int env_patch = getenv("RGIE_GEMM_PATCH") ? atoi(getenv("RGIE_GEMM_PATCH")) : 0;
+  if (env_patch && d.Cin == 64 && bn <= 64 && d.Cout == bn && d.ntaps >= 3 && d.A2 == nullptr && d.src.planes == 1 &&
+      d.m_begin == 0 && d.m_end == d.a_rows && d.a_rows == d.src.rows() && d.src.P >= 16 && d.mask == nullptr) {
+    const int P = d.src.P;
+    int dy[kMaxTaps], dx[kMaxTaps], dymin = 1 << 30, dymax = -(1 << 30), dxmin = 1 << 30, dxmax = -(1 << 30);
+    for (int t = 0; t < d.ntaps; ++t) {
+      const long off = d.row_off[t];
+      long y = (off >= 0 ? off + P / 2 : off - P / 2) / P;     // nearest line
+      dy[t] = (int)y; dx[t] = (int)(off - y * P);
+      dymin = dy[t] < dymin ? dy[t] : dymin; dymax = dy[t] > dymax ? dy[t] : dymax;
+      dxmin = dx[t] < dxmin ? dx[t] : dxmin; dxmax = dx[t] > dxmax ? dx[t] : dxmax;
+    }
+    const int ny = dymax - dymin + 1, nx = dxmax - dxmin + 1;
+    if (ny <= 4 && nx <= 4 && dxmin >= -4 && dxmax <= 4 && (long)d.ntaps * bn * 128 <= PATCH_W_BYTES) {
+      for (int y = 0; y < 4; ++y)
+        for (int x = 0; x < 4; ++x) p->patch_tap[y][x] = -1;
+      bool ok = true;
+      for (int t = 0; t < d.ntaps; ++t) {
+        int& slot = p->patch_tap[dy[t] - dymin][dx[t] - dxmin];
+        if (slot >= 0) ok = false;
+        slot = t;
+      }
+      if (ok) {
+        p->patch = 1;
+        p->patch_ny = ny; p->patch_nx = nx; p->patch_dy0 = dymin; p->patch_dx0 = dxmin;
+        const long lines = d.a_rows / P;
+        p->patch_wt = (P + 7) / 8;
+        p->num_m_tiles = (int)(((lines + 15) / 16) * p->patch_wt);
+        p->num_n_tiles = 1;
+        int sms = gemm_sm100_num_sms();
+        p->grid = p->num_m_tiles < sms ? p->num_m_tiles : sms;
+        p->epi = 0;
+        p->tmA2 = p->tmA; p->tmD = p->tmA; p->tmR = p->tmA;
+        int rc = make_map_3d(&p->tmA, d.A, (uint64_t)P, (uint64_t)lines, (uint32_t)(16 + ny - 1));
+        if (rc) return rc;
+        p->tmA2 = p->tmA; p->tmD = p->tmA; p->tmR = p->tmA;
+        return make_map_2d(&p->tmB, d.Wt, (uint64_t)d.ntaps * d.Cin, (uint64_t)d.n_pad, BK, (uint32_t)bn);
+      }
+    }
+  }
   long M = d.m_end - d.m_begin;
   p->num_m_tiles = ceil_div(M, BM);
   p->num_n_tiles = d.Cout / bn;
@@ -779,6 +1043,7 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
 
 int run_gemm_sm100(const GemmPlanSm100& p, cudaStream_t st) {
   if (p.d.m_end <= p.d.m_begin) return 0;
+  if (p.patch) return p.bn == 64 ? run_patch<64>(p, st) : run_patch<16>(p, st);
   switch (p.bn) {
     case 256:
       switch (p.epi) {

@@ -10,6 +10,8 @@ struct GemmPlanSm100 {
   CUtensorMap tmD, tmR;            // output / residual boxes of the TMA-store epilogue (epi >= 1 / >= 2)
   int epi;                          // epilogue variant (gemm_sm100.cu: SmemLayout)
   int bn;
+  // patch-tile variant (gemm_sm100.cu: gemm_patch_kernel): taps on a (dy, dx) grid, 16 x 8 pixel output tiles
+  int patch, patch_ny, patch_nx, patch_dy0, patch_dx0, patch_wt, patch_tap[4][4];
   int num_m_tiles, num_n_tiles;
   int grid;
 };

@@ -504,8 +504,10 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
   R->gZZ = make_geom(1, N, H0, H0, 2, 1, 0, 0);
   R->gDY = make_geom(1, N, H0, H0, 1, 2, 1, 2);
   for (int s = 1; s <= 4; ++s) {
-    R->gS[s] = make_geom(1, N, R->Hs[s], R->Hs[s], 1, 1, 1, 1);
-    R->gPh[s] = make_geom(4, N, R->Hs[s], R->Hs[s], 1, 1, 1, 1);
+    // one zero pad line above and one zero pad column left of every image: the pad line of the NEXT image (or the TMA
+    // out-of-range fill after the last one) is the bottom padding, the pad column of the next line the right padding
+    R->gS[s] = make_geom(1, N, R->Hs[s], R->Hs[s], 1, 0, 1, 0);
+    R->gPh[s] = make_geom(4, N, R->Hs[s], R->Hs[s], 1, 0, 1, 0);
   }
   const int esz = R->esz;
 
