@@ -152,6 +152,8 @@ def main():
         Wc = min(W, 1)
         val, sec, K = cpu_reference_leg(K, Wc, H, H, threads, budget)
         W = Wc
+        config = dict(config, precision="fp32 (torch CPU)", micro_batch=1,
+                      parallelism=f"{threads} host threads, one image at a time (the reference's own loop)")
         line = {"metric": "edited images/sec (100 steps, 512^2)", "value": val, "unit": "images/s", "n_gpus": args.gpus,
                 "steps": K, "warmup": W, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference", "config": config,
@@ -228,27 +230,50 @@ def main():
             eng.counter.fill_(min(done, eng.steps - 1))
             eng._step()
             torch.cuda.synchronize(dev)
-            ms_a = (C.c_float * nops)(); fl_a = (C.c_double * nops)(); info = (C.c_int * (4 * nops))(); n = C.c_int(0)
-            _lib.check(lib.rgie_regressor_get_profile(eng.reg._h, ms_a, fl_a, info, nops, C.byref(n)))
+            ms_a = (C.c_float * nops)(); fl_a = (C.c_double * nops)(); by_a = (C.c_double * nops)()
+            info = (C.c_int * (4 * nops))(); n = C.c_int(0)
+            _lib.check(lib.rgie_regressor_get_profile(eng.reg._h, ms_a, fl_a, by_a, info, nops, C.byref(n)))
             # the profile holds the LAST micro-batch of the step; all micro-batches are identical in shape
             tot_ms += sum(ms_a) * (B // eng.mb)
             tot_fl += sum(fl_a) * (B // eng.mb)
+            tot_by = sum(by_a) * (B // eng.mb)
             per_rep.append(list(ms_a))
         med = [sorted(x)[len(x) // 2] for x in zip(*per_rep)]
         mn = [min(x) for x in zip(*per_rep)]
         table = [{"dir": "fwd" if info[4 * i] == 0 else "bwd", "N": info[4 * i + 1], "K": info[4 * i + 2],
-                  "m_tiles": info[4 * i + 3], "ms": med[i], "ms_min": mn[i], "tflops": fl_a[i] / max(med[i], 1e-9) / 1e9}
+                  "m_tiles": info[4 * i + 3], "ms": med[i], "ms_min": mn[i], "tflops": fl_a[i] / max(med[i], 1e-9) / 1e9,
+                  "algorithmic_GB": by_a[i] / 1e9, "algorithmic_GBs": by_a[i] / max(med[i], 1e-9) / 1e6}
                  for i in range(n.value)]
         lib.rgie_regressor_set_profiling(eng.reg._h, 0)
         gemm_ms_per_step = tot_ms / reps_prof
         peaks, which = _peaks()
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         achieved = tot_fl / reps_prof / (gemm_ms_per_step / 1e3) / 1e12
+        n_launch = nops * (B // eng.mb)
+        # DRAM bytes per launch of the same kernel family from the committed ncu capture (profiles/*_step_B32.json:
+        # dram__bytes_read.sum + dram__bytes_write.sum over the GEMM launches of one optimisation step, micro-batch 32)
+        traffic, traffic_src = None, None
+        try:
+            import glob
+            cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_step_B32.json")))
+            if cands and eng.mb == 32:
+                pj = json.load(open(cands[-1]))
+                traffic, traffic_src = pj["gemm_dram_bytes_per_launch"], os.path.relpath(cands[-1], ROOT)
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         prof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": which + " (sustained bf16 cuBLAS)", "kernel": "gemm_sm100_kernel<BN,STAGES>",
-                "launches_per_step": nops * (B // eng.mb), "gemm_ms_per_step": gemm_ms_per_step,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": which + " (sustained bf16 cuBLAS)", "kernel": "gemm_sm100_kernel<BN,STAGES,EPI,NEW>",
+                "launches_per_step": n_launch, "gemm_ms_per_step": gemm_ms_per_step,
                 "share_of_step": gemm_ms_per_step / (ms_max / Kt),
-                "algorithmic_flop_per_step": tot_fl / reps_prof}
+                "algorithmic_flop_per_step": tot_fl / reps_prof,
+                "algorithmic_flop_per_launch": tot_fl / reps_prof / n_launch,
+                "algorithmic_bytes_per_launch": tot_by / n_launch,
+                "avg_launch_ms": gemm_ms_per_step / n_launch,
+                "hbm": {"achieved_GBs": tot_by / (gemm_ms_per_step / 1e3) / 1e9, "peak_GBs": hbm_peak,
+                        "frac": tot_by / (gemm_ms_per_step / 1e3) / 1e9 / hbm_peak,
+                        "note": "the family mixes tensor-bound (K >= 1024) and HBM-bound (1x1 expansions) launches"}}
         if args.profile_out:
             os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)
             json.dump({"per_gemm": table, "summary": prof, "ms_per_step": ms_max / Kt}, open(args.profile_out, "w"), indent=1)

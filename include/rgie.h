@@ -107,10 +107,12 @@ int rgie_regressor_forward_ex(RgieRegressor* r, const float* img, int B, int Hr,
 int rgie_regressor_backward(RgieRegressor* r, const float* dlogits, float* dimg, void* stream);
 /* per-GEMM timing of the last forward/backward (cudaEvent pairs around every row-shifted GEMM launch; used by bench.py
  * for the live roofline figure).  get_profile synchronises on the recorded events.  h_info[4*i..]: {0 fwd | 1 bwd,
- * Cout, K, m_tiles}; h_flops: algorithmic FLOPs (valid pixels only, padding excluded). */
+ * Cout, K, m_tiles}; h_flops: algorithmic FLOPs (valid pixels only, padding excluded); h_bytes: algorithmic HBM bytes
+ * (every distinct operand element read once, every output element written once). */
 int rgie_regressor_set_profiling(RgieRegressor* r, int on);
 int rgie_regressor_num_ops(const RgieRegressor* r);
-int rgie_regressor_get_profile(RgieRegressor* r, float* h_ms, double* h_flops, int* h_info, int capacity, int* n_out);
+int rgie_regressor_get_profile(RgieRegressor* r, float* h_ms, double* h_flops, double* h_bytes, int* h_info, int capacity,
+                               int* n_out);
 /* number of kernel launches this library has issued in this process (bench.py's gpu_launches evidence) */
 long rgie_launch_count(void);
 

@@ -48,7 +48,7 @@ SIGNATURES = {
     "rgie_regressor_backward": (_i, [_vp, _vp, _vp, _vp]),
     "rgie_regressor_set_profiling": (_i, [_vp, _i]),
     "rgie_regressor_num_ops": (_i, [_vp]),
-    "rgie_regressor_get_profile": (_i, [_vp, _vp, _vp, _vp, _i, C.POINTER(_i)]),
+    "rgie_regressor_get_profile": (_i, [_vp, _vp, _vp, _vp, _vp, _i, C.POINTER(_i)]),
     "rgie_launch_count": (_l, []),
     "rgie_regressor_tap": (_i, [_vp, C.c_char_p, _vp, _l, C.POINTER(_l), _vp]),
     "rgie_va_head": (_i, [_vp, _i, _i, _i, _i, _vp, _f, _f, _i, _f, _vp, _vp, _vp, _vp]),

@@ -458,6 +458,23 @@ double op_flops(const GemmDesc& d, double useful_frac) {
   return f;
 }
 
+// algorithmic HBM bytes of one op: every distinct operand element read once, every output element written once
+// (valid pixels only; the zero padding is never written and costs no algorithmic traffic)
+double op_bytes(const GemmDesc& d, int esz) {
+  const Geom& g = d.src;
+  const double valid_frac = (double)g.H * g.W / (double)g.S;
+  const double out_rows = (double)(d.m_end - d.m_begin) * valid_frac;
+  double b = (double)d.a_rows * valid_frac * d.Cin * esz;                          // A
+  if (d.A2 != nullptr) b += (double)d.a2_rows * valid_frac * d.Cin2 * esz;        // second operand
+  b += (double)d.n_pad * (d.ntaps * d.Cin + (d.A2 ? d.Cin2 : 0)) * esz;            // weights
+  b += out_rows * d.Cout * (d.d_fp32 ? 4 : esz);                                   // D
+  if (d.res != nullptr) b += (double)(d.res_rows < d.m_end - d.m_begin ? d.res_rows : d.m_end - d.m_begin) * valid_frac * d.Cout * esz;
+  if (d.mask != nullptr) b += out_rows * d.Cout * esz;
+  if (d.mask_bits != nullptr) b += out_rows * d.Cout / 8.0;
+  if (d.D_bits != nullptr) b += out_rows * d.Cout / 8.0;
+  return b;
+}
+
 // set the ReLU mask of a backward op: sign bits in the bf16 modes, the activation itself in fp32 parity mode
 void set_mask(const RgieRegressor* R, GemmDesc& d, const void* act, const uint32_t* bits, int channels) {
   if (R->dtype == 1) { d.mask = nullptr; d.mask_bits = bits; d.ld_mb = channels / 32; }
@@ -909,8 +926,9 @@ int rgie_regressor_set_profiling(RgieRegressor* R, int on) {
 
 int rgie_regressor_num_ops(const RgieRegressor* R) { return R ? (int)(R->fwd_ops.size() + R->bwd_ops.size()) : 0; }
 
-int rgie_regressor_get_profile(RgieRegressor* R, float* h_ms, double* h_flops, int* h_info, int capacity, int* n_out) {
-  RGIE_CHECK(R && h_ms && h_flops && h_info && n_out, "rgie_regressor_get_profile: null");
+int rgie_regressor_get_profile(RgieRegressor* R, float* h_ms, double* h_flops, double* h_bytes, int* h_info, int capacity,
+                               int* n_out) {
+  RGIE_CHECK(R && h_ms && h_flops && h_bytes && h_info && n_out, "rgie_regressor_get_profile: null");
   RGIE_CHECK(!R->ev.empty(), "rgie_regressor_get_profile: profiling was never enabled");
   const int n = (int)(R->fwd_ops.size() + R->bwd_ops.size());
   RGIE_CHECK(capacity >= n, "rgie_regressor_get_profile: capacity");
@@ -926,6 +944,7 @@ int rgie_regressor_get_profile(RgieRegressor* R, float* h_ms, double* h_flops, i
     if (fwd && i == 0) useful = 147.0 / 256.0;
     if (!fwd && i == n - 1) useful = (147.0 * 64.0) / (16.0 * 16.0 * 64.0);
     h_flops[i] = op_flops(op.d, useful);
+    h_bytes[i] = op_bytes(op.d, R->esz);
     h_info[4 * i + 0] = fwd ? 0 : 1;
     h_info[4 * i + 1] = op.d.Cout;
     h_info[4 * i + 2] = op.d.ntaps * op.d.Cin + (op.d.A2 ? op.d.Cin2 : 0);
