@@ -168,11 +168,12 @@ __host__ __device__ constexpr int tmem_cols(int bn, int nacc = 2) {
 // by TMA loads issued EPI chunks ahead (4 = a whole tile ahead).  Staging boxes are 128 rows x 32 columns (64-byte rows,
 // SWIZZLE_64B): per column half two output boxes and EPI residual boxes of 8 KB.
 constexpr int EPI_BOX_BYTES = BM * 32 * 2;
-template <int BN, int STAGES, int EPI>
+template <int BN, int STAGES, int EPI, bool PAIR = false>
 struct SmemLayout {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int A_BYTES = (PAIR ? 2 : 1) * A_STAGE_BYTES;   // PAIR: two M-adjacent 128-row tiles per stage
   static constexpr int A_OFF = 0;
-  static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
+  static constexpr int B_OFF = STAGES * A_BYTES;
   static constexpr int OB_OFF = B_OFF + STAGES * B_STAGE_BYTES;                 // [half][2] output boxes
   static constexpr int RB_OFF = OB_OFF + (EPI >= 1 ? 4 * EPI_BOX_BYTES : 0);    // [half][EPI] residual boxes
   static constexpr int BAR_OFF = RB_OFF + (EPI >= 2 ? 2 * EPI * EPI_BOX_BYTES : 0);   // full[S], empty[S], tfull[2], tempty[2], rfull[8]
@@ -372,7 +373,10 @@ __device__ __forceinline__ void epilogue_store_role(const GemmDesc& d, const CUt
 // TSPLIT = true : the warp groups take alternate TILES (all columns; NACC accumulator buffers, one arrive group per
 //                 buffer): with narrow N tiles the epilogue of a tile is a latency chain, not a throughput problem, so
 //                 two tiles in flight halve its cost.
-template <int BN, int NEW, bool TSPLIT = false, int NACC = 2>
+// PAIR = true   : the CTA's tile sequence is made of PAIRS of M-adjacent tiles of the same N tile (num_tiles counts
+//                 pairs); the producer loads each weight tile once per pair.  Tile 2k / 2k+1 of the sequence use
+//                 accumulator 0 / 1, exactly like consecutive tiles do without pairing, so only the decode changes.
+template <int BN, int NEW, bool TSPLIT = false, int NACC = 2, bool PAIR = false>
 __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sbias, const uint32_t tmem_base,
                                               const uint32_t tfull0, const uint32_t tempty0, const int warp, const int lane,
                                               const int num_tiles, const int num_n_tiles, const FastDiv fd_nt,
@@ -411,13 +415,29 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
   uint32_t bits_nxt[CPW];
   const __nv_bfloat16* nres = nullptr;             // residual row of the next tile (null: nothing to read)
   const __nv_bfloat16* cres = nullptr;             // residual row of the current tile
-  auto locate = [&](int tile) {
+  // seq-th tile of this warp group -> (mt, nt); false past the end
+  auto decode = [&](int seq, int& mt, int& nt) -> bool {
+    if (PAIR) {
+      const int pr = (int)blockIdx.x + (seq >> 1) * (int)gridDim.x;
+      if (pr >= num_tiles) return false;
+      const int mp = (int)fd_nt.div((uint32_t)pr);
+      nt = pr - mp * num_n_tiles;
+      mt = 2 * mp + (seq & 1);
+      return true;
+    }
+    const int tile = tile0 + seq * tile_step;
+    if (tile >= num_tiles) return false;
+    mt = (int)fd_nt.div((uint32_t)tile);
+    nt = tile - mt * num_n_tiles;
+    return true;
+  };
+  auto locate = [&](int seq) {
     cres = nres;
     nres = nullptr;
 #pragma unroll
     for (int i = 0; i < CPW; ++i) bits_nxt[i] = 0u;
-    if (tile < num_tiles && active) {
-      const int mt = (int)fd_nt.div((uint32_t)tile), nt = tile - mt * num_n_tiles;
+    int mt, nt;
+    if (decode(seq, mt, nt) && active) {
       const long m = row_m(mt);
       if (res != nullptr && m < res_lim) nres = res + m * d.ld_res + nt * BN + c_begin * CH;
       if (mbits != nullptr && m < d.m_end) {
@@ -436,7 +456,7 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
       for (int j = 0; j < CH / 16; ++j) ldg256(p + cc * CH + j * 16, rbuf[cj % NB] + 8 * j);
     }
   };
-  locate(tile0);           // nres = first tile
+  locate(0);               // nres = first tile
   {
     const __nv_bfloat16* first = nres;
     cres = first;
@@ -445,8 +465,8 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
   }
 
   int it = TSPLIT ? part : 0;                      // index of the tile in this CTA's sequence
-  for (int tile = tile0; tile < num_tiles; tile += tile_step, it += TSTEP) {
-    const int mt = (int)fd_nt.div((uint32_t)tile), nt = tile - mt * num_n_tiles;
+  int mt, nt;
+  for (int seq = 0; decode(seq, mt, nt); ++seq, it += TSTEP) {
     const int acc = it % NACC;
     const uint32_t acc_phase = (it / NACC) & 1;
     const long m = row_m(mt);
@@ -459,7 +479,7 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
     uint32_t bits_cur[CPW], bits_out[CPW];
 #pragma unroll
     for (int i = 0; i < CPW; ++i) { bits_cur[i] = bits_nxt[i]; bits_out[i] = 0u; }
-    locate(tile + tile_step);                      // cres = this tile, nres / mask words = next tile
+    locate(seq + 1);                               // cres = this tile, nres / mask words = next tile
     mbar_wait(tfull_bar(acc), acc_phase);
     tcgen05_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
@@ -551,13 +571,14 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
   }
 }
 
-template <int BN, int STAGES, int EPI, int NEW>
+template <int BN, int STAGES, int EPI, int NEW, bool PAIR>
 __global__ void __launch_bounds__(num_threads(NEW), 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
                   const __grid_constant__ CUtensorMap tmR, const GemmDesc d, const int num_m_tiles, const int num_n_tiles,
                   const FastDiv fd_nt) {
-  using L = SmemLayout<BN, STAGES, EPI>;
+  using L = SmemLayout<BN, STAGES, EPI, PAIR>;
+  static_assert(!PAIR || EPI == 0, "tile pairing uses the row-per-thread epilogue");
   constexpr uint32_t TMEM_COLS = tmem_cols(BN);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -616,14 +637,17 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = (int)fd_nt.div((uint32_t)tile), nt = tile - mt * num_n_tiles;
+        const int mt = (PAIR ? 2 : 1) * (int)fd_nt.div((uint32_t)tile);
+        const int nt = tile - (int)fd_nt.div((uint32_t)tile) * num_n_tiles;
         const long m0 = d.m_begin + (long)mt * BM;
         int tap = 0, cb = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_expect_tx(full_bar(stage), A_STAGE_BYTES + L::B_STAGE_BYTES);
-          tma_load_2d(smem_base + L::A_OFF + stage * A_STAGE_BYTES, &tmA, cb * BK, (int)(m0 + d.row_off[tap]),
-                      full_bar(stage));
+          mbar_expect_tx(full_bar(stage), L::A_BYTES + L::B_STAGE_BYTES);
+          tma_load_2d(smem_base + L::A_OFF + stage * L::A_BYTES, &tmA, cb * BK, (int)(m0 + d.row_off[tap]), full_bar(stage));
+          if (PAIR)
+            tma_load_2d(smem_base + L::A_OFF + stage * L::A_BYTES + A_STAGE_BYTES, &tmA, cb * BK,
+                        (int)(m0 + BM + d.row_off[tap]), full_bar(stage));
           tma_load_2d(smem_base + L::B_OFF + stage * L::B_STAGE_BYTES, &tmB, kb * BK, nt * BN, full_bar(stage));
           if (++cb == kb_per_tap) { cb = 0; ++tap; }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -631,8 +655,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (m0 < d.a2_rows) {
           for (int kb = 0; kb < num_kb2; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1);
-            mbar_expect_tx(full_bar(stage), A_STAGE_BYTES + L::B_STAGE_BYTES);
-            tma_load_2d(smem_base + L::A_OFF + stage * A_STAGE_BYTES, &tmA2, kb * BK, (int)m0, full_bar(stage));
+            mbar_expect_tx(full_bar(stage), L::A_BYTES + L::B_STAGE_BYTES);
+            tma_load_2d(smem_base + L::A_OFF + stage * L::A_BYTES, &tmA2, kb * BK, (int)m0, full_bar(stage));
+            if (PAIR)
+              tma_load_2d(smem_base + L::A_OFF + stage * L::A_BYTES + A_STAGE_BYTES, &tmA2, kb * BK, (int)(m0 + BM),
+                          full_bar(stage));
             tma_load_2d(smem_base + L::B_OFF + stage * L::B_STAGE_BYTES, &tmB, (num_kb + kb) * BK, nt * BN, full_bar(stage));
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -646,28 +673,37 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it += (PAIR ? 2 : 1)) {
+        const int acc = it & 1;                    // PAIR: it is even, the pair uses accumulators 0 and 1
         const uint32_t acc_phase = (it >> 1) & 1;
-        const long m0 = d.m_begin + (long)fd_nt.div((uint32_t)tile) * BM;
+        const long m0 = d.m_begin + (long)((PAIR ? 2 : 1) * (int)fd_nt.div((uint32_t)tile)) * BM;
         const int kb_total = num_kb + (m0 < d.a2_rows ? num_kb2 : 0);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        if (PAIR) mbar_wait(tempty_bar(1), acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
-          const uint64_t adesc = make_smem_desc(smem_base + L::A_OFF + stage * A_STAGE_BYTES);
+          const uint64_t adesc = make_smem_desc(smem_base + L::A_OFF + stage * L::A_BYTES);
           const uint64_t bdesc = make_smem_desc(smem_base + L::B_OFF + stage * L::B_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr>>4) start field
             umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           }
+          if (PAIR) {
+            const uint64_t adesc1 = make_smem_desc(smem_base + L::A_OFF + stage * L::A_BYTES + A_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(tmem_base + (uint32_t)BN, adesc1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                        (kb | k) != 0 ? 1u : 0u);
+          }
           umma_commit(empty_bar(stage));          // frees the smem slot once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar(acc));              // accumulator complete -> epilogue
+        umma_commit(tfull_bar(acc));              // accumulator(s) complete -> epilogue
+        if (PAIR) umma_commit(tfull_bar(1));
       }
     }
   } else if constexpr (EPI >= 1) {
@@ -676,8 +712,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                  smem_base + L::RB_OFF, rfull_bar(0), tmem_base, tfull_bar(0), tempty_bar(0), warp, lane,
                                  num_tiles, num_n_tiles, fd_nt);
   } else {
-    epilogue_role<BN, NEW>(d, reinterpret_cast<const float*>(smem + L::BIAS_OFF), tmem_base, tfull_bar(0), tempty_bar(0), warp,
-                           lane, num_tiles, num_n_tiles, fd_nt, PatchMap{0, 0, 0, FastDiv{1, 0, 0}});
+    epilogue_role<BN, NEW, false, 2, PAIR>(d, reinterpret_cast<const float*>(smem + L::BIAS_OFF), tmem_base, tfull_bar(0),
+                                           tempty_bar(0), warp, lane, num_tiles, num_n_tiles, fd_nt,
+                                           PatchMap{0, 0, 0, FastDiv{1, 0, 0}});
   }
 
   // ===================== teardown =====================
@@ -726,10 +763,10 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
 
-template <int BN>
+template <int BN, int NY, int NX>
 __global__ void __launch_bounds__(num_threads(8), 1)
 gemm_patch_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmB, const GemmDesc d,
-                  const PatchTaps tp, const PatchMap pm, const int num_tiles, const int dbg) {
+                  const PatchTaps tp, const PatchMap pm, const int num_tiles) {
   using L = PatchSmem;
   constexpr int NACC = 4;                         // accumulator buffers: two tiles in the epilogue, two in the tensor pipe
   constexpr uint32_t TMEM_COLS = tmem_cols(BN, NACC);
@@ -746,7 +783,7 @@ gemm_patch_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_PTR_OFF);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t slab_bytes = (uint32_t)((16 + tp.ny - 1) * 8 * 128);
+  constexpr uint32_t slab_bytes = (uint32_t)((16 + NY - 1) * 8 * 128);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA3) : "memory");
@@ -786,14 +823,12 @@ gemm_patch_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int ht = (int)pm.fd_wt.div((uint32_t)tile), wt = tile - ht * pm.WT;
-        for (int xi = 0; xi < tp.nx; ++xi) {
+#pragma unroll
+        for (int xi = 0; xi < NX; ++xi) {
           mbar_wait(aempty_bar(slot), phase ^ 1);
-          if (dbg & 2) { mbar_arrive(afull_bar(slot)); }
-          else {
           mbar_expect_tx(afull_bar(slot), slab_bytes);
           tma_load_3d(smem_base + L::A_OFF + slot * PATCH_SLAB_BYTES, &tmA3, 0, wt * 8 + tp.dx0 + xi, ht * 16 + tp.dy0,
                       afull_bar(slot));
-          }
           if (++slot == PATCH_SLABS) { slot = 0; phase ^= 1; }
         }
       }
@@ -803,6 +838,7 @@ gemm_patch_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
       mbar_wait(wfull_bar, 0);
+      const uint64_t wdesc0 = make_smem_desc(smem_base + L::W_OFF);
       int slot = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -812,22 +848,22 @@ gemm_patch_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        uint32_t accum = 0u;
-        for (int xi = 0; xi < tp.nx; ++xi) {
+        // the single issuing thread is the critical resource of these narrow-N tiles (an MMA is 45-48 cycles of tensor
+        // time): the tap loops are fully unrolled, descriptors differ by compile-time constants, the tap table sits in
+        // the constant bank
+#pragma unroll
+        for (int xi = 0; xi < NX; ++xi) {
           mbar_wait(afull_bar(slot), phase);
           tcgen05_fence_after();
-          const uint32_t slab = smem_base + L::A_OFF + slot * PATCH_SLAB_BYTES;
-          for (int yi = 0; yi < tp.ny; ++yi) {
-            const int t = tp.tap[yi][xi];
-            if (t < 0 || ((dbg & 1) && (xi | yi))) continue;
-            // vertical tap yi: the same box, yi pixel lines (= yi swizzle atoms of 8 rows x 128 B) further down
-            const uint64_t adesc = make_smem_desc(slab + (uint32_t)(yi * 1024));
-            const uint64_t bdesc = make_smem_desc(smem_base + L::W_OFF + t * W_TAP_BYTES);
+          const uint64_t adesc0 = make_smem_desc(smem_base + L::A_OFF + slot * PATCH_SLAB_BYTES);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accum);
-              accum = 1u;
-            }
+          for (int yi = 0; yi < NY; ++yi) {
+            // vertical tap yi: the same box, yi pixel lines (= yi swizzle atoms of 8 rows x 128 B = 64 descriptor units) down
+            const uint64_t adesc = adesc0 + (uint64_t)(yi * 64);
+            const uint64_t bdesc = wdesc0 + (uint64_t)(tp.tap[yi][xi] * (W_TAP_BYTES >> 4));
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (xi | yi | k) != 0 ? 1u : 0u);
           }
           umma_commit(aempty_bar(slot));
           if (++slot == PATCH_SLABS) { slot = 0; phase ^= 1; }
@@ -895,11 +931,12 @@ int make_map_3d(CUtensorMap* map, const void* base, uint64_t P, uint64_t lines, 
   return 0;
 }
 
-template <int BN>
+template <int BN, int NY, int NX>
 int run_patch(const GemmPlanSm100& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    RGIE_CUDA_OK(cudaFuncSetAttribute(gemm_patch_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, PatchSmem::DYN_BYTES));
+    RGIE_CUDA_OK(cudaFuncSetAttribute(gemm_patch_kernel<BN, NY, NX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      PatchSmem::DYN_BYTES));
     attr_set = true;
   }
   PatchTaps tp;
@@ -908,24 +945,24 @@ int run_patch(const GemmPlanSm100& p, cudaStream_t st) {
     for (int x = 0; x < 4; ++x) tp.tap[y][x] = p.patch_tap[y][x];
   PatchMap pm;
   pm.enabled = 1; pm.P = p.d.src.P; pm.WT = p.patch_wt; pm.fd_wt = make_fastdiv((uint32_t)p.patch_wt);
-  static const int dbg = getenv("RGIE_PATCH_DEBUG") ? atoi(getenv("RGIE_PATCH_DEBUG")) : 0;
-  gemm_patch_kernel<BN><<<p.grid, num_threads(8), PatchSmem::DYN_BYTES, st>>>(p.tmA, p.tmB, p.d, tp, pm, p.num_m_tiles, dbg);
+  gemm_patch_kernel<BN, NY, NX><<<p.grid, num_threads(8), PatchSmem::DYN_BYTES, st>>>(p.tmA, p.tmB, p.d, tp, pm, p.num_m_tiles);
   RGIE_LAUNCH_OK();
   return 0;
 }
 
-template <int BN, int STAGES, int EPI, int NEW>
+template <int BN, int STAGES, int EPI, int NEW, bool PAIR = false>
 int run_impl(const GemmPlanSm100& p, cudaStream_t st) {
-  using L = SmemLayout<BN, STAGES, EPI>;
+  using L = SmemLayout<BN, STAGES, EPI, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
-    RGIE_CUDA_OK(cudaFuncSetAttribute(gemm_sm100_kernel<BN, STAGES, EPI, NEW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      L::DYN_BYTES));
+    RGIE_CUDA_OK(cudaFuncSetAttribute(gemm_sm100_kernel<BN, STAGES, EPI, NEW, PAIR>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
     attr_set = true;
   }
-  gemm_sm100_kernel<BN, STAGES, EPI, NEW><<<p.grid, num_threads(NEW), L::DYN_BYTES, st>>>(p.tmA, p.tmA2, p.tmB, p.tmD, p.tmR,
-                                                                                          p.d, p.num_m_tiles, p.num_n_tiles,
-                                                                                          make_fastdiv((uint32_t)p.num_n_tiles));
+  // PAIR: the kernel walks pairs of M-adjacent tiles (num_m_tiles then counts pairs)
+  const int m_units = PAIR ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
+  gemm_sm100_kernel<BN, STAGES, EPI, NEW, PAIR><<<p.grid, num_threads(NEW), L::DYN_BYTES, st>>>(
+      p.tmA, p.tmA2, p.tmB, p.tmD, p.tmR, p.d, m_units, p.num_n_tiles, make_fastdiv((uint32_t)p.num_n_tiles));
   RGIE_LAUNCH_OK();
   return 0;
 }
@@ -959,9 +996,10 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
   p->patch = 0;
   // ---- patch-tile variant: Cin = 64, one N tile, single-plane source whose rows are whole pixel lines, taps on a
   //      (dy, dx) grid of at most 4 x 4 with |dx| well below the pitch
-  //      MEASURED SLOWER than the flat kernel on B200 (3x3 layer1: 0.70 vs 0.52 ms, conv1 dgrad 4.2 vs 3.7 ms per 320 crops;
-  //      profiles/README.md): operand traffic was not the limiter of these layers.  Kept behind RGIE_GEMM_PATCH=1.
-  static const int env_patch = getenv("RGIE_GEMM_PATCH") ? atoi(getenv("RGIE_GEMM_PATCH")) : 0;
+  //      Measured on B200 (320 crops): 3x3 layer1 0.52 -> 0.41 ms, conv1 forward 1.08 -> 0.76 ms, conv1 input gradient
+  //      3.6 -> 2.5 ms.  (A first version with a generic tap loop in the issuing thread was SLOWER than the flat kernel:
+  //      for narrow N tiles the single MMA-issuing thread is the critical resource.)  RGIE_GEMM_PATCH=0 disables it.
+  static const int env_patch = getenv("RGIE_GEMM_PATCH") ? atoi(getenv("RGIE_GEMM_PATCH")) : 1;
   if (env_patch && d.Cin == 64 && bn <= 64 && d.Cout == bn && d.ntaps >= 3 && d.A2 == nullptr && d.src.planes == 1 &&
       d.m_begin == 0 && d.m_end == d.a_rows && d.a_rows == d.src.rows() && d.src.P >= 16 && d.mask == nullptr) {
     const int P = d.src.P;
@@ -983,8 +1021,14 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
         if (slot >= 0) ok = false;
         slot = t;
       }
-      if (ok) {
-        p->patch = 1;
+      int variant = 0;
+      if (ok && d.ntaps == ny * nx) {
+        if (bn == 64 && ny == 3 && nx == 3) variant = 1;
+        else if (bn == 64 && ny == 4 && nx == 1) variant = 2;
+        else if (bn == 16 && ny == 4 && nx == 4) variant = 3;
+      }
+      if (variant) {
+        p->patch = variant;
         p->patch_ny = ny; p->patch_nx = nx; p->patch_dy0 = dymin; p->patch_dx0 = dxmin;
         const long lines = d.a_rows / P;
         p->patch_wt = (P + 7) / 8;
@@ -1022,6 +1066,16 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
       p->epi = 1;
     }
   }
+  // tile pairing (two M-adjacent tiles share every weight-tile load): the large-K layers are bound by the L2->SM operand
+  // feed (48 KB per 128x256x64 k-block vs ~54 B/clk/SM measured), pairing cuts it to 32 KB per k-block and tile
+  //      MEASURED: no gain on B200 (N=256,K=2304: 0.242 -> 0.275 ms; N=512,K=4608: 0.240 -> 0.234 ms per 320 crops): these layers
+  //      already run at 88-91 % of the sustained (power-capped) cuBLAS rate, the operand feed is not their limiter.  Off by default.
+  static const int env_pair = getenv("RGIE_GEMM_PAIR_MINK") ? atoi(getenv("RGIE_GEMM_PAIR_MINK")) : 0;
+  if (bn == 256 && p->epi == 0 && env_pair > 0 && ktot >= env_pair && p->num_m_tiles >= 2) {
+    p->epi = -2;
+    const long pairs = (long)((p->num_m_tiles + 1) / 2) * p->num_n_tiles;
+    p->grid = (int)(pairs < sms ? pairs : sms);
+  }
   p->tmD = p->tmA; p->tmR = p->tmA;
   int rc = 0;
   if (p->epi >= 1) {
@@ -1043,7 +1097,9 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
 
 int run_gemm_sm100(const GemmPlanSm100& p, cudaStream_t st) {
   if (p.d.m_end <= p.d.m_begin) return 0;
-  if (p.patch) return p.bn == 64 ? run_patch<64>(p, st) : run_patch<16>(p, st);
+  if (p.patch == 1) return run_patch<64, 3, 3>(p, st);     // 3x3, 64 -> 64 (layer1)
+  if (p.patch == 2) return run_patch<64, 4, 1>(p, st);     // conv1 forward: 4 vertical taps over the packed input
+  if (p.patch == 3) return run_patch<16, 4, 4>(p, st);     // conv1 input gradient: 4 x 4 taps, 64 -> 16
   switch (p.bn) {
     case 256:
       switch (p.epi) {
@@ -1051,6 +1107,7 @@ int run_gemm_sm100(const GemmPlanSm100& p, cudaStream_t st) {
         case 2: return run_impl<256, 3, 2, 8>(p, st);
         case 1: return run_impl<256, 3, 1, 8>(p, st);
         case -16: return run_impl<256, 4, 0, 16>(p, st);
+        case -2: return run_impl<256, 3, 0, 8, true>(p, st);
         default: return run_impl<256, 4, 0, 8>(p, st);
       }
     case 128: return run_impl<128, 6, 0, 8>(p, st);
