@@ -1,0 +1,84 @@
+"""GPU: SURVEY.md 8a O7 -- latent (style-code) optimisation through a generator: the reference call surface
+`initialize_imaginaire` + `objective_function_imaginaire` + `optimization` (generic path: native regressor autograd
+Function + fused native Adam/best-x kernel) against the CPU oracle restatement, same seeds.
+
+The MUNIT generator of the reference (external/imaginaire) cannot travel to the GPU box; a seeded test double with the
+same interface (`autoencoder_a.encode(img) -> (content, style)`, `decode(content, style) -> img`, style [B,8,1,1]) stands
+in for it -- the generator is PyTorch on both sides, what is under test is the native regressor / update path around it.
+"""
+import copy
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+class _AutoEncoder(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.enc = nn.Conv2d(3, 16, 8, stride=8)
+        self.sty = nn.Linear(3, 8)
+        self.mod = nn.Linear(8, 32)
+        self.dec1 = nn.Conv2d(16, 16, 3, padding=1)
+        self.dec2 = nn.Conv2d(16, 3 * 64, 1)
+
+    def encode(self, img):
+        return torch.tanh(self.enc(img)), self.sty(img.mean((2, 3))).view(-1, 8, 1, 1)
+
+    def decode(self, content, style):
+        gb = self.mod(style.flatten(1))
+        gamma, beta = gb[:, :16, None, None], gb[:, 16:, None, None]
+        h = F.relu(self.dec1(content) * (1 + gamma) + beta)          # AdaIN-like modulation by the style code
+        return 1.5 * torch.tanh(F.pixel_shuffle(self.dec2(h), 8))    # overshoots [-1, 1] like the MUNIT decoder
+
+
+class _Gen(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.autoencoder_a = _AutoEncoder()
+
+
+def test_latent_optimisation_matches_oracle():
+    from regressor_guided_image_editing_b200 import optimize_image_imaginaire as oii
+    from regressor_guided_image_editing_b200.baselines import optimize_image as oi
+    from regressor_guided_image_editing_b200.baselines.losses.ValenceArousalLoss import ValenceArousalLoss
+    steps, h = 3, 128
+    sd = O.make_regressor_state_dict()
+    torch.manual_seed(11)
+    gen_cpu = _Gen().eval()
+    gen_gpu = copy.deepcopy(gen_cpu).to(DEV)
+    image = 2.0 * O.synthetic_image(3, h, h)[None] - 1.0
+    torch.manual_seed(2003)
+    offs = O.draw_crop_offsets(1 + steps, 1, 480, 480)
+    w_clf, w_rec, lr = 0.2, 1.0, 0.05                               # optimize_image_imaginaire.py:32-37
+
+    # ---- oracle (CPU)
+    with torch.no_grad():
+        content, style = gen_cpu.autoencoder_a.encode(image)
+        pred0 = O.regressor_predict(image, sd, offs[0], normalize=False)[:, [0, 1]]
+    target = O.get_condition_from_alpha(pred0, 0.1)
+    ref = O.optimize_generic(style.flatten(), lambda x, s: O.objective_imaginaire(
+        x, gen_cpu, content, sd, offs[1 + s], target, w_clf, w_rec)[0], lr, steps)
+
+    # ---- native (reference call surface)
+    clf = ValenceArousalLoss(sd, torch.device(DEV), 1, is_minimized=True, is_input_range_0_1=False, requires_grad=True,
+                             precision="fp32")
+    params = {"gen": gen_gpu, "clf": clf, "dis": None, "gan_loss": None, "weight_clf": w_clf, "weight_dis": 0.0,
+              "weight_recon": w_rec}
+    torch.manual_seed(2003)                                         # the crop draws come from torch's global CPU generator
+    x0, params = oii.initialize_imaginaire(image.to(DEV), params)
+    params["target"] = oi.get_condition_from_alpha(0.1, clf, image.to(DEV))
+    best = oi.optimization(x0.flatten(), params, oii.objective_function_imaginaire, learning_rate=lr, num_steps=steps)
+    torch.cuda.synchronize()
+    assert (params["target"].cpu() - target).abs().max().item() <= 1e-5
+    err = (best.cpu() - ref["best_x"]).abs().max().item()
+    print("best style (native)", best.cpu().tolist(), "oracle", ref["best_x"].tolist(), "max diff", err)
+    # Adam normalises the gradient: one step moves every coordinate by ~lr regardless of its magnitude, so the
+    # trajectories agree to fp32 round-off as long as no gradient component sits at a sign flip
+    assert err <= 2e-4
