@@ -45,7 +45,12 @@ enum RgieFilter {
   RGIE_F_CONTRAST = 4,   /* 1 param  */
   RGIE_F_SHARP = 5,      /* 1 param  */
   RGIE_F_BLUR = 6,       /* 1 param (sigma, 25x25 kernel, reflect) */
-  RGIE_F_SCALE = 7       /* 4 params (sx, sy, cx, cy) */
+  RGIE_F_SCALE = 7,      /* 4 params (sx, sy, cx, cy) */
+  RGIE_F_GAMMA = 8,      /* 1 param: clamp(x^gamma, 0, 1)                      image_transformations.py:176-185 */
+  RGIE_F_BRIGHT = 9,     /* 1 param: clamp(x + p, 0, 1)                        :136-143 */
+  RGIE_F_BW = 10,        /* 1 param: lerp(x, 0.27 r + 0.67 g + 0.06 b, p)      :156-163 */
+  RGIE_F_HUE = 11,       /* 1 param: hsv hue shift, fmod(h + p, 2 pi)          :166-173 */
+  RGIE_F_WB = 12         /* 1 param: lerp(x, x * 0.5 / mean_HW(x), p)          :126-133 */
 };
 int rgie_filter_param_count(int kind);
 /* floats of scratch `ws` that rgie_filter_fwd / rgie_filter_bwd need for a [B,3,H,W] batch */

@@ -9,6 +9,8 @@ parameter tensor with a leading dimension equal to the batch is applied per imag
 """
 from __future__ import annotations
 
+import math
+
 import torch
 
 from ... import _lib, ops
@@ -85,10 +87,37 @@ def apply_scale(im, scale_param):                            # :209-221
     return _Filter.apply(im, scale_param, _lib.F_SCALE, 4)
 
 
+def apply_white_balance(im, white_balance_param):            # :126-133 -> img_trans_torch_diff.py:51-57
+    return _Filter.apply(im, _as_tensor(white_balance_param, im), _lib.F_WB, 1)
+
+
+def apply_brightness(im, brightness_param):                  # :136-143
+    return _Filter.apply(im, torch.clamp(_as_tensor(brightness_param, im), min=0, max=1), _lib.F_BRIGHT, 1)
+
+
+def apply_black_white(im, bw_param):                         # :156-163 -> img_trans_torch_diff.py:67-70
+    return _Filter.apply(im, _as_tensor(bw_param, im), _lib.F_BW, 1)
+
+
+def apply_hue(im, hue_param):                                # :166-173
+    return _Filter.apply(im, torch.clamp(_as_tensor(hue_param, im), min=-math.pi, max=math.pi), _lib.F_HUE, 1)
+
+
+def apply_gamma(im, gamma_param):                            # :176-185
+    return _Filter.apply(im, torch.clamp(_as_tensor(gamma_param, im), min=0), _lib.F_GAMMA, 1)
+
+
+def apply_affine_transformation(im, matrices):               # :198-206
+    raise _lib.RgieError("the general affine warp is not implemented natively yet (SURVEY.md 8f rank 1); "
+                         "apply_scale covers the reference's default filter list")
+
+
 _DISPATCH = {
     "exposure": apply_exposure, "saturation": apply_saturation, "tone": apply_tone_curve_adjustment,
     "color": apply_color_curve_adjustment, "contrast": apply_contrast, "sharp": apply_sharpening,
     "blur": apply_gaussian_blur, "scale": apply_scale,
+    "gamma": apply_gamma, "wb": apply_white_balance, "bright": apply_brightness, "bw": apply_black_white, "hue": apply_hue,
+    "affine": apply_affine_transformation,
 }
 
 

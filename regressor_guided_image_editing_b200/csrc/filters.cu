@@ -262,6 +262,198 @@ struct ContrastOp {            // F5: kornia adjust_contrast_with_mean_subtracti
 };
 
 // ---------------------------------------------------------------------------------------------------------------
+// the remaining pointwise filters of apply_params
+// ---------------------------------------------------------------------------------------------------------------
+struct GammaOp {               // kornia.enhance.adjust_gamma(im, clamp(gamma, min=0), gain=1): clamp(x^gamma, 0, 1)
+  static constexpr int NP = 1;                  // image_transformations.py:176-185
+  const float* p; int stride; float gam;
+  __device__ void load(int b) { gam = p[(long)b * stride]; }
+  __device__ void fwd(const float* x, float* y) const {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) y[c] = clamp01(powf(x[c], gam));
+  }
+  __device__ void bwd(const float* x, const float* g, float* gx, float* gp) const {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float pre = powf(x[c], gam);
+      const float gg = in01(pre) ? g[c] : 0.f;
+      // torch pow_backward: d/dx = gamma * x^(gamma-1) (0 when gamma == 0); d/dgamma = x^gamma * ln x (0 at x == 0, gamma >= 0)
+      gx[c] = gam == 0.f ? 0.f : gg * gam * powf(x[c], gam - 1.0f);
+      gp[0] += (x[c] == 0.f && gam >= 0.f) ? 0.f : gg * pre * logf(x[c]);
+    }
+  }
+};
+
+struct BrightOp {              // kornia.enhance.adjust_brightness(im, clamp(p, 0, 1), clip_output=True): clamp(x + p, 0, 1)
+  static constexpr int NP = 1;                  // image_transformations.py:136-143
+  const float* p; int stride; float f;
+  __device__ void load(int b) { f = p[(long)b * stride]; }
+  __device__ void fwd(const float* x, float* y) const {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) y[c] = clamp01(__fadd_rn(x[c], f));
+  }
+  __device__ void bwd(const float* x, const float* g, float* gx, float* gp) const {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float gg = in01(__fadd_rn(x[c], f)) ? g[c] : 0.f;
+      gx[c] = gg;
+      gp[0] += gg;
+    }
+  }
+};
+
+struct BwOp {                  // img_trans_torch_diff.py:67-70: lerp(im, rgb2lum(im), p); lum = 0.27 r + 0.67 g + 0.06 b
+  static constexpr int NP = 1;                  // (color_transformations.py:74-81); then apply_params' clamp(0, 1)
+  const float* p; int stride; float f;
+  __device__ void load(int b) { f = p[(long)b * stride]; }
+  __device__ float lum(const float* x) const {
+    return __fadd_rn(__fadd_rn(__fmul_rn(0.27f, x[0]), __fmul_rn(0.67f, x[1])), __fmul_rn(0.06f, x[2]));
+  }
+  __device__ void fwd(const float* x, float* y) const {
+    const float l = lum(x);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) y[c] = clamp01(__fadd_rn(__fmul_rn(1.0f - f, x[c]), __fmul_rn(f, l)));
+  }
+  __device__ void bwd(const float* x, const float* g, float* gx, float* gp) const {
+    const float l = lum(x);
+    const float wc[3] = {0.27f, 0.67f, 0.06f};
+    float gg[3], gl = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float pre = __fadd_rn(__fmul_rn(1.0f - f, x[c]), __fmul_rn(f, l));
+      gg[c] = in01(pre) ? g[c] : 0.f;
+      gl += gg[c];
+      gp[0] += gg[c] * (l - x[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gx[c] = gg[c] * (1.0f - f) + gl * f * wc[c];
+  }
+};
+
+struct HueOp {                 // kornia.enhance.adjust_hue(im, clamp(p, -pi, pi)): rgb_to_hsv -> h = fmod(h + p, 2 pi) -> hsv_to_rgb
+  static constexpr int NP = 1;                  // image_transformations.py:166-173
+  const float* p; int stride; float F;
+  __device__ void load(int b) { F = p[(long)b * stride]; }
+
+  struct Mid { float M, mn, delta, dc, hnum, hsel, s, v, f; int a, imin, hi; };
+
+  __device__ void forward_mid(const float* x, Mid& m, float* y) const {
+    const float r = x[0], g = x[1], b = x[2];
+    m.a = (r >= g && r >= b) ? 0 : (g >= b ? 1 : 2);              // first max (torch CPU tie rule)
+    m.imin = (r <= g && r <= b) ? 0 : (g <= b ? 1 : 2);           // first min
+    m.M = fmaxf(r, fmaxf(g, b));
+    m.mn = fminf(r, fminf(g, b));
+    m.delta = m.M - m.mn;
+    m.v = m.M;
+    m.s = m.delta / (m.M + 1e-8f);
+    m.dc = (m.delta == 0.f) ? 1.f : m.delta;
+    const float rc = m.M - r, gc = m.M - g, bc = m.M - b;
+    m.hnum = (m.a == 0) ? (bc - gc) : (m.a == 1 ? __fadd_rn(rc - bc, __fmul_rn(2.0f, m.dc))
+                                                 : __fadd_rn(gc - rc, __fmul_rn(4.0f, m.dc)));
+    m.hsel = m.hnum / m.dc;
+    float hm = fmodf(m.hsel / 6.0f, 1.0f);
+    if (hm != 0.f && hm < 0.f) hm += 1.0f;
+    const float h = fmodf(__fadd_rn(__fmul_rn(kTwoPi, hm), F), kTwoPi);   // torch.fmod: sign of the dividend
+    // hsv_to_rgb
+    const float hn = h / kTwoPi;
+    const float h6 = __fmul_rn(hn, 6.0f);
+    float fl = floorf(h6);
+    float him = fmodf(fl, 6.0f);
+    if (him != 0.f && him < 0.f) him += 6.0f;
+    float h6m = fmodf(h6, 6.0f);
+    if (h6m != 0.f && h6m < 0.f) h6m += 6.0f;
+    m.f = h6m - him;
+    m.hi = (int)him;
+    const float v = m.v, s2 = m.s, f = m.f;
+    const float pp = __fmul_rn(v, 1.0f - s2);
+    const float qq = __fmul_rn(v, 1.0f - __fmul_rn(f, s2));
+    const float tt = __fmul_rn(v, 1.0f - __fmul_rn(1.0f - f, s2));
+    switch (m.hi) {
+      case 0: y[0] = v; y[1] = tt; y[2] = pp; break;
+      case 1: y[0] = qq; y[1] = v; y[2] = pp; break;
+      case 2: y[0] = pp; y[1] = v; y[2] = tt; break;
+      case 3: y[0] = pp; y[1] = qq; y[2] = v; break;
+      case 4: y[0] = tt; y[1] = pp; y[2] = v; break;
+      default: y[0] = v; y[1] = pp; y[2] = qq; break;
+    }
+  }
+  __device__ void fwd(const float* x, float* y) const {
+    Mid m;
+    forward_mid(x, m, y);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) y[c] = clamp01(y[c]);
+  }
+  __device__ void bwd(const float* x, const float* g, float* gx, float* gp) const {
+    Mid m;
+    float y[3];
+    forward_mid(x, m, y);
+    float go[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) go[c] = in01(y[c]) ? g[c] : 0.f;
+    float g_v = 0.f, g_p = 0.f, g_q = 0.f, g_t = 0.f;
+    switch (m.hi) {
+      case 0: g_v = go[0]; g_t = go[1]; g_p = go[2]; break;
+      case 1: g_q = go[0]; g_v = go[1]; g_p = go[2]; break;
+      case 2: g_p = go[0]; g_v = go[1]; g_t = go[2]; break;
+      case 3: g_p = go[0]; g_q = go[1]; g_v = go[2]; break;
+      case 4: g_t = go[0]; g_p = go[1]; g_v = go[2]; break;
+      default: g_v = go[0]; g_p = go[1]; g_q = go[2]; break;
+    }
+    const float v = m.v, s2 = m.s, f = m.f;
+    float gv = g_v + g_p * (1.0f - s2) + g_q * (1.0f - f * s2) + g_t * (1.0f - (1.0f - f) * s2);
+    const float gs = -v * (g_p + f * g_q + (1.0f - f) * g_t);
+    const float gf = v * s2 * (g_t - g_q);
+    // f <- h6 = 6 h / 2pi,  h = fmod(h0 + F, 2pi),  h0 = 2pi * fmod(hsel / 6, 1)
+    const float gh = gf * 6.0f / kTwoPi;
+    gp[0] += gh;
+    const float ghsel = gh * kTwoPi / 6.0f;
+    float ghnum = ghsel / m.dc;
+    float gdc = -ghsel * m.hsel / m.dc;
+    float grc = 0.f, ggc = 0.f, gbc = 0.f;
+    if (m.a == 0) { gbc += ghnum; ggc -= ghnum; }
+    else if (m.a == 1) { grc += ghnum; gbc -= ghnum; gdc += 2.0f * ghnum; }
+    else { ggc += ghnum; grc -= ghnum; gdc += 4.0f * ghnum; }
+    float gM = grc + ggc + gbc;
+    gx[0] = -grc; gx[1] = -ggc; gx[2] = -gbc;
+    float gdelta = (m.delta != 0.f) ? gdc : 0.f;
+    const float Me = m.M + 1e-8f;
+    gdelta += gs / Me;
+    gM += -gs * m.s / Me;
+    gM += gv;
+    gM += gdelta;
+    const float gmn = -gdelta;
+    gx[m.a] += gM;
+    gx[m.imin] += gmn;
+  }
+};
+
+struct WbOp {                  // img_trans_torch_diff.py:51-57: clamp(lerp(im, im * 0.5 / (mean_HW(im) + 1e-9), p), 0, 1)
+  static constexpr int NP = 4;                  // [0]: d/dp ; [1..3]: sum_px gg * x per channel (mean path)
+  const float* p; int stride; const float* mean_all; float f, bal[3];
+  __device__ void load(int b) {
+    f = p[(long)b * stride];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) bal[c] = 0.5f / mean_all[3 * b + c];
+  }
+  __device__ void fwd(const float* x, float* y) const {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      y[c] = clamp01(__fadd_rn(__fmul_rn(1.0f - f, x[c]), __fmul_rn(f, __fmul_rn(x[c], bal[c]))));
+  }
+  __device__ void bwd(const float* x, const float* g, float* gx, float* gp) const {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float wb = __fmul_rn(x[c], bal[c]);
+      const float pre = __fadd_rn(__fmul_rn(1.0f - f, x[c]), __fmul_rn(f, wb));
+      const float gg = in01(pre) ? g[c] : 0.f;
+      gx[c] = gg * ((1.0f - f) + f * bal[c]);
+      gp[0] += gg * (wb - x[c]);
+      gp[1 + c] += gg * x[c];
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
 template <class Op, int VEC, bool BWD>
 __global__ void __launch_bounds__(kThreads) pointwise_kernel(const float* __restrict__ in, const float* __restrict__ gout,
                                                             float* __restrict__ out, Op op, float* __restrict__ partial,
@@ -364,6 +556,43 @@ __global__ void __launch_bounds__(kThreads) contrast_bwd_mean_kernel(float* __re
   const float wc[3] = {0.299f, 0.587f, 0.114f};
   const long base = (long)b * 3 * HW;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * HW; i += gridDim.x * blockDim.x) gin[base + i] += wc[i / HW] * k;
+}
+
+// white balance: per-channel sums (forward pre-pass), mean finalize (+1e-9), backward mean path
+__global__ void __launch_bounds__(kThreads) chan_sum_kernel(const float* __restrict__ in, float* __restrict__ partial,
+                                                           int HW, int chunk) {
+  const int b = blockIdx.y;
+  const long base = (long)b * 3 * HW;
+  const int p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, HW);
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int px = p0 + threadIdx.x; px < p1; px += kThreads) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[c] += in[base + (long)c * HW + px];
+  }
+  block_reduce_store<3>(acc, partial + ((long)b * gridDim.x + blockIdx.x) * 3);
+}
+__global__ void chan_mean_finalize(const float* __restrict__ partial, int nblk, float inv_hw, float* __restrict__ mean) {
+  const int b = blockIdx.x;
+  if (threadIdx.x < 3) {
+    float s = 0.f;
+    for (int k = 0; k < nblk; ++k) s += partial[((long)b * nblk + k) * 3 + threadIdx.x];
+    mean[3 * b + threadIdx.x] = s * inv_hw + 1e-9f;
+  }
+}
+// gin[c] += d(loss)/d(mean_c) / HW with d/d(mean_c) = -p * (0.5 / mean_c^2) * sum_px gg * x_c
+__global__ void __launch_bounds__(kThreads) wb_bwd_mean_kernel(float* __restrict__ gin, const float* __restrict__ p, int stride,
+                                                              const float* __restrict__ mean, const float* __restrict__ sums,
+                                                              int HW) {
+  const int b = blockIdx.y;
+  const float f = p[(long)b * stride];
+  float k[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float mc = mean[3 * b + c];
+    k[c] = -f * (0.5f / (mc * mc)) * sums[4 * b + 1 + c] / (float)HW;
+  }
+  const long base = (long)b * 3 * HW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * HW; i += gridDim.x * blockDim.x) gin[base + i] += k[i / HW];
 }
 
 // ===============================================================================================================
@@ -767,6 +996,7 @@ long rgie_filter_ws_floats(int B, int H, int W) {
 int rgie_filter_param_count(int kind) {
   switch (kind) {
     case RGIE_F_EXPOSURE: case RGIE_F_SATURATION: case RGIE_F_CONTRAST: case RGIE_F_SHARP: case RGIE_F_BLUR: return 1;
+    case RGIE_F_GAMMA: case RGIE_F_BRIGHT: case RGIE_F_BW: case RGIE_F_HUE: case RGIE_F_WB: return 1;
     case RGIE_F_TONE: return 8;
     case RGIE_F_COLOR: return 24;
     case RGIE_F_SCALE: return 4;
@@ -797,6 +1027,23 @@ int rgie_filter_fwd(int kind, const float* in, float* out, const float* p, int p
       RGIE_LAUNCH_OK();
       ContrastOp op{p, p_stride, mu, 0.f, 0.f};
       return launch_pointwise<ContrastOp, false>(in, nullptr, out, op, nullptr, B, HW, st);
+    }
+    case RGIE_F_GAMMA: { GammaOp op{p, p_stride, 0.f}; return launch_pointwise<GammaOp, false>(in, nullptr, out, op, nullptr, B, HW, st); }
+    case RGIE_F_BRIGHT: { BrightOp op{p, p_stride, 0.f}; return launch_pointwise<BrightOp, false>(in, nullptr, out, op, nullptr, B, HW, st); }
+    case RGIE_F_BW: { BwOp op{p, p_stride, 0.f}; return launch_pointwise<BwOp, false>(in, nullptr, out, op, nullptr, B, HW, st); }
+    case RGIE_F_HUE: { HueOp op{p, p_stride, 0.f}; return launch_pointwise<HueOp, false>(in, nullptr, out, op, nullptr, B, HW, st); }
+    case RGIE_F_WB: {
+      RGIE_CHECK(ws != nullptr, "rgie_filter_fwd(wb): workspace required");
+      LaunchShape s = shape_for(HW);
+      float* partial = ws;                      // [B, nblk, 3]
+      float* mean = ws + (long)B * kMaxBlk * 4; // [B, 3]
+      dim3 grid(s.nblk, B);
+      chan_sum_kernel<<<grid, kThreads, 0, st>>>(in, partial, HW, s.chunk);
+      RGIE_LAUNCH_OK();
+      chan_mean_finalize<<<B, 32, 0, st>>>(partial, s.nblk, 1.0f / (float)HW, mean);
+      RGIE_LAUNCH_OK();
+      WbOp op; op.p = p; op.stride = p_stride; op.mean_all = mean;
+      return launch_pointwise<WbOp, false>(in, nullptr, out, op, nullptr, B, HW, st);
     }
     case RGIE_F_SHARP: {
       RGIE_CHECK(H >= 3 && W >= 3, "sharp: image too small");
@@ -877,6 +1124,49 @@ int rgie_filter_bwd(int kind, const float* in, const float* gout, float* gin, co
       contrast_bwd_mean_kernel<<<g2, kThreads, 0, st>>>(gin, p, p_stride, sums, 2, HW);
       RGIE_LAUNCH_OK();
       copy_strided_kernel<<<ceil_div(B, 128), 128, 0, st>>>(sums, 2, gp, gp_stride, B);   // sums[b,0] -> gp[b]
+      break;
+    }
+    case RGIE_F_GAMMA: {
+      GammaOp op{p, p_stride, 0.f};
+      if (int rc = launch_pointwise<GammaOp, true>(in, gout, gin, op, partial, B, HW, st)) return rc;
+      finalize_partials<<<B, 32, 0, st>>>(partial, s.nblk, 1, gp, gp_stride);
+      break;
+    }
+    case RGIE_F_BRIGHT: {
+      BrightOp op{p, p_stride, 0.f};
+      if (int rc = launch_pointwise<BrightOp, true>(in, gout, gin, op, partial, B, HW, st)) return rc;
+      finalize_partials<<<B, 32, 0, st>>>(partial, s.nblk, 1, gp, gp_stride);
+      break;
+    }
+    case RGIE_F_BW: {
+      BwOp op{p, p_stride, 0.f};
+      if (int rc = launch_pointwise<BwOp, true>(in, gout, gin, op, partial, B, HW, st)) return rc;
+      finalize_partials<<<B, 32, 0, st>>>(partial, s.nblk, 1, gp, gp_stride);
+      break;
+    }
+    case RGIE_F_HUE: {
+      HueOp op{p, p_stride, 0.f};
+      if (int rc = launch_pointwise<HueOp, true>(in, gout, gin, op, partial, B, HW, st)) return rc;
+      finalize_partials<<<B, 32, 0, st>>>(partial, s.nblk, 1, gp, gp_stride);
+      break;
+    }
+    case RGIE_F_WB: {
+      // channel means are recomputed (cheap) so that backward does not depend on forward-call state
+      float* mean = ws + (long)B * kMaxBlk * 4;   // [B,3]
+      float* sums = mean + 3L * B;                // [B,4]
+      dim3 grid(s.nblk, B);
+      chan_sum_kernel<<<grid, kThreads, 0, st>>>(in, partial, HW, s.chunk);
+      RGIE_LAUNCH_OK();
+      chan_mean_finalize<<<B, 32, 0, st>>>(partial, s.nblk, 1.0f / (float)HW, mean);
+      RGIE_LAUNCH_OK();
+      WbOp op; op.p = p; op.stride = p_stride; op.mean_all = mean;
+      if (int rc = launch_pointwise<WbOp, true>(in, gout, gin, op, partial, B, HW, st)) return rc;
+      finalize_partials<<<B, 32, 0, st>>>(partial, s.nblk, 4, sums, 4);
+      RGIE_LAUNCH_OK();
+      dim3 g2(plane_blocks(3 * HW), B);
+      wb_bwd_mean_kernel<<<g2, kThreads, 0, st>>>(gin, p, p_stride, mean, sums, HW);
+      RGIE_LAUNCH_OK();
+      copy_strided_kernel<<<ceil_div(B, 128), 128, 0, st>>>(sums, 4, gp, gp_stride, B);   // sums[b,0] -> gp[b]
       break;
     }
     case RGIE_F_SHARP: {

@@ -1,4 +1,5 @@
-"""GPU: the 8 default filter kernels (forward + backward) against the CPU oracle and the reference-generated goldens."""
+"""GPU: the filter kernels (8 default filters + gamma / brightness / b&w / hue / white balance; forward + backward)
+against the CPU oracle and the reference-generated goldens."""
 import os
 
 import pytest
@@ -27,6 +28,8 @@ def _param_tensor(name, val):
         return torch.tensor(val, dtype=torch.float32).view(1, 3, 8, 1)
     if name == "scale":
         return torch.tensor(val, dtype=torch.float32).view(1, 4)
+    if name == "bw":
+        return torch.tensor(val, dtype=torch.float32).view(1)      # the reference indexes bw_param[:, None, None, None]
     return torch.tensor(val, dtype=torch.float32)
 
 
@@ -44,6 +47,13 @@ SINGLE_CASES = [
     # torch.linspace (platform dependent); identity is checked separately (forward + d(image) only)
     ("scale", [1.0, 1.0, 0.0, 0.0]), ("scale", [1.2371, 1.1113, 9.37, 14.21]), ("scale", [1.5311, 1.0173, 30.19, 5.23]),
     ("scale", [1.0537, 1.3071, 0.0, 40.43]),
+    # the remaining pointwise filters of apply_params.  gamma < 1 is left out on purpose: the test
+    # image holds exact zeros, where d(x^gamma)/dx is +inf in the reference too
+    ("gamma", 1.0), ("gamma", 2.2), ("gamma", 1.3), ("gamma", 0.0),
+    ("bright", 0.0), ("bright", 0.3), ("bright", 1.0),
+    ("bw", 0.0), ("bw", 0.4), ("bw", 1.0),
+    ("hue", 0.0), ("hue", 0.7), ("hue", -2.1), ("hue", 3.0),
+    ("wb", 0.0), ("wb", 0.5), ("wb", 1.0),
 ]
 
 
