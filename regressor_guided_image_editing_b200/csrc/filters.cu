@@ -724,30 +724,67 @@ __device__ __forceinline__ bool gauss_weights(float sigma, float* w, float* dw) 
 }
 __device__ __forceinline__ int reflect(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * (n - 1) - i : i); }
 
-// horizontal pass: t = H_w(in) and (optionally) td = H_dw(in)
-__global__ void __launch_bounds__(kThreads) blur_h_kernel(const float* __restrict__ in, float* __restrict__ t,
-                                                         float* __restrict__ td, const float* __restrict__ p, int stride,
-                                                         int H, int W) {
-  __shared__ float w[kTaps], dw[kTaps];
-  __shared__ int is_delta;
-  const int b = blockIdx.z, c = blockIdx.y;
+// The per-image 1-D kernels are computed ONCE per launch group by blur_weights_kernel into wbuf[b] = {w[25], dw[25],
+// is_delta} (a serial 25-term expf loop per thread block was the dominant cost of the pass kernels).  When the kernel is
+// an exact delta -- the reference's start value sigma = 1e-4, where d/d(sigma) underflows to 0 so Adam never moves it --
+// every pass degenerates to a float4 copy / clamp / mask.
+constexpr int kWStride = 2 * kTaps + 2;
+__global__ void blur_weights_kernel(const float* __restrict__ p, int stride, float* __restrict__ wbuf) {
+  const int b = blockIdx.x;
   if (threadIdx.x == 0) {
     float lw[kTaps], ldw[kTaps];
-    is_delta = gauss_weights(p[(long)b * stride], lw, ldw);
-    for (int k = 0; k < kTaps; ++k) { w[k] = lw[k]; dw[k] = ldw[k]; }
+    const bool delta = gauss_weights(p[(long)b * stride], lw, ldw);
+    float* o = wbuf + (long)b * kWStride;
+    for (int k = 0; k < kTaps; ++k) { o[k] = lw[k]; o[kTaps + k] = ldw[k]; }
+    o[2 * kTaps] = delta ? 1.f : 0.f;
   }
+}
+struct BlurW {
+  float w[kTaps], dw[kTaps];
+  int is_delta;
+};
+__device__ __forceinline__ void load_blur_w(const float* __restrict__ wbuf, int b, BlurW* sw) {
+  const float* o = wbuf + (long)b * kWStride;
+  if (threadIdx.x < kTaps) { sw->w[threadIdx.x] = o[threadIdx.x]; sw->dw[threadIdx.x] = o[kTaps + threadIdx.x]; }
+  if (threadIdx.x == 0) sw->is_delta = o[2 * kTaps] != 0.f;
   __syncthreads();
+}
+
+// horizontal pass: t = H_w(in) and (optionally) td = H_dw(in)
+__global__ void __launch_bounds__(kThreads) blur_h_kernel(const float* __restrict__ in, float* __restrict__ t,
+                                                         float* __restrict__ td, const float* __restrict__ wbuf,
+                                                         int H, int W) {
+  __shared__ BlurW sw;
+  const int b = blockIdx.z, c = blockIdx.y;
+  load_blur_w(wbuf, b, &sw);
   const long off = ((long)b * 3 + c) * H * W;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
-    if (is_delta) { t[off + i] = in[off + i]; if (td) td[off + i] = 0.f; continue; }
+  const int HW = H * W;
+  if (sw.is_delta) {
+    if ((HW & 3) == 0) {
+      const float4* s4 = reinterpret_cast<const float4*>(in + off);
+      float4* t4 = reinterpret_cast<float4*>(t + off);
+      float4* d4 = td ? reinterpret_cast<float4*>(td + off) : nullptr;
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW / 4; i += gridDim.x * blockDim.x) {
+        t4[i] = s4[i];
+        if (d4) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        t[off + i] = in[off + i];
+        if (td) td[off + i] = 0.f;
+      }
+    }
+    return;
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
     const int y = i / W, x = i - y * W;
     const float* row = in + off + (long)y * W;
     float s = 0.f, sd = 0.f;
 #pragma unroll
     for (int k = 0; k < kTaps; ++k) {
       const float v = row[reflect(x + k - kRad, W)];
-      s = fmaf(w[k], v, s);
-      sd = fmaf(dw[k], v, sd);
+      s = fmaf(sw.w[k], v, s);
+      sd = fmaf(sw.dw[k], v, sd);
     }
     t[off + i] = s;
     if (td) td[off + i] = sd;
@@ -755,54 +792,70 @@ __global__ void __launch_bounds__(kThreads) blur_h_kernel(const float* __restric
 }
 // vertical pass (forward): out = clamp(V_w(t))
 __global__ void __launch_bounds__(kThreads) blur_v_kernel(const float* __restrict__ t, float* __restrict__ out,
-                                                         const float* __restrict__ p, int stride, int H, int W) {
-  __shared__ float w[kTaps];
-  __shared__ int is_delta;
+                                                         const float* __restrict__ wbuf, int H, int W) {
+  __shared__ BlurW sw;
   const int b = blockIdx.z, c = blockIdx.y;
-  if (threadIdx.x == 0) {
-    float lw[kTaps];
-    is_delta = gauss_weights(p[(long)b * stride], lw, nullptr);
-    for (int k = 0; k < kTaps; ++k) w[k] = lw[k];
-  }
-  __syncthreads();
+  load_blur_w(wbuf, b, &sw);
   const long off = ((long)b * 3 + c) * H * W;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
-    if (is_delta) { out[off + i] = clamp01(t[off + i]); continue; }
+  const int HW = H * W;
+  if (sw.is_delta) {
+    if ((HW & 3) == 0) {
+      const float4* s4 = reinterpret_cast<const float4*>(t + off);
+      float4* o4 = reinterpret_cast<float4*>(out + off);
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW / 4; i += gridDim.x * blockDim.x) {
+        const float4 v = s4[i];
+        o4[i] = make_float4(clamp01(v.x), clamp01(v.y), clamp01(v.z), clamp01(v.w));
+      }
+    } else {
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) out[off + i] = clamp01(t[off + i]);
+    }
+    return;
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
     const int y = i / W, x = i - y * W;
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < kTaps; ++k) s = fmaf(w[k], t[off + (long)reflect(y + k - kRad, H) * W + x], s);
+    for (int k = 0; k < kTaps; ++k) s = fmaf(sw.w[k], t[off + (long)reflect(y + k - kRad, H) * W + x], s);
     out[off + i] = clamp01(s);
   }
 }
 // backward vertical: pre = V_w(t) -> mask; gm = g*mask; acc += gm * V_dw(t); writes gm (masked gradient)
 __global__ void __launch_bounds__(kThreads) blur_bwd_mask_kernel(const float* __restrict__ t, const float* __restrict__ gout,
-                                                                float* __restrict__ gm, const float* __restrict__ p,
-                                                                int stride, float* __restrict__ partial, int H, int W) {
-  __shared__ float w[kTaps], dw[kTaps];
-  __shared__ int is_delta;
+                                                                float* __restrict__ gm, const float* __restrict__ wbuf,
+                                                                float* __restrict__ partial, int H, int W) {
+  __shared__ BlurW sw;
   const int b = blockIdx.z, c = blockIdx.y;
-  if (threadIdx.x == 0) {
-    float lw[kTaps], ldw[kTaps];
-    is_delta = gauss_weights(p[(long)b * stride], lw, ldw);
-    for (int k = 0; k < kTaps; ++k) { w[k] = lw[k]; dw[k] = ldw[k]; }
-  }
-  __syncthreads();
+  load_blur_w(wbuf, b, &sw);
   const long off = ((long)b * 3 + c) * H * W;
+  const int HW = H * W;
   float acc[1] = {0.f};
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
-    if (is_delta) { gm[off + i] = in01(t[off + i]) ? gout[off + i] : 0.f; continue; }
-    const int y = i / W, x = i - y * W;
-    float s = 0.f, sd = 0.f;
-#pragma unroll
-    for (int k = 0; k < kTaps; ++k) {
-      const float v = t[off + (long)reflect(y + k - kRad, H) * W + x];
-      s = fmaf(w[k], v, s);
-      sd = fmaf(dw[k], v, sd);
+  if (sw.is_delta) {
+    if ((HW & 3) == 0) {
+      const float4* t4 = reinterpret_cast<const float4*>(t + off);
+      const float4* g4 = reinterpret_cast<const float4*>(gout + off);
+      float4* o4 = reinterpret_cast<float4*>(gm + off);
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW / 4; i += gridDim.x * blockDim.x) {
+        const float4 v = t4[i], g = g4[i];
+        o4[i] = make_float4(in01(v.x) ? g.x : 0.f, in01(v.y) ? g.y : 0.f, in01(v.z) ? g.z : 0.f, in01(v.w) ? g.w : 0.f);
+      }
+    } else {
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x)
+        gm[off + i] = in01(t[off + i]) ? gout[off + i] : 0.f;
     }
-    const float g = in01(s) ? gout[off + i] : 0.f;
-    gm[off + i] = g;
-    acc[0] += g * sd;
+  } else {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+      const int y = i / W, x = i - y * W;
+      float s = 0.f, sd = 0.f;
+#pragma unroll
+      for (int k = 0; k < kTaps; ++k) {
+        const float v = t[off + (long)reflect(y + k - kRad, H) * W + x];
+        s = fmaf(sw.w[k], v, s);
+        sd = fmaf(sw.dw[k], v, sd);
+      }
+      const float g = in01(s) ? gout[off + i] : 0.f;
+      gm[off + i] = g;
+      acc[0] += g * sd;
+    }
   }
   block_reduce_store<1>(acc, partial + ((long)b * 3 + c) * gridDim.x + blockIdx.x);
 }
@@ -811,40 +864,45 @@ __global__ void __launch_bounds__(kThreads) blur_bwd_mask_kernel(const float* __
 // optional: acc += out * other  (second d(sigma) term)
 template <int AXIS>
 __global__ void __launch_bounds__(kThreads) blur_bwd_t_kernel(const float* __restrict__ g, float* __restrict__ out,
-                                                             const float* __restrict__ other, const float* __restrict__ p,
-                                                             int stride, float* __restrict__ partial, int H, int W) {
-  __shared__ float w[kTaps];
-  __shared__ int is_delta;
+                                                             const float* __restrict__ other, const float* __restrict__ wbuf,
+                                                             float* __restrict__ partial, int H, int W) {
+  __shared__ BlurW sw;
   const int b = blockIdx.z, c = blockIdx.y;
-  if (threadIdx.x == 0) {
-    float lw[kTaps];
-    is_delta = gauss_weights(p[(long)b * stride], lw, nullptr);
-    for (int k = 0; k < kTaps; ++k) w[k] = lw[k];
-  }
-  __syncthreads();
+  load_blur_w(wbuf, b, &sw);
   const long off = ((long)b * 3 + c) * H * W;
+  const int HW = H * W;
   const int n = AXIS == 0 ? H : W;
   float acc[1] = {0.f};
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
-    if (is_delta) { out[off + i] = g[off + i]; continue; }
-    const int y = i / W, x = i - y * W;
-    const int pos = AXIS == 0 ? y : x;
-    float s = 0.f;
-    int us[3] = {pos, -pos, 2 * (n - 1) - pos};
-    bool ok[3] = {true, pos >= 1 && pos <= kRad, pos <= n - 2 && pos >= n - 1 - kRad};
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      if (!ok[q]) continue;
-#pragma unroll
-      for (int k = 0; k < kTaps; ++k) {
-        const int src = us[q] - k + kRad;
-        if (src < 0 || src >= n) continue;
-        const float v = AXIS == 0 ? g[off + (long)src * W + x] : g[off + (long)y * W + src];
-        s = fmaf(w[k], v, s);
-      }
+  if (sw.is_delta) {
+    // the kernel is a delta: out = g; the d(sigma) term multiplies by `other` = H_dw(in) = 0
+    if ((HW & 3) == 0) {
+      const float4* g4 = reinterpret_cast<const float4*>(g + off);
+      float4* o4 = reinterpret_cast<float4*>(out + off);
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW / 4; i += gridDim.x * blockDim.x) o4[i] = g4[i];
+    } else {
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) out[off + i] = g[off + i];
     }
-    out[off + i] = s;
-    if (other) acc[0] += s * other[off + i];
+  } else {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+      const int y = i / W, x = i - y * W;
+      const int pos = AXIS == 0 ? y : x;
+      float s = 0.f;
+      int us[3] = {pos, -pos, 2 * (n - 1) - pos};
+      bool ok[3] = {true, pos >= 1 && pos <= kRad, pos <= n - 2 && pos >= n - 1 - kRad};
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        if (!ok[q]) continue;
+#pragma unroll
+        for (int k = 0; k < kTaps; ++k) {
+          const int src = us[q] - k + kRad;
+          if (src < 0 || src >= n) continue;
+          const float v = AXIS == 0 ? g[off + (long)src * W + x] : g[off + (long)y * W + src];
+          s = fmaf(sw.w[k], v, s);
+        }
+      }
+      out[off + i] = s;
+      if (other) acc[0] += s * other[off + i];
+    }
   }
   if (other) block_reduce_store<1>(acc, partial + ((long)b * 3 + c) * gridDim.x + blockIdx.x);
 }
@@ -1055,11 +1113,14 @@ int rgie_filter_fwd(int kind, const float* in, float* out, const float* p, int p
     case RGIE_F_BLUR: {
       RGIE_CHECK(ws != nullptr, "rgie_filter_fwd(blur): workspace required");
       RGIE_CHECK(H > kRad && W > kRad, "blur: reflect padding needs H,W > 12");
-      float* t = ws;
+      float* wbuf = ws;                         // [B, kWStride]
+      float* t = ws + (long)B * kMaxBlk * 24;
       dim3 grid(plane_blocks(HW), 3, B);
-      blur_h_kernel<<<grid, kThreads, 0, st>>>(in, t, nullptr, p, p_stride, H, W);
+      blur_weights_kernel<<<B, 32, 0, st>>>(p, p_stride, wbuf);
       RGIE_LAUNCH_OK();
-      blur_v_kernel<<<grid, kThreads, 0, st>>>(t, out, p, p_stride, H, W);
+      blur_h_kernel<<<grid, kThreads, 0, st>>>(in, t, nullptr, wbuf, H, W);
+      RGIE_LAUNCH_OK();
+      blur_v_kernel<<<grid, kThreads, 0, st>>>(t, out, wbuf, H, W);
       RGIE_LAUNCH_OK();
       return 0;
     }
@@ -1185,19 +1246,22 @@ int rgie_filter_bwd(int kind, const float* in, const float* gout, float* gin, co
       RGIE_CHECK(H > kRad && W > kRad, "blur: reflect padding needs H,W > 12");
       const int nb = plane_blocks(HW);
       const long plane = (long)B * 3 * HW;
-      float* part2 = ws + (long)B * kMaxBlk * 12;
+      float* part2 = ws + (long)B * kMaxBlk * 8;
+      float* wbuf = ws + (long)B * kMaxBlk * 16;   // [B, kWStride] (kWStride = 52 <= 8 * kMaxBlk)
       float* t = ws + (long)B * kMaxBlk * 24;
       float* td = t + plane;
       float* gm = td + plane;
       dim3 grid(nb, 3, B);
-      blur_h_kernel<<<grid, kThreads, 0, st>>>(in, t, td, p, p_stride, H, W);
+      blur_weights_kernel<<<B, 32, 0, st>>>(p, p_stride, wbuf);
       RGIE_LAUNCH_OK();
-      blur_bwd_mask_kernel<<<grid, kThreads, 0, st>>>(t, gout, gm, p, p_stride, partial, H, W);
+      blur_h_kernel<<<grid, kThreads, 0, st>>>(in, t, td, wbuf, H, W);
+      RGIE_LAUNCH_OK();
+      blur_bwd_mask_kernel<<<grid, kThreads, 0, st>>>(t, gout, gm, wbuf, partial, H, W);
       RGIE_LAUNCH_OK();
       // t is dead now: reuse it for V^T gm
-      blur_bwd_t_kernel<0><<<grid, kThreads, 0, st>>>(gm, t, td, p, p_stride, part2, H, W);
+      blur_bwd_t_kernel<0><<<grid, kThreads, 0, st>>>(gm, t, td, wbuf, part2, H, W);
       RGIE_LAUNCH_OK();
-      blur_bwd_t_kernel<1><<<grid, kThreads, 0, st>>>(t, gin, nullptr, p, p_stride, nullptr, H, W);
+      blur_bwd_t_kernel<1><<<grid, kThreads, 0, st>>>(t, gin, nullptr, wbuf, nullptr, H, W);
       RGIE_LAUNCH_OK();
       // d(sigma) = sum(partial) + sum(part2): both live in one contiguous [B, 2*3*nb] view when nb == kMaxBlk*12/(3*nb)...
       // keep it simple: finalize each into a 2-float scratch then add
