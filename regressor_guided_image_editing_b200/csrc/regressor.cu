@@ -25,41 +25,42 @@ template <typename T>
 __global__ void __launch_bounds__(256) pack_crops_kernel(const float* __restrict__ img, const int* __restrict__ offsets,
                                                         const int* __restrict__ step_ptr, long off_step_stride,
                                                         T* __restrict__ zz, Geom g, int reps, int Hr, int Wr,
-                                                        int normalize, long total) {
+                                                        int normalize) {
+  // one thread block = one output line (n, i): no per-element division; a thread = one (pixel j, horizontal tap bi)
   const int* offs = offsets + (step_ptr ? (long)(*step_ptr) * off_step_stride : 0);
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int bi = (int)(idx & 3);
-    long q = idx >> 2;
-    const int j = (int)(q % g.W); q /= g.W;
-    const int i = (int)(q % g.H);
-    const int n = (int)(q / g.H);
-    const int b = n / reps;
-    const int top = offs[2 * n], left = offs[2 * n + 1];
+  const int n = blockIdx.x / g.H, i = blockIdx.x - n * g.H;
+  const int b = n / reps;
+  const int top = offs[2 * n], left = offs[2 * n + 1];
+  const float* src = img + (long)b * 3 * Hr * Wr + (long)(top + 2 * i) * Wr + left;
+  const long plane = (long)Hr * Wr;
+  T* dst_row = zz + geom_row(g, 0, n, i, 0) * 64;
+  for (int t = threadIdx.x; t < g.W * 4; t += blockDim.x) {
+    const int bi = t & 3, j = t >> 2;
     const int jj = j + bi - 2;
     T vals[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) vals[k] = from_f<T>(0.f);
     if (jj >= 0 && jj < g.W) {
 #pragma unroll
-      for (int pr = 0; pr < 2; ++pr)
+      for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int pc = 0; pc < 2; ++pc)
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float v = img[(((long)b * 3 + c) * Hr + (top + 2 * i + pr)) * Wr + (left + 2 * jj + pc)];
-            if (normalize) v = (v - 0.5f) / 0.5f;
-            vals[(pr * 2 + pc) * 3 + c] = from_f<T>(v);
-          }
+        for (int pr = 0; pr < 2; ++pr) {
+          const float* q = src + c * plane + pr * Wr + 2 * jj;     // (crop offsets are arbitrary: no vector alignment)
+          float v0 = q[0], v1 = q[1];
+          if (normalize) { v0 = (v0 - 0.5f) / 0.5f; v1 = (v1 - 0.5f) / 0.5f; }
+          vals[(pr * 2 + 0) * 3 + c] = from_f<T>(v0);
+          vals[(pr * 2 + 1) * 3 + c] = from_f<T>(v1);
+        }
     }
-    T* dst = zz + geom_row(g, 0, n, i, j) * 64 + bi * 16;
+    T* dst = dst_row + (long)j * 64 + bi * 16;
     if (sizeof(T) == 2) {
-      const uint4* s = reinterpret_cast<const uint4*>(vals);
-      reinterpret_cast<uint4*>(dst)[0] = s[0];
-      reinterpret_cast<uint4*>(dst)[1] = s[1];
+      const uint4* sv = reinterpret_cast<const uint4*>(vals);
+      reinterpret_cast<uint4*>(dst)[0] = sv[0];
+      reinterpret_cast<uint4*>(dst)[1] = sv[1];
     } else {
-      const float4* s = reinterpret_cast<const float4*>(vals);
+      const float4* sv = reinterpret_cast<const float4*>(vals);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) reinterpret_cast<float4*>(dst)[k] = s[k];
+      for (int k = 0; k < 4; ++k) reinterpret_cast<float4*>(dst)[k] = sv[k];
     }
   }
 }
@@ -282,14 +283,12 @@ __global__ void __launch_bounds__(256) crop_grad_gather_kernel(const float* __re
                                                               const int* __restrict__ step_ptr, long off_step_stride,
                                                               float* __restrict__ dimg, int B, int reps, int Hr, int Wr,
                                                               int crop, float nscale) {
+  // one thread block = one image line (b, Y); threads along X (no per-element division)
   const int* offs = offsets + (step_ptr ? (long)(*step_ptr) * off_step_stride : 0);
   const int Ho = crop / 2;
-  const long total = (long)B * Hr * Wr;
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int X = (int)(idx % Wr);
-    long q = idx / Wr;
-    const int Y = (int)(q % Hr);
-    const int b = (int)(q / Hr);
+  const int b = blockIdx.x / Hr, Y = blockIdx.x - b * Hr;
+  const long plane = (long)Hr * Wr;
+  for (int X = threadIdx.x; X < Wr; X += blockDim.x) {
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
     for (int r = 0; r < reps; ++r) {
       const int n = b * reps + r;
@@ -298,7 +297,6 @@ __global__ void __launch_bounds__(256) crop_grad_gather_kernel(const float* __re
       const float* p = dz + (((long)n * Ho + (y >> 1)) * Ho + (x >> 1)) * 16 + ((y & 1) * 2 + (x & 1)) * 3;
       s0 += p[0]; s1 += p[1]; s2 += p[2];
     }
-    const long plane = (long)Hr * Wr;
     float* o = dimg + (long)b * 3 * plane + (long)Y * Wr + X;
     o[0] = s0 * nscale; o[plane] = s1 * nscale; o[2 * plane] = s2 * nscale;
   }
@@ -845,14 +843,12 @@ int rgie_regressor_forward_ex(RgieRegressor* R, const float* img, int B, int Hr,
   R->offsets = offsets; R->step_ptr = step_ptr; R->off_stride = off_step_stride;
   R->B = B; R->reps = reps; R->Hr = Hr; R->Wr = Wr; R->normalize = normalize;
   const int N = R->N, H0 = R->H0, H1 = R->Hs[1];
-  const long tot_pack = (long)N * H0 * H0 * 4;
   if (R->dtype == 0) {
-    pack_crops_kernel<float><<<grid_for(tot_pack), 256, 0, st>>>(img, offsets, step_ptr, off_step_stride, (float*)R->zz,
-                                                               R->gZZ, reps, Hr, Wr, normalize, tot_pack);
+    pack_crops_kernel<float><<<N * H0, 256, 0, st>>>(img, offsets, step_ptr, off_step_stride, (float*)R->zz, R->gZZ, reps, Hr,
+                                                     Wr, normalize);
   } else {
-    pack_crops_kernel<__nv_bfloat16><<<grid_for(tot_pack), 256, 0, st>>>(img, offsets, step_ptr, off_step_stride,
-                                                                       (__nv_bfloat16*)R->zz, R->gZZ, reps, Hr, Wr,
-                                                                       normalize, tot_pack);
+    pack_crops_kernel<__nv_bfloat16><<<N * H0, 256, 0, st>>>(img, offsets, step_ptr, off_step_stride, (__nv_bfloat16*)R->zz,
+                                                             R->gZZ, reps, Hr, Wr, normalize);
   }
   RGIE_LAUNCH_OK();
   if (int rc = run_op(R, R->fwd_ops[0], st, 0)) return rc;
@@ -907,8 +903,7 @@ int rgie_regressor_backward(RgieRegressor* R, const float* dlogits, float* dimg,
     maxpool_bwd_kernel<__nv_bfloat16><<<N * R->Hs[1], 256, 0, st>>>((const __nv_bfloat16*)dP, R->arg, (__nv_bfloat16*)R->dC1, R->gS[1], R->gDY, 64);
   RGIE_LAUNCH_OK();
   if (int rc = run_op(R, R->bwd_ops[nb - 1], st, R->fwd_ops.size() + nb - 1)) return rc;
-  const long totg = (long)R->B * R->Hr * R->Wr;
-  crop_grad_gather_kernel<<<grid_for(totg), 256, 0, st>>>(R->dZ, R->offsets, R->step_ptr, R->off_stride, dimg, R->B, R->reps,
+  crop_grad_gather_kernel<<<R->B * R->Hr, 256, 0, st>>>(R->dZ, R->offsets, R->step_ptr, R->off_stride, dimg, R->B, R->reps,
                                                           R->Hr, R->Wr, R->crop, R->normalize ? 2.0f : 1.0f);
   RGIE_LAUNCH_OK();
   return 0;

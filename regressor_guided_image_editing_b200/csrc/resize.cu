@@ -82,61 +82,72 @@ static void free_axis(AxisTable* t) {
   cudaFree(t->xmin); cudaFree(t->xsize); cudaFree(t->w); cudaFree(t->t_start); cudaFree(t->t_out); cudaFree(t->t_w);
 }
 
-// out[plane, y, xo] = sum_j w[xo, j] * in[plane, y, xmin[xo] + j]        (AXIS 1: along x, rows = in_h)
-// out[plane, yo, x] = sum_j w[yo, j] * in[plane, ymin[yo] + j, x]        (AXIS 0: along y, cols = width)
+// out[plane, y, xo] = sum_j w[xo, j] * in[plane, y, xmin[xo] + j]        (AXIS 1: along x)
+// out[plane, yo, x] = sum_j w[yo, j] * in[plane, ymin[yo] + j, x]        (AXIS 0: along y)
+// One thread block = one OUTPUT ROW (blockIdx.x = plane * rows_out + row; no per-element division), threads along x so
+// every load / store of a warp is contiguous (AXIS 0) or within a few cache lines (AXIS 1: neighbouring outputs share taps).
 template <int AXIS>
 __global__ void __launch_bounds__(256) resample_fwd_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                           const int* __restrict__ xmin, const int* __restrict__ xsize,
                                                           const float* __restrict__ w, int kmax, int in_size, int out_size,
-                                                          int other, long total) {
-  // AXIS 1: in [planes, other, in_size] -> out [planes, other, out_size]
-  // AXIS 0: in [planes, in_size, other] -> out [planes, out_size, other]
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    long plane;
-    int o, r;
-    if (AXIS == 1) { o = (int)(i % out_size); long q = i / out_size; r = (int)(q % other); plane = q / other; }
-    else { r = (int)(i % other); long q = i / other; o = (int)(q % out_size); plane = q / out_size; }
+                                                          int other) {
+  // AXIS 1: in [planes, other, in_size] -> out [planes, other, out_size]   (row = plane * other + r)
+  // AXIS 0: in [planes, in_size, other] -> out [planes, out_size, other]   (row = plane * out_size + o)
+  const long row = blockIdx.x;
+  if (AXIS == 1) {
+    const float* src = in + row * (long)in_size;
+    float* dst = out + row * (long)out_size;
+    for (int o = threadIdx.x; o < out_size; o += blockDim.x) {
+      const int lo = xmin[o], n = xsize[o];
+      const float* wk = w + (long)o * kmax;
+      float s = 0.f;
+      for (int j = 0; j < n; ++j) s = fmaf(wk[j], src[lo + j], s);
+      dst[o] = s;
+    }
+  } else {
+    const long plane = row / out_size;
+    const int o = (int)(row - plane * out_size);
     const int lo = xmin[o], n = xsize[o];
     const float* wk = w + (long)o * kmax;
-    float s = 0.f;
-    if (AXIS == 1) {
-      const float* src = in + (plane * other + r) * (long)in_size + lo;
-      for (int j = 0; j < n; ++j) s = fmaf(wk[j], src[j], s);
-    } else {
-      const float* src = in + (plane * in_size + lo) * (long)other + r;
-      for (int j = 0; j < n; ++j) s = fmaf(wk[j], src[(long)j * other], s);
+    const float* src = in + (plane * in_size + lo) * (long)other;
+    float* dst = out + row * (long)other;
+    for (int r = threadIdx.x; r < other; r += blockDim.x) {
+      float s = 0.f;
+      for (int j = 0; j < n; ++j) s = fmaf(wk[j], src[(long)j * other + r], s);
+      dst[r] = s;
     }
-    out[i] = s;
   }
 }
-// transpose: gin[plane, .., s] = sum_e t_w[e] * gout[plane, .., t_out[e]]
+// transpose: gin[plane, .., s] = sum_e t_w[e] * gout[plane, .., t_out[e]]    (one block = one row of gin)
 template <int AXIS>
 __global__ void __launch_bounds__(256) resample_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin,
                                                           const int* __restrict__ t_start, const int* __restrict__ t_out,
                                                           const float* __restrict__ t_w, int in_size, int out_size,
-                                                          int other, long total) {
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    long plane;
-    int s_idx, r;
-    if (AXIS == 1) { s_idx = (int)(i % in_size); long q = i / in_size; r = (int)(q % other); plane = q / other; }
-    else { r = (int)(i % other); long q = i / other; s_idx = (int)(q % in_size); plane = q / in_size; }
-    float s = 0.f;
-    const int e0 = t_start[s_idx], e1 = t_start[s_idx + 1];
-    if (AXIS == 1) {
-      const float* src = gout + (plane * other + r) * (long)out_size;
+                                                          int other) {
+  // AXIS 1: gout [planes, other, out_size] -> gin [planes, other, in_size]   (row = plane * other + r)
+  // AXIS 0: gout [planes, out_size, other] -> gin [planes, in_size, other]   (row = plane * in_size + s)
+  const long row = blockIdx.x;
+  if (AXIS == 1) {
+    const float* src = gout + row * (long)out_size;
+    float* dst = gin + row * (long)in_size;
+    for (int s_idx = threadIdx.x; s_idx < in_size; s_idx += blockDim.x) {
+      float s = 0.f;
+      const int e0 = t_start[s_idx], e1 = t_start[s_idx + 1];
       for (int e = e0; e < e1; ++e) s = fmaf(t_w[e], src[t_out[e]], s);
-    } else {
-      const float* src = gout + plane * (long)out_size * other + r;
-      for (int e = e0; e < e1; ++e) s = fmaf(t_w[e], src[(long)t_out[e] * other], s);
+      dst[s_idx] = s;
     }
-    gin[i] = s;
+  } else {
+    const long plane = row / in_size;
+    const int s_idx = (int)(row - plane * in_size);
+    const int e0 = t_start[s_idx], e1 = t_start[s_idx + 1];
+    const float* src = gout + plane * (long)out_size * other;
+    float* dst = gin + row * (long)other;
+    for (int r = threadIdx.x; r < other; r += blockDim.x) {
+      float s = 0.f;
+      for (int e = e0; e < e1; ++e) s = fmaf(t_w[e], src[(long)t_out[e] * other + r], s);
+      dst[r] = s;
+    }
   }
-}
-
-static int grid_for(long total) {
-  long g = (total + 255) / 256;
-  long cap = 148L * 16;
-  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
 }  // namespace rgie
@@ -170,13 +181,11 @@ void rgie_resize_destroy(RgieResize* r) {
 int rgie_resize_fwd(const RgieResize* r, const float* in, float* out, int planes, float* tmp, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   RGIE_CHECK(r && in && out && tmp && planes > 0, "rgie_resize_fwd: bad arguments");
-  long t1 = (long)planes * r->in_h * r->out_w;
-  resample_fwd_kernel<1><<<grid_for(t1), 256, 0, st>>>(in, tmp, r->ax_w.xmin, r->ax_w.xsize, r->ax_w.w, r->ax_w.kmax,
-                                                       r->in_w, r->out_w, r->in_h, t1);
+  resample_fwd_kernel<1><<<planes * r->in_h, 256, 0, st>>>(in, tmp, r->ax_w.xmin, r->ax_w.xsize, r->ax_w.w, r->ax_w.kmax,
+                                                           r->in_w, r->out_w, r->in_h);
   RGIE_LAUNCH_OK();
-  long t2 = (long)planes * r->out_h * r->out_w;
-  resample_fwd_kernel<0><<<grid_for(t2), 256, 0, st>>>(tmp, out, r->ax_h.xmin, r->ax_h.xsize, r->ax_h.w, r->ax_h.kmax,
-                                                       r->in_h, r->out_h, r->out_w, t2);
+  resample_fwd_kernel<0><<<planes * r->out_h, 256, 0, st>>>(tmp, out, r->ax_h.xmin, r->ax_h.xsize, r->ax_h.w, r->ax_h.kmax,
+                                                            r->in_h, r->out_h, r->out_w);
   RGIE_LAUNCH_OK();
   return 0;
 }
@@ -185,13 +194,11 @@ int rgie_resize_bwd(const RgieResize* r, const float* gout, float* gin, int plan
   cudaStream_t st = (cudaStream_t)stream;
   RGIE_CHECK(r && gout && gin && tmp && planes > 0, "rgie_resize_bwd: bad arguments");
   // transpose of (vertical o horizontal) = horizontal^T o vertical^T ; tmp: [planes, in_h, out_w]
-  long t1 = (long)planes * r->in_h * r->out_w;
-  resample_bwd_kernel<0><<<grid_for(t1), 256, 0, st>>>(gout, tmp, r->ax_h.t_start, r->ax_h.t_out, r->ax_h.t_w, r->in_h,
-                                                       r->out_h, r->out_w, t1);
+  resample_bwd_kernel<0><<<planes * r->in_h, 256, 0, st>>>(gout, tmp, r->ax_h.t_start, r->ax_h.t_out, r->ax_h.t_w, r->in_h,
+                                                           r->out_h, r->out_w);
   RGIE_LAUNCH_OK();
-  long t2 = (long)planes * r->in_h * r->in_w;
-  resample_bwd_kernel<1><<<grid_for(t2), 256, 0, st>>>(tmp, gin, r->ax_w.t_start, r->ax_w.t_out, r->ax_w.t_w, r->in_w,
-                                                       r->out_w, r->in_h, t2);
+  resample_bwd_kernel<1><<<planes * r->in_h, 256, 0, st>>>(tmp, gin, r->ax_w.t_start, r->ax_w.t_out, r->ax_w.t_w, r->in_w,
+                                                           r->out_w, r->in_h);
   RGIE_LAUNCH_OK();
   return 0;
 }
