@@ -884,6 +884,182 @@ gemm_patch_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
   }
 }
 
+// ===============================================================================================================
+// conv1 input gradient, "horizontal taps as N":  the 7x7/2 stem's input gradient in the 2x2 phase-split form is a 4x4-tap
+// convolution of the 64-channel gradient with only 12 outputs per pixel.  With N = 12(16) every one of the 64 MMAs of a
+// tile re-reads its 128 x 16 operand slice from shared memory for 16 columns of output -- the patch kernel above is
+// bound by those reads.  Here the four HORIZONTAL taps become the N dimension instead:
+//     D[r, (j, q)] = sum_yi sum_co  dC1[r + (yi + dy0) lines, co] * W[(j, q), yi, co]          N = 4 x 12 = 48, K = 4 x 64
+// over a source patch of 8 lines x 16 pixels (one 3-D TMA box of 11 lines serves the 4 vertical taps), 16 MMAs per
+// tile instead of 64, and the epilogue finishes the horizontal part in registers:
+//     dZ[(l, w), q] = sum_j D[(l, w + j + dx0), (j, q)]                                       warp shuffles inside a 16-lane line
+// A tile therefore yields 8 x 13 output pixels (source columns 1..13 of its 16); tiles step by 13 columns.
+// ===============================================================================================================
+constexpr int HS_NJ = 4, HS_NQ = 12, HS_N = HS_NJ * HS_NQ, HS_NY = 4, HS_OUTW = 16 - (HS_NJ - 1);
+constexpr int HS_SLAB_BYTES = (8 + HS_NY - 1) * 16 * 128;      // 22528
+constexpr int HS_SLABS = 6;
+constexpr int HS_W_TAP_BYTES = HS_N * BK * 2;                   // 6144
+struct HsSmem {
+  static constexpr int A_OFF = 0;
+  static constexpr int W_OFF = HS_SLABS * HS_SLAB_BYTES;
+  static constexpr int BAR_OFF = W_OFF + HS_NY * HS_W_TAP_BYTES;   // afull[S], aempty[S], tfull[4], tempty[4], wfull
+  static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * HS_SLABS + 10) * 8;
+  static constexpr int TOTAL = TMEM_PTR_OFF + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;
+};
+struct HsParams {
+  int WT;            // column tiles per line group
+  FastDiv fd_wt;
+  int dy0, dx0;      // first vertical / horizontal tap offset (lines / pixels)
+  int col0;          // source column of tile 0, lane 0 (pad_l + dx0 so that output lane -dx0 is the first valid pixel)
+  long lines;        // pixel lines of the source tensor
+};
+
+__global__ void __launch_bounds__(num_threads(8), 1)
+conv_hshare_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmB, const GemmDesc d,
+                   const HsParams hp, const int num_tiles) {
+  using L = HsSmem;
+  constexpr int NACC = 4;
+  constexpr int ACC_COLS = 64;                    // accumulator stride in TMEM columns (48 used)
+  constexpr uint32_t TMEM_COLS = NACC * ACC_COLS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_base + L::BAR_OFF;
+  auto afull_bar = [&](int s) { return bar_base + 8u * s; };
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (HS_SLABS + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * HS_SLABS + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * HS_SLABS + NACC + a); };
+  const uint32_t wfull_bar = bar_base + 8u * (2 * HS_SLABS + 2 * NACC);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_PTR_OFF);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA3) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+    for (int s = 0; s < HS_SLABS; ++s) {
+      mbar_init(afull_bar(s), 1);
+      mbar_init(aempty_bar(s), 1);
+    }
+    for (int a = 0; a < NACC; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    mbar_init(wfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_base + L::TMEM_PTR_OFF),
+                 "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(wfull_bar, (uint32_t)(HS_NY * HS_W_TAP_BYTES));
+      for (int t = 0; t < HS_NY; ++t) tma_load_2d(smem_base + L::W_OFF + t * HS_W_TAP_BYTES, &tmB, t * BK, 0, wfull_bar);
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int g = (int)hp.fd_wt.div((uint32_t)tile), k = tile - g * hp.WT;
+        mbar_wait(aempty_bar(slot), phase ^ 1);
+        mbar_expect_tx(afull_bar(slot), HS_SLAB_BYTES);
+        tma_load_3d(smem_base + L::A_OFF + slot * HS_SLAB_BYTES, &tmA3, 0, hp.col0 + HS_OUTW * k, 8 * g + hp.dy0, afull_bar(slot));
+        if (++slot == HS_SLABS) { slot = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, HS_N);
+      mbar_wait(wfull_bar, 0);
+      const uint64_t wdesc0 = make_smem_desc(smem_base + L::W_OFF);
+      int slot = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it % NACC;
+        const uint32_t acc_phase = (it / NACC) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * ACC_COLS);
+        mbar_wait(afull_bar(slot), phase);
+        tcgen05_fence_after();
+        const uint64_t adesc0 = make_smem_desc(smem_base + L::A_OFF + slot * HS_SLAB_BYTES);
+#pragma unroll
+        for (int yi = 0; yi < HS_NY; ++yi) {
+          // vertical tap yi: the same box, yi lines of 16 pixels (= 2 swizzle atoms = 128 descriptor units) further down
+          const uint64_t adesc = adesc0 + (uint64_t)(yi * 128);
+          const uint64_t bdesc = wdesc0 + (uint64_t)(yi * (HS_W_TAP_BYTES >> 4));
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk)
+            umma_bf16(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (yi | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(aempty_bar(slot));
+        if (++slot == HS_SLABS) { slot = 0; phase ^= 1; }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    // ===================== epilogue: two groups of 4 warps take alternate tiles =====================
+    const int q4 = warp & 3;                       // TMEM lane quarter: rows 32 q4 .. 32 q4 + 31 = source lines 2 q4, 2 q4 + 1
+    const int part = (warp - 2) >> 2;
+    const int row = q4 * 32 + lane;
+    const int l = row >> 4, w = row & 15;
+    const bool w_ok = w >= -hp.dx0 && w < -hp.dx0 + HS_OUTW;
+    float* dz = reinterpret_cast<float*>(d.D);
+    for (int it = part, tile = blockIdx.x + part * gridDim.x; tile < num_tiles; it += 2, tile += 2 * gridDim.x) {
+      const int g = (int)hp.fd_wt.div((uint32_t)tile), k = tile - g * hp.WT;
+      const int acc = it % NACC;
+      const uint32_t acc_phase = (it / NACC) & 1;
+      const long line = 8L * g + l;
+      const int col = hp.col0 + HS_OUTW * k + w;
+      long dest = -1;
+      if (w_ok && line < hp.lines && col < d.src.P) dest = map_row(d.src, d.dst_kind, d.dst, line * d.src.P + col);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * ACC_COLS);
+      uint32_t r0[32], r1[16];
+      tmem_ld<32>(taddr, r0);
+      tmem_ld<16>(taddr + 32u, r1);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));   // the accumulator is in registers: release it before the shuffles
+      float o[HS_NQ];
+#pragma unroll
+      for (int qq = 0; qq < HS_NQ; ++qq) o[qq] = 0.f;
+#pragma unroll
+      for (int j = 0; j < HS_NJ; ++j) {
+#pragma unroll
+        for (int qq = 0; qq < HS_NQ; ++qq) {
+          const int n = j * HS_NQ + qq;
+          const float v = __uint_as_float(n < 32 ? r0[n] : r1[n - 32]);
+          // output pixel w needs D[(l, w + j + dx0), (j, q)]: pull it from the lane that holds that source pixel
+          o[qq] += __shfl_sync(0xffffffffu, v, lane + j + hp.dx0);
+        }
+      }
+      if (dest >= 0) {
+        float4* op = reinterpret_cast<float4*>(dz + dest * d.ldd);
+        op[0] = make_float4(o[0], o[1], o[2], o[3]);
+        op[1] = make_float4(o[4], o[5], o[6], o[7]);
+        op[2] = make_float4(o[8], o[9], o[10], o[11]);
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -994,6 +1170,7 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
   p->d = d;
   p->bn = bn;
   p->patch = 0;
+  p->special = 0;
   // ---- patch-tile variant: Cin = 64, one N tile, single-plane source whose rows are whole pixel lines, taps on a
   //      (dy, dx) grid of at most 4 x 4 with |dx| well below the pitch
   //      Measured on B200 (320 crops): 3x3 layer1 0.52 -> 0.41 ms, conv1 forward 1.08 -> 0.76 ms, conv1 input gradient
@@ -1095,8 +1272,56 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
   return make_map_2d(&p->tmB, d.Wt, (uint64_t)d.ntaps * d.Cin + (d.A2 ? d.Cin2 : 0), (uint64_t)d.n_pad, BK, (uint32_t)bn);
 }
 
+// Plan for conv_hshare_kernel.  d: the 16-tap input-gradient descriptor of the flat formulation (geometry, source,
+// destination); Wh: [48, 4 * 64] bf16, row j * 12 + q, column yi * 64 + co; taps (dy0 + yi, dx0 + j).
+int build_conv_hshare_sm100(const GemmDesc& d, const void* Wh, int dy0, int dx0, GemmPlanSm100* p) {
+  RGIE_CHECK(d.Cin == 64 && d.src.planes == 1 && d.d_fp32 && d.ldd >= HS_NQ && d.ldd % 4 == 0 && d.a_rows == d.src.rows(),
+             "conv_hshare: unsupported descriptor");
+  RGIE_CHECK(dx0 <= 0 && dx0 + HS_NJ - 1 >= 0 && d.src.pad_l + dx0 >= 0, "conv_hshare: tap range");
+  p->d = d;
+  p->bn = HS_N;
+  p->patch = 0; p->epi = 0;
+  p->special = 1;
+  const int P = d.src.P;
+  const long lines = d.a_rows / P;
+  p->hs_wt = ceil_div(d.src.W, HS_OUTW);
+  p->hs_dy0 = dy0; p->hs_dx0 = dx0; p->hs_col0 = d.src.pad_l + dx0; p->hs_lines = lines;
+  p->num_m_tiles = (int)(((lines + 7) / 8) * p->hs_wt);
+  p->num_n_tiles = 1;
+  const int sms = gemm_sm100_num_sms();
+  p->grid = p->num_m_tiles < sms ? p->num_m_tiles : sms;
+  // A as [C = 64, P, lines] with a box of 16 pixels x 11 lines
+  PFN_encodeTiled enc = get_encode_fn();
+  RGIE_CHECK(enc != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
+  cuuint64_t gdim[3] = {64, (cuuint64_t)P, (cuuint64_t)lines};
+  cuuint64_t gstride[2] = {64 * 2, (cuuint64_t)P * 64 * 2};
+  cuuint32_t box[3] = {64, 16, 8 + HS_NY - 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(&p->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d.A), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (hshare) failed with CUresult " + std::to_string((int)r));
+  p->tmA2 = p->tmA; p->tmD = p->tmA; p->tmR = p->tmA;
+  return make_map_2d(&p->tmB, Wh, (uint64_t)HS_NY * 64, (uint64_t)HS_N, BK, (uint32_t)HS_N);
+}
+
+static int run_conv_hshare(const GemmPlanSm100& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    RGIE_CUDA_OK(cudaFuncSetAttribute(conv_hshare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HsSmem::DYN_BYTES));
+    attr_set = true;
+  }
+  HsParams hp;
+  hp.WT = p.hs_wt; hp.fd_wt = make_fastdiv((uint32_t)p.hs_wt); hp.dy0 = p.hs_dy0; hp.dx0 = p.hs_dx0; hp.col0 = p.hs_col0;
+  hp.lines = p.hs_lines;
+  conv_hshare_kernel<<<p.grid, num_threads(8), HsSmem::DYN_BYTES, st>>>(p.tmA, p.tmB, p.d, hp, p.num_m_tiles);
+  RGIE_LAUNCH_OK();
+  return 0;
+}
+
 int run_gemm_sm100(const GemmPlanSm100& p, cudaStream_t st) {
   if (p.d.m_end <= p.d.m_begin) return 0;
+  if (p.special == 1) return run_conv_hshare(p, st);
   if (p.patch == 1) return run_patch<64, 3, 3>(p, st);     // 3x3, 64 -> 64 (layer1)
   if (p.patch == 2) return run_patch<64, 4, 1>(p, st);     // conv1 forward: 4 vertical taps over the packed input
   if (p.patch == 3) return run_patch<16, 4, 4>(p, st);     // conv1 input gradient: 4 x 4 taps, 64 -> 16

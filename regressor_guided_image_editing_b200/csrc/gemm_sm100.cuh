@@ -12,11 +12,15 @@ struct GemmPlanSm100 {
   int bn;
   // patch-tile variant (gemm_sm100.cu: gemm_patch_kernel): taps on a (dy, dx) grid, 16 x 8 pixel output tiles
   int patch, patch_ny, patch_nx, patch_dy0, patch_dx0, patch_wt, patch_tap[4][4];
+  // special == 1: conv_hshare_kernel (conv1 input gradient with the horizontal taps as the N dimension)
+  int special, hs_wt, hs_dy0, hs_dx0, hs_col0;
+  long hs_lines;
   int num_m_tiles, num_n_tiles;
   int grid;
 };
 
 int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p);
+int build_conv_hshare_sm100(const GemmDesc& d, const void* Wh, int dy0, int dx0, GemmPlanSm100* p);
 int run_gemm_sm100(const GemmPlanSm100& p, cudaStream_t st);
 int gemm_sm100_num_sms();
 

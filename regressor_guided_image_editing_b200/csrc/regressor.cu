@@ -6,6 +6,7 @@
 // zero-padded flat pixel layout; stride-2 convs read a 2x2 phase-split layout so they are row shifts too; conv1 7x7/2
 // becomes 4 vertical taps over a space-to-depth + 4-horizontal-tap packed input with 64 channels).  Backward keeps only
 // the post-ReLU activations (for the ReLU masks) and the max-pool argmax; weight gradients are never computed.
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -825,7 +826,33 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
       for (int j = 0; j < 4; ++j) d.row_off[a * 4 + j] = -((long)(a - 2) * R->gDY.P + ((3 - j) - 2));   // ascending in j
     d.m_begin = 0; d.m_end = R->gDY.rows(); d.Cout = 16;
     d.src = R->gDY; d.dst_kind = DST_TO_PLAIN; d.dst = R->gDY; d.D = R->dZ; d.ldd = 16; d.d_fp32 = 1;
-    if (int rc = add_op(R, R->bwd_ops, d)) return rc;
+    static const int env_hs = getenv("RGIE_CONV1_HSHARE") ? atoi(getenv("RGIE_CONV1_HSHARE")) : 1;
+    if (R->precision == RGIE_PREC_BF16 && env_hs) {
+      // tcgen05 path: the four horizontal taps become the N dimension (gemm_sm100.cu: conv_hshare_kernel).
+      // Wh[(j*12 + q), yi*64 + co] = weight of tap (dy = yi - 1, dx = j - 1) for output q = (pr*2+pc)*3 + c; in the 16-tap
+      // matrix above tap slot (a, j) has dy = 2 - a, dx = j - 1, so yi = 3 - a.
+      std::vector<float> wh((size_t)48 * 256, 0.f);
+      // rebuild from the folded conv1 weights exactly like wc1t (same index algebra)
+      for (int k = 0; k < 64; ++k)
+        for (int c = 0; c < 3; ++c)
+          for (int r = 0; r < 7; ++r)
+            for (int s7 = 0; s7 < 7; ++s7) {
+              const int dr = r - 3, dc = s7 - 3;
+              const int pr = dr & 1, pc = dc & 1;
+              const int a = (dr - pr) / 2, b = (dc - pc) / 2;      // in {-2,..,1}
+              const int ai = a + 2, bi = b + 2, q = (pr * 2 + pc) * 3 + c;
+              const int j = 3 - bi, yi = 3 - ai;
+              wh[(size_t)(j * 12 + q) * 256 + yi * 64 + k] = conv1.w[((k * 3 + c) * 7 + r) * 7 + s7];
+            }
+      void* wh_dev = nullptr;
+      if (int rc = upload(R, wh, &wh_dev)) return rc;
+      GemmOp op;
+      op.d = d;
+      if (int rc = build_conv_hshare_sm100(d, wh_dev, -1, -1, &op.plan)) return rc;
+      R->bwd_ops.push_back(op);
+    } else {
+      if (int rc = add_op(R, R->bwd_ops, d)) return rc;
+    }
   }
   RGIE_CUDA_OK(cudaDeviceSynchronize());
   guard.ok = true;
