@@ -751,8 +751,12 @@ __device__ __forceinline__ void load_blur_w(const float* __restrict__ wbuf, int 
 }
 
 // horizontal pass: t = H_w(in) and (optionally) td = H_dw(in)
+// Delta images (sigma ~ 0: the whole blur is the identity) are FINISHED here, the later passes skip them:
+//   forward  (fin = out,  gout = null): out = clamp(in)
+//   backward (fin = gin,  gout = g)   : gin = g * [0 <= in <= 1], d(sigma) = 0
 __global__ void __launch_bounds__(kThreads) blur_h_kernel(const float* __restrict__ in, float* __restrict__ t,
                                                          float* __restrict__ td, const float* __restrict__ wbuf,
+                                                         float* __restrict__ fin, const float* __restrict__ gout,
                                                          int H, int W) {
   __shared__ BlurW sw;
   const int b = blockIdx.z, c = blockIdx.y;
@@ -762,16 +766,21 @@ __global__ void __launch_bounds__(kThreads) blur_h_kernel(const float* __restric
   if (sw.is_delta) {
     if ((HW & 3) == 0) {
       const float4* s4 = reinterpret_cast<const float4*>(in + off);
-      float4* t4 = reinterpret_cast<float4*>(t + off);
-      float4* d4 = td ? reinterpret_cast<float4*>(td + off) : nullptr;
+      const float4* g4 = gout ? reinterpret_cast<const float4*>(gout + off) : nullptr;
+      float4* o4 = reinterpret_cast<float4*>(fin + off);
       for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW / 4; i += gridDim.x * blockDim.x) {
-        t4[i] = s4[i];
-        if (d4) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 v = s4[i];
+        if (g4) {
+          const float4 g = g4[i];
+          o4[i] = make_float4(in01(v.x) ? g.x : 0.f, in01(v.y) ? g.y : 0.f, in01(v.z) ? g.z : 0.f, in01(v.w) ? g.w : 0.f);
+        } else {
+          o4[i] = make_float4(clamp01(v.x), clamp01(v.y), clamp01(v.z), clamp01(v.w));
+        }
       }
     } else {
       for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
-        t[off + i] = in[off + i];
-        if (td) td[off + i] = 0.f;
+        const float v = in[off + i];
+        fin[off + i] = gout ? (in01(v) ? gout[off + i] : 0.f) : clamp01(v);
       }
     }
     return;
@@ -798,19 +807,7 @@ __global__ void __launch_bounds__(kThreads) blur_v_kernel(const float* __restric
   load_blur_w(wbuf, b, &sw);
   const long off = ((long)b * 3 + c) * H * W;
   const int HW = H * W;
-  if (sw.is_delta) {
-    if ((HW & 3) == 0) {
-      const float4* s4 = reinterpret_cast<const float4*>(t + off);
-      float4* o4 = reinterpret_cast<float4*>(out + off);
-      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW / 4; i += gridDim.x * blockDim.x) {
-        const float4 v = s4[i];
-        o4[i] = make_float4(clamp01(v.x), clamp01(v.y), clamp01(v.z), clamp01(v.w));
-      }
-    } else {
-      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) out[off + i] = clamp01(t[off + i]);
-    }
-    return;
-  }
+  if (sw.is_delta) return;                       // finished by blur_h_kernel
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
     const int y = i / W, x = i - y * W;
     float s = 0.f;
@@ -830,18 +827,7 @@ __global__ void __launch_bounds__(kThreads) blur_bwd_mask_kernel(const float* __
   const int HW = H * W;
   float acc[1] = {0.f};
   if (sw.is_delta) {
-    if ((HW & 3) == 0) {
-      const float4* t4 = reinterpret_cast<const float4*>(t + off);
-      const float4* g4 = reinterpret_cast<const float4*>(gout + off);
-      float4* o4 = reinterpret_cast<float4*>(gm + off);
-      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW / 4; i += gridDim.x * blockDim.x) {
-        const float4 v = t4[i], g = g4[i];
-        o4[i] = make_float4(in01(v.x) ? g.x : 0.f, in01(v.y) ? g.y : 0.f, in01(v.z) ? g.z : 0.f, in01(v.w) ? g.w : 0.f);
-      }
-    } else {
-      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x)
-        gm[off + i] = in01(t[off + i]) ? gout[off + i] : 0.f;
-    }
+    // finished by blur_h_kernel; only the (zero) d(sigma) partial is written
   } else {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
       const int y = i / W, x = i - y * W;
@@ -874,14 +860,7 @@ __global__ void __launch_bounds__(kThreads) blur_bwd_t_kernel(const float* __res
   const int n = AXIS == 0 ? H : W;
   float acc[1] = {0.f};
   if (sw.is_delta) {
-    // the kernel is a delta: out = g; the d(sigma) term multiplies by `other` = H_dw(in) = 0
-    if ((HW & 3) == 0) {
-      const float4* g4 = reinterpret_cast<const float4*>(g + off);
-      float4* o4 = reinterpret_cast<float4*>(out + off);
-      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW / 4; i += gridDim.x * blockDim.x) o4[i] = g4[i];
-    } else {
-      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) out[off + i] = g[off + i];
-    }
+    // finished by blur_h_kernel (gin = masked g, d(sigma) = 0)
   } else {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
       const int y = i / W, x = i - y * W;
@@ -1118,7 +1097,7 @@ int rgie_filter_fwd(int kind, const float* in, float* out, const float* p, int p
       dim3 grid(plane_blocks(HW), 3, B);
       blur_weights_kernel<<<B, 32, 0, st>>>(p, p_stride, wbuf);
       RGIE_LAUNCH_OK();
-      blur_h_kernel<<<grid, kThreads, 0, st>>>(in, t, nullptr, wbuf, H, W);
+      blur_h_kernel<<<grid, kThreads, 0, st>>>(in, t, nullptr, wbuf, out, nullptr, H, W);
       RGIE_LAUNCH_OK();
       blur_v_kernel<<<grid, kThreads, 0, st>>>(t, out, wbuf, H, W);
       RGIE_LAUNCH_OK();
@@ -1254,7 +1233,7 @@ int rgie_filter_bwd(int kind, const float* in, const float* gout, float* gin, co
       dim3 grid(nb, 3, B);
       blur_weights_kernel<<<B, 32, 0, st>>>(p, p_stride, wbuf);
       RGIE_LAUNCH_OK();
-      blur_h_kernel<<<grid, kThreads, 0, st>>>(in, t, td, wbuf, H, W);
+      blur_h_kernel<<<grid, kThreads, 0, st>>>(in, t, td, wbuf, gin, gout, H, W);
       RGIE_LAUNCH_OK();
       blur_bwd_mask_kernel<<<grid, kThreads, 0, st>>>(t, gout, gm, wbuf, partial, H, W);
       RGIE_LAUNCH_OK();

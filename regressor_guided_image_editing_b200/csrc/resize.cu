@@ -84,37 +84,39 @@ static void free_axis(AxisTable* t) {
 
 // out[plane, y, xo] = sum_j w[xo, j] * in[plane, y, xmin[xo] + j]        (AXIS 1: along x)
 // out[plane, yo, x] = sum_j w[yo, j] * in[plane, ymin[yo] + j, x]        (AXIS 0: along y)
-// One thread block = one OUTPUT ROW (blockIdx.x = plane * rows_out + row; no per-element division), threads along x so
+constexpr int kRowsPerBlock = 8;
+// One thread block = kRowsPerBlock OUTPUT ROWS (row = plane * rows_out + r; no per-element division), threads along x so
 // every load / store of a warp is contiguous (AXIS 0) or within a few cache lines (AXIS 1: neighbouring outputs share taps).
 template <int AXIS>
 __global__ void __launch_bounds__(256) resample_fwd_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                           const int* __restrict__ xmin, const int* __restrict__ xsize,
                                                           const float* __restrict__ w, int kmax, int in_size, int out_size,
-                                                          int other) {
+                                                          int other, long rows) {
   // AXIS 1: in [planes, other, in_size] -> out [planes, other, out_size]   (row = plane * other + r)
   // AXIS 0: in [planes, in_size, other] -> out [planes, out_size, other]   (row = plane * out_size + o)
-  const long row = blockIdx.x;
-  if (AXIS == 1) {
-    const float* src = in + row * (long)in_size;
-    float* dst = out + row * (long)out_size;
-    for (int o = threadIdx.x; o < out_size; o += blockDim.x) {
+  for (long row = (long)blockIdx.x * kRowsPerBlock; row < min((long)(blockIdx.x + 1) * kRowsPerBlock, rows); ++row) {
+    if (AXIS == 1) {
+      const float* src = in + row * (long)in_size;
+      float* dst = out + row * (long)out_size;
+      for (int o = threadIdx.x; o < out_size; o += blockDim.x) {
+        const int lo = xmin[o], n = xsize[o];
+        const float* wk = w + (long)o * kmax;
+        float s = 0.f;
+        for (int j = 0; j < n; ++j) s = fmaf(wk[j], src[lo + j], s);
+        dst[o] = s;
+      }
+    } else {
+      const long plane = row / out_size;
+      const int o = (int)(row - plane * out_size);
       const int lo = xmin[o], n = xsize[o];
       const float* wk = w + (long)o * kmax;
-      float s = 0.f;
-      for (int j = 0; j < n; ++j) s = fmaf(wk[j], src[lo + j], s);
-      dst[o] = s;
-    }
-  } else {
-    const long plane = row / out_size;
-    const int o = (int)(row - plane * out_size);
-    const int lo = xmin[o], n = xsize[o];
-    const float* wk = w + (long)o * kmax;
-    const float* src = in + (plane * in_size + lo) * (long)other;
-    float* dst = out + row * (long)other;
-    for (int r = threadIdx.x; r < other; r += blockDim.x) {
-      float s = 0.f;
-      for (int j = 0; j < n; ++j) s = fmaf(wk[j], src[(long)j * other + r], s);
-      dst[r] = s;
+      const float* src = in + (plane * in_size + lo) * (long)other;
+      float* dst = out + row * (long)other;
+      for (int r = threadIdx.x; r < other; r += blockDim.x) {
+        float s = 0.f;
+        for (int j = 0; j < n; ++j) s = fmaf(wk[j], src[(long)j * other + r], s);
+        dst[r] = s;
+      }
     }
   }
 }
@@ -123,29 +125,30 @@ template <int AXIS>
 __global__ void __launch_bounds__(256) resample_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin,
                                                           const int* __restrict__ t_start, const int* __restrict__ t_out,
                                                           const float* __restrict__ t_w, int in_size, int out_size,
-                                                          int other) {
+                                                          int other, long rows) {
   // AXIS 1: gout [planes, other, out_size] -> gin [planes, other, in_size]   (row = plane * other + r)
   // AXIS 0: gout [planes, out_size, other] -> gin [planes, in_size, other]   (row = plane * in_size + s)
-  const long row = blockIdx.x;
-  if (AXIS == 1) {
-    const float* src = gout + row * (long)out_size;
-    float* dst = gin + row * (long)in_size;
-    for (int s_idx = threadIdx.x; s_idx < in_size; s_idx += blockDim.x) {
-      float s = 0.f;
+  for (long row = (long)blockIdx.x * kRowsPerBlock; row < min((long)(blockIdx.x + 1) * kRowsPerBlock, rows); ++row) {
+    if (AXIS == 1) {
+      const float* src = gout + row * (long)out_size;
+      float* dst = gin + row * (long)in_size;
+      for (int s_idx = threadIdx.x; s_idx < in_size; s_idx += blockDim.x) {
+        float s = 0.f;
+        const int e0 = t_start[s_idx], e1 = t_start[s_idx + 1];
+        for (int e = e0; e < e1; ++e) s = fmaf(t_w[e], src[t_out[e]], s);
+        dst[s_idx] = s;
+      }
+    } else {
+      const long plane = row / in_size;
+      const int s_idx = (int)(row - plane * in_size);
       const int e0 = t_start[s_idx], e1 = t_start[s_idx + 1];
-      for (int e = e0; e < e1; ++e) s = fmaf(t_w[e], src[t_out[e]], s);
-      dst[s_idx] = s;
-    }
-  } else {
-    const long plane = row / in_size;
-    const int s_idx = (int)(row - plane * in_size);
-    const int e0 = t_start[s_idx], e1 = t_start[s_idx + 1];
-    const float* src = gout + plane * (long)out_size * other;
-    float* dst = gin + row * (long)other;
-    for (int r = threadIdx.x; r < other; r += blockDim.x) {
-      float s = 0.f;
-      for (int e = e0; e < e1; ++e) s = fmaf(t_w[e], src[(long)t_out[e] * other + r], s);
-      dst[r] = s;
+      const float* src = gout + plane * (long)out_size * other;
+      float* dst = gin + row * (long)other;
+      for (int r = threadIdx.x; r < other; r += blockDim.x) {
+        float s = 0.f;
+        for (int e = e0; e < e1; ++e) s = fmaf(t_w[e], src[(long)t_out[e] * other + r], s);
+        dst[r] = s;
+      }
     }
   }
 }
@@ -181,11 +184,13 @@ void rgie_resize_destroy(RgieResize* r) {
 int rgie_resize_fwd(const RgieResize* r, const float* in, float* out, int planes, float* tmp, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   RGIE_CHECK(r && in && out && tmp && planes > 0, "rgie_resize_fwd: bad arguments");
-  resample_fwd_kernel<1><<<planes * r->in_h, 256, 0, st>>>(in, tmp, r->ax_w.xmin, r->ax_w.xsize, r->ax_w.w, r->ax_w.kmax,
-                                                           r->in_w, r->out_w, r->in_h);
+  const long rows_in = (long)planes * r->in_h, rows_out = (long)planes * r->out_h;
+  const int g_in = (int)((rows_in + kRowsPerBlock - 1) / kRowsPerBlock), g_out = (int)((rows_out + kRowsPerBlock - 1) / kRowsPerBlock);
+  resample_fwd_kernel<1><<<g_in, 256, 0, st>>>(in, tmp, r->ax_w.xmin, r->ax_w.xsize, r->ax_w.w, r->ax_w.kmax, r->in_w, r->out_w,
+                                               r->in_h, rows_in);
   RGIE_LAUNCH_OK();
-  resample_fwd_kernel<0><<<planes * r->out_h, 256, 0, st>>>(tmp, out, r->ax_h.xmin, r->ax_h.xsize, r->ax_h.w, r->ax_h.kmax,
-                                                            r->in_h, r->out_h, r->out_w);
+  resample_fwd_kernel<0><<<g_out, 256, 0, st>>>(tmp, out, r->ax_h.xmin, r->ax_h.xsize, r->ax_h.w, r->ax_h.kmax, r->in_h, r->out_h,
+                                                r->out_w, rows_out);
   RGIE_LAUNCH_OK();
   return 0;
 }
@@ -194,11 +199,13 @@ int rgie_resize_bwd(const RgieResize* r, const float* gout, float* gin, int plan
   cudaStream_t st = (cudaStream_t)stream;
   RGIE_CHECK(r && gout && gin && tmp && planes > 0, "rgie_resize_bwd: bad arguments");
   // transpose of (vertical o horizontal) = horizontal^T o vertical^T ; tmp: [planes, in_h, out_w]
-  resample_bwd_kernel<0><<<planes * r->in_h, 256, 0, st>>>(gout, tmp, r->ax_h.t_start, r->ax_h.t_out, r->ax_h.t_w, r->in_h,
-                                                           r->out_h, r->out_w);
+  const long rows_in = (long)planes * r->in_h;
+  const int g_in = (int)((rows_in + kRowsPerBlock - 1) / kRowsPerBlock);
+  resample_bwd_kernel<0><<<g_in, 256, 0, st>>>(gout, tmp, r->ax_h.t_start, r->ax_h.t_out, r->ax_h.t_w, r->in_h, r->out_h, r->out_w,
+                                               rows_in);
   RGIE_LAUNCH_OK();
-  resample_bwd_kernel<1><<<planes * r->in_h, 256, 0, st>>>(tmp, gin, r->ax_w.t_start, r->ax_w.t_out, r->ax_w.t_w, r->in_w,
-                                                           r->out_w, r->in_h);
+  resample_bwd_kernel<1><<<g_in, 256, 0, st>>>(tmp, gin, r->ax_w.t_start, r->ax_w.t_out, r->ax_w.t_w, r->in_w, r->out_w, r->in_h,
+                                               rows_in);
   RGIE_LAUNCH_OK();
   return 0;
 }
