@@ -110,6 +110,13 @@ int rgie_regressor_forward_ex(RgieRegressor* r, const float* img, int B, int Hr,
                               void* stream);
 /* dlogits: [B*reps, num_classes]; dimg: [B,3,Hr,Wr] gradient w.r.t. `img` of the preceding forward (overwritten) */
 int rgie_regressor_backward(RgieRegressor* r, const float* dlogits, float* dimg, void* stream);
+/* `normalize` of the forward calls: 0 = crops as they are, 1 = (v - 0.5) / 0.5 (ReplicateAndCrop.py:26-28), 2 = the
+ * handle's input transform: t = clamp(v * pre_scale + pre_shift, 0, 1); (t - mean_c) / std_c  -- the EmoNet ten-crop
+ * pipeline (src/baselines/models/EmoNet.py:63-88: denorm, /255, ImageNet normalisation).  In mode 2 the backward pass
+ * re-reads `img` of the forward call (clamp mask), which must still be alive.  A crop whose `left` offset has bit 30 set
+ * is mirrored horizontally (EmoNet's flipped crops). */
+int rgie_regressor_set_input_transform(RgieRegressor* r, float pre_scale, float pre_shift, const float* mean3,
+                                       const float* std3);
 /* per-GEMM timing of the last forward/backward (cudaEvent pairs around every row-shifted GEMM launch; used by bench.py
  * for the live roofline figure).  get_profile synchronises on the recorded events.  h_info[4*i..]: {0 fwd | 1 bwd,
  * Cout, K, m_tiles}; h_flops: algorithmic FLOPs (valid pixels only, padding excluded); h_bytes: algorithmic HBM bytes

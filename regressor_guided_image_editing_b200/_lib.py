@@ -48,6 +48,7 @@ SIGNATURES = {
     "rgie_regressor_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "rgie_regressor_forward_ex": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _l, _i, _i, _vp, _vp]),
     "rgie_regressor_backward": (_i, [_vp, _vp, _vp, _vp]),
+    "rgie_regressor_set_input_transform": (_i, [_vp, C.c_float, C.c_float, _vp, _vp]),
     "rgie_regressor_set_profiling": (_i, [_vp, _i]),
     "rgie_regressor_num_ops": (_i, [_vp]),
     "rgie_regressor_get_profile": (_i, [_vp, _vp, _vp, _vp, _vp, _i, C.POINTER(_i)]),

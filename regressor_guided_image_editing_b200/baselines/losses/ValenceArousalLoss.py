@@ -20,20 +20,23 @@ class ValenceArousalLoss(EmotionImageLoss):
                  precision: str = DEFAULT_PRECISION):
         super().__init__(device, weight, is_minimized)
         name = path_to_model if isinstance(path_to_model, str) else ""
-        if "EmoNet" in name:
-            raise _lib.RgieError("the EmoNet regressor is not implemented natively yet (SURVEY.md 8f rank 1)")
-        num_classes = 4
-        activ_func = torch.nn.Sigmoid()
-        if "no_sigmoid" in name:
-            activ_func = None
-        if "mse" in name:
-            num_classes = 2
-            activ_func = None
-        if "arousal_nll" in name:
-            num_classes = 2
-        self.model = load_model_eval(path_to_model, num_classes, normalize=is_input_range_0_1,
-                                     activation_function=activ_func, input_size=input_size, crop_size=crop_size,
-                                     is_ten_crop=True, requires_grad=requires_grad, precision=precision)
+        if "EmoNet" in name:                                                                             # :31-33
+            from ..models.EmoNet import load_model_eval as load_model_eval_emo_net
+            self.model = load_model_eval_emo_net(path_to_model, normalize=is_input_range_0_1,
+                                                 requires_grad=requires_grad, precision=precision)
+        else:
+            num_classes = 4
+            activ_func = torch.nn.Sigmoid()
+            if "no_sigmoid" in name:
+                activ_func = None
+            if "mse" in name:
+                num_classes = 2
+                activ_func = None
+            if "arousal_nll" in name:
+                num_classes = 2
+            self.model = load_model_eval(path_to_model, num_classes, normalize=is_input_range_0_1,
+                                         activation_function=activ_func, input_size=input_size, crop_size=crop_size,
+                                         is_ten_crop=True, requires_grad=requires_grad, precision=precision)
         if loss == "valence":
             self.get_error = self.get_valence_error
             self.output_ixs = [0]

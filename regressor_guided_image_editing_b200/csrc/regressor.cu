@@ -21,17 +21,30 @@ namespace {
 // small kernels around the GEMMs (templated on the activation type T: float = parity mode, bf16 = throughput mode)
 // ---------------------------------------------------------------------------------------------------------------
 
+// Input transform applied while the crops are packed.  mode 0: identity; 1: (v - 0.5) / 0.5 (ReplicateAndCrop's
+// Normalize(.5,.5)); 2: the EmoNet ten-crop pipeline (EmoNet.py:63-88): t = clamp(v * ps + pb, 0, 1) ("denorm"), * 255,
+// / 255, then ImageNet (t - mean_c) / std_c.  A crop whose `left` offset has bit 30 set is mirrored horizontally
+// (EmoNet's flipped crops 5..9).
+struct InXform {
+  int mode;
+  float ps, pb, mean[3], std[3];
+};
+constexpr int kFlipBit = 1 << 30;
+
 // crop + normalise + 2x2 space-to-depth + 4 horizontal taps -> ZZ[n, i, j, bi*16 + (pr*2+pc)*3 + c]
 template <typename T>
 __global__ void __launch_bounds__(256) pack_crops_kernel(const float* __restrict__ img, const int* __restrict__ offsets,
                                                         const int* __restrict__ step_ptr, long off_step_stride,
                                                         T* __restrict__ zz, Geom g, int reps, int Hr, int Wr,
-                                                        int normalize) {
+                                                        InXform xf) {
   // one thread block = one output line (n, i): no per-element division; a thread = one (pixel j, horizontal tap bi)
   const int* offs = offsets + (step_ptr ? (long)(*step_ptr) * off_step_stride : 0);
   const int n = blockIdx.x / g.H, i = blockIdx.x - n * g.H;
   const int b = n / reps;
-  const int top = offs[2 * n], left = offs[2 * n + 1];
+  const int top = offs[2 * n], left_raw = offs[2 * n + 1];
+  const bool flip = (left_raw & kFlipBit) != 0;
+  const int left = left_raw & (kFlipBit - 1);
+  const int cw = 2 * g.W;                          // crop width
   const float* src = img + (long)b * 3 * Hr * Wr + (long)(top + 2 * i) * Wr + left;
   const long plane = (long)Hr * Wr;
   T* dst_row = zz + geom_row(g, 0, n, i, 0) * 64;
@@ -46,9 +59,15 @@ __global__ void __launch_bounds__(256) pack_crops_kernel(const float* __restrict
       for (int c = 0; c < 3; ++c)
 #pragma unroll
         for (int pr = 0; pr < 2; ++pr) {
-          const float* q = src + c * plane + pr * Wr + 2 * jj;     // (crop offsets are arbitrary: no vector alignment)
-          float v0 = q[0], v1 = q[1];
-          if (normalize) { v0 = (v0 - 0.5f) / 0.5f; v1 = (v1 - 0.5f) / 0.5f; }
+          const float* q = src + c * plane + pr * Wr;               // (crop offsets are arbitrary: no vector alignment)
+          float v0 = flip ? q[cw - 1 - 2 * jj] : q[2 * jj], v1 = flip ? q[cw - 2 - 2 * jj] : q[2 * jj + 1];
+          if (xf.mode == 1) { v0 = (v0 - 0.5f) / 0.5f; v1 = (v1 - 0.5f) / 0.5f; }
+          else if (xf.mode == 2) {
+            v0 = fminf(fmaxf(__fadd_rn(__fmul_rn(v0, xf.ps), xf.pb), 0.f), 1.f) * 255.0f / 255.0f;
+            v1 = fminf(fmaxf(__fadd_rn(__fmul_rn(v1, xf.ps), xf.pb), 0.f), 1.f) * 255.0f / 255.0f;
+            v0 = (v0 - xf.mean[c]) / xf.std[c];
+            v1 = (v1 - xf.mean[c]) / xf.std[c];
+          }
           vals[(pr * 2 + 0) * 3 + c] = from_f<T>(v0);
           vals[(pr * 2 + 1) * 3 + c] = from_f<T>(v1);
         }
@@ -282,8 +301,8 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restric
 // dimg[b,c,Y,X] = nscale * sum_r dZ[(b*reps+r), (Y-top)>>1, (X-left)>>1, ((Y-top)&1)*2+((X-left)&1))*3 + c]
 __global__ void __launch_bounds__(256) crop_grad_gather_kernel(const float* __restrict__ dz, const int* __restrict__ offsets,
                                                               const int* __restrict__ step_ptr, long off_step_stride,
-                                                              float* __restrict__ dimg, int B, int reps, int Hr, int Wr,
-                                                              int crop, float nscale) {
+                                                              float* __restrict__ dimg, const float* __restrict__ img, int B,
+                                                              int reps, int Hr, int Wr, int crop, InXform xf) {
   // one thread block = one image line (b, Y); threads along X (no per-element division)
   const int* offs = offsets + (step_ptr ? (long)(*step_ptr) * off_step_stride : 0);
   const int Ho = crop / 2;
@@ -293,13 +312,26 @@ __global__ void __launch_bounds__(256) crop_grad_gather_kernel(const float* __re
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
     for (int r = 0; r < reps; ++r) {
       const int n = b * reps + r;
-      const int y = Y - offs[2 * n], x = X - offs[2 * n + 1];
+      const int left_raw = offs[2 * n + 1];
+      const int y = Y - offs[2 * n];
+      int x = X - (left_raw & (kFlipBit - 1));
       if (y < 0 || y >= crop || x < 0 || x >= crop) continue;
+      if (left_raw & kFlipBit) x = crop - 1 - x;
       const float* p = dz + (((long)n * Ho + (y >> 1)) * Ho + (x >> 1)) * 16 + ((y & 1) * 2 + (x & 1)) * 3;
       s0 += p[0]; s1 += p[1]; s2 += p[2];
     }
     float* o = dimg + (long)b * 3 * plane + (long)Y * Wr + X;
-    o[0] = s0 * nscale; o[plane] = s1 * nscale; o[2 * plane] = s2 * nscale;
+    float k0 = 1.f, k1 = 1.f, k2 = 1.f;
+    if (xf.mode == 1) { k0 = k1 = k2 = 2.0f; }
+    else if (xf.mode == 2) {
+      const float* ip = img + (long)b * 3 * plane + (long)Y * Wr + X;
+      const float t0 = __fadd_rn(__fmul_rn(ip[0], xf.ps), xf.pb), t1 = __fadd_rn(__fmul_rn(ip[plane], xf.ps), xf.pb),
+                  t2 = __fadd_rn(__fmul_rn(ip[2 * plane], xf.ps), xf.pb);
+      k0 = (t0 >= 0.f && t0 <= 1.f) ? xf.ps / xf.std[0] : 0.f;
+      k1 = (t1 >= 0.f && t1 <= 1.f) ? xf.ps / xf.std[1] : 0.f;
+      k2 = (t2 >= 0.f && t2 <= 1.f) ? xf.ps / xf.std[2] : 0.f;
+    }
+    o[0] = s0 * k0; o[plane] = s1 * k1; o[2 * plane] = s2 * k2;
   }
 }
 
@@ -381,6 +413,8 @@ struct RgieRegressor {
   // call state
   const int* offsets = nullptr; const int* step_ptr = nullptr; long off_stride = 0;
   int B = 0, reps = 0, Hr = 0, Wr = 0, normalize = 1;
+  const float* img = nullptr;               // resized input of the last forward (read again by backward in transform mode 2)
+  InXform xf2 = {2, 1.f, 0.f, {0.485f, 0.456f, 0.406f}, {0.229f, 0.224f, 0.225f}};   // mode-2 transform (EmoNet defaults)
   void* final_dout = nullptr;   // where the tail backward writes d(layer4 out)
   // optional per-GEMM timing (cudaEvent pairs), enabled by rgie_regressor_set_profiling
   bool profiling = false;
@@ -868,14 +902,17 @@ int rgie_regressor_forward_ex(RgieRegressor* R, const float* img, int B, int Hr,
   RGIE_CHECK(B * reps == R->N, "rgie_regressor_forward: B*reps must equal the max_crops the handle was created with");
   RGIE_CHECK(Hr >= R->crop && Wr >= R->crop, "rgie_regressor_forward: image smaller than the crop");
   R->offsets = offsets; R->step_ptr = step_ptr; R->off_stride = off_step_stride;
-  R->B = B; R->reps = reps; R->Hr = Hr; R->Wr = Wr; R->normalize = normalize;
+  R->B = B; R->reps = reps; R->Hr = Hr; R->Wr = Wr; R->normalize = normalize; R->img = img;
+  RGIE_CHECK(normalize >= 0 && normalize <= 2, "rgie_regressor_forward: normalize must be 0, 1 or 2");
+  InXform xf = R->xf2;
+  xf.mode = normalize;
   const int N = R->N, H0 = R->H0, H1 = R->Hs[1];
   if (R->dtype == 0) {
     pack_crops_kernel<float><<<N * H0, 256, 0, st>>>(img, offsets, step_ptr, off_step_stride, (float*)R->zz, R->gZZ, reps, Hr,
-                                                     Wr, normalize);
+                                                     Wr, xf);
   } else {
     pack_crops_kernel<__nv_bfloat16><<<N * H0, 256, 0, st>>>(img, offsets, step_ptr, off_step_stride, (__nv_bfloat16*)R->zz,
-                                                             R->gZZ, reps, Hr, Wr, normalize);
+                                                             R->gZZ, reps, Hr, Wr, xf);
   }
   RGIE_LAUNCH_OK();
   if (int rc = run_op(R, R->fwd_ops[0], st, 0)) return rc;
@@ -930,9 +967,19 @@ int rgie_regressor_backward(RgieRegressor* R, const float* dlogits, float* dimg,
     maxpool_bwd_kernel<__nv_bfloat16><<<N * R->Hs[1], 256, 0, st>>>((const __nv_bfloat16*)dP, R->arg, (__nv_bfloat16*)R->dC1, R->gS[1], R->gDY, 64);
   RGIE_LAUNCH_OK();
   if (int rc = run_op(R, R->bwd_ops[nb - 1], st, R->fwd_ops.size() + nb - 1)) return rc;
-  crop_grad_gather_kernel<<<R->B * R->Hr, 256, 0, st>>>(R->dZ, R->offsets, R->step_ptr, R->off_stride, dimg, R->B, R->reps,
-                                                          R->Hr, R->Wr, R->crop, R->normalize ? 2.0f : 1.0f);
+  InXform xf = R->xf2;
+  xf.mode = R->normalize;
+  crop_grad_gather_kernel<<<R->B * R->Hr, 256, 0, st>>>(R->dZ, R->offsets, R->step_ptr, R->off_stride, dimg, R->img, R->B, R->reps,
+                                                        R->Hr, R->Wr, R->crop, xf);
   RGIE_LAUNCH_OK();
+  return 0;
+}
+
+int rgie_regressor_set_input_transform(RgieRegressor* R, float pre_scale, float pre_shift, const float* mean3,
+                                       const float* std3) {
+  RGIE_CHECK(R && mean3 && std3, "rgie_regressor_set_input_transform: null");
+  R->xf2.mode = 2; R->xf2.ps = pre_scale; R->xf2.pb = pre_shift;
+  for (int c = 0; c < 3; ++c) { R->xf2.mean[c] = mean3[c]; R->xf2.std[c] = std3[c]; }
   return 0;
 }
 

@@ -191,6 +191,12 @@ class Regressor:
                                                     stream_ptr(img.device)), "rgie_regressor_forward")
         return logits
 
+    def set_input_transform(self, pre_scale: float, pre_shift: float, mean, std) -> None:
+        """`normalize=2` of forward(): t = clamp(v * pre_scale + pre_shift, 0, 1); (t - mean_c) / std_c (EmoNet pipeline)."""
+        m = (C.c_float * 3)(*[float(v) for v in mean]); s = (C.c_float * 3)(*[float(v) for v in std])
+        check(_lib.load().rgie_regressor_set_input_transform(self._h, float(pre_scale), float(pre_shift), m, s),
+              "rgie_regressor_set_input_transform")
+
     def backward(self, dlogits: torch.Tensor, dimg: torch.Tensor) -> torch.Tensor:
         _require_cuda(dlogits, "dlogits"); _require_cuda(dimg, "dimg")
         check(_lib.load().rgie_regressor_backward(self._h, ptr(dlogits), ptr(dimg), stream_ptr(dimg.device)),
