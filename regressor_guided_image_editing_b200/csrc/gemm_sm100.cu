@@ -13,6 +13,9 @@
 // (tmem_full/tmem_empty) between MMA and epilogue so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <stdlib.h>
 #include "common.cuh"
+#ifndef RGIE_WAIT_HINT_NS
+#define RGIE_WAIT_HINT_NS 100000
+#endif
 #include "gemm_sm100.cuh"
 
 namespace rgie {
@@ -25,6 +28,8 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;
 __host__ __device__ constexpr int num_threads(int new_warps) { return 64 + 32 * new_warps; }   // TMA warp + MMA warp + NEW epilogue warps
 constexpr int MAX_BIAS = 2048;
 
+constexpr uint32_t kWaitHintNs = RGIE_WAIT_HINT_NS;
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -36,16 +41,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Wait for a barrier phase.  try_wait suspends the thread in hardware until the phase completes or the time hint expires.
+// (Measured: a 100 us hint vs none makes no difference to step time or clocks on the power-capped B200 -- 79.6 vs 79.6 ms.)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
       "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
       "@P1 bra DONE;\n"
       "bra LAB_WAIT;\n"
       "DONE:\n"
-      "}" ::"r"(bar), "r"(parity) : "memory");
+      "}" ::"r"(bar), "r"(parity), "r"(kWaitHintNs) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile(
