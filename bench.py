@@ -274,6 +274,17 @@ def main():
                 "hbm": {"achieved_GBs": tot_by / (gemm_ms_per_step / 1e3) / 1e9, "peak_GBs": hbm_peak,
                         "frac": tot_by / (gemm_ms_per_step / 1e3) / 1e9 / hbm_peak,
                         "note": "the family mixes tensor-bound (K >= 1024) and HBM-bound (1x1 expansions) launches"}}
+        # per-class reading: the family mixes tensor-bound launches (K >= 1024: the 3x3 convs of layer2-4 and the deep 1x1s)
+        # and HBM-bound ones (everything else); each class against its own measured peak
+        cls = {"tensor_bound": [0, 0.0, 0.0, 0.0], "hbm_bound": [0, 0.0, 0.0, 0.0]}
+        for i in range(n.value):
+            c = cls["tensor_bound" if info[4 * i + 2] >= 1024 and info[4 * i + 1] >= 128 else "hbm_bound"]
+            c[0] += 1; c[1] += med[i]; c[2] += fl_a[i]; c[3] += by_a[i]
+        prof["classes"] = {
+            k: {"launches_per_micro_batch": v[0], "ms_per_micro_batch": v[1],
+                "TFLOPs": v[2] / max(v[1], 1e-9) / 1e9, "tensor_frac": v[2] / max(v[1], 1e-9) / 1e9 / peak,
+                "GBs": v[3] / max(v[1], 1e-9) / 1e6, "hbm_frac": v[3] / max(v[1], 1e-9) / 1e6 / hbm_peak}
+            for k, v in cls.items()}
         if args.profile_out:
             os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)
             json.dump({"per_gemm": table, "summary": prof, "ms_per_step": ms_max / Kt}, open(args.profile_out, "w"), indent=1)

@@ -746,7 +746,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // ===============================================================================================================
 constexpr int PATCH_SLAB_H = 19;                               // 16 + up to 3 halo lines
 constexpr int PATCH_SLAB_BYTES = PATCH_SLAB_H * 8 * 128;       // 19456 (a multiple of 1024)
-constexpr int PATCH_SLABS = 6;
+#ifndef RGIE_PATCH_SLABS
+#define RGIE_PATCH_SLABS 6
+#endif
+constexpr int PATCH_SLABS = RGIE_PATCH_SLABS;
 constexpr int PATCH_W_BYTES = 72 * 1024;                       // resident weights: ntaps * BN * 128 B <= 72 KB
 struct PatchSmem {
   static constexpr int A_OFF = 0;
@@ -904,7 +907,10 @@ gemm_patch_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
 // ===============================================================================================================
 constexpr int HS_NJ = 4, HS_NQ = 12, HS_N = HS_NJ * HS_NQ, HS_NY = 4, HS_OUTW = 16 - (HS_NJ - 1);
 constexpr int HS_SLAB_BYTES = (8 + HS_NY - 1) * 16 * 128;      // 22528
-constexpr int HS_SLABS = 6;
+#ifndef RGIE_HS_SLABS
+#define RGIE_HS_SLABS 6
+#endif
+constexpr int HS_SLABS = RGIE_HS_SLABS;
 constexpr int HS_W_TAP_BYTES = HS_N * BK * 2;                   // 6144
 struct HsSmem {
   static constexpr int A_OFF = 0;
