@@ -1,5 +1,10 @@
-// MiDU guidance head (Stable-Diffusion variant): src/guidance_classifier/MiduClassifier.py:145-160
-//   Conv(1280->256,3,p1) ReLU MaxPool2 Conv(256->128,3,p1) ReLU AdaptiveAvgPool(2,2) Flatten Linear(512,64) ReLU Linear(64,n)
+// MiDU guidance head: src/guidance_classifier/MiduClassifier.py:121-161
+//   SD   (:145-160): Conv(1280->256,3,p1) ReLU MaxPool2 Conv(256->128,3,p1) ReLU AdaptiveAvgPool(2,2) Flatten
+//                    Linear(512,64) ReLU Linear(64,n)                                  on 8x8 mid-block features
+//   SDXL (:125-143): [Conv(3,p1) ReLU MaxPool2] x4 with 1280->512->256->128->64, Flatten, Linear(256,128) ReLU
+//                    Linear(128,n)                                                     on 32x32 mid-block features
+// Both are a list of conv stages (3x3 conv + ReLU, optional 2x2 max pool) followed by one tail kernel
+// (2x2 adaptive average + flatten + two linears).
 // forward + input-gradient backward (d score / d feature), so the caller's autograd continues into its UNet
 // (pipelines/InversionResamplingStableDiffusionPipeline.py:132-134).  The two convolutions run on the row-shifted GEMM
 // (tcgen05 in bf16 mode, CUDA cores in fp32 parity mode); the tail is one small kernel per direction.
@@ -74,14 +79,16 @@ __global__ void __launch_bounds__(256) pool2_bwd_kernel(const T* __restrict__ do
     din[r] = from_f<T>(g);
   }
 }
-// AdaptiveAvgPool(2,2) over the HxH map (H even) + Flatten (c*4 + i*2 + j) + Linear(512,64) + ReLU + Linear(64,n_out)
+// AdaptiveAvgPool(2,2) over the HxH map (H even; H == 2: identity) + Flatten (c*4 + i*2 + j) + Linear(4C, NH) + ReLU +
+// Linear(NH, n_out)                                                           (SD: C = 128, NH = 64; SDXL: C = 64, NH = 128)
 template <typename T>
-__global__ void __launch_bounds__(256) midu_tail_fwd_kernel(const T* __restrict__ h, Geom g, int C, const float* __restrict__ w7,
+__global__ void __launch_bounds__(256) midu_tail_fwd_kernel(const T* __restrict__ h, Geom g, int C, int NH,
+                                                           const float* __restrict__ w7,
                                                            const float* __restrict__ b7, const float* __restrict__ w9,
                                                            const float* __restrict__ b9, int n_out, float* __restrict__ v_out,
                                                            float* __restrict__ u_out, float* __restrict__ pred) {
   __shared__ float v[512];
-  __shared__ float u[64];
+  __shared__ float u[128];
   const int n = blockIdx.x;
   const int hb = g.H / 2;
   for (int e = threadIdx.x; e < C * 4; e += blockDim.x) {
@@ -93,36 +100,36 @@ __global__ void __launch_bounds__(256) midu_tail_fwd_kernel(const T* __restrict_
     v_out[(long)n * C * 4 + e] = v[e];
   }
   __syncthreads();
-  if (threadIdx.x < 64) {
+  if (threadIdx.x < NH) {
     float s = b7[threadIdx.x];
     for (int e = 0; e < C * 4; ++e) s = fmaf(w7[(long)threadIdx.x * C * 4 + e], v[e], s);
     u[threadIdx.x] = fmaxf(s, 0.f);
-    u_out[(long)n * 64 + threadIdx.x] = u[threadIdx.x];
+    u_out[(long)n * NH + threadIdx.x] = u[threadIdx.x];
   }
   __syncthreads();
   if (threadIdx.x < n_out) {
     float s = b9[threadIdx.x];
-    for (int e = 0; e < 64; ++e) s = fmaf(w9[threadIdx.x * 64 + e], u[e], s);
+    for (int e = 0; e < NH; ++e) s = fmaf(w9[threadIdx.x * NH + e], u[e], s);
     pred[(long)n * n_out + threadIdx.x] = s;
   }
 }
 template <typename T>
 __global__ void __launch_bounds__(256) midu_tail_bwd_kernel(const float* __restrict__ dpred, int n_out, const float* __restrict__ w9,
                                                            const float* __restrict__ w7, const float* __restrict__ u,
-                                                           const T* __restrict__ h, T* __restrict__ dh, Geom g, int C) {
-  __shared__ float du[64];
+                                                           const T* __restrict__ h, T* __restrict__ dh, Geom g, int C, int NH) {
+  __shared__ float du[128];
   __shared__ float dv[512];
   const int n = blockIdx.x;
   const int hb = g.H / 2;
-  if (threadIdx.x < 64) {
+  if (threadIdx.x < NH) {
     float s = 0.f;
-    for (int k = 0; k < n_out; ++k) s = fmaf(w9[k * 64 + threadIdx.x], dpred[(long)n * n_out + k], s);
-    du[threadIdx.x] = u[(long)n * 64 + threadIdx.x] > 0.f ? s : 0.f;
+    for (int k = 0; k < n_out; ++k) s = fmaf(w9[k * NH + threadIdx.x], dpred[(long)n * n_out + k], s);
+    du[threadIdx.x] = u[(long)n * NH + threadIdx.x] > 0.f ? s : 0.f;
   }
   __syncthreads();
   for (int e = threadIdx.x; e < C * 4; e += blockDim.x) {
     float s = 0.f;
-    for (int k = 0; k < 64; ++k) s = fmaf(w7[(long)k * C * 4 + e], du[k], s);
+    for (int k = 0; k < NH; ++k) s = fmaf(w7[(long)k * C * 4 + e], du[k], s);
     dv[e] = s / (float)(hb * hb);
   }
   __syncthreads();
@@ -147,19 +154,30 @@ int grid_for(long total) {
 
 using namespace rgie;
 
+constexpr int kMaxStages = 4;
+struct MiduStage {
+  int ci = 0, co = 0, hw = 0;
+  bool pool = false;
+  Geom g, gp;                      // conv geometry / pooled geometry
+  void *w = nullptr, *wt = nullptr;
+  float* b = nullptr;
+  void *in = nullptr, *h = nullptr, *p = nullptr;      // padded NHWC: conv input, conv output (post ReLU), pooled output
+  void *dh = nullptr, *dp = nullptr;                   // gradients w.r.t. h / p
+  uint8_t* arg = nullptr;
+  GemmDesc d_fwd, d_bwd;
+  GemmPlanSm100 p_fwd, p_bwd;
+};
+
 struct RgieMiduHead {
   int precision = 0, dtype = 0, esz = 4;
-  int B = 0, hw = 0, n_out = 2;
-  Geom gA, gB;
+  int B = 0, hw = 0, n_out = 2, n_stages = 0, C_tail = 0, NH = 0;
+  MiduStage st[kMaxStages];
+  Geom g_tail;
+  void* tail_in = nullptr;         // last stage's p (pooled) or h
+  void* d_tail_in = nullptr;
   std::vector<void*> allocs;
-  void *w0 = nullptr, *w0t = nullptr, *w3 = nullptr, *w3t = nullptr;
-  float *b0 = nullptr, *b3 = nullptr, *w7 = nullptr, *b7 = nullptr, *w9 = nullptr, *b9 = nullptr;
-  void *x = nullptr, *h0 = nullptr, *p0 = nullptr, *h1 = nullptr;
-  void *dh1 = nullptr, *dp0 = nullptr, *dh0 = nullptr;
+  float *w7 = nullptr, *b7 = nullptr, *w9 = nullptr, *b9 = nullptr;
   float *dx = nullptr, *v = nullptr, *u = nullptr;
-  uint8_t* arg = nullptr;
-  GemmDesc d[4];
-  GemmPlanSm100 plan[4];
 };
 
 namespace {
@@ -198,9 +216,24 @@ void pack3x3(const float* w, int co, int ci, std::vector<float>& f, std::vector<
         t[(size_t)c * 9 * co + (size_t)kk * co + n] = v;
       }
 }
-int midu_run(RgieMiduHead* M, int i, cudaStream_t st) {
-  if (M->precision == RGIE_PREC_BF16) return run_gemm_sm100(M->plan[i], st);
-  return launch_gemm_simt(M->d[i], M->dtype, st);
+void conv_desc(GemmDesc& d, const void* A, const Geom& g, int ci, const void* W, int co, float* bias, int relu, void* D,
+               int d_fp32, bool transpose) {
+  memset(&d, 0, sizeof(d));
+  d.A = A; d.a_rows = g.rows(); d.Cin = ci; d.Wt = W; d.n_pad = co; d.ntaps = 9;
+  for (int k = 0; k < 9; ++k) {
+    if (!transpose) d.row_off[k] = (long)(k / 3 - 1) * g.P + (k % 3 - 1);
+    else {
+      const int t = (k / 3) * 3 + (2 - k % 3);             // slot k holds kernel tap t (see pack3x3)
+      d.row_off[k] = -((long)(t / 3 - 1) * g.P + (t % 3 - 1));
+    }
+  }
+  d.m_begin = 0; d.m_end = g.rows(); d.Cout = co;
+  d.src = g; d.dst_kind = DST_SAME; d.dst = g; d.D = D; d.ldd = co; d.d_fp32 = d_fp32;
+  d.bias = bias; d.relu = relu;
+}
+int midu_run(RgieMiduHead* M, const GemmDesc& d, const GemmPlanSm100& plan, cudaStream_t st) {
+  if (M->precision == RGIE_PREC_BF16) return run_gemm_sm100(plan, st);
+  return launch_gemm_simt(d, M->dtype, st);
 }
 }  // namespace
 
@@ -215,8 +248,8 @@ void rgie_midu_destroy(RgieMiduHead* M) {
 int rgie_midu_create(const float* const* h_tensors, int n_tensors, int n_out, int max_batch, int hw, int precision,
                      RgieMiduHead** out) {
   RGIE_CHECK(h_tensors && out, "rgie_midu_create: null argument");
-  RGIE_CHECK(n_tensors == 8, "rgie_midu_create: expected 8 tensors (0.w,0.b,3.w,3.b,7.w,7.b,9.w,9.b)");
-  RGIE_CHECK(hw == 8, "rgie_midu_create: the SD head takes 8x8 mid-block features (SDXL variant: SURVEY.md 8f rank 4)");
+  RGIE_CHECK((n_tensors == 8 && hw == 8) || (n_tensors == 12 && hw == 32),
+             "rgie_midu_create: expected 8 tensors on 8x8 features (SD head) or 12 tensors on 32x32 features (SDXL head)");
   RGIE_CHECK(n_out >= 1 && n_out <= 64 && max_batch >= 1 && precision >= 0 && precision <= 2, "rgie_midu_create: bad argument");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("rgie_midu_create: no CUDA device (there is no CPU fallback)");
@@ -225,56 +258,69 @@ int rgie_midu_create(const float* const* h_tensors, int n_tensors, int n_out, in
   M->precision = precision; M->dtype = precision == RGIE_PREC_FP32 ? 0 : 1; M->esz = M->dtype == 0 ? 4 : 2;
   M->B = max_batch; M->hw = hw; M->n_out = n_out;
   const int B = max_batch, esz = M->esz;
-  M->gA = make_geom(1, B, hw, hw, 1, 1, 1, 1);
-  M->gB = make_geom(1, B, hw / 2, hw / 2, 1, 1, 1, 1);
-  std::vector<float> f, t;
-  pack3x3(h_tensors[0], 256, 1280, f, t);
-  if (int rc = midu_upload(M, f, &M->w0)) return rc;
-  if (int rc = midu_upload(M, t, &M->w0t)) return rc;
-  pack3x3(h_tensors[2], 128, 256, f, t);
-  if (int rc = midu_upload(M, f, &M->w3)) return rc;
-  if (int rc = midu_upload(M, t, &M->w3t)) return rc;
-  if (int rc = midu_upload_f32(M, h_tensors[1], 256, &M->b0)) return rc;
-  if (int rc = midu_upload_f32(M, h_tensors[3], 128, &M->b3)) return rc;
-  if (int rc = midu_upload_f32(M, h_tensors[4], 64 * 512, &M->w7)) return rc;
-  if (int rc = midu_upload_f32(M, h_tensors[5], 64, &M->b7)) return rc;
-  if (int rc = midu_upload_f32(M, h_tensors[6], (size_t)n_out * 64, &M->w9)) return rc;
-  if (int rc = midu_upload_f32(M, h_tensors[7], n_out, &M->b9)) return rc;
-  const long rA = M->gA.rows(), rB = M->gB.rows();
-  if (int rc = midu_alloc(M, &M->x, (size_t)rA * 1280 * esz)) return rc;
-  if (int rc = midu_alloc(M, &M->h0, (size_t)rA * 256 * esz)) return rc;
-  if (int rc = midu_alloc(M, &M->p0, (size_t)rB * 256 * esz)) return rc;
-  if (int rc = midu_alloc(M, &M->h1, (size_t)rB * 128 * esz)) return rc;
-  if (int rc = midu_alloc(M, &M->dh1, (size_t)rB * 128 * esz)) return rc;
-  if (int rc = midu_alloc(M, &M->dp0, (size_t)rB * 256 * esz)) return rc;
-  if (int rc = midu_alloc(M, &M->dh0, (size_t)rA * 256 * esz)) return rc;
-  if (int rc = midu_alloc(M, (void**)&M->dx, (size_t)rA * 1280 * 4)) return rc;
-  if (int rc = midu_alloc(M, (void**)&M->v, (size_t)B * 512 * 4)) return rc;
-  if (int rc = midu_alloc(M, (void**)&M->u, (size_t)B * 64 * 4)) return rc;
-  if (int rc = midu_alloc(M, (void**)&M->arg, (size_t)B * (hw / 2) * (hw / 2) * 256)) return rc;
-
-  auto conv = [&](GemmDesc& d, const void* A, const Geom& g, int ci, const void* W, int co, float* bias, int relu,
-                  const void* mask, int ld_mask, void* D, int d_fp32, bool transpose) {
-    memset(&d, 0, sizeof(d));
-    d.A = A; d.a_rows = g.rows(); d.Cin = ci; d.Wt = W; d.n_pad = co; d.ntaps = 9;
-    for (int k = 0; k < 9; ++k) {
-      if (!transpose) d.row_off[k] = (long)(k / 3 - 1) * g.P + (k % 3 - 1);
-      else {
-        const int t = (k / 3) * 3 + (2 - k % 3);             // slot k holds kernel tap t (see pack3x3)
-        d.row_off[k] = -((long)(t / 3 - 1) * g.P + (t % 3 - 1));
-      }
+  const bool sdxl = n_tensors == 12;
+  // stage list
+  const int chans_sd[3] = {1280, 256, 128}, chans_xl[5] = {1280, 512, 256, 128, 64};
+  const int* ch = sdxl ? chans_xl : chans_sd;
+  M->n_stages = sdxl ? 4 : 2;
+  int cur = hw;
+  for (int s = 0; s < M->n_stages; ++s) {
+    MiduStage& S = M->st[s];
+    S.ci = ch[s]; S.co = ch[s + 1]; S.hw = cur;
+    S.pool = sdxl || s == 0;                         // SD: only the first conv is followed by a max pool
+    S.g = make_geom(1, B, cur, cur, 1, 1, 1, 1);
+    if (S.pool) { cur /= 2; S.gp = make_geom(1, B, cur, cur, 1, 1, 1, 1); }
+    std::vector<float> f, t;
+    pack3x3(h_tensors[2 * s], S.co, S.ci, f, t);
+    if (int rc = midu_upload(M, f, &S.w)) return rc;
+    if (int rc = midu_upload(M, t, &S.wt)) return rc;
+    if (int rc = midu_upload_f32(M, h_tensors[2 * s + 1], S.co, &S.b)) return rc;
+  }
+  M->C_tail = ch[M->n_stages];
+  M->NH = sdxl ? 128 : 64;
+  const int t0 = 2 * M->n_stages;
+  if (int rc = midu_upload_f32(M, h_tensors[t0], (size_t)M->NH * M->C_tail * 4, &M->w7)) return rc;
+  if (int rc = midu_upload_f32(M, h_tensors[t0 + 1], M->NH, &M->b7)) return rc;
+  if (int rc = midu_upload_f32(M, h_tensors[t0 + 2], (size_t)n_out * M->NH, &M->w9)) return rc;
+  if (int rc = midu_upload_f32(M, h_tensors[t0 + 3], n_out, &M->b9)) return rc;
+  // buffers
+  for (int s = 0; s < M->n_stages; ++s) {
+    MiduStage& S = M->st[s];
+    const long r = S.g.rows();
+    if (s == 0) { if (int rc = midu_alloc(M, &S.in, (size_t)r * S.ci * esz)) return rc; }
+    else S.in = M->st[s - 1].pool ? M->st[s - 1].p : M->st[s - 1].h;
+    if (int rc = midu_alloc(M, &S.h, (size_t)r * S.co * esz)) return rc;
+    if (int rc = midu_alloc(M, &S.dh, (size_t)r * S.co * esz)) return rc;
+    if (S.pool) {
+      const long rp = S.gp.rows();
+      if (int rc = midu_alloc(M, &S.p, (size_t)rp * S.co * esz)) return rc;
+      if (int rc = midu_alloc(M, &S.dp, (size_t)rp * S.co * esz)) return rc;
+      if (int rc = midu_alloc(M, (void**)&S.arg, (size_t)B * S.gp.H * S.gp.W * S.co)) return rc;
     }
-    d.m_begin = 0; d.m_end = g.rows(); d.Cout = co;
-    d.src = g; d.dst_kind = DST_SAME; d.dst = g; d.D = D; d.ldd = co; d.d_fp32 = d_fp32;
-    d.bias = bias; d.relu = relu; d.mask = mask; d.ld_mask = ld_mask;
-  };
-  conv(M->d[0], M->x, M->gA, 1280, M->w0, 256, M->b0, 1, nullptr, 0, M->h0, 0, false);
-  conv(M->d[1], M->p0, M->gB, 256, M->w3, 128, M->b3, 1, nullptr, 0, M->h1, 0, false);
-  conv(M->d[2], M->dh1, M->gB, 128, M->w3t, 256, nullptr, 0, nullptr, 0, M->dp0, 0, true);
-  conv(M->d[3], M->dh0, M->gA, 256, M->w0t, 1280, nullptr, 0, nullptr, 0, M->dx, 1, true);
-  if (precision == RGIE_PREC_BF16)
-    for (int i = 0; i < 4; ++i)
-      if (int rc = build_gemm_sm100(M->d[i], &M->plan[i])) return rc;
+  }
+  const MiduStage& L = M->st[M->n_stages - 1];
+  M->g_tail = L.pool ? L.gp : L.g;
+  M->tail_in = L.pool ? L.p : L.h;
+  M->d_tail_in = L.pool ? L.dp : L.dh;
+  if (int rc = midu_alloc(M, (void**)&M->dx, (size_t)M->st[0].g.rows() * 1280 * 4)) return rc;
+  if (int rc = midu_alloc(M, (void**)&M->v, (size_t)B * 512 * 4)) return rc;
+  if (int rc = midu_alloc(M, (void**)&M->u, (size_t)B * 128 * 4)) return rc;
+  // GEMM descriptors: forward conv + ReLU; backward: d(conv input) = conv^T(d h); its destination is the previous stage's
+  // dp (pooled gradient) / dh, or the fp32 d(feature) buffer for the first stage
+  for (int s = 0; s < M->n_stages; ++s) {
+    MiduStage& S = M->st[s];
+    conv_desc(S.d_fwd, S.in, S.g, S.ci, S.w, S.co, S.b, 1, S.h, 0, false);
+    void* dst = s == 0 ? (void*)M->dx : (M->st[s - 1].pool ? M->st[s - 1].dp : M->st[s - 1].dh);
+    conv_desc(S.d_bwd, S.dh, S.g, S.co, S.wt, S.ci, nullptr, 0, dst, s == 0 ? 1 : 0, true);
+    if (s > 0 && !M->st[s - 1].pool) {
+      // no pool in between: the previous ReLU's mask is applied by this GEMM's epilogue
+      S.d_bwd.mask = M->st[s - 1].h; S.d_bwd.ld_mask = M->st[s - 1].co;
+    }
+    if (precision == RGIE_PREC_BF16) {
+      if (int rc = build_gemm_sm100(S.d_fwd, &S.p_fwd)) return rc;
+      if (int rc = build_gemm_sm100(S.d_bwd, &S.p_bwd)) return rc;
+    }
+  }
   RGIE_CUDA_OK(cudaDeviceSynchronize());
   guard.ok = true;
   *out = M;
@@ -286,17 +332,21 @@ int rgie_midu_forward(RgieMiduHead* M, const float* feat, int B, float* pred, vo
   RGIE_CHECK(M && feat && pred, "rgie_midu_forward: null argument");
   RGIE_CHECK(B == M->B, "rgie_midu_forward: batch must equal the max_batch the handle was created with");
   const long t_pack = (long)B * M->hw * M->hw * 1280;
-  const long t_pool = (long)B * (M->hw / 2) * (M->hw / 2) * 256;
-  if (M->dtype == 0) midu_pack_kernel<float><<<grid_for(t_pack), 256, 0, st>>>(feat, (float*)M->x, M->gA, 1280, t_pack);
-  else midu_pack_kernel<__nv_bfloat16><<<grid_for(t_pack), 256, 0, st>>>(feat, (__nv_bfloat16*)M->x, M->gA, 1280, t_pack);
+  if (M->dtype == 0) midu_pack_kernel<float><<<grid_for(t_pack), 256, 0, st>>>(feat, (float*)M->st[0].in, M->st[0].g, 1280, t_pack);
+  else midu_pack_kernel<__nv_bfloat16><<<grid_for(t_pack), 256, 0, st>>>(feat, (__nv_bfloat16*)M->st[0].in, M->st[0].g, 1280, t_pack);
   RGIE_LAUNCH_OK();
-  if (int rc = midu_run(M, 0, st)) return rc;
-  if (M->dtype == 0) pool2_fwd_kernel<float><<<grid_for(t_pool), 256, 0, st>>>((const float*)M->h0, (float*)M->p0, M->arg, M->gA, M->gB, 256, t_pool);
-  else pool2_fwd_kernel<__nv_bfloat16><<<grid_for(t_pool), 256, 0, st>>>((const __nv_bfloat16*)M->h0, (__nv_bfloat16*)M->p0, M->arg, M->gA, M->gB, 256, t_pool);
-  RGIE_LAUNCH_OK();
-  if (int rc = midu_run(M, 1, st)) return rc;
-  if (M->dtype == 0) midu_tail_fwd_kernel<float><<<B, 256, 0, st>>>((const float*)M->h1, M->gB, 128, M->w7, M->b7, M->w9, M->b9, M->n_out, M->v, M->u, pred);
-  else midu_tail_fwd_kernel<__nv_bfloat16><<<B, 256, 0, st>>>((const __nv_bfloat16*)M->h1, M->gB, 128, M->w7, M->b7, M->w9, M->b9, M->n_out, M->v, M->u, pred);
+  for (int s = 0; s < M->n_stages; ++s) {
+    MiduStage& S = M->st[s];
+    if (int rc = midu_run(M, S.d_fwd, S.p_fwd, st)) return rc;
+    if (S.pool) {
+      const long t_pool = (long)B * S.gp.H * S.gp.W * S.co;
+      if (M->dtype == 0) pool2_fwd_kernel<float><<<grid_for(t_pool), 256, 0, st>>>((const float*)S.h, (float*)S.p, S.arg, S.g, S.gp, S.co, t_pool);
+      else pool2_fwd_kernel<__nv_bfloat16><<<grid_for(t_pool), 256, 0, st>>>((const __nv_bfloat16*)S.h, (__nv_bfloat16*)S.p, S.arg, S.g, S.gp, S.co, t_pool);
+      RGIE_LAUNCH_OK();
+    }
+  }
+  if (M->dtype == 0) midu_tail_fwd_kernel<float><<<B, 256, 0, st>>>((const float*)M->tail_in, M->g_tail, M->C_tail, M->NH, M->w7, M->b7, M->w9, M->b9, M->n_out, M->v, M->u, pred);
+  else midu_tail_fwd_kernel<__nv_bfloat16><<<B, 256, 0, st>>>((const __nv_bfloat16*)M->tail_in, M->g_tail, M->C_tail, M->NH, M->w7, M->b7, M->w9, M->b9, M->n_out, M->v, M->u, pred);
   RGIE_LAUNCH_OK();
   return 0;
 }
@@ -305,17 +355,23 @@ int rgie_midu_backward(RgieMiduHead* M, const float* dpred, float* dfeat, void* 
   cudaStream_t st = (cudaStream_t)stream;
   RGIE_CHECK(M && dpred && dfeat, "rgie_midu_backward: null argument");
   const int B = M->B;
-  const long t_in = (long)B * M->hw * M->hw * 256;
+  // tail: d(tail input), masked by (tail input > 0) -- the ReLU of the last conv (a max pool of post-ReLU values is
+  // positive exactly where its arg-max is)
+  if (M->dtype == 0) midu_tail_bwd_kernel<float><<<B, 256, 0, st>>>(dpred, M->n_out, M->w9, M->w7, M->u, (const float*)M->tail_in, (float*)M->d_tail_in, M->g_tail, M->C_tail, M->NH);
+  else midu_tail_bwd_kernel<__nv_bfloat16><<<B, 256, 0, st>>>(dpred, M->n_out, M->w9, M->w7, M->u, (const __nv_bfloat16*)M->tail_in, (__nv_bfloat16*)M->d_tail_in, M->g_tail, M->C_tail, M->NH);
+  RGIE_LAUNCH_OK();
+  for (int s = M->n_stages - 1; s >= 0; --s) {
+    MiduStage& S = M->st[s];
+    if (S.pool) {
+      const long t_in = (long)B * S.hw * S.hw * S.co;
+      if (M->dtype == 0) pool2_bwd_kernel<float><<<grid_for(t_in), 256, 0, st>>>((const float*)S.dp, S.arg, (const float*)S.h, (float*)S.dh, S.g, S.gp, S.co, t_in);
+      else pool2_bwd_kernel<__nv_bfloat16><<<grid_for(t_in), 256, 0, st>>>((const __nv_bfloat16*)S.dp, S.arg, (const __nv_bfloat16*)S.h, (__nv_bfloat16*)S.dh, S.g, S.gp, S.co, t_in);
+      RGIE_LAUNCH_OK();
+    }
+    if (int rc = midu_run(M, S.d_bwd, S.p_bwd, st)) return rc;
+  }
   const long t_un = (long)B * 1280 * M->hw * M->hw;
-  if (M->dtype == 0) midu_tail_bwd_kernel<float><<<B, 256, 0, st>>>(dpred, M->n_out, M->w9, M->w7, M->u, (const float*)M->h1, (float*)M->dh1, M->gB, 128);
-  else midu_tail_bwd_kernel<__nv_bfloat16><<<B, 256, 0, st>>>(dpred, M->n_out, M->w9, M->w7, M->u, (const __nv_bfloat16*)M->h1, (__nv_bfloat16*)M->dh1, M->gB, 128);
-  RGIE_LAUNCH_OK();
-  if (int rc = midu_run(M, 2, st)) return rc;
-  if (M->dtype == 0) pool2_bwd_kernel<float><<<grid_for(t_in), 256, 0, st>>>((const float*)M->dp0, M->arg, (const float*)M->h0, (float*)M->dh0, M->gA, M->gB, 256, t_in);
-  else pool2_bwd_kernel<__nv_bfloat16><<<grid_for(t_in), 256, 0, st>>>((const __nv_bfloat16*)M->dp0, M->arg, (const __nv_bfloat16*)M->h0, (__nv_bfloat16*)M->dh0, M->gA, M->gB, 256, t_in);
-  RGIE_LAUNCH_OK();
-  if (int rc = midu_run(M, 3, st)) return rc;
-  midu_unpack_kernel<<<grid_for(t_un), 256, 0, st>>>(M->dx, dfeat, M->gA, 1280, t_un);
+  midu_unpack_kernel<<<grid_for(t_un), 256, 0, st>>>(M->dx, dfeat, M->st[0].g, 1280, t_un);
   RGIE_LAUNCH_OK();
   return 0;
 }

@@ -1,7 +1,8 @@
 """Drop-in for src/guidance_classifier/MiduClassifier.py: same constructor, hook and `forward(latents, t, prompt_embeds)`.
 
-`self.model` stays the reference's nn.Sequential (state_dict compatible, :121-161) but its arithmetic runs in the native
-head (csrc/midu.cu): a torch.autograd.Function maps the hooked mid-block feature [B,1280,8,8] to [B,n_out] and returns
+`self.model` stays the reference's nn.Sequential (state_dict compatible, :121-161; SD and SDXL variants) but its
+arithmetic runs in the native head (csrc/midu.cu): a torch.autograd.Function maps the hooked mid-block feature
+[B,1280,8,8] (SD) / [B,1280,32,32] (SDXL) to [B,n_out] and returns
 d/d(feature) on backward, so `torch.autograd.grad(loss, latents)` in the caller's sampling loop
 (pipelines/InversionResamplingStableDiffusionPipeline.py:132-134) continues into the caller's own UNet.
 The UNet itself is third-party (diffusers) and out of scope here.
@@ -24,10 +25,10 @@ DEFAULT_PRECISION = os.environ.get("RGIE_PRECISION", "bf16")
 
 
 class NativeMiduHead:
-    """librgie.so handle for the SD head, rebuilt when the batch size or the weights change."""
+    """librgie.so handle for the SD / SDXL head, rebuilt when the batch size or the weights change."""
 
-    def __init__(self, model: nn.Sequential, precision: str):
-        self.model, self.precision = model, precision
+    def __init__(self, model: nn.Sequential, precision: str, is_sdxl: bool = False):
+        self.model, self.precision, self.is_sdxl = model, precision, is_sdxl
         self._h, self._key = C.c_void_p(0), None
 
     def _weights_version(self):
@@ -38,10 +39,11 @@ class NativeMiduHead:
         if key != self._key:
             self.close()
             sd = self.model.state_dict()
-            names = ["0.weight", "0.bias", "3.weight", "3.bias", "7.weight", "7.bias", "9.weight", "9.bias"]
+            layers = ["0", "3", "6", "9", "13", "15"] if self.is_sdxl else ["0", "3", "7", "9"]   # convs then the two linears
+            names = [f"{l}.{k}" for l in layers for k in ("weight", "bias")]
             arrs = [np.ascontiguousarray(sd[n].detach().float().cpu().numpy()) for n in names]
             pt = (C.c_void_p * len(arrs))(*[a.ctypes.data_as(C.c_void_p) for a in arrs])
-            n_out = int(sd["9.weight"].shape[0])
+            n_out = int(sd[layers[-1] + ".weight"].shape[0])
             check(_lib.load().rgie_midu_create(pt, len(arrs), n_out, batch, hw, _lib.PRECISIONS[self.precision],
                                                C.byref(self._h)), "rgie_midu_create")
             self._key, self.n_out = key, n_out
@@ -86,8 +88,6 @@ class MiduClassifier(GuidanceClassifier):
     def __init__(self, pipe, device: str, ckp_path: str = None, num_outputs: int = 1, is_minimized: bool = True,
                  is_sdxl: bool = False, precision: str = DEFAULT_PRECISION):
         super().__init__(device)
-        if is_sdxl:
-            raise _lib.RgieError("the SDXL head variant is not implemented natively yet (SURVEY.md 8f rank 4)")
         self.pipe = pipe
         self.is_minimized = is_minimized
         self.pipe.unet.mid_block.register_forward_hook(self.__hook_fn)
@@ -97,7 +97,7 @@ class MiduClassifier(GuidanceClassifier):
             self.model.eval()
         self.criterion = nn.MSELoss()
         self.reference_value = None
-        self._native = NativeMiduHead(self.model, precision)
+        self._native = NativeMiduHead(self.model, precision, is_sdxl)
 
     def head(self, feature: Tensor) -> Tensor:
         """self.model(feature) evaluated by the native kernels (differentiable w.r.t. feature)."""
@@ -139,6 +139,14 @@ class MiduClassifier(GuidanceClassifier):
 
     @staticmethod
     def _create_midu_classifier(device, num_outputs=10, is_sdxl=False):                                # :121-161
+        if is_sdxl:                                                                                    # :125-143
+            m = nn.Sequential(
+                nn.Conv2d(1280, 512, kernel_size=3, padding=1), nn.ReLU(), nn.MaxPool2d(2, 2),
+                nn.Conv2d(512, 256, kernel_size=3, padding=1), nn.ReLU(), nn.MaxPool2d(2, 2),
+                nn.Conv2d(256, 128, kernel_size=3, padding=1), nn.ReLU(), nn.MaxPool2d(2, 2),
+                nn.Conv2d(128, 64, kernel_size=3, padding=1), nn.ReLU(), nn.MaxPool2d(2, 2),
+                nn.Flatten(), nn.Linear(64 * 2 * 2, 128), nn.ReLU(), nn.Linear(128, num_outputs))
+            return m.to(device)
         m = nn.Sequential(
             nn.Conv2d(1280, 256, kernel_size=3, padding=1), nn.ReLU(), nn.MaxPool2d(2, 2),
             nn.Conv2d(256, 128, kernel_size=3, padding=1), nn.ReLU(), nn.AdaptiveAvgPool2d(output_size=(2, 2)),

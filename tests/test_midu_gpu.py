@@ -80,6 +80,37 @@ def test_head_vs_oracle(precision, tol):
     assert abs(gn.norm().item() / gc.norm().item() - 1) <= (1e-3 if precision == "fp32" else 3e-2)
 
 
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 2e-2)])
+def test_sdxl_head_vs_oracle(precision, tol):
+    """SDXL head variant (MiduClassifier.py:125-143): four conv + ReLU + max-pool stages on 32x32 mid-block features."""
+    from regressor_guided_image_editing_b200.guidance_classifier.ValenceArousalMidu import ValenceArousalMidu
+    sd = O.make_midu_head_state_dict(4, is_sdxl=True)
+    B = 4
+    feat = torch.randn(B, 1280, 32, 32, generator=torch.Generator().manual_seed(6))
+    fc = feat.clone().requires_grad_(True)
+    pc = O.midu_head_forward(fc, sd)
+    lc = O.valence_arousal_score(pc, True, None)
+    gc, = torch.autograd.grad(lc, fc)
+    clf = ValenceArousalMidu(_pipe(DEV), DEV, is_sdxl=True, precision=precision)
+    clf.model.load_state_dict(sd)
+    # the nn.Sequential mirror itself must agree with the oracle's functional restatement
+    assert torch.allclose(clf.model.cpu()(feat), pc.detach(), atol=1e-5)
+    clf.model.to(DEV)
+    f = feat.to(DEV).requires_grad_(True)
+    pn = clf.head(f)
+    ln = clf._calculate_score(f, clf.head, DEV, True, None)
+    gn, = torch.autograd.grad(ln, f)
+    scale = pc.abs().max().item()
+    assert (pn.detach().cpu() - pc.detach()).abs().max().item() <= tol * max(scale, 1.0)
+    cos = torch.nn.functional.cosine_similarity(gn.cpu().flatten(), gc.flatten(), dim=0).item()
+    print(f"sdxl {precision}: pred err {(pn.detach().cpu() - pc.detach()).abs().max().item():.3e} cos {cos:.5f} "
+          f"norm ratio {gn.norm().item() / gc.norm().item():.4f}")
+    # bf16: four max-pools in a row route the gradient through arg-max positions; near-ties of the random-init features
+    # flip in bf16, so the direction is checked more loosely than for the SD head (one pool)
+    assert cos >= (0.9999 if precision == "fp32" else 0.95), cos
+    assert abs(gn.norm().item() / gc.norm().item() - 1) <= (1e-3 if precision == "fp32" else 5e-2)
+
+
 def test_guidance_step_through_test_double_unet():
     """The guidance lines :126-142 with the native head + native normalised update vs the same lines in torch on CPU."""
     from regressor_guided_image_editing_b200 import ops
