@@ -907,11 +907,12 @@ int rgie_regressor_forward_ex(RgieRegressor* R, const float* img, int B, int Hr,
   InXform xf = R->xf2;
   xf.mode = normalize;
   const int N = R->N, H0 = R->H0, H1 = R->Hs[1];
+  const int pack_threads = (H0 * 4) % 224 == 0 ? 224 : 256;     // 4 work items per output pixel: whole iterations per line
   if (R->dtype == 0) {
-    pack_crops_kernel<float><<<N * H0, 256, 0, st>>>(img, offsets, step_ptr, off_step_stride, (float*)R->zz, R->gZZ, reps, Hr,
+    pack_crops_kernel<float><<<N * H0, pack_threads, 0, st>>>(img, offsets, step_ptr, off_step_stride, (float*)R->zz, R->gZZ, reps, Hr,
                                                      Wr, xf);
   } else {
-    pack_crops_kernel<__nv_bfloat16><<<N * H0, 256, 0, st>>>(img, offsets, step_ptr, off_step_stride, (__nv_bfloat16*)R->zz,
+    pack_crops_kernel<__nv_bfloat16><<<N * H0, pack_threads, 0, st>>>(img, offsets, step_ptr, off_step_stride, (__nv_bfloat16*)R->zz,
                                                              R->gZZ, reps, Hr, Wr, xf);
   }
   RGIE_LAUNCH_OK();

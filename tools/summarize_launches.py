@@ -35,9 +35,10 @@ for i in step:
     f[1] += e.get("gpu__time_duration.sum", 0.0)
     f[2] += e.get("dram__bytes_read.sum", 0.0) + e.get("dram__bytes_write.sum", 0.0)
 tot = sum(v[1] for v in fam.values())
-gemm = sum(v[1] for k, v in fam.items() if k.startswith("gemm_"))
-gemm_n = sum(v[0] for k, v in fam.items() if k.startswith("gemm_"))
-gemm_b = sum(v[2] for k, v in fam.items() if k.startswith("gemm_"))
+is_gemm = lambda k: k.startswith("gemm_") or k.startswith("conv_hshare")      # the tcgen05 row-shifted GEMM family
+gemm = sum(v[1] for k, v in fam.items() if is_gemm(k))
+gemm_n = sum(v[0] for k, v in fam.items() if is_gemm(k))
+gemm_b = sum(v[2] for k, v in fam.items() if is_gemm(k))
 print(f"# one optimisation step: {len(step)} launches, {tot:.1f} us (cold-cache, serialised under ncu: compare SHARES)")
 print(f"# GEMM family: {gemm_n} launches, {gemm:.1f} us, share {100 * gemm / tot:.1f}%, DRAM {gemm_b / 1e9:.2f} GB "
       f"({gemm_b / max(gemm_n, 1) / 1e6:.1f} MB per launch)")
