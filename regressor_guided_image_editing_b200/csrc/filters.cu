@@ -621,8 +621,9 @@ __global__ void __launch_bounds__(kThreads) sharp_fwd_kernel(const float* __rest
   const int mode = sharp_mode(f);
   const float* pl = in + ((long)b * 3 + c) * H * W;
   float* po = out + ((long)b * 3 + c) * H * W;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
-    const int y = i / W, x = i - y * W;
+  for (int y = blockIdx.x * ((H + gridDim.x - 1) / gridDim.x); y < min(H, (int)(blockIdx.x + 1) * (int)((H + gridDim.x - 1) / gridDim.x)); ++y)   // contiguous rows per block: vertical reuse stays in L1
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {       // row loop: no per-pixel division
+    const int i = y * W + x;
     const float xin = pl[i];
     float result = xin;
     if (y >= 1 && y < H - 1 && x >= 1 && x < W - 1) result = clamp01(sharp_conv(pl, y, x, W));
@@ -649,8 +650,9 @@ __global__ void __launch_bounds__(kThreads) sharp_bwd_a_kernel(const float* __re
   const long off = ((long)b * 3 + c) * H * W;
   const float* pl = in + off;
   float acc[1] = {0.f};
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
-    const int y = i / W, x = i - y * W;
+  for (int y = blockIdx.x * ((H + gridDim.x - 1) / gridDim.x); y < min(H, (int)(blockIdx.x + 1) * (int)((H + gridDim.x - 1) / gridDim.x)); ++y)   // contiguous rows per block: vertical reuse stays in L1
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    const int i = y * W + x;
     const float xin = pl[i];
     const bool interior = y >= 1 && y < H - 1 && x >= 1 && x < W - 1;
     float conv = 0.f, result = xin;
@@ -678,8 +680,9 @@ __global__ void __launch_bounds__(kThreads) sharp_bwd_b_kernel(const float* __re
   const int b = blockIdx.z, c = blockIdx.y;
   const long off = ((long)b * 3 + c) * H * W;
   const float k1 = 1.0f / 13.0f, k5 = 5.0f / 13.0f;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
-    const int y = i / W, x = i - y * W;
+  for (int y = blockIdx.x * ((H + gridDim.x - 1) / gridDim.x); y < min(H, (int)(blockIdx.x + 1) * (int)((H + gridDim.x - 1) / gridDim.x)); ++y)   // contiguous rows per block: vertical reuse stays in L1
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    const int i = y * W + x;
     float s = 0.f;
 #pragma unroll
     for (int dy = -1; dy <= 1; ++dy) {
@@ -932,8 +935,9 @@ __global__ void __launch_bounds__(kThreads) scale_kernel(const float* __restrict
   const long base = (long)b * 3 * H * W;
   const int HW = H * W;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
-    const int y = i / W, x = i - y * W;
+  for (int y = blockIdx.x * ((H + gridDim.x - 1) / gridDim.x); y < min(H, (int)(blockIdx.x + 1) * (int)((H + gridDim.x - 1) / gridDim.x)); ++y)   // contiguous rows per block: vertical reuse stays in L1
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    const int i = y * W + x;
     const SampleCoord sxc = sample_coord(x, W, k.inv_sx, k.t02), syc = sample_coord(y, H, k.inv_sy, k.t12);
     const int x0 = sxc.i0, y0 = syc.i0, x1 = x0 + 1, y1 = y0 + 1;
     const float wx1 = sxc.w1, wx0 = 1.0f - wx1, wy1 = syc.w1, wy0 = 1.0f - wy1;
@@ -984,8 +988,9 @@ __global__ void __launch_bounds__(kThreads) scale_bwd_gather_kernel(const float*
   const float gy0 = lin_coord(0, H) * k.inv_sy + k.t12, gy1 = lin_coord(H - 1, H) * k.inv_sy + k.t12;
   const float c0y = ((gy0 + 1.0f) * 0.5f) * (float)(H - 1);
   const float sly = (((gy1 + 1.0f) * 0.5f) * (float)(H - 1) - c0y) / (float)(H - 1);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
-    const int v = i / W, u = i - v * W;
+  for (int v = blockIdx.x * ((H + gridDim.x - 1) / gridDim.x); v < min(H, (int)(blockIdx.x + 1) * (int)((H + gridDim.x - 1) / gridDim.x)); ++v)
+  for (int u = threadIdx.x; u < W; u += blockDim.x) {
+    const int i = v * W + u;
     int xlo = (int)floorf(((float)(u - 1) - c0x) / slx) - 1, xhi = (int)ceilf(((float)(u + 1) - c0x) / slx) + 1;
     int ylo = (int)floorf(((float)(v - 1) - c0y) / sly) - 1, yhi = (int)ceilf(((float)(v + 1) - c0y) / sly) + 1;
     xlo = max(xlo, 0); xhi = min(xhi, W - 1); ylo = max(ylo, 0); yhi = min(yhi, H - 1);
