@@ -50,7 +50,8 @@ enum RgieFilter {
   RGIE_F_BRIGHT = 9,     /* 1 param: clamp(x + p, 0, 1)                        :136-143 */
   RGIE_F_BW = 10,        /* 1 param: lerp(x, 0.27 r + 0.67 g + 0.06 b, p)      :156-163 */
   RGIE_F_HUE = 11,       /* 1 param: hsv hue shift, fmod(h + p, 2 pi)          :166-173 */
-  RGIE_F_WB = 12         /* 1 param: lerp(x, x * 0.5 / mean_HW(x), p)          :126-133 */
+  RGIE_F_WB = 12,        /* 1 param: lerp(x, x * 0.5 / mean_HW(x), p)          :126-133 */
+  RGIE_F_AFFINE = 13     /* 6 params: 2x3 matrix, bilinear warp, border padding :198-206 (d(image) by atomic scatter) */
 };
 int rgie_filter_param_count(int kind);
 /* floats of scratch `ws` that rgie_filter_fwd / rgie_filter_bwd need for a [B,3,H,W] batch */

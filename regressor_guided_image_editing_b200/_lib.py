@@ -12,10 +12,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librgie.so")
 
 F_EXPOSURE, F_SATURATION, F_TONE, F_COLOR, F_CONTRAST, F_SHARP, F_BLUR, F_SCALE = range(8)
-F_GAMMA, F_BRIGHT, F_BW, F_HUE, F_WB = range(8, 13)
+F_GAMMA, F_BRIGHT, F_BW, F_HUE, F_WB, F_AFFINE = range(8, 14)
 FILTER_KINDS = {"exposure": F_EXPOSURE, "saturation": F_SATURATION, "tone": F_TONE, "color": F_COLOR,
                 "contrast": F_CONTRAST, "sharp": F_SHARP, "blur": F_BLUR, "scale": F_SCALE,
-                "gamma": F_GAMMA, "bright": F_BRIGHT, "bw": F_BW, "hue": F_HUE, "wb": F_WB}
+                "gamma": F_GAMMA, "bright": F_BRIGHT, "bw": F_BW, "hue": F_HUE, "wb": F_WB, "affine": F_AFFINE}
 FILTER_NPARAM = {"exposure": 1, "saturation": 1, "tone": 8, "color": 24, "contrast": 1, "sharp": 1, "blur": 1,
                  "scale": 4}
 PREC_FP32, PREC_BF16, PREC_BF16_SIMT = 0, 1, 2

@@ -108,8 +108,8 @@ def apply_gamma(im, gamma_param):                            # :176-185
 
 
 def apply_affine_transformation(im, matrices):               # :198-206
-    raise _lib.RgieError("the general affine warp is not implemented natively yet (SURVEY.md 8f rank 1); "
-                         "apply_scale covers the reference's default filter list")
+    """kornia.geometry.transform.affine(im, matrices, padding_mode='border') + clamp; matrices [2,3] or [B,2,3]."""
+    return _Filter.apply(im, matrices, _lib.F_AFFINE, 6)
 
 
 _DISPATCH = {

@@ -1018,6 +1018,115 @@ __global__ void __launch_bounds__(kThreads) scale_bwd_gather_kernel(const float*
   }
 }
 
+// ===============================================================================================================
+// affine: kornia.geometry.transform.affine(im, M[2x3], padding_mode='border') + clamp   (image_transformations.py:198-206)
+//   warp_affine: theta = inv(N M3 N^-1)[:2] with N the pixel -> [-1,1] normalisation, affine_grid(align_corners=True),
+//   grid_sample(bilinear, border, align_corners=True).  Border padding clips the sampling coordinate to [0, size-1]; the
+//   gradient through a clipped coordinate is zero (ATen clip_coordinates_set_grad).
+// Forward: one gather per pixel.  Backward: d(theta) by block reductions (6 sums), d(image) by atomic scatter-add of the
+// four bilinear corners (summation order is not fixed), then d(M) from d(theta) through the 3x3 inverse in a one-thread
+// kernel per image.
+// ===============================================================================================================
+struct AffCoef { float t00, t01, t02, t10, t11, t12; };
+__device__ __forceinline__ AffCoef affine_theta(const float* m, int H, int W) {
+  const float a = 2.0f / (float)(W - 1), b = 2.0f / (float)(H - 1), ia = 0.5f * (float)(W - 1), ib = 0.5f * (float)(H - 1);
+  const float A00 = m[0], A01 = m[1] * (a * ib), A02 = a * (m[0] * ia + m[1] * ib + m[2]) - 1.0f;
+  const float A10 = m[3] * (b * ia), A11 = m[4], A12 = b * (m[3] * ia + m[4] * ib + m[5]) - 1.0f;
+  const float det = A00 * A11 - A01 * A10;
+  AffCoef t;
+  t.t00 = A11 / det; t.t01 = -A01 / det; t.t10 = -A10 / det; t.t11 = A00 / det;
+  t.t02 = -(t.t00 * A02 + t.t01 * A12);
+  t.t12 = -(t.t10 * A02 + t.t11 * A12);
+  return t;
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(kThreads) affine_kernel(const float* __restrict__ in, const float* __restrict__ gout,
+                                                         float* __restrict__ out, const float* __restrict__ p, int stride,
+                                                         float* __restrict__ partial, int H, int W) {
+  const int b = blockIdx.y;
+  const AffCoef k = affine_theta(p + (long)b * stride, H, W);
+  const long base = (long)b * 3 * H * W;
+  const int HW = H * W;
+  float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int y = blockIdx.x * ((H + gridDim.x - 1) / gridDim.x); y < min(H, (int)(blockIdx.x + 1) * (int)((H + gridDim.x - 1) / gridDim.x)); ++y)
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    const int i = y * W + x;
+    const float xn = lin_coord(x, W), yn = lin_coord(y, H);
+    const float xs = xn * k.t00 + yn * k.t01 + k.t02, ys = xn * k.t10 + yn * k.t11 + k.t12;
+    float ix = ((xs + 1.0f) * 0.5f) * (float)(W - 1), iy = ((ys + 1.0f) * 0.5f) * (float)(H - 1);
+    // ATen clip_coordinates_set_grad: the coordinate gradient is zero for in <= 0 and in >= size - 1
+    const bool cx = ix <= 0.f || ix >= (float)(W - 1), cy = iy <= 0.f || iy >= (float)(H - 1);
+    ix = fminf((float)(W - 1), fmaxf(ix, 0.f));
+    iy = fminf((float)(H - 1), fmaxf(iy, 0.f));
+    const float fx = floorf(ix), fy = floorf(iy);
+    const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+    const float wx1 = ix - fx, wx0 = 1.0f - wx1, wy1 = iy - fy, wy0 = 1.0f - wy1;
+    const bool vx1 = x1 < W, vy1 = y1 < H;                     // x0, y0 are always inside after the clip
+    float gix = 0.f, giy = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* pl = in + base + (long)c * HW;
+      const float v00 = pl[(long)y0 * W + x0];
+      const float v01 = vx1 ? pl[(long)y0 * W + x1] : 0.f;
+      const float v10 = vy1 ? pl[(long)y1 * W + x0] : 0.f;
+      const float v11 = (vy1 && vx1) ? pl[(long)y1 * W + x1] : 0.f;
+      const float o = v00 * (wx0 * wy0) + v01 * (wx1 * wy0) + v10 * (wx0 * wy1) + v11 * (wx1 * wy1);
+      if (!BWD) {
+        out[base + (long)c * HW + i] = clamp01(o);
+      } else {
+        const float g = in01(o) ? gout[base + (long)c * HW + i] : 0.f;
+        float* go = out + base + (long)c * HW;                  // d(image), zeroed by the launcher
+        atomicAdd(go + (long)y0 * W + x0, g * (wx0 * wy0));
+        if (vx1) atomicAdd(go + (long)y0 * W + x1, g * (wx1 * wy0));
+        if (vy1) atomicAdd(go + (long)y1 * W + x0, g * (wx0 * wy1));
+        if (vy1 && vx1) atomicAdd(go + (long)y1 * W + x1, g * (wx1 * wy1));
+        gix += g * ((v01 - v00) * wy0 + (v11 - v10) * wy1);
+        giy += g * ((v10 - v00) * wx0 + (v11 - v01) * wx1);
+      }
+    }
+    if (BWD) {
+      const float gxs = cx ? 0.f : gix * 0.5f * (float)(W - 1), gys = cy ? 0.f : giy * 0.5f * (float)(H - 1);
+      acc[0] += gxs * xn; acc[1] += gxs * yn; acc[2] += gxs;
+      acc[3] += gys * xn; acc[4] += gys * yn; acc[5] += gys;
+    }
+  }
+  if (BWD) block_reduce_store<6>(acc, partial + ((long)b * gridDim.x + blockIdx.x) * 6);
+}
+
+// d(M) from d(theta): theta = inv(A)[:2], A = N M3 N^-1  =>  dA = -T^T dT T^T, then the chain through A(M)
+__global__ void affine_param_grad_kernel(const float* __restrict__ dtheta, const float* __restrict__ p, int stride,
+                                         float* __restrict__ gp, int gp_stride, int B, int H, int W) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* m = p + (long)b * stride;
+  const AffCoef k = affine_theta(m, H, W);
+  const float T[3][3] = {{k.t00, k.t01, k.t02}, {k.t10, k.t11, k.t12}, {0.f, 0.f, 1.f}};
+  const float* g = dtheta + 6L * b;
+  const float G[3][3] = {{g[0], g[1], g[2]}, {g[3], g[4], g[5]}, {0.f, 0.f, 0.f}};
+  float TG[3][3], dA[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      float s = 0.f;
+      for (int q = 0; q < 3; ++q) s += T[q][i] * G[q][j];          // T^T G
+      TG[i][j] = s;
+    }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      float s = 0.f;
+      for (int q = 0; q < 3; ++q) s += TG[i][q] * T[j][q];          // (T^T G) T^T
+      dA[i][j] = -s;
+    }
+  const float a = 2.0f / (float)(W - 1), bb = 2.0f / (float)(H - 1), ia = 0.5f * (float)(W - 1), ib = 0.5f * (float)(H - 1);
+  float* o = gp + (long)b * gp_stride;
+  o[0] = dA[0][0] + dA[0][2] * (a * ia);
+  o[1] = (dA[0][1] + dA[0][2]) * (a * ib);
+  o[2] = dA[0][2] * a;
+  o[3] = (dA[1][0] + dA[1][2]) * (bb * ia);
+  o[4] = dA[1][1] + dA[1][2] * (bb * ib);
+  o[5] = dA[1][2] * bb;
+}
+
 int plane_blocks(int HW) { int n = ceil_div(HW, kThreads * 4); return n > 64 ? 64 : (n < 1 ? 1 : n); }
 
 }  // namespace
@@ -1039,6 +1148,7 @@ int rgie_filter_param_count(int kind) {
   switch (kind) {
     case RGIE_F_EXPOSURE: case RGIE_F_SATURATION: case RGIE_F_CONTRAST: case RGIE_F_SHARP: case RGIE_F_BLUR: return 1;
     case RGIE_F_GAMMA: case RGIE_F_BRIGHT: case RGIE_F_BW: case RGIE_F_HUE: case RGIE_F_WB: return 1;
+    case RGIE_F_AFFINE: return 6;
     case RGIE_F_TONE: return 8;
     case RGIE_F_COLOR: return 24;
     case RGIE_F_SCALE: return 4;
@@ -1112,6 +1222,13 @@ int rgie_filter_fwd(int kind, const float* in, float* out, const float* p, int p
       RGIE_CHECK(H >= 2 && W >= 2, "scale: image too small");
       dim3 grid(plane_blocks(HW), B);
       scale_kernel<false><<<grid, kThreads, 0, st>>>(in, nullptr, out, p, p_stride, nullptr, H, W);
+      RGIE_LAUNCH_OK();
+      return 0;
+    }
+    case RGIE_F_AFFINE: {
+      RGIE_CHECK(H >= 2 && W >= 2, "affine: image too small");
+      dim3 grid(plane_blocks(HW), B);
+      affine_kernel<false><<<grid, kThreads, 0, st>>>(in, nullptr, out, p, p_stride, nullptr, H, W);
       RGIE_LAUNCH_OK();
       return 0;
     }
@@ -1266,6 +1383,19 @@ int rgie_filter_bwd(int kind, const float* in, const float* gout, float* gin, co
       scale_bwd_gather_kernel<<<grid, kThreads, 0, st>>>(gm, gin, p, p_stride, H, W);
       RGIE_LAUNCH_OK();
       finalize_partials<<<B, 32, 0, st>>>(partial, nb, 4, gp, gp_stride);
+      break;
+    }
+    case RGIE_F_AFFINE: {
+      RGIE_CHECK(H >= 2 && W >= 2, "affine: image too small");
+      const int nb = plane_blocks(HW);
+      float* dtheta = ws + (long)B * kMaxBlk * 8;      // [B, 6]
+      dim3 grid(nb, B);
+      RGIE_CUDA_OK(cudaMemsetAsync(gin, 0, (size_t)B * 3 * HW * sizeof(float), st));
+      affine_kernel<true><<<grid, kThreads, 0, st>>>(in, gout, gin, p, p_stride, partial, H, W);
+      RGIE_LAUNCH_OK();
+      finalize_partials<<<B, 32, 0, st>>>(partial, nb, 6, dtheta, 6);
+      RGIE_LAUNCH_OK();
+      affine_param_grad_kernel<<<ceil_div(B, 128), 128, 0, st>>>(dtheta, p, p_stride, gp, gp_stride, B, H, W);
       break;
     }
     default:

@@ -28,6 +28,8 @@ def _param_tensor(name, val):
         return torch.tensor(val, dtype=torch.float32).view(1, 3, 8, 1)
     if name == "scale":
         return torch.tensor(val, dtype=torch.float32).view(1, 4)
+    if name == "affine":
+        return torch.tensor(val, dtype=torch.float32).view(1, 2, 3)
     if name == "bw":
         return torch.tensor(val, dtype=torch.float32).view(1)      # the reference indexes bw_param[:, None, None, None]
     return torch.tensor(val, dtype=torch.float32)
@@ -54,6 +56,9 @@ SINGLE_CASES = [
     ("bw", 0.0), ("bw", 0.4), ("bw", 1.0),
     ("hue", 0.0), ("hue", 0.7), ("hue", -2.1), ("hue", 3.0),
     ("wb", 0.0), ("wb", 0.5), ("wb", 1.0),
+    # general affine warp with border padding (generic values; identity is a kink for d(param) like scale's)
+    ("affine", [1.0, 0.0, 0.0, 0.0, 1.0, 0.0]), ("affine", [1.0371, 0.0513, 1.37, -0.0431, 0.9713, -2.21]),
+    ("affine", [0.8713, -0.1211, 3.19, 0.0917, 1.1307, 1.43]),
 ]
 
 
@@ -78,18 +83,19 @@ def test_single_filter_vs_oracle(name, val, hw):
     gi_g, gp_g = torch.autograd.grad((out_g * gout.to(DEV)).sum(), [im_g, p_g], allow_unused=True)
     gp_g = torch.zeros_like(p_g) if gp_g is None else gp_g
 
-    fwd_tol = 2e-4 if name == "scale" else 2e-6     # bilinear sampling positions differ at the 1e-5 px level
+    warp = name in ("scale", "affine")
+    fwd_tol = 2e-4 if warp else 2e-6                # bilinear sampling positions differ at the 1e-5 px level
     err = (out_g.cpu() - out_c).abs().max().item()
     assert err <= fwd_tol, f"{name} forward max-abs {err}"
     # image gradient: robust relative-L1 criterion (isolated pixels sit exactly on clamp / tie boundaries)
     gden = gi_c.abs().mean().item() + 1e-12
     gerr = (gi_g.cpu() - gi_c).abs().mean().item() / gden
-    gtol = 2e-3 if name == "scale" else 1e-4
+    gtol = 2e-3 if warp else 1e-4
     assert gerr <= gtol, f"{name} d(image) relative L1 {gerr}"
     pden = gp_c.abs().max().item() + 1e-6 * gout.numel() ** 0.5
     perr = (gp_g.cpu() - gp_c).abs().max().item() / pden
-    ptol = 5e-3 if name == "scale" else 5e-4
-    if name == "scale" and list(val) == [1.0, 1.0, 0.0, 0.0]:
+    ptol = 5e-3 if warp else 5e-4
+    if (name == "scale" and list(val) == [1.0, 1.0, 0.0, 0.0]) or (name == "affine" and list(val) == [1.0, 0.0, 0.0, 0.0, 1.0, 0.0]):
         return            # d(param) at exact identity is a kink (see SINGLE_CASES comment)
     assert perr <= ptol, f"{name} d(param) {gp_g.cpu().flatten()[:4]} vs {gp_c.flatten()[:4]} rel {perr}"
 
