@@ -25,7 +25,9 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;                 // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-__host__ __device__ constexpr int num_threads(int new_warps) { return 64 + 32 * new_warps; }   // TMA warp + MMA warp + NEW epilogue warps
+// TMA warp + MMA warp + NEW epilogue warps.  NEW = 16: warps 0..3 form the producer warpgroup (TMA, MMA, two idle warps)
+// so that setmaxnreg can move registers from it to the four epilogue warpgroups (warps 4..19).
+__host__ __device__ constexpr int num_threads(int new_warps) { return new_warps == 16 ? 640 : 64 + 32 * new_warps; }
 constexpr int MAX_BIAS = 2048;
 
 constexpr uint32_t kWaitHintNs = RGIE_WAIT_HINT_NS;
@@ -578,6 +580,135 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
   }
 }
 
+// ===================== lean epilogue for 16 epilogue warps (BN = 256, bf16 output, no activation mask) =====================
+// The HBM-bound 1x1 expansions are limited by the latency chain of their epilogue (tcgen05.ld -> math -> store) at two
+// epilogue warps per scheduler.  This variant runs FOUR warps per scheduler: warps 4..19, each a TMEM lane quarter
+// (warp & 3) x a 64-column part, walking its part in 16-column chunks so that the whole role fits in 120 registers
+// (setmaxnreg moves registers from the producer warpgroup).  Same arithmetic and the same bit-mask layout as
+// epilogue_role.
+template <int BN>
+__device__ __forceinline__ void epilogue_lean_role(const GemmDesc& d, const float* sbias, const uint32_t tmem_base,
+                                                   const uint32_t tfull0, const uint32_t tempty0, const int warp,
+                                                   const int lane, const int num_tiles, const int num_n_tiles,
+                                                   const FastDiv fd_nt) {
+  static_assert(BN == 256, "lean epilogue: 4 parts of 64 columns");
+  constexpr int CH = 16, CPW = 4;
+  auto tfull_bar = [&](int a) { return tfull0 + 8u * a; };
+  auto tempty_bar = [&](int a) { return tempty0 + 8u * a; };
+  const int q = warp & 3;
+  const int part = (warp - 4) >> 2;
+  const int row = q * 32 + lane;
+  const int col0 = part * 64;
+  const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(d.res);
+  const uint32_t* mbits = d.mask_bits;
+  const bool has_bias = d.bias != nullptr;
+  const long res_lim = d.res_rows < d.m_end ? d.res_rows : d.m_end;
+
+  uint32_t rbuf[2][CH / 2];                        // residual: chunk ci lives in buffer ci & 1, refilled two chunks ahead
+  uint32_t bits_nxt[2];
+  const __nv_bfloat16* nres = nullptr;
+  const __nv_bfloat16* cres = nullptr;
+  auto locate = [&](int tile) {
+    cres = nres;
+    nres = nullptr;
+    bits_nxt[0] = bits_nxt[1] = 0u;
+    if (tile < num_tiles) {
+      const int mt = (int)fd_nt.div((uint32_t)tile), nt = tile - mt * num_n_tiles;
+      const long m = d.m_begin + (long)mt * BM + row;
+      if (res != nullptr && m < res_lim) nres = res + m * d.ld_res + nt * BN + col0;
+      if (mbits != nullptr && m < d.m_end) {
+        const int w0 = (nt * BN + col0) / 32;
+        bits_nxt[0] = __ldg(mbits + bits_index(m, w0, d.ld_mb));
+        bits_nxt[1] = __ldg(mbits + bits_index(m, w0 + 1, d.ld_mb));
+      }
+    }
+  };
+  auto res_fetch = [&](int cj) {
+    const __nv_bfloat16* p = cj < CPW ? cres : nres;
+    const int cc = cj < CPW ? cj : cj - CPW;
+    if (p != nullptr) ldg256(p + cc * CH, rbuf[cj & 1]);
+  };
+  locate(blockIdx.x);
+  cres = nres;
+  res_fetch(0);
+  res_fetch(1);
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    const int mt = (int)fd_nt.div((uint32_t)tile), nt = tile - mt * num_n_tiles;
+    const int acc = it & 1;
+    const uint32_t acc_phase = (it >> 1) & 1;
+    const long m = d.m_begin + (long)mt * BM + row;
+    long dest = -1;
+    if (m < d.m_end) dest = map_row(d.src, d.dst_kind, d.dst, m);
+    const bool live = dest >= 0;
+    const bool use_res = live && res != nullptr && m < d.res_rows;
+    const uint32_t bits_cur0 = bits_nxt[0], bits_cur1 = bits_nxt[1];
+    uint32_t bits_out0 = 0u, bits_out1 = 0u;
+    locate(tile + gridDim.x);
+    mbar_wait(tfull_bar(acc), acc_phase);
+    tcgen05_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + col0);
+#pragma unroll
+    for (int ci = 0; ci < CPW; ++ci) {
+      uint32_t r[CH];
+      tmem_ld<CH>(taddr + (uint32_t)(ci * CH), r);
+      tmem_ld_wait();
+      const int n0 = nt * BN + col0 + ci * CH;
+      float v[CH];
+#pragma unroll
+      for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
+      if (use_res) {
+#pragma unroll
+        for (int j = 0; j < CH / 2; ++j) { v[2 * j] += bf16_lo(rbuf[ci & 1][j]); v[2 * j + 1] += bf16_hi(rbuf[ci & 1][j]); }
+      }
+      res_fetch(ci + 2);
+      if (live) {
+        if (has_bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(sbias + n0);
+#pragma unroll
+          for (int j = 0; j < CH / 4; ++j) {
+            const float4 b = b4[j];
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          }
+        }
+        uint32_t wout = 0u;
+        if (d.relu) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
+          if (d.D_bits != nullptr) {
+#pragma unroll
+            for (int j = CH - 1; j >= 0; --j) wout = push_positive_bit(wout, v[j]);
+          }
+        } else if (d.D_bits != nullptr) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) wout |= (v[j] > 0.f ? 1u : 0u) << j;
+        }
+        if (mbits != nullptr) {
+          const uint32_t w = ((ci < 2 ? bits_cur0 : bits_cur1) >> (16 * (ci & 1))) & 0xFFFFu;
+          wout &= w;
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] = keep_if_bit(v[j], w, j);
+        }
+        if (ci < 2) bits_out0 |= wout << (16 * (ci & 1)); else bits_out1 |= wout << (16 * (ci & 1));
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(d.D) + dest * d.ldd + n0;
+        uint32_t pk[CH / 2];
+#pragma unroll
+        for (int j = 0; j < CH / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+        stg256(o, pk);
+      }
+    }
+    if (live && d.D_bits != nullptr) {
+      const int w0 = (nt * BN + col0) / 32;
+      d.D_bits[bits_index(dest, w0, d.ld_db)] = bits_out0;
+      d.D_bits[bits_index(dest, w0 + 1, d.ld_db)] = bits_out1;
+    }
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty_bar(acc));
+  }
+}
+
 template <int BN, int STAGES, int EPI, int NEW, bool PAIR>
 __global__ void __launch_bounds__(num_threads(NEW), 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
@@ -638,6 +769,17 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  // NEW == 16: register re-allocation between warpgroups -- 640 threads launch with 96 registers each; the producer
+  // warpgroup (warps 0..3) keeps 32, which lets the 16 epilogue warps grow to 112 (the pool is the CTA's own allocation: 128 x 32 + 512 x 112 = 640 x 96).
+  // Every warp of a warpgroup executes the SAME setmaxnreg instruction (.sync.aligned), and it dominates the role code
+  // so that ptxas allocates each role against its own budget.
+  if (NEW == 16 && warp >= 4) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    if constexpr (NEW == 16)
+      epilogue_lean_role<BN>(d, reinterpret_cast<const float*>(smem + L::BIAS_OFF), tmem_base, tfull_bar(0), tempty_bar(0), warp,
+                             lane, num_tiles, num_n_tiles, fd_nt);
+  } else {
+  if (NEW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -713,6 +855,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (PAIR) umma_commit(tfull_bar(1));
       }
     }
+  } else if constexpr (NEW == 16) {
+    static_assert(EPI == 0 && !PAIR, "16 epilogue warps: lean row-per-thread epilogue only");
+    // warps 2, 3: idle members of the producer warpgroup
   } else if constexpr (EPI >= 1) {
     static_assert(EPI == 0 || NEW == 8, "the store epilogue runs with 8 epilogue warps");
     epilogue_store_role<BN, EPI>(d, &tmD, &tmR, reinterpret_cast<const float*>(smem + L::BIAS_OFF), smem_base + L::OB_OFF,
@@ -722,6 +867,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     epilogue_role<BN, NEW, false, 2, PAIR>(d, reinterpret_cast<const float*>(smem + L::BIAS_OFF), tmem_base, tfull_bar(0),
                                            tempty_bar(0), warp, lane, num_tiles, num_n_tiles, fd_nt,
                                            PatchMap{0, 0, 0, FastDiv{1, 0, 0}});
+  }
   }
 
   // ===================== teardown =====================
@@ -1242,12 +1388,15 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
   int sms = gemm_sm100_num_sms();
   p->grid = (int)(tiles < sms ? tiles : sms);
   if (p->grid < 1) p->grid = 1;
-  // epilogue variant (measured per shape class on B200, profiles/README.md): the TMA-store epilogue wins where the epilogue
-  // reads a residual AND a bit mask (conv1 input gradients of the identity blocks); everywhere else the row-per-thread
-  // epilogue is as fast or faster.  RGIE_GEMM_EPI = 0 / 1 / 2 / 4 forces a variant for A/B experiments.
+  // epilogue variant (measured per shape class on B200, profiles/README.md): 256-wide bf16 tiles use the 16-warp lean epilogue
+  // (setmaxnreg: producer warpgroup 32 registers, epilogue warpgroups 112; 0.81 -> 0.64 ms on the layer1 expansion, 3 % of the
+  // GEMM family); the TMA-store epilogue stays where the epilogue reads a residual AND a bit mask (conv1 input gradients of the
+  // identity blocks, a tie with the lean one); everything else takes the classic 8-warp row-per-thread epilogue.
+  // RGIE_GEMM_EPI = 0 (classic everywhere) / 1 / 2 / 4 (TMA-store variants) / -16 (lean wherever eligible) for A/B experiments.
   static const int env_epi = getenv("RGIE_GEMM_EPI") ? atoi(getenv("RGIE_GEMM_EPI")) : -1;
   const int ktot = d.ntaps * d.Cin + (d.A2 ? d.Cin2 : 0);
-  p->epi = env_epi == -16 ? -16 : 0;
+  const bool lean_ok = bn == 256 && !d.d_fp32 && d.mask == nullptr;
+  p->epi = (lean_ok && (env_epi == -16 || env_epi == -1)) ? -16 : 0;
   if (bn == 256 && d.dst_kind == DST_SAME && !d.d_fp32 && d.mask == nullptr && env_epi != 0 && env_epi != -16) {
     if (d.res != nullptr) {
       if (env_epi == 2 || env_epi == 4) p->epi = env_epi;
@@ -1261,7 +1410,7 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
   //      MEASURED: no gain on B200 (N=256,K=2304: 0.242 -> 0.275 ms; N=512,K=4608: 0.240 -> 0.234 ms per 320 crops): these layers
   //      already run at 88-91 % of the sustained (power-capped) cuBLAS rate, the operand feed is not their limiter.  Off by default.
   static const int env_pair = getenv("RGIE_GEMM_PAIR_MINK") ? atoi(getenv("RGIE_GEMM_PAIR_MINK")) : 0;
-  if (bn == 256 && p->epi == 0 && env_pair > 0 && ktot >= env_pair && p->num_m_tiles >= 2) {
+  if (bn == 256 && (p->epi == 0 || p->epi == -16) && env_pair > 0 && ktot >= env_pair && p->num_m_tiles >= 2) {
     p->epi = -2;
     const long pairs = (long)((p->num_m_tiles + 1) / 2) * p->num_n_tiles;
     p->grid = (int)(pairs < sms ? pairs : sms);
