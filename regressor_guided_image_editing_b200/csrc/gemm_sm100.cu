@@ -90,6 +90,43 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
+// ---- cta_group::2 (CTA pair) variants: one MMA of M = 256 spans the two SMs of a TPC; each CTA holds its own 128 A rows and
+// HALF of the B tile, so the shared-memory operand traffic per SM drops from 48 KB to 32 KB per 128x256x64 k-block.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {   // same offset in CTA `rank` of the cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of a CTA pair: the bytes land in THIS CTA's shared memory, the transaction count goes to the leader's barrier
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(leader_bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -586,11 +623,19 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
 // (warp & 3) x a 64-column part, walking its part in 16-column chunks so that the whole role fits in 120 registers
 // (setmaxnreg moves registers from the producer warpgroup).  Same arithmetic and the same bit-mask layout as
 // epilogue_role.
-template <int BN>
+#ifndef RGIE_LEAN_NRB
+#define RGIE_LEAN_NRB 4
+#endif
+// TWO: CTA-pair kernel -- `num_tiles` counts PAIRS of M-adjacent tiles, cluster c walks pairs c, c + clusters, ...; the CTA
+// of rank r owns tile 2 * pair_m + r, and the accumulator-free arrive goes to the leader CTA's barrier.
+template <int BN, bool TWO = false>
 __device__ __forceinline__ void epilogue_lean_role(const GemmDesc& d, const float* sbias, const uint32_t tmem_base,
                                                    const uint32_t tfull0, const uint32_t tempty0, const int warp,
                                                    const int lane, const int num_tiles, const int num_n_tiles,
                                                    const FastDiv fd_nt) {
+  const int t_first = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int t_stride = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int t_rank = TWO ? (int)cluster_ctarank() : 0;
   static_assert(BN == 256, "lean epilogue: 4 parts of 64 columns");
   constexpr int CH = 16, CPW = 4;
   auto tfull_bar = [&](int a) { return tfull0 + 8u * a; };
@@ -604,7 +649,9 @@ __device__ __forceinline__ void epilogue_lean_role(const GemmDesc& d, const floa
   const bool has_bias = d.bias != nullptr;
   const long res_lim = d.res_rows < d.m_end ? d.res_rows : d.m_end;
 
-  uint32_t rbuf[2][CH / 2];                        // residual: chunk ci lives in buffer ci & 1, refilled two chunks ahead
+  constexpr int NRB = RGIE_LEAN_NRB;               // residual: chunk ci lives in buffer ci % NRB, refilled NRB chunks ahead
+  static_assert(NRB == 2 || NRB == 4, "NRB");
+  uint32_t rbuf[NRB][CH / 2];
   uint32_t bits_nxt[2];
   const __nv_bfloat16* nres = nullptr;
   const __nv_bfloat16* cres = nullptr;
@@ -613,7 +660,8 @@ __device__ __forceinline__ void epilogue_lean_role(const GemmDesc& d, const floa
     nres = nullptr;
     bits_nxt[0] = bits_nxt[1] = 0u;
     if (tile < num_tiles) {
-      const int mt = (int)fd_nt.div((uint32_t)tile), nt = tile - mt * num_n_tiles;
+      const int tq = (int)fd_nt.div((uint32_t)tile), nt = tile - tq * num_n_tiles;
+      const int mt = TWO ? 2 * tq + t_rank : tq;
       const long m = d.m_begin + (long)mt * BM + row;
       if (res != nullptr && m < res_lim) nres = res + m * d.ld_res + nt * BN + col0;
       if (mbits != nullptr && m < d.m_end) {
@@ -626,16 +674,17 @@ __device__ __forceinline__ void epilogue_lean_role(const GemmDesc& d, const floa
   auto res_fetch = [&](int cj) {
     const __nv_bfloat16* p = cj < CPW ? cres : nres;
     const int cc = cj < CPW ? cj : cj - CPW;
-    if (p != nullptr) ldg256(p + cc * CH, rbuf[cj & 1]);
+    if (p != nullptr) ldg256(p + cc * CH, rbuf[cj & (NRB - 1)]);
   };
-  locate(blockIdx.x);
+  locate(t_first);
   cres = nres;
-  res_fetch(0);
-  res_fetch(1);
+#pragma unroll
+  for (int cj = 0; cj < NRB; ++cj) res_fetch(cj);
 
   int it = 0;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-    const int mt = (int)fd_nt.div((uint32_t)tile), nt = tile - mt * num_n_tiles;
+  for (int tile = t_first; tile < num_tiles; tile += t_stride, ++it) {
+    const int tq = (int)fd_nt.div((uint32_t)tile), nt = tile - tq * num_n_tiles;
+    const int mt = TWO ? 2 * tq + t_rank : tq;
     const int acc = it & 1;
     const uint32_t acc_phase = (it >> 1) & 1;
     const long m = d.m_begin + (long)mt * BM + row;
@@ -645,7 +694,7 @@ __device__ __forceinline__ void epilogue_lean_role(const GemmDesc& d, const floa
     const bool use_res = live && res != nullptr && m < d.res_rows;
     const uint32_t bits_cur0 = bits_nxt[0], bits_cur1 = bits_nxt[1];
     uint32_t bits_out0 = 0u, bits_out1 = 0u;
-    locate(tile + gridDim.x);
+    locate(tile + t_stride);
     mbar_wait(tfull_bar(acc), acc_phase);
     tcgen05_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + col0);
@@ -660,9 +709,11 @@ __device__ __forceinline__ void epilogue_lean_role(const GemmDesc& d, const floa
       for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
       if (use_res) {
 #pragma unroll
-        for (int j = 0; j < CH / 2; ++j) { v[2 * j] += bf16_lo(rbuf[ci & 1][j]); v[2 * j + 1] += bf16_hi(rbuf[ci & 1][j]); }
+        for (int j = 0; j < CH / 2; ++j) {
+          v[2 * j] += bf16_lo(rbuf[ci & (NRB - 1)][j]); v[2 * j + 1] += bf16_hi(rbuf[ci & (NRB - 1)][j]);
+        }
       }
-      res_fetch(ci + 2);
+      res_fetch(ci + NRB);
       if (live) {
         if (has_bias) {
           const float4* b4 = reinterpret_cast<const float4*>(sbias + n0);
@@ -705,7 +756,9 @@ __device__ __forceinline__ void epilogue_lean_role(const GemmDesc& d, const floa
     }
     tcgen05_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(tempty_bar(acc));
+    if (lane == 0) {
+      if (TWO) mbar_arrive_cluster(mapa_rank(tempty_bar(acc), 0)); else mbar_arrive(tempty_bar(acc));
+    }
   }
 }
 
@@ -876,6 +929,166 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ===============================================================================================================
+// CTA-pair kernel (cta_group::2): a cluster of two CTAs (the two SMs of a TPC) computes a 256 x 256 output tile = two
+// M-adjacent 128-row tiles with the same 256 output channels.  Per k-block each CTA loads its own 128 x 64 A tile and HALF
+// of the 256 x 64 weight tile (32 KB instead of 48 KB per SM); the leader CTA's single thread issues
+// tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 16), each CTA's TMEM receives its own 128 accumulator rows, and each CTA
+// runs the 16-warp lean epilogue on them.
+//   full[s]   (leader's): leader expects the bytes of BOTH CTAs; the peer's TMA loads signal it (cta_group::2 loads)
+//   empty[s]  (each CTA's own): multicast tcgen05.commit of the leader
+//   tfull[a]  (each CTA's own): multicast tcgen05.commit
+//   tempty[a] (leader's): 32 arrivals = 16 epilogue warps x 2 CTAs (the peer arrives remotely)
+// ===============================================================================================================
+template <int STAGES>
+struct Smem2 {
+  static constexpr int B_HALF_BYTES = 128 * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_HALF_BYTES;
+  static constexpr int A_OFF = 0;
+  static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;              // full[S], empty[S], tfull[2], tempty[2]
+  static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * STAGES + 4) * 8;
+  static constexpr int BIAS_OFF = (TMEM_PTR_OFF + 16 + 15) & ~15;
+  static constexpr int TOTAL = BIAS_OFF + MAX_BIAS * 4;
+  static constexpr int DYN_BYTES = TOTAL + 1024;
+  static_assert(DYN_BYTES <= 232448, "shared memory plan exceeds 227 KB");
+};
+
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1)
+gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                       const __grid_constant__ CUtensorMap tmBh, const GemmDesc d, const int num_m_tiles,
+                       const int num_n_tiles, const FastDiv fd_nt) {
+  using L = Smem2<STAGES>;
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_base + L::BAR_OFF;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_PTR_OFF);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair_first = (int)(blockIdx.x >> 1), pair_stride = (int)(gridDim.x >> 1);
+  const int num_pairs = ((num_m_tiles + 1) >> 1) * num_n_tiles;
+  const int kb_per_tap = d.Cin / BK;
+  const int num_kb = d.ntaps * kb_per_tap;
+  const int num_kb2 = d.A2 != nullptr ? d.Cin2 / BK : 0;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmBh) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_base + L::TMEM_PTR_OFF),
+                 "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (d.bias != nullptr) {
+    float* sb = reinterpret_cast<float*>(smem + L::BIAS_OFF);
+    for (int i = threadIdx.x; i < d.Cout; i += 640) sb[i] = d.bias[i];
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // the peer's barriers are initialised and its TMEM is allocated before anything crosses over
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp >= 4) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    epilogue_lean_role<BN, true>(d, reinterpret_cast<const float*>(smem + L::BIAS_OFF), tmem_base, tfull_bar(0), tempty_bar(0),
+                                 warp, lane, num_pairs, num_n_tiles, fd_nt);
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    if (warp == 0) {
+      // ===================== TMA producer (both CTAs) =====================
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int pair = pair_first; pair < num_pairs; pair += pair_stride) {
+          const int tq = (int)fd_nt.div((uint32_t)pair), nt = pair - tq * num_n_tiles;
+          const long m0_pair = d.m_begin + (long)(2 * tq) * BM;
+          const long m0 = m0_pair + (long)rank * BM;
+          const int n0 = nt * BN + (int)rank * 128;
+          int tap = 0, cb = 0;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            const uint32_t lfull = mapa_rank(full_bar(stage), 0);
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);
+            tma_load_2d_2cta(smem_base + L::A_OFF + stage * A_STAGE_BYTES, &tmA, cb * BK, (int)(m0 + d.row_off[tap]), lfull);
+            tma_load_2d_2cta(smem_base + L::B_OFF + stage * L::B_HALF_BYTES, &tmBh, kb * BK, n0, lfull);
+            if (++cb == kb_per_tap) { cb = 0; ++tap; }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (m0_pair < d.a2_rows) {
+            for (int kb = 0; kb < num_kb2; ++kb) {
+              mbar_wait(empty_bar(stage), phase ^ 1);
+              const uint32_t lfull = mapa_rank(full_bar(stage), 0);
+              if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);
+              tma_load_2d_2cta(smem_base + L::A_OFF + stage * A_STAGE_BYTES, &tmA2, kb * BK, (int)m0, lfull);
+              tma_load_2d_2cta(smem_base + L::B_OFF + stage * L::B_HALF_BYTES, &tmBh, (num_kb + kb) * BK, n0, lfull);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer (one thread of the leader CTA) =====================
+      if (lane == 0 && rank == 0) {
+        constexpr uint32_t idesc = make_idesc(2 * BM, BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int pair = pair_first; pair < num_pairs; pair += pair_stride, ++it) {
+          const int acc = it & 1;
+          const uint32_t acc_phase = (it >> 1) & 1;
+          const long m0_pair = d.m_begin + (long)(2 * (int)fd_nt.div((uint32_t)pair)) * BM;
+          const int kb_total = num_kb + (m0_pair < d.a2_rows ? num_kb2 : 0);
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+          for (int kb = 0; kb < kb_total; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tcgen05_fence_after();
+            const uint64_t adesc = make_smem_desc(smem_base + L::A_OFF + stage * A_STAGE_BYTES);
+            const uint64_t bdesc = make_smem_desc(smem_base + L::B_OFF + stage * L::B_HALF_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_2cta(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2cta(empty_bar(stage));
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit_2cta(tfull_bar(acc));
+        }
+      }
+    }
+  }
+
+  // ===================== teardown: nobody leaves while the peer may still signal into this CTA =====================
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -1285,6 +1498,23 @@ int run_patch(const GemmPlanSm100& p, cudaStream_t st) {
   return 0;
 }
 
+#ifndef RGIE_2CTA_STAGES
+#define RGIE_2CTA_STAGES 6
+#endif
+int run_2cta(const GemmPlanSm100& p, cudaStream_t st) {
+  using L = Smem2<RGIE_2CTA_STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RGIE_CUDA_OK(cudaFuncSetAttribute(gemm_sm100_2cta_kernel<RGIE_2CTA_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      L::DYN_BYTES));
+    attr_set = true;
+  }
+  gemm_sm100_2cta_kernel<RGIE_2CTA_STAGES><<<p.grid, 640, L::DYN_BYTES, st>>>(
+      p.tmA, p.tmA2, p.tmB, p.d, p.num_m_tiles, p.num_n_tiles, make_fastdiv((uint32_t)p.num_n_tiles));
+  RGIE_LAUNCH_OK();
+  return 0;
+}
+
 template <int BN, int STAGES, int EPI, int NEW, bool PAIR = false>
 int run_impl(const GemmPlanSm100& p, cudaStream_t st) {
   using L = SmemLayout<BN, STAGES, EPI, PAIR>;
@@ -1405,6 +1635,17 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
       p->epi = 1;
     }
   }
+  // CTA pairs (cta_group::2, M = 256 across the two SMs of a TPC) for the tensor-bound 256-wide tiles: contraction >= 768.
+  // Measured (320 crops, same box, clock drift removed): K >= 1024 layers -6 % (1.36-1.47 PFLOP/s); K <= 640 layers are
+  // epilogue-bound and LOSE 7-28 % (the leader's MMA waits for the epilogues of BOTH CTAs across the TPC), so they stay on
+  // the single-CTA kernel.  RGIE_GEMM_2CTA = 0 switches pairs off, = K sets the contraction threshold.
+  static const int env_2cta = getenv("RGIE_GEMM_2CTA") ? atoi(getenv("RGIE_GEMM_2CTA")) : 768;
+  if (p->epi == -16 && env_2cta > 0 && ktot >= env_2cta && p->num_m_tiles >= 2) {
+    p->epi = -32;
+    const long pairs = (long)((p->num_m_tiles + 1) / 2) * p->num_n_tiles;
+    const long ctas = 2 * pairs < (long)(sms & ~1) ? 2 * pairs : (long)(sms & ~1);
+    p->grid = (int)ctas;
+  }
   // tile pairing (two M-adjacent tiles share every weight-tile load): the large-K layers are bound by the L2->SM operand
   // feed (48 KB per 128x256x64 k-block vs ~54 B/clk/SM measured), pairing cuts it to 32 KB per k-block and tile
   //      MEASURED: no gain on B200 (N=256,K=2304: 0.242 -> 0.275 ms; N=512,K=4608: 0.240 -> 0.234 ms per 320 crops): these layers
@@ -1431,7 +1672,8 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
   if (d.A2 != nullptr) rc = make_map_2d(&p->tmA2, d.A2, (uint64_t)d.Cin2, (uint64_t)d.a2_rows, BK, BM);
   else p->tmA2 = p->tmA;
   if (rc) return rc;
-  return make_map_2d(&p->tmB, d.Wt, (uint64_t)d.ntaps * d.Cin + (d.A2 ? d.Cin2 : 0), (uint64_t)d.n_pad, BK, (uint32_t)bn);
+  return make_map_2d(&p->tmB, d.Wt, (uint64_t)d.ntaps * d.Cin + (d.A2 ? d.Cin2 : 0), (uint64_t)d.n_pad, BK,
+                     (uint32_t)(p->epi == -32 ? 128 : bn));   // CTA pairs: each CTA loads half of the 256 weight rows
 }
 
 // Plan for conv_hshare_kernel.  d: the 16-tap input-gradient descriptor of the flat formulation (geometry, source,
@@ -1494,6 +1736,7 @@ int run_gemm_sm100(const GemmPlanSm100& p, cudaStream_t st) {
         case 2: return run_impl<256, 3, 2, 8>(p, st);
         case 1: return run_impl<256, 3, 1, 8>(p, st);
         case -16: return run_impl<256, 4, 0, 16>(p, st);
+        case -32: return run_2cta(p, st);
         case -2: return run_impl<256, 3, 0, 8, true>(p, st);
         default: return run_impl<256, 4, 0, 8>(p, st);
       }

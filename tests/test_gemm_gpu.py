@@ -130,6 +130,12 @@ EX_CASES = [
     (40000, 256, 0, 0, 1024, [0], True, False, True),            # residual ring, many tiles per CTA
     (3000, 64, 0, 0, 64, [-59, -58, -57, -1, 0, 1, 57, 58, 59], False, True, True),
     (6000, 512, 0, 0, 128, [0], False, True, True),
+    # CTA-pair kernel (cta_group::2; contraction >= 768, 256-wide tiles): odd tile count, residual + bits
+    (9000, 1024, 0, 0, 512, [0], True, False, True),
+    # CTA pairs, nine row-shifted taps, ReLU bit mask
+    (5000, 128, 0, 0, 256, [-71, -70, -69, -1, 0, 1, 69, 70, 71], False, True, True),
+    # CTA pairs, second operand ends inside a pair (tile 10 is below a2_rows, its partner tile 11 is not)
+    (5000, 512, 512, 1400, 256, [0], False, True, False),
 ]
 
 
