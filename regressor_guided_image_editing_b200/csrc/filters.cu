@@ -66,9 +66,16 @@ struct LaunchShape {
   int nblk;    // blocks per image
   int chunk;   // pixels per block (multiple of 4)
 };
-LaunchShape shape_for(int HW) {
+// Forward passes: 2048 pixels per block.  Backward passes end in a block reduction of up to 24 parameter gradients
+// (5 shuffles each + shared memory), which costs as much as ~25 pixels of arithmetic per thread: they take 8192 pixels per
+// block (32 per thread) unless that would leave the GPU with fewer than ~4 blocks per SM.
+LaunchShape shape_for(int HW, int B = 1, bool bwd = false) {
   LaunchShape s;
   s.nblk = ceil_div(HW, 2048);
+  if (bwd) {
+    const int coarse = ceil_div(HW, 8192);
+    if ((long)coarse * B >= 592) s.nblk = coarse;
+  }
   if (s.nblk > kMaxBlk) s.nblk = kMaxBlk;
   if (s.nblk < 1) s.nblk = 1;
   s.chunk = ceil_div(ceil_div(HW, s.nblk), 4) * 4;
@@ -455,7 +462,7 @@ struct WbOp {                  // img_trans_torch_diff.py:51-57: clamp(lerp(im, 
 
 // ---------------------------------------------------------------------------------------------------------------
 template <class Op, int VEC, bool BWD>
-__global__ void __launch_bounds__(kThreads) pointwise_kernel(const float* __restrict__ in, const float* __restrict__ gout,
+__global__ void __launch_bounds__(kThreads, BWD ? 3 : 4) pointwise_kernel(const float* __restrict__ in, const float* __restrict__ gout,
                                                             float* __restrict__ out, Op op, float* __restrict__ partial,
                                                             int HW, int chunk) {
   const int b = blockIdx.y;
@@ -511,7 +518,7 @@ __global__ void __launch_bounds__(kThreads) pointwise_kernel(const float* __rest
 template <class Op, bool BWD>
 int launch_pointwise(const float* in, const float* gout, float* out, Op op, float* partial, int B, int HW,
                      cudaStream_t st) {
-  LaunchShape s = shape_for(HW);
+  LaunchShape s = shape_for(HW, B, BWD);
   dim3 grid(s.nblk, B);
   if (HW % 4 == 0) pointwise_kernel<Op, 4, BWD><<<grid, kThreads, 0, st>>>(in, gout, out, op, partial, HW, s.chunk);
   else pointwise_kernel<Op, 1, BWD><<<grid, kThreads, 0, st>>>(in, gout, out, op, partial, HW, s.chunk);
@@ -1241,7 +1248,7 @@ int rgie_filter_bwd(int kind, const float* in, const float* gout, float* gin, co
   cudaStream_t st = (cudaStream_t)stream;
   const int HW = H * W;
   RGIE_CHECK(B > 0 && H > 0 && W > 0 && ws != nullptr, "rgie_filter_bwd: bad arguments");
-  LaunchShape s = shape_for(HW);
+  LaunchShape s = shape_for(HW, B, true);
   float* partial = ws;
   switch (kind) {
     case RGIE_F_EXPOSURE: {
