@@ -1,6 +1,7 @@
 """Drop-in for the hot-path functions of src/optimize_image_param.py: `init_params` (:121-209),
-`initialize_parametric` (:212-234), `objective_function_parametric` (:237-259), `get_params_from_vector` (:262-292).
-Script glue (main, output_transform, file I/O, CLIP / discriminator terms) is out of scope.
+`initialize_parametric` (:212-234), `objective_function_parametric` (:237-259), `get_params_from_vector` (:262-292),
+and the caller right after the loop, `output_transform` (:295-312: evaluation + full-resolution re-render of the edit,
+SURVEY.md 8f rank 4).  Script glue (main, dataset loop, JPEG save, CLIP / discriminator terms) is out of scope (section 8).
 """
 from __future__ import annotations
 
@@ -8,6 +9,21 @@ import torch
 
 from . import _lib
 from .baselines.image_transformations.image_transformations import apply_params
+
+STATS = {}                 # :21   per-adaptation evaluation statistics filled by output_transform
+OUTPUT_TRANSFORM = None    # :22   set by configure_output(); the reference builds it in main() (:78-82)
+DATA_DIR = None            # the reference takes it from paths.py
+
+
+def configure_output(output_size=1024, data_dir=None):
+    """The part of the reference's main() (:78-82) that output_transform depends on: Resize + CenterCrop + ToTensor."""
+    global OUTPUT_TRANSFORM, DATA_DIR
+    from torchvision import transforms
+    OUTPUT_TRANSFORM = transforms.Compose([transforms.Resize(output_size), transforms.CenterCrop(output_size),
+                                           transforms.ToTensor()])
+    if data_dir is not None:
+        DATA_DIR = data_dir
+
 
 DEFAULT_TRANS = ['exposure', 'saturation', 'tone', 'color', 'contrast', 'sharp', 'blur', 'scale']
 
@@ -86,3 +102,29 @@ def objective_function_parametric(x_opt, image, params, clf, weight_clf, weight_
         raise _lib.RgieError("the CLIP reconstruction term (optimize_image.py:152-183) is out of scope here "
                              "(SURVEY.md 8f rank 3): run with weight_recon=0")
     return loss
+
+
+def output_transform(image, x_opt, obj_params, eval_params, adaptation, image_path):      # :295-312
+    """Evaluate the optimised parameters on the working-size image, then re-render the edit on the full-resolution file
+    (every filter is resolution-independent; `scale` centres are rescaled by get_params_from_vector's input_size)."""
+    from .baselines.run_img_trans import compare_emotions
+    from .baselines.utils import check_init_stats_adapt
+    params_x = get_params_from_vector(x_opt, 1, obj_params["params"], image.size(2))
+    outputs = apply_params(image, params_x)
+    if "scale" in params_x:
+        print(f"optimized scale: {params_x['scale'].tolist()}")
+
+    check_init_stats_adapt(STATS, adaptation)
+    compare_emotions(obj_params["clf"], image, outputs[-1], eval_params["emotion_type_labels"], STATS[adaptation])
+
+    if OUTPUT_TRANSFORM is None:
+        raise _lib.RgieError("output_transform: call configure_output(output_size, data_dir) first (reference main() :78-82)")
+    import PIL.Image
+    path = f"{DATA_DIR}/images/{image_path[0]}"
+    print(path)
+    input_image = PIL.Image.open(path)
+    if input_image.mode != "RGB":
+        input_image = input_image.convert('RGB')
+    input_image_tensor = OUTPUT_TRANSFORM(input_image).unsqueeze(0).to(image.device)
+    output_image_tensor = apply_params(input_image_tensor, params_x)[-1]
+    return input_image_tensor, output_image_tensor
