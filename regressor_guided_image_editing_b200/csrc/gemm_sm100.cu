@@ -127,6 +127,21 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {   // arrives on
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                "h"((uint16_t)3) : "memory");
 }
+// ---- A operand from tensor memory (back-to-back GEMM): D[tmem] (+)= A[tmem] * B[smem]; the A fragment of one K = 16 step is
+// 128 lanes x 8 columns of packed bf16 pairs (lane = row, column c holds k = 2c, 2c + 1)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -1093,6 +1108,311 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 }
 
 // ===============================================================================================================
+// Back-to-back GEMM: a 256-wide stage-1 tile (1x1 expansion + residual / second operand + ReLU / masks, exactly the lean
+// kernel's work) is ALSO the complete K = 256 operand row block of the next layer's 1x1 reduction (256 -> 64), so the
+// second GEMM runs on the tile while it is still on chip and the next layer never re-reads the 256-channel tensor from HBM:
+//   stage 1: acc1[128 x 256] = A * W1^T (+ A2 * W1b^T)      smem operands, TMEM columns [0, 256)
+//            epilogue 1 (16 warps): bias / residual / ReLU / masks -> bf16 -> global D  AND  tcgen05.st into TMEM columns
+//            [256, 384) as the packed bf16 A operand of stage 2
+//   stage 2: acc2[128 x 64] = that operand (TMEM) * W2^T     W2 (64 x 256, 32 KB) resident in smem, TMEM columns 384 + 64 * buf
+//            epilogue 2: bias2 / ReLU / bit mask -> bf16 -> global D2 (+ sign bits)
+// Barriers: full/empty ring as usual; acc1_full (commit); e1_done (16 warps: acc1 drained AND the stage-2 operand written);
+// acc2_full[2] (commit).  The MMA thread issues, per tile t: [wait e1_done(t-1); MMA2(t-1)]; MMA1(t) -- and the epilogue warps
+// run epilogue1(t), then epilogue2(t-1), so the second GEMM's latency hides behind the next tile's first epilogue.
+// ===============================================================================================================
+struct B2bParams {
+  const float* bias2;
+  void* D2; int ldd2;
+  int relu2;
+  const uint32_t* mask_bits2; int ld_mb2;
+  uint32_t* D2_bits; int ld_db2;
+};
+constexpr int B2B_N2 = 64;
+constexpr int B2B_STAGES = 3;
+struct SmemB2b {
+  static constexpr int B_STAGE_BYTES = 256 * BK * 2;
+  static constexpr int A_OFF = 0;
+  static constexpr int B_OFF = B2B_STAGES * A_STAGE_BYTES;
+  static constexpr int W2_OFF = B_OFF + B2B_STAGES * B_STAGE_BYTES;          // 4 k-blocks of [64 rows x 128 B]
+  static constexpr int W2_BYTES = B2B_N2 * 256 * 2;
+  static constexpr int BAR_OFF = W2_OFF + W2_BYTES;                          // full[S], empty[S], acc1_full, e1_done, acc2_full[2], w2full
+  static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * B2B_STAGES + 6) * 8;
+  static constexpr int BIAS_OFF = (TMEM_PTR_OFF + 16 + 15) & ~15;
+  static constexpr int BIAS2_OFF = BIAS_OFF + 256 * 4;
+  static constexpr int TOTAL = BIAS2_OFF + B2B_N2 * 4;
+  static constexpr int DYN_BYTES = TOTAL + 1024;
+  static_assert(DYN_BYTES <= 232448, "shared memory plan exceeds 227 KB");
+};
+
+__global__ void __launch_bounds__(640, 1)
+gemm_b2b_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmW2, const GemmDesc d,
+                const B2bParams q2, const int num_tiles) {
+  using L = SmemB2b;
+  constexpr int BN = 256, N2 = B2B_N2, STAGES = B2B_STAGES;
+  constexpr uint32_t A2_COL = 256, ACC2_COL = 384;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_base + L::BAR_OFF;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t acc1_full = bar_base + 8u * (2 * STAGES);
+  const uint32_t e1_done = bar_base + 8u * (2 * STAGES + 1);
+  auto acc2_full = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+  const uint32_t w2full = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_PTR_OFF);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kb_per_tap = d.Cin / BK;
+  const int num_kb = d.ntaps * kb_per_tap;
+  const int num_kb2 = d.A2 != nullptr ? d.Cin2 / BK : 0;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmW2) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(acc1_full, 1);
+    mbar_init(e1_done, 16);
+    mbar_init(acc2_full(0), 1);
+    mbar_init(acc2_full(1), 1);
+    mbar_init(w2full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_base + L::TMEM_PTR_OFF),
+                 "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {
+    float* sb = reinterpret_cast<float*>(smem + L::BIAS_OFF);
+    for (int i = threadIdx.x; i < 256; i += 640) sb[i] = d.bias != nullptr ? d.bias[i] : 0.f;
+    float* sb2 = reinterpret_cast<float*>(smem + L::BIAS2_OFF);
+    for (int i = threadIdx.x; i < N2; i += 640) sb2[i] = q2.bias2 != nullptr ? q2.bias2[i] : 0.f;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp >= 4) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    // ===================== epilogue warps: TMEM lane quarter (warp & 3) x 64-column part =====================
+    constexpr int CH = 16, CPW = 4;
+    const int qd = warp & 3;
+    const int part = (warp - 4) >> 2;
+    const int row = qd * 32 + lane;
+    const int col0 = part * 64;
+    const float* sbias = reinterpret_cast<const float*>(smem + L::BIAS_OFF);
+    const float* sbias2 = reinterpret_cast<const float*>(smem + L::BIAS2_OFF);
+    const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(d.res);
+    const uint32_t* mbits = d.mask_bits;
+    const long res_lim = d.res_rows < d.m_end ? d.res_rows : d.m_end;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
+    long dest_prev = -1;
+
+    auto stage2 = [&](int it_prev, long dest) {      // epilogue 2 of the tile handled one iteration ago
+      const int b = it_prev & 1;
+      mbar_wait(acc2_full(b), (uint32_t)((it_prev >> 1) & 1));
+      tcgen05_fence_after();
+      uint32_t r[CH];
+      tmem_ld<CH>(lane_addr + ACC2_COL + (uint32_t)(b * N2 + part * CH), r);
+      tmem_ld_wait();
+      if (dest >= 0) {
+        const int n0 = part * CH;
+        float v[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]) + sbias2[n0 + j];
+        uint32_t wout = 0u;
+        if (q2.relu2) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
+#pragma unroll
+          for (int j = CH - 1; j >= 0; --j) wout = push_positive_bit(wout, v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) wout |= (v[j] > 0.f ? 1u : 0u) << j;
+        }
+        if (q2.mask_bits2 != nullptr) {
+          const uint32_t w = (__ldg(q2.mask_bits2 + bits_index(dest, n0 / 32, q2.ld_mb2)) >> (16 * (part & 1))) & 0xFFFFu;
+          wout &= w;
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] = keep_if_bit(v[j], w, j);
+        }
+        uint32_t pk[CH / 2];
+#pragma unroll
+        for (int j = 0; j < CH / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+        stg256(reinterpret_cast<__nv_bfloat16*>(q2.D2) + dest * q2.ldd2 + n0, pk);
+        if (q2.D2_bits != nullptr)
+          reinterpret_cast<uint16_t*>(q2.D2_bits + bits_index(dest, n0 / 32, q2.ld_db2))[part & 1] = (uint16_t)wout;
+      }
+    };
+
+    // residual row and mask words of the NEXT tile are fetched while epilogue 2 of the previous one runs
+    uint32_t rbuf[CPW][CH / 2];
+    uint32_t bits_nxt0 = 0u, bits_nxt1 = 0u;
+    auto prefetch = [&](int tile) {
+      bits_nxt0 = bits_nxt1 = 0u;
+      if (tile >= num_tiles) return;
+      const long m = d.m_begin + (long)tile * BM + row;
+      if (res != nullptr && m < res_lim) {
+#pragma unroll
+        for (int ci = 0; ci < CPW; ++ci) ldg256(res + m * d.ld_res + col0 + ci * CH, rbuf[ci]);
+      }
+      if (mbits != nullptr && m < d.m_end) {
+        bits_nxt0 = __ldg(mbits + bits_index(m, col0 / 32, d.ld_mb));
+        bits_nxt1 = __ldg(mbits + bits_index(m, col0 / 32 + 1, d.ld_mb));
+      }
+    };
+    prefetch(blockIdx.x);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const long m = d.m_begin + (long)tile * BM + row;
+      long dest = -1;
+      if (m < d.m_end) dest = map_row(d.src, d.dst_kind, d.dst, m);
+      const bool live = dest >= 0;
+      const bool use_res = res != nullptr && m < res_lim;
+      const uint32_t bits_cur0 = bits_nxt0, bits_cur1 = bits_nxt1;
+      uint32_t bits_out0 = 0u, bits_out1 = 0u;
+      mbar_wait(acc1_full, (uint32_t)(it & 1));
+      tcgen05_fence_after();
+#pragma unroll
+      for (int ci = 0; ci < CPW; ++ci) {
+        uint32_t r[CH];
+        tmem_ld<CH>(lane_addr + (uint32_t)(col0 + ci * CH), r);
+        tmem_ld_wait();
+        const int n0 = col0 + ci * CH;
+        float v[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]) + sbias[n0 + j];
+        if (use_res) {
+#pragma unroll
+          for (int j = 0; j < CH / 2; ++j) { v[2 * j] += bf16_lo(rbuf[ci][j]); v[2 * j + 1] += bf16_hi(rbuf[ci][j]); }
+        }
+        uint32_t wout = 0u;
+        if (d.relu) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
+#pragma unroll
+          for (int j = CH - 1; j >= 0; --j) wout = push_positive_bit(wout, v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) wout |= (v[j] > 0.f ? 1u : 0u) << j;
+        }
+        if (mbits != nullptr) {
+          const uint32_t w = ((ci < 2 ? bits_cur0 : bits_cur1) >> (16 * (ci & 1))) & 0xFFFFu;
+          wout &= w;
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] = keep_if_bit(v[j], w, j);
+        }
+        if (ci < 2) bits_out0 |= wout << (16 * (ci & 1)); else bits_out1 |= wout << (16 * (ci & 1));
+        uint32_t pk[CH / 2];
+#pragma unroll
+        for (int j = 0; j < CH / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+        tmem_st8(lane_addr + A2_COL + (uint32_t)(n0 / 2), pk);          // stage-2 operand: the ROUNDED values the next layer reads
+        if (live) stg256(reinterpret_cast<__nv_bfloat16*>(d.D) + dest * d.ldd + n0, pk);
+      }
+      if (live && d.D_bits != nullptr) {
+        d.D_bits[bits_index(dest, col0 / 32, d.ld_db)] = bits_out0;
+        d.D_bits[bits_index(dest, col0 / 32 + 1, d.ld_db)] = bits_out1;
+      }
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(e1_done);
+      prefetch(tile + gridDim.x);
+      if (it > 0) stage2(it - 1, dest_prev);
+      dest_prev = dest;
+    }
+    if (it > 0) stage2(it - 1, dest_prev);
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        mbar_expect_tx(w2full, L::W2_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem_base + L::W2_OFF + kb * (N2 * 128), &tmW2, kb * BK, 0, w2full);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          const long m0 = d.m_begin + (long)tile * BM;
+          int tap = 0, cb = 0;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            mbar_expect_tx(full_bar(stage), A_STAGE_BYTES + L::B_STAGE_BYTES);
+            tma_load_2d(smem_base + L::A_OFF + stage * A_STAGE_BYTES, &tmA, cb * BK, (int)(m0 + d.row_off[tap]), full_bar(stage));
+            tma_load_2d(smem_base + L::B_OFF + stage * L::B_STAGE_BYTES, &tmB, kb * BK, 0, full_bar(stage));
+            if (++cb == kb_per_tap) { cb = 0; ++tap; }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (m0 < d.a2_rows) {
+            for (int kb = 0; kb < num_kb2; ++kb) {
+              mbar_wait(empty_bar(stage), phase ^ 1);
+              mbar_expect_tx(full_bar(stage), A_STAGE_BYTES + L::B_STAGE_BYTES);
+              tma_load_2d(smem_base + L::A_OFF + stage * A_STAGE_BYTES, &tmA2, kb * BK, (int)m0, full_bar(stage));
+              tma_load_2d(smem_base + L::B_OFF + stage * L::B_STAGE_BYTES, &tmB, (num_kb + kb) * BK, 0, full_bar(stage));
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer (one thread) =====================
+      if (lane == 0) {
+        constexpr uint32_t idesc1 = make_idesc(BM, BN);
+        constexpr uint32_t idesc2 = make_idesc(BM, N2);
+        auto issue_stage2 = [&](int it_prev) {
+          mbar_wait(e1_done, (uint32_t)(it_prev & 1));
+          tcgen05_fence_after();
+          const uint32_t tmem_d2 = tmem_base + ACC2_COL + (uint32_t)((it_prev & 1) * N2);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const uint64_t bdesc = make_smem_desc(smem_base + L::W2_OFF + (k >> 2) * (N2 * 128)) + (uint64_t)(2 * (k & 3));
+            umma_bf16_ts(tmem_d2, tmem_base + A2_COL + (uint32_t)(8 * k), bdesc, idesc2, k != 0 ? 1u : 0u);
+          }
+          umma_commit(acc2_full(it_prev & 1));
+        };
+        mbar_wait(w2full, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+          const long m0 = d.m_begin + (long)tile * BM;
+          const int kb_total = num_kb + (m0 < d.a2_rows ? num_kb2 : 0);
+          if (it > 0) issue_stage2(it - 1);          // also the point where acc1 is free again
+          for (int kb = 0; kb < kb_total; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tcgen05_fence_after();
+            const uint64_t adesc = make_smem_desc(smem_base + L::A_OFF + stage * A_STAGE_BYTES);
+            const uint64_t bdesc = make_smem_desc(smem_base + L::B_OFF + stage * L::B_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc1, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(empty_bar(stage));
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(acc1_full);
+        }
+        if (it > 0) issue_stage2(it - 1);
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ===============================================================================================================
 // Patch-tile variant for the small-channel multi-tap convolutions (Cin = 64, Cout <= 64: conv1 forward / input
 // gradient, the 3x3 convs of layer1).  With flat 128-row tiles every tap re-loads its own 16 KB operand tile, and these
 // layers run at the L2->SM bandwidth ceiling (~42 B/clk/SM) instead of the tensor or HBM roofline.  Here
@@ -1498,6 +1818,20 @@ int run_patch(const GemmPlanSm100& p, cudaStream_t st) {
   return 0;
 }
 
+int run_b2b(const GemmPlanSm100& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    RGIE_CUDA_OK(cudaFuncSetAttribute(gemm_b2b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemB2b::DYN_BYTES));
+    attr_set = true;
+  }
+  B2bParams q;
+  q.bias2 = p.d2.bias; q.D2 = p.d2.D; q.ldd2 = p.d2.ldd; q.relu2 = p.d2.relu;
+  q.mask_bits2 = p.d2.mask_bits; q.ld_mb2 = p.d2.ld_mb; q.D2_bits = p.d2.D_bits; q.ld_db2 = p.d2.ld_db;
+  gemm_b2b_kernel<<<p.grid, 640, SmemB2b::DYN_BYTES, st>>>(p.tmA, p.tmA2, p.tmB, p.tmW2, p.d, q, p.num_m_tiles);
+  RGIE_LAUNCH_OK();
+  return 0;
+}
+
 #ifndef RGIE_2CTA_STAGES
 #define RGIE_2CTA_STAGES 6
 #endif
@@ -1560,6 +1894,7 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
   p->bn = bn;
   p->patch = 0;
   p->special = 0;
+  p->b2b = 0;
   // ---- patch-tile variant: Cin = 64, one N tile, single-plane source whose rows are whole pixel lines, taps on a
   //      (dy, dx) grid of at most 4 x 4 with |dx| well below the pitch
   //      Measured on B200 (320 crops): 3x3 layer1 0.52 -> 0.41 ms, conv1 forward 1.08 -> 0.76 ms, conv1 input gradient
@@ -1678,13 +2013,50 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
 
 // Plan for conv_hshare_kernel.  d: the 16-tap input-gradient descriptor of the flat formulation (geometry, source,
 // destination); Wh: [48, 4 * 64] bf16, row j * 12 + q, column yi * 64 + co; taps (dy0 + yi, dx0 + j).
+// ---- back-to-back fusion: d1 = a 256-wide single-tap op whose output rows are its own rows (DST_SAME), d2 = the single-tap
+//      256 -> 64 op that reads exactly that output over the same rows
+bool gemm_b2b_eligible(const GemmDesc& d1, const GemmDesc& d2) {
+  auto same_geom = [](const Geom& a, const Geom& b) {
+    return a.planes == b.planes && a.n_img == b.n_img && a.H == b.H && a.W == b.W && a.pad_t == b.pad_t && a.pad_l == b.pad_l &&
+           a.P == b.P && a.S == b.S;
+  };
+  if (d1.Cout != 256 || d1.n_pad != 256 || d1.d_fp32 || d1.mask != nullptr || d1.ntaps != 1 || d1.row_off[0] != 0) return false;
+  if (d1.dst_kind != DST_SAME || d1.ldd != 256 || d1.Cin % BK != 0 || (d1.A2 != nullptr && d1.Cin2 % BK != 0)) return false;
+  if (d2.A != d1.D || d2.Cin != 256 || d2.ntaps != 1 || d2.row_off[0] != 0 || d2.A2 != nullptr || d2.res != nullptr) return false;
+  if (d2.mask != nullptr || d2.d_fp32 || d2.Cout != B2B_N2 || d2.n_pad != B2B_N2 || d2.dst_kind != DST_SAME) return false;
+  if (d2.m_begin != d1.m_begin || d2.m_end != d1.m_end || d2.ldd % 16 != 0) return false;
+  if (!same_geom(d1.src, d2.src) || d1.m_end <= d1.m_begin) return false;
+  if (d1.res != nullptr && d1.ld_res % 16 != 0) return false;
+  return true;
+}
+
+int build_gemm_b2b_sm100(const GemmDesc& d1, const GemmDesc& d2, GemmPlanSm100* p) {
+  RGIE_CHECK(gemm_b2b_eligible(d1, d2), "gemm_b2b: the two ops cannot be fused");
+  RGIE_CHECK(d1.a_rows < (1L << 31) && (d1.A2 == nullptr || d1.a2_rows < (1L << 31)), "gemm_b2b: too many rows for a TMA coordinate");
+  p->d = d1; p->d2 = d2;
+  p->bn = 256; p->patch = 0; p->special = 0; p->epi = 0; p->b2b = 1;
+  p->num_m_tiles = ceil_div(d1.m_end - d1.m_begin, (long)BM);
+  p->num_n_tiles = 1;
+  const int sms = gemm_sm100_num_sms();
+  p->grid = p->num_m_tiles < sms ? p->num_m_tiles : sms;
+  p->tmD = p->tmA; p->tmR = p->tmA;
+  int rc = make_map_2d(&p->tmA, d1.A, (uint64_t)d1.Cin, (uint64_t)d1.a_rows, BK, BM);
+  if (rc) return rc;
+  p->tmA2 = p->tmA;
+  if (d1.A2 != nullptr) rc = make_map_2d(&p->tmA2, d1.A2, (uint64_t)d1.Cin2, (uint64_t)d1.a2_rows, BK, BM);
+  if (rc) return rc;
+  rc = make_map_2d(&p->tmB, d1.Wt, (uint64_t)d1.ntaps * d1.Cin + (d1.A2 ? d1.Cin2 : 0), (uint64_t)d1.n_pad, BK, 256);
+  if (rc) return rc;
+  return make_map_2d(&p->tmW2, d2.Wt, 256, (uint64_t)B2B_N2, BK, (uint32_t)B2B_N2);
+}
+
 int build_conv_hshare_sm100(const GemmDesc& d, const void* Wh, int dy0, int dx0, GemmPlanSm100* p) {
   RGIE_CHECK(d.Cin == 64 && d.src.planes == 1 && d.d_fp32 && d.ldd >= HS_NQ && d.ldd % 4 == 0 && d.a_rows == d.src.rows(),
              "conv_hshare: unsupported descriptor");
   RGIE_CHECK(dx0 <= 0 && dx0 + HS_NJ - 1 >= 0 && d.src.pad_l + dx0 >= 0, "conv_hshare: tap range");
   p->d = d;
   p->bn = HS_N;
-  p->patch = 0; p->epi = 0;
+  p->patch = 0; p->epi = 0; p->b2b = 0;
   p->special = 1;
   const int P = d.src.P;
   const long lines = d.a_rows / P;
@@ -1724,6 +2096,7 @@ static int run_conv_hshare(const GemmPlanSm100& p, cudaStream_t st) {
 }
 
 int run_gemm_sm100(const GemmPlanSm100& p, cudaStream_t st) {
+  if (p.b2b == 1) return run_b2b(p, st);
   if (p.d.m_end <= p.d.m_begin) return 0;
   if (p.special == 1) return run_conv_hshare(p, st);
   if (p.patch == 1) return run_patch<64, 3, 3>(p, st);     // 3x3, 64 -> 64 (layer1)

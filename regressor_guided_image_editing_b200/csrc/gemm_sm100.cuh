@@ -17,10 +17,17 @@ struct GemmPlanSm100 {
   long hs_lines;
   int num_m_tiles, num_n_tiles;
   int grid;
+  // b2b == 1: gemm_b2b_kernel -- `d` (256-wide 1x1 stage) and the next layer's 1x1 reduction `d2` (256 -> 64) in one launch
+  int b2b;
+  GemmDesc d2;
+  CUtensorMap tmW2;
 };
 
 int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p);
 int build_conv_hshare_sm100(const GemmDesc& d, const void* Wh, int dy0, int dx0, GemmPlanSm100* p);
+// back-to-back fusion of two consecutive 1x1 ops (the second one reads exactly what the first one writes)
+bool gemm_b2b_eligible(const GemmDesc& d1, const GemmDesc& d2);
+int build_gemm_b2b_sm100(const GemmDesc& d1, const GemmDesc& d2, GemmPlanSm100* p);
 int run_gemm_sm100(const GemmPlanSm100& p, cudaStream_t st);
 int gemm_sm100_num_sms();
 

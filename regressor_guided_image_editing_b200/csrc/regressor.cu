@@ -390,6 +390,8 @@ struct Block {
 struct GemmOp {
   GemmDesc d;
   GemmPlanSm100 plan;
+  int fused_next = 0;   // this launch also computes the NEXT op of the list (gemm_b2b_kernel)
+  int absorbed = 0;     // computed by the previous launch: skipped at run time
 };
 
 struct RgieRegressor {
@@ -469,7 +471,29 @@ int add_op(RgieRegressor* R, std::vector<GemmOp>& ops, const GemmDesc& d) {
   return 0;
 }
 
+// Back-to-back fusion pass over an op list (bf16 tcgen05 mode): a 256-wide 1x1 op followed by the 256 -> 64 1x1 op that reads
+// its output (layer1: conv3 + skip -> next block's conv1; conv1 input gradient + skip gradient -> previous block's conv3
+// input gradient) becomes ONE launch, and the 256-channel tensor is not re-read from HBM (-8.2 GB of 127.9 GB per 320 crops).
+// MEASURED (B200, 320 crops): correct (tests/test_regressor_gpu.py passes with it), but SLOWER -- fused 1.59 / 1.69 / 1.87 ms
+// vs 0.70 + 0.41 / 0.98 + 0.40 / 0.89 + 0.39 ms for the two separate launches: TMEM has room for only ONE 256-column
+// stage-1 accumulator next to the stage-2 operand and accumulators, so the epilogue waits for every tile's MMAs (30 % of
+// its samples at the accumulator barrier, tensor pipe 7 % active).  OFF by default; RGIE_GEMM_B2B=1 enables it.
+int fuse_b2b(RgieRegressor* R, std::vector<GemmOp>& ops) {
+  static const int env_b2b = getenv("RGIE_GEMM_B2B") ? atoi(getenv("RGIE_GEMM_B2B")) : 0;
+  if (R->precision != RGIE_PREC_BF16 || !env_b2b) return 0;
+  for (size_t i = 0; i + 1 < ops.size(); ++i) {
+    if (ops[i].absorbed || ops[i].plan.special || ops[i].plan.patch) continue;
+    if (!gemm_b2b_eligible(ops[i].d, ops[i + 1].d)) continue;
+    if (int rc = build_gemm_b2b_sm100(ops[i].d, ops[i + 1].d, &ops[i].plan)) return rc;
+    ops[i].fused_next = 1;
+    ops[i + 1].absorbed = 1;
+    ++i;
+  }
+  return 0;
+}
+
 int run_op_raw(RgieRegressor* R, const GemmOp& op, cudaStream_t st) {
+  if (op.absorbed) return 0;
   if (R->precision == RGIE_PREC_BF16) return run_gemm_sm100(op.plan, st);
   return launch_gemm_simt(op.d, R->dtype, st);
 }
@@ -888,6 +912,8 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
       if (int rc = add_op(R, R->bwd_ops, d)) return rc;
     }
   }
+  if (int rc = fuse_b2b(R, R->fwd_ops)) return rc;
+  if (int rc = fuse_b2b(R, R->bwd_ops)) return rc;
   RGIE_CUDA_OK(cudaDeviceSynchronize());
   guard.ok = true;
   *out = R;
@@ -1015,6 +1041,14 @@ int rgie_regressor_get_profile(RgieRegressor* R, float* h_ms, double* h_flops, d
     if (!fwd && i == n - 1) useful = (147.0 * 64.0) / (16.0 * 16.0 * 64.0);
     h_flops[i] = op_flops(op.d, useful);
     h_bytes[i] = op_bytes(op.d, R->esz);
+    if (op.absorbed) { h_flops[i] = 0.0; h_bytes[i] = 0.0; h_ms[i] = 0.f; }
+    if (op.fused_next) {
+      // the fused launch does both ops; the second one's A operand never travels through HBM
+      const GemmOp& nx = fwd ? R->fwd_ops[i + 1] : R->bwd_ops[i + 1 - R->fwd_ops.size()];
+      const double valid_frac = (double)nx.d.src.H * nx.d.src.W / (double)nx.d.src.S;
+      h_flops[i] += op_flops(nx.d, 1.0);
+      h_bytes[i] += op_bytes(nx.d, R->esz) - (double)nx.d.a_rows * valid_frac * nx.d.Cin * R->esz;
+    }
     h_info[4 * i + 0] = fwd ? 0 : 1;
     h_info[4 * i + 1] = op.d.Cout;
     h_info[4 * i + 2] = op.d.ntaps * op.d.Cin + (op.d.A2 ? op.d.Cin2 : 0);

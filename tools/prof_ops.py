@@ -28,7 +28,7 @@ for r in range(a.reps + 1):
     if r == 0: continue
     best = list(ms) if best is None else [min(x, y) for x, y in zip(best, ms)]
 only = [int(x) for x in a.only.split(",")] if a.only else range(nops)
-tab = [{"i": i, "dir": "fwd" if info[4*i] == 0 else "bwd", "N": info[4*i+1], "K": info[4*i+2], "m_tiles": info[4*i+3], "ms_min": best[i], "tflops": fl[i]/best[i]/1e9, "alg_GBs": by[i]/best[i]/1e6} for i in range(nops)]
+tab = [{"i": i, "dir": "fwd" if info[4*i] == 0 else "bwd", "N": info[4*i+1], "K": info[4*i+2], "m_tiles": info[4*i+3], "ms_min": best[i], "tflops": fl[i]/max(best[i], 1e-9)/1e9, "alg_GBs": by[i]/max(best[i], 1e-9)/1e6} for i in range(nops)]
 for t in tab:
     if t["i"] in only: print(t)
 print("total_ms_min", sum(best), "TF/s", sum(fl)/sum(best)/1e9, "algorithmic GB", sum(by)/1e9, "GB/s", sum(by)/sum(best)/1e6)
