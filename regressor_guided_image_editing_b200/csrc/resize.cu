@@ -6,14 +6,20 @@
 // first source index, tap count, normalised fp32 weights; and the CSR transpose for backward) are built once on the
 // host with the same float arithmetic as ATen's `_compute_indices_weights_aa` and live in the handle.
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 #include "common.cuh"
 #include "rgie.h"
 
 namespace rgie {
 
+constexpr int kFuseRows = 8;      // output rows per block of the fused kernels
+constexpr int kMaxTapsReg = 8;
+
 struct AxisTable {
   int in_size = 0, out_size = 0, kmax = 0, tmax = 0;
+  int span = 0;             // max source rows needed by a group of kFuseRows consecutive outputs (fused kernel strip height)
+  int tspan = 0;            // max OUTPUT rows touched by a group of kFuseRows consecutive inputs (transpose)
   int* xmin = nullptr;      // [out]
   int* xsize = nullptr;     // [out]
   float* w = nullptr;       // [out, kmax]
@@ -53,6 +59,11 @@ static int build_axis(int in_size, int out_size, AxisTable* t) {
       tr[lo + j].push_back({i, w[(size_t)i * kmax + j]});
     }
   }
+  for (int o0 = 0; o0 < out_size; o0 += kFuseRows) {
+    const int o1 = (o0 + kFuseRows < out_size ? o0 + kFuseRows : out_size) - 1;
+    const int need = xmin[o1] + xsize[o1] - xmin[o0];
+    if (need > t->span) t->span = need;
+  }
   std::vector<int> ts(in_size + 1, 0), to;
   std::vector<float> tw;
   int tmax = 0;
@@ -63,6 +74,13 @@ static int build_axis(int in_size, int out_size, AxisTable* t) {
   }
   ts[in_size] = (int)to.size();
   t->tmax = tmax;
+  for (int s0 = 0; s0 < in_size; s0 += kFuseRows) {
+    const int s1 = s0 + kFuseRows < in_size ? s0 + kFuseRows : in_size;
+    if (ts[s1] > ts[s0]) {
+      const int need = to[ts[s1] - 1] - to[ts[s0]] + 1;
+      if (need > t->tspan) t->tspan = need;
+    }
+  }
   if (to.empty()) { to.push_back(0); tw.push_back(0.f); }
   RGIE_CUDA_OK(cudaMalloc(&t->xmin, sizeof(int) * out_size));
   RGIE_CUDA_OK(cudaMalloc(&t->xsize, sizeof(int) * out_size));
@@ -153,6 +171,103 @@ __global__ void __launch_bounds__(256) resample_bwd_kernel(const float* __restri
   }
 }
 
+// ---- fused separable passes: the intermediate [rows, out_w] strip lives in shared memory, so a forward resize moves
+// N_in + N_out bytes and nothing else.  Per-element arithmetic (tap order, fmaf chain, fp32 rounding of the intermediate)
+// is exactly that of the two-pass kernels above, so results are bit-identical.
+// Both kernels first stage the source rows they need in shared memory with coalesced 16-byte loads (every global element is
+// read once per block, all loads independent), then run the two separable passes out of shared memory.
+__device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__ src, int nrows, int width) {
+  const long total = (long)nrows * width;                 // rows are contiguous in global memory
+  if ((width & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (long i = threadIdx.x; i < total / 4; i += blockDim.x) d4[i] = s4[i];
+  } else {
+    for (long i = threadIdx.x; i < total; i += blockDim.x) dst[i] = src[i];
+  }
+}
+
+// forward: one block = kFuseRows output rows of one plane; needs input rows [ymin[o0], ymin[o1] + ysize[o1])
+__global__ void __launch_bounds__(256) resize_fused_fwd_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                              const int* __restrict__ xmin, const int* __restrict__ xsize,
+                                                              const float* __restrict__ xw, int xk,
+                                                              const int* __restrict__ ymin, const int* __restrict__ ysize,
+                                                              const float* __restrict__ yw, int yk, int in_h, int in_w,
+                                                              int out_h, int out_w, int blocks_per_plane, int max_rows) {
+  extern __shared__ __align__(16) float smem_f[];
+  float* rows = smem_f;                                  // [nrows, in_w]   source rows
+  float* strip = smem_f + (long)max_rows * in_w;         // [nrows, out_w]  after the horizontal pass
+  const int plane = blockIdx.x / blocks_per_plane;
+  const int o0 = (blockIdx.x - plane * blocks_per_plane) * kFuseRows;
+  const int o1 = min(o0 + kFuseRows, out_h) - 1;
+  const int y_lo = ymin[o0], nrows = ymin[o1] + ysize[o1] - y_lo;
+  stage_rows(rows, in + ((long)plane * in_h + y_lo) * in_w, nrows, in_w);
+  __syncthreads();
+  for (int xo = threadIdx.x; xo < out_w; xo += blockDim.x) {
+    const int lo = xmin[xo], n = xsize[xo];
+    float wk[kMaxTapsReg];
+#pragma unroll
+    for (int j = 0; j < kMaxTapsReg; ++j) wk[j] = j < n ? xw[(long)xo * xk + j] : 0.f;
+    for (int r = 0; r < nrows; ++r) {
+      const float* row = rows + r * in_w + lo;
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < kMaxTapsReg; ++j)
+        if (j < n) acc = fmaf(wk[j], row[j], acc);
+      strip[r * out_w + xo] = acc;
+    }
+  }
+  __syncthreads();
+  float* dst = out + ((long)plane * out_h + o0) * out_w;
+  for (int o = o0; o <= o1; ++o) {
+    const int lo = ymin[o] - y_lo, n = ysize[o];
+    const float* wk = yw + (long)o * yk;
+    for (int x = threadIdx.x; x < out_w; x += blockDim.x) {
+      float acc = 0.f;
+      for (int j = 0; j < n; ++j) acc = fmaf(wk[j], strip[(lo + j) * out_w + x], acc);
+      dst[(long)(o - o0) * out_w + x] = acc;
+    }
+  }
+}
+
+// backward: one block = kFuseRows rows of gin of one plane; needs gout rows [yo[ys[s0]], yo[ys[s0 + ns] - 1]]
+__global__ void __launch_bounds__(256) resize_fused_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin,
+                                                              const int* __restrict__ ys, const int* __restrict__ yo,
+                                                              const float* __restrict__ yw, const int* __restrict__ xs,
+                                                              const int* __restrict__ xo_tab, const float* __restrict__ xw,
+                                                              int in_h, int in_w, int out_h, int out_w, int blocks_per_plane,
+                                                              int max_rows) {
+  extern __shared__ __align__(16) float smem_f[];
+  float* rows = smem_f;                                  // [nrows, out_w]      gout rows
+  float* strip = smem_f + (long)max_rows * out_w;        // [kFuseRows, out_w]  after the vertical transpose
+  const int plane = blockIdx.x / blocks_per_plane;
+  const int s0 = (blockIdx.x - plane * blocks_per_plane) * kFuseRows;
+  const int ns = min(s0 + kFuseRows, in_h) - s0;
+  const int e_lo = ys[s0], e_hi = ys[s0 + ns];
+  const int r_lo = e_hi > e_lo ? yo[e_lo] : 0;
+  const int nrows = e_hi > e_lo ? yo[e_hi - 1] - r_lo + 1 : 0;
+  stage_rows(rows, gout + ((long)plane * out_h + r_lo) * out_w, nrows, out_w);
+  __syncthreads();
+  for (int r = 0; r < ns; ++r) {
+    const int e0 = ys[s0 + r], e1 = ys[s0 + r + 1];
+    for (int x = threadIdx.x; x < out_w; x += blockDim.x) {
+      float acc = 0.f;
+      for (int e = e0; e < e1; ++e) acc = fmaf(yw[e], rows[(yo[e] - r_lo) * out_w + x], acc);
+      strip[r * out_w + x] = acc;
+    }
+  }
+  __syncthreads();
+  float* dst = gin + ((long)plane * in_h + s0) * in_w;
+  for (int x = threadIdx.x; x < in_w; x += blockDim.x) {
+    const int e0 = xs[x], e1 = xs[x + 1];
+    for (int r = 0; r < ns; ++r) {
+      float acc = 0.f;
+      for (int e = e0; e < e1; ++e) acc = fmaf(xw[e], strip[r * out_w + xo_tab[e]], acc);
+      dst[(long)r * in_w + x] = acc;
+    }
+  }
+}
+
 }  // namespace rgie
 
 using namespace rgie;
@@ -160,6 +275,8 @@ using namespace rgie;
 struct RgieResize {
   AxisTable ax_w, ax_h;
   int in_h, in_w, out_h, out_w;
+  int fwd_rows = 0, bwd_rows = 0;   // source rows a block of the fused forward / backward kernel stages at most
+  bool fused = false;
 };
 
 extern "C" {
@@ -170,6 +287,19 @@ int rgie_resize_create(int in_h, int in_w, int out_h, int out_w, RgieResize** ou
   r->in_h = in_h; r->in_w = in_w; r->out_h = out_h; r->out_w = out_w;
   if (int rc = build_axis(in_w, out_w, &r->ax_w)) { delete r; return rc; }
   if (int rc = build_axis(in_h, out_h, &r->ax_h)) { delete r; return rc; }
+  {
+    // fused single-kernel path: the shared-memory strip must fit and the taps of one output column fit the register array
+    r->fwd_rows = r->ax_h.span;
+    r->bwd_rows = r->ax_h.tspan;
+    const size_t smem_f = (size_t)r->fwd_rows * (in_w + out_w) * sizeof(float);
+    const size_t smem_b = (size_t)(r->bwd_rows + kFuseRows) * out_w * sizeof(float);
+    static const bool env_off = getenv("RGIE_RESIZE_FUSED") && atoi(getenv("RGIE_RESIZE_FUSED")) == 0;
+    r->fused = !env_off && r->ax_w.kmax <= kMaxTapsReg && smem_f <= 100 * 1024 && smem_b <= 100 * 1024;
+    if (r->fused) {
+      RGIE_CUDA_OK(cudaFuncSetAttribute(resize_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      RGIE_CUDA_OK(cudaFuncSetAttribute(resize_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    }
+  }
   *out = r;
   return 0;
 }
@@ -184,6 +314,14 @@ void rgie_resize_destroy(RgieResize* r) {
 int rgie_resize_fwd(const RgieResize* r, const float* in, float* out, int planes, float* tmp, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   RGIE_CHECK(r && in && out && tmp && planes > 0, "rgie_resize_fwd: bad arguments");
+  if (r->fused) {
+    const int bpp = (r->out_h + kFuseRows - 1) / kFuseRows;
+    resize_fused_fwd_kernel<<<planes * bpp, 256, (size_t)r->fwd_rows * (r->in_w + r->out_w) * sizeof(float), st>>>(
+        in, out, r->ax_w.xmin, r->ax_w.xsize, r->ax_w.w, r->ax_w.kmax, r->ax_h.xmin, r->ax_h.xsize, r->ax_h.w, r->ax_h.kmax,
+        r->in_h, r->in_w, r->out_h, r->out_w, bpp, r->fwd_rows);
+    RGIE_LAUNCH_OK();
+    return 0;
+  }
   const long rows_in = (long)planes * r->in_h, rows_out = (long)planes * r->out_h;
   const int g_in = (int)((rows_in + kRowsPerBlock - 1) / kRowsPerBlock), g_out = (int)((rows_out + kRowsPerBlock - 1) / kRowsPerBlock);
   resample_fwd_kernel<1><<<g_in, 256, 0, st>>>(in, tmp, r->ax_w.xmin, r->ax_w.xsize, r->ax_w.w, r->ax_w.kmax, r->in_w, r->out_w,
@@ -199,6 +337,14 @@ int rgie_resize_bwd(const RgieResize* r, const float* gout, float* gin, int plan
   cudaStream_t st = (cudaStream_t)stream;
   RGIE_CHECK(r && gout && gin && tmp && planes > 0, "rgie_resize_bwd: bad arguments");
   // transpose of (vertical o horizontal) = horizontal^T o vertical^T ; tmp: [planes, in_h, out_w]
+  if (r->fused) {
+    const int bpp = (r->in_h + kFuseRows - 1) / kFuseRows;
+    resize_fused_bwd_kernel<<<planes * bpp, 256, (size_t)(r->bwd_rows + kFuseRows) * r->out_w * sizeof(float), st>>>(
+        gout, gin, r->ax_h.t_start, r->ax_h.t_out, r->ax_h.t_w, r->ax_w.t_start, r->ax_w.t_out, r->ax_w.t_w, r->in_h, r->in_w,
+        r->out_h, r->out_w, bpp, r->bwd_rows);
+    RGIE_LAUNCH_OK();
+    return 0;
+  }
   const long rows_in = (long)planes * r->in_h;
   const int g_in = (int)((rows_in + kRowsPerBlock - 1) / kRowsPerBlock);
   resample_bwd_kernel<0><<<g_in, 256, 0, st>>>(gout, tmp, r->ax_h.t_start, r->ax_h.t_out, r->ax_h.t_w, r->in_h, r->out_h, r->out_w,
