@@ -88,13 +88,25 @@ def _run_ex(backend, A, A2, a2_rows, W, offs, m_end, Cin, Cin2, Cout, bias, res,
     from regressor_guided_image_editing_b200 import _lib
     from regressor_guided_image_editing_b200._lib import ptr, stream_ptr, check
     lib = _lib.load()
-    D = torch.zeros(m_end, Cout, device=A.device, dtype=torch.bfloat16)
-    Db = torch.zeros((m_end + 31) // 32 * 32 * (Cout // 32), device=A.device, dtype=torch.int32) if want_bits else None
+    # guard bands around both outputs (compute-sanitizer is not available on the pool): a kernel that writes outside
+    # [0, m_end) x Cout or outside the blocked bit words would disturb the sentinel
+    G = 256
+    Dg = torch.full((m_end + 2 * G, Cout), -7.0, device=A.device, dtype=torch.bfloat16)
+    D = Dg[G:G + m_end]
+    D.zero_()
+    nbw = (m_end + 31) // 32 * 32 * (Cout // 32)
+    Dbg = torch.full((nbw + 2 * G,), 0x5A5A5A5A, device=A.device, dtype=torch.int32) if want_bits else None
+    Db = Dbg[G:G + nbw] if want_bits else None
+    if want_bits:
+        Db.zero_()
     offs_c = (C.c_long * len(offs))(*offs)
     check(lib.rgie_gemm_selftest_ex(backend, ptr(A), A.shape[0], Cin, ptr(A2), a2_rows, Cin2, ptr(W), W.shape[0], len(offs),
                                     offs_c, 0, m_end, Cout, ptr(bias), ptr(res), ptr(mask_bits), int(relu), ptr(D), 0,
                                     ptr(Db), stream_ptr(A.device)), "gemm_selftest_ex")
     torch.cuda.synchronize()
+    assert (Dg[:G] == -7.0).all() and (Dg[G + m_end:] == -7.0).all(), f"backend {backend}: write outside the output rows"
+    if want_bits:
+        assert (Dbg[:G] == 0x5A5A5A5A).all() and (Dbg[G + nbw:] == 0x5A5A5A5A).all(), f"backend {backend}: write outside the bit words"
     return D.float(), Db
 
 
