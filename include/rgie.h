@@ -109,7 +109,9 @@ int rgie_regressor_forward(RgieRegressor* r, const float* img, int B, int Hr, in
 int rgie_regressor_forward_ex(RgieRegressor* r, const float* img, int B, int Hr, int Wr, const int* offsets,
                               const int* step_ptr, long off_step_stride, int reps, int normalize, float* logits,
                               void* stream);
-/* dlogits: [B*reps, num_classes]; dimg: [B,3,Hr,Wr] gradient w.r.t. `img` of the preceding forward (overwritten) */
+/* dlogits: [B*reps, num_classes]; dimg: [B,3,Hr,Wr] gradient w.r.t. `img` of the preceding forward (overwritten).
+ * LIFETIME: backward re-reads `offsets` (and `step_ptr`; `img` in input-transform mode 2) of the preceding forward call
+ * through the pointers that call was given -- they must stay valid and unchanged until backward has run. */
 int rgie_regressor_backward(RgieRegressor* r, const float* dlogits, float* dimg, void* stream);
 /* `normalize` of the forward calls: 0 = crops as they are, 1 = (v - 0.5) / 0.5 (ReplicateAndCrop.py:26-28), 2 = the
  * handle's input transform: t = clamp(v * pre_scale + pre_shift, 0, 1); (t - mean_c) / std_c  -- the EmoNet ten-crop

@@ -189,6 +189,10 @@ class Regressor:
         check(_lib.load().rgie_regressor_forward_ex(self._h, ptr(img), B, Hr, Wr, ptr(offsets), ptr(step_ptr),
                                                     off_step_stride, reps, int(normalize), ptr(logits),
                                                     stream_ptr(img.device)), "rgie_regressor_forward")
+        # the handle keeps the RAW pointers of the image, the crop offsets and the step counter for backward()
+        # (crop_grad_gather_kernel reads them): hold the tensors so that a caller's temporaries cannot be recycled by the
+        # caching allocator between forward and backward
+        self._fwd_refs = (img, offsets, step_ptr)
         return logits
 
     def set_input_transform(self, pre_scale: float, pre_shift: float, mean, std) -> None:
