@@ -28,6 +28,31 @@ def test_resize_aa_fwd_bwd(shape):
     assert (gin.cpu() - gref).abs().max().item() <= 2e-5
 
 
+def test_fused_resize_is_bit_identical_to_the_two_pass_kernels(tmp_path):
+    """The single-kernel resize keeps the tap order and the fp32 rounding of the intermediate, so it must reproduce the two
+    separable kernels (RGIE_RESIZE_FUSED=0, read once per process -> child process) bit for bit, forward and transpose."""
+    import os, subprocess, sys
+    from regressor_guided_image_editing_b200 import ops
+    code = (
+        "import sys, torch\n"
+        "sys.path.insert(0, %r)\n"
+        "from regressor_guided_image_editing_b200 import ops\n"
+        "x = torch.rand(3, 3, 512, 512, generator=torch.Generator().manual_seed(11)).cuda()\n"
+        "g = torch.randn(3, 3, 480, 480, generator=torch.Generator().manual_seed(12)).cuda()\n"
+        "rs = ops.Resize(512, 512, 480, 480)\n"
+        "torch.save({'out': rs.fwd(x).cpu(), 'gin': rs.bwd(g).cpu()}, %r)\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(tmp_path / "two_pass.pt"))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, RGIE_RESIZE_FUSED="0"), capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    want = torch.load(tmp_path / "two_pass.pt")
+    x = torch.rand(3, 3, 512, 512, generator=torch.Generator().manual_seed(11)).to(DEV)
+    g = torch.randn(3, 3, 480, 480, generator=torch.Generator().manual_seed(12)).to(DEV)
+    rs = ops.Resize(512, 512, 480, 480)
+    assert torch.equal(rs.fwd(x).cpu(), want["out"])
+    assert torch.equal(rs.bwd(g).cpu(), want["gin"])
+
+
 def test_resize_output_size_rule():
     from regressor_guided_image_editing_b200 import ops
     for h, w in [(256, 256), (512, 512), (300, 400), (400, 300), (1024, 683)]:
