@@ -8,6 +8,7 @@
 // reduction (warp shuffle -> block partials in `ws` -> fixed-order finalize), no atomics.
 //
 // All kernels are HBM-bound elementwise/stencil passes: float4-vectorised over pixels when H*W % 4 == 0.
+#include <stdlib.h>
 #include "common.cuh"
 #include "rgie.h"
 
@@ -1134,6 +1135,136 @@ __global__ void affine_param_grad_kernel(const float* __restrict__ dtheta, const
   o[5] = dA[1][2] * bb;
 }
 
+// ---- shared-memory band versions of the sharpen kernels: one block = `R` image rows of one plane at full width.  The rows a
+// band needs (1 halo row forward; 2 halo rows of `in` and 1 of `gout` backward) are staged with coalesced 16-byte loads, every
+// 3x3 neighbourhood is then read from shared memory, and backward runs both of its passes (gradient of the clamped smoothing,
+// then its transposed 3x3) on the band, so the intermediate never goes to HBM: forward 2N bytes, backward 3N.
+// Arithmetic (fmaf order, clamp masks) is that of the kernels above.
+__device__ __forceinline__ void stage_band(float* dst, const float* __restrict__ src, long n_floats) {
+  if ((n_floats & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (long i = threadIdx.x; i < n_floats / 4; i += blockDim.x) d4[i] = s4[i];
+  } else {
+    for (long i = threadIdx.x; i < n_floats; i += blockDim.x) dst[i] = src[i];
+  }
+}
+// 3x3 smoothing of pixel (r, x) of a staged band (row r of `t`, width W); the caller guarantees an interior pixel
+__device__ __forceinline__ float sharp_conv_s(const float* t, int r, int x, int W) {
+  const float k1 = 1.0f / 13.0f, k5 = 5.0f / 13.0f;
+  const float* r0 = t + (r - 1) * W + x;
+  const float* r1 = r0 + W;
+  const float* r2 = r1 + W;
+  float s = 0.f;
+  s = fmaf(k1, r0[-1], s); s = fmaf(k1, r0[0], s); s = fmaf(k1, r0[1], s);
+  s = fmaf(k1, r1[-1], s); s = fmaf(k5, r1[0], s); s = fmaf(k1, r1[1], s);
+  s = fmaf(k1, r2[-1], s); s = fmaf(k1, r2[0], s); s = fmaf(k1, r2[1], s);
+  return s;
+}
+
+__global__ void __launch_bounds__(kThreads) sharp_fwd_band_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                                 const float* __restrict__ p, int stride, int H, int W, int R) {
+  extern __shared__ __align__(16) float band[];            // rows [ya, yb) of the plane
+  const int b = blockIdx.z, c = blockIdx.y;
+  const float f = p[(long)b * stride];
+  const int mode = sharp_mode(f);
+  const long off = ((long)b * 3 + c) * H * W;
+  const int y0 = blockIdx.x * R, y1 = min(y0 + R, H);
+  const int ya = max(y0 - 1, 0), yb = min(y1 + 1, H);
+  stage_band(band, in + off + (long)ya * W, (long)(yb - ya) * W);
+  __syncthreads();
+  for (int y = y0; y < y1; ++y)
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {      // row loops: no per-pixel division
+    const float xin = band[(y - ya) * W + x];
+    float result = xin;
+    if (y >= 1 && y < H - 1 && x >= 1 && x < W - 1) result = clamp01(sharp_conv_s(band, y - ya, x, W));
+    float o;
+    if (mode == 0) o = result;
+    else if (mode == 1) o = xin;
+    else {
+      o = __fadd_rn(result, __fmul_rn(xin - result, f));
+      if (mode == 3) o = clamp01(o);
+    }
+    out[off + (long)y * W + x] = clamp01(o);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) sharp_bwd_band_kernel(const float* __restrict__ in, const float* __restrict__ gout,
+                                                                 float* __restrict__ gin, const float* __restrict__ p,
+                                                                 int stride, float* __restrict__ partial, int H, int W, int R) {
+  extern __shared__ __align__(16) float smem_s[];
+  const int b = blockIdx.z, c = blockIdx.y;
+  const float f = p[(long)b * stride];
+  const int mode = sharp_mode(f);
+  const long off = ((long)b * 3 + c) * H * W;
+  const int y0 = blockIdx.x * R, y1 = min(y0 + R, H);
+  const int ga = max(y0 - 1, 0), gb = min(y1 + 1, H);      // rows whose smoothing gradient this band needs
+  const int ia = max(ga - 1, 0), ib = min(gb + 1, H);      // rows of `in` needed to recompute the smoothing there
+  float* s_in = smem_s;                                    // [(R + 4), W]
+  float* s_g = s_in + (R + 4) * W;                         // [(R + 2), W]  gout rows [ga, gb)
+  float* s_deg = s_g + (R + 2) * W;                        // [(R + 2), W]  d(clamped smoothing) rows [ga, gb)
+  float* s_gx = s_deg + (R + 2) * W;                       // [R, W]        direct d(in) term rows [y0, y1)
+  stage_band(s_in, in + off + (long)ia * W, (long)(ib - ia) * W);
+  stage_band(s_g, gout + off + (long)ga * W, (long)(gb - ga) * W);
+  __syncthreads();
+  float acc[1] = {0.f};
+  for (int y = ga; y < gb; ++y)
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    const int yr = y - ga;
+    const float xin = s_in[(y - ia) * W + x];
+    const bool interior = y >= 1 && y < H - 1 && x >= 1 && x < W - 1;
+    float conv = 0.f, result = xin;
+    if (interior) { conv = sharp_conv_s(s_in, y - ia, x, W); result = clamp01(conv); }
+    float g = s_g[yr * W + x];
+    float g_res = 0.f, g_x = 0.f;
+    const bool own = y >= y0 && y < y1;                    // rows of this band (the halo rows belong to the neighbours)
+    if (mode == 0) { g = in01(result) ? g : 0.f; g_res = g; }
+    else if (mode == 1) { g = in01(xin) ? g : 0.f; g_x = g; }
+    else {
+      const float o = __fadd_rn(result, __fmul_rn(xin - result, f));
+      g = in01(o) ? g : 0.f;
+      g_res = g - g * f;
+      g_x = g * f;
+      if (own) acc[0] += g * (xin - result);
+    }
+    if (interior) s_deg[yr * W + x] = in01(conv) ? g_res : 0.f;
+    else { s_deg[yr * W + x] = 0.f; g_x += g_res; }
+    if (own) s_gx[(y - y0) * W + x] = g_x;
+  }
+  __syncthreads();
+  const float k1 = 1.0f / 13.0f, k5 = 5.0f / 13.0f;
+  for (int y = y0; y < y1; ++y)
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    const int yr = y - y0;
+    float s = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= W) continue;
+        s = fmaf((dy == 0 && dx == 0) ? k5 : k1, s_deg[(yy - ga) * W + xx], s);
+      }
+    }
+    gin[off + (long)y * W + x] = s_gx[yr * W + x] + s;
+  }
+  block_reduce_store<1>(acc, partial + ((long)b * 3 + c) * gridDim.x + blockIdx.x);
+}
+// rows per band and shared-memory bytes of the band kernels (0 rows = fall back to the global-memory kernels)
+struct SharpBand { int R, nb; size_t smem_f, smem_b; };
+SharpBand sharp_band(int H, int W) {
+  SharpBand s;
+  s.R = ceil_div(H, 64) < 8 ? 8 : ceil_div(H, 64);          // at most 64 bands per plane (partials per image: 3 * 64)
+  s.nb = ceil_div(H, s.R);
+  s.smem_f = (size_t)(s.R + 2) * W * sizeof(float);
+  s.smem_b = (size_t)(4 * s.R + 8) * W * sizeof(float);
+  static const bool env_on = getenv("RGIE_SHARP_BAND") && atoi(getenv("RGIE_SHARP_BAND")) == 1;   // opt-in until measured
+  if (!env_on || s.smem_b > 160 * 1024) s.R = 0;
+  return s;
+}
+
 int plane_blocks(int HW) { int n = ceil_div(HW, kThreads * 4); return n > 64 ? 64 : (n < 1 ? 1 : n); }
 
 }  // namespace
@@ -1206,6 +1337,18 @@ int rgie_filter_fwd(int kind, const float* in, float* out, const float* p, int p
     }
     case RGIE_F_SHARP: {
       RGIE_CHECK(H >= 3 && W >= 3, "sharp: image too small");
+      const SharpBand sb = sharp_band(H, W);
+      if (sb.R > 0) {
+        static bool attr_set = false;
+        if (!attr_set) {
+          RGIE_CUDA_OK(cudaFuncSetAttribute(sharp_fwd_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+          RGIE_CUDA_OK(cudaFuncSetAttribute(sharp_bwd_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+          attr_set = true;
+        }
+        sharp_fwd_band_kernel<<<dim3(sb.nb, 3, B), kThreads, sb.smem_f, st>>>(in, out, p, p_stride, H, W, sb.R);
+        RGIE_LAUNCH_OK();
+        return 0;
+      }
       dim3 grid(plane_blocks(HW), 3, B);
       sharp_fwd_kernel<<<grid, kThreads, 0, st>>>(in, out, p, p_stride, H, W);
       RGIE_LAUNCH_OK();
@@ -1340,6 +1483,19 @@ int rgie_filter_bwd(int kind, const float* in, const float* gout, float* gin, co
     }
     case RGIE_F_SHARP: {
       RGIE_CHECK(H >= 3 && W >= 3, "sharp: image too small");
+      const SharpBand sb = sharp_band(H, W);
+      if (sb.R > 0) {
+        static bool attr_set = false;
+        if (!attr_set) {
+          RGIE_CUDA_OK(cudaFuncSetAttribute(sharp_fwd_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+          RGIE_CUDA_OK(cudaFuncSetAttribute(sharp_bwd_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+          attr_set = true;
+        }
+        sharp_bwd_band_kernel<<<dim3(sb.nb, 3, B), kThreads, sb.smem_b, st>>>(in, gout, gin, p, p_stride, partial, H, W, sb.R);
+        RGIE_LAUNCH_OK();
+        finalize_partials<<<B, 32, 0, st>>>(partial, 3 * sb.nb, 1, gp, gp_stride);
+        break;
+      }
       const int nb = plane_blocks(HW);
       float* gdeg = ws + (long)B * kMaxBlk * 24;
       dim3 grid(nb, 3, B);

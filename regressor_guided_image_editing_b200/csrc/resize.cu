@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) resample_bwd_kernel(const float* __restri
 // read once per block, all loads independent), then run the two separable passes out of shared memory.
 __device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__ src, int nrows, int width) {
   const long total = (long)nrows * width;                 // rows are contiguous in global memory
-  if ((width & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+  if ((width & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
     const float4* s4 = reinterpret_cast<const float4*>(src);
     float4* d4 = reinterpret_cast<float4*>(dst);
     for (long i = threadIdx.x; i < total / 4; i += blockDim.x) d4[i] = s4[i];
