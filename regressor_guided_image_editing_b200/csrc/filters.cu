@@ -1253,15 +1253,19 @@ __global__ void __launch_bounds__(kThreads) sharp_bwd_band_kernel(const float* _
   block_reduce_store<1>(acc, partial + ((long)b * 3 + c) * gridDim.x + blockIdx.x);
 }
 // rows per band and shared-memory bytes of the band kernels (0 rows = fall back to the global-memory kernels)
+// MEASURED (B200, 64 x 512^2): forward 0.156 -> 0.125 ms (default on); the fused backward is SLOWER than the two global-memory
+// passes (0.583 vs 0.529 ms: 80 KB of shared memory per block, three shared-memory passes of scalar 3x3 reads), so backward
+// keeps the two-pass kernels unless RGIE_SHARP_BAND=1.
 struct SharpBand { int R, nb; size_t smem_f, smem_b; };
-SharpBand sharp_band(int H, int W) {
+SharpBand sharp_band(int H, int W, bool backward) {
   SharpBand s;
   s.R = ceil_div(H, 64) < 8 ? 8 : ceil_div(H, 64);          // at most 64 bands per plane (partials per image: 3 * 64)
   s.nb = ceil_div(H, s.R);
   s.smem_f = (size_t)(s.R + 2) * W * sizeof(float);
   s.smem_b = (size_t)(4 * s.R + 8) * W * sizeof(float);
-  static const bool env_on = getenv("RGIE_SHARP_BAND") && atoi(getenv("RGIE_SHARP_BAND")) == 1;   // opt-in until measured
-  if (!env_on || s.smem_b > 160 * 1024) s.R = 0;
+  static const int env_band = getenv("RGIE_SHARP_BAND") ? atoi(getenv("RGIE_SHARP_BAND")) : -1;   // 0 off, 1 on for both
+  const bool on = env_band == 1 || (env_band != 0 && !backward);
+  if (!on || (backward ? s.smem_b : s.smem_f) > 160 * 1024) s.R = 0;
   return s;
 }
 
@@ -1337,7 +1341,7 @@ int rgie_filter_fwd(int kind, const float* in, float* out, const float* p, int p
     }
     case RGIE_F_SHARP: {
       RGIE_CHECK(H >= 3 && W >= 3, "sharp: image too small");
-      const SharpBand sb = sharp_band(H, W);
+      const SharpBand sb = sharp_band(H, W, false);
       if (sb.R > 0) {
         static bool attr_set = false;
         if (!attr_set) {
@@ -1483,7 +1487,7 @@ int rgie_filter_bwd(int kind, const float* in, const float* gout, float* gin, co
     }
     case RGIE_F_SHARP: {
       RGIE_CHECK(H >= 3 && W >= 3, "sharp: image too small");
-      const SharpBand sb = sharp_band(H, W);
+      const SharpBand sb = sharp_band(H, W, true);
       if (sb.R > 0) {
         static bool attr_set = false;
         if (!attr_set) {
