@@ -651,20 +651,20 @@ __device__ __forceinline__ void epilogue_lean_role(const GemmDesc& d, const floa
   const int t_first = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int t_stride = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int t_rank = TWO ? (int)cluster_ctarank() : 0;
-  static_assert(BN == 256, "lean epilogue: 4 parts of 64 columns");
-  constexpr int CH = 16, CPW = 4;
+  static_assert(BN == 256 || BN == 128, "lean epilogue: 4 parts of 64 (BN = 256) or 32 (BN = 128) columns");
+  constexpr int CH = 16, PW = BN / 4, CPW = PW / CH, NW = PW / 32;   // columns, chunks and bit words per part
   auto tfull_bar = [&](int a) { return tfull0 + 8u * a; };
   auto tempty_bar = [&](int a) { return tempty0 + 8u * a; };
   const int q = warp & 3;
   const int part = (warp - 4) >> 2;
   const int row = q * 32 + lane;
-  const int col0 = part * 64;
+  const int col0 = part * PW;
   const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(d.res);
   const uint32_t* mbits = d.mask_bits;
   const bool has_bias = d.bias != nullptr;
   const long res_lim = d.res_rows < d.m_end ? d.res_rows : d.m_end;
 
-  constexpr int NRB = RGIE_LEAN_NRB;               // residual: chunk ci lives in buffer ci % NRB, refilled NRB chunks ahead
+  constexpr int NRB = RGIE_LEAN_NRB < CPW ? RGIE_LEAN_NRB : CPW;   // residual: chunk ci lives in buffer ci % NRB, refilled NRB chunks ahead
   static_assert(NRB == 2 || NRB == 4, "NRB");
   uint32_t rbuf[NRB][CH / 2];
   uint32_t bits_nxt[2];
@@ -682,7 +682,7 @@ __device__ __forceinline__ void epilogue_lean_role(const GemmDesc& d, const floa
       if (mbits != nullptr && m < d.m_end) {
         const int w0 = (nt * BN + col0) / 32;
         bits_nxt[0] = __ldg(mbits + bits_index(m, w0, d.ld_mb));
-        bits_nxt[1] = __ldg(mbits + bits_index(m, w0 + 1, d.ld_mb));
+        if (NW == 2) bits_nxt[1] = __ldg(mbits + bits_index(m, w0 + 1, d.ld_mb));
       }
     }
   };
@@ -767,7 +767,7 @@ __device__ __forceinline__ void epilogue_lean_role(const GemmDesc& d, const floa
     if (live && d.D_bits != nullptr) {
       const int w0 = (nt * BN + col0) / 32;
       d.D_bits[bits_index(dest, w0, d.ld_db)] = bits_out0;
-      d.D_bits[bits_index(dest, w0 + 1, d.ld_db)] = bits_out1;
+      if (NW == 2) d.D_bits[bits_index(dest, w0 + 1, d.ld_db)] = bits_out1;
     }
     tcgen05_fence_before();
     __syncwarp();
@@ -958,9 +958,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 //   tfull[a]  (each CTA's own): multicast tcgen05.commit
 //   tempty[a] (leader's): 32 arrivals = 16 epilogue warps x 2 CTAs (the peer arrives remotely)
 // ===============================================================================================================
-template <int STAGES>
+template <int BN, int STAGES>
 struct Smem2 {
-  static constexpr int B_HALF_BYTES = 128 * BK * 2;
+  static constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_HALF_BYTES;
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
@@ -972,13 +972,13 @@ struct Smem2 {
   static_assert(DYN_BYTES <= 232448, "shared memory plan exceeds 227 KB");
 };
 
-template <int STAGES>
+template <int BN, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1)
 gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                        const __grid_constant__ CUtensorMap tmBh, const GemmDesc d, const int num_m_tiles,
                        const int num_n_tiles, const FastDiv fd_nt) {
-  using L = Smem2<STAGES>;
-  constexpr int BN = 256;
+  using L = Smem2<BN, STAGES>;
+  constexpr uint32_t TMEM_COLS = tmem_cols(BN);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_base = smem_u32(smem);
@@ -1014,7 +1014,7 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_base + L::TMEM_PTR_OFF),
-                 "r"(512u) : "memory");
+                 "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   if (d.bias != nullptr) {
@@ -1042,7 +1042,7 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const int tq = (int)fd_nt.div((uint32_t)pair), nt = pair - tq * num_n_tiles;
           const long m0_pair = d.m_begin + (long)(2 * tq) * BM;
           const long m0 = m0_pair + (long)rank * BM;
-          const int n0 = nt * BN + (int)rank * 128;
+          const int n0 = nt * BN + (int)rank * (BN / 2);
           int tap = 0, cb = 0;
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1);
@@ -1103,7 +1103,7 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   cluster_sync_all();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -1832,18 +1832,16 @@ int run_b2b(const GemmPlanSm100& p, cudaStream_t st) {
   return 0;
 }
 
-#ifndef RGIE_2CTA_STAGES
-#define RGIE_2CTA_STAGES 6
-#endif
+template <int BN, int STAGES>
 int run_2cta(const GemmPlanSm100& p, cudaStream_t st) {
-  using L = Smem2<RGIE_2CTA_STAGES>;
+  using L = Smem2<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    RGIE_CUDA_OK(cudaFuncSetAttribute(gemm_sm100_2cta_kernel<RGIE_2CTA_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RGIE_CUDA_OK(cudaFuncSetAttribute(gemm_sm100_2cta_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       L::DYN_BYTES));
     attr_set = true;
   }
-  gemm_sm100_2cta_kernel<RGIE_2CTA_STAGES><<<p.grid, 640, L::DYN_BYTES, st>>>(
+  gemm_sm100_2cta_kernel<BN, STAGES><<<p.grid, 640, L::DYN_BYTES, st>>>(
       p.tmA, p.tmA2, p.tmB, p.d, p.num_m_tiles, p.num_n_tiles, make_fastdiv((uint32_t)p.num_n_tiles));
   RGIE_LAUNCH_OK();
   return 0;
@@ -1975,7 +1973,11 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
   // epilogue-bound and LOSE 7-28 % (the leader's MMA waits for the epilogues of BOTH CTAs across the TPC), so they stay on
   // the single-CTA kernel.  RGIE_GEMM_2CTA = 0 switches pairs off, = K sets the contraction threshold.
   static const int env_2cta = getenv("RGIE_GEMM_2CTA") ? atoi(getenv("RGIE_GEMM_2CTA")) : 768;
-  if (p->epi == -16 && env_2cta > 0 && ktot >= env_2cta && p->num_m_tiles >= 2) {
+  // 128-wide tiles (the 3x3 convs of layer2, K = 1152): same kernel with 64 weight rows per CTA.  MEASURED: slower than the
+  // single-CTA 128-wide kernel (0.30 -> 0.35 ms per launch, 320 crops), so it is opt-in: RGIE_GEMM_2CTA128=1.
+  static const int env_2cta128 = getenv("RGIE_GEMM_2CTA128") ? atoi(getenv("RGIE_GEMM_2CTA128")) : 0;
+  const bool pair128 = bn == 128 && env_2cta128 && !d.d_fp32 && d.mask == nullptr && (env_epi == -1 || env_epi == -16);
+  if ((p->epi == -16 || pair128) && env_2cta > 0 && ktot >= env_2cta && p->num_m_tiles >= 2) {
     p->epi = -32;
     const long pairs = (long)((p->num_m_tiles + 1) / 2) * p->num_n_tiles;
     const long ctas = 2 * pairs < (long)(sms & ~1) ? 2 * pairs : (long)(sms & ~1);
@@ -2008,7 +2010,7 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
   else p->tmA2 = p->tmA;
   if (rc) return rc;
   return make_map_2d(&p->tmB, d.Wt, (uint64_t)d.ntaps * d.Cin + (d.A2 ? d.Cin2 : 0), (uint64_t)d.n_pad, BK,
-                     (uint32_t)(p->epi == -32 ? 128 : bn));   // CTA pairs: each CTA loads half of the 256 weight rows
+                     (uint32_t)(p->epi == -32 ? bn / 2 : bn));   // CTA pairs: each CTA loads half of the weight rows
 }
 
 // Plan for conv_hshare_kernel.  d: the 16-tap input-gradient descriptor of the flat formulation (geometry, source,
@@ -2109,11 +2111,11 @@ int run_gemm_sm100(const GemmPlanSm100& p, cudaStream_t st) {
         case 2: return run_impl<256, 3, 2, 8>(p, st);
         case 1: return run_impl<256, 3, 1, 8>(p, st);
         case -16: return run_impl<256, 4, 0, 16>(p, st);
-        case -32: return run_2cta(p, st);
+        case -32: return run_2cta<256, 6>(p, st);
         case -2: return run_impl<256, 3, 0, 8, true>(p, st);
         default: return run_impl<256, 4, 0, 8>(p, st);
       }
-    case 128: return run_impl<128, 6, 0, 8>(p, st);
+    case 128: return p.epi == -32 ? run_2cta<128, 8>(p, st) : run_impl<128, 6, 0, 8>(p, st);
     case 64: return run_impl<64, 8, 0, 8>(p, st);
     case 16: return run_impl<16, 8, 0, 8>(p, st);
   }

@@ -148,6 +148,9 @@ EX_CASES = [
     (5000, 128, 0, 0, 256, [-71, -70, -69, -1, 0, 1, 69, 70, 71], False, True, True),
     # CTA pairs, second operand ends inside a pair (tile 10 is below a2_rows, its partner tile 11 is not)
     (5000, 512, 512, 1400, 256, [0], False, True, False),
+    # CTA pairs with 128-wide tiles (64 weight rows per CTA): the 3x3 convs of layer2, and a residual + bits case
+    (8100, 128, 0, 0, 128, [-91, -90, -89, -1, 0, 1, 89, 90, 91], False, True, True),
+    (5000, 1024, 0, 0, 128, [0], True, False, True),
 ]
 
 
