@@ -236,8 +236,8 @@ struct SmemLayout {
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = STAGES * A_BYTES;
   static constexpr int OB_OFF = B_OFF + STAGES * B_STAGE_BYTES;                 // [half][2] output boxes
-  static constexpr int RB_OFF = OB_OFF + (EPI >= 1 ? 4 * EPI_BOX_BYTES : 0);    // [half][EPI] residual boxes
-  static constexpr int BAR_OFF = RB_OFF + (EPI >= 2 ? 2 * EPI * EPI_BOX_BYTES : 0);   // full[S], empty[S], tfull[2], tempty[2], rfull[8]
+  static constexpr int RB_OFF = OB_OFF + (EPI == 8 ? 4 * BM * 128 : (EPI >= 1 ? 4 * EPI_BOX_BYTES : 0));    // [half][EPI] residual boxes
+  static constexpr int BAR_OFF = RB_OFF + ((EPI >= 2 && EPI != 8) ? 2 * EPI * EPI_BOX_BYTES : 0);   // full[S], empty[S], tfull[2], tempty[2], rfull[8]
   static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * STAGES + 12) * 8;
   static constexpr int BIAS_OFF = TMEM_PTR_OFF + 16;                // whole bias vector (<= MAX_BIAS floats)
   static constexpr int TOTAL = BIAS_OFF + MAX_BIAS * 4;
@@ -643,11 +643,17 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
 #endif
 // TWO: CTA-pair kernel -- `num_tiles` counts PAIRS of M-adjacent tiles, cluster c walks pairs c, c + clusters, ...; the CTA
 // of rank r owns tile 2 * pair_m + r, and the accumulator-free arrive goes to the leader CTA's barrier.
-template <int BN, bool TWO = false>
+// STORE (BN = 256, DST_SAME): the output does not leave through 32-byte row-per-thread global stores (32 distinct lines =
+// 32 L1TEX wavefronts per warp instruction; ncu: LSU data pipe 73-82 % busy on the HBM-bound launches) but through a
+// 128 x 64 SWIZZLE_128B box per column part in shared memory (two st.shared.v4 per chunk, conflict-free) and ONE TMA store
+// per part and tile.  The four warps of a part meet at a named barrier before the store and before the box is reused.
+template <int BN, bool TWO = false, bool STORE = false>
 __device__ __forceinline__ void epilogue_lean_role(const GemmDesc& d, const float* sbias, const uint32_t tmem_base,
                                                    const uint32_t tfull0, const uint32_t tempty0, const int warp,
                                                    const int lane, const int num_tiles, const int num_n_tiles,
-                                                   const FastDiv fd_nt) {
+                                                   const FastDiv fd_nt, const CUtensorMap* tmD = nullptr,
+                                                   const uint32_t ob_smem = 0) {
+  static_assert(!STORE || (BN == 256 && !TWO), "the store variant is instantiated for single-CTA 256-wide tiles");
   const int t_first = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int t_stride = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int t_rank = TWO ? (int)cluster_ctarank() : 0;
@@ -696,6 +702,13 @@ __device__ __forceinline__ void epilogue_lean_role(const GemmDesc& d, const floa
 #pragma unroll
   for (int cj = 0; cj < NRB; ++cj) res_fetch(cj);
 
+  // STORE: this thread's row inside its part's box, the box leader, the named barrier of the part (ids 1..4)
+  const uint32_t box = ob_smem + (uint32_t)(part * (BM * 128));
+  const uint32_t box_row = box + (uint32_t)row * 128u;
+  const uint32_t swz = (uint32_t)(row & 7);
+  const bool box_leader = STORE && q == 0 && lane == 0;
+  const int bar_id = 1 + part;
+
   int it = 0;
   for (int tile = t_first; tile < num_tiles; tile += t_stride, ++it) {
     const int tq = (int)fd_nt.div((uint32_t)tile), nt = tile - tq * num_n_tiles;
@@ -713,6 +726,10 @@ __device__ __forceinline__ void epilogue_lean_role(const GemmDesc& d, const floa
     mbar_wait(tfull_bar(acc), acc_phase);
     tcgen05_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + col0);
+    if (STORE && it > 0) {
+      if (box_leader) bulk_wait_read0();            // the previous tile's TMA store has finished reading the box
+      named_bar_sync(bar_id, 128);
+    }
 #pragma unroll
     for (int ci = 0; ci < CPW; ++ci) {
       uint32_t r[CH];
@@ -757,11 +774,27 @@ __device__ __forceinline__ void epilogue_lean_role(const GemmDesc& d, const floa
           for (int j = 0; j < CH; ++j) v[j] = keep_if_bit(v[j], w, j);
         }
         if (ci < 2) bits_out0 |= wout << (16 * (ci & 1)); else bits_out1 |= wout << (16 * (ci & 1));
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(d.D) + dest * d.ldd + n0;
         uint32_t pk[CH / 2];
 #pragma unroll
         for (int j = 0; j < CH / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-        stg256(o, pk);
+        if (STORE) {
+          sts128(box_row + (((uint32_t)(2 * ci) ^ swz) << 4), pk);
+          sts128(box_row + (((uint32_t)(2 * ci + 1) ^ swz) << 4), pk + 4);
+        } else {
+          stg256(reinterpret_cast<__nv_bfloat16*>(d.D) + dest * d.ldd + n0, pk);
+        }
+      } else if (STORE) {
+        const uint32_t z[4] = {0u, 0u, 0u, 0u};       // pad rows are zero by construction and stay zero
+        sts128(box_row + (((uint32_t)(2 * ci) ^ swz) << 4), z);
+        sts128(box_row + (((uint32_t)(2 * ci + 1) ^ swz) << 4), z);
+      }
+    }
+    if (STORE) {
+      fence_async_smem();
+      named_bar_sync(bar_id, 128);
+      if (box_leader) {
+        tma_store_2d(tmD, box, nt * BN + col0, (int)(d.m_begin + (long)mt * BM));
+        bulk_commit();
       }
     }
     if (live && d.D_bits != nullptr) {
@@ -775,6 +808,7 @@ __device__ __forceinline__ void epilogue_lean_role(const GemmDesc& d, const floa
       if (TWO) mbar_arrive_cluster(mapa_rank(tempty_bar(acc), 0)); else mbar_arrive(tempty_bar(acc));
     }
   }
+  if (box_leader) bulk_wait0();
 }
 
 template <int BN, int STAGES, int EPI, int NEW, bool PAIR>
@@ -844,8 +878,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (NEW == 16 && warp >= 4) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     if constexpr (NEW == 16)
-      epilogue_lean_role<BN>(d, reinterpret_cast<const float*>(smem + L::BIAS_OFF), tmem_base, tfull_bar(0), tempty_bar(0), warp,
-                             lane, num_tiles, num_n_tiles, fd_nt);
+      epilogue_lean_role<BN, false, EPI == 8>(d, reinterpret_cast<const float*>(smem + L::BIAS_OFF), tmem_base, tfull_bar(0),
+                                              tempty_bar(0), warp, lane, num_tiles, num_n_tiles, fd_nt, &tmD,
+                                              smem_base + L::OB_OFF);
   } else {
   if (NEW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
   if (warp == 0) {
@@ -924,10 +959,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if constexpr (NEW == 16) {
-    static_assert(EPI == 0 && !PAIR, "16 epilogue warps: lean row-per-thread epilogue only");
+    static_assert((EPI == 0 || EPI == 8) && !PAIR, "16 epilogue warps: lean epilogue (row-per-thread or TMA-store) only");
     // warps 2, 3: idle members of the producer warpgroup
   } else if constexpr (EPI >= 1) {
-    static_assert(EPI == 0 || NEW == 8, "the store epilogue runs with 8 epilogue warps");
+    static_assert(EPI == 0 || EPI == 8 || NEW == 8, "the store epilogue runs with 8 epilogue warps");
     epilogue_store_role<BN, EPI>(d, &tmD, &tmR, reinterpret_cast<const float*>(smem + L::BIAS_OFF), smem_base + L::OB_OFF,
                                  smem_base + L::RB_OFF, rfull_bar(0), tmem_base, tfull_bar(0), tempty_bar(0), warp, lane,
                                  num_tiles, num_n_tiles, fd_nt);
@@ -1952,18 +1987,20 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
   p->grid = (int)(tiles < sms ? tiles : sms);
   if (p->grid < 1) p->grid = 1;
   // epilogue variant (measured per shape class on B200, profiles/README.md): 256-wide bf16 tiles use the 16-warp lean epilogue
-  // (setmaxnreg: producer warpgroup 32 registers, epilogue warpgroups 112; 0.81 -> 0.64 ms on the layer1 expansion, 3 % of the
-  // GEMM family); the TMA-store epilogue stays where the epilogue reads a residual AND a bit mask (conv1 input gradients of the
-  // identity blocks, a tie with the lean one); everything else takes the classic 8-warp row-per-thread epilogue.
-  // RGIE_GEMM_EPI = 0 (classic everywhere) / 1 / 2 / 4 (TMA-store variants) / -16 (lean wherever eligible) for A/B experiments.
+  // (setmaxnreg: producer warpgroup 32 registers, epilogue warpgroups 112); where the destination rows are the source rows
+  // (DST_SAME) and the launch is HBM-bound (contraction < 768) its output leaves through shared-memory boxes and TMA stores
+  // (-17: ncu showed the L1TEX LSU data pipe 73-82 % busy with the 32-byte row-per-thread stores; 0.61 -> 0.53, 0.89 -> 0.77,
+  // 0.50 -> 0.41, 0.29 -> 0.23 ms on the layer1-3 expansions).  Everything else takes the classic 8-warp row-per-thread epilogue.
+  // RGIE_GEMM_EPI = 0 (classic everywhere) / 1 / 2 / 4 (8-warp TMA-store variants) / -16 (lean without the TMA-store path) for
+  // A/B experiments.
   static const int env_epi = getenv("RGIE_GEMM_EPI") ? atoi(getenv("RGIE_GEMM_EPI")) : -1;
   const int ktot = d.ntaps * d.Cin + (d.A2 ? d.Cin2 : 0);
   const bool lean_ok = bn == 256 && !d.d_fp32 && d.mask == nullptr;
-  p->epi = (lean_ok && (env_epi == -16 || env_epi == -1)) ? -16 : 0;
-  if (bn == 256 && d.dst_kind == DST_SAME && !d.d_fp32 && d.mask == nullptr && env_epi != 0 && env_epi != -16) {
+  p->epi = (lean_ok && (env_epi == -16 || env_epi == -1 || env_epi == -17)) ? -16 : 0;
+  if ((env_epi == -17 || env_epi == -1) && lean_ok && d.dst_kind == DST_SAME && ktot < 768) p->epi = -17;
+  if (bn == 256 && d.dst_kind == DST_SAME && !d.d_fp32 && d.mask == nullptr && env_epi >= 1) {
     if (d.res != nullptr) {
       if (env_epi == 2 || env_epi == 4) p->epi = env_epi;
-      else if (env_epi < 0 && d.mask_bits != nullptr) p->epi = 2;
     } else if (env_epi >= 1 && ktot <= 768) {
       p->epi = 1;
     }
@@ -1995,6 +2032,10 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
   }
   p->tmD = p->tmA; p->tmR = p->tmA;
   int rc = 0;
+  if (p->epi == -17) {
+    rc = make_map_2d(&p->tmD, d.D, (uint64_t)d.ldd, (uint64_t)d.m_end, 64, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
   if (p->epi >= 1) {
     rc = make_map_2d(&p->tmD, d.D, (uint64_t)d.ldd, (uint64_t)d.m_end, 32, BM, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
@@ -2111,6 +2152,7 @@ int run_gemm_sm100(const GemmPlanSm100& p, cudaStream_t st) {
         case 2: return run_impl<256, 3, 2, 8>(p, st);
         case 1: return run_impl<256, 3, 1, 8>(p, st);
         case -16: return run_impl<256, 4, 0, 16>(p, st);
+        case -17: return run_impl<256, 3, 8, 16>(p, st);
         case -32: return run_2cta<256, 6>(p, st);
         case -2: return run_impl<256, 3, 0, 8, true>(p, st);
         default: return run_impl<256, 4, 0, 8>(p, st);
