@@ -3,7 +3,7 @@
 //   D[map(m), n] = epi( sum_t sum_c A[m + row_off[t], c] * Wt[n, t*Cin + c] + sum_c A2[m, c] * Wt[n, ntaps*Cin + c] )
 //                                                                                     bf16 x bf16 -> fp32 (TMEM)
 //
-// One persistent CTA per SM, 320 threads:
+// One persistent CTA per SM (gemm_sm100_kernel), 320 threads:
 //   warp 0      : TMA producer   (cp.async.bulk.tensor.2d, 128B swizzle, zero fill for out-of-range rows = conv padding)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (cta_group::1, M=128, N=BN, K=16 per instruction)
 //   warps 2..9  : epilogue       (tcgen05.ld 32x32b -> bias / residual / ReLU / ReLU-mask -> row-remapped 32B stores
@@ -11,6 +11,15 @@
 //                                 in registers (its HBM latency is never exposed); ReLU masks are 1 bit per element.
 // Pipelines: STAGES-deep smem ring (full/empty mbarriers) between TMA and MMA; 2 TMEM accumulator buffers
 // (tmem_full/tmem_empty) between MMA and epilogue so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Variants in this file (selection: build_gemm_sm100; measurements: profiles/README.md):
+//   * 640 threads, 16 epilogue warps (epilogue_lean_role, setmaxnreg register hand-over) for 256-wide bf16 tiles; output by
+//     32-byte global stores or, where destination rows = source rows, through shared-memory boxes + one TMA store per part;
+//   * gemm_sm100_2cta_kernel: CTA pairs (cta_group::2, M = 256 across a TPC) for contractions >= 768;
+//   * 8-warp TMA-store epilogues (EPI 1 / 2 / 4), tile pairing (PAIR), gemm_b2b_kernel: measured alternatives kept behind
+//     environment switches;
+//   * gemm_patch_kernel (16 x 8 pixel patch tiles, resident weights) for the 64-channel multi-tap convolutions and
+//     conv_hshare_kernel (horizontal taps as N) for the conv1 input gradient.
 #include <stdlib.h>
 #include "common.cuh"
 #ifndef RGIE_WAIT_HINT_NS
