@@ -28,66 +28,70 @@ def configure_output(output_size=1024, data_dir=None):
 DEFAULT_TRANS = ['exposure', 'saturation', 'tone', 'color', 'contrast', 'sharp', 'blur', 'scale']
 
 
-def init_params(trans_to_apply):                                                          # :121-209
-    x0, params = [], {}
+# Start value of every filter the reference can optimise (:121-209): a float for the scalar filters, a tensor for the others.
+# (A factory per entry: each call of init_params must hand out fresh tensors.)
+_START = {
+    "gamma": lambda: 1.0, "contrast": lambda: 1.0, "saturation": lambda: 1.0,
+    "sharp": lambda: 0.0, "wb": lambda: 0.0, "bright": lambda: 0.0, "exposure": lambda: 0.0, "bw": lambda: 0.0,
+    "hue": lambda: 0.0,
+    "blur": lambda: 1e-4,                                             # sigma ~ 0: the 25-tap Gaussian is a delta
+    "tone": lambda: torch.ones(1, 8, 1),                              # identity curve, shared by the colour channels
+    "color": lambda: torch.ones(3, 8, 1),                             # identity curve per colour channel
+    "affine": lambda: torch.eye(2, 3),
+    "scale": lambda: torch.tensor([[1.0, 1.0, 0.0, 0.0]]),            # (sx, sy, cx, cy)
+}
+
+
+def init_params(trans_to_apply):
+    """-> (dict filter -> start value, in application order; flat start vector x0 in the same order).  Unknown names are
+    skipped, as in the reference."""
+    params, flat = {}, []
     for name in trans_to_apply:
-        if name in ("gamma", "contrast", "saturation"):
-            params[name] = 1.0
-            x0.append(params[name])
-        elif name in ("sharp", "wb", "bright", "exposure", "bw", "hue"):
-            params[name] = 0.0
-            x0.append(params[name])
-        elif name == "blur":
-            params["blur"] = 1e-4
-            x0.append(params["blur"])
-        elif name == "tone":
-            params["tone"] = torch.ones(1, 8, 1)
-            x0.extend(params["tone"].view(-1).tolist())
-        elif name == "color":
-            params["color"] = torch.ones(3, 8, 1)
-            x0.extend(params["color"].view(-1).tolist())
-        elif name == "affine":
-            params["affine"] = torch.eye(2, 3)
-            x0.extend(params["affine"].view(-1).tolist())
-        elif name == "scale":
-            params["scale"] = torch.ones(1, 4)
-            params["scale"][0, 2:4] = 0.0
-            x0.extend(params["scale"].view(-1).tolist())
-    return params, torch.tensor(x0)
+        if name not in _START:
+            continue
+        value = _START[name]()
+        params[name] = value
+        flat.extend(value.reshape(-1).tolist() if torch.is_tensor(value) else [value])
+    return params, torch.tensor(flat)
 
 
-def initialize_parametric(image, obj_params):                                             # :212-234
+def initialize_parametric(image, obj_params):
+    """Objective arguments + start vector for the default eight-filter chain (:212-234)."""
     params_trans, x0 = init_params(DEFAULT_TRANS)
-    x0 = x0.to(image.device)
-    obj_params["image"] = image
-    obj_params["params"] = params_trans
-    return x0, obj_params
+    obj_params.update(image=image, params=params_trans)
+    return x0.to(image.device), obj_params
 
 
-def get_params_from_vector(x, batch_size, params, input_size=480):                        # :262-292
-    ix_start = 0
-    for name in params.keys():
-        len_param = 1 if isinstance(params[name], float) else len(params[name].view(-1))
-        if len_param == 1:
-            params[name] = x[ix_start]
-        else:
-            param_tensor = x[ix_start:ix_start + len_param]
-            if "tone" == name:
-                params["tone"] = param_tensor.view(batch_size, 1, 8, 1)
-            elif "color" == name:
-                params["color"] = param_tensor.view(batch_size, 3, 8, 1)
-            elif "affine" == name:
-                params["affine"] = param_tensor.view(2, 3)[None].repeat(batch_size, 1, 1)
-            elif "scale" == name:
-                if param_tensor.size(0) == 4:
-                    clamped_scale = param_tensor[0:2].clamp(min=1.0, max=torch.inf)
-                    clamped_center = param_tensor[2:].clamp(min=0.0, max=input_size)
-                    param_tensor = torch.cat((clamped_scale, clamped_center))
-                else:
-                    param_tensor = param_tensor.clamp(min=1.0, max=5.0)
-                params["scale"] = param_tensor.repeat(batch_size, 1)
-        ix_start += len_param
-    params["contrast"] = 0.0 if params["contrast"] < 0 else params["contrast"]
+def _param_len(template) -> int:
+    return 1 if isinstance(template, float) else template.numel()
+
+
+def get_params_from_vector(x, batch_size, params, input_size=480):
+    """Slice the flat vector `x` back into the filter dictionary `params` (in place, in its key order) with the reference's
+    shapes and clamps (:262-292): curves as [B, C, 8, 1]; affine as [B, 2, 3]; scale factors >= 1 (no black margin) and,
+    for the 4-value form, the centre inside [0, input_size]; a negative contrast becomes the python float 0.0.  The clamps
+    are torch ops on slices of `x`, so gradients flow exactly as in the reference."""
+    start = 0
+    for name in list(params.keys()):
+        n = _param_len(params[name])
+        piece = x[start] if n == 1 else x[start:start + n]
+        start += n
+        if n == 1:
+            params[name] = piece
+        elif name == "tone":
+            params[name] = piece.view(batch_size, 1, 8, 1)
+        elif name == "color":
+            params[name] = piece.view(batch_size, 3, 8, 1)
+        elif name == "affine":
+            params[name] = piece.view(2, 3)[None].repeat(batch_size, 1, 1)
+        elif name == "scale":
+            if piece.size(0) == 4:
+                piece = torch.cat((piece[0:2].clamp(min=1.0, max=torch.inf), piece[2:].clamp(min=0.0, max=input_size)))
+            else:
+                piece = piece.clamp(min=1.0, max=5.0)
+            params[name] = piece.repeat(batch_size, 1)
+    if params["contrast"] < 0:                      # 'contrast' is a required key, as in the reference
+        params["contrast"] = 0.0
     return params
 
 

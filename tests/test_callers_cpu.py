@@ -64,3 +64,86 @@ def test_helpers_equal_reference(capsys):
     want = capsys.readouterr().out
     U.print_stats(s_new)
     assert capsys.readouterr().out == want
+
+
+@needs_ref
+@pytest.mark.parametrize("is_minimized", [True, False])
+def test_loss_expressions_equal_reference(is_minimized):
+    """The [B, 2]-sized loss expressions of the ValenceArousalLoss mirror against the reference class (both built without
+    their regressor: the model is irrelevant to these methods), values and gradients bit for bit; same RNG consumption."""
+    import importlib
+    ref_harness.install()
+    RefLoss = importlib.import_module("baselines.losses.ValenceArousalLoss").ValenceArousalLoss
+    from regressor_guided_image_editing_b200.baselines.losses.ValenceArousalLoss import ValenceArousalLoss, _MODES
+
+    def bare(cls, mode):
+        obj = cls.__new__(cls)
+        torch.nn.Module.__init__(obj)
+        obj.device, obj.weight, obj.is_minimized = torch.device("cpu"), 0.15, is_minimized
+        cols, err = _MODES[mode]
+        obj.output_ixs, obj.get_error = list(cols), getattr(obj, err)
+        return obj
+
+    g = torch.Generator().manual_seed(3)
+    pred = torch.rand(5, 2, generator=g)
+    target = torch.rand(5, 2, generator=g)
+    for mode in ("va", "valence", "arousal"):
+        a, b = bare(RefLoss, mode), bare(ValenceArousalLoss, mode)
+        for tgt in (None, target):
+            pa = pred.clone().requires_grad_(True)
+            pb = pred.clone().requires_grad_(True)
+            sel = (lambda t: t) if mode == "va" else (lambda t: t[:, a.output_ixs[0]])
+            ea = a.get_error(sel(pa), None if tgt is None else sel(tgt))
+            eb = b.get_error(sel(pb), None if tgt is None else sel(tgt))
+            assert torch.equal(ea, eb), (mode, tgt is None)
+            la, lb = torch.mean(a.weight * ea), torch.mean(b.weight * eb)
+            ga, = torch.autograd.grad(la, pa)
+            gb, = torch.autograd.grad(lb, pb)
+            assert torch.equal(la, lb) and torch.equal(ga, gb)
+        torch.manual_seed(11)
+        ra = a.get_random_condition_tensor(7)
+        torch.manual_seed(11)
+        rb = b.get_random_condition_tensor(7)
+        assert torch.equal(ra, rb)
+
+
+@needs_ref
+def test_parameter_packing_equals_reference():
+    """init_params / initialize_parametric / get_params_from_vector of the mirror against the reference's own functions:
+    same dictionaries (keys, order, types, shapes, values), same flat start vector, same gradients through the clamps, and
+    the same behaviour on a second call (when the scalar entries have become 0-d tensors)."""
+    r = ref_harness.ref().optimize_image_param
+    from regressor_guided_image_editing_b200 import optimize_image_param as m
+    names = ['exposure', 'saturation', 'tone', 'color', 'contrast', 'sharp', 'blur', 'scale', 'gamma', 'wb', 'bright', 'bw',
+             'hue', 'affine', 'not_a_filter']
+    for lst in (m.DEFAULT_TRANS, names, list(reversed(names))):
+        pr, xr = r.init_params(lst)
+        pm, xm = m.init_params(lst)
+        assert list(pr) == list(pm) and torch.equal(xr, xm) and xr.dtype == xm.dtype
+        for k in pr:
+            assert type(pr[k]) is type(pm[k]), k
+            assert (pr[k] == pm[k]) if isinstance(pr[k], float) else torch.equal(pr[k], pm[k]), k
+        g = torch.Generator().manual_seed(len(lst))
+        x = xr + 0.3 * torch.randn(xr.shape, generator=g)
+        if "scale" in pr:
+            x[-1 if lst[-1] == "scale" else 0] += 0.0
+        for call in range(2):
+            xa = x.clone().requires_grad_(True)
+            xb = x.clone().requires_grad_(True)
+            qa = r.get_params_from_vector(xa, 1, pr, 480)
+            qb = m.get_params_from_vector(xb, 1, pm, 480)
+            assert list(qa) == list(qb)
+            tot_a = sum((v.float().sum() if torch.is_tensor(v) else torch.tensor(v)) for v in qa.values())
+            tot_b = sum((v.float().sum() if torch.is_tensor(v) else torch.tensor(v)) for v in qb.values())
+            for k in qa:
+                if torch.is_tensor(qa[k]):
+                    assert torch.is_tensor(qb[k]) and qa[k].shape == qb[k].shape and torch.equal(qa[k], qb[k]), (k, call)
+                else:
+                    assert qa[k] == qb[k], (k, call)
+            ga, = torch.autograd.grad(tot_a, xa)
+            gb, = torch.autograd.grad(tot_b, xb)
+            assert torch.equal(ga, gb), call
+    img = torch.rand(1, 3, 8, 8)
+    xa, oa = r.initialize_parametric(img, {"clf": None})
+    xb, ob = m.initialize_parametric(img, {"clf": None})
+    assert torch.equal(xa, xb) and list(oa) == list(ob) and oa["image"] is img and ob["image"] is img
