@@ -1,4 +1,5 @@
-"""Drop-in for src/baselines/models/utilities/MeanReplicatedCrops.py:18-27 (a view + mean over [B*reps, k] logits)."""
+"""Average the predictions of the replicated crops of each image -- drop-in for
+src/baselines/models/utilities/MeanReplicatedCrops.py:18-27: [B * reps, k] -> [B, k], crops of one image being consecutive rows."""
 import torch.nn as nn
 
 
@@ -8,5 +9,6 @@ class MeanReplicatedCrops(nn.Module):
         self.num_replications = num_replications
 
     def forward(self, x):
-        b, w = x.size()
-        return x.view(b // self.num_replications, self.num_replications, w).mean(dim=1)
+        rows, width = x.shape
+        per_image = x.view(rows // self.num_replications, self.num_replications, width)
+        return per_image.mean(dim=1)

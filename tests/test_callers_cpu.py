@@ -147,3 +147,27 @@ def test_parameter_packing_equals_reference():
     xa, oa = r.initialize_parametric(img, {"clf": None})
     xb, ob = m.initialize_parametric(img, {"clf": None})
     assert torch.equal(xa, xb) and list(oa) == list(ob) and oa["image"] is img and ob["image"] is img
+
+
+@needs_ref
+def test_score_and_crop_mean_equal_reference():
+    """guidance_scores.valence_arousal_score (value and gradient) and MeanReplicatedCrops against the reference's own."""
+    import importlib
+    ref_harness.install()
+    R = importlib.import_module("guidance_classifier.guidance_scores")
+    RM = importlib.import_module("baselines.models.utilities.MeanReplicatedCrops").MeanReplicatedCrops
+    from regressor_guided_image_editing_b200.guidance_classifier.guidance_scores import valence_arousal_score
+    from regressor_guided_image_editing_b200.baselines.models.utilities.MeanReplicatedCrops import MeanReplicatedCrops
+    g = torch.Generator().manual_seed(1)
+    for B in (1, 4):
+        p = torch.rand(B, 2, generator=g)
+        for minimised in (True, False):
+            for ref_value in (None, torch.rand(B, 2, generator=g)):
+                a, b = p.clone().requires_grad_(True), p.clone().requires_grad_(True)
+                sa = R.valence_arousal_score(a, "cpu", minimised, ref_value)
+                sb = valence_arousal_score(b, "cpu", minimised, ref_value)
+                ga, = torch.autograd.grad(sa, a)
+                gb, = torch.autograd.grad(sb, b)
+                assert torch.equal(sa, sb) and torch.equal(ga, gb)
+    x = torch.rand(30, 4, generator=g)
+    assert torch.equal(MeanReplicatedCrops(10)(x), RM(10)(x))
