@@ -16,6 +16,12 @@ same, the default K=100 is exactly one full edit of the batch.
           MEASURED bf16 peak (MEASURED_PEAKS.json, sustained figure since the kernels run inside a long step).
   cpu_baseline : the oracle port of the reference loop (oracle/oracle.py, weight-gradient work included as the reference
           does it) timed on this box's host cores on a bounded sample (rank 0, N=1 only).
+  regressor_fwd_bwd_ms : cudaEvents around resize -> crop pack -> resnet50 fwd -> VA head -> resnet50 dgrad -> crop gather ->
+          resize^T of eager steps; roofline.achieved / frac are computed on THIS span (all of the regressor,
+          not the GEMM subset); the GEMM-only figures sit under roofline.gemm_only.
+  --images N : BASELINE.json configs[4] -- a strong-scaling sweep of N images sharded over the ranks (shard.partition), each
+          rank running ceil(N/W)/B engine batches of 100 steps through ONE engine + CUDA graph, then ONE gather of uint8 edited
+          images + predictions + per-step losses to rank 0 (NCCL) and their D2H; everything inside the timed region.
 --impl reference : times that same CPU implementation alone (the reference is pure Python/PyTorch; /root/reference does
           not exist on the GPU box, the oracle port is its restatement validated bit-exactly against it).
 """
@@ -41,6 +47,15 @@ def _peaks():
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
     except Exception:
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def _lib_sha():
+    import hashlib
+    try:
+        with open(os.path.join(ROOT, "regressor_guided_image_editing_b200", "librgie.so"), "rb") as f:
+            return hashlib.sha256(f.read()).hexdigest()[:16]
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -118,6 +133,111 @@ def cpu_reference_leg(steps: int, warmup: int, h: int, w: int, threads: int, bud
     return 1.0 / (STEPS_PER_IMAGE * sec_per_step), sec_per_step, len(times)
 
 
+def run_sweep(args, rank, world, dev, lib):
+    """BASELINE.json configs[4]: --images N synthetic images, strong split over the ranks, final gather to rank 0."""
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle as O          # seeded synthetic inputs / weights only
+    from regressor_guided_image_editing_b200 import engine, shard
+
+    N, B, H, S = args.images, args.batch, args.size, args.sweep_steps
+    begin, end = shard.partition(N, world, rank)
+    batches = shard.micro_batches(begin, end, B)
+    sd = O.make_regressor_state_dict()
+    eng = engine.ParametricEditEngine(sd, batch=B, height=H, width=H, num_steps=S, precision=args.precision,
+                                      micro_batch=args.micro_batch, device=dev)
+    n_local = end - begin
+    # host inputs of this rank (pinned), per-image seeds: results do not depend on the world size
+    images_h = torch.empty(max(n_local, 1), 3, H, H, dtype=torch.float32).pin_memory()
+    offs_h = torch.empty(1 + S, max(n_local, 1), 10, 2, dtype=torch.int32).pin_memory()
+    for k, i in enumerate(range(begin, end)):
+        images_h[k] = O.synthetic_image(i, H, H)
+        g = torch.Generator().manual_seed(2000 + i)
+        offs_h[:, k] = torch.randint(0, eng.Hr - 448 + 1, (1 + S, 10, 2), generator=g, dtype=torch.int32)
+    edited_d = torch.empty(max(n_local, 1), 3, H, H, dtype=torch.uint8, device=dev)
+    preds_d = torch.empty(max(n_local, 1), 2, dtype=torch.float32, device=dev)
+    pred0_d = torch.empty_like(preds_d); target_d = torch.empty_like(preds_d)
+    losses_d = torch.empty(max(n_local, 1), S, dtype=torch.float32, device=dev)
+
+    def one_batch(b0, b1):
+        n = b1 - b0
+        idx = list(range(b0 - begin, b1 - begin)) + [b0 - begin] * (B - n)          # a short last batch repeats an image
+        img = images_h[idx] if n < B else images_h[b0 - begin:b1 - begin]
+        off = offs_h[:, idx] if n < B else offs_h[:, b0 - begin:b1 - begin]
+        eng.load_problem(img.to(dev, non_blocking=True), off.contiguous().to(dev, non_blocking=True))
+        eng.advance(S)
+        res = eng.results()
+        sl = slice(b0 - begin, b1 - begin)
+        edited_d[sl] = (res["edited"][:n] * 255.0).round_().clamp_(0, 255).to(torch.uint8)
+        preds_d[sl] = res["preds"][-1, :n, :2]; pred0_d[sl] = res["pred0"][:n, :2]; target_d[sl] = res["target"][:n]
+        losses_d[sl] = res["losses"][:, :n].t()
+
+    # warm-up: one short run so that every kernel is instantiated and the step graph is captured (untimed)
+    lps = 0
+    if batches:
+        eng.load_problem(images_h[:1].expand(B, 3, H, H).contiguous().to(dev), offs_h[:, :1].expand(1 + S, B, 10, 2).contiguous().to(dev))
+        l0 = lib.rgie_launch_count()
+        eng.advance(1)
+        torch.cuda.synchronize(dev)
+        lps = int(lib.rgie_launch_count() - l0)
+        eng.advance(min(3, S) - 1)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    t0 = time.perf_counter()
+    with ClockSampler(dev.index) as clk:
+        e0.record()
+        for b0, b1 in batches:
+            one_batch(b0, b1)
+        e1.record()
+        local = {"edited": edited_d[:n_local], "preds": preds_d[:n_local], "pred0": pred0_d[:n_local],
+                 "target": target_d[:n_local], "losses": losses_d[:n_local]}
+        out = shard.gather_to_rank0(local)
+        if rank == 0:
+            host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
+            for k, v in out.items():
+                host[k].copy_(v, non_blocking=True)
+        e2.record()
+        torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - t0
+    t = torch.tensor([e0.elapsed_time(e2), e0.elapsed_time(e1)], device=dev)
+    per_rank = [t.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, t)
+        tmax = torch.stack(per_rank).max(0).values
+    else:
+        tmax = t
+    if rank != 0:
+        return None
+    total_ms, compute_ms = float(tmax[0]), float(tmax[1])
+    stats = shard.target_error_stats(host["preds"], host["target"], host["pred0"])
+    gathered = sum(v.numel() * v.element_size() for v in host.values())
+    steps_total = len(batches) * S
+    line = {"metric": "edited images/sec (100 steps, 512^2)", "value": N * (S / STEPS_PER_IMAGE) / (total_ms / 1e3),
+            "unit": "images/s", "n_gpus": world, "steps": steps_total, "warmup": min(3, S), "ms_per_step": compute_ms / max(steps_total, 1),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else args.precision, "data": "synthetic",
+            "config": {"workload": f"configs[4]: batch-sharded sweep of {N} synthetic {H}x{H} images, {S} steps/image, "
+                                   f"8 default filters, random-init resnet50 VA regressor on 10 random 448 crops",
+                       "images": N, "batch_per_engine": B, "micro_batch": args.micro_batch, "engine_batches_per_rank": len(batches),
+                       "precision": args.precision, "parallelism": f"dp{world} (contiguous image blocks, no collective in the loop, "
+                                                                     f"one final gather to rank 0)",
+                       "cache": "working set (>10 GB of activations per step) exceeds the 126 MB L2; no flush needed"},
+            "clocks": clk.summary(),
+            "e2e": {"value": N * (S / STEPS_PER_IMAGE) / (total_ms / 1e3), "unit": "images/s",
+                    "h2d_bytes_per_step": int((images_h.numel() * 4 + offs_h.numel() * 4) / max(steps_total, 1)),
+                    "d2h_bytes_per_step": int(gathered / max(steps_total, 1))},
+            "sweep": {"images": N, "total_s": total_ms / 1e3, "loop_s": compute_ms / 1e3, "gather_and_d2h_s": (total_ms - compute_ms) / 1e3,
+                      "wall_s": wall, "gathered_bytes": gathered, "per_rank_total_ms": [float(x[0]) for x in per_rank],
+                      "target_error_stats": stats,
+                      "edited_uint8_checksum": int(host["edited"].to(torch.int64).sum().item()),
+                      "mean_final_loss": float(host["losses"][:, -1].mean().item())},
+            "gpu_launches": lps * steps_total, "launches_per_step": lps}
+    return line
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -131,6 +251,9 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-GEMM timing table (json) here")
+    ap.add_argument("--images", type=int, default=0,
+                    help="configs[4]: strong-scaling sweep of this many images over all ranks (0 = the weak-scaling headline)")
+    ap.add_argument("--sweep-steps", type=int, default=STEPS_PER_IMAGE, help="optimisation steps per image in --images mode")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -179,6 +302,14 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
+    if args.images > 0:
+        line = run_sweep(args, rank, world, dev, lib)
+        if line is not None:
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     sd = O.make_regressor_state_dict()
     n_steps_total = W + K
     eng = engine.ParametricEditEngine(sd, batch=B, height=H, width=H, num_steps=max(n_steps_total, 1),
@@ -210,10 +341,12 @@ def main():
         e1.record()
         torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], device=dev)
+    clk_own = clk.summary()
+    t = torch.tensor([ms, float(clk_own["sm_mhz"] or 0.0)], device=dev)
+    per_rank = [t.clone() for _ in range(world)]
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+        dist.all_gather(per_rank, t)            # attribution of the max: every rank's own time and median SM clock
+    ms_max = max(float(x[0]) for x in per_rank)
     value = world * B * (Kt / STEPS_PER_IMAGE) / (ms_max / 1e3)
 
     # ---- live roofline of the GEMM family: a few eager steps with cudaEvent pairs around every GEMM launch
@@ -245,6 +378,18 @@ def main():
                   "algorithmic_GB": by_a[i] / 1e9, "algorithmic_GBs": by_a[i] / max(med[i], 1e-9) / 1e6}
                  for i in range(n.value)]
         lib.rgie_regressor_set_profiling(eng.reg._h, 0)
+        # regressor fwd+bwd span: events around resize -> ... -> resize^T of eager steps, no per-op events
+        span = []
+        eng.span_events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        for r in range(reps_prof + 1):
+            eng.counter.fill_(min(done, eng.steps - 1))
+            eng._step()
+            torch.cuda.synchronize(dev)
+            if r > 0:
+                span.append(eng.span_events[0].elapsed_time(eng.span_events[1]))
+        eng.span_events = None
+        span.sort()
+        regressor_span_ms = span[len(span) // 2]
         gemm_ms_per_step = tot_ms / reps_prof
         peaks, which = _peaks()
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
@@ -252,19 +397,30 @@ def main():
         n_launch = nops * (B // eng.mb)
         # DRAM bytes per launch of the same kernel family from the committed ncu capture (profiles/*_step_B32.json:
         # dram__bytes_read.sum + dram__bytes_write.sum over the GEMM launches of one optimisation step, micro-batch 32)
+        # ... only from a capture of THIS build: tools/summarize_launches.py stamps the sha256 of the librgie.so it profiled
         traffic, traffic_src = None, None
         try:
             import glob
-            cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_step_B32.json")))
-            if cands and eng.mb == 32:
-                pj = json.load(open(cands[-1]))
-                traffic, traffic_src = pj["gemm_dram_bytes_per_launch"], os.path.relpath(cands[-1], ROOT)
+            sha = _lib_sha()
+            for cand in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_step_B32.json")), reverse=True):
+                pj = json.load(open(cand))
+                if eng.mb == 32 and sha is not None and pj.get("lib_sha256") == sha:
+                    traffic, traffic_src = pj["gemm_dram_bytes_per_launch"], os.path.relpath(cand, ROOT)
+                    break
+            if traffic is None:
+                traffic_src = "no ncu capture of this build (librgie.so sha256 %s) under profiles/: not reported" % sha
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        prof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+        span_achieved = FLOP_PER_IMAGE_STEP * B / (regressor_span_ms / 1e3) / 1e12
+        prof = {"bound": "tensor", "achieved": span_achieved, "peak": peak, "unit": "TFLOP/s", "frac": span_achieved / peak,
+                "span": "whole regressor fwd+bwd (resize -> pack -> resnet50 fwd -> head -> dgrad -> crop gather -> resize^T), "
+                        "algorithmic 653.9 GFLOP per image per step over regressor_fwd_bwd_ms",
+                "regressor_fwd_bwd_ms": regressor_span_ms,
+                "frac_of_whole_step": FLOP_PER_IMAGE_STEP * B / (ms_max / Kt / 1e3) / 1e12 / peak,
                 "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": which + " (sustained bf16 cuBLAS)", "kernel": "gemm_sm100_kernel<BN,STAGES,EPI,NEW>",
+                "peak_source": which + " (sustained bf16 cuBLAS)", "kernel": "gemm_sm100_kernel<BN,STAGES,EPI,NEW> family",
+                "gemm_only": {"achieved": achieved, "frac": achieved / peak, "ms_per_step": gemm_ms_per_step},
                 "launches_per_step": n_launch, "gemm_ms_per_step": gemm_ms_per_step,
                 "share_of_step": gemm_ms_per_step / (ms_max / Kt),
                 "algorithmic_flop_per_step": tot_fl / reps_prof,
@@ -334,11 +490,14 @@ def main():
     line = {"metric": "edited images/sec (100 steps, 512^2)", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": Kt, "warmup": done, "ms_per_step": ms_max / Kt, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else args.precision, "data": "synthetic",
-            "config": config, "clocks": clk.summary(),
+            "config": config, "clocks": clk_own,
+            "per_rank": {"ms_per_step": [float(x[0]) / Kt for x in per_rank], "sm_mhz": [float(x[1]) for x in per_rank]},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches_per_step * Kt), "launches_per_step": int(launches_per_step),
             "roofline": prof, "cpu_baseline": cpu_base,
-            "regressor_fwd_bwd_ms": None if prof is None else prof["gemm_ms_per_step"],
+            "regressor_fwd_bwd_ms": None if prof is None else prof["regressor_fwd_bwd_ms"],
+            "gemm_ms_per_step": None if prof is None else prof["gemm_ms_per_step"],
+            "lib_sha256": _lib_sha(),
             "final_mean_best_loss": float(res["best_loss"].mean().item())}
     print(json.dumps(line))
     if world > 1:

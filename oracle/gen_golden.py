@@ -3,7 +3,7 @@
 Generates tests/golden/*.pt by running the UNMODIFIED reference Python (imported from /root/reference/src through
 oracle/ref_harness.py) on CPU.  Run in the build container only:
 
-    python -m oracle.gen_golden [--only filters|regressor|loop|midu]
+    python -m oracle.gen_golden [--only filters|regressor|loop|loopk|loop512|midu]
 
 The reference ships no tests/fixtures, so these vectors are the pin for the standalone oracle
 (oracle/oracle.py) and, through it, for the CUDA path.  Inputs are regenerated from seeds at test time; only outputs
@@ -128,22 +128,40 @@ def gen_regressor(r):
     torch.save(out, os.path.join(GOLDEN_DIR, "regressor.pt"))
 
 
-def gen_loop(r, h=256, w=256, num_steps=50, tag="c1", image_index=0):
-    """BASELINE.json configs[0]: one synthetic 256x256 image, random-init regressor, 50 steps, CPU."""
+# Start points off the identity presets.  The 50-step run keeps blur at its preset: with a real sigma the optimiser walks
+# sigma down through 0 within ~20 steps and the REFERENCE itself turns NaN there (kornia's gaussian with sigma <= 0), and at
+# the preset 1e-4 d/d(sigma) underflows to exactly 0 in every implementation (a dead parameter, not a kink).  The short
+# 512x512 run does start from a real sigma so that the separable blur and its sigma-gradient are inside the loop test.
+KINK_FREE_X0 = dict(sharp=[0.3], scale=[1.05, 1.03, 3.0, 5.0])
+KINK_FREE_X0_BLUR = dict(sharp=[0.3], blur=[0.8], scale=[1.05, 1.03, 3.0, 5.0])
+
+
+def gen_loop(r, h=256, w=256, num_steps=50, tag="c1", image_index=0, x0_override=None):
+    """BASELINE.json configs[0]: one synthetic 256x256 image, random-init regressor, 50 steps, CPU.
+    x0_override ({filter: values}) moves the start point off the identity presets: the scale filter's bilinear kink,
+    the sharp == 0 and the blur sigma -> 0 branches all sit exactly AT the reference's start values, so a start point
+    next to them gives a trajectory on which every parameter gradient is smooth (tag "c1k").
+    Also stored: d(loss)/d(x) of every step (one extra autograd.grad per step on the reference's own graph)."""
     sd = O.make_regressor_state_dict()
     clf = _ref_clf(r, sd)
     image = O.synthetic_image(image_index, h, w)[None]
     torch.manual_seed(2000 + image_index)
     obj = {"clf": clf, "dis": None, "weight_clf": 0.15, "weight_dis": 0.0, "weight_recon": 0.0, "alpha": 0.1}
     x0, obj = r.optimize_image_param.initialize_parametric(image, obj)
+    if x0_override:
+        lay = O.param_layout(O.DEFAULT_FILTERS)
+        x0 = x0.clone()
+        for name, vals in x0_override.items():
+            x0[lay[name][0]:lay[name][0] + len(vals)] = torch.tensor(vals)
     obj["target"] = r.optimize_image.get_condition_from_alpha(obj["alpha"], obj["clf"], image)
     del obj["alpha"]
-    losses, preds, xs = [], [], []
+    losses, preds, xs, grads = [], [], [], []
     orig = r.optimize_image_param.objective_function_parametric
 
     def wrapped(x, **kw):
         xs.append(x.detach().clone())
         l = orig(x, **kw)
+        grads.append(torch.autograd.grad(l, x, retain_graph=True)[0].detach().clone())
         losses.append(float(l))
         preds.append(clf.fake_loss_metric.detach().clone()[0])
         return l
@@ -158,7 +176,8 @@ def gen_loop(r, h=256, w=256, num_steps=50, tag="c1", image_index=0):
     offs = O.draw_crop_offsets(1 + num_steps, 1, 480, 480)
     out = dict(h=h, w=w, num_steps=num_steps, image_index=image_index, alpha=0.1, learning_rate=0.05, weight_clf=0.15,
                target=obj["target"].clone(), losses=torch.tensor(losses), preds=torch.stack(preds),
-               xs=torch.stack(xs), best_x=best_x.clone(), edited=edited.clone(), offsets=offs,
+               xs=torch.stack(xs), grads=torch.stack(grads), x0=x0.detach().clone(), best_x=best_x.clone(),
+               edited=(edited if h * w <= 256 * 256 else edited[..., ::4, ::4]).clone(), offsets=offs,
                ref_seconds=dt, ref_threads=torch.get_num_threads())
     torch.save(out, os.path.join(GOLDEN_DIR, f"loop_{tag}.pt"))
     print(f"loop_{tag}.pt: {num_steps} steps in {dt:.1f}s; loss {losses[0]:.6f} -> {min(losses):.6f}")
@@ -201,8 +220,10 @@ def main():
         gen_regressor(r)
     if "loop" in todo:
         gen_loop(r)
+    if "loopk" in todo:
+        gen_loop(r, tag="c1k", x0_override=KINK_FREE_X0)
     if "loop512" in todo:
-        gen_loop(r, 512, 512, 10, "c2_10steps", image_index=1)
+        gen_loop(r, 512, 512, 3, "c2_3steps", image_index=1, x0_override=KINK_FREE_X0_BLUR)
 
 
 if __name__ == "__main__":

@@ -39,12 +39,19 @@ class _RegressorFn(torch.autograd.Function):
         reg = mod._regressor(B * reps)
         logits = reg.forward(xr, offs, normalize=mod.normalize)
         ctx.rs, ctx.reg, ctx.shape = rs, reg, (B, 3, oh, ow)
+        # the native handle keeps the activations (sign bits, pool argmax) of its LAST forward only: remember which
+        # forward this was, and what it ran on, so that backward can restore the state if another forward came between
+        # (ValenceArousalLoss.forward(fake, real_imgs=...) runs the model twice before backpropagating the first call)
+        ctx.generation, ctx.fwd_args, ctx.normalize = reg.generation, (xr, offs), mod.normalize
         mod.last_offsets = offs
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
         dx = torch.empty(ctx.shape, dtype=torch.float32, device=dlogits.device)
+        if ctx.reg.generation != ctx.generation:
+            xr, offs = ctx.fwd_args
+            ctx.reg.forward(xr, offs, normalize=ctx.normalize)        # same inputs, same offsets: identical activations
         ctx.reg.backward(dlogits.contiguous().float(), dx)
         return ctx.rs.bwd(dx), None
 

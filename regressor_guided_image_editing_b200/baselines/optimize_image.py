@@ -19,8 +19,6 @@ import torch
 from .. import _lib, ops
 from ..engine import ParametricEditEngine, lr_schedule
 
-_ENGINES = {}
-
 
 def get_condition_from_alpha(alpha, clf, img):                                            # :119-123
     condition = clf.predict_loss_metric(img)
@@ -53,13 +51,16 @@ def _optimization_fused(x0, params, learning_rate, num_steps):
     clf, image = params["clf"], params["image"]
     core = clf.model[0]
     _, _, H, W = image.shape
-    key = (id(core), H, W, num_steps, core.precision)
-    eng = _ENGINES.get(key)
-    if eng is None:
-        _ENGINES.clear()
+    # the engine (packed weights + workspace) is cached ON the model object, so it can never outlive it or be handed to
+    # another model that happens to get the same id()
+    key = (H, W, num_steps, core.precision)
+    cached = getattr(core, "_fused_engine", None)
+    if cached is None or cached[0] != key:
+        core._fused_engine = None
         eng = ParametricEditEngine(core._sd, 1, H, W, num_steps, precision=core.precision,
                                    input_size=core.input_size, crop_size=core.crop_size, folded=core._folded)
-        _ENGINES[key] = eng
+        core._fused_engine = (key, eng)
+    eng = core._fused_engine[1]
     offs = torch.stack([draw_crop_offsets(1, eng.Hr, eng.Wr, core.crop_size, 10) for _ in range(num_steps)])
     eng.load_problem(image.float().contiguous(), offs.to(image.device), alpha=None, target=params["target"],
                      learning_rate=learning_rate, weight_clf=params["weight_clf"], clf_weight=clf.weight,

@@ -37,6 +37,21 @@ void count_launch();
 
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
+// Per-device one-time setup at a call site (cudaFuncSetAttribute is a per-device property): a bit per device ordinal,
+// updated atomically so that two host threads driving two GPUs cannot race.
+struct DeviceOnce {
+  unsigned long long done_bits = 0ull;
+  bool needed() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    return ((__atomic_load_n(&done_bits, __ATOMIC_ACQUIRE) >> dev) & 1ull) == 0ull;
+  }
+  void done() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) __atomic_fetch_or(&done_bits, 1ull << dev, __ATOMIC_RELEASE);
+  }
+};
+
 // ---------------------------------------------------------------------------------------------------------------
 // Pixel-row geometry of an activation matrix [rows, channels] (channels contiguous, NHWC-like).
 // A tensor is `planes` stacked planes; each plane holds n_img images of (H + pad_t + pad_b) x P pixel rows,
@@ -143,6 +158,9 @@ constexpr int kMaxTaps = 16;
 struct GemmDesc {
   // operands
   const void* A;      long a_rows;  int Cin;     // A: [a_rows, Cin] row-major
+  int a_ld;                                       // elements between consecutive rows of A; 0 = Cin (dense).  a_ld < Cin: rows
+                                                  // OVERLAP (row m = the Cin elements starting at element m * a_ld) -- conv1 reads
+                                                  // its 16-channel packed pixels as 4-pixel windows without replicating them
   const void* Wt;     int  n_pad;                 // Wt: [n_pad, ntaps*Cin] row-major (K-major), n_pad >= Cout
   int ntaps;          long row_off[kMaxTaps];
   const void* A2;     long a2_rows; int Cin2;    // optional second operand [a2_rows, Cin2] (row offset 0), or null

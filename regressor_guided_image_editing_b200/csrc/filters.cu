@@ -1343,11 +1343,11 @@ int rgie_filter_fwd(int kind, const float* in, float* out, const float* p, int p
       RGIE_CHECK(H >= 3 && W >= 3, "sharp: image too small");
       const SharpBand sb = sharp_band(H, W, false);
       if (sb.R > 0) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static DeviceOnce attr_once;
+        if (attr_once.needed()) {
           RGIE_CUDA_OK(cudaFuncSetAttribute(sharp_fwd_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
           RGIE_CUDA_OK(cudaFuncSetAttribute(sharp_bwd_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-          attr_set = true;
+          attr_once.done();
         }
         sharp_fwd_band_kernel<<<dim3(sb.nb, 3, B), kThreads, sb.smem_f, st>>>(in, out, p, p_stride, H, W, sb.R);
         RGIE_LAUNCH_OK();
@@ -1489,11 +1489,11 @@ int rgie_filter_bwd(int kind, const float* in, const float* gout, float* gin, co
       RGIE_CHECK(H >= 3 && W >= 3, "sharp: image too small");
       const SharpBand sb = sharp_band(H, W, true);
       if (sb.R > 0) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static DeviceOnce attr_once;
+        if (attr_once.needed()) {
           RGIE_CUDA_OK(cudaFuncSetAttribute(sharp_fwd_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
           RGIE_CUDA_OK(cudaFuncSetAttribute(sharp_bwd_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-          attr_set = true;
+          attr_once.done();
         }
         sharp_bwd_band_kernel<<<dim3(sb.nb, 3, B), kThreads, sb.smem_b, st>>>(in, gout, gin, p, p_stride, partial, H, W, sb.R);
         RGIE_LAUNCH_OK();

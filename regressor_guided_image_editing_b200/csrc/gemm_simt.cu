@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDesc d) {
     for (int c0 = 0; c0 < cin; c0 += TK) {
       float av[4] = {0.f, 0.f, 0.f, 0.f}, wv[4] = {0.f, 0.f, 0.f, 0.f};
       if (a_ok) {
-        const T* p = At + arow * cin + c0 + lk;
+        const T* p = At + arow * (second || d.a_ld == 0 ? cin : d.a_ld) + c0 + lk;
 #pragma unroll
         for (int q = 0; q < 4; ++q) av[q] = to_f<T>(p[q]);
       }

@@ -1814,11 +1814,11 @@ PFN_encodeTiled get_encode_fn() {
 }
 
 int make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows,
-                CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+                CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, uint64_t row_elems = 0) {
   PFN_encodeTiled enc = get_encode_fn();
   RGIE_CHECK(enc != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
   cuuint64_t gdim[2] = {inner, rows};
-  cuuint64_t gstride[1] = {inner * 2};
+  cuuint64_t gstride[1] = {(row_elems ? row_elems : inner) * 2};     // row_elems < inner: overlapped rows (GemmDesc::a_ld)
   cuuint32_t box[2] = {box_inner, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
@@ -1829,11 +1829,12 @@ int make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t row
 }
 
 // A as [C = 64, P, lines] with a box of 8 pixels x box_lines lines (one 128-byte row per pixel, SWIZZLE_128B)
-int make_map_3d(CUtensorMap* map, const void* base, uint64_t P, uint64_t lines, uint32_t box_lines) {
+// pix_elems: elements between consecutive pixels in memory (64 = dense; 16 = overlapped 4-pixel windows, GemmDesc::a_ld)
+int make_map_3d(CUtensorMap* map, const void* base, uint64_t P, uint64_t lines, uint32_t box_lines, uint64_t pix_elems = 64) {
   PFN_encodeTiled enc = get_encode_fn();
   RGIE_CHECK(enc != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
   cuuint64_t gdim[3] = {64, P, lines};
-  cuuint64_t gstride[2] = {64 * 2, P * 64 * 2};
+  cuuint64_t gstride[2] = {pix_elems * 2, P * pix_elems * 2};
   cuuint32_t box[3] = {64, 8, box_lines};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
@@ -1845,11 +1846,11 @@ int make_map_3d(CUtensorMap* map, const void* base, uint64_t P, uint64_t lines, 
 
 template <int BN, int NY, int NX>
 int run_patch(const GemmPlanSm100& p, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
     RGIE_CUDA_OK(cudaFuncSetAttribute(gemm_patch_kernel<BN, NY, NX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       PatchSmem::DYN_BYTES));
-    attr_set = true;
+    attr_once.done();
   }
   PatchTaps tp;
   tp.ny = p.patch_ny; tp.nx = p.patch_nx; tp.dy0 = p.patch_dy0; tp.dx0 = p.patch_dx0;
@@ -1863,10 +1864,10 @@ int run_patch(const GemmPlanSm100& p, cudaStream_t st) {
 }
 
 int run_b2b(const GemmPlanSm100& p, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
     RGIE_CUDA_OK(cudaFuncSetAttribute(gemm_b2b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemB2b::DYN_BYTES));
-    attr_set = true;
+    attr_once.done();
   }
   B2bParams q;
   q.bias2 = p.d2.bias; q.D2 = p.d2.D; q.ldd2 = p.d2.ldd; q.relu2 = p.d2.relu;
@@ -1879,11 +1880,11 @@ int run_b2b(const GemmPlanSm100& p, cudaStream_t st) {
 template <int BN, int STAGES>
 int run_2cta(const GemmPlanSm100& p, cudaStream_t st) {
   using L = Smem2<BN, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
     RGIE_CUDA_OK(cudaFuncSetAttribute(gemm_sm100_2cta_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       L::DYN_BYTES));
-    attr_set = true;
+    attr_once.done();
   }
   gemm_sm100_2cta_kernel<BN, STAGES><<<p.grid, 640, L::DYN_BYTES, st>>>(
       p.tmA, p.tmA2, p.tmB, p.d, p.num_m_tiles, p.num_n_tiles, make_fastdiv((uint32_t)p.num_n_tiles));
@@ -1894,11 +1895,11 @@ int run_2cta(const GemmPlanSm100& p, cudaStream_t st) {
 template <int BN, int STAGES, int EPI, int NEW, bool PAIR = false>
 int run_impl(const GemmPlanSm100& p, cudaStream_t st) {
   using L = SmemLayout<BN, STAGES, EPI, PAIR>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
     RGIE_CUDA_OK(cudaFuncSetAttribute(gemm_sm100_kernel<BN, STAGES, EPI, NEW, PAIR>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
-    attr_set = true;
+    attr_once.done();
   }
   // PAIR: the kernel walks pairs of M-adjacent tiles (num_m_tiles then counts pairs)
   const int m_units = PAIR ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
@@ -1911,14 +1912,15 @@ int run_impl(const GemmPlanSm100& p, cudaStream_t st) {
 }  // namespace
 
 int gemm_sm100_num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+  static int cache[64] = {0};                  // per device ordinal (a benign race: every writer stores the same value)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cache[dev]) {
+    int n = 0;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    cache[dev] = n > 0 ? n : 148;
   }
-  return n;
+  return cache[dev];
 }
 
 int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
@@ -1981,7 +1983,8 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
         p->grid = p->num_m_tiles < sms ? p->num_m_tiles : sms;
         p->epi = 0;
         p->tmA2 = p->tmA; p->tmD = p->tmA; p->tmR = p->tmA;
-        int rc = make_map_3d(&p->tmA, d.A, (uint64_t)P, (uint64_t)lines, (uint32_t)(16 + ny - 1));
+        int rc = make_map_3d(&p->tmA, d.A, (uint64_t)P, (uint64_t)lines, (uint32_t)(16 + ny - 1),
+                             (uint64_t)(d.a_ld ? d.a_ld : 64));
         if (rc) return rc;
         p->tmA2 = p->tmA; p->tmD = p->tmA; p->tmR = p->tmA;
         return make_map_2d(&p->tmB, d.Wt, (uint64_t)d.ntaps * d.Cin, (uint64_t)d.n_pad, BK, (uint32_t)bn);
@@ -2054,7 +2057,7 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
     rc = make_map_2d(&p->tmR, d.res, (uint64_t)d.ld_res, (uint64_t)rr, 32, BM, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   }
-  rc = make_map_2d(&p->tmA, d.A, (uint64_t)d.Cin, (uint64_t)d.a_rows, BK, BM);
+  rc = make_map_2d(&p->tmA, d.A, (uint64_t)d.Cin, (uint64_t)d.a_rows, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B, (uint64_t)d.a_ld);
   if (rc) return rc;
   if (d.A2 != nullptr) rc = make_map_2d(&p->tmA2, d.A2, (uint64_t)d.Cin2, (uint64_t)d.a2_rows, BK, BM);
   else p->tmA2 = p->tmA;
@@ -2134,10 +2137,10 @@ int build_conv_hshare_sm100(const GemmDesc& d, const void* Wh, int dy0, int dx0,
 }
 
 static int run_conv_hshare(const GemmPlanSm100& p, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
     RGIE_CUDA_OK(cudaFuncSetAttribute(conv_hshare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HsSmem::DYN_BYTES));
-    attr_set = true;
+    attr_once.done();
   }
   HsParams hp;
   hp.WT = p.hs_wt; hp.fd_wt = make_fastdiv((uint32_t)p.hs_wt); hp.dy0 = p.hs_dy0; hp.dx0 = p.hs_dx0; hp.col0 = p.hs_col0;

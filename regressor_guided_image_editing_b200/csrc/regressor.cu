@@ -85,6 +85,60 @@ __global__ void __launch_bounds__(256) pack_crops_kernel(const float* __restrict
   }
 }
 
+// The same operand WITHOUT the 4x horizontal-tap replication: Z16[n, i, jm, (pr*2+pc)*3 + c] (12 of 16 channels used), one
+// 16-channel pixel per 2x2 input quad, memory pixel jm = j + 2 of a line of P = W + 4 pixels (two zero pixels left, two
+// right: they are the conv's horizontal padding).  conv1 reads row m as the 64 elements starting at pixel m: the window over
+// memory pixels m .. m+3 = image columns j-2 .. j+1, i.e. exactly the four horizontal taps -- the rows of the GEMM operand
+// OVERLAP in memory (GemmDesc::a_ld = 16 < Cin = 64; the TMA tensor map simply has a 32-byte row stride).  The operand
+// shrinks from 128 to 32 bytes per conv1 output pixel (6.5 -> 1.7 MB per crop), for the pack's writes and conv1's reads.
+template <typename T>
+__global__ void __launch_bounds__(256) pack_crops16_kernel(const float* __restrict__ img, const int* __restrict__ offsets,
+                                                          const int* __restrict__ step_ptr, long off_step_stride,
+                                                          T* __restrict__ zz, Geom g, int reps, int Hr, int Wr, InXform xf) {
+  // one thread block = one output line (n, i); a thread = one 16-channel pixel
+  const int* offs = offsets + (step_ptr ? (long)(*step_ptr) * off_step_stride : 0);
+  const int n = blockIdx.x / g.H, i = blockIdx.x - n * g.H;
+  const int b = n / reps;
+  const int top = offs[2 * n], left_raw = offs[2 * n + 1];
+  const bool flip = (left_raw & kFlipBit) != 0;
+  const int left = left_raw & (kFlipBit - 1);
+  const int cw = 2 * g.W;
+  const float* src = img + (long)b * 3 * Hr * Wr + (long)(top + 2 * i) * Wr + left;
+  const long plane = (long)Hr * Wr;
+  T* dst_row = zz + (geom_row(g, 0, n, i, 0) + 2) * 16;
+  for (int j = threadIdx.x; j < g.W; j += blockDim.x) {
+    T vals[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) vals[k] = from_f<T>(0.f);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int pr = 0; pr < 2; ++pr) {
+        const float* q = src + c * plane + pr * Wr;
+        float v0 = flip ? q[cw - 1 - 2 * j] : q[2 * j], v1 = flip ? q[cw - 2 - 2 * j] : q[2 * j + 1];
+        if (xf.mode == 1) { v0 = (v0 - 0.5f) / 0.5f; v1 = (v1 - 0.5f) / 0.5f; }
+        else if (xf.mode == 2) {
+          v0 = fminf(fmaxf(__fadd_rn(__fmul_rn(v0, xf.ps), xf.pb), 0.f), 1.f) * 255.0f / 255.0f;
+          v1 = fminf(fmaxf(__fadd_rn(__fmul_rn(v1, xf.ps), xf.pb), 0.f), 1.f) * 255.0f / 255.0f;
+          v0 = (v0 - xf.mean[c]) / xf.std[c];
+          v1 = (v1 - xf.mean[c]) / xf.std[c];
+        }
+        vals[(pr * 2 + 0) * 3 + c] = from_f<T>(v0);
+        vals[(pr * 2 + 1) * 3 + c] = from_f<T>(v1);
+      }
+    T* dst = dst_row + (long)j * 16;
+    if (sizeof(T) == 2) {
+      const uint4* sv = reinterpret_cast<const uint4*>(vals);
+      reinterpret_cast<uint4*>(dst)[0] = sv[0];
+      reinterpret_cast<uint4*>(dst)[1] = sv[1];
+    } else {
+      const float4* sv = reinterpret_cast<const float4*>(vals);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) reinterpret_cast<float4*>(dst)[k] = sv[k];
+    }
+  }
+}
+
 // 16-byte vector of activations: 8 bf16 or 4 fp32
 template <typename T> struct Vec16 { static constexpr int N = 16 / sizeof(T); };
 template <typename T>
@@ -398,6 +452,7 @@ struct RgieRegressor {
   int precision = 0, dtype = 0, esz = 4;     // dtype 0 fp32 / 1 bf16
   int N = 0, crop = 0, K = 0;
   int H0 = 0;
+  int zz16 = 0;          // conv1 operand as 16-channel pixels read through overlapped rows (pack_crops16_kernel)
   int Hs[5] = {0, 0, 0, 0, 0};
   Geom gZZ, gDY, gS[5], gPh[5];
   std::vector<Block> blocks;
@@ -521,7 +576,7 @@ double op_bytes(const GemmDesc& d, int esz) {
   const Geom& g = d.src;
   const double valid_frac = (double)g.H * g.W / (double)g.S;
   const double out_rows = (double)(d.m_end - d.m_begin) * valid_frac;
-  double b = (double)d.a_rows * valid_frac * d.Cin * esz;                          // A
+  double b = (double)d.a_rows * valid_frac * (d.a_ld ? d.a_ld : d.Cin) * esz;      // A (overlapped rows: every element once)
   if (d.A2 != nullptr) b += (double)d.a2_rows * valid_frac * d.Cin2 * esz;        // second operand
   b += (double)d.n_pad * (d.ntaps * d.Cin + (d.A2 ? d.Cin2 : 0)) * esz;            // weights
   b += out_rows * d.Cout * (d.d_fp32 ? 4 : esz);                                   // D
@@ -575,7 +630,10 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
   R->K = num_classes;
   const int H0 = R->H0 = crop_size / 2;
   for (int s = 1; s <= 4; ++s) R->Hs[s] = H0 >> s;
-  R->gZZ = make_geom(1, N, H0, H0, 2, 1, 0, 0);
+  // RGIE_ZZ16=0 keeps the replicated 64-channel conv1 operand (pack_crops_kernel)
+  static const int env_zz16 = getenv("RGIE_ZZ16") ? atoi(getenv("RGIE_ZZ16")) : 0;
+  R->zz16 = env_zz16;
+  R->gZZ = R->zz16 ? make_geom(1, N, H0, H0, 2, 1, 0, 4) : make_geom(1, N, H0, H0, 2, 1, 0, 0);
   R->gDY = make_geom(1, N, H0, H0, 1, 2, 1, 2);
   for (int s = 1; s <= 4; ++s) {
     // one zero pad line above and one zero pad column left of every image: the pad line of the NEXT image (or the TMA
@@ -633,7 +691,8 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
   if (int rc = upload_f32(R, h_bfc, num_classes, &R->bfc)) return rc;
 
   // ---- stem buffers
-  if (int rc = dev_alloc(R, &R->zz, (size_t)R->gZZ.rows() * 64 * esz, true)) return rc;
+  // (zz16: the last rows' windows reach 3 pixels past the last row; + one zero line keeps them inside the allocation)
+  if (int rc = dev_alloc(R, &R->zz, ((size_t)R->gZZ.rows() + R->gZZ.P) * (R->zz16 ? 16 : 64) * esz, true)) return rc;
   if (int rc = dev_alloc(R, &R->c1, (size_t)N * H0 * H0 * 64 * esz, true)) return rc;
   if (int rc = dev_alloc(R, &R->p1, (size_t)R->gS[1].rows() * 64 * esz, true)) return rc;
   if (int rc = dev_alloc(R, (void**)&R->arg, (size_t)N * R->Hs[1] * R->Hs[1] * 64, true)) return rc;
@@ -656,6 +715,7 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
   {
     GemmDesc d = base_desc();
     d.A = R->zz; d.a_rows = R->gZZ.rows(); d.Cin = 64;
+    d.a_ld = R->zz16 ? 16 : 0;
     d.Wt = R->wc1; d.n_pad = 64; d.ntaps = 4;
     for (int a = 0; a < 4; ++a) d.row_off[a] = (long)(a - 2) * R->gZZ.P;
     d.m_begin = 0; d.m_end = R->gZZ.rows(); d.Cout = 64;
@@ -934,7 +994,13 @@ int rgie_regressor_forward_ex(RgieRegressor* R, const float* img, int B, int Hr,
   xf.mode = normalize;
   const int N = R->N, H0 = R->H0, H1 = R->Hs[1];
   const int pack_threads = (H0 * 4) % 224 == 0 ? 224 : 256;     // 4 work items per output pixel: whole iterations per line
-  if (R->dtype == 0) {
+  if (R->zz16) {
+    if (R->dtype == 0)
+      pack_crops16_kernel<float><<<N * H0, 224, 0, st>>>(img, offsets, step_ptr, off_step_stride, (float*)R->zz, R->gZZ, reps, Hr, Wr, xf);
+    else
+      pack_crops16_kernel<__nv_bfloat16><<<N * H0, 224, 0, st>>>(img, offsets, step_ptr, off_step_stride, (__nv_bfloat16*)R->zz,
+                                                                 R->gZZ, reps, Hr, Wr, xf);
+  } else if (R->dtype == 0) {
     pack_crops_kernel<float><<<N * H0, pack_threads, 0, st>>>(img, offsets, step_ptr, off_step_stride, (float*)R->zz, R->gZZ, reps, Hr,
                                                      Wr, xf);
   } else {

@@ -35,6 +35,17 @@ def lr_schedule(step: int, num_steps: int, learning_rate: float, lr_rampdown_len
     return float(learning_rate * lr_ramp)
 
 
+def _on_own_device(fn):
+    """Run a method with the engine's device current: handles, launches and streams all belong to self.dev."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **kw):
+        with torch.cuda.device(self.dev):
+            return fn(self, *a, **kw)
+    return wrapped
+
+
 class ParametricEditEngine:
     def __init__(self, state_dict: Dict[str, torch.Tensor], batch: int, height: int, width: int, num_steps: int,
                  precision: str = "bf16", micro_batch: Optional[int] = None, input_size: int = 480,
@@ -43,6 +54,14 @@ class ParametricEditEngine:
             raise _lib.RgieError("ParametricEditEngine needs a CUDA device: there is no CPU path")
         self.lib = _lib.load()
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.dev.index is None:
+            self.dev = torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.device(self.dev):
+            self._build(state_dict, batch, height, width, num_steps, precision, micro_batch, input_size, crop_size, reps,
+                        use_graph, folded)
+
+    def _build(self, state_dict, batch, height, width, num_steps, precision, micro_batch, input_size, crop_size, reps,
+               use_graph, folded):
         self.B, self.H, self.W, self.steps = batch, height, width, num_steps
         self.reps, self.input_size, self.crop = reps, input_size, crop_size
         self.mb = batch if micro_batch is None else micro_batch
@@ -88,6 +107,10 @@ class ParametricEditEngine:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = 0
         self._warm = False
+        self.steps_done = 0
+        # optional (start, end) torch.cuda.Event pair around resize -> crops -> resnet50 fwd -> VA head -> resnet50 bwd ->
+        # crop gather -> resize^T of an EAGER step (SURVEY.md 8d "regressor fwd+bwd ms"); never set while capturing
+        self.span_events = None
 
     # ------------------------------------------------------------------------------------------------------------
     def _st(self):
@@ -117,6 +140,8 @@ class ParametricEditEngine:
         check(lib.rgie_params_default_fwd(ptr(self.x), ptr(self.p), B, float(self.H), st), "params_fwd")
         check(lib.rgie_record(ptr(self.x), ptr(self.x_log), ptr(self.counter), B * self.NP, st), "record")
         self._filters_fwd(self.p)
+        if self.span_events is not None:           # eager timing of the regressor span (bench.py: regressor_fwd_bwd_ms)
+            self.span_events[0].record()
         src = self._regressor_fwd(self.stage[-1], self.offsets, self.counter, 0)
         dsrc = self.gA if self.resize.identity else self.dresized
         stride = B * reps * 2
@@ -137,6 +162,8 @@ class ParametricEditEngine:
         if not self.resize.identity:
             check(lib.rgie_resize_bwd(self.resize._h, ptr(self.dresized), ptr(g_cur), B * 3, ptr(self.rs_tmp), st),
                   "resize_bwd")
+        if self.span_events is not None:
+            self.span_events[1].record()
         for k in reversed(range(len(self.kinds))):
             check(lib.rgie_filter_bwd(self.kinds[k], ptr(self.stage[k]), ptr(g_cur), ptr(g_nxt),
                                       self.p.data_ptr() + 4 * self.poff[k], self.NP, self.gp.data_ptr() + 4 * self.poff[k],
@@ -149,6 +176,7 @@ class ParametricEditEngine:
         check(lib.rgie_counter_add(ptr(self.counter), 1, st), "counter")
         return n_launch
 
+    @_on_own_device
     def predict(self, images: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
         """No-grad regressor prediction (ValenceArousalLoss.predict_loss_metric, :131-138): [B,nc] after sigmoid."""
         lib, st = self.lib, self._st()
@@ -166,13 +194,23 @@ class ParametricEditEngine:
         return preds
 
     # ------------------------------------------------------------------------------------------------------------
+    @_on_own_device
     def load_problem(self, images: torch.Tensor, offsets: torch.Tensor, alpha: Optional[float] = 0.1,
                      target: Optional[torch.Tensor] = None, learning_rate: float = 0.05, weight_clf: float = 0.15,
                      clf_weight: float = 1.0, x0: Optional[torch.Tensor] = None) -> None:
         """images [B,3,H,W] (device), offsets int32 [1+steps, B, reps, 2] (device): draw 0 feeds
         get_condition_from_alpha (optimize_image.py:34-36,119-123), draw 1+s feeds step s."""
-        assert images.shape == (self.B, 3, self.H, self.W) and images.is_cuda
-        assert offsets.dtype == torch.int32 and offsets.shape[1:] == (self.B, self.reps, 2)
+        if tuple(images.shape) != (self.B, 3, self.H, self.W) or not images.is_cuda:
+            raise _lib.RgieError(f"load_problem: images must be a CUDA tensor of shape {(self.B, 3, self.H, self.W)}")
+        if offsets.dtype != torch.int32 or tuple(offsets.shape[1:]) != (self.B, self.reps, 2):
+            raise _lib.RgieError(f"load_problem: offsets must be int32 [1+steps or steps, {self.B}, {self.reps}, 2]")
+        if offsets.shape[0] not in (self.steps, 1 + self.steps):
+            raise _lib.RgieError(f"load_problem: offsets hold {offsets.shape[0]} draws, expected {self.steps} or {1 + self.steps}")
+        # the crop kernels index the resized image with these: (top, left) must keep the crop inside it
+        lo, hi_t, hi_l = int(offsets.min()), int(offsets[..., 0].max()), int(offsets[..., 1].max())
+        if lo < 0 or hi_t > self.Hr - self.crop or hi_l > self.Wr - self.crop:
+            raise _lib.RgieError(f"load_problem: crop offsets outside [0, {self.Hr - self.crop}] x [0, {self.Wr - self.crop}]")
+        self.steps_done = 0
         self.stage[0].copy_(images)
         new_scale = float(weight_clf) * float(clf_weight)
         if new_scale != self.scale:
@@ -182,7 +220,8 @@ class ParametricEditEngine:
             self.offsets.copy_(offsets[1:])
             self.pred0 = self.predict(self.stage[0], offsets[0])
         else:
-            assert offsets.shape[0] == self.steps and target is not None, "offsets must be [1+steps,...] unless a target is given"
+            if target is None:
+                raise _lib.RgieError("load_problem: offsets must be [1+steps, ...] unless a target is given")
             self.offsets.copy_(offsets)
             self.pred0 = torch.zeros(self.B, self.nc, dtype=torch.float32, device=self.dev)
         if target is None:
@@ -199,6 +238,7 @@ class ParametricEditEngine:
             sched[s] = ops.adam_scalars(lr, s + 1)
         self.sched.copy_(torch.from_numpy(sched.astype(np.float32)))
 
+    @_on_own_device
     def ensure_graph(self) -> None:
         """Capture one step into a CUDA graph (capturing does not execute; needs one prior eager step so that every
         kernel is instantiated and its function attributes are set outside the capture)."""
@@ -212,8 +252,14 @@ class ParametricEditEngine:
             self._step()
         self.graph = g
 
+    @_on_own_device
     def advance(self, n_steps: int) -> None:
-        """Run n_steps optimisation steps: the very first step of an engine eagerly, the rest as CUDA-graph replays."""
+        """Run n_steps optimisation steps: the very first step of an engine eagerly, the rest as CUDA-graph replays.
+        The device step counter indexes the per-step tables (offsets, schedule, logs): never step past num_steps."""
+        if self.steps_done + n_steps > self.steps:
+            raise _lib.RgieError(f"advance({n_steps}): {self.steps_done} of {self.steps} steps already done "
+                                 f"(load_problem() starts a new run)")
+        self.steps_done += n_steps
         done = 0
         if self.use_graph and self.graph is None and n_steps > 0:
             self._step()
@@ -227,6 +273,23 @@ class ParametricEditEngine:
             else:
                 self._step()
 
+    @_on_own_device
+    def probe_gradient(self, x: torch.Tensor, step: int) -> Dict[str, torch.Tensor]:
+        """Diagnostic (teacher forcing): evaluate the objective and d(loss)/d(x) of all B problems AT the given raw
+        parameter vectors x [B,NP] with the crop draws of optimisation step `step`, without touching the run state that
+        matters afterwards (x, Adam moments, best-x and the counter are restored).  Returns loss [B], preds, grad [B,NP]."""
+        if not 0 <= step < self.steps:
+            raise _lib.RgieError(f"probe_gradient: step {step} outside [0, {self.steps})")
+        keep = [t.clone() for t in (self.x, self.m, self.v, self.best_x, self.best_loss, self.best_step, self.counter)]
+        self.x.copy_(x.to(self.dev).reshape(-1, self.NP).expand(self.B, self.NP))
+        self.counter.fill_(step)
+        self._step()
+        out = dict(loss=self.loss.clone(), preds=self.preds.clone(), grad=self.gp.clone())
+        for dst, src in zip((self.x, self.m, self.v, self.best_x, self.best_loss, self.best_step, self.counter), keep):
+            dst.copy_(src)
+        return out
+
+    @_on_own_device
     def results(self) -> Dict[str, torch.Tensor]:
         """Edited images from best_x (optimize_image.py:97 returns best_x; output_transform re-applies the filters)."""
         lib, st = self.lib, self._st()

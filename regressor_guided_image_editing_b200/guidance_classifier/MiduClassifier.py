@@ -24,12 +24,28 @@ from .GuidanceClassifier import GuidanceClassifier
 DEFAULT_PRECISION = os.environ.get("RGIE_PRECISION", "bf16")
 
 
+class _MiduHandle:
+    """Owns one native head handle; destroyed when the last reference (the cache or an autograd ctx) goes away, so a
+    backward can never run on a handle that a later forward with another batch size / new weights replaced."""
+
+    def __init__(self, h: C.c_void_p, n_out: int):
+        self.h, self.n_out, self.generation = h, n_out, 0
+
+    def __del__(self):
+        try:
+            if self.h:
+                _lib.load().rgie_midu_destroy(self.h)
+                self.h = C.c_void_p(0)
+        except Exception:
+            pass
+
+
 class NativeMiduHead:
     """librgie.so handle for the SD / SDXL head, rebuilt when the batch size or the weights change."""
 
     def __init__(self, model: nn.Sequential, precision: str, is_sdxl: bool = False):
         self.model, self.precision, self.is_sdxl = model, precision, is_sdxl
-        self._h, self._key = C.c_void_p(0), None
+        self._cur, self._key = None, None
 
     def _weights_version(self):
         return tuple(p._version for p in self.model.parameters()) + tuple(p.data_ptr() for p in self.model.parameters())
@@ -37,28 +53,21 @@ class NativeMiduHead:
     def handle(self, batch: int, hw: int):
         key = (batch, hw, self._weights_version())
         if key != self._key:
-            self.close()
+            self._cur = None                       # an autograd ctx that still needs the old handle keeps it alive
             sd = self.model.state_dict()
             layers = ["0", "3", "6", "9", "13", "15"] if self.is_sdxl else ["0", "3", "7", "9"]   # convs then the two linears
             names = [f"{l}.{k}" for l in layers for k in ("weight", "bias")]
             arrs = [np.ascontiguousarray(sd[n].detach().float().cpu().numpy()) for n in names]
             pt = (C.c_void_p * len(arrs))(*[a.ctypes.data_as(C.c_void_p) for a in arrs])
             n_out = int(sd[layers[-1] + ".weight"].shape[0])
+            h = C.c_void_p(0)
             check(_lib.load().rgie_midu_create(pt, len(arrs), n_out, batch, hw, _lib.PRECISIONS[self.precision],
-                                               C.byref(self._h)), "rgie_midu_create")
-            self._key, self.n_out = key, n_out
-        return self._h
+                                               C.byref(h)), "rgie_midu_create")
+            self._cur, self._key, self.n_out = _MiduHandle(h, n_out), key, n_out
+        return self._cur
 
     def close(self):
-        if self._h:
-            _lib.load().rgie_midu_destroy(self._h)
-            self._h = C.c_void_p(0)
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
+        self._cur, self._key = None, None
 
 
 class _MiduHeadFn(torch.autograd.Function):
@@ -70,16 +79,26 @@ class _MiduHeadFn(torch.autograd.Function):
         B, Cc, H, W = f.shape
         if Cc != 1280 or H != W:
             raise _lib.RgieError(f"unexpected mid-block feature shape {tuple(f.shape)}")
-        h = head.handle(B, H)
-        pred = torch.empty(B, head.n_out, dtype=torch.float32, device=f.device)
-        check(_lib.load().rgie_midu_forward(h, ptr(f), B, ptr(pred), stream_ptr(f.device)), "rgie_midu_forward")
-        ctx.head_handle, ctx.shape, ctx.in_dtype = h, f.shape, feat.dtype
+        hd = head.handle(B, H)
+        pred = torch.empty(B, hd.n_out, dtype=torch.float32, device=f.device)
+        check(_lib.load().rgie_midu_forward(hd.h, ptr(f), B, ptr(pred), stream_ptr(f.device)), "rgie_midu_forward")
+        hd.generation += 1
+        # the handle holds the activations of its last forward only: keep the object (not the raw pointer) and the input
+        ctx.hd, ctx.generation, ctx.feat = hd, hd.generation, f
+        ctx.shape, ctx.in_dtype = f.shape, feat.dtype
         return pred
 
     @staticmethod
     def backward(ctx, dpred):
+        hd = ctx.hd
+        if hd.generation != ctx.generation:        # another forward ran on this handle in between: restore its state
+            scratch = torch.empty(ctx.shape[0], hd.n_out, dtype=torch.float32, device=dpred.device)
+            check(_lib.load().rgie_midu_forward(hd.h, ptr(ctx.feat), ctx.shape[0], ptr(scratch), stream_ptr(dpred.device)),
+                  "rgie_midu_forward")
+            hd.generation += 1
+            ctx.generation = hd.generation
         dfeat = torch.empty(ctx.shape, dtype=torch.float32, device=dpred.device)
-        check(_lib.load().rgie_midu_backward(ctx.head_handle, ptr(dpred.contiguous().float()), ptr(dfeat),
+        check(_lib.load().rgie_midu_backward(hd.h, ptr(dpred.contiguous().float()), ptr(dfeat),
                                              stream_ptr(dpred.device)), "rgie_midu_backward")
         return dfeat.to(ctx.in_dtype), None
 

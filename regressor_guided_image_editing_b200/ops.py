@@ -165,6 +165,7 @@ class Regressor:
                                                     _lib.PRECISIONS[precision], C.byref(self._h)),
                   "rgie_regressor_create")
         self._arrs = None
+        self.generation = 0          # number of forwards run on this handle (backward belongs to the last one)
 
     def __del__(self):
         try:
@@ -193,6 +194,7 @@ class Regressor:
         # (crop_grad_gather_kernel reads them): hold the tensors so that a caller's temporaries cannot be recycled by the
         # caching allocator between forward and backward
         self._fwd_refs = (img, offsets, step_ptr)
+        self.generation += 1
         return logits
 
     def set_input_transform(self, pre_scale: float, pre_shift: float, mean, std) -> None:

@@ -44,8 +44,9 @@ def gather_to_rank0(local: Dict[str, torch.Tensor], counts: Optional[List[int]] 
     for k, v in local.items():
         pad = torch.zeros((n_max,) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
         pad[:v.shape[0]] = v
-        bufs = [torch.zeros_like(pad) for _ in range(world)]
-        dist.all_gather(bufs, pad, group=group)
+        # a true gather: only rank 0 holds the receive buffers (N x 3 x H x W edited images are the bulk of the job's output)
+        bufs = [torch.zeros_like(pad) for _ in range(world)] if rank == 0 else None
+        dist.gather(pad, gather_list=bufs, dst=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         if rank == 0:
             out[k] = torch.cat([b[:n] for b, n in zip(bufs, ns)], 0)
     return out if rank == 0 else None

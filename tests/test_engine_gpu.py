@@ -176,3 +176,150 @@ def test_dropin_optimization_fused_and_generic_paths(sd):
     assert (best_f[:37] - ref["best_x"][:37]).abs().max().item() <= 1e-4, (best_f, ref["best_x"])
     assert (best_g[:37] - ref["best_x"][:37]).abs().max().item() <= 1e-4, (best_g, ref["best_x"])
     assert (best_f[:37] - best_g[:37]).abs().max().item() <= 1e-5
+
+
+# =================================================================================================================
+# Teacher-forced gradients, the kink-free full trajectory and the headline shape ("parity gap on the loop")
+# =================================================================================================================
+LAYOUT = dict(exposure=(0, 1), saturation=(1, 1), tone=(2, 8), color=(10, 24), contrast=(34, 1), sharp=(35, 1), blur=(36, 1),
+              scale=(37, 4))
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name))
+
+
+def _engine_for(sd, gold, precision, batch=1, micro_batch=None, slot=0):
+    """Engine of `batch` problems whose problem `slot` is the golden's image (the others are other synthetic images)."""
+    from regressor_guided_image_editing_b200 import engine
+    h, w, steps = gold["h"], gold["w"], gold["num_steps"]
+    eng = engine.ParametricEditEngine(sd, batch=batch, height=h, width=w, num_steps=steps, precision=precision,
+                                      micro_batch=micro_batch)
+    imgs = torch.stack([O.synthetic_image(gold["image_index"] if b == slot else 100 + b, h, w) for b in range(batch)])
+    g = torch.Generator().manual_seed(77)
+    offs = torch.randint(0, eng.Hr - 448 + 1, (1 + steps, batch, 10, 2), generator=g, dtype=torch.int32)
+    offs[:, slot] = gold["offsets"][:, 0]
+    x0 = gold.get("x0", None)
+    eng.load_problem(imgs.to(DEV), offs.to(DEV), alpha=gold["alpha"], learning_rate=gold["learning_rate"],
+                     weight_clf=gold["weight_clf"], x0=x0)
+    return eng
+
+
+def _per_filter_rel(g_mine, g_ref, skip=()):
+    """max over filters of |g_mine - g_ref|_inf / |g_ref|_inf (per filter block); returns (worst, table)."""
+    table, worst = {}, 0.0
+    for name, (o, n) in LAYOUT.items():
+        a, b = g_mine[o:o + n], g_ref[o:o + n]
+        scale = b.abs().max().item()
+        err = (a - b).abs().max().item()
+        rel = err / scale if scale > 0 else (0.0 if err == 0 else float("inf"))
+        table[name] = (err, scale, rel)
+        if name not in skip:
+            worst = max(worst, rel)
+    return worst, table
+
+
+@pytest.mark.parametrize("gname,precision,tol", [
+    ("loop_c1.pt", "fp32", 1e-3), ("loop_c1k.pt", "fp32", 1e-3),
+    ("loop_c1.pt", "bf16", 0.35), ("loop_c1k.pt", "bf16", 0.35)])
+def test_teacher_forced_parameter_gradients(sd, golden_dir, gname, precision, tol):
+    """ONE engine step AT the reference's own x (golden xs[s]) with the reference's crop draws of step s: the 41-vector
+    d(loss)/d(x) the optimiser consumes, per filter, against the reference's autograd.grad at the same point.  This
+    separates 'a d(param) error' from 'trajectory sensitivity': no Adam, no history.
+      fp32 mode: relative error per filter block <= 1e-3 (of the block's largest |gradient|).
+      bf16 mode: reported; bounded at 35 % of the block's largest |gradient| (bf16 activations + bf16 gradients through 53
+                 convs; the optimiser's direction is what has to survive, test_loop_* bound the resulting trajectory).
+    Excluded only where the reference's value is itself decided by round-off (tests/test_filters_gpu.py): the scale block
+    while scale sits EXACTLY at identity (golden c1, every step whose xs has scale == (1,1,0,0))."""
+    gold = _load(golden_dir, gname)
+    eng = _engine_for(sd, gold, precision)
+    assert (eng.target.cpu() - gold["target"]).abs().max().item() <= (1e-5 if precision == "fp32" else 1e-2)
+    eng.target.copy_(gold["target"].to(DEV))            # teacher forcing: the reference's own target, too
+    worst_all = 0.0
+    for s in (0, 1, 2, 5, 10, 25, 40, 49):
+        x = gold["xs"][s]
+        out = eng.probe_gradient(x, s)
+        g_mine, g_ref = out["grad"][0].cpu(), gold["grads"][s]
+        at_identity = torch.equal(x[37:41], torch.tensor([1.0, 1.0, 0.0, 0.0]))
+        worst, table = _per_filter_rel(g_mine, g_ref, skip=("scale",) if at_identity else ())
+        dl = abs(out["loss"][0].item() - gold["losses"][s].item())
+        print(f"{gname} {precision} step {s:2d}: |dloss| {dl:.2e}  " +
+              "  ".join(f"{k} {v[2]:.1e}" for k, v in table.items()) + ("  [scale at identity: excluded]" if at_identity else ""))
+        assert dl <= (2e-6 if precision == "fp32" else 2e-4), (s, dl)
+        assert worst <= tol, (s, table)
+        worst_all = max(worst_all, worst)
+    print(f"{gname} {precision}: worst per-filter relative gradient error {worst_all:.3e}")
+
+
+def test_loop_c1k_fp32_full_trajectory_and_edited_image(sd, golden_dir):
+    """configs[0] from a start point NEXT to the identity presets (sharp 0.3, scale (1.05, 1.03, 3, 5)): no parameter sits
+    on a kink, so the WHOLE loop must reproduce the reference's CPU run -- all 50 parameter vectors, best_x and the
+    engine's own edited image (north_star: max-abs pixel error <= 1e-3 in fp32 mode)."""
+    gold = _load(golden_dir, "loop_c1k.pt")
+    eng = _engine_for(sd, gold, "fp32")
+    eng.advance(gold["num_steps"])
+    torch.cuda.synchronize()
+    out = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in eng.results().items()}
+    dl = (out["losses"][:, 0] - gold["losses"]).abs()
+    dp = (out["preds"][:, 0, :2] - gold["preds"]).abs().max(1).values
+    dx = (out["xs"][:, 0] - gold["xs"]).abs().max(1).values
+    print("c1k fp32 per-step |dx|   :", [f"{v:.1e}" for v in dx.tolist()])
+    print("c1k fp32 per-step |dloss|:", [f"{v:.1e}" for v in dl.tolist()])
+    err_img = (out["edited"][0] - gold["edited"][0]).abs()
+    print(f"c1k fp32: max|dx| {dx.max().item():.3e}  |d best_x| {(out['best_x'][0] - gold['best_x']).abs().max().item():.3e}  "
+          f"edited max-abs {err_img.max().item():.3e} mean-abs {err_img.mean().item():.3e}")
+    assert dl.max().item() <= 5e-6 and dp.max().item() <= 2e-4
+    assert dx.max().item() <= 1e-3, "parameter trajectory"
+    assert (out["best_x"][0] - gold["best_x"]).abs().max().item() <= 1e-3
+    assert err_img.max().item() <= 1e-3, "edited image (engine's own best_x through its own filters) vs the reference's"
+
+
+def test_loop_c1k_bf16_trajectory_bound(sd, golden_dir):
+    """Same run on the tcgen05 bf16 regressor.  Stated bound: parameters within 0.05 of the reference's over all 50
+    steps (Adam moves a parameter by <= lr = 0.05 per step), per-step loss within 2e-4, predictions within 1e-2, edited
+    image mean-abs <= 5e-3 and max-abs <= 0.1."""
+    gold = _load(golden_dir, "loop_c1k.pt")
+    eng = _engine_for(sd, gold, "bf16")
+    eng.advance(gold["num_steps"])
+    torch.cuda.synchronize()
+    out = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in eng.results().items()}
+    dl = (out["losses"][:, 0] - gold["losses"]).abs()
+    dp = (out["preds"][:, 0, :2] - gold["preds"]).abs().max(1).values
+    dx = (out["xs"][:, 0] - gold["xs"]).abs().max(1).values
+    err_img = (out["edited"][0] - gold["edited"][0]).abs()
+    print("c1k bf16 per-step |dx|:", [f"{v:.1e}" for v in dx.tolist()])
+    print(f"c1k bf16: max|dx| {dx.max().item():.3e} max|dloss| {dl.max().item():.3e} max|dpred| {dp.max().item():.3e} "
+          f"edited max-abs {err_img.max().item():.3e} mean-abs {err_img.mean().item():.3e}")
+    assert dl.max().item() <= 2e-4 and dp.max().item() <= 1e-2
+    assert dx.max().item() <= 0.05
+    assert err_img.mean().item() <= 5e-3 and err_img.max().item() <= 0.1
+
+
+@pytest.mark.parametrize("precision,batch,mb,slot", [("bf16", 64, 32, 37), ("fp32", 2, 1, 1)])
+def test_headline_shape_against_reference_golden(sd, golden_dir, precision, batch, mb, slot):
+    """BASELINE.json configs[1] shape: one 512x512 image x 3 steps of the REFERENCE (tests/golden/loop_c2_3steps.pt, start
+    point with a real blur sigma) as problem `slot` of a batch-64 / micro-batch-32 bf16 engine (CTA-pair kernels, 512 -> 480
+    down-resize, second micro-batch), and of a small fp32 engine: per-step losses, predictions, parameters and the
+    teacher-forced d(x)."""
+    gold = _load(golden_dir, "loop_c2_3steps.pt")
+    eng = _engine_for(sd, gold, precision, batch=batch, micro_batch=mb, slot=slot)
+    tol = dict(loss=2e-6, pred=2e-4, x=1e-4, grad=1e-3) if precision == "fp32" else dict(loss=2e-4, pred=1e-2, x=0.05, grad=0.35)
+    assert (eng.target[slot].cpu() - gold["target"][0]).abs().max().item() <= tol["pred"]
+    for s in range(gold["num_steps"]):
+        xs = eng.x.clone()
+        xs[slot] = gold["xs"][s].to(DEV)
+        out = eng.probe_gradient(xs, s)
+        worst, table = _per_filter_rel(out["grad"][slot].cpu(), gold["grads"][s])
+        print(f"512^2 {precision} step {s}: " + "  ".join(f"{k} {v[2]:.1e}" for k, v in table.items()))
+        assert worst <= tol["grad"], (s, table)
+    eng.advance(gold["num_steps"])
+    torch.cuda.synchronize()
+    out = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in eng.results().items()}
+    dl = (out["losses"][:, slot] - gold["losses"]).abs().max().item()
+    dp = (out["preds"][:, slot, :2] - gold["preds"]).abs().max().item()
+    dx = (out["xs"][:, slot] - gold["xs"]).abs().max().item()
+    print(f"512^2 {precision} batch {batch}/mb {mb}: max|dloss| {dl:.2e} max|dpred| {dp:.2e} max|dx| {dx:.2e}")
+    assert dl <= tol["loss"] and dp <= tol["pred"] and dx <= tol["x"]
+    if precision == "fp32":
+        err = (out["edited"][slot][..., ::4, ::4] - gold["edited"][0]).abs().max().item()
+        assert err <= 1e-3, err

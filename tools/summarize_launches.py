@@ -46,6 +46,11 @@ for k, v in sorted(fam.items(), key=lambda kv: -kv[1][1]):
     print(f"{v[1]:10.1f} us {100 * v[1] / tot:5.1f}%  x{v[0]:3d}  {v[2] / 1e9:7.3f} GB  {k}")
 if "--json" in sys.argv:
     out = sys.argv[sys.argv.index("--json") + 1]
-    json.dump({"step_launches": len(step), "step_us": tot, "gemm_launches": gemm_n, "gemm_us": gemm, "gemm_share": gemm / tot,
+    import hashlib, os
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "regressor_guided_image_editing_b200", "librgie.so")
+    sha = hashlib.sha256(open(so, "rb").read()).hexdigest()[:16] if os.path.exists(so) else None
+    if "--sha" in sys.argv:          # the build that was profiled, when the in-tree library has been rebuilt since (bench.py prints lib_sha256)
+        sha = sys.argv[sys.argv.index("--sha") + 1]
+    json.dump({"lib_sha256": sha, "step_launches": len(step), "step_us": tot, "gemm_launches": gemm_n, "gemm_us": gemm, "gemm_share": gemm / tot,
                "gemm_dram_bytes": gemm_b, "gemm_dram_bytes_per_launch": gemm_b / max(gemm_n, 1),
                "families": {k: {"launches": v[0], "us": v[1], "dram_bytes": v[2]} for k, v in fam.items()}}, open(out, "w"), indent=1)
