@@ -455,10 +455,20 @@ def main():
     ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ee0.record()
     eng.load_problem(images_h.to(dev, non_blocking=True), offs_h[:1 + eng.steps].to(dev, non_blocking=True))
+    # every step's loss vector is read back (the reference prints float(loss) per step); the read of step s is awaited
+    # while step s + 1 is already running (two pinned buffers), so the host round trip never idles the GPU
+    loss_hh = [loss_h, torch.empty_like(loss_h).pin_memory()]
+    evs = [torch.cuda.Event(), torch.cuda.Event()]
+    loss_trace = []
     for s in range(Ke):
         eng.advance(1)
-        loss_h.copy_(eng.loss, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
+        loss_hh[s & 1].copy_(eng.loss, non_blocking=True)
+        evs[s & 1].record()
+        if s > 0:
+            evs[(s - 1) & 1].synchronize()
+            loss_trace.append(float(loss_hh[(s - 1) & 1][0]))
+    evs[(Ke - 1) & 1].synchronize()
+    loss_trace.append(float(loss_hh[(Ke - 1) & 1][0]))
     res = eng.results()
     edited_h.copy_(res["edited"], non_blocking=True)
     preds_h.copy_(eng.preds, non_blocking=True)

@@ -132,8 +132,11 @@ def gen_regressor(r):
 # sigma down through 0 within ~20 steps and the REFERENCE itself turns NaN there (kornia's gaussian with sigma <= 0), and at
 # the preset 1e-4 d/d(sigma) underflows to exactly 0 in every implementation (a dead parameter, not a kink).  The short
 # 512x512 run does start from a real sigma so that the separable blur and its sigma-gradient are inside the loop test.
-KINK_FREE_X0 = dict(sharp=[0.3], scale=[1.05, 1.03, 3.0, 5.0])
-KINK_FREE_X0_BLUR = dict(sharp=[0.3], blur=[0.8], scale=[1.05, 1.03, 3.0, 5.0])
+# Scale values must be GENERIC: with sx = 1.05 = 21/20 and cx = 3 the sample position (x - cx) / sx + cx is an exact
+# integer for every 21st column (a whole family of pixels sits ON the bilinear kink, and the reference's own d/d(scale)
+# changes by 4-10 % between an fp32 and an fp64 evaluation of the same expression -- measured, tools/scale_kink_check.py).
+KINK_FREE_X0 = dict(sharp=[0.3], scale=[1.0537, 1.0311, 3.3, 5.7])
+KINK_FREE_X0_BLUR = dict(sharp=[0.3], blur=[0.8], scale=[1.0537, 1.0311, 3.3, 5.7])
 
 
 def gen_loop(r, h=256, w=256, num_steps=50, tag="c1", image_index=0, x0_override=None):

@@ -136,21 +136,6 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {   // arrives on
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                "h"((uint16_t)3) : "memory");
 }
-// ---- A operand from tensor memory (back-to-back GEMM): D[tmem] (+)= A[tmem] * B[smem]; the A fragment of one K = 16 step is
-// 128 lanes x 8 columns of packed bf16 pairs (lane = row, column c holds k = 2c, 2c + 1)
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
-      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
-               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -195,6 +180,12 @@ __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t* r) {
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
+}
+template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -1155,14 +1146,20 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 // Back-to-back GEMM: a 256-wide stage-1 tile (1x1 expansion + residual / second operand + ReLU / masks, exactly the lean
 // kernel's work) is ALSO the complete K = 256 operand row block of the next layer's 1x1 reduction (256 -> 64), so the
 // second GEMM runs on the tile while it is still on chip and the next layer never re-reads the 256-channel tensor from HBM:
-//   stage 1: acc1[128 x 256] = A * W1^T (+ A2 * W1b^T)      smem operands, TMEM columns [0, 256)
-//            epilogue 1 (16 warps): bias / residual / ReLU / masks -> bf16 -> global D  AND  tcgen05.st into TMEM columns
-//            [256, 384) as the packed bf16 A operand of stage 2
-//   stage 2: acc2[128 x 64] = that operand (TMEM) * W2^T     W2 (64 x 256, 32 KB) resident in smem, TMEM columns 384 + 64 * buf
-//            epilogue 2: bias2 / ReLU / bit mask -> bf16 -> global D2 (+ sign bits)
-// Barriers: full/empty ring as usual; acc1_full (commit); e1_done (16 warps: acc1 drained AND the stage-2 operand written);
-// acc2_full[2] (commit).  The MMA thread issues, per tile t: [wait e1_done(t-1); MMA2(t-1)]; MMA1(t) -- and the epilogue warps
-// run epilogue1(t), then epilogue2(t-1), so the second GEMM's latency hides behind the next tile's first epilogue.
+//   stage 1: acc1[128 x 256] = A * W1^T (+ A2 * W1b^T)      smem operands, TMEM columns [0, 256), ONE buffer
+//            epilogue 1 (16 warps, lean role): bias / residual / ReLU / masks -> bf16 -> four 128 x 64 SWIZZLE_128B boxes in
+//            shared memory (one per 64-column part).  A box is (a) the source of the TMA store that writes D, and (b) a
+//            K-major operand tile of stage 2 as it stands -- no tcgen05.st, no second copy.
+//   stage 2: acc2[128 x 64] += box_p (smem) * W2[:, 64 p ..]^T for p = 0..3;  W2 (64 x 256, 32 KB) resident in smem,
+//            TMEM columns 256 + 64 * buf (two buffers)
+//            epilogue 2 (the same 16 warps, 16 columns each): bias2 / ReLU / bit mask -> bf16 -> global D2 (+ sign bits)
+// acc1 has ONE buffer (2 x 256 + 2 x 64 columns do not fit in TMEM), but it is released as soon as the last tcgen05.ld of a
+// tile has completed (t1empty), i.e. before the last chunk's arithmetic, the box hand-over and epilogue 2 -- the MMAs of the
+// next tile (K = 64: 4 instructions) run underneath.  (Round 1's version released it after the whole epilogue and fed stage 2
+// from TMEM with tcgen05.st: tensor pipe 7 % active, 30 % of the epilogue samples at the accumulator barrier.)
+// MMA thread per tile t:  wait t1empty(t-1); MMA1(t); commit t1full;  then for p: wait bfull[p](t-1); MMA2(t-1, p); commit
+// bfree[p];  commit t2full(t-1).   Epilogue warps per tile t:  E1(t) (box p reusable once the TMA store of t-1 has read it
+// AND bfree[p](t-1)), then E2(t-1).
 // ===============================================================================================================
 struct B2bParams {
   const float* bias2;
@@ -1172,39 +1169,44 @@ struct B2bParams {
   uint32_t* D2_bits; int ld_db2;
 };
 constexpr int B2B_N2 = 64;
-constexpr int B2B_STAGES = 3;
+constexpr int B2B_STAGES = 2;
 struct SmemB2b {
   static constexpr int B_STAGE_BYTES = 256 * BK * 2;
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = B2B_STAGES * A_STAGE_BYTES;
   static constexpr int W2_OFF = B_OFF + B2B_STAGES * B_STAGE_BYTES;          // 4 k-blocks of [64 rows x 128 B]
   static constexpr int W2_BYTES = B2B_N2 * 256 * 2;
-  static constexpr int BAR_OFF = W2_OFF + W2_BYTES;                          // full[S], empty[S], acc1_full, e1_done, acc2_full[2], w2full
-  static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * B2B_STAGES + 6) * 8;
+  static constexpr int OB_OFF = W2_OFF + W2_BYTES;                           // 4 boxes of 128 rows x 128 B
+  static constexpr int BAR_OFF = OB_OFF + 4 * BM * 128;   // full[S], empty[S], t1full, t1empty, t2full[2], t2empty[2], bfull[4], bfree[4], w2full
+  static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * B2B_STAGES + 16) * 8;
   static constexpr int BIAS_OFF = (TMEM_PTR_OFF + 16 + 15) & ~15;
   static constexpr int BIAS2_OFF = BIAS_OFF + 256 * 4;
   static constexpr int TOTAL = BIAS2_OFF + B2B_N2 * 4;
   static constexpr int DYN_BYTES = TOTAL + 1024;
+  static_assert(OB_OFF % 1024 == 0 && W2_OFF % 1024 == 0, "operand tiles must be 1024-byte aligned");
   static_assert(DYN_BYTES <= 232448, "shared memory plan exceeds 227 KB");
 };
 
 __global__ void __launch_bounds__(640, 1)
 gemm_b2b_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmW2, const GemmDesc d,
-                const B2bParams q2, const int num_tiles) {
+                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmW2,
+                const __grid_constant__ CUtensorMap tmD, const GemmDesc d, const B2bParams q2, const int num_tiles) {
   using L = SmemB2b;
   constexpr int BN = 256, N2 = B2B_N2, STAGES = B2B_STAGES;
-  constexpr uint32_t A2_COL = 256, ACC2_COL = 384;
+  constexpr uint32_t ACC2_COL = 256;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_base + L::BAR_OFF;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  const uint32_t acc1_full = bar_base + 8u * (2 * STAGES);
-  const uint32_t e1_done = bar_base + 8u * (2 * STAGES + 1);
-  auto acc2_full = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
-  const uint32_t w2full = bar_base + 8u * (2 * STAGES + 4);
+  const uint32_t t1full = bar_base + 8u * (2 * STAGES);
+  const uint32_t t1empty = bar_base + 8u * (2 * STAGES + 1);
+  auto t2full = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+  auto t2empty = [&](int b) { return bar_base + 8u * (2 * STAGES + 4 + b); };
+  auto bfull = [&](int p) { return bar_base + 8u * (2 * STAGES + 6 + p); };
+  auto bfree = [&](int p) { return bar_base + 8u * (2 * STAGES + 10 + p); };
+  const uint32_t w2full = bar_base + 8u * (2 * STAGES + 14);
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_PTR_OFF);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -1217,14 +1219,21 @@ gemm_b2b_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA2) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmW2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmD) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(acc1_full, 1);
-    mbar_init(e1_done, 16);
-    mbar_init(acc2_full(0), 1);
-    mbar_init(acc2_full(1), 1);
+    mbar_init(t1full, 1);
+    mbar_init(t1empty, 16);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(t2full(b), 1);
+      mbar_init(t2empty(b), 16);
+    }
+    for (int p = 0; p < 4; ++p) {
+      mbar_init(bfull(p), 1);
+      mbar_init(bfree(p), 1);
+    }
     mbar_init(w2full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1256,45 +1265,55 @@ gemm_b2b_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const float* sbias2 = reinterpret_cast<const float*>(smem + L::BIAS2_OFF);
     const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(d.res);
     const uint32_t* mbits = d.mask_bits;
-    const long res_lim = d.res_rows < d.m_end ? d.res_rows : d.m_end;
+    const int m_end = (int)d.m_end;                    // all row indices are < 2^31 (checked where the plan is built)
+    const int res_lim = (int)(d.res_rows < d.m_end ? d.res_rows : d.m_end);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
-    long dest_prev = -1;
+    const uint32_t box = smem_base + L::OB_OFF + (uint32_t)(part * (BM * 128));
+    const uint32_t box_row = box + (uint32_t)row * 128u;
+    const uint32_t swz = (uint32_t)(row & 7);
+    const bool box_leader = qd == 0 && lane == 0;
+    const int bar_id = 1 + part;
+    int dest_prev = -1;
+    uint32_t wmask2_prev = 0xFFFFu;
 
-    auto stage2 = [&](int it_prev, long dest) {      // epilogue 2 of the tile handled one iteration ago
+    // wmask: this row's 16 stage-2 mask bits, loaded one tile earlier (an HBM latency the epilogue must not wait for)
+    auto stage2 = [&](int it_prev, int dest, uint32_t wmask) {      // epilogue 2 of the tile handled one iteration ago
       const int b = it_prev & 1;
-      mbar_wait(acc2_full(b), (uint32_t)((it_prev >> 1) & 1));
+      mbar_wait(t2full(b), (uint32_t)((it_prev >> 1) & 1));
       tcgen05_fence_after();
-      uint32_t r[CH];
-      tmem_ld<CH>(lane_addr + ACC2_COL + (uint32_t)(b * N2 + part * CH), r);
-      tmem_ld_wait();
-      if (dest >= 0) {
-        const int n0 = part * CH;
-        float v[CH];
+      const int n0 = part * CH;
+      uint32_t wout = 0u;
 #pragma unroll
-        for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]) + sbias2[n0 + j];
-        uint32_t wout = 0u;
-        if (q2.relu2) {
-#pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
-#pragma unroll
-          for (int j = CH - 1; j >= 0; --j) wout = push_positive_bit(wout, v[j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < CH; ++j) wout |= (v[j] > 0.f ? 1u : 0u) << j;
+      for (int h = 1; h >= 0; --h) {                 // two halves of 8 columns, upper half first (bit order of wout)
+        uint32_t r[8];
+        tmem_ld<8>(lane_addr + ACC2_COL + (uint32_t)(b * N2 + n0 + 8 * h), r);
+        tmem_ld_wait();
+        if (h == 0) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(t2empty(b));    // the accumulator is in registers: stage 2 of tile it_prev + 2 may overwrite it
         }
-        if (q2.mask_bits2 != nullptr) {
-          const uint32_t w = (__ldg(q2.mask_bits2 + bits_index(dest, n0 / 32, q2.ld_mb2)) >> (16 * (part & 1))) & 0xFFFFu;
-          wout &= w;
+        if (dest >= 0) {
+          uint32_t pk[4];
 #pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] = keep_if_bit(v[j], w, j);
+          for (int j = 3; j >= 0; --j) {
+            const int c = 8 * h + 2 * j;
+            float hi = __uint_as_float(r[2 * j + 1]) + sbias2[n0 + c + 1], lo = __uint_as_float(r[2 * j]) + sbias2[n0 + c];
+            if (q2.relu2) {
+              hi = fmaxf(hi, 0.f); lo = fmaxf(lo, 0.f);
+              wout = push_positive_bit(push_positive_bit(wout, hi), lo);
+            } else {
+              wout = (wout << 2) | (hi > 0.f ? 2u : 0u) | (lo > 0.f ? 1u : 0u);
+            }
+            hi = keep_if_bit(hi, wmask, c + 1); lo = keep_if_bit(lo, wmask, c);
+            pk[j] = pack_bf16x2(lo, hi);
+          }
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(q2.D2) + (long)dest * q2.ldd2 + n0 + 8 * h) =
+              make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
-        uint32_t pk[CH / 2];
-#pragma unroll
-        for (int j = 0; j < CH / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-        stg256(reinterpret_cast<__nv_bfloat16*>(q2.D2) + dest * q2.ldd2 + n0, pk);
-        if (q2.D2_bits != nullptr)
-          reinterpret_cast<uint16_t*>(q2.D2_bits + bits_index(dest, n0 / 32, q2.ld_db2))[part & 1] = (uint16_t)wout;
       }
+      if (dest >= 0 && q2.D2_bits != nullptr)
+        reinterpret_cast<uint16_t*>(q2.D2_bits + bits_index(dest, n0 / 32, q2.ld_db2))[part & 1] = (uint16_t)(wout & wmask);
     };
 
     // residual row and mask words of the NEXT tile are fetched while epilogue 2 of the previous one runs
@@ -1303,12 +1322,12 @@ gemm_b2b_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     auto prefetch = [&](int tile) {
       bits_nxt0 = bits_nxt1 = 0u;
       if (tile >= num_tiles) return;
-      const long m = d.m_begin + (long)tile * BM + row;
+      const int m = (int)d.m_begin + tile * BM + row;
       if (res != nullptr && m < res_lim) {
 #pragma unroll
-        for (int ci = 0; ci < CPW; ++ci) ldg256(res + m * d.ld_res + col0 + ci * CH, rbuf[ci]);
+        for (int ci = 0; ci < CPW; ++ci) ldg256(res + (long)m * d.ld_res + col0 + ci * CH, rbuf[ci]);
       }
-      if (mbits != nullptr && m < d.m_end) {
+      if (mbits != nullptr && m < m_end) {
         bits_nxt0 = __ldg(mbits + bits_index(m, col0 / 32, d.ld_mb));
         bits_nxt1 = __ldg(mbits + bits_index(m, col0 / 32 + 1, d.ld_mb));
       }
@@ -1316,64 +1335,94 @@ gemm_b2b_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     prefetch(blockIdx.x);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const long m = d.m_begin + (long)tile * BM + row;
-      long dest = -1;
-      if (m < d.m_end) dest = map_row(d.src, d.dst_kind, d.dst, m);
+      const int m0 = (int)d.m_begin + tile * BM;
+      const int m = m0 + row;
+      int dest = -1;                                       // DST_SAME: the destination row is the source row (pad rows: none)
+      if (m < m_end) dest = (int)map_row(d.src, d.dst_kind, d.dst, m);
       const bool live = dest >= 0;
-      const bool use_res = res != nullptr && m < res_lim;
+      const bool use_res = live && res != nullptr && m < res_lim;
       const uint32_t bits_cur0 = bits_nxt0, bits_cur1 = bits_nxt1;
       uint32_t bits_out0 = 0u, bits_out1 = 0u;
-      mbar_wait(acc1_full, (uint32_t)(it & 1));
+      uint32_t wmask2 = 0xFFFFu;
+      if (live && q2.mask_bits2 != nullptr)
+        wmask2 = (__ldg(q2.mask_bits2 + bits_index(dest, (part * CH) / 32, q2.ld_mb2)) >> (16 * (part & 1))) & 0xFFFFu;
+      mbar_wait(t1full, (uint32_t)(it & 1));
       tcgen05_fence_after();
+      if (it > 0) {
+        if (box_leader) {
+          bulk_wait_read0();                                   // the TMA store of the previous tile has read the box ...
+          mbar_wait(bfree(part), (uint32_t)((it - 1) & 1));    // ... and so have the stage-2 MMAs of the previous tile
+        }
+        named_bar_sync(bar_id, 128);
+      }
 #pragma unroll
       for (int ci = 0; ci < CPW; ++ci) {
         uint32_t r[CH];
         tmem_ld<CH>(lane_addr + (uint32_t)(col0 + ci * CH), r);
         tmem_ld_wait();
+        if (ci == CPW - 1) {
+          // this warp's part of acc1 is in registers: once all 16 warps are here the next tile's MMAs may overwrite it
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(t1empty);
+        }
         const int n0 = col0 + ci * CH;
-        float v[CH];
+        if (live) {
+          float v[CH];
 #pragma unroll
-        for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]) + sbias[n0 + j];
-        if (use_res) {
+          for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]) + sbias[n0 + j];
+          if (use_res) {
 #pragma unroll
-          for (int j = 0; j < CH / 2; ++j) { v[2 * j] += bf16_lo(rbuf[ci][j]); v[2 * j + 1] += bf16_hi(rbuf[ci][j]); }
-        }
-        uint32_t wout = 0u;
-        if (d.relu) {
+            for (int j = 0; j < CH / 2; ++j) { v[2 * j] += bf16_lo(rbuf[ci][j]); v[2 * j + 1] += bf16_hi(rbuf[ci][j]); }
+          }
+          uint32_t wout = 0u;
+          if (d.relu) {
 #pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
+            for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
+            if (d.D_bits != nullptr) {
 #pragma unroll
-          for (int j = CH - 1; j >= 0; --j) wout = push_positive_bit(wout, v[j]);
+              for (int j = CH - 1; j >= 0; --j) wout = push_positive_bit(wout, v[j]);
+            }
+          } else if (d.D_bits != nullptr) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) wout |= (v[j] > 0.f ? 1u : 0u) << j;
+          }
+          if (mbits != nullptr) {
+            const uint32_t w = ((ci < 2 ? bits_cur0 : bits_cur1) >> (16 * (ci & 1))) & 0xFFFFu;
+            wout &= w;
+#pragma unroll
+            for (int j = 0; j < CH; ++j) v[j] = keep_if_bit(v[j], w, j);
+          }
+          if (ci < 2) bits_out0 |= wout << (16 * (ci & 1)); else bits_out1 |= wout << (16 * (ci & 1));
+          uint32_t pk[CH / 2];
+#pragma unroll
+          for (int j = 0; j < CH / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          sts128(box_row + (((uint32_t)(2 * ci) ^ swz) << 4), pk);
+          sts128(box_row + (((uint32_t)(2 * ci + 1) ^ swz) << 4), pk + 4);
         } else {
-#pragma unroll
-          for (int j = 0; j < CH; ++j) wout |= (v[j] > 0.f ? 1u : 0u) << j;
+          const uint32_t z[4] = {0u, 0u, 0u, 0u};       // pad rows / rows past the end: zero in D and zero in the stage-2 operand
+          sts128(box_row + (((uint32_t)(2 * ci) ^ swz) << 4), z);
+          sts128(box_row + (((uint32_t)(2 * ci + 1) ^ swz) << 4), z);
         }
-        if (mbits != nullptr) {
-          const uint32_t w = ((ci < 2 ? bits_cur0 : bits_cur1) >> (16 * (ci & 1))) & 0xFFFFu;
-          wout &= w;
-#pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] = keep_if_bit(v[j], w, j);
-        }
-        if (ci < 2) bits_out0 |= wout << (16 * (ci & 1)); else bits_out1 |= wout << (16 * (ci & 1));
-        uint32_t pk[CH / 2];
-#pragma unroll
-        for (int j = 0; j < CH / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-        tmem_st8(lane_addr + A2_COL + (uint32_t)(n0 / 2), pk);          // stage-2 operand: the ROUNDED values the next layer reads
-        if (live) stg256(reinterpret_cast<__nv_bfloat16*>(d.D) + dest * d.ldd + n0, pk);
+      }
+      fence_async_smem();                        // the box is read by the async proxy (TMA store, tcgen05.mma)
+      named_bar_sync(bar_id, 128);
+      if (box_leader) {
+        tma_store_2d(&tmD, box, col0, m0);
+        bulk_commit();
+        mbar_arrive(bfull(part));
       }
       if (live && d.D_bits != nullptr) {
         d.D_bits[bits_index(dest, col0 / 32, d.ld_db)] = bits_out0;
         d.D_bits[bits_index(dest, col0 / 32 + 1, d.ld_db)] = bits_out1;
       }
-      tmem_st_wait();
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(e1_done);
       prefetch(tile + gridDim.x);
-      if (it > 0) stage2(it - 1, dest_prev);
+      if (it > 0) stage2(it - 1, dest_prev, wmask2_prev);
       dest_prev = dest;
+      wmask2_prev = wmask2;
     }
-    if (it > 0) stage2(it - 1, dest_prev);
+    if (it > 0) stage2(it - 1, dest_prev, wmask2_prev);
+    if (box_leader) bulk_wait0();
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == 0) {
@@ -1412,15 +1461,21 @@ gemm_b2b_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         constexpr uint32_t idesc1 = make_idesc(BM, BN);
         constexpr uint32_t idesc2 = make_idesc(BM, N2);
         auto issue_stage2 = [&](int it_prev) {
-          mbar_wait(e1_done, (uint32_t)(it_prev & 1));
-          tcgen05_fence_after();
-          const uint32_t tmem_d2 = tmem_base + ACC2_COL + (uint32_t)((it_prev & 1) * N2);
+          const int b = it_prev & 1;
+          mbar_wait(t2empty(b), (uint32_t)(((it_prev >> 1) & 1) ^ 1));      // epilogue 2 of tile it_prev - 2 has drained this buffer
+          const uint32_t tmem_d2 = tmem_base + ACC2_COL + (uint32_t)(b * N2);
+#pragma unroll 1
+          for (int p = 0; p < 4; ++p) {
+            mbar_wait(bfull(p), (uint32_t)(it_prev & 1));
+            tcgen05_fence_after();
+            const uint64_t adesc = make_smem_desc(smem_base + L::OB_OFF + p * (BM * 128));
+            const uint64_t bdesc = make_smem_desc(smem_base + L::W2_OFF + p * (N2 * 128));
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const uint64_t bdesc = make_smem_desc(smem_base + L::W2_OFF + (k >> 2) * (N2 * 128)) + (uint64_t)(2 * (k & 3));
-            umma_bf16_ts(tmem_d2, tmem_base + A2_COL + (uint32_t)(8 * k), bdesc, idesc2, k != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(tmem_d2, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc2, (p | k) != 0 ? 1u : 0u);
+            umma_commit(bfree(p));                   // box p may be overwritten once these MMAs have read it
           }
-          umma_commit(acc2_full(it_prev & 1));
+          umma_commit(t2full(b));
         };
         mbar_wait(w2full, 0);
         int stage = 0;
@@ -1429,7 +1484,8 @@ gemm_b2b_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
           const long m0 = d.m_begin + (long)tile * BM;
           const int kb_total = num_kb + (m0 < d.a2_rows ? num_kb2 : 0);
-          if (it > 0) issue_stage2(it - 1);          // also the point where acc1 is free again
+          mbar_wait(t1empty, (uint32_t)((it & 1) ^ 1));       // all 16 epilogue warps hold tile it - 1's accumulator in registers
+          tcgen05_fence_after();
           for (int kb = 0; kb < kb_total; ++kb) {
             mbar_wait(full_bar(stage), phase);
             tcgen05_fence_after();
@@ -1441,7 +1497,8 @@ gemm_b2b_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             umma_commit(empty_bar(stage));
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(acc1_full);
+          umma_commit(t1full);
+          if (it > 0) issue_stage2(it - 1);
         }
         if (it > 0) issue_stage2(it - 1);
       }
@@ -1872,7 +1929,7 @@ int run_b2b(const GemmPlanSm100& p, cudaStream_t st) {
   B2bParams q;
   q.bias2 = p.d2.bias; q.D2 = p.d2.D; q.ldd2 = p.d2.ldd; q.relu2 = p.d2.relu;
   q.mask_bits2 = p.d2.mask_bits; q.ld_mb2 = p.d2.ld_mb; q.D2_bits = p.d2.D_bits; q.ld_db2 = p.d2.ld_db;
-  gemm_b2b_kernel<<<p.grid, 640, SmemB2b::DYN_BYTES, st>>>(p.tmA, p.tmA2, p.tmB, p.tmW2, p.d, q, p.num_m_tiles);
+  gemm_b2b_kernel<<<p.grid, 640, SmemB2b::DYN_BYTES, st>>>(p.tmA, p.tmA2, p.tmB, p.tmW2, p.tmD, p.d, q, p.num_m_tiles);
   RGIE_LAUNCH_OK();
   return 0;
 }
@@ -2101,6 +2158,8 @@ int build_gemm_b2b_sm100(const GemmDesc& d1, const GemmDesc& d2, GemmPlanSm100* 
   if (d1.A2 != nullptr) rc = make_map_2d(&p->tmA2, d1.A2, (uint64_t)d1.Cin2, (uint64_t)d1.a2_rows, BK, BM);
   if (rc) return rc;
   rc = make_map_2d(&p->tmB, d1.Wt, (uint64_t)d1.ntaps * d1.Cin + (d1.A2 ? d1.Cin2 : 0), (uint64_t)d1.n_pad, BK, 256);
+  if (rc) return rc;
+  rc = make_map_2d(&p->tmD, d1.D, (uint64_t)d1.ldd, (uint64_t)d1.m_end, 64, BM, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   return make_map_2d(&p->tmW2, d2.Wt, 256, (uint64_t)B2B_N2, BK, (uint32_t)B2B_N2);
 }

@@ -205,12 +205,43 @@ def _engine_for(sd, gold, precision, batch=1, micro_batch=None, slot=0):
     return eng
 
 
-def _per_filter_rel(g_mine, g_ref, skip=()):
-    """max over filters of |g_mine - g_ref|_inf / |g_ref|_inf (per filter block); returns (worst, table)."""
+def _scale_rows_near_kink(p, h, w, eps):
+    """True when some row or column of the scale warp samples within `eps` pixels of a pixel centre (kornia scale ->
+    affine_grid / grid_sample, align_corners=True; same coordinate algebra as csrc/filters.cu: warp_coef / sample_coord)."""
+    sx, sy, cx, cy = [float(v) for v in p]
+    sx, sy = max(sx, 1.0), max(sy, 1.0)                                  # optimize_image_param.py:279-280
+    cx, cy = min(max(cx, 0.0), float(h)), min(max(cy, 0.0), float(h))
+    out = False
+    for n, s, c, t in ((w, sx, cx, (1.0 - sx) * cx), (h, sy, cy, (1.0 - sx) * cy)):
+        a = 2.0 / (n - 1)
+        g = torch.linspace(-1, 1, n, dtype=torch.float64) / s - (s + a * t - 1.0) / s
+        ix = (g + 1.0) * 0.5 * (n - 1)
+        inside = (ix > -1) & (ix < n)
+        d = (ix - ix.round()).abs()[inside]
+        out = out or bool((d < eps).any())
+    return out
+
+
+def _check_scale_block(table, x, gold, tol, s):
+    """scale: bilinear sampling of a NOISE image -- d/d(position) jumps wherever a sample point crosses a pixel centre, and
+    a whole row / column of sample points crosses together (the warp is separable).  A row whose floor() side is decided by
+    round-off changes d(scale) by ~1/sqrt(rows) of its size (tools/scale_kink_check.py: 4-10 % between an fp32 and an fp64
+    evaluation of the reference's own expression when rows sit exactly on pixel centres).  Bound: `tol` where no row / column
+    is within 1e-4 px of a pixel centre, max(tol, 0.15) otherwise; never checked at exact identity.  Returns the kink flag."""
+    at_identity = torch.equal(x[37:41], torch.tensor([1.0, 1.0, 0.0, 0.0]))
+    kink = at_identity or _scale_rows_near_kink(x[37:41], gold["h"], gold["w"], 1e-4)
+    if not at_identity:
+        tol_scale = tol if not kink else max(tol, 0.15)
+        assert table["scale"][2] <= tol_scale, (s, "scale", table["scale"], "near kink" if kink else "")
+    return kink
+
+
+def _per_filter_rel(g_mine, g_ref, skip=(), floor=0.0):
+    """max over filters of |g_mine - g_ref|_inf / (|g_ref|_inf + floor) (per filter block); returns (worst, table)."""
     table, worst = {}, 0.0
     for name, (o, n) in LAYOUT.items():
         a, b = g_mine[o:o + n], g_ref[o:o + n]
-        scale = b.abs().max().item()
+        scale = b.abs().max().item() + floor
         err = (a - b).abs().max().item()
         rel = err / scale if scale > 0 else (0.0 if err == 0 else float("inf"))
         table[name] = (err, scale, rel)
@@ -227,24 +258,29 @@ def test_teacher_forced_parameter_gradients(sd, golden_dir, gname, precision, to
     d(loss)/d(x) the optimiser consumes, per filter, against the reference's autograd.grad at the same point.  This
     separates 'a d(param) error' from 'trajectory sensitivity': no Adam, no history.
       fp32 mode: relative error per filter block <= 1e-3 (of the block's largest |gradient|).
-      bf16 mode: reported; bounded at 35 % of the block's largest |gradient| (bf16 activations + bf16 gradients through 53
-                 convs; the optimiser's direction is what has to survive, test_loop_* bound the resulting trajectory).
-    Excluded only where the reference's value is itself decided by round-off (tests/test_filters_gpu.py): the scale block
-    while scale sits EXACTLY at identity (golden c1, every step whose xs has scale == (1,1,0,0))."""
+      bf16 mode: reported; bounded at 35 % of (the block's largest |gradient| + 2 % of the largest |gradient| of step 0).
+                 bf16 activations + bf16 gradients through 53 convs leave an absolute noise floor of ~3e-6 on d(x) (0.4 % of
+                 the initial gradient): early steps come out within 2-10 %, and near convergence, where the true gradient
+                 falls below that floor, only the floor is meaningful.
+    The scale block is bounded separately (_check_scale_block): never at exact identity, loosely where a row / column of
+    sample points sits within 1e-4 px of a pixel centre, at the same tolerance everywhere else."""
     gold = _load(golden_dir, gname)
     eng = _engine_for(sd, gold, precision)
     assert (eng.target.cpu() - gold["target"]).abs().max().item() <= (1e-5 if precision == "fp32" else 1e-2)
     eng.target.copy_(gold["target"].to(DEV))            # teacher forcing: the reference's own target, too
     worst_all = 0.0
+    floor = 0.0 if precision == "fp32" else 0.02 * gold["grads"][0].abs().max().item()
     for s in (0, 1, 2, 5, 10, 25, 40, 49):
         x = gold["xs"][s]
         out = eng.probe_gradient(x, s)
         g_mine, g_ref = out["grad"][0].cpu(), gold["grads"][s]
         at_identity = torch.equal(x[37:41], torch.tensor([1.0, 1.0, 0.0, 0.0]))
-        worst, table = _per_filter_rel(g_mine, g_ref, skip=("scale",) if at_identity else ())
+        worst, table = _per_filter_rel(g_mine, g_ref, skip=("scale",), floor=floor)
+        kink = _check_scale_block(table, x, gold, tol, s)
         dl = abs(out["loss"][0].item() - gold["losses"][s].item())
         print(f"{gname} {precision} step {s:2d}: |dloss| {dl:.2e}  " +
-              "  ".join(f"{k} {v[2]:.1e}" for k, v in table.items()) + ("  [scale at identity: excluded]" if at_identity else ""))
+              "  ".join(f"{k} {v[2]:.1e}" for k, v in table.items()) +
+              ("  [scale at identity: excluded]" if at_identity else ("  [scale: a row/column within 1e-4 px of a kink]" if kink else "")))
         assert dl <= (2e-6 if precision == "fp32" else 2e-4), (s, dl)
         assert worst <= tol, (s, table)
         worst_all = max(worst_all, worst)
@@ -309,8 +345,10 @@ def test_headline_shape_against_reference_golden(sd, golden_dir, precision, batc
         xs = eng.x.clone()
         xs[slot] = gold["xs"][s].to(DEV)
         out = eng.probe_gradient(xs, s)
-        worst, table = _per_filter_rel(out["grad"][slot].cpu(), gold["grads"][s])
-        print(f"512^2 {precision} step {s}: " + "  ".join(f"{k} {v[2]:.1e}" for k, v in table.items()))
+        floor = 0.0 if precision == "fp32" else 0.02 * gold["grads"][0].abs().max().item()
+        worst, table = _per_filter_rel(out["grad"][slot].cpu(), gold["grads"][s], skip=("scale",), floor=floor)
+        kink = _check_scale_block(table, gold["xs"][s], gold, tol["grad"], s)
+        print(f"512^2 {precision} step {s}: " + "  ".join(f"{k} {v[2]:.1e}" for k, v in table.items()) + ("  [scale near a kink]" if kink else ""))
         assert worst <= tol["grad"], (s, table)
     eng.advance(gold["num_steps"])
     torch.cuda.synchronize()
