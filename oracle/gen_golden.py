@@ -3,7 +3,7 @@
 Generates tests/golden/*.pt by running the UNMODIFIED reference Python (imported from /root/reference/src through
 oracle/ref_harness.py) on CPU.  Run in the build container only:
 
-    python -m oracle.gen_golden [--only filters|regressor|loop|loopk|loop512|midu]
+    python -m oracle.gen_golden [--only filters|regressor|loop|loopk|loops|loop512|midu]
 
 The reference ships no tests/fixtures, so these vectors are the pin for the standalone oracle
 (oracle/oracle.py) and, through it, for the CUDA path.  Inputs are regenerated from seeds at test time; only outputs
@@ -139,7 +139,7 @@ KINK_FREE_X0 = dict(sharp=[0.3], scale=[1.0537, 1.0311, 3.3, 5.7])
 KINK_FREE_X0_BLUR = dict(sharp=[0.3], blur=[0.8], scale=[1.0537, 1.0311, 3.3, 5.7])
 
 
-def gen_loop(r, h=256, w=256, num_steps=50, tag="c1", image_index=0, x0_override=None):
+def gen_loop(r, h=256, w=256, num_steps=50, tag="c1", image_index=0, x0_override=None, smooth=False):
     """BASELINE.json configs[0]: one synthetic 256x256 image, random-init regressor, 50 steps, CPU.
     x0_override ({filter: values}) moves the start point off the identity presets: the scale filter's bilinear kink,
     the sharp == 0 and the blur sigma -> 0 branches all sit exactly AT the reference's start values, so a start point
@@ -147,7 +147,7 @@ def gen_loop(r, h=256, w=256, num_steps=50, tag="c1", image_index=0, x0_override
     Also stored: d(loss)/d(x) of every step (one extra autograd.grad per step on the reference's own graph)."""
     sd = O.make_regressor_state_dict()
     clf = _ref_clf(r, sd)
-    image = O.synthetic_image(image_index, h, w)[None]
+    image = (O.smooth_image if smooth else O.synthetic_image)(image_index, h, w)[None]
     torch.manual_seed(2000 + image_index)
     obj = {"clf": clf, "dis": None, "weight_clf": 0.15, "weight_dis": 0.0, "weight_recon": 0.0, "alpha": 0.1}
     x0, obj = r.optimize_image_param.initialize_parametric(image, obj)
@@ -177,7 +177,7 @@ def gen_loop(r, h=256, w=256, num_steps=50, tag="c1", image_index=0, x0_override
         edited = r.image_transformations.apply_params(image, px)[-1]
     torch.manual_seed(2000 + image_index)
     offs = O.draw_crop_offsets(1 + num_steps, 1, 480, 480)
-    out = dict(h=h, w=w, num_steps=num_steps, image_index=image_index, alpha=0.1, learning_rate=0.05, weight_clf=0.15,
+    out = dict(h=h, w=w, num_steps=num_steps, image_index=image_index, smooth=smooth, alpha=0.1, learning_rate=0.05, weight_clf=0.15,
                target=obj["target"].clone(), losses=torch.tensor(losses), preds=torch.stack(preds),
                xs=torch.stack(xs), grads=torch.stack(grads), x0=x0.detach().clone(), best_x=best_x.clone(),
                edited=(edited if h * w <= 256 * 256 else edited[..., ::4, ::4]).clone(), offsets=offs,
@@ -225,6 +225,8 @@ def main():
         gen_loop(r)
     if "loopk" in todo:
         gen_loop(r, tag="c1k", x0_override=KINK_FREE_X0)
+    if "loops" in todo:       # band-limited image, the reference's own start point: the end-to-end edited-image parity case
+        gen_loop(r, tag="c1s", smooth=True)
     if "loop512" in todo:
         gen_loop(r, 512, 512, 3, "c2_3steps", image_index=1, x0_override=KINK_FREE_X0_BLUR)
 

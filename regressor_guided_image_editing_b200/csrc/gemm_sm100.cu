@@ -1274,14 +1274,16 @@ gemm_b2b_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const bool box_leader = qd == 0 && lane == 0;
     const int bar_id = 1 + part;
     int dest_prev = -1;
-    uint32_t wmask2_prev = 0xFFFFu;
+    uint32_t wmask2_prev = 0xFFFFFFFFu;
 
-    // wmask: this row's 16 stage-2 mask bits, loaded one tile earlier (an HBM latency the epilogue must not wait for)
-    auto stage2 = [&](int it_prev, int dest, uint32_t wmask) {      // epilogue 2 of the tile handled one iteration ago
+    // wraw: the word holding this row's 16 stage-2 mask bits, loaded one tile earlier and not touched until here (an HBM
+    // latency the epilogue must not wait for: ncu showed 4 % of all samples on the shift that followed the load)
+    auto stage2 = [&](int it_prev, int dest, uint32_t wraw) {      // epilogue 2 of the tile handled one iteration ago
       const int b = it_prev & 1;
       mbar_wait(t2full(b), (uint32_t)((it_prev >> 1) & 1));
       tcgen05_fence_after();
       const int n0 = part * CH;
+      const uint32_t wmask = (wraw >> (16 * (part & 1))) & 0xFFFFu;
       uint32_t wout = 0u;
 #pragma unroll
       for (int h = 1; h >= 0; --h) {                 // two halves of 8 columns, upper half first (bit order of wout)
@@ -1316,25 +1318,37 @@ gemm_b2b_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         reinterpret_cast<uint16_t*>(q2.D2_bits + bits_index(dest, n0 / 32, q2.ld_db2))[part & 1] = (uint16_t)(wout & wmask);
     };
 
-    // residual row and mask words of the NEXT tile are fetched while epilogue 2 of the previous one runs
+    // Residual row and mask words of the NEXT tile: the mask words are fetched at the end of a tile, residual chunk ci right
+    // after chunk ci of the current tile has been consumed (its register buffer is free then) -- one 32-sector request per
+    // warp at a time instead of a burst of 64 requests per CTA at the tile boundary (ncu: the burst backs up the LSU queue
+    // and the epilogue warps wait for their address registers to be released).
     uint32_t rbuf[CPW][CH / 2];
     uint32_t bits_nxt0 = 0u, bits_nxt1 = 0u;
-    auto prefetch = [&](int tile) {
+    const __nv_bfloat16* nres = nullptr;             // residual row of the next tile, or null
+    auto locate_next = [&](int tile) {
+      nres = nullptr;
+      if (tile >= num_tiles) return;
+      const int m = (int)d.m_begin + tile * BM + row;
+      if (res != nullptr && m < res_lim) nres = res + (long)m * d.ld_res + col0;
+    };
+    auto prefetch_bits = [&](int tile) {
       bits_nxt0 = bits_nxt1 = 0u;
       if (tile >= num_tiles) return;
       const int m = (int)d.m_begin + tile * BM + row;
-      if (res != nullptr && m < res_lim) {
-#pragma unroll
-        for (int ci = 0; ci < CPW; ++ci) ldg256(res + (long)m * d.ld_res + col0 + ci * CH, rbuf[ci]);
-      }
       if (mbits != nullptr && m < m_end) {
         bits_nxt0 = __ldg(mbits + bits_index(m, col0 / 32, d.ld_mb));
         bits_nxt1 = __ldg(mbits + bits_index(m, col0 / 32 + 1, d.ld_mb));
       }
     };
-    prefetch(blockIdx.x);
+    locate_next(blockIdx.x);
+    if (nres != nullptr) {
+#pragma unroll
+      for (int ci = 0; ci < CPW; ++ci) ldg256(nres + ci * CH, rbuf[ci]);
+    }
+    prefetch_bits(blockIdx.x);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      locate_next(tile + gridDim.x);
       const int m0 = (int)d.m_begin + tile * BM;
       const int m = m0 + row;
       int dest = -1;                                       // DST_SAME: the destination row is the source row (pad rows: none)
@@ -1343,9 +1357,8 @@ gemm_b2b_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const bool use_res = live && res != nullptr && m < res_lim;
       const uint32_t bits_cur0 = bits_nxt0, bits_cur1 = bits_nxt1;
       uint32_t bits_out0 = 0u, bits_out1 = 0u;
-      uint32_t wmask2 = 0xFFFFu;
-      if (live && q2.mask_bits2 != nullptr)
-        wmask2 = (__ldg(q2.mask_bits2 + bits_index(dest, (part * CH) / 32, q2.ld_mb2)) >> (16 * (part & 1))) & 0xFFFFu;
+      uint32_t wmask2 = 0xFFFFFFFFu;
+      if (live && q2.mask_bits2 != nullptr) wmask2 = __ldg(q2.mask_bits2 + bits_index(dest, (part * CH) / 32, q2.ld_mb2));
       mbar_wait(t1full, (uint32_t)(it & 1));
       tcgen05_fence_after();
       if (it > 0) {
@@ -1404,6 +1417,7 @@ gemm_b2b_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           sts128(box_row + (((uint32_t)(2 * ci) ^ swz) << 4), z);
           sts128(box_row + (((uint32_t)(2 * ci + 1) ^ swz) << 4), z);
         }
+        if (nres != nullptr) ldg256(nres + ci * CH, rbuf[ci]);      // chunk ci of the NEXT tile into the buffer just consumed
       }
       fence_async_smem();                        // the box is read by the async proxy (TMA store, tcgen05.mma)
       named_bar_sync(bar_id, 128);
@@ -1416,7 +1430,7 @@ gemm_b2b_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         d.D_bits[bits_index(dest, col0 / 32, d.ld_db)] = bits_out0;
         d.D_bits[bits_index(dest, col0 / 32 + 1, d.ld_db)] = bits_out1;
       }
-      prefetch(tile + gridDim.x);
+      prefetch_bits(tile + gridDim.x);
       if (it > 0) stage2(it - 1, dest_prev, wmask2_prev);
       dest_prev = dest;
       wmask2_prev = wmask2;
