@@ -437,7 +437,10 @@ __device__ __forceinline__ void epilogue_store_role(const GemmDesc& d, const CUt
 // PAIR = true   : the CTA's tile sequence is made of PAIRS of M-adjacent tiles of the same N tile (num_tiles counts
 //                 pairs); the producer loads each weight tile once per pair.  Tile 2k / 2k+1 of the sequence use
 //                 accumulator 0 / 1, exactly like consecutive tiles do without pairing, so only the decode changes.
-template <int BN, int NEW, bool TSPLIT = false, int NACC = 2, bool PAIR = false>
+// TWO = true    : CTA-pair patch kernel (cta_group::2): the tile sequence of a CTA is unchanged (CTA b walks tiles b, b + grid,
+//                 ...; CTAs 2c and 2c + 1 walk M-adjacent tiles in lockstep), only the accumulator-free arrive goes to the
+//                 LEADER CTA's barrier (remotely for the peer).
+template <int BN, int NEW, bool TSPLIT = false, int NACC = 2, bool PAIR = false, bool TWO = false>
 __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sbias, const uint32_t tmem_base,
                                               const uint32_t tfull0, const uint32_t tempty0, const int warp, const int lane,
                                               const int num_tiles, const int num_n_tiles, const FastDiv fd_nt,
@@ -628,7 +631,9 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
     }
     tcgen05_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(tempty_bar(acc));
+    if (lane == 0) {
+      if (TWO) mbar_arrive_cluster(mapa_rank(tempty_bar(acc), 0)); else mbar_arrive(tempty_bar(acc));
+    }
   }
 }
 
@@ -1689,6 +1694,148 @@ gemm_patch_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
 }
 
 // ===============================================================================================================
+// CTA-pair form of the patch kernel (cta_group::2).  ncu on gemm_patch_kernel<64,3,3> (profiles/README.md, r2_d): the TC
+// pipe is 77 % busy while the tensor datapath is 36 % active -- an N = 64, K = 16 instruction holds the pipe ~72 cycles
+// for 32 cycles of math, so these layers are bound by the NUMBER of tcgen05.mma instructions.  One cta_group::2
+// instruction (M = 256: the two SMs of a TPC, each with its own 16 x 8 pixel patch) does the work of two at the cost of
+// one (tools/microbench/umma_rate_2cta.cu: 45.6 cycles per instruction for N <= 64).  Each CTA loads its own boxes and keeps
+// HALF of the weight rows resident; barriers as in gemm_sm100_2cta_kernel: afull / wfull / tempty live in the leader CTA
+// (the peer's TMA loads and epilogue warps signal them remotely), aempty / tfull are signalled in both CTAs by the
+// leader's multicast tcgen05.commit.  The tile sequence of a CTA is unchanged (CTA b: tiles b, b + grid, ...), so CTAs
+// 2c and 2c + 1 walk horizontally adjacent patches in lockstep; the plan rounds the tile count up to an even number (a
+// phantom tile lies beyond the last line: its boxes are zero-filled and none of its rows is a row).
+// ===============================================================================================================
+__device__ __forceinline__ void tma_load_3d_2cta(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2), "r"(leader_bar) : "memory");
+}
+
+template <int BN, int NY, int NX>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(num_threads(8), 1)
+gemm_patch_2cta_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmBh, const GemmDesc d,
+                       const PatchTaps tp, const PatchMap pm, const int num_tiles) {
+  using L = PatchSmem;
+  constexpr int NACC = 4;
+  constexpr uint32_t TMEM_COLS = tmem_cols(BN, NACC);
+  constexpr int W_TAP_HALF = (BN / 2) * BK * 2;             // this CTA's half of one tap's weight rows
+  static_assert(BN % 16 == 0 && (BN / 2) % 8 == 0, "half weight tiles must be whole swizzle atoms");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_base + L::BAR_OFF;
+  auto afull_bar = [&](int s) { return bar_base + 8u * s; };
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (PATCH_SLABS + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * PATCH_SLABS + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * PATCH_SLABS + NACC + a); };
+  const uint32_t wfull_bar = bar_base + 8u * (2 * PATCH_SLABS + 2 * NACC);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_PTR_OFF);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  constexpr uint32_t slab_bytes = (uint32_t)((16 + NY - 1) * 8 * 128);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA3) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmBh) : "memory");
+    for (int s = 0; s < PATCH_SLABS; ++s) {
+      mbar_init(afull_bar(s), 1);
+      mbar_init(aempty_bar(s), 1);
+    }
+    for (int a = 0; a < NACC; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 8);     // the 4 warps of the owning group in BOTH CTAs
+    }
+    mbar_init(wfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_base + L::TMEM_PTR_OFF),
+                 "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (d.bias != nullptr) {
+    float* sb = reinterpret_cast<float*>(smem + L::BIAS_OFF);
+    for (int i = threadIdx.x; i < d.Cout; i += num_threads(8)) sb[i] = d.bias[i];
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // the peer's barriers are initialised and its TMEM is allocated before anything crosses over
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs): this CTA's half of the weights once, then its own boxes =====================
+    if (lane == 0) {
+      const uint32_t lwfull = mapa_rank(wfull_bar, 0);
+      if (rank == 0) mbar_expect_tx(wfull_bar, (uint32_t)(2 * d.ntaps * W_TAP_HALF));
+      for (int t = 0; t < d.ntaps; ++t)
+        tma_load_2d_2cta(smem_base + L::W_OFF + t * W_TAP_HALF, &tmBh, t * BK, (int)rank * (BN / 2), lwfull);
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int ht = (int)pm.fd_wt.div((uint32_t)tile), wt = tile - ht * pm.WT;
+#pragma unroll
+        for (int xi = 0; xi < NX; ++xi) {
+          mbar_wait(aempty_bar(slot), phase ^ 1);
+          const uint32_t lfull = mapa_rank(afull_bar(slot), 0);
+          if (rank == 0) mbar_expect_tx(afull_bar(slot), 2 * slab_bytes);
+          tma_load_3d_2cta(smem_base + L::A_OFF + slot * PATCH_SLAB_BYTES, &tmA3, 0, wt * 8 + tp.dx0 + xi, ht * 16 + tp.dy0, lfull);
+          if (++slot == PATCH_SLABS) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread of the leader CTA) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc(2 * BM, BN);
+      mbar_wait(wfull_bar, 0);
+      tcgen05_fence_after();
+      const uint64_t wdesc0 = make_smem_desc(smem_base + L::W_OFF);
+      int slot = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it % NACC;
+        const uint32_t acc_phase = (it / NACC) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+#pragma unroll
+        for (int xi = 0; xi < NX; ++xi) {
+          mbar_wait(afull_bar(slot), phase);
+          tcgen05_fence_after();
+          const uint64_t adesc0 = make_smem_desc(smem_base + L::A_OFF + slot * PATCH_SLAB_BYTES);
+#pragma unroll
+          for (int yi = 0; yi < NY; ++yi) {
+            const uint64_t adesc = adesc0 + (uint64_t)(yi * 64);
+            const uint64_t bdesc = wdesc0 + (uint64_t)(tp.tap[yi][xi] * (W_TAP_HALF >> 4));
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_2cta(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (xi | yi | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2cta(aempty_bar(slot));
+          if (++slot == PATCH_SLABS) { slot = 0; phase ^= 1; }
+        }
+        umma_commit_2cta(tfull_bar(acc));
+      }
+    }
+  } else {
+    epilogue_role<BN, 8, true, NACC, false, true>(d, reinterpret_cast<const float*>(smem + L::BIAS_OFF), tmem_base, tfull_bar(0),
+                                                  tempty_bar(0), warp, lane, num_tiles, 1, FastDiv{1, 0, 0}, pm);
+  }
+
+  // ===================== teardown: nobody leaves while the peer may still signal into this CTA =====================
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ===============================================================================================================
 // conv1 input gradient, "horizontal taps as N":  the 7x7/2 stem's input gradient in the 2x2 phase-split form is a 4x4-tap
 // convolution of the 64-channel gradient with only 12 outputs per pixel.  With N = 12(16) every one of the 64 MMAs of a
 // tile re-reads its 128 x 16 operand slice from shared memory for 16 columns of output -- the patch kernel above is
@@ -1934,6 +2081,25 @@ int run_patch(const GemmPlanSm100& p, cudaStream_t st) {
   return 0;
 }
 
+template <int BN, int NY, int NX>
+int run_patch_2cta(const GemmPlanSm100& p, cudaStream_t st) {
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
+    RGIE_CUDA_OK(cudaFuncSetAttribute(gemm_patch_2cta_kernel<BN, NY, NX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      PatchSmem::DYN_BYTES));
+    attr_once.done();
+  }
+  PatchTaps tp;
+  tp.ny = p.patch_ny; tp.nx = p.patch_nx; tp.dy0 = p.patch_dy0; tp.dx0 = p.patch_dx0;
+  for (int y = 0; y < 4; ++y)
+    for (int x = 0; x < 4; ++x) tp.tap[y][x] = p.patch_tap[y][x];
+  PatchMap pm;
+  pm.enabled = 1; pm.P = p.d.src.P; pm.WT = p.patch_wt; pm.fd_wt = make_fastdiv((uint32_t)p.patch_wt);
+  gemm_patch_2cta_kernel<BN, NY, NX><<<p.grid, num_threads(8), PatchSmem::DYN_BYTES, st>>>(p.tmA, p.tmB, p.d, tp, pm, p.num_m_tiles);
+  RGIE_LAUNCH_OK();
+  return 0;
+}
+
 int run_b2b(const GemmPlanSm100& p, cudaStream_t st) {
   static DeviceOnce attr_once;
   if (attr_once.needed()) {
@@ -2008,6 +2174,7 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
   p->d = d;
   p->bn = bn;
   p->patch = 0;
+  p->patch_2cta = 0;
   p->special = 0;
   p->b2b = 0;
   // ---- patch-tile variant: Cin = 64, one N tile, single-plane source whose rows are whole pixel lines, taps on a
@@ -2053,12 +2220,24 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
         int sms = gemm_sm100_num_sms();
         p->grid = p->num_m_tiles < sms ? p->num_m_tiles : sms;
         p->epi = 0;
+        // CTA pairs (gemm_patch_2cta_kernel) for the 3x3 variant (36 MMAs per tile).  Measured (B200, 320 crops, same box):
+        // layer1 3x3 forward 0.468 -> 0.414 ms, input gradient 0.476 -> 0.434 ms.  conv1 forward (16 MMAs and ONE box per
+        // tile) LOSES with pairs, 0.88 -> 1.21 ms: the cross-SM barrier round trip per tile is no longer hidden.
+        // RGIE_PATCH_2CTA=0 keeps one CTA per tile, =2 also pairs conv1.
+        static const int env_p2 = getenv("RGIE_PATCH_2CTA") ? atoi(getenv("RGIE_PATCH_2CTA")) : 1;
+        p->patch_2cta = (env_p2 && bn == 64 && (variant == 1 || (variant == 2 && env_p2 >= 2)) && p->num_m_tiles >= 2 && sms >= 2) ? 1 : 0;
+        if (p->patch_2cta) {
+          p->num_m_tiles = (p->num_m_tiles + 1) & ~1;          // a phantom last tile keeps the pairs whole
+          const int even_sms = sms & ~1;
+          p->grid = p->num_m_tiles < even_sms ? p->num_m_tiles : even_sms;
+        }
         p->tmA2 = p->tmA; p->tmD = p->tmA; p->tmR = p->tmA;
         int rc = make_map_3d(&p->tmA, d.A, (uint64_t)P, (uint64_t)lines, (uint32_t)(16 + ny - 1),
                              (uint64_t)(d.a_ld ? d.a_ld : 64));
         if (rc) return rc;
         p->tmA2 = p->tmA; p->tmD = p->tmA; p->tmR = p->tmA;
-        return make_map_2d(&p->tmB, d.Wt, (uint64_t)d.ntaps * d.Cin, (uint64_t)d.n_pad, BK, (uint32_t)bn);
+        return make_map_2d(&p->tmB, d.Wt, (uint64_t)d.ntaps * d.Cin, (uint64_t)d.n_pad, BK,
+                           (uint32_t)(p->patch_2cta ? bn / 2 : bn));   // CTA pairs: each CTA loads half of the weight rows
       }
     }
   }
@@ -2227,8 +2406,8 @@ int run_gemm_sm100(const GemmPlanSm100& p, cudaStream_t st) {
   if (p.b2b == 1) return run_b2b(p, st);
   if (p.d.m_end <= p.d.m_begin) return 0;
   if (p.special == 1) return run_conv_hshare(p, st);
-  if (p.patch == 1) return run_patch<64, 3, 3>(p, st);     // 3x3, 64 -> 64 (layer1)
-  if (p.patch == 2) return run_patch<64, 4, 1>(p, st);     // conv1 forward: 4 vertical taps over the packed input
+  if (p.patch == 1) return p.patch_2cta ? run_patch_2cta<64, 3, 3>(p, st) : run_patch<64, 3, 3>(p, st);     // 3x3, 64 -> 64 (layer1)
+  if (p.patch == 2) return p.patch_2cta ? run_patch_2cta<64, 4, 1>(p, st) : run_patch<64, 4, 1>(p, st);     // conv1 forward: 4 vertical taps
   if (p.patch == 3) return run_patch<16, 4, 4>(p, st);     // conv1 input gradient: 4 x 4 taps, 64 -> 16
   switch (p.bn) {
     case 256:

@@ -12,6 +12,7 @@ struct GemmPlanSm100 {
   int bn;
   // patch-tile variant (gemm_sm100.cu: gemm_patch_kernel): taps on a (dy, dx) grid, 16 x 8 pixel output tiles
   int patch, patch_ny, patch_nx, patch_dy0, patch_dx0, patch_wt, patch_tap[4][4];
+  int patch_2cta;                   // 1: gemm_patch_2cta_kernel (cta_group::2, a CTA pair per pair of horizontally adjacent patches)
   // special == 1: conv_hshare_kernel (conv1 input gradient with the horizontal taps as the N dimension)
   int special, hs_wt, hs_dy0, hs_dx0, hs_col0;
   long hs_lines;
