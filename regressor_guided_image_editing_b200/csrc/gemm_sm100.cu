@@ -236,9 +236,9 @@ struct SmemLayout {
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = STAGES * A_BYTES;
   static constexpr int OB_OFF = B_OFF + STAGES * B_STAGE_BYTES;                 // [half][2] output boxes
-  static constexpr int RB_OFF = OB_OFF + (EPI == 8 ? 4 * BM * 128 : (EPI >= 1 ? 4 * EPI_BOX_BYTES : 0));    // [half][EPI] residual boxes
-  static constexpr int BAR_OFF = RB_OFF + ((EPI >= 2 && EPI != 8) ? 2 * EPI * EPI_BOX_BYTES : 0);   // full[S], empty[S], tfull[2], tempty[2], rfull[8]
-  static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * STAGES + 12) * 8;
+  static constexpr int RB_OFF = OB_OFF + (EPI >= 8 ? 4 * BM * 128 : (EPI >= 1 ? 4 * EPI_BOX_BYTES : 0));    // [half][EPI] residual boxes
+  static constexpr int BAR_OFF = RB_OFF + ((EPI >= 2 && EPI < 8) ? 2 * EPI * EPI_BOX_BYTES : 0);   // full[S], empty[S], tfull[2], tempty[2], rfull[8], ready[8]
+  static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * STAGES + 20) * 8;
   static constexpr int BIAS_OFF = TMEM_PTR_OFF + 16;                // whole bias vector (<= MAX_BIAS floats)
   static constexpr int TOTAL = BIAS_OFF + MAX_BIAS * 4;
   static constexpr int DYN_BYTES = TOTAL + 1024;   // + slack for manual 1024 B alignment
@@ -816,6 +816,194 @@ __device__ __forceinline__ void epilogue_lean_role(const GemmDesc& d, const floa
   if (box_leader) bulk_wait0();
 }
 
+// ===================== lean epilogue with a DMA thread (EPI 9): BN = 256, DST_SAME, bf16 output =====================
+// The 16-warp lean role above still fetches its residual operand with row-per-thread 32-byte loads: 32 distinct lines per
+// warp instruction, the other half of the L1TEX/LSU load that the TMA-store output path removed (ncu on the fused kernel:
+// epilogue warps stalled on the release of their address registers behind the LSU queue).  Here every byte of the epilogue
+// moves by TMA.  A 64-column part is split into two half boxes of 128 rows x 32 columns (64-byte rows, SWIZZLE_64B, 8 KB); a
+// half box holds, in turn, the RESIDUAL of a tile (TMA load), then -- written in place by the thread that owns the row --
+// the OUTPUT of that tile (TMA store).  One otherwise idle thread of the producer warpgroup (warp 2) is the DMA engine of all
+// eight half boxes: for each box in turn it waits for `ready` (the 4 warps of the part have written it), issues the TMA
+// store, waits until the PREVIOUS store has finished reading its box and refills that box with the next tile's residual
+// (`rfull`: the 4 warps wait for it before they touch the box again).  The residual of half box (p, h) is therefore loaded
+// while the other half of the tile is being processed, and the epilogue warps execute no global memory instruction at all
+// besides the 1-bit mask words; no named barriers either.
+template <int BN>
+__device__ __forceinline__ void epilogue_lean_dma_role(const GemmDesc& d, const float* sbias, const uint32_t tmem_base,
+                                                       const uint32_t tfull0, const uint32_t tempty0, const uint32_t rfull0,
+                                                       const uint32_t ready0, const int warp, const int lane,
+                                                       const int num_tiles, const int num_n_tiles, const FastDiv fd_nt,
+                                                       const uint32_t ob_smem) {
+  static_assert(BN == 256, "EPI 9 is instantiated for 256-wide tiles");
+  constexpr int CH = 16, PW = 64, CPW = 4;
+  auto tfull_bar = [&](int a) { return tfull0 + 8u * a; };
+  auto tempty_bar = [&](int a) { return tempty0 + 8u * a; };
+  const int q = warp & 3;
+  const int part = (warp - 4) >> 2;
+  const int row = q * 32 + lane;
+  const int col0 = part * PW;
+  const bool has_res = d.res != nullptr;
+  const uint32_t* mbits = d.mask_bits;
+  const bool has_bias = d.bias != nullptr;
+  // this thread's 64-byte row inside a half box: 16-byte piece j lives at piece (j ^ ((row >> 1) & 3))  (SWIZZLE_64B)
+  const uint32_t row_off = (uint32_t)row * 64u;
+  const uint32_t swz = (uint32_t)((row >> 1) & 3);
+  auto box_addr = [&](int h) { return ob_smem + (uint32_t)((part * 2 + h) * EPI_BOX_BYTES); };
+  auto rfull_bar = [&](int h) { return rfull0 + 8u * (part * 2 + h); };
+  auto ready_bar = [&](int h) { return ready0 + 8u * (part * 2 + h); };
+
+  uint32_t bits_nxt[2];
+  auto bits_fetch = [&](int tile) {
+    bits_nxt[0] = bits_nxt[1] = 0u;
+    if (mbits != nullptr && tile < num_tiles) {
+      const int mt = (int)fd_nt.div((uint32_t)tile), nt = tile - mt * num_n_tiles;
+      const long m = d.m_begin + (long)mt * BM + row;
+      if (m < d.m_end) {
+        const int w0 = (nt * BN + col0) / 32;
+        bits_nxt[0] = __ldg(mbits + bits_index(m, w0, d.ld_mb));
+        bits_nxt[1] = __ldg(mbits + bits_index(m, w0 + 1, d.ld_mb));
+      }
+    }
+  };
+  bits_fetch(blockIdx.x);
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    const int mt = (int)fd_nt.div((uint32_t)tile), nt = tile - mt * num_n_tiles;
+    const int acc = it & 1;
+    const uint32_t acc_phase = (it >> 1) & 1;
+    const long m = d.m_begin + (long)mt * BM + row;
+    long dest = -1;
+    if (m < d.m_end) dest = map_row(d.src, d.dst_kind, d.dst, m);
+    const bool live = dest >= 0;
+    const bool use_res = live && has_res && m < d.res_rows;
+    const uint32_t bits_cur[2] = {bits_nxt[0], bits_nxt[1]};
+    uint32_t bits_out[2] = {0u, 0u};
+    bits_fetch(tile + gridDim.x);
+    mbar_wait(tfull_bar(acc), acc_phase);
+    tcgen05_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + col0);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      // the box is ours again: the TMA store of the previous tile has read it and (if there is one) this tile's residual is in it
+      mbar_wait(rfull_bar(h), (uint32_t)(it & 1));
+      const uint32_t brow = box_addr(h) + row_off;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int ci = 2 * h + cc;
+        uint32_t r[CH];
+        tmem_ld<CH>(taddr + (uint32_t)(ci * CH), r);
+        const uint32_t a0 = brow + (((uint32_t)(2 * cc) ^ swz) << 4), a1 = brow + (((uint32_t)(2 * cc + 1) ^ swz) << 4);
+        uint32_t rs[8];
+        if (use_res) { lds128(a0, rs); lds128(a1, rs + 4); }
+        tmem_ld_wait();
+        if (ci == CPW - 1) {
+          // the accumulator is in registers: hand the TMEM buffer back before the arithmetic of the last chunk
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        if (live) {
+          const int n0 = nt * BN + col0 + ci * CH;
+          float v[CH];
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
+          if (use_res) {
+#pragma unroll
+            for (int j = 0; j < CH / 2; ++j) { v[2 * j] += bf16_lo(rs[j]); v[2 * j + 1] += bf16_hi(rs[j]); }
+          }
+          if (has_bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(sbias + n0);
+#pragma unroll
+            for (int j = 0; j < CH / 4; ++j) {
+              const float4 b = b4[j];
+              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+          }
+          uint32_t wout = 0u;
+          if (d.relu) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
+            if (d.D_bits != nullptr) {
+#pragma unroll
+              for (int j = CH - 1; j >= 0; --j) wout = push_positive_bit(wout, v[j]);
+            }
+          } else if (d.D_bits != nullptr) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) wout |= (v[j] > 0.f ? 1u : 0u) << j;
+          }
+          if (mbits != nullptr) {
+            const uint32_t w = (bits_cur[h] >> (16 * cc)) & 0xFFFFu;
+            wout &= w;
+#pragma unroll
+            for (int j = 0; j < CH; ++j) v[j] = keep_if_bit(v[j], w, j);
+          }
+          bits_out[h] |= wout << (16 * cc);
+          uint32_t pk[CH / 2];
+#pragma unroll
+          for (int j = 0; j < CH / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          sts128(a0, pk);
+          sts128(a1, pk + 4);
+        } else {
+          const uint32_t z[4] = {0u, 0u, 0u, 0u};       // pad rows are zero by construction and stay zero
+          sts128(a0, z);
+          sts128(a1, z);
+        }
+      }
+      fence_async_smem();                 // generic-proxy writes -> visible to the TMA store
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ready_bar(h));
+    }
+    if (live && d.D_bits != nullptr) {
+      const int w0 = (nt * BN + col0) / 32;
+      d.D_bits[bits_index(dest, w0, d.ld_db)] = bits_out[0];
+      d.D_bits[bits_index(dest, w0 + 1, d.ld_db)] = bits_out[1];
+    }
+  }
+}
+
+// A DMA thread of EPI 9 (lane 0 of warp 2 serves parts 0-1, lane 0 of warp 3 parts 2-3).  Box k = part * 2 + half.  Per box:
+// wait until the part has written it, store it, wait until the store has read it (a few hundred ns), refill it with the next
+// tile's residual -- which then has the processing time of the OTHER half of the tile to arrive.
+template <int BN>
+__device__ __forceinline__ void epilogue_dma_thread(const GemmDesc& d, const CUtensorMap* tmD, const CUtensorMap* tmR,
+                                                    const uint32_t rfull0, const uint32_t ready0, const int part0,
+                                                    const int num_tiles, const int num_n_tiles, const FastDiv fd_nt,
+                                                    const uint32_t ob_smem) {
+  const bool has_res = d.res != nullptr;
+  auto box_of = [&](int k) { return ob_smem + (uint32_t)(k * EPI_BOX_BYTES); };
+  // hand box k to the epilogue warps for `tile`: with this tile's residual in it, or as it is when there is none
+  auto refill = [&](int k, int tile) {
+    if (tile >= num_tiles) return;
+    const uint32_t bar = rfull0 + 8u * k;
+    if (has_res) {
+      const int mt = (int)fd_nt.div((uint32_t)tile), nt = tile - mt * num_n_tiles;
+      mbar_expect_tx(bar, EPI_BOX_BYTES);
+      tma_load_2d(box_of(k), tmR, nt * BN + (k >> 1) * 64 + (k & 1) * 32, (int)(d.m_begin + (long)mt * BM), bar);
+    } else {
+      mbar_arrive(bar);
+    }
+  };
+#pragma unroll 1
+  for (int s = 0; s < 4; ++s) refill((part0 + (s & 1)) * 2 + (s >> 1), blockIdx.x);
+  int it = 0;
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    const int mt = (int)fd_nt.div((uint32_t)tile), nt = tile - mt * num_n_tiles;
+    const int m0 = (int)(d.m_begin + (long)mt * BM);
+#pragma unroll 1
+    for (int s = 0; s < 4; ++s) {
+      const int k = (part0 + (s & 1)) * 2 + (s >> 1);          // half 0 of both parts, then half 1 of both parts
+      mbar_wait(ready0 + 8u * k, (uint32_t)(it & 1));
+      tma_store_2d(tmD, box_of(k), nt * BN + (k >> 1) * 64 + (k & 1) * 32, m0);
+      bulk_commit();
+      bulk_wait_read0();                                        // the store has read the box
+      refill(k, tile + (int)gridDim.x);
+    }
+  }
+  bulk_wait0();
+}
+
 template <int BN, int STAGES, int EPI, int NEW, bool PAIR>
 __global__ void __launch_bounds__(num_threads(NEW), 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
@@ -856,6 +1044,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(tempty_bar(a), NEW);   // one arrive per epilogue warp
     }
     for (int a = 0; a < 8; ++a) mbar_init(rfull_bar(a), 1);
+    if (EPI == 9)
+      for (int a = 0; a < 8; ++a) mbar_init(rfull_bar(8 + a), 4);     // ready[8]: the 4 warps of a part
     if (EPI >= 1) {
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmD) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmR) : "memory");
@@ -882,7 +1072,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // so that ptxas allocates each role against its own budget.
   if (NEW == 16 && warp >= 4) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
-    if constexpr (NEW == 16)
+    if constexpr (NEW == 16 && EPI == 9)
+      epilogue_lean_dma_role<BN>(d, reinterpret_cast<const float*>(smem + L::BIAS_OFF), tmem_base, tfull_bar(0), tempty_bar(0),
+                                 rfull_bar(0), rfull_bar(8), warp, lane, num_tiles, num_n_tiles, fd_nt, smem_base + L::OB_OFF);
+    else if constexpr (NEW == 16)
       epilogue_lean_role<BN, false, EPI == 8>(d, reinterpret_cast<const float*>(smem + L::BIAS_OFF), tmem_base, tfull_bar(0),
                                               tempty_bar(0), warp, lane, num_tiles, num_n_tiles, fd_nt, &tmD,
                                               smem_base + L::OB_OFF);
@@ -964,10 +1157,15 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if constexpr (NEW == 16) {
-    static_assert((EPI == 0 || EPI == 8) && !PAIR, "16 epilogue warps: lean epilogue (row-per-thread or TMA-store) only");
-    // warps 2, 3: idle members of the producer warpgroup
+    static_assert((EPI == 0 || EPI == 8 || EPI == 9) && !PAIR, "16 epilogue warps: lean epilogue (row-per-thread or TMA-store) only");
+    // warps 2, 3: idle members of the producer warpgroup -- with EPI 9 their lane 0 is a DMA thread of the epilogue
+    if constexpr (EPI == 9) {
+      if (lane == 0)
+        epilogue_dma_thread<BN>(d, &tmD, &tmR, rfull_bar(0), rfull_bar(8), (warp - 2) * 2, num_tiles, num_n_tiles, fd_nt,
+                                smem_base + L::OB_OFF);
+    }
   } else if constexpr (EPI >= 1) {
-    static_assert(EPI == 0 || EPI == 8 || NEW == 8, "the store epilogue runs with 8 epilogue warps");
+    static_assert(EPI == 0 || EPI >= 8 || NEW == 8, "the store epilogue runs with 8 epilogue warps");
     epilogue_store_role<BN, EPI>(d, &tmD, &tmR, reinterpret_cast<const float*>(smem + L::BIAS_OFF), smem_base + L::OB_OFF,
                                  smem_base + L::RB_OFF, rfull_bar(0), tmem_base, tfull_bar(0), tempty_bar(0), warp, lane,
                                  num_tiles, num_n_tiles, fd_nt);
@@ -2260,6 +2458,13 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
   const bool lean_ok = bn == 256 && !d.d_fp32 && d.mask == nullptr;
   p->epi = (lean_ok && (env_epi == -16 || env_epi == -1 || env_epi == -17)) ? -16 : 0;
   if ((env_epi == -17 || env_epi == -1) && lean_ok && d.dst_kind == DST_SAME && ktot < 768) p->epi = -17;
+  // -18: the same launches with the residual operand ALSO moved by TMA (epilogue_lean_dma_role: in-place half boxes served by
+  // two DMA threads).  RGIE_LEAN_DMA=0 keeps -17, =1 (default) uses it for the ops that have a residual, =2 for every -17 op.
+  // Measured (B200, 320 crops, same box): conv1 input gradient + skip of layer1 0.875 -> 0.773 ms, of layer2 0.455 -> 0.389 ms,
+  // conv3 + skip 0.768 -> 0.746 / 0.412 -> 0.389 ms; GEMM family 30.7 -> 30.0 ms per micro-batch, step 74.7 -> 73.6 ms.
+  static const int env_dma = getenv("RGIE_LEAN_DMA") ? atoi(getenv("RGIE_LEAN_DMA")) : 1;
+  if (p->epi == -17 && env_dma > 0 && (d.res != nullptr || env_dma >= 2) && d.ldd % 32 == 0 && (d.res == nullptr || d.ld_res % 32 == 0))
+    p->epi = -18;
   if (bn == 256 && d.dst_kind == DST_SAME && !d.d_fp32 && d.mask == nullptr && env_epi >= 1) {
     if (d.res != nullptr) {
       if (env_epi == 2 || env_epi == 4) p->epi = env_epi;
@@ -2297,6 +2502,16 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
   if (p->epi == -17) {
     rc = make_map_2d(&p->tmD, d.D, (uint64_t)d.ldd, (uint64_t)d.m_end, 64, BM, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
+  }
+  if (p->epi == -18) {
+    rc = make_map_2d(&p->tmD, d.D, (uint64_t)d.ldd, (uint64_t)d.m_end, 32, BM, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    if (d.res != nullptr) {
+      // rows at or beyond res_rows are out of range for the map: zero fill = "no residual" there
+      const long rr = d.res_rows < d.m_end ? d.res_rows : d.m_end;
+      rc = make_map_2d(&p->tmR, d.res, (uint64_t)d.ld_res, (uint64_t)rr, 32, BM, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+    }
   }
   if (p->epi >= 1) {
     rc = make_map_2d(&p->tmD, d.D, (uint64_t)d.ldd, (uint64_t)d.m_end, 32, BM, CU_TENSOR_MAP_SWIZZLE_64B);
@@ -2417,6 +2632,7 @@ int run_gemm_sm100(const GemmPlanSm100& p, cudaStream_t st) {
         case 1: return run_impl<256, 3, 1, 8>(p, st);
         case -16: return run_impl<256, 4, 0, 16>(p, st);
         case -17: return run_impl<256, 3, 8, 16>(p, st);
+        case -18: return run_impl<256, 3, 9, 16>(p, st);
         case -32: return run_2cta<256, 6>(p, st);
         case -2: return run_impl<256, 3, 0, 8, true>(p, st);
         default: return run_impl<256, 4, 0, 8>(p, st);
