@@ -90,10 +90,12 @@ int rgie_resize_bwd(const RgieResize* r, const float* gout, float* gin, int plan
  * layer4.2): c1.w[Cm,Ci,1,1], c1.b, c2.w[Cm,Cm,3,3], c2.b, c3.w[Co,Cm,1,1], c3.b, and for the first block of each
  * layer ds.w[Co,Ci,1,1], ds.b; finally fc.w[num_classes,2048], fc.b.  Conv weights/biases have eval-mode BatchNorm
  * already folded in (w*gamma/sqrt(var+eps), beta-mean*gamma/sqrt(var+eps)).  n_tensors must be 2 + 2*(3*16+4) + 2.
- * precision: RGIE_PREC_FP32 (CUDA-core fp32, parity mode) | RGIE_PREC_BF16 (tcgen05/TMEM/TMA, throughput mode) |
- *            RGIE_PREC_BF16_SIMT (bf16 storage on CUDA cores: on-device cross-check of the tcgen05 kernels).
+ * precision: RGIE_PREC_FP32 (parity mode: fp32 storage, fp32-accurate GEMMs on the tcgen05 tensor cores through an exact
+ *            bf16x3 operand split, csrc/gemm_tc32.cu) | RGIE_PREC_BF16 (tcgen05/TMEM/TMA, throughput mode) |
+ *            RGIE_PREC_BF16_SIMT (bf16 storage on CUDA cores: on-device cross-check of the tcgen05 kernels) |
+ *            RGIE_PREC_FP32_SIMT (fp32 on CUDA cores: cross-check of the fp32 tensor-core mode).
  * ------------------------------------------------------------------------------------------------------------ */
-enum RgiePrecision { RGIE_PREC_FP32 = 0, RGIE_PREC_BF16 = 1, RGIE_PREC_BF16_SIMT = 2 };
+enum RgiePrecision { RGIE_PREC_FP32 = 0, RGIE_PREC_BF16 = 1, RGIE_PREC_BF16_SIMT = 2, RGIE_PREC_FP32_SIMT = 3 };
 typedef struct RgieRegressor RgieRegressor;
 int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_classes, int crop_size, int max_crops,
                           int precision, RgieRegressor** out);
@@ -202,6 +204,12 @@ int rgie_gemm_selftest_ex(int backend, const void* A, long a_rows, int Cin, cons
                           const void* W, int n_pad, int ntaps, const long* h_row_off, long m_begin, long m_end, int Cout,
                           const float* bias, const void* res, const unsigned* mask_bits, int relu, void* D, int d_fp32,
                           unsigned* D_bits, void* stream);
+/* fp32 form (tests only): fp32 device buffers A [a_rows, a_ld or Cin], A2 [a2_rows, Cin2], res / mask [m, Cout], D [m, Cout];
+ * W is a HOST fp32 matrix [Cout, ntaps*Cin + Cin2].  backend 0 = CUDA cores (gemm_simt), 2 = tcgen05 with the exact bf16x3
+ * operand split (gemm_tc32: the weights are split and uploaded inside the call).  Synchronises the stream before returning. */
+int rgie_gemm_selftest_fp32(int backend, const float* A, long a_rows, int Cin, int a_ld, const float* A2, long a2_rows,
+                            int Cin2, const float* h_W, int ntaps, const long* h_row_off, long m_begin, long m_end, int Cout,
+                            const float* bias, const float* res, const float* mask, int relu, float* D, void* stream);
 
 #ifdef __cplusplus
 }

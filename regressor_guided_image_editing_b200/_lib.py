@@ -18,8 +18,8 @@ FILTER_KINDS = {"exposure": F_EXPOSURE, "saturation": F_SATURATION, "tone": F_TO
                 "gamma": F_GAMMA, "bright": F_BRIGHT, "bw": F_BW, "hue": F_HUE, "wb": F_WB, "affine": F_AFFINE}
 FILTER_NPARAM = {"exposure": 1, "saturation": 1, "tone": 8, "color": 24, "contrast": 1, "sharp": 1, "blur": 1,
                  "scale": 4}
-PREC_FP32, PREC_BF16, PREC_BF16_SIMT = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16_simt": PREC_BF16_SIMT}
+PREC_FP32, PREC_BF16, PREC_BF16_SIMT, PREC_FP32_SIMT = 0, 1, 2, 3
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16_simt": PREC_BF16_SIMT, "fp32_simt": PREC_FP32_SIMT}
 
 
 class RgieError(RuntimeError):
@@ -65,6 +65,8 @@ SIGNATURES = {
     "rgie_midu_forward": (_i, [_vp, _vp, _i, _vp, _vp]),
     "rgie_midu_backward": (_i, [_vp, _vp, _vp, _vp]),
     "rgie_gemm_selftest": (_i, [_i, _vp, _l, _i, _vp, _i, _i, C.POINTER(_l), _l, _l, _i, _vp, _vp, _i, _vp, _i, _vp]),
+    "rgie_gemm_selftest_fp32": (_i, [_i, _vp, _l, _i, _i, _vp, _l, _i, _vp, _i, C.POINTER(_l), _l, _l, _i, _vp, _vp, _vp, _i,
+                                     _vp, _vp]),
     "rgie_gemm_selftest_ex": (_i, [_i, _vp, _l, _i, _vp, _l, _i, _vp, _i, _i, C.POINTER(_l), _l, _l, _i, _vp, _vp, _vp, _i,
                                    _vp, _i, _vp, _vp]),
 }

@@ -22,206 +22,12 @@
 //     conv_hshare_kernel (horizontal taps as N) for the conv1 input gradient.
 #include <stdlib.h>
 #include "common.cuh"
-#ifndef RGIE_WAIT_HINT_NS
-#define RGIE_WAIT_HINT_NS 100000
-#endif
+#include "sm100_ptx.cuh"
 #include "gemm_sm100.cuh"
 
 namespace rgie {
 
 namespace {
-
-constexpr int BM = 128;
-constexpr int BK = 64;                 // 64 bf16 = 128 B = one swizzle-128B row
-constexpr int A_STAGE_BYTES = BM * BK * 2;
-// TMA warp + MMA warp + NEW epilogue warps.  NEW = 16: warps 0..3 form the producer warpgroup (TMA, MMA, two idle warps)
-// so that setmaxnreg can move registers from it to the four epilogue warpgroups (warps 4..19).
-__host__ __device__ constexpr int num_threads(int new_warps) { return new_warps == 16 ? 640 : 64 + 32 * new_warps; }
-constexpr int MAX_BIAS = 2048;
-
-constexpr uint32_t kWaitHintNs = RGIE_WAIT_HINT_NS;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// Wait for a barrier phase.  try_wait suspends the thread in hardware until the phase completes or the time hint expires.
-// (Measured: a 100 us hint vs none makes no difference to step time or clocks on the power-capped B200 -- 79.6 vs 79.6 ms.)
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(bar), "r"(parity), "r"(kWaitHintNs) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(bar) : "memory");
-}
-// TMA store (shared -> global, bulk async-group completion) and the fences / named barriers the store epilogue needs
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"((uint64_t)map), "r"(c0),
-               "r"(c1), "r"(src) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void sts128(uint32_t addr, const uint32_t* r) {
-  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
-}
-__device__ __forceinline__ void lds128(uint32_t addr, uint32_t* r) {
-  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-// ---- cta_group::2 (CTA pair) variants: one MMA of M = 256 spans the two SMs of a TPC; each CTA holds its own 128 A rows and
-// HALF of the B tile, so the shared-memory operand traffic per SM drops from 48 KB to 32 KB per 128x256x64 k-block.
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {   // same offset in CTA `rank` of the cluster
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// TMA load of a CTA pair: the bytes land in THIS CTA's shared memory, the transaction count goes to the leader's barrier
-__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(leader_bar) : "memory");
-}
-__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// K-major, SWIZZLE_128B operand tile (rows of 128 B, 8-row groups 1024 B apart): the sm_100 shared-memory matrix
-// descriptor -- start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024>>4 |
-// version=1 [46,48) | layout=2 (SWIZZLE_128B) [61,64).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-  uint64_t desc = 0;
-  desc |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  desc |= (uint64_t)1 << 16;
-  desc |= (uint64_t)(1024 >> 4) << 32;
-  desc |= (uint64_t)1 << 46;
-  desc |= (uint64_t)2 << 61;
-  return desc;
-}
-
-// instruction descriptor: c=f32 [4,6)=1 | a=bf16 [7,10)=1 | b=bf16 [10,13)=1 | K-major A,B (bits 15,16 = 0) |
-// N>>3 [17,23) | M>>4 [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-template <int N>
-__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t* r);
-template <>
-__device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-template <>
-__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-      "[%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-template <>
-__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, uint32_t* r) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-// 256-bit global accesses (sm_100): one thread moves a full 32-byte sector per instruction, which halves the L1TEX
-// request/sector count of the row-per-thread epilogue compared with 128-bit accesses
-__device__ __forceinline__ void ldg256(const void* p, uint32_t* r) {
-  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "l"(p));
-}
-__device__ __forceinline__ void stg256(void* p, const uint32_t* r) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
-               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
-}
-// v AND (bit j of w ? all-ones : 0): signed 1-bit field extract gives 0 / -1 in one instruction
-__device__ __forceinline__ float keep_if_bit(float v, uint32_t w, int j) {
-  int m;
-  asm("bfe.s32 %0, %1, %2, 1;" : "=r"(m) : "r"(w), "r"(j));
-  return __uint_as_float(__float_as_uint(v) & (uint32_t)m);
-}
-// w = (w << 1) | (x > 0) for a NON-NEGATIVE float x (post-ReLU): x > 0 <=> bit pattern i >= 1 <=> sign bit of
-// i + 0x7FFFFFFF.  Pushing elements CH-1 .. 0 leaves the bit of element j at position j.  Exact, including x == 0
-// (about 1e-8 of all fp32 accumulators are exactly zero; measured by tests/test_gemm_gpu.py).
-__device__ __forceinline__ uint32_t push_positive_bit(uint32_t w, float x_nonneg) {
-  return __funnelshift_l(__float_as_uint(x_nonneg) + 0x7FFFFFFFu, w, 1);
-}
-__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
-
-__host__ __device__ constexpr int tmem_cols(int bn, int nacc = 2) {
-  return nacc * bn <= 32 ? 32 : (nacc * bn <= 64 ? 64 : (nacc * bn <= 128 ? 128 : (nacc * bn <= 256 ? 256 : 512)));
-}
 
 // EPI selects the epilogue: 0 = row-per-thread global accesses (any destination mapping, fp32 or bf16 output);
 // 1 = output tile staged in shared memory and written by TMA stores (DST_SAME bf16 outputs: every global write is a
@@ -2228,6 +2034,29 @@ PFN_encodeTiled get_encode_fn() {
   }
   return fn;
 }
+
+}  // namespace
+
+// General 2-D map (exported for gemm_tc32.cu): `dtype` 0 = bf16, 1 = fp32; row_elems = elements between rows (0 = dense)
+int make_tensor_map_2d(CUtensorMap* map, const void* base, int dtype, uint64_t inner, uint64_t rows, uint32_t box_inner,
+                       uint32_t box_rows, int swizzle_bytes, uint64_t row_elems) {
+  PFN_encodeTiled enc = get_encode_fn();
+  RGIE_CHECK(enc != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
+  const uint64_t esz = dtype == 1 ? 4 : 2;
+  cuuint64_t gdim[2] = {inner, rows};
+  cuuint64_t gstride[1] = {(row_elems ? row_elems : inner) * esz};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
+  CUresult r = enc(map, dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+  return 0;
+}
+
+namespace {
 
 int make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows,
                 CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, uint64_t row_elems = 0) {

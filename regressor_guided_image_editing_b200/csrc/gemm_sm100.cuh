@@ -30,6 +30,8 @@ int build_conv_hshare_sm100(const GemmDesc& d, const void* Wh, int dy0, int dx0,
 bool gemm_b2b_eligible(const GemmDesc& d1, const GemmDesc& d2);
 int build_gemm_b2b_sm100(const GemmDesc& d1, const GemmDesc& d2, GemmPlanSm100* p);
 int run_gemm_sm100(const GemmPlanSm100& p, cudaStream_t st);
+int make_tensor_map_2d(CUtensorMap* map, const void* base, int dtype, uint64_t inner, uint64_t rows, uint32_t box_inner,
+                       uint32_t box_rows, int swizzle_bytes, uint64_t row_elems);
 int gemm_sm100_num_sms();
 
 }  // namespace rgie

@@ -12,7 +12,9 @@
 #include <vector>
 #include "common.cuh"
 #include "gemm_sm100.cuh"
+#include "gemm_tc32.cuh"
 #include "rgie.h"
+#include <stdlib.h>
 
 namespace rgie {
 namespace {
@@ -166,10 +168,12 @@ struct MiduStage {
   uint8_t* arg = nullptr;
   GemmDesc d_fwd, d_bwd;
   GemmPlanSm100 p_fwd, p_bwd;
+  GemmPlanTc32 t_fwd, t_bwd;       // fp32 mode: bf16x3 tensor-core plans
 };
 
 struct RgieMiduHead {
   int precision = 0, dtype = 0, esz = 4;
+  int tc32 = 0;                    // fp32 mode on the tensor cores (gemm_tc32.cu); RGIE_FP32_SIMT=1 keeps the CUDA-core GEMM
   int B = 0, hw = 0, n_out = 2, n_stages = 0, C_tail = 0, NH = 0;
   MiduStage st[kMaxStages];
   Geom g_tail;
@@ -188,6 +192,13 @@ int midu_alloc(RgieMiduHead* M, void** p, size_t bytes) {
   return 0;
 }
 int midu_upload(RgieMiduHead* M, const std::vector<float>& h, void** dptr) {
+  if (M->tc32) {
+    std::vector<__nv_bfloat16> planes(3 * h.size());
+    split_weights_bf16x3(h.data(), h.size(), planes.data());
+    if (int rc = midu_alloc(M, dptr, planes.size() * 2)) return rc;
+    RGIE_CUDA_OK(cudaMemcpy(*dptr, planes.data(), planes.size() * 2, cudaMemcpyHostToDevice));
+    return 0;
+  }
   if (int rc = midu_alloc(M, dptr, h.size() * M->esz)) return rc;
   if (M->dtype == 0) {
     RGIE_CUDA_OK(cudaMemcpy(*dptr, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
@@ -231,8 +242,9 @@ void conv_desc(GemmDesc& d, const void* A, const Geom& g, int ci, const void* W,
   d.src = g; d.dst_kind = DST_SAME; d.dst = g; d.D = D; d.ldd = co; d.d_fp32 = d_fp32;
   d.bias = bias; d.relu = relu;
 }
-int midu_run(RgieMiduHead* M, const GemmDesc& d, const GemmPlanSm100& plan, cudaStream_t st) {
+int midu_run(RgieMiduHead* M, const GemmDesc& d, const GemmPlanSm100& plan, const GemmPlanTc32& tplan, cudaStream_t st) {
   if (M->precision == RGIE_PREC_BF16) return run_gemm_sm100(plan, st);
+  if (M->tc32) return run_gemm_tc32(tplan, st);
   return launch_gemm_simt(d, M->dtype, st);
 }
 }  // namespace
@@ -256,6 +268,8 @@ int rgie_midu_create(const float* const* h_tensors, int n_tensors, int n_out, in
   RgieMiduHead* M = new RgieMiduHead();
   struct Guard { RgieMiduHead* m; bool ok = false; ~Guard() { if (!ok) rgie_midu_destroy(m); } } guard{M};
   M->precision = precision; M->dtype = precision == RGIE_PREC_FP32 ? 0 : 1; M->esz = M->dtype == 0 ? 4 : 2;
+  static const int env_simt = getenv("RGIE_FP32_SIMT") ? atoi(getenv("RGIE_FP32_SIMT")) : 0;
+  M->tc32 = (precision == RGIE_PREC_FP32 && !env_simt) ? 1 : 0;
   M->B = max_batch; M->hw = hw; M->n_out = n_out;
   const int B = max_batch, esz = M->esz;
   const bool sdxl = n_tensors == 12;
@@ -319,6 +333,9 @@ int rgie_midu_create(const float* const* h_tensors, int n_tensors, int n_out, in
     if (precision == RGIE_PREC_BF16) {
       if (int rc = build_gemm_sm100(S.d_fwd, &S.p_fwd)) return rc;
       if (int rc = build_gemm_sm100(S.d_bwd, &S.p_bwd)) return rc;
+    } else if (M->tc32) {
+      if (int rc = build_gemm_tc32(S.d_fwd, &S.t_fwd)) return rc;
+      if (int rc = build_gemm_tc32(S.d_bwd, &S.t_bwd)) return rc;
     }
   }
   RGIE_CUDA_OK(cudaDeviceSynchronize());
@@ -337,7 +354,7 @@ int rgie_midu_forward(RgieMiduHead* M, const float* feat, int B, float* pred, vo
   RGIE_LAUNCH_OK();
   for (int s = 0; s < M->n_stages; ++s) {
     MiduStage& S = M->st[s];
-    if (int rc = midu_run(M, S.d_fwd, S.p_fwd, st)) return rc;
+    if (int rc = midu_run(M, S.d_fwd, S.p_fwd, S.t_fwd, st)) return rc;
     if (S.pool) {
       const long t_pool = (long)B * S.gp.H * S.gp.W * S.co;
       if (M->dtype == 0) pool2_fwd_kernel<float><<<grid_for(t_pool), 256, 0, st>>>((const float*)S.h, (float*)S.p, S.arg, S.g, S.gp, S.co, t_pool);
@@ -368,7 +385,7 @@ int rgie_midu_backward(RgieMiduHead* M, const float* dpred, float* dfeat, void* 
       else pool2_bwd_kernel<__nv_bfloat16><<<grid_for(t_in), 256, 0, st>>>((const __nv_bfloat16*)S.dp, S.arg, (const __nv_bfloat16*)S.h, (__nv_bfloat16*)S.dh, S.g, S.gp, S.co, t_in);
       RGIE_LAUNCH_OK();
     }
-    if (int rc = midu_run(M, S.d_bwd, S.p_bwd, st)) return rc;
+    if (int rc = midu_run(M, S.d_bwd, S.p_bwd, S.t_bwd, st)) return rc;
   }
   const long t_un = (long)B * 1280 * M->hw * M->hw;
   midu_unpack_kernel<<<grid_for(t_un), 256, 0, st>>>(M->dx, dfeat, M->st[0].g, 1280, t_un);

@@ -12,6 +12,7 @@
 #include <vector>
 #include "common.cuh"
 #include "gemm_sm100.cuh"
+#include "gemm_tc32.cuh"
 #include "rgie.h"
 
 namespace rgie {
@@ -491,6 +492,7 @@ struct Block {
 struct GemmOp {
   GemmDesc d;
   GemmPlanSm100 plan;
+  GemmPlanTc32 tplan;   // fp32 mode: the bf16x3 tensor-core plan (gemm_tc32.cu)
   int fused_next = 0;   // this launch also computes the NEXT op of the list (gemm_b2b_kernel)
   int absorbed = 0;     // computed by the previous launch: skipped at run time
 };
@@ -500,6 +502,7 @@ struct RgieRegressor {
   int N = 0, crop = 0, K = 0;
   int H0 = 0;
   int zz16 = 0;          // conv1 operand as 16-channel pixels read through overlapped rows (pack_crops16_kernel)
+  int tc32 = 0;          // fp32 mode on the tensor cores: weights are three bf16 planes, GEMMs run gemm_tc32_kernel
   int Hs[5] = {0, 0, 0, 0, 0};
   Geom gZZ, gDY, gS[5], gPh[5];
   std::vector<Block> blocks;
@@ -538,6 +541,14 @@ int dev_alloc(RgieRegressor* R, void** p, size_t bytes, bool zero) {
 
 // upload a host fp32 matrix as T (fp32 or bf16)
 int upload(RgieRegressor* R, const std::vector<float>& h, void** dptr) {
+  if (R->tc32) {
+    // fp32-accurate tensor-core mode: w = hi + mid + lo as three bf16 planes [3][rows][K]
+    std::vector<__nv_bfloat16> planes(3 * h.size());
+    split_weights_bf16x3(h.data(), h.size(), planes.data());
+    if (int rc = dev_alloc(R, dptr, planes.size() * 2, false)) return rc;
+    RGIE_CUDA_OK(cudaMemcpy(*dptr, planes.data(), planes.size() * 2, cudaMemcpyHostToDevice));
+    return 0;
+  }
   if (int rc = dev_alloc(R, dptr, h.size() * R->esz, false)) return rc;
   if (R->dtype == 0) {
     RGIE_CUDA_OK(cudaMemcpy(*dptr, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
@@ -568,6 +579,8 @@ int add_op(RgieRegressor* R, std::vector<GemmOp>& ops, const GemmDesc& d) {
   op.d = d;
   if (R->precision == RGIE_PREC_BF16) {
     if (int rc = build_gemm_sm100(d, &op.plan)) return rc;
+  } else if (R->tc32) {
+    if (int rc = build_gemm_tc32(d, &op.tplan)) return rc;
   }
   ops.push_back(op);
   return 0;
@@ -597,6 +610,7 @@ int fuse_b2b(RgieRegressor* R, std::vector<GemmOp>& ops) {
 int run_op_raw(RgieRegressor* R, const GemmOp& op, cudaStream_t st) {
   if (op.absorbed) return 0;
   if (R->precision == RGIE_PREC_BF16) return run_gemm_sm100(op.plan, st);
+  if (R->tc32) return run_gemm_tc32(op.tplan, st);
   return launch_gemm_simt(op.d, R->dtype, st);
 }
 // idx: position in [fwd_ops..., bwd_ops...]
@@ -663,14 +677,17 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
   RGIE_CHECK(crop_size % 32 == 0 && crop_size >= 64, "rgie_regressor_create: crop_size must be a multiple of 32");
   RGIE_CHECK(num_classes >= 1 && num_classes <= 8, "rgie_regressor_create: num_classes must be in 1..8");
   RGIE_CHECK(max_crops >= 1, "rgie_regressor_create: max_crops");
-  RGIE_CHECK(precision >= 0 && precision <= 2, "rgie_regressor_create: precision");
+  RGIE_CHECK(precision >= 0 && precision <= 3, "rgie_regressor_create: precision");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("rgie_regressor_create: no CUDA device (there is no CPU fallback)");
 
   RgieRegressor* R = new RgieRegressor();
   struct Guard { RgieRegressor* r; bool ok = false; ~Guard() { if (!ok) rgie_regressor_destroy(r); } } guard{R};
   R->precision = precision;
-  R->dtype = precision == RGIE_PREC_FP32 ? 0 : 1;
+  R->dtype = (precision == RGIE_PREC_FP32 || precision == RGIE_PREC_FP32_SIMT) ? 0 : 1;
+  // fp32 mode: GEMMs on the tensor cores with the exact bf16x3 split (RGIE_FP32_SIMT=1 forces the CUDA-core kernel)
+  static const int env_simt = getenv("RGIE_FP32_SIMT") ? atoi(getenv("RGIE_FP32_SIMT")) : 0;
+  R->tc32 = (precision == RGIE_PREC_FP32 && !env_simt) ? 1 : 0;
   R->esz = R->dtype == 0 ? 4 : 2;
   const int N = R->N = max_crops;
   R->crop = crop_size;
@@ -1232,6 +1249,47 @@ int rgie_gemm_selftest_ex(int backend, const void* A, long a_rows, int Cin, cons
   d.mask_bits = mask_bits; d.ld_mb = Cout / 32; d.D_bits = D_bits; d.ld_db = Cout / 32;
   if (backend == 1) return launch_gemm_sm100(d, (cudaStream_t)stream);
   return launch_gemm_simt(d, 1, (cudaStream_t)stream);
+}
+
+int rgie_gemm_selftest_fp32(int backend, const float* A, long a_rows, int Cin, int a_ld, const float* A2, long a2_rows,
+                            int Cin2, const float* h_W, int ntaps, const long* h_row_off, long m_begin, long m_end, int Cout,
+                            const float* bias, const float* res, const float* mask, int relu, float* D, void* stream) {
+  RGIE_CHECK(ntaps >= 1 && ntaps <= kMaxTaps && h_W != nullptr, "rgie_gemm_selftest_fp32: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmDesc d;
+  memset(&d, 0, sizeof(d));
+  const size_t ktot = (size_t)ntaps * Cin + (A2 ? Cin2 : 0);
+  d.A = A; d.a_rows = a_rows; d.Cin = Cin; d.a_ld = a_ld; d.n_pad = Cout; d.ntaps = ntaps;
+  d.A2 = A2; d.a2_rows = a2_rows; d.Cin2 = Cin2;
+  for (int t = 0; t < ntaps; ++t) d.row_off[t] = h_row_off[t];
+  d.m_begin = m_begin; d.m_end = m_end; d.Cout = Cout;
+  d.src = make_geom(1, 1, (int)m_end, 1, 0, 0, 0, 0);
+  d.dst_kind = DST_SAME; d.dst = d.src;
+  d.D = D; d.ldd = Cout; d.d_fp32 = 1; d.bias = bias;
+  d.res = res; d.ld_res = Cout; d.res_rows = m_end; d.relu = relu;
+  d.mask = mask; d.ld_mask = Cout;
+  void* w_dev = nullptr;
+  int rc = 0;
+  if (backend == 2) {
+    std::vector<__nv_bfloat16> planes(3 * (size_t)Cout * ktot);
+    split_weights_bf16x3(h_W, (size_t)Cout * ktot, planes.data());
+    RGIE_CUDA_OK(cudaMalloc(&w_dev, planes.size() * 2));
+    RGIE_CUDA_OK(cudaMemcpy(w_dev, planes.data(), planes.size() * 2, cudaMemcpyHostToDevice));
+    d.Wt = w_dev;
+    GemmPlanTc32 plan;
+    rc = build_gemm_tc32(d, &plan);
+    if (!rc) rc = run_gemm_tc32(plan, st);
+  } else {
+    RGIE_CUDA_OK(cudaMalloc(&w_dev, (size_t)Cout * ktot * 4));
+    RGIE_CUDA_OK(cudaMemcpy(w_dev, h_W, (size_t)Cout * ktot * 4, cudaMemcpyHostToDevice));
+    d.Wt = w_dev;
+    rc = launch_gemm_simt(d, 0, st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(w_dev);
+  if (rc) return rc;
+  RGIE_CUDA_OK(e);
+  return 0;
 }
 
 int rgie_gemm_selftest(int backend, const void* A, long a_rows, int Cin, const void* W, int n_pad, int ntaps,

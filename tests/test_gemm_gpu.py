@@ -180,3 +180,100 @@ def test_second_operand_and_bit_masks(case):
         if want_bits:
             got = _unpack_bits(bits, rows, Cout)
             assert torch.equal(got, out > 0), f"backend {backend}: sign bits differ from the stored values"
+
+
+# =================================================================================================================
+# fp32 parity mode on the tensor cores: gemm_tc32_kernel (exact bf16x3 operand split, six partial products) against a
+# float64 restatement and against the CUDA-core fp32 kernel
+# =================================================================================================================
+def _ref64(A, a_ld, Cin, A2, W, offs, m_begin, m_end, bias, res, mask, relu):
+    """float64 restatement; A may have overlapping rows (row m = the Cin elements starting at element m * a_ld)."""
+    dev = A.device
+    flat = A.double().flatten()
+    a_rows = (flat.numel() - Cin) // a_ld + 1 if a_ld else A.shape[0]
+    Wd = W.double().to(dev)
+    m = torch.arange(m_begin, m_end, device=dev)
+    out = torch.zeros(len(m), W.shape[0], dtype=torch.float64, device=dev)
+    cols = torch.arange(Cin, device=dev)
+    for t, off in enumerate(offs):
+        rows = m + off
+        ok = (rows >= 0) & (rows < a_rows)
+        a = torch.zeros(len(m), Cin, dtype=torch.float64, device=dev)
+        if a_ld:
+            a[ok] = flat[(rows[ok] * a_ld)[:, None] + cols[None, :]]
+        else:
+            a[ok] = A.double()[rows[ok]]
+        out += a @ Wd[:, t * Cin:(t + 1) * Cin].T
+    if A2 is not None:
+        ok = m < A2.shape[0]
+        a = torch.zeros(len(m), A2.shape[1], dtype=torch.float64, device=dev)
+        a[ok] = A2.double()[m[ok]]
+        out += a @ Wd[:, len(offs) * Cin:].T
+    if bias is not None:
+        out += bias.double()
+    if res is not None:
+        out += res.double()[m_begin:m_end]
+    if relu:
+        out = out.relu()
+    if mask is not None:
+        out = out * (mask[m_begin:m_end] > 0)
+    return out
+
+
+def _run_fp32(backend, A, a_rows, Cin, a_ld, A2, W, offs, m_begin, m_end, Cout, bias, res, mask, relu):
+    from regressor_guided_image_editing_b200 import _lib
+    from regressor_guided_image_editing_b200._lib import ptr, stream_ptr, check
+    lib = _lib.load()
+    D = torch.zeros(m_end, Cout, device=A.device, dtype=torch.float32)
+    offs_c = (C.c_long * len(offs))(*offs)
+    Wh = W.float().cpu().contiguous()
+    check(lib.rgie_gemm_selftest_fp32(backend, ptr(A), a_rows, Cin, a_ld, ptr(A2), 0 if A2 is None else A2.shape[0],
+                                      0 if A2 is None else A2.shape[1], C.c_void_p(Wh.data_ptr()), len(offs), offs_c, m_begin,
+                                      m_end, Cout, ptr(bias), ptr(res), ptr(mask), int(relu), ptr(D), stream_ptr(A.device)),
+          "gemm_selftest_fp32")
+    torch.cuda.synchronize()
+    return D[m_begin:m_end]
+
+
+FP32_CASES = [
+    # (rows, Cin, Cout, offs, m_begin, m_end_delta, bias, res, relu, mask, Cin2, a_ld)
+    (700, 64, 64, [0], 0, 0, False, False, False, False, 0, 0),
+    (3000, 256, 128, [0], 0, 0, True, True, True, False, 0, 0),
+    (2500, 128, 256, [-31, -30, -29, -1, 0, 1, 29, 30, 31], 0, 0, True, False, True, False, 0, 0),
+    (5000, 64, 16, [-(a * 227 + b) for a in range(-2, 2) for b in range(-2, 2)], 0, 0, False, False, False, False, 0, 0),
+    (4000, 128, 512, [0], 0, 0, True, False, True, False, 256, 0),          # second operand: K-concatenated downsample branch
+    (3500, 64, 256, [0], 0, 0, False, True, False, True, 0, 0),            # input-gradient form: residual + ReLU mask
+    (6000, 64, 64, [-2 * 228, -228, 0, 228], 0, 0, True, False, True, False, 0, 16),   # conv1: overlapped 16-channel rows
+    (9000, 128, 128, [3000 + d for d in (-59, -58, 0, 1)], 3000, -3000, False, False, False, False, 0, 0),
+    (1500, 512, 2048, [0], 0, 0, True, False, True, False, 0, 0),
+]
+
+
+@pytest.mark.parametrize("case", FP32_CASES, ids=[f"fp32-{i}" for i in range(len(FP32_CASES))])
+def test_fp32_tensor_core_gemm_matches_float64(case):
+    """|error| of the bf16x3 tensor-core GEMM against float64 must be at the level of the CUDA-core fp32 kernel's own error
+    (both accumulate in fp32): <= 8x the CUDA-core error + 1e-6 of the output scale, and <= 5e-6 relative to the scale."""
+    rows, Cin, Cout, offs, m_begin, m_end_delta, use_bias, use_res, relu, use_mask, Cin2, a_ld = case
+    g = torch.Generator().manual_seed(rows + Cin + Cout)
+    dev = "cuda"
+    m_end = rows + m_end_delta
+    if a_ld:
+        flat = torch.randn(rows * a_ld + Cin, generator=g)
+        A = flat.to(dev)
+        a_rows = rows
+    else:
+        A = torch.randn(rows, Cin, generator=g).to(dev)
+        a_rows = rows
+    A2 = torch.randn(rows // 2, Cin2, generator=g).to(dev) if Cin2 else None
+    W = torch.randn(Cout, len(offs) * Cin + Cin2, generator=g) / (len(offs) * Cin + Cin2) ** 0.5
+    bias = torch.randn(Cout, generator=g).to(dev) if use_bias else None
+    res = torch.randn(m_end, Cout, generator=g).to(dev) if use_res else None
+    mask = torch.randn(m_end, Cout, generator=g).to(dev) if use_mask else None
+    ref = _ref64(A, a_ld, Cin, A2, W, offs, m_begin, m_end, bias, res, mask, relu)
+    out_tc = _run_fp32(2, A, a_rows, Cin, a_ld, A2, W, offs, m_begin, m_end, Cout, bias, res, mask, relu).double()
+    out_cc = _run_fp32(0, A, a_rows, Cin, a_ld, A2, W, offs, m_begin, m_end, Cout, bias, res, mask, relu).double()
+    scale = ref.abs().max().item()
+    e_tc, e_cc = (out_tc - ref).abs().max().item(), (out_cc - ref).abs().max().item()
+    print(f"{case[:3]}: scale {scale:.3f}  tensor-core fp32 err {e_tc:.2e}  CUDA-core fp32 err {e_cc:.2e}")
+    assert e_tc <= 5e-6 * scale, (e_tc, scale)
+    assert e_tc <= 8 * e_cc + 1e-6 * scale
