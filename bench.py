@@ -393,6 +393,10 @@ def main():
         gemm_ms_per_step = tot_ms / reps_prof
         peaks, which = _peaks()
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        peak_note = " (sustained bf16 cuBLAS)"
+        if args.precision == "fp32":
+            # fp32 parity mode = exact bf16x3 operand split: six bf16 tensor instructions per fp32 product block
+            peak, peak_note = peak / 6.0, " (sustained bf16 cuBLAS / 6: the fp32 mode issues six bf16 MMAs per fp32 product block)"
         achieved = tot_fl / reps_prof / (gemm_ms_per_step / 1e3) / 1e12
         n_launch = nops * (B // eng.mb)
         # DRAM bytes per launch of the same kernel family from the committed ncu capture (profiles/*_step_B32.json:
@@ -419,7 +423,8 @@ def main():
                 "regressor_fwd_bwd_ms": regressor_span_ms,
                 "frac_of_whole_step": FLOP_PER_IMAGE_STEP * B / (ms_max / Kt / 1e3) / 1e12 / peak,
                 "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": which + " (sustained bf16 cuBLAS)", "kernel": "gemm_sm100_kernel<BN,STAGES,EPI,NEW> family",
+                "peak_source": which + peak_note,
+                "kernel": "gemm_tc32_kernel" if args.precision == "fp32" else "gemm_sm100_kernel<BN,STAGES,EPI,NEW> family",
                 "gemm_only": {"achieved": achieved, "frac": achieved / peak, "ms_per_step": gemm_ms_per_step},
                 "launches_per_step": n_launch, "gemm_ms_per_step": gemm_ms_per_step,
                 "share_of_step": gemm_ms_per_step / (ms_max / Kt),
@@ -499,7 +504,7 @@ def main():
                               f"extrapolated to {STEPS_PER_IMAGE} steps/image"}
     line = {"metric": "edited images/sec (100 steps, 512^2)", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": Kt, "warmup": done, "ms_per_step": ms_max / Kt, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else args.precision, "data": "synthetic",
+            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32 (bf16x3 split on tcgen05)", "data": "synthetic",
             "config": config, "clocks": clk_own,
             "per_rank": {"ms_per_step": [float(x[0]) / Kt for x in per_rank], "sm_mhz": [float(x[1]) for x in per_rank]},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},

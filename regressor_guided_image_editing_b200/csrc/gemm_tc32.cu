@@ -14,7 +14,11 @@
 //   warps 2..5  converters: thread r splits row r of the raw tile into the three bf16 operand tiles (SWIZZLE_128B K-major)
 //   warp 1      one thread issues the 6 x 4 tcgen05.mma of the k-block (M = 128, N = 64, K = 16)
 //   warps 6..9  epilogue: tcgen05.ld -> + bias, + residual (fp32), ReLU, ReLU mask (fp32 activation) -> fp32 rows
-// Two smem stages (raw 32 KB + operand tiles 48 KB + weights 24 KB each), two TMEM accumulators.
+// Two smem stages (raw 32 KB + operand tiles 48 KB + weights 24 KB each).  The tensor core adds into its fp32 accumulator
+// with truncation (measured: the error grows linearly with the number of accumulating instructions, 3.9e-5 of 7 at
+// K = 1152 against 6e-6 for an FMA chain), so a tile has TWO accumulators: hi*whi -- the only product of full magnitude --
+// goes to the first (K/16 instructions), the five small products (<= 2^-8 of it) to the second, and the epilogue adds the
+// two in fp32.  Two tiles in flight: 2 x 2 x 64 TMEM columns.
 // It replaces gemm_simt_kernel<float> as the fp32 mode's GEMM (gemm_simt stays as the cross-check in tests/).
 #include <stdlib.h>
 #include <vector>
@@ -89,7 +93,7 @@ gemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_base + L::TMEM_PTR_OFF),
-                 "r"(128u) : "memory");
+                 "r"(256u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (d.bias != nullptr) {
@@ -150,7 +154,8 @@ gemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int kb_total = num_kb + (m0 < d.a2_rows ? num_kb2 : 0);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t tmem_big = tmem_base + (uint32_t)(acc * 2 * BN);        // hi * whi
+        const uint32_t tmem_small = tmem_big + (uint32_t)BN;                   // the five small products
         for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(full_bar(stage), phase);          // the weight planes have landed
           mbar_wait(conv_bar(stage), phase);          // the three operand tiles are written
@@ -159,9 +164,11 @@ gemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int pr = 0; pr < 6; ++pr) {
             const uint64_t adesc = make_smem_desc(smem_base + L::A_OFF + (stage * 3 + kPairA[pr]) * TC_A_PLANE);
             const uint64_t bdesc = make_smem_desc(smem_base + L::W_OFF + (stage * 3 + kPairW[pr]) * TC_W_PLANE);
+            const uint32_t tmem_d = pr == 5 ? tmem_big : tmem_small;
+            const int first = pr == 5 ? 0 : pr;        // pair 5 opens the big accumulator, pair 0 the small one
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | pr | k) != 0 ? 1u : 0u);
+              umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | first | k) != 0 ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -231,17 +238,18 @@ gemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (m < d.m_end) dest = map_row(d.src, d.dst_kind, d.dst, m);
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * BN);
 #pragma unroll
       for (int ci = 0; ci < BN / CH; ++ci) {
-        uint32_t r[CH];
+        uint32_t r[CH], r2[CH];
         tmem_ld<CH>(taddr + (uint32_t)(ci * CH), r);
+        tmem_ld<CH>(taddr + (uint32_t)(BN + ci * CH), r2);
         tmem_ld_wait();
         const int n0 = nt * BN + ci * CH;
         if (dest >= 0 && n0 < d.Cout) {
           float v[CH];
 #pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
+          for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
           if (d.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < CH; ++j) v[j] += sbias[n0 + j];
@@ -282,7 +290,7 @@ gemm_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
   }
 }
 

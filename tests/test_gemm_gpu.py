@@ -186,11 +186,10 @@ def test_second_operand_and_bit_masks(case):
 # fp32 parity mode on the tensor cores: gemm_tc32_kernel (exact bf16x3 operand split, six partial products) against a
 # float64 restatement and against the CUDA-core fp32 kernel
 # =================================================================================================================
-def _ref64(A, a_ld, Cin, A2, W, offs, m_begin, m_end, bias, res, mask, relu):
+def _ref64(A, a_rows, a_ld, Cin, A2, W, offs, m_begin, m_end, bias, res, mask, relu):
     """float64 restatement; A may have overlapping rows (row m = the Cin elements starting at element m * a_ld)."""
     dev = A.device
     flat = A.double().flatten()
-    a_rows = (flat.numel() - Cin) // a_ld + 1 if a_ld else A.shape[0]
     Wd = W.double().to(dev)
     m = torch.arange(m_begin, m_end, device=dev)
     out = torch.zeros(len(m), W.shape[0], dtype=torch.float64, device=dev)
@@ -269,7 +268,7 @@ def test_fp32_tensor_core_gemm_matches_float64(case):
     bias = torch.randn(Cout, generator=g).to(dev) if use_bias else None
     res = torch.randn(m_end, Cout, generator=g).to(dev) if use_res else None
     mask = torch.randn(m_end, Cout, generator=g).to(dev) if use_mask else None
-    ref = _ref64(A, a_ld, Cin, A2, W, offs, m_begin, m_end, bias, res, mask, relu)
+    ref = _ref64(A, a_rows, a_ld, Cin, A2, W, offs, m_begin, m_end, bias, res, mask, relu)
     out_tc = _run_fp32(2, A, a_rows, Cin, a_ld, A2, W, offs, m_begin, m_end, Cout, bias, res, mask, relu).double()
     out_cc = _run_fp32(0, A, a_rows, Cin, a_ld, A2, W, offs, m_begin, m_end, Cout, bias, res, mask, relu).double()
     scale = ref.abs().max().item()
