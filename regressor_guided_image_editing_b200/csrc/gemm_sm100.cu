@@ -16,8 +16,8 @@
 //   * 640 threads, 16 epilogue warps (epilogue_lean_role, setmaxnreg register hand-over) for 256-wide bf16 tiles; output by
 //     32-byte global stores or, where destination rows = source rows, through shared-memory boxes + one TMA store per part;
 //   * gemm_sm100_2cta_kernel: CTA pairs (cta_group::2, M = 256 across a TPC) for contractions >= 768;
-//   * 8-warp TMA-store epilogues (EPI 1 / 2 / 4), tile pairing (PAIR), gemm_b2b_kernel: measured alternatives kept behind
-//     environment switches;
+//   * lean role with DMA threads (EPI 9): output AND residual move by TMA through in-place half boxes;
+//   * gemm_b2b_kernel (opt-in): a 256-wide 1x1 stage and the next layer's 256 -> 64 reduction in one launch;
 //   * gemm_patch_kernel (16 x 8 pixel patch tiles, resident weights) for the 64-channel multi-tap convolutions and
 //     conv_hshare_kernel (horizontal taps as N) for the conv1 input gradient.
 #include <stdlib.h>
@@ -29,21 +29,18 @@ namespace rgie {
 
 namespace {
 
-// EPI selects the epilogue: 0 = row-per-thread global accesses (any destination mapping, fp32 or bf16 output);
-// 1 = output tile staged in shared memory and written by TMA stores (DST_SAME bf16 outputs: every global write is a
-// full-line bulk transfer instead of 32 scattered sectors per warp instruction); 2 or 4 = 1 + the residual operand arrives
-// by TMA loads issued EPI chunks ahead (4 = a whole tile ahead).  Staging boxes are 128 rows x 32 columns (64-byte rows,
-// SWIZZLE_64B): per column half two output boxes and EPI residual boxes of 8 KB.
+// EPI selects the epilogue: 0 = row-per-thread global accesses (any destination mapping, fp32 or bf16 output; 8 or 16 warps);
+// 8 = lean 16-warp role whose output leaves through four 128 x 64 SWIZZLE_128B boxes and TMA stores; 9 = 8 + the residual
+// operand arrives by TMA as well (in-place half boxes of 128 x 32, SWIZZLE_64B, served by two DMA threads).
 constexpr int EPI_BOX_BYTES = BM * 32 * 2;
-template <int BN, int STAGES, int EPI, bool PAIR = false>
+template <int BN, int STAGES, int EPI>
 struct SmemLayout {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
-  static constexpr int A_BYTES = (PAIR ? 2 : 1) * A_STAGE_BYTES;   // PAIR: two M-adjacent 128-row tiles per stage
+  static constexpr int A_BYTES = A_STAGE_BYTES;
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = STAGES * A_BYTES;
-  static constexpr int OB_OFF = B_OFF + STAGES * B_STAGE_BYTES;                 // [half][2] output boxes
-  static constexpr int RB_OFF = OB_OFF + (EPI >= 8 ? 4 * BM * 128 : (EPI >= 1 ? 4 * EPI_BOX_BYTES : 0));    // [half][EPI] residual boxes
-  static constexpr int BAR_OFF = RB_OFF + ((EPI >= 2 && EPI < 8) ? 2 * EPI * EPI_BOX_BYTES : 0);   // full[S], empty[S], tfull[2], tempty[2], rfull[8], ready[8]
+  static constexpr int OB_OFF = B_OFF + STAGES * B_STAGE_BYTES;                 // output boxes (EPI 8: 4 x 16 KB, EPI 9: 8 x 8 KB)
+  static constexpr int BAR_OFF = OB_OFF + (EPI >= 8 ? 4 * BM * 128 : 0);       // full[S], empty[S], tfull[2], tempty[2], rfull[8], ready[8]
   static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * STAGES + 20) * 8;
   static constexpr int BIAS_OFF = TMEM_PTR_OFF + 16;                // whole bias vector (<= MAX_BIAS floats)
   static constexpr int TOTAL = BIAS_OFF + MAX_BIAS * 4;
@@ -59,173 +56,6 @@ struct PatchMap {
   FastDiv fd_wt;
 };
 
-// ===================== store epilogue (EPI 1 / 2): BN == 256, DST_SAME, bf16 output =====================
-// The 8 epilogue warps form two groups of 4 (column halves of 128); a group walks its 32-column chunks, tile after tile.
-// Per chunk: tcgen05.ld -> (+bias, +residual from the TMA-loaded box, ReLU, bit mask; pad rows and rows >= m_end forced
-// to 0) -> bf16 -> st.shared into a swizzled 128x32 box -> one named barrier -> the group leader issues the TMA store of
-// that box and the TMA load of the residual box the group will need one tile later.  Pad rows receive zeros (they are
-// zero by construction), rows >= m_end are clipped by the tensor map.
-template <int BN, int EPI>
-__device__ __forceinline__ void epilogue_store_role(const GemmDesc& d, const CUtensorMap* tmD, const CUtensorMap* tmR,
-                                                    const float* sbias, const uint32_t ob_smem, const uint32_t rb_smem,
-                                                    const uint32_t rfull0, const uint32_t tmem_base, const uint32_t tfull0,
-                                                    const uint32_t tempty0, const int warp, const int lane,
-                                                    const int num_tiles, const int num_n_tiles, const FastDiv fd_nt) {
-  constexpr int CH = 32;
-  constexpr int CPW = BN / 64;                     // chunks per group per tile
-  static_assert(CPW == 4, "the store epilogue is instantiated for BN = 256");
-  auto tfull_bar = [&](int a) { return tfull0 + 8u * a; };
-  auto tempty_bar = [&](int a) { return tempty0 + 8u * a; };
-  const int q = warp & 3;
-  const int half = (warp - 2) >> 2;
-  const int row = q * 32 + lane;
-  const int c_begin = half * CPW;
-  const bool leader = (warp == 2 + 4 * half) && lane == 0;
-  constexpr int NRB = EPI >= 2 ? EPI : 1;          // residual boxes per group (power of two)
-  const bool has_res = EPI >= 2 && d.res != nullptr;
-  const bool has_bias = d.bias != nullptr;
-  const uint32_t* mbits = d.mask_bits;
-  // this thread's 64-byte row inside a box: 16-byte piece j lives at piece (j ^ ((row >> 1) & 3))  (SWIZZLE_64B)
-  const uint32_t row_off = (uint32_t)row * 64u;
-  const uint32_t swz = (uint32_t)((row >> 1) & 3);
-  auto ob_addr = [&](int b) { return ob_smem + (uint32_t)((half * 2 + b) * EPI_BOX_BYTES); };
-  auto rb_addr = [&](int b) { return rb_smem + (uint32_t)((half * NRB + b) * EPI_BOX_BYTES); };
-  auto rfull_bar = [&](int b) { return rfull0 + 8u * (half * NRB + b); };
-
-  // residual boxes: chunk sequence s = it * CPW + ci uses box s % NRB and is loaded NRB chunks ahead
-  int p_tile = blockIdx.x, p_ci = 0, p_s = 0;
-  auto res_issue = [&]() {        // leader only
-    if (p_tile < num_tiles) {
-      const int mt = (int)fd_nt.div((uint32_t)p_tile), nt = p_tile - mt * num_n_tiles;
-      const int b = p_s & (NRB - 1);
-      mbar_expect_tx(rfull_bar(b), EPI_BOX_BYTES);
-      tma_load_2d(rb_addr(b), tmR, nt * BN + (c_begin + p_ci) * CH, (int)(d.m_begin + (long)mt * BM), rfull_bar(b));
-    }
-    ++p_s;
-    if (++p_ci == CPW) { p_ci = 0; p_tile += gridDim.x; }
-  };
-  if (has_res && leader) {
-#pragma unroll
-    for (int i = 0; i < NRB; ++i) res_issue();
-  }
-
-  uint32_t bits_nxt[CPW];
-  auto bits_fetch = [&](int tile) {
-#pragma unroll
-    for (int i = 0; i < CPW; ++i) bits_nxt[i] = 0u;
-    if (mbits != nullptr && tile < num_tiles) {
-      const int mt = (int)fd_nt.div((uint32_t)tile), nt = tile - mt * num_n_tiles;
-      const long m = d.m_begin + (long)mt * BM + row;
-      if (m < d.m_end) {
-        const int w0 = (nt * BN) / 32 + c_begin;
-#pragma unroll
-        for (int i = 0; i < CPW; ++i) bits_nxt[i] = __ldg(mbits + bits_index(m, w0 + i, d.ld_mb));
-      }
-    }
-  };
-  bits_fetch(blockIdx.x);
-
-  int it = 0, s = 0;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-    const int mt = (int)fd_nt.div((uint32_t)tile), nt = tile - mt * num_n_tiles;
-    const int acc = it & 1;
-    const uint32_t acc_phase = (it >> 1) & 1;
-    const long m0 = d.m_begin + (long)mt * BM;
-    const long m = m0 + row;
-    long dest = -1;
-    if (m < d.m_end) dest = map_row(d.src, d.dst_kind, d.dst, m);
-    const bool live = dest >= 0;
-    const bool use_res = has_res && live && m < d.res_rows;
-    uint32_t bits_cur[CPW], bits_out[CPW];
-#pragma unroll
-    for (int i = 0; i < CPW; ++i) { bits_cur[i] = bits_nxt[i]; bits_out[i] = 0u; }
-    bits_fetch(tile + gridDim.x);
-    mbar_wait(tfull_bar(acc), acc_phase);
-    tcgen05_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-    uint32_t racc[2][CH];
-    tmem_ld<CH>(taddr + (uint32_t)(c_begin * CH), racc[0]);
-#pragma unroll
-    for (int ci = 0; ci < CPW; ++ci, ++s) {
-      const int c = c_begin + ci;
-      const int b = s & 1;
-      tmem_ld_wait();
-      if (ci + 1 < CPW) tmem_ld<CH>(taddr + (uint32_t)((c + 1) * CH), racc[(ci + 1) & 1]);   // in flight during this chunk
-      const uint32_t* r = racc[ci & 1];
-      const int n0 = nt * BN + c * CH;
-      float v[CH];
-#pragma unroll
-      for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
-      if (has_res) {
-        const int rb = s & (NRB - 1);
-        mbar_wait(rfull_bar(rb), (uint32_t)((s / NRB) & 1));
-        if (use_res) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t w4[4];
-            lds128(rb_addr(rb) + row_off + (((uint32_t)j ^ swz) << 4), w4);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { v[8 * j + 2 * e] += bf16_lo(w4[e]); v[8 * j + 2 * e + 1] += bf16_hi(w4[e]); }
-          }
-        }
-      }
-      if (has_bias) {
-        const float4* b4 = reinterpret_cast<const float4*>(sbias + n0);
-#pragma unroll
-        for (int j = 0; j < CH / 4; ++j) {
-          const float4 bb = b4[j];
-          v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
-        }
-      }
-      uint32_t keep = live ? 0xFFFFFFFFu : 0u;     // pad rows / rows >= m_end store zeros
-      if (mbits != nullptr) keep &= bits_cur[ci];
-      if (d.relu) {
-#pragma unroll
-        for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
-        if (d.D_bits != nullptr) {
-          uint32_t w = 0u;
-#pragma unroll
-          for (int j = CH - 1; j >= 0; --j) w = push_positive_bit(w, v[j]);
-          bits_out[ci] = w & keep;
-        }
-      } else if (d.D_bits != nullptr) {
-        uint32_t w = 0u;
-#pragma unroll
-        for (int j = 0; j < CH; ++j) w |= (v[j] > 0.f ? 1u : 0u) << j;
-        bits_out[ci] = w & keep;
-      }
-      if (keep != 0xFFFFFFFFu) {
-#pragma unroll
-        for (int j = 0; j < CH; ++j) v[j] = keep_if_bit(v[j], keep, j);
-      }
-      uint32_t pk[CH / 2];
-#pragma unroll
-      for (int j = 0; j < CH / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-      // box b was handed to the TMA store two chunks ago; the barrier of the previous chunk (after the leader's
-      // wait_group.read) guarantees that store has finished reading it
-#pragma unroll
-      for (int j = 0; j < 4; ++j) sts128(ob_addr(b) + row_off + (((uint32_t)j ^ swz) << 4), pk + 4 * j);
-      fence_async_smem();
-      if (leader) bulk_wait_read0();               // the store of the previous chunk (other box) has read its box
-      named_bar_sync(1 + half, 128);
-      if (leader) {
-        tma_store_2d(tmD, ob_addr(b), n0, (int)m0);
-        bulk_commit();
-        if (has_res) res_issue();                  // this chunk's residual box is free again: fetch the chunk NRB steps ahead
-      }
-    }
-    if (live && d.D_bits != nullptr) {
-      const int w0 = (nt * BN) / 32 + c_begin;
-#pragma unroll
-      for (int i = 0; i < CPW; ++i) d.D_bits[bits_index(dest, w0 + i, d.ld_db)] = bits_out[i];
-    }
-    tcgen05_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(tempty_bar(acc));
-  }
-  if (leader) bulk_wait0();
-}
-
 // ===================== epilogue role (8 warps; one TMEM lane = one output row per thread) =====================
 // warps 2..9: lane quarter q = warp & 3 (hardware restriction on tcgen05.ld), column half = (warp - 2) >> 2.
 // A thread walks the 32-column chunks of its row / column half, tile after tile.  Operands it has to read:
@@ -240,13 +70,10 @@ __device__ __forceinline__ void epilogue_store_role(const GemmDesc& d, const CUt
 // TSPLIT = true : the warp groups take alternate TILES (all columns; NACC accumulator buffers, one arrive group per
 //                 buffer): with narrow N tiles the epilogue of a tile is a latency chain, not a throughput problem, so
 //                 two tiles in flight halve its cost.
-// PAIR = true   : the CTA's tile sequence is made of PAIRS of M-adjacent tiles of the same N tile (num_tiles counts
-//                 pairs); the producer loads each weight tile once per pair.  Tile 2k / 2k+1 of the sequence use
-//                 accumulator 0 / 1, exactly like consecutive tiles do without pairing, so only the decode changes.
 // TWO = true    : CTA-pair patch kernel (cta_group::2): the tile sequence of a CTA is unchanged (CTA b walks tiles b, b + grid,
 //                 ...; CTAs 2c and 2c + 1 walk M-adjacent tiles in lockstep), only the accumulator-free arrive goes to the
 //                 LEADER CTA's barrier (remotely for the peer).
-template <int BN, int NEW, bool TSPLIT = false, int NACC = 2, bool PAIR = false, bool TWO = false>
+template <int BN, int NEW, bool TSPLIT = false, int NACC = 2, bool TWO = false>
 __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sbias, const uint32_t tmem_base,
                                               const uint32_t tfull0, const uint32_t tempty0, const int warp, const int lane,
                                               const int num_tiles, const int num_n_tiles, const FastDiv fd_nt,
@@ -287,14 +114,6 @@ __device__ __forceinline__ void epilogue_role(const GemmDesc& d, const float* sb
   const __nv_bfloat16* cres = nullptr;             // residual row of the current tile
   // seq-th tile of this warp group -> (mt, nt); false past the end
   auto decode = [&](int seq, int& mt, int& nt) -> bool {
-    if (PAIR) {
-      const int pr = (int)blockIdx.x + (seq >> 1) * (int)gridDim.x;
-      if (pr >= num_tiles) return false;
-      const int mp = (int)fd_nt.div((uint32_t)pr);
-      nt = pr - mp * num_n_tiles;
-      mt = 2 * mp + (seq & 1);
-      return true;
-    }
     const int tile = tile0 + seq * tile_step;
     if (tile >= num_tiles) return false;
     mt = (int)fd_nt.div((uint32_t)tile);
@@ -810,14 +629,13 @@ __device__ __forceinline__ void epilogue_dma_thread(const GemmDesc& d, const CUt
   bulk_wait0();
 }
 
-template <int BN, int STAGES, int EPI, int NEW, bool PAIR>
+template <int BN, int STAGES, int EPI, int NEW>
 __global__ void __launch_bounds__(num_threads(NEW), 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
                   const __grid_constant__ CUtensorMap tmR, const GemmDesc d, const int num_m_tiles, const int num_n_tiles,
                   const FastDiv fd_nt) {
-  using L = SmemLayout<BN, STAGES, EPI, PAIR>;
-  static_assert(!PAIR || EPI == 0, "tile pairing uses the row-per-thread epilogue");
+  using L = SmemLayout<BN, STAGES, EPI>;
   constexpr uint32_t TMEM_COLS = tmem_cols(BN);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -893,17 +711,14 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = (PAIR ? 2 : 1) * (int)fd_nt.div((uint32_t)tile);
-        const int nt = tile - (int)fd_nt.div((uint32_t)tile) * num_n_tiles;
+        const int mt = (int)fd_nt.div((uint32_t)tile);
+        const int nt = tile - mt * num_n_tiles;
         const long m0 = d.m_begin + (long)mt * BM;
         int tap = 0, cb = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           mbar_expect_tx(full_bar(stage), L::A_BYTES + L::B_STAGE_BYTES);
           tma_load_2d(smem_base + L::A_OFF + stage * L::A_BYTES, &tmA, cb * BK, (int)(m0 + d.row_off[tap]), full_bar(stage));
-          if (PAIR)
-            tma_load_2d(smem_base + L::A_OFF + stage * L::A_BYTES + A_STAGE_BYTES, &tmA, cb * BK,
-                        (int)(m0 + BM + d.row_off[tap]), full_bar(stage));
           tma_load_2d(smem_base + L::B_OFF + stage * L::B_STAGE_BYTES, &tmB, kb * BK, nt * BN, full_bar(stage));
           if (++cb == kb_per_tap) { cb = 0; ++tap; }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -913,9 +728,6 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait(empty_bar(stage), phase ^ 1);
             mbar_expect_tx(full_bar(stage), L::A_BYTES + L::B_STAGE_BYTES);
             tma_load_2d(smem_base + L::A_OFF + stage * L::A_BYTES, &tmA2, kb * BK, (int)m0, full_bar(stage));
-            if (PAIR)
-              tma_load_2d(smem_base + L::A_OFF + stage * L::A_BYTES + A_STAGE_BYTES, &tmA2, kb * BK, (int)(m0 + BM),
-                          full_bar(stage));
             tma_load_2d(smem_base + L::B_OFF + stage * L::B_STAGE_BYTES, &tmB, (num_kb + kb) * BK, nt * BN, full_bar(stage));
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -929,13 +741,12 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it += (PAIR ? 2 : 1)) {
-        const int acc = it & 1;                    // PAIR: it is even, the pair uses accumulators 0 and 1
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        const long m0 = d.m_begin + (long)((PAIR ? 2 : 1) * (int)fd_nt.div((uint32_t)tile)) * BM;
+        const long m0 = d.m_begin + (long)((int)fd_nt.div((uint32_t)tile)) * BM;
         const int kb_total = num_kb + (m0 < d.a2_rows ? num_kb2 : 0);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-        if (PAIR) mbar_wait(tempty_bar(1), acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < kb_total; ++kb) {
@@ -948,35 +759,23 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr>>4) start field
             umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          if (PAIR) {
-            const uint64_t adesc1 = make_smem_desc(smem_base + L::A_OFF + stage * L::A_BYTES + A_STAGE_BYTES);
-#pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_bf16(tmem_base + (uint32_t)BN, adesc1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                        (kb | k) != 0 ? 1u : 0u);
-          }
           umma_commit(empty_bar(stage));          // frees the smem slot once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar(acc));              // accumulator(s) complete -> epilogue
-        if (PAIR) umma_commit(tfull_bar(1));
+        umma_commit(tfull_bar(acc));              // accumulator complete -> epilogue
       }
     }
   } else if constexpr (NEW == 16) {
-    static_assert((EPI == 0 || EPI == 8 || EPI == 9) && !PAIR, "16 epilogue warps: lean epilogue (row-per-thread or TMA-store) only");
+    static_assert(EPI == 0 || EPI == 8 || EPI == 9, "16 epilogue warps: lean epilogue (row-per-thread, TMA-store or DMA) only");
     // warps 2, 3: idle members of the producer warpgroup -- with EPI 9 their lane 0 is a DMA thread of the epilogue
     if constexpr (EPI == 9) {
       if (lane == 0)
         epilogue_dma_thread<BN>(d, &tmD, &tmR, rfull_bar(0), rfull_bar(8), (warp - 2) * 2, num_tiles, num_n_tiles, fd_nt,
                                 smem_base + L::OB_OFF);
     }
-  } else if constexpr (EPI >= 1) {
-    static_assert(EPI == 0 || EPI >= 8 || NEW == 8, "the store epilogue runs with 8 epilogue warps");
-    epilogue_store_role<BN, EPI>(d, &tmD, &tmR, reinterpret_cast<const float*>(smem + L::BIAS_OFF), smem_base + L::OB_OFF,
-                                 smem_base + L::RB_OFF, rfull_bar(0), tmem_base, tfull_bar(0), tempty_bar(0), warp, lane,
-                                 num_tiles, num_n_tiles, fd_nt);
   } else {
-    epilogue_role<BN, NEW, false, 2, PAIR>(d, reinterpret_cast<const float*>(smem + L::BIAS_OFF), tmem_base, tfull_bar(0),
+    static_assert(EPI == 0, "8 epilogue warps: the row-per-thread role");
+    epilogue_role<BN, NEW, false, 2>(d, reinterpret_cast<const float*>(smem + L::BIAS_OFF), tmem_base, tfull_bar(0),
                                            tempty_bar(0), warp, lane, num_tiles, num_n_tiles, fd_nt,
                                            PatchMap{0, 0, 0, FastDiv{1, 0, 0}});
   }
@@ -1825,7 +1624,7 @@ gemm_patch_2cta_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_co
       }
     }
   } else {
-    epilogue_role<BN, 8, true, NACC, false, true>(d, reinterpret_cast<const float*>(smem + L::BIAS_OFF), tmem_base, tfull_bar(0),
+    epilogue_role<BN, 8, true, NACC, true>(d, reinterpret_cast<const float*>(smem + L::BIAS_OFF), tmem_base, tfull_bar(0),
                                                   tempty_bar(0), warp, lane, num_tiles, 1, FastDiv{1, 0, 0}, pm);
   }
 
@@ -2156,19 +1955,17 @@ int run_2cta(const GemmPlanSm100& p, cudaStream_t st) {
   return 0;
 }
 
-template <int BN, int STAGES, int EPI, int NEW, bool PAIR = false>
+template <int BN, int STAGES, int EPI, int NEW>
 int run_impl(const GemmPlanSm100& p, cudaStream_t st) {
-  using L = SmemLayout<BN, STAGES, EPI, PAIR>;
+  using L = SmemLayout<BN, STAGES, EPI>;
   static DeviceOnce attr_once;
   if (attr_once.needed()) {
-    RGIE_CUDA_OK(cudaFuncSetAttribute(gemm_sm100_kernel<BN, STAGES, EPI, NEW, PAIR>,
+    RGIE_CUDA_OK(cudaFuncSetAttribute(gemm_sm100_kernel<BN, STAGES, EPI, NEW>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
     attr_once.done();
   }
-  // PAIR: the kernel walks pairs of M-adjacent tiles (num_m_tiles then counts pairs)
-  const int m_units = PAIR ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
-  gemm_sm100_kernel<BN, STAGES, EPI, NEW, PAIR><<<p.grid, num_threads(NEW), L::DYN_BYTES, st>>>(
-      p.tmA, p.tmA2, p.tmB, p.tmD, p.tmR, p.d, m_units, p.num_n_tiles, make_fastdiv((uint32_t)p.num_n_tiles));
+  gemm_sm100_kernel<BN, STAGES, EPI, NEW><<<p.grid, num_threads(NEW), L::DYN_BYTES, st>>>(
+      p.tmA, p.tmA2, p.tmB, p.tmD, p.tmR, p.d, p.num_m_tiles, p.num_n_tiles, make_fastdiv((uint32_t)p.num_n_tiles));
   RGIE_LAUNCH_OK();
   return 0;
 }
@@ -2275,56 +2072,37 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
   int sms = gemm_sm100_num_sms();
   p->grid = (int)(tiles < sms ? tiles : sms);
   if (p->grid < 1) p->grid = 1;
-  // epilogue variant (measured per shape class on B200, profiles/README.md): 256-wide bf16 tiles use the 16-warp lean epilogue
-  // (setmaxnreg: producer warpgroup 32 registers, epilogue warpgroups 112); where the destination rows are the source rows
-  // (DST_SAME) and the launch is HBM-bound (contraction < 768) its output leaves through shared-memory boxes and TMA stores
-  // (-17: ncu showed the L1TEX LSU data pipe 73-82 % busy with the 32-byte row-per-thread stores; 0.61 -> 0.53, 0.89 -> 0.77,
-  // 0.50 -> 0.41, 0.29 -> 0.23 ms on the layer1-3 expansions).  Everything else takes the classic 8-warp row-per-thread epilogue.
-  // RGIE_GEMM_EPI = 0 (classic everywhere) / 1 / 2 / 4 (8-warp TMA-store variants) / -16 (lean without the TMA-store path) for
-  // A/B experiments.
+  // Epilogue variant (measured per shape class on B200, profiles/README.md).  256-wide bf16 tiles take the 16-warp lean role
+  // (setmaxnreg: producer warpgroup 32 registers, epilogue warpgroups 112): -16.  Where the destination rows are the source
+  // rows (DST_SAME) and the launch is HBM-bound (contraction < 768) the output leaves through shared-memory boxes and TMA
+  // stores: -17 (ncu: the L1TEX LSU data pipe was 73-82 % busy with the 32-byte row-per-thread stores; 0.61 -> 0.53,
+  // 0.89 -> 0.77, 0.50 -> 0.41, 0.29 -> 0.23 ms on the layer1-3 expansions).  -18: the same launches with the residual
+  // operand ALSO moved by TMA (epilogue_lean_dma_role: in-place half boxes served by two DMA threads); measured (320 crops,
+  // same box): conv1 input gradient + skip of layer1 0.875 -> 0.773 ms, of layer2 0.455 -> 0.389 ms, conv3 + skip 0.768 ->
+  // 0.746 / 0.412 -> 0.389 ms, GEMM family 30.7 -> 30.0 ms per micro-batch, step 74.7 -> 73.6 ms.  Everything else takes the
+  // classic 8-warp row-per-thread role: 0.
+  // Switches for A/B runs: RGIE_GEMM_EPI = 0 (classic everywhere) / -16 (lean without the TMA-store path);
+  // RGIE_LEAN_DMA = 0 (keep -17) / 1 (default: -18 for the ops that have a residual) / 2 (-18 for every -17 op).
+  // Variants that were measured and LOST are no longer in the file (numbers in profiles/README.md): 8-warp TMA-store
+  // epilogues, two M tiles per weight load inside one CTA, CTA pairs for 128-wide tiles.
   static const int env_epi = getenv("RGIE_GEMM_EPI") ? atoi(getenv("RGIE_GEMM_EPI")) : -1;
   const int ktot = d.ntaps * d.Cin + (d.A2 ? d.Cin2 : 0);
-  const bool lean_ok = bn == 256 && !d.d_fp32 && d.mask == nullptr;
-  p->epi = (lean_ok && (env_epi == -16 || env_epi == -1 || env_epi == -17)) ? -16 : 0;
-  if ((env_epi == -17 || env_epi == -1) && lean_ok && d.dst_kind == DST_SAME && ktot < 768) p->epi = -17;
-  // -18: the same launches with the residual operand ALSO moved by TMA (epilogue_lean_dma_role: in-place half boxes served by
-  // two DMA threads).  RGIE_LEAN_DMA=0 keeps -17, =1 (default) uses it for the ops that have a residual, =2 for every -17 op.
-  // Measured (B200, 320 crops, same box): conv1 input gradient + skip of layer1 0.875 -> 0.773 ms, of layer2 0.455 -> 0.389 ms,
-  // conv3 + skip 0.768 -> 0.746 / 0.412 -> 0.389 ms; GEMM family 30.7 -> 30.0 ms per micro-batch, step 74.7 -> 73.6 ms.
+  const bool lean_ok = bn == 256 && !d.d_fp32 && d.mask == nullptr && env_epi != 0;
+  p->epi = lean_ok ? -16 : 0;
+  if (lean_ok && env_epi != -16 && d.dst_kind == DST_SAME && ktot < 768) p->epi = -17;
   static const int env_dma = getenv("RGIE_LEAN_DMA") ? atoi(getenv("RGIE_LEAN_DMA")) : 1;
   if (p->epi == -17 && env_dma > 0 && (d.res != nullptr || env_dma >= 2) && d.ldd % 32 == 0 && (d.res == nullptr || d.ld_res % 32 == 0))
     p->epi = -18;
-  if (bn == 256 && d.dst_kind == DST_SAME && !d.d_fp32 && d.mask == nullptr && env_epi >= 1) {
-    if (d.res != nullptr) {
-      if (env_epi == 2 || env_epi == 4) p->epi = env_epi;
-    } else if (env_epi >= 1 && ktot <= 768) {
-      p->epi = 1;
-    }
-  }
   // CTA pairs (cta_group::2, M = 256 across the two SMs of a TPC) for the tensor-bound 256-wide tiles: contraction >= 768.
   // Measured (320 crops, same box, clock drift removed): K >= 1024 layers -6 % (1.36-1.47 PFLOP/s); K <= 640 layers are
   // epilogue-bound and LOSE 7-28 % (the leader's MMA waits for the epilogues of BOTH CTAs across the TPC), so they stay on
   // the single-CTA kernel.  RGIE_GEMM_2CTA = 0 switches pairs off, = K sets the contraction threshold.
   static const int env_2cta = getenv("RGIE_GEMM_2CTA") ? atoi(getenv("RGIE_GEMM_2CTA")) : 768;
-  // 128-wide tiles (the 3x3 convs of layer2, K = 1152): same kernel with 64 weight rows per CTA.  MEASURED: slower than the
-  // single-CTA 128-wide kernel (0.30 -> 0.35 ms per launch, 320 crops), so it is opt-in: RGIE_GEMM_2CTA128=1.
-  static const int env_2cta128 = getenv("RGIE_GEMM_2CTA128") ? atoi(getenv("RGIE_GEMM_2CTA128")) : 0;
-  const bool pair128 = bn == 128 && env_2cta128 && !d.d_fp32 && d.mask == nullptr && (env_epi == -1 || env_epi == -16);
-  if ((p->epi == -16 || pair128) && env_2cta > 0 && ktot >= env_2cta && p->num_m_tiles >= 2) {
+  if (p->epi == -16 && env_2cta > 0 && ktot >= env_2cta && p->num_m_tiles >= 2) {
     p->epi = -32;
     const long pairs = (long)((p->num_m_tiles + 1) / 2) * p->num_n_tiles;
     const long ctas = 2 * pairs < (long)(sms & ~1) ? 2 * pairs : (long)(sms & ~1);
     p->grid = (int)ctas;
-  }
-  // tile pairing (two M-adjacent tiles share every weight-tile load): the large-K layers are bound by the L2->SM operand
-  // feed (48 KB per 128x256x64 k-block vs ~54 B/clk/SM measured), pairing cuts it to 32 KB per k-block and tile
-  //      MEASURED: no gain on B200 (N=256,K=2304: 0.242 -> 0.275 ms; N=512,K=4608: 0.240 -> 0.234 ms per 320 crops): these layers
-  //      already run at 88-91 % of the sustained (power-capped) cuBLAS rate, the operand feed is not their limiter.  Off by default.
-  static const int env_pair = getenv("RGIE_GEMM_PAIR_MINK") ? atoi(getenv("RGIE_GEMM_PAIR_MINK")) : 0;
-  if (bn == 256 && (p->epi == 0 || p->epi == -16) && env_pair > 0 && ktot >= env_pair && p->num_m_tiles >= 2) {
-    p->epi = -2;
-    const long pairs = (long)((p->num_m_tiles + 1) / 2) * p->num_n_tiles;
-    p->grid = (int)(pairs < sms ? pairs : sms);
   }
   p->tmD = p->tmA; p->tmR = p->tmA;
   int rc = 0;
@@ -2341,15 +2119,6 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
       rc = make_map_2d(&p->tmR, d.res, (uint64_t)d.ld_res, (uint64_t)rr, 32, BM, CU_TENSOR_MAP_SWIZZLE_64B);
       if (rc) return rc;
     }
-  }
-  if (p->epi >= 1) {
-    rc = make_map_2d(&p->tmD, d.D, (uint64_t)d.ldd, (uint64_t)d.m_end, 32, BM, CU_TENSOR_MAP_SWIZZLE_64B);
-    if (rc) return rc;
-  }
-  if (p->epi >= 2) {
-    const long rr = d.res_rows < d.m_end ? d.res_rows : d.m_end;
-    rc = make_map_2d(&p->tmR, d.res, (uint64_t)d.ld_res, (uint64_t)rr, 32, BM, CU_TENSOR_MAP_SWIZZLE_64B);
-    if (rc) return rc;
   }
   rc = make_map_2d(&p->tmA, d.A, (uint64_t)d.Cin, (uint64_t)d.a_rows, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B, (uint64_t)d.a_ld);
   if (rc) return rc;
@@ -2456,17 +2225,13 @@ int run_gemm_sm100(const GemmPlanSm100& p, cudaStream_t st) {
   switch (p.bn) {
     case 256:
       switch (p.epi) {
-        case 4: return run_impl<256, 2, 4, 8>(p, st);
-        case 2: return run_impl<256, 3, 2, 8>(p, st);
-        case 1: return run_impl<256, 3, 1, 8>(p, st);
         case -16: return run_impl<256, 4, 0, 16>(p, st);
         case -17: return run_impl<256, 3, 8, 16>(p, st);
         case -18: return run_impl<256, 3, 9, 16>(p, st);
         case -32: return run_2cta<256, 6>(p, st);
-        case -2: return run_impl<256, 3, 0, 8, true>(p, st);
         default: return run_impl<256, 4, 0, 8>(p, st);
       }
-    case 128: return p.epi == -32 ? run_2cta<128, 8>(p, st) : run_impl<128, 6, 0, 8>(p, st);
+    case 128: return run_impl<128, 6, 0, 8>(p, st);
     case 64: return run_impl<64, 8, 0, 8>(p, st);
     case 16: return run_impl<16, 8, 0, 8>(p, st);
   }
