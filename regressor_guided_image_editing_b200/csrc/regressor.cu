@@ -37,12 +37,12 @@ template <typename T>
 __global__ void __launch_bounds__(256) pack_crops_kernel(const float* __restrict__ img, const int* __restrict__ offsets,
                                                         const int* __restrict__ step_ptr, long off_step_stride,
                                                         T* __restrict__ zz, Geom g, int reps, int Hr, int Wr,
-                                                        InXform xf) {
+                                                        InXform xf, int n0) {
   // one thread block = one output line (n, i): no per-element division; a thread = one (pixel j, horizontal tap bi)
   const int* offs = offsets + (step_ptr ? (long)(*step_ptr) * off_step_stride : 0);
   const int n = blockIdx.x / g.H, i = blockIdx.x - n * g.H;
-  const int b = n / reps;
-  const int top = offs[2 * n], left_raw = offs[2 * n + 1];
+  const int b = (n0 + n) / reps;
+  const int top = offs[2 * (n0 + n)], left_raw = offs[2 * (n0 + n) + 1];
   const bool flip = (left_raw & kFlipBit) != 0;
   const int left = left_raw & (kFlipBit - 1);
   const int cw = 2 * g.W;                          // crop width
@@ -95,12 +95,13 @@ __global__ void __launch_bounds__(256) pack_crops_kernel(const float* __restrict
 template <typename T>
 __global__ void __launch_bounds__(256) pack_crops16_kernel(const float* __restrict__ img, const int* __restrict__ offsets,
                                                           const int* __restrict__ step_ptr, long off_step_stride,
-                                                          T* __restrict__ zz, Geom g, int reps, int Hr, int Wr, InXform xf) {
-  // one thread block = one output line (n, i); a thread = one 16-channel pixel
+                                                          T* __restrict__ zz, Geom g, int reps, int Hr, int Wr, InXform xf,
+                                                          int n0) {
+  // one thread block = one output line (n, i); a thread = one 16-channel pixel; n0: index of this launch's first crop in the batch
   const int* offs = offsets + (step_ptr ? (long)(*step_ptr) * off_step_stride : 0);
   const int n = blockIdx.x / g.H, i = blockIdx.x - n * g.H;
-  const int b = n / reps;
-  const int top = offs[2 * n], left_raw = offs[2 * n + 1];
+  const int b = (n0 + n) / reps;
+  const int top = offs[2 * (n0 + n)], left_raw = offs[2 * (n0 + n) + 1];
   const bool flip = (left_raw & kFlipBit) != 0;
   const int left = left_raw & (kFlipBit - 1);
   const int cw = 2 * g.W;
@@ -503,6 +504,14 @@ struct RgieRegressor {
   int H0 = 0;
   int zz16 = 0;          // conv1 operand as 16-channel pixels read through overlapped rows (pack_crops16_kernel)
   int tc32 = 0;          // fp32 mode on the tensor cores: weights are three bf16 planes, GEMMs run gemm_tc32_kernel
+  // L2-resident stem: pack -> conv1 -> max-pool (and max-pool^T -> conv1 input gradient) run per group of `stem_sub` crops
+  // through ONE small set of buffers that is overwritten group after group, so the 64-channel 224 x 224 tensors (6.4 MB per
+  // crop each way) are produced and consumed inside the 126 MB L2 instead of travelling through HBM.  0 = whole batch at once.
+  int stem_sub = 0;
+  Geom gZZs, gDYs;       // geometry of one group
+  void *zz_s = nullptr, *c1_s = nullptr, *dC1_s = nullptr;
+  GemmOp conv1_s, conv1t_s;   // conv1 forward / input gradient over one group
+  void* wh_dev = nullptr;     // conv_hshare weights (bf16 mode)
   int Hs[5] = {0, 0, 0, 0, 0};
   Geom gZZ, gDY, gS[5], gPh[5];
   std::vector<Block> blocks;
@@ -1030,12 +1039,51 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
             }
       void* wh_dev = nullptr;
       if (int rc = upload(R, wh, &wh_dev)) return rc;
+      R->wh_dev = wh_dev;
       GemmOp op;
       op.d = d;
       if (int rc = build_conv_hshare_sm100(d, wh_dev, -1, -1, &op.plan)) return rc;
       R->bwd_ops.push_back(op);
     } else {
       if (int rc = add_op(R, R->bwd_ops, d)) return rc;
+    }
+  }
+  // ---- L2-resident stem (see RgieRegressor::stem_sub).  RGIE_STEM_SUB = crops per group (default 8: 51 MB of stem
+  //      activation per group), 0 = off.  Used when the batch holds at least two whole groups.
+  {
+    static const int env_sub = getenv("RGIE_STEM_SUB") ? atoi(getenv("RGIE_STEM_SUB")) : 8;
+    if (env_sub > 0 && N % env_sub == 0 && N >= 2 * env_sub) {
+      R->stem_sub = env_sub;
+      const int NS = env_sub;
+      R->gZZs = R->zz16 ? make_geom(1, NS, H0, H0, 2, 1, 0, 4) : make_geom(1, NS, H0, H0, 2, 1, 0, 0);
+      R->gDYs = make_geom(1, NS, H0, H0, 1, 2, 1, 2);
+      if (int rc = dev_alloc(R, &R->zz_s, ((size_t)R->gZZs.rows() + R->gZZs.P) * (R->zz16 ? 16 : 64) * esz, true)) return rc;
+      if (int rc = dev_alloc(R, &R->c1_s, (size_t)NS * H0 * H0 * 64 * esz, true)) return rc;
+      if (int rc = dev_alloc(R, &R->dC1_s, (size_t)R->gDYs.rows() * 64 * esz, true)) return rc;
+      // conv1 forward over one group: the batch-wide descriptor with the group's geometry and buffers
+      GemmDesc d = R->fwd_ops[0].d;
+      d.A = R->zz_s; d.a_rows = R->gZZs.rows(); d.m_end = R->gZZs.rows();
+      d.src = R->gZZs; d.dst = R->gZZs; d.D = R->c1_s;
+      for (int a = 0; a < 4; ++a) d.row_off[a] = (long)(a - 2) * R->gZZs.P;
+      R->conv1_s.d = d;
+      if (R->precision == RGIE_PREC_BF16) { if (int rc = build_gemm_sm100(d, &R->conv1_s.plan)) return rc; }
+      else if (R->tc32) { if (int rc = build_gemm_tc32(d, &R->conv1_s.tplan)) return rc; }
+      // conv1 input gradient over one group (its destination pointer is moved group by group at run time)
+      GemmDesc t = R->bwd_ops.back().d;
+      t.A = R->dC1_s; t.a_rows = R->gDYs.rows(); t.m_end = R->gDYs.rows();
+      t.src = R->gDYs; t.dst = R->gDYs;
+      for (int a = 0; a < 4; ++a)
+        for (int j = 0; j < 4; ++j) t.row_off[a * 4 + j] = -((long)(a - 2) * R->gDYs.P + ((3 - j) - 2));
+      R->conv1t_s.d = t;
+      if (R->precision == RGIE_PREC_BF16) {
+        if (R->bwd_ops.back().plan.special == 1) {
+          if (int rc = build_conv_hshare_sm100(t, R->wh_dev, -1, -1, &R->conv1t_s.plan)) return rc;
+        } else {
+          if (int rc = build_gemm_sm100(t, &R->conv1t_s.plan)) return rc;
+        }
+      } else if (R->tc32) {
+        if (int rc = build_gemm_tc32(t, &R->conv1t_s.tplan)) return rc;
+      }
     }
   }
   if (int rc = fuse_b2b(R, R->fwd_ops)) return rc;
@@ -1060,26 +1108,40 @@ int rgie_regressor_forward_ex(RgieRegressor* R, const float* img, int B, int Hr,
   xf.mode = normalize;
   const int N = R->N, H0 = R->H0, H1 = R->Hs[1];
   const int pack_threads = (H0 * 4) % 224 == 0 ? 224 : 256;     // 4 work items per output pixel: whole iterations per line
-  if (R->zz16) {
+  // stem: pack -> conv1 -> max-pool, over the whole batch or (L2-resident) group by group through the small buffers; the
+  // per-GEMM profiling mode times the batch-wide launches
+  const bool sub = R->stem_sub > 0 && !R->profiling;
+  const int NG = sub ? R->stem_sub : N;                 // crops per group
+  const Geom& gz = sub ? R->gZZs : R->gZZ;
+  void* zz = sub ? R->zz_s : R->zz;
+  void* c1 = sub ? R->c1_s : R->c1;
+  const size_t p1_group = (size_t)NG * R->gS[1].S * 64 * R->esz;            // bytes of pooled rows per group
+  const size_t arg_group = (size_t)NG * H1 * H1 * 64;
+  for (int n0 = 0; n0 < N; n0 += NG) {
+    if (R->zz16) {
+      if (R->dtype == 0)
+        pack_crops16_kernel<float><<<NG * H0, 224, 0, st>>>(img, offsets, step_ptr, off_step_stride, (float*)zz, gz, reps, Hr, Wr, xf, n0);
+      else
+        pack_crops16_kernel<__nv_bfloat16><<<NG * H0, 224, 0, st>>>(img, offsets, step_ptr, off_step_stride, (__nv_bfloat16*)zz, gz,
+                                                                    reps, Hr, Wr, xf, n0);
+    } else if (R->dtype == 0) {
+      pack_crops_kernel<float><<<NG * H0, pack_threads, 0, st>>>(img, offsets, step_ptr, off_step_stride, (float*)zz, gz, reps, Hr, Wr,
+                                                                 xf, n0);
+    } else {
+      pack_crops_kernel<__nv_bfloat16><<<NG * H0, pack_threads, 0, st>>>(img, offsets, step_ptr, off_step_stride, (__nv_bfloat16*)zz,
+                                                                         gz, reps, Hr, Wr, xf, n0);
+    }
+    RGIE_LAUNCH_OK();
+    if (sub) { if (int rc = run_op_raw(R, R->conv1_s, st)) return rc; }
+    else if (int rc = run_op(R, R->fwd_ops[0], st, 0)) return rc;
+    char* p1g = (char*)R->p1 + (size_t)(n0 / NG) * p1_group;
+    uint8_t* argg = R->arg + (size_t)(n0 / NG) * arg_group;
     if (R->dtype == 0)
-      pack_crops16_kernel<float><<<N * H0, 224, 0, st>>>(img, offsets, step_ptr, off_step_stride, (float*)R->zz, R->gZZ, reps, Hr, Wr, xf);
+      maxpool_fwd_kernel<float><<<NG * H1, 256, 0, st>>>((const float*)c1, (float*)p1g, argg, R->gS[1], H0, 64);
     else
-      pack_crops16_kernel<__nv_bfloat16><<<N * H0, 224, 0, st>>>(img, offsets, step_ptr, off_step_stride, (__nv_bfloat16*)R->zz,
-                                                                 R->gZZ, reps, Hr, Wr, xf);
-  } else if (R->dtype == 0) {
-    pack_crops_kernel<float><<<N * H0, pack_threads, 0, st>>>(img, offsets, step_ptr, off_step_stride, (float*)R->zz, R->gZZ, reps, Hr,
-                                                     Wr, xf);
-  } else {
-    pack_crops_kernel<__nv_bfloat16><<<N * H0, pack_threads, 0, st>>>(img, offsets, step_ptr, off_step_stride, (__nv_bfloat16*)R->zz,
-                                                             R->gZZ, reps, Hr, Wr, xf);
+      maxpool_fwd_kernel<__nv_bfloat16><<<NG * H1, 256, 0, st>>>((const __nv_bfloat16*)c1, (__nv_bfloat16*)p1g, argg, R->gS[1], H0, 64);
+    RGIE_LAUNCH_OK();
   }
-  RGIE_LAUNCH_OK();
-  if (int rc = run_op(R, R->fwd_ops[0], st, 0)) return rc;
-  if (R->dtype == 0)
-    maxpool_fwd_kernel<float><<<N * H1, 256, 0, st>>>((const float*)R->c1, (float*)R->p1, R->arg, R->gS[1], H0, 64);
-  else
-    maxpool_fwd_kernel<__nv_bfloat16><<<N * H1, 256, 0, st>>>((const __nv_bfloat16*)R->c1, (__nv_bfloat16*)R->p1, R->arg, R->gS[1], H0, 64);
-  RGIE_LAUNCH_OK();
   for (size_t i = 1; i < R->fwd_ops.size(); ++i)
     if (int rc = run_op(R, R->fwd_ops[i], st, i)) return rc;
   const Block& last = R->blocks.back();
@@ -1120,12 +1182,31 @@ int rgie_regressor_backward(RgieRegressor* R, const float* dlogits, float* dimg,
     if (int rc = run_op(R, R->bwd_ops[i], st, R->fwd_ops.size() + i)) return rc;
   // d(pool out) is the destination of the last block op (layer1.0 c1 dgrad)
   const void* dP = R->bwd_ops[nb - 2].d.D;
-  if (R->dtype == 0)
-    maxpool_bwd_kernel<float><<<N * R->Hs[1], 256, 0, st>>>((const float*)dP, R->arg, (float*)R->dC1, R->gS[1], R->gDY, 64);
-  else
-    maxpool_bwd_kernel<__nv_bfloat16><<<N * R->Hs[1], 256, 0, st>>>((const __nv_bfloat16*)dP, R->arg, (__nv_bfloat16*)R->dC1, R->gS[1], R->gDY, 64);
-  RGIE_LAUNCH_OK();
-  if (int rc = run_op(R, R->bwd_ops[nb - 1], st, R->fwd_ops.size() + nb - 1)) return rc;
+  {
+    const bool sub = R->stem_sub > 0 && !R->profiling;
+    const int NG = sub ? R->stem_sub : N;
+    const int H0 = R->H0, H1 = R->Hs[1];
+    const Geom& gd = sub ? R->gDYs : R->gDY;
+    void* dC1 = sub ? R->dC1_s : R->dC1;
+    const size_t dp_group = (size_t)NG * R->gS[1].S * 64 * R->esz;
+    const size_t arg_group = (size_t)NG * H1 * H1 * 64;
+    const size_t dz_group = (size_t)NG * H0 * H0 * 16;                      // floats of packed input gradient per group
+    for (int n0 = 0; n0 < N; n0 += NG) {
+      const char* dPg = (const char*)dP + (size_t)(n0 / NG) * dp_group;
+      const uint8_t* argg = R->arg + (size_t)(n0 / NG) * arg_group;
+      if (R->dtype == 0)
+        maxpool_bwd_kernel<float><<<NG * H1, 256, 0, st>>>((const float*)dPg, argg, (float*)dC1, R->gS[1], gd, 64);
+      else
+        maxpool_bwd_kernel<__nv_bfloat16><<<NG * H1, 256, 0, st>>>((const __nv_bfloat16*)dPg, argg, (__nv_bfloat16*)dC1, R->gS[1], gd, 64);
+      RGIE_LAUNCH_OK();
+      if (sub) {
+        GemmOp o = R->conv1t_s;                 // same plan, destination moved to this group's rows of dZ
+        float* dzg = R->dZ + (size_t)(n0 / NG) * dz_group;
+        o.d.D = dzg; o.plan.d.D = dzg; o.tplan.d.D = dzg;
+        if (int rc = run_op_raw(R, o, st)) return rc;
+      } else if (int rc = run_op(R, R->bwd_ops[nb - 1], st, R->fwd_ops.size() + nb - 1)) return rc;
+    }
+  }
   InXform xf = R->xf2;
   xf.mode = R->normalize;
   crop_grad_gather_kernel<<<R->B * R->Hr, 256, 0, st>>>(R->dZ, R->offsets, R->step_ptr, R->off_stride, dimg, R->img, R->B, R->reps,
