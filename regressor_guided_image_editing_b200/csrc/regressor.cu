@@ -1048,10 +1048,14 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
       if (int rc = add_op(R, R->bwd_ops, d)) return rc;
     }
   }
-  // ---- L2-resident stem (see RgieRegressor::stem_sub).  RGIE_STEM_SUB = crops per group (default 8: 51 MB of stem
-  //      activation per group), 0 = off.  Used when the batch holds at least two whole groups.
+  // ---- L2-resident stem (see RgieRegressor::stem_sub).  RGIE_STEM_SUB = crops per group, 0 = off (default).
+  //      MEASURED (B200, 640 crops per step, same box, bit-identical results): whole batch 72.8 / 72.9 ms per step; groups of
+  //      16 crops 74.3, of 8 crops (51 MB of stem activation per group) 74.2 / 74.2, of 4 crops 75.9 ms -- the 8 GB per
+  //      micro-batch that stop travelling through HBM are paid back with interest by 40-160 small launches per pass (tails,
+  //      prologues, 390-790 more graph nodes per step).  The depth-first schedule does NOT pay even where it is cheapest
+  //      (three kernels, the largest tensors of the network); kept as an opt-in experiment.
   {
-    static const int env_sub = getenv("RGIE_STEM_SUB") ? atoi(getenv("RGIE_STEM_SUB")) : 8;
+    static const int env_sub = getenv("RGIE_STEM_SUB") ? atoi(getenv("RGIE_STEM_SUB")) : 0;
     if (env_sub > 0 && N % env_sub == 0 && N >= 2 * env_sub) {
       R->stem_sub = env_sub;
       const int NS = env_sub;
