@@ -955,19 +955,21 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 // kernel's work) is ALSO the complete K = 256 operand row block of the next layer's 1x1 reduction (256 -> 64), so the
 // second GEMM runs on the tile while it is still on chip and the next layer never re-reads the 256-channel tensor from HBM:
 //   stage 1: acc1[128 x 256] = A * W1^T (+ A2 * W1b^T)      smem operands, TMEM columns [0, 256), ONE buffer
-//            epilogue 1 (16 warps, lean role): bias / residual / ReLU / masks -> bf16 -> four 128 x 64 SWIZZLE_128B boxes in
-//            shared memory (one per 64-column part).  A box is (a) the source of the TMA store that writes D, and (b) a
-//            K-major operand tile of stage 2 as it stands -- no tcgen05.st, no second copy.
-//   stage 2: acc2[128 x 64] += box_p (smem) * W2[:, 64 p ..]^T for p = 0..3;  W2 (64 x 256, 32 KB) resident in smem,
-//            TMEM columns 256 + 64 * buf (two buffers)
+//            epilogue 1 = the DMA-thread lean role (epilogue_lean_dma_role): eight half boxes of 128 x 32 (SWIZZLE_64B); a
+//            half box receives the tile's residual by TMA load, is overwritten in place with the bf16 output, and is then
+//            (a) the source of the TMA store that writes D and (b) a K-major operand tile (K = 32) of stage 2 as it stands.
+//   stage 2: acc2[128 x 64] += box_k (smem, SWIZZLE_64B descriptor) * W2[:, 32 k ..]^T for the eight boxes;  W2 (64 x 256,
+//            32 KB, SWIZZLE_128B) resident in smem, TMEM columns 256 + 64 * buf (two buffers)
 //            epilogue 2 (the same 16 warps, 16 columns each): bias2 / ReLU / bit mask -> bf16 -> global D2 (+ sign bits)
 // acc1 has ONE buffer (2 x 256 + 2 x 64 columns do not fit in TMEM), but it is released as soon as the last tcgen05.ld of a
-// tile has completed (t1empty), i.e. before the last chunk's arithmetic, the box hand-over and epilogue 2 -- the MMAs of the
-// next tile (K = 64: 4 instructions) run underneath.  (Round 1's version released it after the whole epilogue and fed stage 2
-// from TMEM with tcgen05.st: tensor pipe 7 % active, 30 % of the epilogue samples at the accumulator barrier.)
-// MMA thread per tile t:  wait t1empty(t-1); MMA1(t); commit t1full;  then for p: wait bfull[p](t-1); MMA2(t-1, p); commit
-// bfree[p];  commit t2full(t-1).   Epilogue warps per tile t:  E1(t) (box p reusable once the TMA store of t-1 has read it
-// AND bfree[p](t-1)), then E2(t-1).
+// tile has completed (t1empty); the MMAs of the next tile (K = 64: 4 instructions) run underneath the rest of the epilogue.
+// MMA thread:  S1(0);  for t: [stage 2 of the four half-0 boxes of t as they become ready]; S1(t+1) once t1empty(t);
+// [stage 2 of the half-1 boxes of t]; commit t2full(t).   DMA threads (lane 0 of warps 2, 3; two parts each), per box:
+// wait ready -> TMA store -> wait for the store's read AND for stage 2's read (bfree) -> refill with the next tile's residual.
+// Epilogue warps per tile t: E1(t), then E2(t-1).
+// History (profiles/README.md): round 1 fed stage 2 from TMEM with tcgen05.st and released acc1 after the whole epilogue
+// (1.59 ms per fused launch against 0.70 + 0.41); round 2's first rewrite used 128 x 64 boxes with register-prefetched
+// residuals (time-neutral: the tile time was set by the LSU-bound epilogue, to which epilogue 2 was added).
 // ===============================================================================================================
 struct B2bParams {
   const float* bias2;
@@ -984,9 +986,9 @@ struct SmemB2b {
   static constexpr int B_OFF = B2B_STAGES * A_STAGE_BYTES;
   static constexpr int W2_OFF = B_OFF + B2B_STAGES * B_STAGE_BYTES;          // 4 k-blocks of [64 rows x 128 B]
   static constexpr int W2_BYTES = B2B_N2 * 256 * 2;
-  static constexpr int OB_OFF = W2_OFF + W2_BYTES;                           // 4 boxes of 128 rows x 128 B
-  static constexpr int BAR_OFF = OB_OFF + 4 * BM * 128;   // full[S], empty[S], t1full, t1empty, t2full[2], t2empty[2], bfull[4], bfree[4], w2full
-  static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * B2B_STAGES + 16) * 8;
+  static constexpr int OB_OFF = W2_OFF + W2_BYTES;                           // 8 half boxes of 128 rows x 64 B
+  static constexpr int BAR_OFF = OB_OFF + 8 * EPI_BOX_BYTES;   // full[S], empty[S], t1full, t1empty, t2full[2], t2empty[2], rfull[8], ready[8], bfree[8], w2full
+  static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * B2B_STAGES + 32) * 8;
   static constexpr int BIAS_OFF = (TMEM_PTR_OFF + 16 + 15) & ~15;
   static constexpr int BIAS2_OFF = BIAS_OFF + 256 * 4;
   static constexpr int TOTAL = BIAS2_OFF + B2B_N2 * 4;
@@ -995,10 +997,22 @@ struct SmemB2b {
   static_assert(DYN_BYTES <= 232448, "shared memory plan exceeds 227 KB");
 };
 
+// K-major SWIZZLE_64B operand tile (rows of 64 B, 8-row groups 512 B apart): layout type 4
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
+  uint64_t desc = 0;
+  desc |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  desc |= (uint64_t)1 << 16;
+  desc |= (uint64_t)(512 >> 4) << 32;
+  desc |= (uint64_t)1 << 46;
+  desc |= (uint64_t)4 << 61;
+  return desc;
+}
+
 __global__ void __launch_bounds__(640, 1)
 gemm_b2b_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmW2,
-                const __grid_constant__ CUtensorMap tmD, const GemmDesc d, const B2bParams q2, const int num_tiles) {
+                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR, const GemmDesc d,
+                const B2bParams q2, const int num_tiles) {
   using L = SmemB2b;
   constexpr int BN = 256, N2 = B2B_N2, STAGES = B2B_STAGES;
   constexpr uint32_t ACC2_COL = 256;
@@ -1012,15 +1026,18 @@ gemm_b2b_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t t1empty = bar_base + 8u * (2 * STAGES + 1);
   auto t2full = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
   auto t2empty = [&](int b) { return bar_base + 8u * (2 * STAGES + 4 + b); };
-  auto bfull = [&](int p) { return bar_base + 8u * (2 * STAGES + 6 + p); };
-  auto bfree = [&](int p) { return bar_base + 8u * (2 * STAGES + 10 + p); };
-  const uint32_t w2full = bar_base + 8u * (2 * STAGES + 14);
+  auto rfull = [&](int k) { return bar_base + 8u * (2 * STAGES + 6 + k); };
+  auto ready = [&](int k) { return bar_base + 8u * (2 * STAGES + 14 + k); };
+  auto bfree = [&](int k) { return bar_base + 8u * (2 * STAGES + 22 + k); };
+  const uint32_t w2full = bar_base + 8u * (2 * STAGES + 30);
+  auto box_of = [&](int k) { return smem_base + L::OB_OFF + (uint32_t)(k * EPI_BOX_BYTES); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_PTR_OFF);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int kb_per_tap = d.Cin / BK;
   const int num_kb = d.ntaps * kb_per_tap;
   const int num_kb2 = d.A2 != nullptr ? d.Cin2 / BK : 0;
+  const bool has_res = d.res != nullptr;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
@@ -1028,6 +1045,7 @@ gemm_b2b_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmW2) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmD) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmR) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -1038,9 +1056,10 @@ gemm_b2b_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(t2full(b), 1);
       mbar_init(t2empty(b), 16);
     }
-    for (int p = 0; p < 4; ++p) {
-      mbar_init(bfull(p), 1);
-      mbar_init(bfree(p), 1);
+    for (int k = 0; k < 8; ++k) {
+      mbar_init(rfull(k), 1);
+      mbar_init(ready(k), 4);
+      mbar_init(bfree(k), 1);
     }
     mbar_init(w2full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1071,21 +1090,16 @@ gemm_b2b_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int col0 = part * 64;
     const float* sbias = reinterpret_cast<const float*>(smem + L::BIAS_OFF);
     const float* sbias2 = reinterpret_cast<const float*>(smem + L::BIAS2_OFF);
-    const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(d.res);
     const uint32_t* mbits = d.mask_bits;
     const int m_end = (int)d.m_end;                    // all row indices are < 2^31 (checked where the plan is built)
-    const int res_lim = (int)(d.res_rows < d.m_end ? d.res_rows : d.m_end);
+    const int res_rows = (int)(d.res_rows < d.m_end ? d.res_rows : d.m_end);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
-    const uint32_t box = smem_base + L::OB_OFF + (uint32_t)(part * (BM * 128));
-    const uint32_t box_row = box + (uint32_t)row * 128u;
-    const uint32_t swz = (uint32_t)(row & 7);
-    const bool box_leader = qd == 0 && lane == 0;
-    const int bar_id = 1 + part;
+    const uint32_t row_off = (uint32_t)row * 64u;      // this thread's 64-byte row inside a half box (SWIZZLE_64B)
+    const uint32_t swz = (uint32_t)((row >> 1) & 3);
     int dest_prev = -1;
     uint32_t wmask2_prev = 0xFFFFFFFFu;
 
-    // wraw: the word holding this row's 16 stage-2 mask bits, loaded one tile earlier and not touched until here (an HBM
-    // latency the epilogue must not wait for: ncu showed 4 % of all samples on the shift that followed the load)
+    // wraw: the word holding this row's 16 stage-2 mask bits, loaded one tile earlier and not touched until here
     auto stage2 = [&](int it_prev, int dest, uint32_t wraw) {      // epilogue 2 of the tile handled one iteration ago
       const int b = it_prev & 1;
       mbar_wait(t2full(b), (uint32_t)((it_prev >> 1) & 1));
@@ -1126,19 +1140,7 @@ gemm_b2b_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         reinterpret_cast<uint16_t*>(q2.D2_bits + bits_index(dest, n0 / 32, q2.ld_db2))[part & 1] = (uint16_t)(wout & wmask);
     };
 
-    // Residual row and mask words of the NEXT tile: the mask words are fetched at the end of a tile, residual chunk ci right
-    // after chunk ci of the current tile has been consumed (its register buffer is free then) -- one 32-sector request per
-    // warp at a time instead of a burst of 64 requests per CTA at the tile boundary (ncu: the burst backs up the LSU queue
-    // and the epilogue warps wait for their address registers to be released).
-    uint32_t rbuf[CPW][CH / 2];
     uint32_t bits_nxt0 = 0u, bits_nxt1 = 0u;
-    const __nv_bfloat16* nres = nullptr;             // residual row of the next tile, or null
-    auto locate_next = [&](int tile) {
-      nres = nullptr;
-      if (tile >= num_tiles) return;
-      const int m = (int)d.m_begin + tile * BM + row;
-      if (res != nullptr && m < res_lim) nres = res + (long)m * d.ld_res + col0;
-    };
     auto prefetch_bits = [&](int tile) {
       bits_nxt0 = bits_nxt1 = 0u;
       if (tile >= num_tiles) return;
@@ -1148,103 +1150,94 @@ gemm_b2b_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         bits_nxt1 = __ldg(mbits + bits_index(m, col0 / 32 + 1, d.ld_mb));
       }
     };
-    locate_next(blockIdx.x);
-    if (nres != nullptr) {
-#pragma unroll
-      for (int ci = 0; ci < CPW; ++ci) ldg256(nres + ci * CH, rbuf[ci]);
-    }
     prefetch_bits(blockIdx.x);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      locate_next(tile + gridDim.x);
-      const int m0 = (int)d.m_begin + tile * BM;
-      const int m = m0 + row;
+      const int m = (int)d.m_begin + tile * BM + row;
       int dest = -1;                                       // DST_SAME: the destination row is the source row (pad rows: none)
       if (m < m_end) dest = (int)map_row(d.src, d.dst_kind, d.dst, m);
       const bool live = dest >= 0;
-      const bool use_res = live && res != nullptr && m < res_lim;
-      const uint32_t bits_cur0 = bits_nxt0, bits_cur1 = bits_nxt1;
-      uint32_t bits_out0 = 0u, bits_out1 = 0u;
+      const bool use_res = live && has_res && m < res_rows;
+      const uint32_t bits_cur[2] = {bits_nxt0, bits_nxt1};
+      uint32_t bits_out[2] = {0u, 0u};
       uint32_t wmask2 = 0xFFFFFFFFu;
       if (live && q2.mask_bits2 != nullptr) wmask2 = __ldg(q2.mask_bits2 + bits_index(dest, (part * CH) / 32, q2.ld_mb2));
+      prefetch_bits(tile + gridDim.x);
       mbar_wait(t1full, (uint32_t)(it & 1));
       tcgen05_fence_after();
-      if (it > 0) {
-        if (box_leader) {
-          bulk_wait_read0();                                   // the TMA store of the previous tile has read the box ...
-          mbar_wait(bfree(part), (uint32_t)((it - 1) & 1));    // ... and so have the stage-2 MMAs of the previous tile
-        }
-        named_bar_sync(bar_id, 128);
-      }
 #pragma unroll
-      for (int ci = 0; ci < CPW; ++ci) {
-        uint32_t r[CH];
-        tmem_ld<CH>(lane_addr + (uint32_t)(col0 + ci * CH), r);
-        tmem_ld_wait();
-        if (ci == CPW - 1) {
-          // this warp's part of acc1 is in registers: once all 16 warps are here the next tile's MMAs may overwrite it
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(t1empty);
-        }
-        const int n0 = col0 + ci * CH;
-        if (live) {
-          float v[CH];
+      for (int h = 0; h < 2; ++h) {
+        const int k = part * 2 + h;
+        // the box is ours again: the TMA store AND stage 2 of the previous tile have read it, this tile's residual is in it
+        mbar_wait(rfull(k), (uint32_t)(it & 1));
+        const uint32_t brow = box_of(k) + row_off;
 #pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]) + sbias[n0 + j];
-          if (use_res) {
-#pragma unroll
-            for (int j = 0; j < CH / 2; ++j) { v[2 * j] += bf16_lo(rbuf[ci][j]); v[2 * j + 1] += bf16_hi(rbuf[ci][j]); }
+        for (int cc = 0; cc < 2; ++cc) {
+          const int ci = 2 * h + cc;
+          uint32_t r[CH];
+          tmem_ld<CH>(lane_addr + (uint32_t)(col0 + ci * CH), r);
+          const uint32_t a0 = brow + (((uint32_t)(2 * cc) ^ swz) << 4), a1 = brow + (((uint32_t)(2 * cc + 1) ^ swz) << 4);
+          uint32_t rs[8];
+          if (use_res) { lds128(a0, rs); lds128(a1, rs + 4); }
+          tmem_ld_wait();
+          if (ci == CPW - 1) {
+            // this warp's part of acc1 is in registers: once all 16 warps are here the next tile's MMAs may overwrite it
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t1empty);
           }
-          uint32_t wout = 0u;
-          if (d.relu) {
+          if (live) {
+            const int n0 = col0 + ci * CH;
+            float v[CH];
 #pragma unroll
-            for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
-            if (d.D_bits != nullptr) {
+            for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]) + sbias[n0 + j];
+            if (use_res) {
 #pragma unroll
-              for (int j = CH - 1; j >= 0; --j) wout = push_positive_bit(wout, v[j]);
+              for (int j = 0; j < CH / 2; ++j) { v[2 * j] += bf16_lo(rs[j]); v[2 * j + 1] += bf16_hi(rs[j]); }
             }
-          } else if (d.D_bits != nullptr) {
+            uint32_t wout = 0u;
+            if (d.relu) {
 #pragma unroll
-            for (int j = 0; j < CH; ++j) wout |= (v[j] > 0.f ? 1u : 0u) << j;
+              for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
+              if (d.D_bits != nullptr) {
+#pragma unroll
+                for (int j = CH - 1; j >= 0; --j) wout = push_positive_bit(wout, v[j]);
+              }
+            } else if (d.D_bits != nullptr) {
+#pragma unroll
+              for (int j = 0; j < CH; ++j) wout |= (v[j] > 0.f ? 1u : 0u) << j;
+            }
+            if (mbits != nullptr) {
+              const uint32_t w = (bits_cur[h] >> (16 * cc)) & 0xFFFFu;
+              wout &= w;
+#pragma unroll
+              for (int j = 0; j < CH; ++j) v[j] = keep_if_bit(v[j], w, j);
+            }
+            bits_out[h] |= wout << (16 * cc);
+            uint32_t pk[CH / 2];
+#pragma unroll
+            for (int j = 0; j < CH / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            sts128(a0, pk);
+            sts128(a1, pk + 4);
+          } else {
+            const uint32_t z[4] = {0u, 0u, 0u, 0u};       // pad rows / rows past the end: zero in D and zero in the stage-2 operand
+            sts128(a0, z);
+            sts128(a1, z);
           }
-          if (mbits != nullptr) {
-            const uint32_t w = ((ci < 2 ? bits_cur0 : bits_cur1) >> (16 * (ci & 1))) & 0xFFFFu;
-            wout &= w;
-#pragma unroll
-            for (int j = 0; j < CH; ++j) v[j] = keep_if_bit(v[j], w, j);
-          }
-          if (ci < 2) bits_out0 |= wout << (16 * (ci & 1)); else bits_out1 |= wout << (16 * (ci & 1));
-          uint32_t pk[CH / 2];
-#pragma unroll
-          for (int j = 0; j < CH / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-          sts128(box_row + (((uint32_t)(2 * ci) ^ swz) << 4), pk);
-          sts128(box_row + (((uint32_t)(2 * ci + 1) ^ swz) << 4), pk + 4);
-        } else {
-          const uint32_t z[4] = {0u, 0u, 0u, 0u};       // pad rows / rows past the end: zero in D and zero in the stage-2 operand
-          sts128(box_row + (((uint32_t)(2 * ci) ^ swz) << 4), z);
-          sts128(box_row + (((uint32_t)(2 * ci + 1) ^ swz) << 4), z);
         }
-        if (nres != nullptr) ldg256(nres + ci * CH, rbuf[ci]);      // chunk ci of the NEXT tile into the buffer just consumed
-      }
-      fence_async_smem();                        // the box is read by the async proxy (TMA store, tcgen05.mma)
-      named_bar_sync(bar_id, 128);
-      if (box_leader) {
-        tma_store_2d(&tmD, box, col0, m0);
-        bulk_commit();
-        mbar_arrive(bfull(part));
+        fence_async_smem();                 // the box is read by the async proxy (TMA store, tcgen05.mma)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ready(k));
       }
       if (live && d.D_bits != nullptr) {
-        d.D_bits[bits_index(dest, col0 / 32, d.ld_db)] = bits_out0;
-        d.D_bits[bits_index(dest, col0 / 32 + 1, d.ld_db)] = bits_out1;
+        d.D_bits[bits_index(dest, col0 / 32, d.ld_db)] = bits_out[0];
+        d.D_bits[bits_index(dest, col0 / 32 + 1, d.ld_db)] = bits_out[1];
       }
-      prefetch_bits(tile + gridDim.x);
       if (it > 0) stage2(it - 1, dest_prev, wmask2_prev);
       dest_prev = dest;
       wmask2_prev = wmask2;
     }
     if (it > 0) stage2(it - 1, dest_prev, wmask2_prev);
-    if (box_leader) bulk_wait0();
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == 0) {
@@ -1282,32 +1275,14 @@ gemm_b2b_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (lane == 0) {
         constexpr uint32_t idesc1 = make_idesc(BM, BN);
         constexpr uint32_t idesc2 = make_idesc(BM, N2);
-        auto issue_stage2 = [&](int it_prev) {
-          const int b = it_prev & 1;
-          mbar_wait(t2empty(b), (uint32_t)(((it_prev >> 1) & 1) ^ 1));      // epilogue 2 of tile it_prev - 2 has drained this buffer
-          const uint32_t tmem_d2 = tmem_base + ACC2_COL + (uint32_t)(b * N2);
-#pragma unroll 1
-          for (int p = 0; p < 4; ++p) {
-            mbar_wait(bfull(p), (uint32_t)(it_prev & 1));
-            tcgen05_fence_after();
-            const uint64_t adesc = make_smem_desc(smem_base + L::OB_OFF + p * (BM * 128));
-            const uint64_t bdesc = make_smem_desc(smem_base + L::W2_OFF + p * (N2 * 128));
-#pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_bf16(tmem_d2, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc2, (p | k) != 0 ? 1u : 0u);
-            umma_commit(bfree(p));                   // box p may be overwritten once these MMAs have read it
-          }
-          umma_commit(t2full(b));
-        };
-        mbar_wait(w2full, 0);
         int stage = 0;
         uint32_t phase = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        auto issue_stage1 = [&](int tile, int it) {
           const long m0 = d.m_begin + (long)tile * BM;
           const int kb_total = num_kb + (m0 < d.a2_rows ? num_kb2 : 0);
           mbar_wait(t1empty, (uint32_t)((it & 1) ^ 1));       // all 16 epilogue warps hold tile it - 1's accumulator in registers
           tcgen05_fence_after();
+#pragma unroll 1
           for (int kb = 0; kb < kb_total; ++kb) {
             mbar_wait(full_bar(stage), phase);
             tcgen05_fence_after();
@@ -1320,10 +1295,65 @@ gemm_b2b_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           umma_commit(t1full);
-          if (it > 0) issue_stage2(it - 1);
+        };
+        // stage 2 of the four boxes of half h of tile `it`: box k = part * 2 + h holds output columns [64 part + 32 h, +32)
+        auto issue_stage2_half = [&](int it, int h) {
+          const int b = it & 1;
+          const uint32_t tmem_d2 = tmem_base + ACC2_COL + (uint32_t)(b * N2);
+          if (h == 0) mbar_wait(t2empty(b), (uint32_t)(((it >> 1) & 1) ^ 1));    // epilogue 2 of tile it - 2 has drained this buffer
+#pragma unroll 1
+          for (int p = 0; p < 4; ++p) {
+            const int k = p * 2 + h;
+            mbar_wait(ready(k), (uint32_t)(it & 1));
+            tcgen05_fence_after();
+            const uint64_t adesc = make_smem_desc_sw64(box_of(k));
+            const uint64_t bdesc = make_smem_desc(smem_base + L::W2_OFF + p * (N2 * 128)) + (uint64_t)(4 * h);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+              umma_bf16(tmem_d2, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc2, (h | p | ks) != 0 ? 1u : 0u);
+            umma_commit(bfree(k));                   // box k may be refilled once these MMAs have read it
+          }
+          if (h == 1) umma_commit(t2full(b));
+        };
+        mbar_wait(w2full, 0);
+        int it = 0;
+        if ((int)blockIdx.x < num_tiles) issue_stage1(blockIdx.x, 0);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+          issue_stage2_half(it, 0);
+          if (tile + (int)gridDim.x < num_tiles) issue_stage1(tile + gridDim.x, it + 1);
+          issue_stage2_half(it, 1);
         }
-        if (it > 0) issue_stage2(it - 1);
       }
+    } else if (lane == 0) {
+      // ===================== DMA threads (warps 2, 3): two parts each =====================
+      const int part0 = (warp - 2) * 2;
+      auto refill = [&](int k, int tile) {
+        if (tile >= num_tiles) return;
+        if (has_res) {
+          mbar_expect_tx(rfull(k), EPI_BOX_BYTES);
+          tma_load_2d(box_of(k), &tmR, (k >> 1) * 64 + (k & 1) * 32, (int)(d.m_begin + (long)tile * BM), rfull(k));
+        } else {
+          mbar_arrive(rfull(k));
+        }
+      };
+#pragma unroll 1
+      for (int s = 0; s < 4; ++s) refill((part0 + (s & 1)) * 2 + (s >> 1), blockIdx.x);
+      int it = 0;
+#pragma unroll 1
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int m0 = (int)(d.m_begin + (long)tile * BM);
+#pragma unroll 1
+        for (int s = 0; s < 4; ++s) {
+          const int k = (part0 + (s & 1)) * 2 + (s >> 1);          // half 0 of both parts, then half 1 of both parts
+          mbar_wait(ready(k), (uint32_t)(it & 1));
+          tma_store_2d(&tmD, box_of(k), (k >> 1) * 64 + (k & 1) * 32, m0);
+          bulk_commit();
+          bulk_wait_read0();                                        // the store has read the box ...
+          mbar_wait(bfree(k), (uint32_t)(it & 1));                  // ... and so have the stage-2 MMAs
+          refill(k, tile + (int)gridDim.x);
+        }
+      }
+      bulk_wait0();
     }
   }
 
@@ -1935,7 +1965,7 @@ int run_b2b(const GemmPlanSm100& p, cudaStream_t st) {
   B2bParams q;
   q.bias2 = p.d2.bias; q.D2 = p.d2.D; q.ldd2 = p.d2.ldd; q.relu2 = p.d2.relu;
   q.mask_bits2 = p.d2.mask_bits; q.ld_mb2 = p.d2.ld_mb; q.D2_bits = p.d2.D_bits; q.ld_db2 = p.d2.ld_db;
-  gemm_b2b_kernel<<<p.grid, 640, SmemB2b::DYN_BYTES, st>>>(p.tmA, p.tmA2, p.tmB, p.tmW2, p.tmD, p.d, q, p.num_m_tiles);
+  gemm_b2b_kernel<<<p.grid, 640, SmemB2b::DYN_BYTES, st>>>(p.tmA, p.tmA2, p.tmB, p.tmW2, p.tmD, p.tmR, p.d, q, p.num_m_tiles);
   RGIE_LAUNCH_OK();
   return 0;
 }
@@ -2165,8 +2195,13 @@ int build_gemm_b2b_sm100(const GemmDesc& d1, const GemmDesc& d2, GemmPlanSm100* 
   if (rc) return rc;
   rc = make_map_2d(&p->tmB, d1.Wt, (uint64_t)d1.ntaps * d1.Cin + (d1.A2 ? d1.Cin2 : 0), (uint64_t)d1.n_pad, BK, 256);
   if (rc) return rc;
-  rc = make_map_2d(&p->tmD, d1.D, (uint64_t)d1.ldd, (uint64_t)d1.m_end, 64, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+  rc = make_map_2d(&p->tmD, d1.D, (uint64_t)d1.ldd, (uint64_t)d1.m_end, 32, BM, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
+  if (d1.res != nullptr) {
+    const long rr = d1.res_rows < d1.m_end ? d1.res_rows : d1.m_end;
+    rc = make_map_2d(&p->tmR, d1.res, (uint64_t)d1.ld_res, (uint64_t)rr, 32, BM, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
   return make_map_2d(&p->tmW2, d2.Wt, 256, (uint64_t)B2B_N2, BK, (uint32_t)B2B_N2);
 }
 

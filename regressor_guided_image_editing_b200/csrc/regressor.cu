@@ -598,12 +598,12 @@ int add_op(RgieRegressor* R, std::vector<GemmOp>& ops, const GemmDesc& d) {
 // Back-to-back fusion pass over an op list (bf16 tcgen05 mode): a 256-wide 1x1 op followed by the 256 -> 64 1x1 op that reads
 // its output (layer1: conv3 + skip -> next block's conv1; conv1 input gradient + skip gradient -> previous block's conv3
 // input gradient) becomes ONE launch, and the 256-channel tensor is not re-read from HBM (-8.2 GB of 127.9 GB per 320 crops).
-// MEASURED (B200, 320 crops): correct (tests/test_regressor_gpu.py passes with it), but SLOWER -- fused 1.59 / 1.69 / 1.87 ms
-// vs 0.70 + 0.41 / 0.98 + 0.40 / 0.89 + 0.39 ms for the two separate launches: TMEM has room for only ONE 256-column
-// stage-1 accumulator next to the stage-2 operand and accumulators, so the epilogue waits for every tile's MMAs (30 % of
-// its samples at the accumulator barrier, tensor pipe 7 % active).  OFF by default; RGIE_GEMM_B2B=1 enables it.
+// MEASURED (B200, 320 crops, same box; gemm_b2b_kernel with the DMA-thread epilogue and SWIZZLE_64B half boxes as stage-2
+// operands): per pair 1.01 -> 0.82, 1.16 -> 0.90, 1.19 -> 0.91, 1.19 -> 0.93 ms; step 74.5 / 74.9 -> 72.9 / 73.1 ms.
+// ON by default; RGIE_GEMM_B2B=0 runs the two launches separately.  (Its two predecessors were slower or neutral, see the
+// kernel's header comment.)
 int fuse_b2b(RgieRegressor* R, std::vector<GemmOp>& ops) {
-  static const int env_b2b = getenv("RGIE_GEMM_B2B") ? atoi(getenv("RGIE_GEMM_B2B")) : 0;
+  static const int env_b2b = getenv("RGIE_GEMM_B2B") ? atoi(getenv("RGIE_GEMM_B2B")) : 1;
   if (R->precision != RGIE_PREC_BF16 || !env_b2b) return 0;
   for (size_t i = 0; i + 1 < ops.size(); ++i) {
     if (ops[i].absorbed || ops[i].plan.special || ops[i].plan.patch) continue;
