@@ -22,6 +22,10 @@ same, the default K=100 is exactly one full edit of the batch.
   --images N : BASELINE.json configs[4] -- a strong-scaling sweep of N images sharded over the ranks (shard.partition), each
           rank running ceil(N/W)/B engine batches of 100 steps through ONE engine + CUDA graph, then ONE gather of uint8 edited
           images + predictions + per-step losses to rank 0 (NCCL) and their D2H; everything inside the timed region.
+  --latent : BASELINE.json configs[2] -- latent (style-code) optimisation through the random-init MUNIT generator + the
+          native regressor, batch 16 at 256x256, through the reference's own call surface (initialize_imaginaire,
+          objective_function_imaginaire, optimization); the generator is PyTorch (library convolutions),
+          the regressor forward + input gradient and the Adam / best-x update are librgie.so.  Single GPU, extra line.
 --impl reference : times that same CPU implementation alone (the reference is pure Python/PyTorch; /root/reference does
           not exist on the GPU box, the oracle port is its restatement validated bit-exactly against it).
 """
@@ -245,6 +249,113 @@ def run_sweep(args, rank, world, dev, lib):
     return line
 
 
+def run_latent(args, dev, lib):
+    """BASELINE.json configs[2]: optimize_image_imaginaire.py's loop at batch 16, 256x256 (one GPU)."""
+    import torch
+    from oracle import oracle as O          # seeded synthetic inputs / regressor weights only
+    from regressor_guided_image_editing_b200 import optimize_image_imaginaire as oii
+    from regressor_guided_image_editing_b200.baselines import optimize_image as oi
+    from regressor_guided_image_editing_b200.baselines.losses.ValenceArousalLoss import ValenceArousalLoss
+    from regressor_guided_image_editing_b200.external.imaginaire.generators.munit import Generator
+
+    B, H, K, W = args.latent_batch, args.latent_size, max(args.steps, 1), max(args.warmup, 3)
+    sd = O.make_regressor_state_dict()
+    torch.manual_seed(0)
+    gen = Generator().to(dev)                                   # imagenet2imagenet.yaml, random init, training mode (:75-79)
+    clf = ValenceArousalLoss(sd, dev, 1, is_minimized=True, is_input_range_0_1=False, requires_grad=True,
+                             precision=args.precision)
+    images_h = torch.stack([2.0 * O.synthetic_image(300 + i, H, H) - 1.0 for i in range(B)]).pin_memory()
+    edited_h = torch.empty(B, 3, H, H).pin_memory()
+    style_h = torch.empty(B, 8, 1, 1).pin_memory()
+
+    def job(steps, images_d=None):
+        """One whole latent edit of the batch: encode -> target -> `steps` optimisation steps -> decode(best)."""
+        img = images_h.to(dev, non_blocking=True) if images_d is None else images_d
+        params = {"gen": gen, "clf": clf, "dis": None, "gan_loss": None, "weight_clf": 0.2, "weight_dis": 0.0,
+                  "weight_recon": 1.0}
+        x0, params = oii.initialize_imaginaire(img, params)
+        params["target"] = oi.get_condition_from_alpha(0.1, clf, img)
+        best = oi.optimization(x0, params, oii.objective_function_imaginaire, learning_rate=0.05, num_steps=steps)
+        with torch.no_grad():
+            edited = torch.clamp(gen.autoencoder_a.decode(params["content"].detach(), best), -1, 1)
+        return best, edited, params
+
+    torch.manual_seed(2300)
+    l0 = lib.rgie_launch_count()
+    _, _, params = job(W)                                       # warm-up: W optimisation steps, every kernel instantiated
+    torch.cuda.synchronize(dev)
+    launches_warm = lib.rgie_launch_count() - l0
+    images_d = images_h.to(dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    with ClockSampler(dev.index) as clk:
+        torch.cuda.synchronize(dev)
+        l0 = lib.rgie_launch_count()
+        ev[0].record()
+        job(K, images_d)                                        # value: inputs resident in HBM
+        ev[1].record()
+        torch.cuda.synchronize(dev)
+        launches = lib.rgie_launch_count() - l0
+        ev[2].record()
+        best, edited, _ = job(K)                                # e2e: pinned host images in, edited images + style codes out
+        edited_h.copy_(edited, non_blocking=True); style_h.copy_(best, non_blocking=True)
+        ev[3].record()
+        torch.cuda.synchronize(dev)
+    ms, ms_e2e = ev[0].elapsed_time(ev[1]), ev[2].elapsed_time(ev[3])
+
+    # split of one objective evaluation + gradient: generator (PyTorch) vs native regressor
+    def timed(fn, n=5):
+        fn(); torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record(); torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / n
+
+    content, x = params["content"].detach(), best.detach().clone().requires_grad_(True)
+    ae = gen.autoencoder_a
+
+    def gen_only():
+        img = torch.clamp(ae.decode(content, x), -1, 1)
+        loss = torch.nn.functional.l1_loss(ae.encode(img)[0], content) + img.mean()
+        torch.autograd.grad(loss, x)
+
+    img_fixed = torch.clamp(ae.decode(content, x), -1, 1).detach()
+
+    def reg_only():
+        im = img_fixed.clone().requires_grad_(True)
+        torch.autograd.grad(clf(im, target=params["target"]), im)
+
+    gen_ms, reg_ms = timed(gen_only), timed(reg_only)
+    reg_flop = B * FLOP_PER_IMAGE_STEP
+    peaks, which = _peaks()
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / (6.0 if args.precision == "fp32" else 1.0)
+    line = {"metric": "edited images/sec (100 steps, 256^2, latent)", "value": B * (K / STEPS_PER_IMAGE) / (ms / 1e3), "unit": "images/s",
+            "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else args.precision, "data": "synthetic",
+            "config": {"workload": f"configs[2]: optimize_image_imaginaire.py latent optimisation through the random-init MUNIT "
+                                   f"generator (imagenet2imagenet.yaml) + random-init resnet50 VA regressor on 10 random 448 crops, "
+                                   f"batch {B} at {H}x{H}, weight_clf 0.2, weight_recon 1.0, lr 0.05, {STEPS_PER_IMAGE} steps/image",
+                       "batch_per_gpu": B, "image": f"{H}x{H}", "precision": args.precision,
+                       "generator": "PyTorch eager fp32 (cuDNN, TF32 convolutions as torch defaults), training mode: one spectral-norm "
+                                    "power iteration per forward",
+                       "regressor_and_update": "librgie.so (tcgen05 regressor forward + input gradient, fused Adam + best-x)",
+                       "includes": "encode + target prediction + K optimisation steps + decode(best) per job",
+                       "cache": "activations per step exceed the 126 MB L2; no flush needed"},
+            "clocks": clk.summary(),
+            "e2e": {"value": B * (K / STEPS_PER_IMAGE) / (ms_e2e / 1e3), "unit": "images/s",
+                    "h2d_bytes_per_step": int(images_h.numel() * 4 / K), "d2h_bytes_per_step": int((edited_h.numel() + style_h.numel()) * 4 / K)},
+            "gpu_launches": int(launches), "launches_per_step": int(launches // K),
+            "breakdown_ms_per_step": {"objective_and_update": ms / K, "generator_decode_encode_fwd_bwd_torch": gen_ms,
+                                      "regressor_fwd_bwd_native": reg_ms},
+            "roofline": {"bound": "tensor", "achieved": reg_flop / (reg_ms / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                         "frac": reg_flop / (reg_ms / 1e3) / 1e12 / peak, "traffic": None,
+                         "span": "native regressor fwd+bwd of one step (resize 256->480, 160 crops, resnet50 fwd + dgrad, resize^T), "
+                                 "653.9 GFLOP per image", "peak_source": which},
+            "cpu_baseline": None, "lib_sha256": _lib_sha()}
+    return line
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -261,6 +372,9 @@ def main():
     ap.add_argument("--images", type=int, default=0,
                     help="configs[4]: strong-scaling sweep of this many images over all ranks (0 = the weak-scaling headline)")
     ap.add_argument("--sweep-steps", type=int, default=STEPS_PER_IMAGE, help="optimisation steps per image in --images mode")
+    ap.add_argument("--latent", action="store_true", help="configs[2]: MUNIT latent optimisation, batch 16 at 256x256 (one GPU)")
+    ap.add_argument("--latent-batch", type=int, default=16)
+    ap.add_argument("--latent-size", type=int, default=256)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -308,6 +422,13 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+
+    if args.latent:
+        if rank == 0:
+            print(json.dumps(run_latent(args, dev, lib)))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     if args.images > 0:
         line = run_sweep(args, rank, world, dev, lib)

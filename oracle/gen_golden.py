@@ -3,7 +3,7 @@
 Generates tests/golden/*.pt by running the UNMODIFIED reference Python (imported from /root/reference/src through
 oracle/ref_harness.py) on CPU.  Run in the build container only:
 
-    python -m oracle.gen_golden [--only filters|regressor|loop|loopk|loops|loop512|midu]
+    python -m oracle.gen_golden [--only filters|regressor|loop|loopk|loops|loop512|midu|munit]
 
 The reference ships no tests/fixtures, so these vectors are the pin for the standalone oracle
 (oracle/oracle.py) and, through it, for the CUDA path.  Inputs are regenerated from seeds at test time; only outputs
@@ -207,6 +207,59 @@ def gen_midu(r):
     print("midu.pt written")
 
 
+MUNIT_SMALL = dict(num_filters=8, num_filters_mlp=32, num_res_blocks=2)     # width / depth overrides of imagenet2imagenet.yaml
+
+
+def gen_munit(r, h=64, w=64, batch=2, num_steps=3):
+    """BASELINE.json configs[2] in miniature, run by the reference itself: its MUNIT `Generator` (imagenet2imagenet.yaml
+    with the MUNIT_SMALL overrides so that the state_dict fits a fixture; the full-width network is compared directly
+    in tests/test_munit_cpu.py when /root/reference is mounted), `initialize_imaginaire`, `objective_function_imaginaire`
+    (weight_clf 0.2, weight_recon 1.0, optimize_image_imaginaire.py:32-37) and `optimization` on a batch of images in
+    [-1, 1].  Stored: the generator's state_dict BEFORE any forward (spectral-norm u / v included: every training-mode
+    forward advances them), content / style codes, per-step losses, the style codes visited, their gradients, best_x."""
+    import importlib
+    Config = importlib.import_module("external.imaginaire.config").Config
+    RefGen = importlib.import_module("external.imaginaire.generators.munit").Generator
+    oii = importlib.import_module("optimize_image_imaginaire")
+    cfg = Config(os.path.join(ref_harness.REFERENCE_SRC, "external/imaginaire/imagenet2imagenet.yaml"))
+    for k, v in MUNIT_SMALL.items():
+        setattr(cfg.gen, k, v)
+    torch.manual_seed(0)
+    gen = RefGen(cfg.gen, cfg.data)
+    state0 = {k: v.detach().clone() for k, v in gen.autoencoder_a.state_dict().items()}      # the loop only uses domain A
+    sd = O.make_regressor_state_dict()
+    tmp = tempfile.mkdtemp()
+    path = os.path.join(tmp, "va_pred_all")
+    torch.save(sd, path)
+    clf = r.ValenceArousalLoss(path, torch.device("cpu"), 1, is_input_range_0_1=False, is_minimized=True, requires_grad=True)
+    image = torch.stack([2.0 * O.synthetic_image(40 + i, h, w) - 1.0 for i in range(batch)])
+    torch.manual_seed(2040)
+    obj = {"gen": gen, "clf": clf, "dis": None, "gan_loss": None, "weight_clf": 0.2, "weight_dis": 0.0, "weight_recon": 1.0}
+    x0, obj = oii.initialize_imaginaire(image, obj)
+    obj["target"] = r.optimize_image.get_condition_from_alpha(0.1, clf, image)
+    losses, xs, grads, imgs = [], [], [], []
+    orig = oii.objective_function_imaginaire
+
+    def wrapped(x, **kw):
+        xs.append(x.detach().clone())
+        l = orig(x, **kw)
+        grads.append(torch.autograd.grad(l, x, retain_graph=True)[0].detach().clone())
+        losses.append(float(l))
+        return l
+
+    best_x = r.optimize_image.optimization(x0, obj, wrapped, learning_rate=0.05, num_steps=num_steps)
+    with torch.no_grad():
+        edited = torch.clamp(gen.autoencoder_a.decode(obj["content"].detach(), best_x), -1, 1)
+    torch.manual_seed(2040)
+    offs = O.draw_crop_offsets(1 + num_steps, batch, 480, 480)
+    out = dict(h=h, w=w, batch=batch, num_steps=num_steps, overrides=dict(MUNIT_SMALL), state0=state0, image_index0=40,
+               content=obj["content"].clone(), x0=x0.clone(), target=obj["target"].clone(), losses=torch.tensor(losses),
+               xs=torch.stack(xs), grads=torch.stack(grads), best_x=best_x.clone(), edited=edited.clone(), offsets=offs,
+               crop_seed=2040, weight_clf=0.2, weight_recon=1.0, learning_rate=0.05)
+    torch.save(out, os.path.join(GOLDEN_DIR, "munit_small.pt"))
+    print("munit_small.pt written: losses", losses)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -227,6 +280,8 @@ def main():
         gen_loop(r, tag="c1k", x0_override=KINK_FREE_X0)
     if "loops" in todo:       # band-limited image, the reference's own start point: the end-to-end edited-image parity case
         gen_loop(r, tag="c1s", smooth=True)
+    if "munit" in todo:
+        gen_munit(r)
     if "loop512" in todo:
         gen_loop(r, 512, 512, 3, "c2_3steps", image_index=1, x0_override=KINK_FREE_X0_BLUR)
 
