@@ -62,6 +62,15 @@ int rgie_filter_fwd(int kind, const float* in, float* out, const float* p, int p
 int rgie_filter_bwd(int kind, const float* in, const float* gout, float* gin, const float* p, int p_stride,
                     float* gp, int gp_stride, int B, int H, int W, float* ws, void* stream);
 
+/* The head of the reference's default filter list (optimize_image_param.py:227: exposure, saturation, tone, color --
+ * image_transformations.py:16-58 applied in that order, each followed by clamp(0,1) :60) as ONE pixel pass each way: the
+ * three intermediate images are never materialised; results are bit-identical to four rgie_filter_fwd calls.
+ * `p` points at image 0's exposure value, followed by saturation, 8 tone and 24 colour values (34 floats, p_stride floats
+ * between images).  bwd produces the 34 parameter gradients only: the input is the fixed original image (no d(in)). */
+int rgie_filter_prefix_fwd(const float* in, float* out, const float* p, int p_stride, int B, int H, int W, void* stream);
+int rgie_filter_prefix_bwd(const float* in, const float* gout, const float* p, int p_stride, float* gp, int gp_stride,
+                           int B, int H, int W, float* ws, void* stream);
+
 /* x (raw optimisation vector, optimize_image_param.py:262-292 `get_params_from_vector`) -> effective parameters for
  * the default filter list ['exposure','saturation','tone','color','contrast','sharp','blur','scale'] (41 floats):
  * saturation/sharp/blur clamp(min=0), scale clamp(min=1), centre clamp(0,input_size), contrast<0 -> 0.

@@ -36,6 +36,8 @@ SIGNATURES = {
     "rgie_filter_ws_floats": (_l, [_i, _i, _i]),
     "rgie_filter_fwd": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "rgie_filter_bwd": (_i, [_i, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "rgie_filter_prefix_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "rgie_filter_prefix_bwd": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "rgie_params_default_fwd": (_i, [_vp, _vp, _i, _f, _vp]),
     "rgie_params_default_bwd": (_i, [_vp, _vp, _i, _f, _vp]),
     "rgie_resize_create": (_i, [_i, _i, _i, _i, C.POINTER(_vp)]),

@@ -126,19 +126,19 @@ struct SaturationOp {          // F2: kornia.enhance.adjust_saturation (rgb_to_h
     m.hnum = (m.a == 0) ? (bc - gc) : (m.a == 1 ? __fadd_rn(rc - bc, __fmul_rn(2.0f, m.dc))
                                                  : __fadd_rn(gc - rc, __fmul_rn(4.0f, m.dc)));
     m.hsel = m.hnum / m.dc;
-    float hm = fmodf(m.hsel / 6.0f, 1.0f);
-    if (hm != 0.f && hm < 0.f) hm += 1.0f;
+    // (hsel / 6) % 1 (python modulo): |hsel / 6| <= 5/6 < 1, so the remainder is the value itself -- no fmodf needed
+    float hm = m.hsel / 6.0f;
+    if (hm < 0.f) hm += 1.0f;
     const float h = __fmul_rn(kTwoPi, hm);
     m.s2pre = __fmul_rn(m.s, F);
     m.s2 = clamp01(m.s2pre);
     // hsv_to_rgb
     const float hn = h / kTwoPi;
     const float h6 = __fmul_rn(hn, 6.0f);
-    float fl = floorf(h6);
-    float him = fmodf(fl, 6.0f);
-    if (him != 0.f && him < 0.f) him += 6.0f;
-    float h6m = fmodf(h6, 6.0f);
-    if (h6m != 0.f && h6m < 0.f) h6m += 6.0f;
+    // floor(h6) % 6 and h6 % 6 with h6 in [0, 6]: exact for one wrap (x - 6 is exact for x in [6, 12))
+    const float fl = floorf(h6);
+    const float him = fl >= 6.0f ? fl - 6.0f : fl;
+    const float h6m = h6 >= 6.0f ? h6 - 6.0f : h6;
     m.f = h6m - him;
     m.hi = (int)him;
     const float v = m.v, s2 = m.s2, f = m.f;
@@ -268,6 +268,36 @@ struct ContrastOp {            // F5: kornia adjust_contrast_with_mean_subtracti
     }
   }
 };
+
+// exposure -> saturation -> tone -> colour as ONE pixel op (the head of the reference's default filter list,
+// optimize_image_param.py:227): the three intermediate images never exist.  Each stage is the op above, clamp included,
+// so the result is bit-identical to running them one after the other; backward recomputes the three intermediates per
+// pixel and chains the four backward functions.  Parameters: 34 consecutive floats (1 + 1 + 8 + 24).
+struct PrefixOp {
+  static constexpr int NP = 34;
+  ExposureOp e; SaturationOp s; CurveOp<1> t; CurveOp<3> c;
+  __device__ void load(int b) { e.load(b); s.load(b); t.load(b); c.load(b); }
+  __device__ void fwd(const float* x, float* y) const {
+    float x1[3], x2[3], x3[3];
+    e.fwd(x, x1); s.fwd(x1, x2); t.fwd(x2, x3); c.fwd(x3, y);
+  }
+  __device__ void bwd(const float* x, const float* g, float* gx, float* gp) const {
+    float x1[3], x2[3], x3[3], g3[3], g2[3], g1[3];
+    e.fwd(x, x1); s.fwd(x1, x2); t.fwd(x2, x3);
+    c.bwd(x3, g, g3, gp + 10);
+    t.bwd(x2, g3, g2, gp + 2);
+    s.bwd(x1, g2, g1, gp + 1);
+    e.bwd(x, g1, gx, gp);
+  }
+};
+PrefixOp make_prefix_op(const float* p, int stride) {
+  PrefixOp op;
+  op.e = ExposureOp{p, stride, 0.f};
+  op.s = SaturationOp{p + 1, stride, 0.f};
+  op.t.p = p + 2; op.t.stride = stride;
+  op.c.p = p + 10; op.c.stride = stride;
+  return op;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // the remaining pointwise filters of apply_params
@@ -462,8 +492,8 @@ struct WbOp {                  // img_trans_torch_diff.py:51-57: clamp(lerp(im, 
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-template <class Op, int VEC, bool BWD>
-__global__ void __launch_bounds__(kThreads, BWD ? 3 : 4) pointwise_kernel(const float* __restrict__ in, const float* __restrict__ gout,
+template <class Op, int VEC, bool BWD, bool WRITE = true, int MINB = (BWD ? 3 : 4)>
+__global__ void __launch_bounds__(kThreads, MINB) pointwise_kernel(const float* __restrict__ in, const float* __restrict__ gout,
                                                             float* __restrict__ out, Op op, float* __restrict__ partial,
                                                             int HW, int chunk) {
   const int b = blockIdx.y;
@@ -504,6 +534,7 @@ __global__ void __launch_bounds__(kThreads, BWD ? 3 : 4) pointwise_kernel(const 
       }
       y[0][v] = yo[0]; y[1][v] = yo[1]; y[2][v] = yo[2];
     }
+    if (!WRITE) continue;                      // first stage of a chain: nothing upstream consumes d(in)
     if (VEC == 4) {
 #pragma unroll
       for (int c = 0; c < 3; ++c)
@@ -563,6 +594,19 @@ __global__ void __launch_bounds__(kThreads) contrast_bwd_mean_kernel(float* __re
   const float k = (1.0f - f) * G / (float)HW;
   const float wc[3] = {0.299f, 0.587f, 0.114f};
   const long base = (long)b * 3 * HW;
+  if ((HW & 3) == 0) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float4* g4 = reinterpret_cast<float4*>(gin + base + (long)c * HW);
+      const float add = wc[c] * k;
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW / 4; i += gridDim.x * blockDim.x) {
+        float4 v = g4[i];
+        v.x += add; v.y += add; v.z += add; v.w += add;
+        g4[i] = v;
+      }
+    }
+    return;
+  }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * HW; i += gridDim.x * blockDim.x) gin[base + i] += wc[i / HW] * k;
 }
 
@@ -779,13 +823,23 @@ __global__ void __launch_bounds__(kThreads) blur_h_kernel(const float* __restric
       const float4* s4 = reinterpret_cast<const float4*>(in + off);
       const float4* g4 = gout ? reinterpret_cast<const float4*>(gout + off) : nullptr;
       float4* o4 = reinterpret_cast<float4*>(fin + off);
-      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW / 4; i += gridDim.x * blockDim.x) {
-        const float4 v = s4[i];
-        if (g4) {
-          const float4 g = g4[i];
-          o4[i] = make_float4(in01(v.x) ? g.x : 0.f, in01(v.y) ? g.y : 0.f, in01(v.z) ? g.z : 0.f, in01(v.w) ? g.w : 0.f);
-        } else {
-          o4[i] = make_float4(clamp01(v.x), clamp01(v.y), clamp01(v.z), clamp01(v.w));
+      // a pure streaming pass: four independent 16-byte loads per thread in flight before the first store (the one-load
+      // loop ran at 43 % of the copy bandwidth, latency-bound)
+      const int n4 = HW / 4, step = gridDim.x * blockDim.x;
+      for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += 4 * step) {
+        float4 v[4], g[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * step;
+          if (i < n4) { v[u] = s4[i]; if (g4) g[u] = g4[i]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * step;
+          if (i >= n4) continue;
+          if (g4) o4[i] = make_float4(in01(v[u].x) ? g[u].x : 0.f, in01(v[u].y) ? g[u].y : 0.f, in01(v[u].z) ? g[u].z : 0.f,
+                                      in01(v[u].w) ? g[u].w : 0.f);
+          else o4[i] = make_float4(clamp01(v[u].x), clamp01(v[u].y), clamp01(v[u].z), clamp01(v[u].w));
         }
       }
     } else {
@@ -1026,6 +1080,239 @@ __global__ void __launch_bounds__(kThreads) scale_bwd_gather_kernel(const float*
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Table-driven scale kernels.  The warp is separable: pixel (y, x) samples source row (i0y(y), w1y(y)) and source column
+// (i0x(x), w1x(x)), both monotone in their index (sx, sy > 0).  Each block builds the column table of its image in
+// shared memory once (W coordinate evaluations, amortised over its band of rows) instead of evaluating two coordinates
+// per pixel, and the gather kernel inverts the tables by binary search -- source column u receives from the contiguous
+// destination range {x : i0x(x) in {u - 1, u}} -- instead of re-deriving candidates with divisions per pixel.
+// Same arithmetic per coordinate (sample_coord) as scale_kernel / scale_bwd_gather_kernel, which remain the reference
+// form (RGIE_SCALE_TAB=0) and the path for tables that would not fit shared memory.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kScaleRows = 16;          // destination (or source) rows per block
+__device__ __forceinline__ void build_coord_table(int* __restrict__ ti0, float* __restrict__ tw1, int n, float inv_s, float t) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const SampleCoord c = sample_coord(i, n, inv_s, t);
+    ti0[i] = c.i0; tw1[i] = c.w1;
+  }
+}
+
+// forward (BWD=false): out = clamp(bilinear(in)); backward pass A (BWD=true): gm = g * [0 <= bilinear(in) <= 1] -> out,
+// block partials of d(sx, sy, cx, cy) from four plain sums (sum ggx, sum ggx*xn, sum ggy, sum ggy*yn)
+template <bool BWD>
+__global__ void __launch_bounds__(kThreads) scale_tab_kernel(const float* __restrict__ in, const float* __restrict__ gout,
+                                                            float* __restrict__ out, const float* __restrict__ p, int stride,
+                                                            float* __restrict__ partial, int H, int W) {
+  extern __shared__ __align__(16) int s_tab[];              // [W] i0x, [W] w1x
+  int* xi0 = s_tab;
+  float* xw1 = reinterpret_cast<float*>(s_tab + W);
+  const int b = blockIdx.y;
+  const float* pb = p + (long)b * stride;
+  const WarpCoef k = warp_coef(pb, H, W);
+  build_coord_table(xi0, xw1, W, k.inv_sx, k.t02);
+  __syncthreads();
+  const long base = (long)b * 3 * H * W;
+  const int HW = H * W;
+  const int ya = blockIdx.x * kScaleRows, yb = min(ya + kScaleRows, H);
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+  for (int y = ya; y < yb; ++y)
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    const SampleCoord syc = sample_coord(y, H, k.inv_sy, k.t12);
+    const int x0 = xi0[x], y0 = syc.i0, x1 = x0 + 1, y1 = y0 + 1;
+    const float wx1 = xw1[x], wx0 = 1.0f - wx1, wy1 = syc.w1, wy0 = 1.0f - wy1;
+    const bool vx0 = x0 >= 0 && x0 < W, vx1 = x1 >= 0 && x1 < W, vy0 = y0 >= 0 && y0 < H, vy1 = y1 >= 0 && y1 < H;
+    const int i = y * W + x;
+    float gix = 0.f, giy = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* pl = in + base + (long)c * HW;
+      const float v00 = (vy0 && vx0) ? pl[(long)y0 * W + x0] : 0.f;
+      const float v01 = (vy0 && vx1) ? pl[(long)y0 * W + x1] : 0.f;
+      const float v10 = (vy1 && vx0) ? pl[(long)y1 * W + x0] : 0.f;
+      const float v11 = (vy1 && vx1) ? pl[(long)y1 * W + x1] : 0.f;
+      const float o = v00 * (wx0 * wy0) + v01 * (wx1 * wy0) + v10 * (wx0 * wy1) + v11 * (wx1 * wy1);
+      if (!BWD) {
+        out[base + (long)c * HW + i] = clamp01(o);
+      } else {
+        const float g = in01(o) ? gout[base + (long)c * HW + i] : 0.f;
+        out[base + (long)c * HW + i] = g;
+        gix += g * ((v01 - v00) * wy0 + (v11 - v10) * wy1);
+        giy += g * ((v10 - v00) * wx0 + (v11 - v01) * wx1);
+      }
+    }
+    if (BWD) {
+      const float ggx = gix * 0.5f * (float)(W - 1), ggy = giy * 0.5f * (float)(H - 1);   // d/d(grid x), d/d(grid y)
+      a0 += ggx; a1 = fmaf(ggx, lin_coord(x, W), a1);
+      b0 += ggy; b1 = fmaf(ggy, lin_coord(y, H), b1);
+    }
+  }
+  if (BWD) {
+    float acc[4] = {a0, a1, b0, b1};
+    __shared__ float sums[4];
+    block_reduce_store<4>(acc, sums);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const float sx = pb[0], sy = pb[1], cx = pb[2], cy = pb[3];
+      const float a = 2.0f / (float)(W - 1), bb = 2.0f / (float)(H - 1);
+      float* dst = partial + ((long)b * gridDim.x + blockIdx.x) * 4;
+      dst[0] = (-sums[1] + (a * cx - 1.0f) * sums[0]) / (sx * sx) + sums[2] * (bb * cy / sy);      // d/dsx
+      dst[1] = (-sums[3] + (bb * (1.0f - sx) * cy - 1.0f) * sums[2]) / (sy * sy);                  // d/dsy
+      dst[2] = sums[0] * (-a * (1.0f - sx) / sx);                                                 // d/dcx
+      dst[3] = sums[2] * (-bb * (1.0f - sx) / sy);                                                // d/dcy
+    }
+  }
+}
+
+// Column-marching form of the same pass: a thread owns ONE destination column (its source columns and weights are
+// loop-invariant registers) and walks down a band of rows; the two source rows of the previous destination row stay in
+// registers, and because consecutive destination rows sample source rows at most one apart when sy >= 1 (the reference
+// clamps the scale factors to >= 1, optimize_image_param.py:279-280) a row step needs 0 or 1 new source rows
+// (6 loads per pixel instead of 12).  Any other step reloads both rows, so every sx, sy > 0 stays correct.
+// Values and operation order per pixel are those of scale_kernel: results are bit-identical.
+constexpr int kScaleColRows = 32;
+template <bool BWD>
+__global__ void __launch_bounds__(kThreads) scale_col_kernel(const float* __restrict__ in, const float* __restrict__ gout,
+                                                            float* __restrict__ out, const float* __restrict__ p, int stride,
+                                                            float* __restrict__ partial, int H, int W) {
+  const int b = blockIdx.z;
+  const float* pb = p + (long)b * stride;
+  const WarpCoef k = warp_coef(pb, H, W);
+  const int x = blockIdx.x * kThreads + threadIdx.x;
+  const bool active = x < W;
+  const int ya = blockIdx.y * kScaleColRows, yb = min(ya + kScaleColRows, H);
+  const long base = (long)b * 3 * H * W;
+  const int HW = H * W;
+  const SampleCoord sxc = sample_coord(active ? x : 0, W, k.inv_sx, k.t02);
+  const int x0 = sxc.i0, x1 = x0 + 1;
+  const float wx1 = sxc.w1, wx0 = 1.0f - wx1;
+  const bool vx0 = x0 >= 0 && x0 < W, vx1 = x1 >= 0 && x1 < W;
+  const float xn = lin_coord(active ? x : 0, W);
+  float top[3][2], bot[3][2];                       // source rows cur, cur + 1 at columns x0, x1 (zero outside the image)
+  int cur = -0x40000000;
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+  auto load_row = [&](int r, float (*dst)[2]) {
+    const bool vr = r >= 0 && r < H;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* row = in + base + (long)c * HW + (long)r * W;
+      dst[c][0] = (vr && vx0) ? row[x0] : 0.f;
+      dst[c][1] = (vr && vx1) ? row[x1] : 0.f;
+    }
+  };
+  if (active)
+  for (int y = ya; y < yb; ++y) {
+    const SampleCoord syc = sample_coord(y, H, k.inv_sy, k.t12);
+    const int y0 = syc.i0;
+    const float wy1 = syc.w1, wy0 = 1.0f - wy1;
+    if (y0 == cur + 1) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { top[c][0] = bot[c][0]; top[c][1] = bot[c][1]; }
+      load_row(y0 + 1, bot);
+    } else if (y0 != cur) {
+      load_row(y0, top);
+      load_row(y0 + 1, bot);
+    }
+    cur = y0;
+    const int i = y * W + x;
+    float gix = 0.f, giy = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v00 = top[c][0], v01 = top[c][1], v10 = bot[c][0], v11 = bot[c][1];
+      const float o = v00 * (wx0 * wy0) + v01 * (wx1 * wy0) + v10 * (wx0 * wy1) + v11 * (wx1 * wy1);
+      if (!BWD) {
+        out[base + (long)c * HW + i] = clamp01(o);
+      } else {
+        const float g = in01(o) ? gout[base + (long)c * HW + i] : 0.f;
+        out[base + (long)c * HW + i] = g;
+        gix += g * ((v01 - v00) * wy0 + (v11 - v10) * wy1);
+        giy += g * ((v10 - v00) * wx0 + (v11 - v01) * wx1);
+      }
+    }
+    if (BWD) {
+      const float ggx = gix * 0.5f * (float)(W - 1), ggy = giy * 0.5f * (float)(H - 1);   // d/d(grid x), d/d(grid y)
+      a0 += ggx; a1 = fmaf(ggx, xn, a1);
+      b0 += ggy; b1 = fmaf(ggy, lin_coord(y, H), b1);
+    }
+  }
+  if (BWD) {
+    float acc[4] = {a0, a1, b0, b1};
+    __shared__ float sums[4];
+    block_reduce_store<4>(acc, sums);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const float sx = pb[0], sy = pb[1], cx = pb[2], cy = pb[3];
+      const float a = 2.0f / (float)(W - 1), bb = 2.0f / (float)(H - 1);
+      float* dst = partial + ((long)b * gridDim.x * gridDim.y + blockIdx.y * gridDim.x + blockIdx.x) * 4;
+      dst[0] = (-sums[1] + (a * cx - 1.0f) * sums[0]) / (sx * sx) + sums[2] * (bb * cy / sy);      // d/dsx
+      dst[1] = (-sums[3] + (bb * (1.0f - sx) * cy - 1.0f) * sums[2]) / (sy * sy);                  // d/dsy
+      dst[2] = sums[0] * (-a * (1.0f - sx) / sx);                                                 // d/dcx
+      dst[3] = sums[2] * (-bb * (1.0f - sx) / sy);                                                // d/dcy
+    }
+  }
+}
+bool scale_col_on() {
+  static const int env = getenv("RGIE_SCALE_COL") ? atoi(getenv("RGIE_SCALE_COL")) : 1;
+  return env != 0;
+}
+
+// first index i in [0, n) with tab[i] >= key (n when none); tab is non-decreasing
+__device__ __forceinline__ int lower_bound_i(const int* __restrict__ tab, int n, int key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (tab[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// backward pass B: d(in)[v, u] = sum_{y in Y(v)} sum_{x in X(u)} wy * wx * gm[y, x]; a deterministic gather
+__global__ void __launch_bounds__(kThreads) scale_gather_tab_kernel(const float* __restrict__ gm, float* __restrict__ gin,
+                                                                   const float* __restrict__ p, int stride, int H, int W) {
+  extern __shared__ __align__(16) int s_tab[];              // [W] i0x, [W] w1x, [H] i0y, [H] w1y, [W+2] lbx, [rows+2] lby
+  int* xi0 = s_tab;
+  float* xw1 = reinterpret_cast<float*>(s_tab + W);
+  int* yi0 = s_tab + 2 * W;
+  float* yw1 = reinterpret_cast<float*>(s_tab + 2 * W + H);
+  int* lbx = s_tab + 2 * W + 2 * H;                         // lbx[key + 1] = first x with i0x(x) >= key, key in [-1, W]
+  int* lby = lbx + W + 2;                                   // lby[key - va + 1] likewise for keys [va - 1, vb]
+  const int b = blockIdx.y;
+  const WarpCoef k = warp_coef(p + (long)b * stride, H, W);
+  build_coord_table(xi0, xw1, W, k.inv_sx, k.t02);
+  build_coord_table(yi0, yw1, H, k.inv_sy, k.t12);
+  __syncthreads();
+  const int va = blockIdx.x * kScaleRows, vb = min(va + kScaleRows, H);
+  for (int i = threadIdx.x; i < W + 2; i += blockDim.x) lbx[i] = lower_bound_i(xi0, W, i - 1);
+  for (int i = threadIdx.x; i < vb - va + 2; i += blockDim.x) lby[i] = lower_bound_i(yi0, H, va + i - 1);
+  __syncthreads();
+  const long base = (long)b * 3 * H * W;
+  const int HW = H * W;
+  for (int v = va; v < vb; ++v) {
+    const int ylo = lby[v - va], yhi = lby[v - va + 2];     // [ylo, yhi): i0y in {v-1, v}
+    for (int u = threadIdx.x; u < W; u += blockDim.x) {
+      const int xlo = lbx[u], xhi = lbx[u + 2];             // [xlo, xhi): i0x in {u-1, u}
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+      for (int y = ylo; y < yhi; ++y) {
+        const float wy = yi0[y] == v ? 1.0f - yw1[y] : yw1[y];
+        for (int x = xlo; x < xhi; ++x) {
+          const float wx = xi0[x] == u ? 1.0f - xw1[x] : xw1[x];
+          const float w = wx * wy;
+          const long o = base + (long)y * W + x;
+          s0 = fmaf(w, gm[o], s0);
+          s1 = fmaf(w, gm[o + HW], s1);
+          s2 = fmaf(w, gm[o + 2L * HW], s2);
+        }
+      }
+      const int i = v * W + u;
+      gin[base + i] = s0; gin[base + HW + i] = s1; gin[base + 2L * HW + i] = s2;
+    }
+  }
+}
+constexpr size_t scale_gather_smem(int H, int W) { return (size_t)(3 * W + 2 * H + kScaleRows + 4) * sizeof(int); }
+bool scale_tab_ok(int H, int W) {
+  static const int env = getenv("RGIE_SCALE_TAB") ? atoi(getenv("RGIE_SCALE_TAB")) : 1;
+  return env != 0 && scale_gather_smem(H, W) <= 44 * 1024;
+}
+
 // ===============================================================================================================
 // affine: kornia.geometry.transform.affine(im, M[2x3], padding_mode='border') + clamp   (image_transformations.py:198-206)
 //   warp_affine: theta = inv(N M3 N^-1)[:2] with N the pixel -> [-1,1] normalisation, affine_grid(align_corners=True),
@@ -1252,6 +1539,176 @@ __global__ void __launch_bounds__(kThreads) sharp_bwd_band_kernel(const float* _
   }
   block_reduce_store<1>(acc, partial + ((long)b * 3 + c) * gridDim.x + blockIdx.x);
 }
+// ---------------------------------------------------------------------------------------------------------------
+// Marching kernels (W % 4 == 0): a thread owns FOUR adjacent columns and walks down a band of rows with the three input
+// rows it needs (6 values each: its 4 columns + one neighbour either side) rolling through registers, so every input
+// element is fetched once per band as part of a 16-byte load.  Backward: the gradient of the clamped 3x3 smoothing
+// (gdeg) goes through a 4-row ring in shared memory (one __syncthreads per row), the transposed 3x3 reads it from
+// there, and the direct term of the previous row waits in registers -- in + g are read once, gin is written once (3N),
+// no intermediate in HBM.  The 9-term fmaf chains are those of sharp_conv / sharp_bwd_b_kernel, in the same order (the
+// [0 <= conv <= 1] mask of a saturated neighbourhood depends on it).
+// ---------------------------------------------------------------------------------------------------------------
+struct Row6 { float v[6]; };     // columns x0-1 .. x0+4 of one row (zero outside the image: only read for interior pixels)
+__device__ __forceinline__ Row6 load_row6(const float* __restrict__ row, int x0, int W, bool valid) {
+  Row6 r;
+  if (!valid) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) r.v[i] = 0.f;
+    return r;
+  }
+  const float4 q = *reinterpret_cast<const float4*>(row + x0);
+  r.v[1] = q.x; r.v[2] = q.y; r.v[3] = q.z; r.v[4] = q.w;
+  r.v[0] = x0 > 0 ? row[x0 - 1] : 0.f;
+  r.v[5] = x0 + 4 < W ? row[x0 + 4] : 0.f;
+  return r;
+}
+__device__ __forceinline__ float conv_rows(const Row6& a, const Row6& b, const Row6& c, int j) {   // pixel column x0 + j
+  const float k1 = 1.0f / 13.0f, k5 = 5.0f / 13.0f;
+  float s = 0.f;
+  s = fmaf(k1, a.v[j], s); s = fmaf(k1, a.v[j + 1], s); s = fmaf(k1, a.v[j + 2], s);
+  s = fmaf(k1, b.v[j], s); s = fmaf(k5, b.v[j + 1], s); s = fmaf(k1, b.v[j + 2], s);
+  s = fmaf(k1, c.v[j], s); s = fmaf(k1, c.v[j + 1], s); s = fmaf(k1, c.v[j + 2], s);
+  return s;
+}
+
+__global__ void __launch_bounds__(1024) sharp_fwd_march_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                              const float* __restrict__ p, int stride, int H, int W, int R) {
+  const int b = blockIdx.z, c = blockIdx.y;
+  const float f = p[(long)b * stride];
+  const int mode = sharp_mode(f);
+  const long off = ((long)b * 3 + c) * H * W;
+  const int x0 = 4 * threadIdx.x;
+  if (x0 >= W) return;
+  const int y0 = blockIdx.x * R, y1 = min(y0 + R, H);
+  const float* pl = in + off;
+  Row6 ra = load_row6(pl + (long)(y0 - 1) * W, x0, W, y0 >= 1);
+  Row6 rb = load_row6(pl + (long)y0 * W, x0, W, true);
+  for (int y = y0; y < y1; ++y) {
+    const Row6 rc = load_row6(pl + (long)(y + 1) * W, x0, W, y + 1 < H);
+    float o4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int x = x0 + j;
+      const float xin = rb.v[j + 1];
+      float result = xin;
+      if (y >= 1 && y < H - 1 && x >= 1 && x < W - 1) result = clamp01(conv_rows(ra, rb, rc, j));
+      float o;
+      if (mode == 0) o = result;
+      else if (mode == 1) o = xin;
+      else {
+        o = __fadd_rn(result, __fmul_rn(xin - result, f));
+        if (mode == 3) o = clamp01(o);
+      }
+      o4[j] = clamp01(o);
+    }
+    *reinterpret_cast<float4*>(out + off + (long)y * W + x0) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+    ra = rb; rb = rc;
+  }
+}
+
+__global__ void __launch_bounds__(1024) sharp_bwd_march_kernel(const float* __restrict__ in, const float* __restrict__ gout,
+                                                               float* __restrict__ gin, const float* __restrict__ p,
+                                                               int stride, float* __restrict__ partial, int H, int W, int R) {
+  extern __shared__ __align__(16) float ring[];            // 4 rows of (W + 8) floats: gdeg with 4 zero columns either side
+  __shared__ float red[32];
+  const int b = blockIdx.z, c = blockIdx.y;
+  const float f = p[(long)b * stride];
+  const int mode = sharp_mode(f);
+  const long off = ((long)b * 3 + c) * H * W;
+  const int Wp = W + 8;
+  const int x0 = 4 * threadIdx.x;
+  const bool active = x0 < W;
+  const int y0 = blockIdx.x * R, y1 = min(y0 + R, H);
+  const int ga = max(y0 - 1, 0), gb = min(y1 + 1, H);      // rows whose smoothing gradient this band needs
+  for (int i = threadIdx.x; i < 4 * Wp; i += blockDim.x) ring[i] = 0.f;
+  __syncthreads();
+  const float* pl = in + off;
+  const float k1 = 1.0f / 13.0f, k5 = 5.0f / 13.0f;
+  Row6 ra, rb;
+  if (active) {
+    ra = load_row6(pl + (long)(ga - 1) * W, x0, W, ga >= 1);
+    rb = load_row6(pl + (long)ga * W, x0, W, true);
+  }
+  float acc = 0.f;
+  float hold[4] = {0.f, 0.f, 0.f, 0.f};                    // direct d(in) term of the previous row
+  for (int y = ga; y <= gb; ++y) {                         // iteration y == gb only emits row gb - 1 (below it: zeros)
+    float gx[4] = {0.f, 0.f, 0.f, 0.f};
+    if (active && y < gb) {
+      const Row6 rc = load_row6(pl + (long)(y + 1) * W, x0, W, y + 1 < H);
+      const float4 g4 = *reinterpret_cast<const float4*>(gout + off + (long)y * W + x0);
+      const float gq[4] = {g4.x, g4.y, g4.z, g4.w};
+      const bool own = y >= y0 && y < y1;
+      float deg[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int x = x0 + j;
+        const float xin = rb.v[j + 1];
+        const bool interior = y >= 1 && y < H - 1 && x >= 1 && x < W - 1;
+        float conv = 0.f, result = xin;
+        if (interior) { conv = conv_rows(ra, rb, rc, j); result = clamp01(conv); }
+        float g = gq[j], g_res = 0.f, g_x = 0.f;
+        if (mode == 0) { g = in01(result) ? g : 0.f; g_res = g; }
+        else if (mode == 1) { g = in01(xin) ? g : 0.f; g_x = g; }
+        else {
+          const float o = __fadd_rn(result, __fmul_rn(xin - result, f));
+          g = in01(o) ? g : 0.f;
+          g_res = g - g * f;
+          g_x = g * f;
+          if (own) acc += g * (xin - result);
+        }
+        if (interior) deg[j] = in01(conv) ? g_res : 0.f;
+        else { deg[j] = 0.f; g_x += g_res; }
+        gx[j] = g_x;
+      }
+      *reinterpret_cast<float4*>(ring + (y & 3) * Wp + 4 + x0) = make_float4(deg[0], deg[1], deg[2], deg[3]);
+      ra = rb; rb = rc;
+    }
+    __syncthreads();
+    const int ye = y - 1;                                  // row to emit: needs gdeg rows ye-1, ye, ye+1 (= y)
+    if (active && ye >= y0 && ye < y1) {
+      float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int yy = ye + dy;
+        if (yy < 0 || yy >= H) continue;
+        const float* rr = ring + (yy & 3) * Wp + 4 + x0;
+        const float4 q = *reinterpret_cast<const float4*>(rr);
+        const float v[6] = {rr[-1], q.x, q.y, q.z, q.w, rr[4]};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          s[j] = fmaf(k1, v[j], s[j]);
+          s[j] = fmaf(dy == 0 ? k5 : k1, v[j + 1], s[j]);
+          s[j] = fmaf(k1, v[j + 2], s[j]);
+        }
+      }
+      *reinterpret_cast<float4*>(gin + off + (long)ye * W + x0) =
+          make_float4(hold[0] + s[0], hold[1] + s[1], hold[2] + s[2], hold[3] + s[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) hold[j] = gx[j];
+  }
+  // block sum of d(factor) over the band's own rows (any block size that is a multiple of 32)
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    partial[((long)b * 3 + c) * gridDim.x + blockIdx.x] = t;
+  }
+}
+struct SharpMarch { int R, nb, threads; size_t smem; };
+SharpMarch sharp_march(int H, int W) {
+  SharpMarch m;
+  m.R = H >= 256 ? 32 : 16;
+  m.nb = ceil_div(H, m.R);
+  m.threads = ceil_div(ceil_div(W, 4), 32) * 32;
+  m.smem = (size_t)4 * (W + 8) * sizeof(float);
+  static const int env = getenv("RGIE_SHARP_MARCH") ? atoi(getenv("RGIE_SHARP_MARCH")) : 1;
+  if (!env || (W & 3) != 0 || m.threads > 1024 || m.nb > 64) m.R = 0;       // fall back (partials: 3 * nb <= 192 per image)
+  return m;
+}
+
 // rows per band and shared-memory bytes of the band kernels (0 rows = fall back to the global-memory kernels)
 // MEASURED (B200, 64 x 512^2): forward 0.156 -> 0.125 ms (default on); the fused backward is SLOWER than the two global-memory
 // passes (0.583 vs 0.529 ms: 80 KB of shared memory per block, three shared-memory passes of scalar 3x3 reads), so backward
@@ -1341,6 +1798,12 @@ int rgie_filter_fwd(int kind, const float* in, float* out, const float* p, int p
     }
     case RGIE_F_SHARP: {
       RGIE_CHECK(H >= 3 && W >= 3, "sharp: image too small");
+      const SharpMarch sm = sharp_march(H, W);
+      if (sm.R > 0) {
+        sharp_fwd_march_kernel<<<dim3(sm.nb, 3, B), sm.threads, 0, st>>>(in, out, p, p_stride, H, W, sm.R);
+        RGIE_LAUNCH_OK();
+        return 0;
+      }
       const SharpBand sb = sharp_band(H, W, false);
       if (sb.R > 0) {
         static DeviceOnce attr_once;
@@ -1374,6 +1837,19 @@ int rgie_filter_fwd(int kind, const float* in, float* out, const float* p, int p
     }
     case RGIE_F_SCALE: {
       RGIE_CHECK(H >= 2 && W >= 2, "scale: image too small");
+      // forward keeps the direct-coordinate kernel: measured 0.135 ms vs 0.152 ms for the table-driven one (64 x 512^2);
+      // the tables pay in the backward passes (0.77 -> 0.50 ms)
+      if (scale_col_on()) {
+        scale_col_kernel<false><<<dim3(ceil_div(W, kThreads), ceil_div(H, kScaleColRows), B), kThreads, 0, st>>>(in, nullptr, out, p, p_stride, nullptr, H, W);
+        RGIE_LAUNCH_OK();
+        return 0;
+      }
+      static const bool fwd_tab = getenv("RGIE_SCALE_TAB_FWD") && atoi(getenv("RGIE_SCALE_TAB_FWD")) != 0;
+      if (fwd_tab && scale_tab_ok(H, W)) {
+        scale_tab_kernel<false><<<dim3(ceil_div(H, kScaleRows), B), kThreads, 2 * W * sizeof(int), st>>>(in, nullptr, out, p, p_stride, nullptr, H, W);
+        RGIE_LAUNCH_OK();
+        return 0;
+      }
       dim3 grid(plane_blocks(HW), B);
       scale_kernel<false><<<grid, kThreads, 0, st>>>(in, nullptr, out, p, p_stride, nullptr, H, W);
       RGIE_LAUNCH_OK();
@@ -1487,6 +1963,13 @@ int rgie_filter_bwd(int kind, const float* in, const float* gout, float* gin, co
     }
     case RGIE_F_SHARP: {
       RGIE_CHECK(H >= 3 && W >= 3, "sharp: image too small");
+      const SharpMarch sm = sharp_march(H, W);
+      if (sm.R > 0) {
+        sharp_bwd_march_kernel<<<dim3(sm.nb, 3, B), sm.threads, sm.smem, st>>>(in, gout, gin, p, p_stride, partial, H, W, sm.R);
+        RGIE_LAUNCH_OK();
+        finalize_partials<<<B, 32, 0, st>>>(partial, 3 * sm.nb, 1, gp, gp_stride);
+        break;
+      }
       const SharpBand sb = sharp_band(H, W, true);
       if (sb.R > 0) {
         static DeviceOnce attr_once;
@@ -1542,6 +2025,19 @@ int rgie_filter_bwd(int kind, const float* in, const float* gout, float* gin, co
     }
     case RGIE_F_SCALE: {
       RGIE_CHECK(H >= 2 && W >= 2, "scale: image too small");
+      if (scale_tab_ok(H, W) && ceil_div(H, kScaleRows) <= kMaxBlk * 6) {
+        const int nbt = ceil_div(H, kScaleRows);
+        float* gmt = ws + (long)B * kMaxBlk * 24;
+        const dim3 gcol(ceil_div(W, kThreads), ceil_div(H, kScaleColRows), B);
+        const bool col = scale_col_on() && (long)gcol.x * gcol.y <= kMaxBlk * 6;
+        if (col) scale_col_kernel<true><<<gcol, kThreads, 0, st>>>(in, gout, gmt, p, p_stride, partial, H, W);
+        else scale_tab_kernel<true><<<dim3(nbt, B), kThreads, 2 * W * sizeof(int), st>>>(in, gout, gmt, p, p_stride, partial, H, W);
+        RGIE_LAUNCH_OK();
+        scale_gather_tab_kernel<<<dim3(nbt, B), kThreads, scale_gather_smem(H, W), st>>>(gmt, gin, p, p_stride, H, W);
+        RGIE_LAUNCH_OK();
+        finalize_partials<<<B, 32, 0, st>>>(partial, col ? (int)(gcol.x * gcol.y) : nbt, 4, gp, gp_stride);
+        break;
+      }
       const int nb = plane_blocks(HW);
       float* gm = ws + (long)B * kMaxBlk * 24;
       dim3 grid(nb, B);
@@ -1568,6 +2064,38 @@ int rgie_filter_bwd(int kind, const float* in, const float* gout, float* gin, co
     default:
       return fail("rgie_filter_bwd: unknown filter kind");
   }
+  RGIE_LAUNCH_OK();
+  return 0;
+}
+
+// exposure -> saturation -> tone -> colour in one pass each way (see PrefixOp).  `p` points at image 0's exposure value,
+// followed by saturation, the 8 tone and the 24 colour values (the layout of the reference's default parameter vector);
+// backward writes the 34 parameter gradients only -- the chain's input is the fixed original image, nothing consumes d(in).
+int rgie_filter_prefix_fwd(const float* in, float* out, const float* p, int p_stride, int B, int H, int W, void* stream) {
+  RGIE_CHECK(B > 0 && H > 0 && W > 0, "rgie_filter_prefix_fwd: bad shape");
+  const int HW = H * W;
+  LaunchShape s = shape_for(HW);
+  dim3 grid(s.nblk, B);
+  PrefixOp op = make_prefix_op(p, p_stride);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (HW % 4 == 0) pointwise_kernel<PrefixOp, 4, false, true, 3><<<grid, kThreads, 0, st>>>(in, nullptr, out, op, nullptr, HW, s.chunk);
+  else pointwise_kernel<PrefixOp, 1, false, true, 3><<<grid, kThreads, 0, st>>>(in, nullptr, out, op, nullptr, HW, s.chunk);
+  RGIE_LAUNCH_OK();
+  return 0;
+}
+
+int rgie_filter_prefix_bwd(const float* in, const float* gout, const float* p, int p_stride, float* gp, int gp_stride,
+                           int B, int H, int W, float* ws, void* stream) {
+  RGIE_CHECK(B > 0 && H > 0 && W > 0 && ws != nullptr, "rgie_filter_prefix_bwd: bad arguments");
+  const int HW = H * W;
+  LaunchShape s = shape_for(HW, B, true);
+  dim3 grid(s.nblk, B);
+  PrefixOp op = make_prefix_op(p, p_stride);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (HW % 4 == 0) pointwise_kernel<PrefixOp, 4, true, false, 2><<<grid, kThreads, 0, st>>>(in, gout, nullptr, op, ws, HW, s.chunk);
+  else pointwise_kernel<PrefixOp, 1, true, false, 2><<<grid, kThreads, 0, st>>>(in, gout, nullptr, op, ws, HW, s.chunk);
+  RGIE_LAUNCH_OK();
+  finalize_partials<<<B, 64, 0, st>>>(ws, s.nblk, PrefixOp::NP, gp, gp_stride);
   RGIE_LAUNCH_OK();
   return 0;
 }

@@ -13,6 +13,7 @@ step counter, so there is no host round trip inside the loop.  PyTorch only owns
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional, Sequence
 
 import numpy as np
@@ -70,6 +71,9 @@ class ParametricEditEngine:
         self.use_graph = use_graph
         self.filters = list(DEFAULT_FILTERS)
         self.kinds = [_lib.FILTER_KINDS[f] for f in self.filters]
+        # exposure -> saturation -> tone -> colour run as one pixel pass each way (rgie_filter_prefix_*): stages 1..3 of
+        # the chain are never materialised.  RGIE_FUSED_PREFIX=0 keeps the four separate passes (bit-identical images).
+        self.n_prefix = 4 if (self.filters[:4] == DEFAULT_FILTERS[:4] and os.environ.get("RGIE_FUSED_PREFIX", "1") != "0") else 0
         self.poff, o = [], 0
         for f in self.filters:
             self.poff.append(o)
@@ -89,7 +93,8 @@ class ParametricEditEngine:
         self.loss = torch.zeros(B, **f32); self.preds = torch.zeros(B, self.nc, **f32)
         self.target = torch.zeros(B, 2, **f32)
         self.logits = torch.zeros(B * reps, self.nc, **f32); self.dlogits = torch.zeros(B * reps, self.nc, **f32)
-        self.stage = [torch.empty(B, 3, height, width, **f32) for _ in range(len(self.filters) + 1)]
+        self.stage = [torch.empty(B, 3, height, width, **f32) if (k == 0 or k >= self.n_prefix) else None
+                      for k in range(len(self.filters) + 1)]
         self.gA = torch.empty(B, 3, height, width, **f32); self.gB = torch.empty(B, 3, height, width, **f32)
         if self.resize.identity:
             self.resized, self.dresized = None, None
@@ -118,7 +123,12 @@ class ParametricEditEngine:
 
     def _filters_fwd(self, p: torch.Tensor):
         lib, st = self.lib, self._st()
+        if self.n_prefix:
+            check(lib.rgie_filter_prefix_fwd(ptr(self.stage[0]), ptr(self.stage[self.n_prefix]), ptr(p), self.NP, self.B,
+                                             self.H, self.W, st), "filter_prefix_fwd")
         for k, kind in enumerate(self.kinds):
+            if k < self.n_prefix:
+                continue
             check(lib.rgie_filter_fwd(kind, ptr(self.stage[k]), ptr(self.stage[k + 1]), p.data_ptr() + 4 * self.poff[k],
                                       self.NP, self.B, self.H, self.W, ptr(self.ws), st), "filter_fwd")
 
@@ -164,11 +174,14 @@ class ParametricEditEngine:
                   "resize_bwd")
         if self.span_events is not None:
             self.span_events[1].record()
-        for k in reversed(range(len(self.kinds))):
+        for k in reversed(range(self.n_prefix, len(self.kinds))):
             check(lib.rgie_filter_bwd(self.kinds[k], ptr(self.stage[k]), ptr(g_cur), ptr(g_nxt),
                                       self.p.data_ptr() + 4 * self.poff[k], self.NP, self.gp.data_ptr() + 4 * self.poff[k],
                                       self.NP, B, self.H, self.W, ptr(self.ws), st), "filter_bwd")
             g_cur, g_nxt = g_nxt, g_cur
+        if self.n_prefix:
+            check(lib.rgie_filter_prefix_bwd(ptr(self.stage[0]), ptr(g_cur), ptr(self.p), self.NP, ptr(self.gp), self.NP, B,
+                                             self.H, self.W, ptr(self.ws), st), "filter_prefix_bwd")
         check(lib.rgie_params_default_bwd(ptr(self.x), ptr(self.gp), B, float(self.H), st), "params_bwd")
         check(lib.rgie_adam_step_sched(ptr(self.x), ptr(self.gp), ptr(self.m), ptr(self.v), B, self.NP, ptr(self.sched),
                                        ptr(self.counter), 1.0 - 0.9, 0.999, 1.0 - 0.999, 1e-8, ptr(self.loss),

@@ -52,6 +52,27 @@ def filter_fwd(kind: int, x: torch.Tensor, p: torch.Tensor, p_stride: int, out: 
     return out
 
 
+def filter_prefix_fwd(x: torch.Tensor, p: torch.Tensor, p_stride: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """exposure -> saturation -> tone -> colour in one pass; p = 34 consecutive effective parameters per image."""
+    _require_cuda(x, "image"); _require_cuda(p, "params")
+    B, _, H, W = x.shape
+    out = torch.empty_like(x) if out is None else out
+    check(_lib.load().rgie_filter_prefix_fwd(ptr(x), ptr(out), ptr(p), p_stride, B, H, W, stream_ptr(x.device)),
+          "rgie_filter_prefix_fwd")
+    return out
+
+
+def filter_prefix_bwd(x: torch.Tensor, gout: torch.Tensor, p: torch.Tensor, p_stride: int, gp: torch.Tensor, gp_stride: int,
+                      ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The 34 parameter gradients of the fused head of the chain (no d(image): its input is the fixed original)."""
+    _require_cuda(x, "image"); _require_cuda(gout, "grad"); _require_cuda(p, "params"); _require_cuda(gp, "gparams")
+    B, _, H, W = x.shape
+    ws = filter_workspace(B, H, W, x.device) if ws is None else ws
+    check(_lib.load().rgie_filter_prefix_bwd(ptr(x), ptr(gout), ptr(p), p_stride, ptr(gp), gp_stride, B, H, W, ptr(ws),
+                                             stream_ptr(x.device)), "rgie_filter_prefix_bwd")
+    return gp
+
+
 def filter_bwd(kind: int, x: torch.Tensor, gout: torch.Tensor, p: torch.Tensor, p_stride: int, gp: torch.Tensor,
                gp_stride: int, gin: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None) -> torch.Tensor:
     _require_cuda(x, "image"); _require_cuda(gout, "grad"); _require_cuda(p, "params"); _require_cuda(gp, "gparams")

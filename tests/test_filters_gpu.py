@@ -145,3 +145,57 @@ def test_chain_vs_golden(golden_dir):
         assert grel <= 2e-2, f"{key}: d(image) rel-L1 {grel}"
         checked += 1
     assert checked >= 8
+
+
+def _raw_fwd(kind, x, p, off, stride):
+    """rgie_filter_fwd on the parameter block that starts `off` floats into each row of the [B, stride] table."""
+    import ctypes as C
+    from regressor_guided_image_editing_b200 import _lib, ops
+    B, _, H, W = x.shape
+    out, ws = torch.empty_like(x), ops.filter_workspace(B, H, W, x.device)
+    _lib.check(_lib.load().rgie_filter_fwd(kind, _lib.ptr(x), _lib.ptr(out), C.c_void_p(p.data_ptr() + 4 * off), stride, B, H, W,
+                                           _lib.ptr(ws), _lib.stream_ptr(x.device)))
+    return out
+
+
+def _raw_bwd(kind, x, gout, p, gp, off, stride):
+    import ctypes as C
+    from regressor_guided_image_editing_b200 import _lib, ops
+    B, _, H, W = x.shape
+    gin, ws = torch.empty_like(x), ops.filter_workspace(B, H, W, x.device)
+    _lib.check(_lib.load().rgie_filter_bwd(kind, _lib.ptr(x), _lib.ptr(gout), _lib.ptr(gin), C.c_void_p(p.data_ptr() + 4 * off),
+                                           stride, C.c_void_p(gp.data_ptr() + 4 * off), stride, B, H, W, _lib.ptr(ws),
+                                           _lib.stream_ptr(x.device)))
+    return gin
+
+
+@pytest.mark.parametrize("hw", [(36, 44), (33, 57), (64, 64)])
+def test_fused_prefix_equals_four_passes(hw):
+    """rgie_filter_prefix_fwd/bwd (exposure -> saturation -> tone -> colour as one pixel pass, the head of the default
+    list) against the four separate kernels: bit-identical image, parameter gradients equal up to summation order."""
+    from regressor_guided_image_editing_b200 import _lib, ops
+    h, w = hw
+    B = 3
+    g = torch.Generator().manual_seed(21)
+    im = torch.stack([torch.clamp(O.synthetic_image(10 + i, h, w) * 1.3 - 0.1, 0, 1) for i in range(B)]).to(DEV)
+    p = torch.cat([0.4 * torch.randn(B, 1, generator=g), 1.0 + 0.5 * torch.rand(B, 1, generator=g),
+                   1.0 + 0.3 * torch.randn(B, 32, generator=g), torch.zeros(B, 7)], dim=1).to(DEV).contiguous()   # stride 41
+    NP = p.shape[1]
+    gout = torch.randn(im.shape, generator=g).to(DEV)
+    fused = ops.filter_prefix_fwd(im, p, NP)
+    names, offs, cnt = ["exposure", "saturation", "tone", "color"], [0, 1, 2, 10], [1, 1, 8, 24]
+    stages = [im]
+    for n, o in zip(names, offs):
+        stages.append(_raw_fwd(_lib.FILTER_KINDS[n], stages[-1], p, o, NP))
+    assert torch.equal(fused, stages[-1])
+    gp_seq = torch.zeros(B, NP, device=DEV)
+    gcur = gout
+    for k in reversed(range(4)):
+        gcur = _raw_bwd(_lib.FILTER_KINDS[names[k]], stages[k], gcur, p, gp_seq, offs[k], NP)
+    gp_fused = torch.zeros(B, NP, device=DEV)
+    ops.filter_prefix_bwd(im, gout, p, NP, gp_fused, NP)
+    torch.cuda.synchronize()
+    assert torch.equal(gp_fused[:, 34:], torch.zeros(B, NP - 34, device=DEV))
+    for o, c in zip(offs, cnt):
+        a, b = gp_fused[:, o:o + c], gp_seq[:, o:o + c]
+        assert (a - b).abs().max().item() <= 2e-5 * (b.abs().max().item() + 1e-3), (o, a, b)

@@ -55,6 +55,16 @@ if True:
     tb = timeit(lambda: ops.filter_bwd(kind, x, g, p, 1, gp, 1, gin=gin, ws=ws))
     rows.append({"filter": name, "fwd_ms": tf, "fwd_GBs": 2 * N / tf / 1e6, "fwd_frac": 2 * N / tf / 1e6 / peak,
                  "bwd_ms": tb, "bwd_GBs": 3 * N / tb / 1e6, "bwd_frac": 3 * N / tb / 1e6 / peak})
+if True:
+    # the fused head of the default chain: exposure -> saturation -> tone -> colour in one pass (fwd 2N; bwd reads x and g: 2N)
+    pv = PARAMS["exposure"] + PARAMS["saturation"] + PARAMS["tone"] + PARAMS["color"]
+    p = torch.tensor(pv, device=dev).repeat(B, 1).contiguous()
+    out = torch.empty_like(x); gp = torch.empty(B, 34, device=dev)
+    ws = ops.filter_workspace(B, H, H, dev)
+    tf = timeit(lambda: ops.filter_prefix_fwd(x, p, 34, out=out))
+    tb = timeit(lambda: ops.filter_prefix_bwd(x, g, p, 34, gp, 34, ws=ws))
+    rows.append({"filter": "prefix(exp,sat,tone,col)", "fwd_ms": tf, "fwd_GBs": 2 * N / tf / 1e6, "fwd_frac": 2 * N / tf / 1e6 / peak,
+                 "bwd_ms": tb, "bwd_GBs": 2 * N / tb / 1e6, "bwd_frac": 2 * N / tb / 1e6 / peak})
 rs = ops.Resize(H, H, 480, 480)
 xo = torch.empty(B, 3, 480, 480, device=dev); go = torch.randn_like(xo); gi = torch.empty_like(x)
 No = xo.numel() * 4
@@ -66,6 +76,8 @@ for r in rows:
     print(f"{r['filter']:22s} fwd {r['fwd_ms']:7.3f} ms {r['fwd_GBs']:7.0f} GB/s ({100*r['fwd_frac']:5.1f}%)   "
           f"bwd {r['bwd_ms']:7.3f} ms {r['bwd_GBs']:7.0f} GB/s ({100*r['bwd_frac']:5.1f}%)")
 tot = sum(r["fwd_ms"] + r["bwd_ms"] for r in rows if r["filter"] in ("exposure", "saturation", "tone", "color", "contrast", "sharp", "blur", "scale", "resize 512->480 (aa)"))
-print(f"default chain (8 filters + resize), fwd+bwd: {tot:.3f} ms")
+print(f"default chain as 8 separate filters + resize, fwd+bwd: {tot:.3f} ms")
+tot2 = sum(r["fwd_ms"] + r["bwd_ms"] for r in rows if r["filter"] in ("prefix(exp,sat,tone,col)", "contrast", "sharp", "blur", "scale", "resize 512->480 (aa)"))
+print(f"default chain as the engine runs it (fused head + contrast, sharp, blur, scale + resize), fwd+bwd: {tot2:.3f} ms")
 if a.out:
     json.dump(rows, open(a.out, "w"), indent=1)
