@@ -92,8 +92,12 @@ def optimization(x0, params, objective_function, learning_rate=0.1, lr_rampdown_
         lr = float(learning_rate * lr_ramp)
         loss = objective_function(x_opt, **params)
         g, = torch.autograd.grad(loss, x_opt)
-        ops.adam_step(x_opt.data, g.contiguous(), m, v, lr, step + 1, loss=loss.detach().reshape(1).float().contiguous(),
-                      best_loss=best_loss, best_x=best_x, best_step=best_step, step=step)
+        # ONE problem whatever the shape of x: the reference compares one scalar loss and snapshots the whole tensor
+        # (:78-81), also when x is a batch of style codes [B, 8, 1, 1] -- hence the flat views (adam_step treats a 2-D+
+        # tensor as one problem per row, with one loss per row)
+        ops.adam_step(x_opt.data.view(-1), g.contiguous().view(-1), m.view(-1), v.view(-1), lr, step + 1,
+                      loss=loss.detach().reshape(1).float().contiguous(), best_loss=best_loss, best_x=best_x.view(-1),
+                      best_step=best_step, step=step)
         if verbose:
             print(f'[ step {step + 1:>4d}/{num_steps}] [ loss: {float(loss):<5.4f}] [ lr: {float(lr):<5.4f}] ')
     return best_x

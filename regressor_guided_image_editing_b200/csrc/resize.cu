@@ -15,6 +15,10 @@ namespace rgie {
 
 // output rows per block of the fused kernels: a group of R outputs needs ~R * in/out + taps source rows, so the halo (rows
 // staged and filtered by two neighbouring blocks) shrinks from ~50 % at R = 8 to ~25 % at R = 16.  RGIE_RESIZE_ROWS overrides.
+// threads per block of the fused kernels: a 480-wide row leaves 224 of 256 threads idle in its second column sweep and a
+// block spends its life in load -> filter -> filter -> store phases, so 512 threads (one sweep, twice the warps to overlap the
+// phases of neighbouring blocks) is the default; RGIE_RESIZE_THREADS=256 restores the old shape.
+static const int kFuseThreads = getenv("RGIE_RESIZE_THREADS") && atoi(getenv("RGIE_RESIZE_THREADS")) == 256 ? 256 : 512;
 static const int kFuseRows = getenv("RGIE_RESIZE_ROWS") ? (atoi(getenv("RGIE_RESIZE_ROWS")) > 0 ? atoi(getenv("RGIE_RESIZE_ROWS")) : 8) : 8;
 constexpr int kMaxTapsReg = 8;
 
@@ -190,7 +194,7 @@ __device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__
 }
 
 // forward: one block = kFuseRows output rows of one plane; needs input rows [ymin[o0], ymin[o1] + ysize[o1])
-__global__ void __launch_bounds__(256) resize_fused_fwd_kernel(const float* __restrict__ in, float* __restrict__ out,
+__global__ void __launch_bounds__(512) resize_fused_fwd_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                               const int* __restrict__ xmin, const int* __restrict__ xsize,
                                                               const float* __restrict__ xw, int xk,
                                                               const int* __restrict__ ymin, const int* __restrict__ ysize,
@@ -233,7 +237,7 @@ __global__ void __launch_bounds__(256) resize_fused_fwd_kernel(const float* __re
 }
 
 // backward: one block = kFuseRows rows of gin of one plane; needs gout rows [yo[ys[s0]], yo[ys[s0 + ns] - 1]]
-__global__ void __launch_bounds__(256) resize_fused_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin,
+__global__ void __launch_bounds__(512) resize_fused_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin,
                                                               const int* __restrict__ ys, const int* __restrict__ yo,
                                                               const float* __restrict__ yw, const int* __restrict__ xs,
                                                               const int* __restrict__ xo_tab, const float* __restrict__ xw,
@@ -318,7 +322,7 @@ int rgie_resize_fwd(const RgieResize* r, const float* in, float* out, int planes
   RGIE_CHECK(r && in && out && tmp && planes > 0, "rgie_resize_fwd: bad arguments");
   if (r->fused) {
     const int bpp = (r->out_h + kFuseRows - 1) / kFuseRows;
-    resize_fused_fwd_kernel<<<planes * bpp, 256, (size_t)r->fwd_rows * (r->in_w + r->out_w) * sizeof(float), st>>>(
+    resize_fused_fwd_kernel<<<planes * bpp, kFuseThreads, (size_t)r->fwd_rows * (r->in_w + r->out_w) * sizeof(float), st>>>(
         in, out, r->ax_w.xmin, r->ax_w.xsize, r->ax_w.w, r->ax_w.kmax, r->ax_h.xmin, r->ax_h.xsize, r->ax_h.w, r->ax_h.kmax,
         r->in_h, r->in_w, r->out_h, r->out_w, bpp, r->fwd_rows, kFuseRows);
     RGIE_LAUNCH_OK();
@@ -341,7 +345,7 @@ int rgie_resize_bwd(const RgieResize* r, const float* gout, float* gin, int plan
   // transpose of (vertical o horizontal) = horizontal^T o vertical^T ; tmp: [planes, in_h, out_w]
   if (r->fused) {
     const int bpp = (r->in_h + kFuseRows - 1) / kFuseRows;
-    resize_fused_bwd_kernel<<<planes * bpp, 256, (size_t)(r->bwd_rows + kFuseRows) * r->out_w * sizeof(float), st>>>(
+    resize_fused_bwd_kernel<<<planes * bpp, kFuseThreads, (size_t)(r->bwd_rows + kFuseRows) * r->out_w * sizeof(float), st>>>(
         gout, gin, r->ax_h.t_start, r->ax_h.t_out, r->ax_h.t_w, r->ax_w.t_start, r->ax_w.t_out, r->ax_w.t_w, r->in_h, r->in_w,
         r->out_h, r->out_w, bpp, r->bwd_rows, kFuseRows);
     RGIE_LAUNCH_OK();

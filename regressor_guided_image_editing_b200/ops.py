@@ -264,6 +264,10 @@ def adam_step(x: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor
     _require_cuda(x, "x"); _require_cuda(g, "g")
     x2 = x.view(1, -1) if x.dim() == 1 else x.view(x.shape[0], -1)
     B, n = x2.shape
+    for name, t in (("loss", loss), ("best_loss", best_loss), ("best_step", best_step)):
+        if t is not None and t.numel() != B:
+            raise _lib.RgieError(f"adam_step: {name} holds {t.numel()} values for {B} problems (x is [{B}, {n}]: one problem "
+                                 f"per row; pass flat views for a single problem)")
     step_size, bc2_sqrt = adam_scalars(lr, k, beta1, beta2)
     check(_lib.load().rgie_adam_step(ptr(x), ptr(g), ptr(m), ptr(v), B, n, step_size, bc2_sqrt, 1.0 - beta1, beta2,
                                      1.0 - beta2, eps, ptr(loss), ptr(best_loss), ptr(best_x), ptr(best_step), step,

@@ -145,7 +145,7 @@ def test_configs2_shape_munit_batch16(precision, tol_loss, tol_x):
     assert e_l <= tol_loss
     if tol_x is not None:
         # Adam moves every component by +-lr per step whatever its gradient's size, so a component whose gradient is at the
-        # round-off level (128 style components, a handful are) may take the other sign and end one or two steps away:
-        # measured on B200: loss within 7e-7 at every step, ONE component off by exactly one step (0.05).  Bound: at most
-        # 4 components beyond tol_x, none further than two full steps.
+        # round-off level may take the other sign and end one or two steps away: at most 4 of the 128 components beyond
+        # tol_x, none further than two full steps.  (This bound is what caught the generic path treating a [B, 8, 1, 1]
+        # style tensor as B problems with one loss each while the reference keeps ONE best-x for the whole tensor.)
         assert n_off <= 4 and e_x <= 2 * lr + 1e-3
