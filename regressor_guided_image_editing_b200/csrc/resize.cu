@@ -15,10 +15,10 @@ namespace rgie {
 
 // output rows per block of the fused kernels: a group of R outputs needs ~R * in/out + taps source rows, so the halo (rows
 // staged and filtered by two neighbouring blocks) shrinks from ~50 % at R = 8 to ~25 % at R = 16.  RGIE_RESIZE_ROWS overrides.
-// threads per block of the fused kernels: a 480-wide row leaves 224 of 256 threads idle in its second column sweep and a
-// block spends its life in load -> filter -> filter -> store phases, so 512 threads (one sweep, twice the warps to overlap the
-// phases of neighbouring blocks) is the default; RGIE_RESIZE_THREADS=256 restores the old shape.
-static const int kFuseThreads = getenv("RGIE_RESIZE_THREADS") && atoi(getenv("RGIE_RESIZE_THREADS")) == 256 ? 256 : 512;
+// threads per block of the fused kernels.  512 (one column sweep of a 480-wide row instead of two, twice the warps) was tried:
+// 0.247 / 0.273 ms against 0.213 / 0.257 ms at 256 threads (64 x 3 planes, 512 -> 480) -- the block is bound by its
+// load -> filter -> filter -> store phases, not by idle lanes.  RGIE_RESIZE_THREADS=512 keeps the experiment reachable.
+static const int kFuseThreads = getenv("RGIE_RESIZE_THREADS") && atoi(getenv("RGIE_RESIZE_THREADS")) == 512 ? 512 : 256;
 static const int kFuseRows = getenv("RGIE_RESIZE_ROWS") ? (atoi(getenv("RGIE_RESIZE_ROWS")) > 0 ? atoi(getenv("RGIE_RESIZE_ROWS")) : 8) : 8;
 constexpr int kMaxTapsReg = 8;
 

@@ -84,14 +84,29 @@ def test_latent_optimisation_matches_oracle():
     assert err <= 2e-4
 
 
-@pytest.mark.parametrize("precision,tol_loss,tol_x", [("fp32", 2e-5, 5e-4), ("bf16", 1e-3, None)])
+_C2_ORACLES = {}          # the two oracle runs are the same for both precisions: ~2 minutes of CPU work, done once
+
+
+@pytest.mark.parametrize("precision,tol_loss,tol_x", [("fp32", 2e-5, 2e-3), ("bf16", 1e-3, None)])
 def test_configs2_shape_munit_batch16(precision, tol_loss, tol_x):
     """BASELINE.json configs[2] as stated: latent optimisation through the random-init MUNIT generator
     (imagenet2imagenet.yaml, full width: regressor_guided_image_editing_b200/external/imaginaire/generators/munit.py, pinned
     to the reference's module in tests/test_munit_cpu.py) + the native regressor, batch 16 at 256x256, the reference's
-    call surface and weights (weight_clf 0.2, weight_recon 1.0, lr 0.05), 3 steps, against the CPU oracle on the same
-    seeds.  With B > 1 the reference's loss is the batch mean and best_x is picked for the batch as a whole
-    (optimize_image.py:78-81) -- kept.  The generator is PyTorch on both sides (cuDNN TF32 off for the comparison)."""
+    call surface and weights (weight_clf 0.2, weight_recon 1.0, lr 0.05), 3 steps, same seeds.  With B > 1 the reference's
+    loss is the batch mean and ONE best_x is kept for the whole style tensor (optimize_image.py:78-81) -- kept.
+
+    Two oracles:
+      * all-CPU (generator + regressor restatement on the CPU): per-step losses and the target must agree (measured 7e-7).
+        The style trajectory is NOT compared against it: d(loss)/d(style) is a sum over ~10^7 activations that cancels to
+        ~1e-5 of its terms, and fp32 cuDNN convolutions leave 5-17 % noise on it against fp64 where CPU fp32 leaves 0.2-0.6 %
+        (tools/diag_latent_conditioning.py, measured on B200 with every TF32 switch off; fp64 GPU == fp64 CPU to 3e-13) --
+        the reference itself, run on a GPU, walks away from its own CPU run by that much, and Adam turns any gradient into
+        +-lr steps.
+      * hybrid: the SAME PyTorch generator on the GPU (the library code both sides share) + the CPU regressor restatement
+        + torch Adam.  What differs from the product path is exactly the native part under test -- regressor forward /
+        input gradient, the fused Adam + best-x kernel -- so here the visited style codes and best_x must agree (fp32).
+    Measured on B200: losses within 2e-6 of both oracles; visited styles / best_x within 2.6e-4 (fp32) and 3.6e-4 (bf16) of
+    the hybrid oracle, 1.9e-2 from the all-CPU one."""
     from regressor_guided_image_editing_b200 import optimize_image_imaginaire as oii
     from regressor_guided_image_editing_b200.baselines import optimize_image as oi
     from regressor_guided_image_editing_b200.baselines.losses.ValenceArousalLoss import ValenceArousalLoss
@@ -100,22 +115,39 @@ def test_configs2_shape_munit_batch16(precision, tol_loss, tol_x):
     sd = O.make_regressor_state_dict()
     torch.manual_seed(0)
     gen_cpu = Generator()                                           # training mode, as the script leaves it (:75-79)
-    gen_gpu = copy.deepcopy(gen_cpu).to(DEV)
+    gen_gpu, gen_hyb = copy.deepcopy(gen_cpu).to(DEV), copy.deepcopy(gen_cpu).to(DEV)
     image = torch.stack([2.0 * O.synthetic_image(300 + i, h, h) - 1.0 for i in range(B)])
     torch.manual_seed(2300)
     offs = O.draw_crop_offsets(1 + steps, B, 480, 480)
     w_clf, w_rec, lr = 0.2, 1.0, 0.05
-
-    with torch.no_grad():
-        content, style = gen_cpu.autoencoder_a.encode(image)
-        pred0 = O.regressor_predict(image, sd, offs[0], normalize=False)[:, [0, 1]]
-    target = O.get_condition_from_alpha(pred0, 0.1)
-    ref = O.optimize_generic(style, lambda x, s: O.objective_imaginaire(
-        x, gen_cpu, content, sd, offs[1 + s], target, w_clf, w_rec)[0], lr, steps)
-
-    tf32 = torch.backends.cudnn.allow_tf32
-    torch.backends.cudnn.allow_tf32 = False
+    tf32, det = torch.backends.cudnn.allow_tf32, torch.backends.cudnn.deterministic
+    torch.backends.cudnn.allow_tf32, torch.backends.cudnn.deterministic = False, True
     try:
+        if not _C2_ORACLES:
+            with torch.no_grad():
+                content, style = gen_cpu.autoencoder_a.encode(image)
+                pred0 = O.regressor_predict(image, sd, offs[0], normalize=False)[:, [0, 1]]
+            target = O.get_condition_from_alpha(pred0, 0.1)
+            ref_cpu = O.optimize_generic(style, lambda x, s: O.objective_imaginaire(
+                x, gen_cpu, content, sd, offs[1 + s], target, w_clf, w_rec)[0], lr, steps)
+
+            # ---- hybrid oracle: generator on the GPU, regressor restatement on the CPU
+            with torch.no_grad():
+                content_h, style_h = gen_hyb.autoencoder_a.encode(image.to(DEV))
+            hyb_xs = []
+
+            def hybrid_objective(x, s):
+                hyb_xs.append(x.detach().clone())
+                img = torch.clamp(gen_hyb.autoencoder_a.decode(content_h, x), min=-1, max=1)
+                pred = O.regressor_predict(img.cpu(), sd, offs[1 + s], normalize=False)[:, [0, 1]]
+                loss = (w_clf * O.va_loss(pred, target, 1.0)).to(DEV)
+                return loss + w_rec * F.l1_loss(gen_hyb.autoencoder_a.encode(img)[0], content_h)
+
+            ref_hyb = O.optimize_generic(style_h, hybrid_objective, lr, steps)
+            _C2_ORACLES.update(target=target, ref_cpu=ref_cpu, ref_hyb=ref_hyb, hyb_xs=hyb_xs)
+        target, ref_cpu, ref_hyb, hyb_xs = (_C2_ORACLES[k] for k in ("target", "ref_cpu", "ref_hyb", "hyb_xs"))
+
+        # ---- native (reference call surface)
         clf = ValenceArousalLoss(sd, torch.device(DEV), 1, is_minimized=True, is_input_range_0_1=False, requires_grad=True,
                                  precision=precision)
         params = {"gen": gen_gpu, "clf": clf, "dis": None, "gan_loss": None, "weight_clf": w_clf, "weight_dis": 0.0,
@@ -123,9 +155,10 @@ def test_configs2_shape_munit_batch16(precision, tol_loss, tol_x):
         torch.manual_seed(2300)
         x0, params = oii.initialize_imaginaire(image.to(DEV), params)
         params["target"] = oi.get_condition_from_alpha(0.1, clf, image.to(DEV))
-        losses = []
+        losses, xs = [], []
 
         def objective(x, **kw):
+            xs.append(x.detach().clone())
             loss = oii.objective_function_imaginaire(x, **kw)
             losses.append(loss.detach())
             return loss
@@ -133,19 +166,18 @@ def test_configs2_shape_munit_batch16(precision, tol_loss, tol_x):
         best = oi.optimization(x0, params, objective, learning_rate=lr, num_steps=steps)
         torch.cuda.synchronize()
     finally:
-        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32, torch.backends.cudnn.deterministic = tf32, det
     losses = torch.stack(losses).cpu()
     e_t = (params["target"].cpu() - target).abs().max().item()
-    e_l = (losses - ref["losses"]).abs().max().item()
-    d_x = (best.cpu() - ref["best_x"]).abs().flatten()
-    e_x, n_off = d_x.max().item(), int((d_x > tol_x).sum()) if tol_x is not None else -1
-    print(f"configs[2] {precision}: target diff {e_t:.2e}, per-step loss diff {e_l:.2e} (losses {losses.tolist()}), best style: "
-          f"max diff {e_x:.2e}, {n_off} of {d_x.numel()} components beyond {tol_x}")
+    e_l_cpu = (losses - ref_cpu["losses"]).abs().max().item()
+    e_l_hyb = (losses - ref_hyb["losses"].cpu()).abs().max().item()
+    e_xs = max((a - b).abs().max().item() for a, b in zip(xs, hyb_xs))
+    e_best = (best - ref_hyb["best_x"]).abs().max().item()
+    e_best_cpu = (best.cpu() - ref_cpu["best_x"]).abs().max().item()
+    print(f"configs[2] {precision}: target diff {e_t:.2e}; per-step loss vs all-CPU oracle {e_l_cpu:.2e}, vs hybrid oracle {e_l_hyb:.2e} "
+          f"(losses {losses.tolist()}); visited styles vs hybrid {e_xs:.2e}, best style vs hybrid {e_best:.2e} "
+          f"(vs all-CPU: {e_best_cpu:.2e}, not bounded)")
     assert e_t <= (1e-5 if precision == "fp32" else 5e-3)
-    assert e_l <= tol_loss
+    assert e_l_cpu <= tol_loss and e_l_hyb <= tol_loss
     if tol_x is not None:
-        # Adam moves every component by +-lr per step whatever its gradient's size, so a component whose gradient is at the
-        # round-off level may take the other sign and end one or two steps away: at most 4 of the 128 components beyond
-        # tol_x, none further than two full steps.  (This bound is what caught the generic path treating a [B, 8, 1, 1]
-        # style tensor as B problems with one loss each while the reference keeps ONE best-x for the whole tensor.)
-        assert n_off <= 4 and e_x <= 2 * lr + 1e-3
+        assert e_xs <= tol_x and e_best <= tol_x
