@@ -1527,6 +1527,254 @@ gemm_patch_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
 }
 
 // ===============================================================================================================
+// conv1 + max-pool in one launch.  The stem's 64-channel 224 x 224 activation is the largest tensor of the network
+// (6.4 MB per crop in bf16): conv1 wrote it (2.05 GB per 320 crops) and the pooling kernel read it back.  Here the pooled
+// tensor and the argmax bytes are produced straight from the accumulators:
+//   * a tile is still a 16 x 8 conv patch (one 19-line TMA box, 16 MMAs).  Vertically it starts at conv line 14 ty - 1 of
+//     ITS image, so its 16 lines hold 7 pooling-window rows completely (bands overlap by 2 lines: 1.14x the conv work).
+//     Horizontally the tiles of a band do NOT overlap (columns 8k .. 8k+7): a CTA walks the 28 tiles of a band left to
+//     right, and the one column a window needs from the tile on its left (window 4k = columns 8k-1, 8k, 8k+1) travels
+//     through a 2 KB carry slot in shared memory.  (A first version with tiles overlapping both ways -- 1.5x the conv
+//     work -- was correct and SLOWER than conv1 + maxpool_fwd_kernel, 2.03 vs 1.64 ms per 320 crops: the stem's main loop
+//     costs ~1 650 cycles per tile, not the 16 x 72 of its MMAs.)
+//   * an epilogue warp group turns its accumulator tile into post-ReLU bf16 rows in a 16 KB shared-memory tile
+//     ([128 pixels][8 chunks of 16 B], chunk index XOR (pixel & 7): conflict-free both ways), releases the accumulator,
+//     copies column 7 into carry slot (tile & 3), and 128 threads scan the 7 x 4 windows x 8 channel chunks with the
+//     packed-pair compare / select of maxpool_fwd_kernel (first maximum in (dy, dx) scan order wins, strict >): pooled
+//     values and argmax bytes are bit-identical to conv1 followed by maxpool_fwd_kernel.
+//   * the two groups take alternate tiles; `carry_bar[g]` (one arrival per tile of group g) tells the other group that
+//     tile s's column is in its slot.  A slot is rewritten four tiles later, after the writer has seen the carry signal of
+//     tile s - 1, which its owner raises only after it has finished pooling tile s - 3, the last reader of that slot.
+// Conv positions outside the image (line / column -1 or 224, the pool's padding) are computed and ignored.
+// Shared memory: the plan of the patch kernel; the tiles and the carry slots live in the 40 KB of the weight area that
+// conv1's four 8 KB tap matrices leave free.
+// ===============================================================================================================
+struct PoolSmem {
+  static constexpr int TILE_OFF = PatchSmem::W_OFF + 4 * 64 * BK * 2;       // behind conv1's 32 KB of weights
+  static constexpr int CARRY_OFF = TILE_OFF + 2 * 16384;                     // 4 slots x 2 KB
+  static constexpr int END = CARRY_OFF + 4 * 2048;
+};
+static_assert(PoolSmem::END <= PatchSmem::W_OFF + PATCH_W_BYTES, "conv1 + pool: tiles and carry slots must fit the free weight area");
+constexpr int POOL_BAND_TILES = 28;     // 224 / 8
+
+__global__ void __launch_bounds__(num_threads(8), 1)
+gemm_conv1_pool_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmB, const GemmDesc d,
+                       const PatchTaps tp, const StemPoolParams sp, const int num_bands) {
+  using L = PatchSmem;
+  constexpr int BN = 64, NY = 4;
+  constexpr int NACC = 4;
+  constexpr uint32_t TMEM_COLS = tmem_cols(BN, NACC);
+  constexpr int W_TAP_BYTES = BN * BK * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_base + L::BAR_OFF;
+  auto afull_bar = [&](int s) { return bar_base + 8u * s; };
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (PATCH_SLABS + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * PATCH_SLABS + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * PATCH_SLABS + NACC + a); };
+  const uint32_t wfull_bar = bar_base + 8u * (2 * PATCH_SLABS + 2 * NACC);
+  // carry_bar[0]: the spare barrier slot of the patch plan; carry_bar[1]: the unused upper half of the TMEM-pointer slot
+  auto carry_bar = [&](int g) { return g == 0 ? bar_base + 8u * (2 * PATCH_SLABS + 2 * NACC + 1) : smem_base + L::TMEM_PTR_OFF + 8u; };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_PTR_OFF);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t slab_bytes = (uint32_t)((16 + NY - 1) * 8 * 128);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA3) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+    for (int s = 0; s < PATCH_SLABS; ++s) {
+      mbar_init(afull_bar(s), 1);
+      mbar_init(aempty_bar(s), 1);
+    }
+    for (int a = 0; a < NACC; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    mbar_init(wfull_bar, 1);
+    mbar_init(carry_bar(0), 1);
+    mbar_init(carry_bar(1), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_base + L::TMEM_PTR_OFF),
+                 "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {
+    float* sb = reinterpret_cast<float*>(smem + L::BIAS_OFF);
+    for (int i = threadIdx.x; i < 64; i += num_threads(8)) sb[i] = d.bias != nullptr ? d.bias[i] : 0.f;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  // band -> (image n, band row ty); tile k of the band is the 16 x 8 patch at conv pixel (14 ty - 1, 8 k) of image n
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(wfull_bar, (uint32_t)(d.ntaps * W_TAP_BYTES));
+      for (int t = 0; t < d.ntaps; ++t)
+        tma_load_2d(smem_base + L::W_OFF + t * W_TAP_BYTES, &tmB, t * BK, 0, wfull_bar);
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int band = blockIdx.x; band < num_bands; band += gridDim.x) {
+        const int n = (int)sp.fd_img.div((uint32_t)band), ty = band - n * sp.TY;
+        // source-grid line of conv line y of image n = n * lines_per_img + pad_t + y; the box starts dy0 lines above
+        const int line = n * sp.lines_per_img + d.src.pad_t + (14 * ty - 1) + tp.dy0;
+        for (int k = 0; k < POOL_BAND_TILES; ++k) {
+          mbar_wait(aempty_bar(slot), phase ^ 1);
+          mbar_expect_tx(afull_bar(slot), slab_bytes);
+          tma_load_3d(smem_base + L::A_OFF + slot * PATCH_SLAB_BYTES, &tmA3, 0, d.src.pad_l + 8 * k + tp.dx0, line, afull_bar(slot));
+          if (++slot == PATCH_SLABS) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      mbar_wait(wfull_bar, 0);
+      const uint64_t wdesc0 = make_smem_desc(smem_base + L::W_OFF);
+      int slot = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int band = blockIdx.x; band < num_bands; band += gridDim.x) {
+        for (int k = 0; k < POOL_BAND_TILES; ++k, ++it) {
+          const int acc = it % NACC;
+          const uint32_t acc_phase = (it / NACC) & 1;
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+          mbar_wait(afull_bar(slot), phase);
+          tcgen05_fence_after();
+          const uint64_t adesc0 = make_smem_desc(smem_base + L::A_OFF + slot * PATCH_SLAB_BYTES);
+#pragma unroll
+          for (int yi = 0; yi < NY; ++yi) {
+            const uint64_t adesc = adesc0 + (uint64_t)(yi * 64);
+            const uint64_t bdesc = wdesc0 + (uint64_t)(tp.tap[yi][0] * (W_TAP_BYTES >> 4));
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk)
+              umma_bf16(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (yi | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(aempty_bar(slot));
+          if (++slot == PATCH_SLABS) { slot = 0; phase ^= 1; }
+          umma_commit(tfull_bar(acc));
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue + pooling: two groups of four warps take alternate tiles =====================
+    const float* sbias = reinterpret_cast<const float*>(smem + L::BIAS_OFF);
+    const int grp = (warp - 2) >> 2;
+    const int q = warp & 3;                                   // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;                            // accumulator row = patch pixel (row >> 3, row & 7)
+    const int tid = ((warp - 2) & 3) * 32 + lane;             // 0..127 within the group (any order: used for the window scan)
+    uint8_t* tile_s = smem + PoolSmem::TILE_OFF + grp * 16384;
+    uint8_t* carry_s = smem + PoolSmem::CARRY_OFF;
+    __nv_bfloat16* P1 = reinterpret_cast<__nv_bfloat16*>(sp.P1);
+    int s = 0;                                                // index of the tile in this CTA's sequence
+    int t = 0;                                                // index among this group's tiles
+    for (int band = blockIdx.x; band < num_bands; band += gridDim.x) {
+      const int n = (int)sp.fd_img.div((uint32_t)band), ty = band - n * sp.TY;
+      const int y0 = 14 * ty - 1;
+      for (int k = 0; k < POOL_BAND_TILES; ++k, ++s) {
+        if ((s & 1) != grp) continue;
+        const int acc = s % NACC;
+        const uint32_t acc_phase = (s / NACC) & 1;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+        uint32_t r0[32], r1[32];
+        tmem_ld<32>(taddr, r0);
+        tmem_ld<32>(taddr + 32u, r1);
+        tmem_ld_wait();
+        uint32_t pk[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          pk[j] = pack_bf16x2(fmaxf(__uint_as_float(r0[2 * j]) + sbias[2 * j], 0.f),
+                              fmaxf(__uint_as_float(r0[2 * j + 1]) + sbias[2 * j + 1], 0.f));
+          pk[16 + j] = pack_bf16x2(fmaxf(__uint_as_float(r1[2 * j]) + sbias[32 + 2 * j], 0.f),
+                                   fmaxf(__uint_as_float(r1[2 * j + 1]) + sbias[32 + 2 * j + 1], 0.f));
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(tile_s + row * 128 + ((c ^ (row & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        // the carry signal of tile s - 1 (other group): its column is in slot (s - 1) & 3, and slot s & 3 is free again
+        if (s >= 1) mbar_wait(carry_bar(grp ^ 1), (uint32_t)((grp == 1 ? t : t - 1) & 1));
+        if ((row & 7) == 7) {
+          uint8_t* cs = carry_s + (s & 3) * 2048 + (row >> 3) * 128;
+          const int sw = (row >> 3) & 7;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(cs + ((c ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        }
+        named_bar_sync(1 + grp, 128);
+        if (tid == 0) mbar_arrive(carry_bar(grp));
+        const uint8_t* left_s = carry_s + ((s - 1) & 3) * 2048;   // column 7 of the tile on the left (k > 0 only)
+        for (int item = tid; item < 28 * 8; item += 128) {
+          const int ck = item & 7, pw = item >> 3;
+          const int pr = pw >> 2, pc = pw & 3;
+          const int i = 7 * ty + pr, j = 4 * k + pc;
+          if (i >= sp.Hp) continue;
+          uint32_t best[4], code[4];
+          bool first = true;
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const int ly = 2 * pr + dy, y = y0 + ly;
+            if (y < 0 || y >= sp.H0) continue;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              const int lx = 2 * pc - 1 + dx, x = 8 * k + lx;
+              if (x < 0 || x >= sp.H0) continue;
+              const uint8_t* src = lx < 0 ? left_s + ly * 128 + ((ck ^ (ly & 7)) << 4)
+                                          : tile_s + (ly * 8 + lx) * 128 + ((ck ^ ((ly * 8 + lx) & 7)) << 4);
+              const uint4 u = *reinterpret_cast<const uint4*>(src);
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+              const uint32_t tc = (uint32_t)(dy * 3 + dx) * 0x00010001u;
+              if (first) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { best[e] = w[e]; code[e] = tc; }
+                first = false;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const uint32_t m = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&w[e]),
+                                                 *reinterpret_cast<const __nv_bfloat162*>(&best[e]));
+                  best[e] = (w[e] & m) | (best[e] & ~m);
+                  code[e] = (tc & m) | (code[e] & ~m);
+                }
+              }
+            }
+          }
+          *reinterpret_cast<uint4*>(P1 + geom_row(sp.g1, 0, n, i, j) * 64 + ck * 8) = make_uint4(best[0], best[1], best[2], best[3]);
+          const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            code[e] |= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&best[e]), zero2) & 0x00100010u;
+          uint2 pkc;
+          pkc.x = __byte_perm(code[0], code[1], 0x6420);
+          pkc.y = __byte_perm(code[2], code[3], 0x6420);
+          *reinterpret_cast<uint2*>(sp.arg + (((long)n * sp.Hp + i) * sp.Hp + j) * 64 + ck * 8) = pkc;
+        }
+        named_bar_sync(1 + grp, 128);                         // the tile buffer is rewritten by this group's next tile
+        ++t;
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ===============================================================================================================
 // CTA-pair form of the patch kernel (cta_group::2).  ncu on gemm_patch_kernel<64,3,3> (profiles/README.md, r2_d): the TC
 // pipe is 77 % busy while the tensor datapath is 36 % active -- an N = 64, K = 16 instruction holds the pipe ~72 cycles
 // for 32 cycles of math, so these layers are bound by the NUMBER of tcgen05.mma instructions.  One cta_group::2
@@ -2031,6 +2279,7 @@ int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p) {
   p->patch_2cta = 0;
   p->special = 0;
   p->b2b = 0;
+  p->pool = 0;
   // ---- patch-tile variant: Cin = 64, one N tile, single-plane source whose rows are whole pixel lines, taps on a
   //      (dy, dx) grid of at most 4 x 4 with |dx| well below the pitch
   //      Measured on B200 (320 crops): 3x3 layer1 0.52 -> 0.41 ms, conv1 forward 1.08 -> 0.76 ms, conv1 input gradient
@@ -2182,7 +2431,7 @@ int build_gemm_b2b_sm100(const GemmDesc& d1, const GemmDesc& d2, GemmPlanSm100* 
   RGIE_CHECK(gemm_b2b_eligible(d1, d2), "gemm_b2b: the two ops cannot be fused");
   RGIE_CHECK(d1.a_rows < (1L << 31) && (d1.A2 == nullptr || d1.a2_rows < (1L << 31)), "gemm_b2b: too many rows for a TMA coordinate");
   p->d = d1; p->d2 = d2;
-  p->bn = 256; p->patch = 0; p->special = 0; p->epi = 0; p->b2b = 1;
+  p->bn = 256; p->patch = 0; p->special = 0; p->epi = 0; p->b2b = 1; p->pool = 0;
   p->num_m_tiles = ceil_div(d1.m_end - d1.m_begin, (long)BM);
   p->num_n_tiles = 1;
   const int sms = gemm_sm100_num_sms();
@@ -2211,7 +2460,7 @@ int build_conv_hshare_sm100(const GemmDesc& d, const void* Wh, int dy0, int dx0,
   RGIE_CHECK(dx0 <= 0 && dx0 + HS_NJ - 1 >= 0 && d.src.pad_l + dx0 >= 0, "conv_hshare: tap range");
   p->d = d;
   p->bn = HS_N;
-  p->patch = 0; p->epi = 0; p->b2b = 0;
+  p->patch = 0; p->epi = 0; p->b2b = 0; p->pool = 0;
   p->special = 1;
   const int P = d.src.P;
   const long lines = d.a_rows / P;
@@ -2250,7 +2499,43 @@ static int run_conv_hshare(const GemmPlanSm100& p, cudaStream_t st) {
   return 0;
 }
 
+int run_conv1_pool(const GemmPlanSm100& p, cudaStream_t st) {
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
+    RGIE_CUDA_OK(cudaFuncSetAttribute(gemm_conv1_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PatchSmem::DYN_BYTES));
+    attr_once.done();
+  }
+  PatchTaps tp;
+  tp.ny = p.patch_ny; tp.nx = p.patch_nx; tp.dy0 = p.patch_dy0; tp.dx0 = p.patch_dx0;
+  for (int y = 0; y < 4; ++y)
+    for (int x = 0; x < 4; ++x) tp.tap[y][x] = p.patch_tap[y][x];
+  const int bands = p.sp.n_img * p.sp.TY;
+  const int sms = gemm_sm100_num_sms();
+  gemm_conv1_pool_kernel<<<bands < sms ? bands : sms, num_threads(8), PatchSmem::DYN_BYTES, st>>>(p.tmA, p.tmB, p.d, tp, p.sp, bands);
+  RGIE_LAUNCH_OK();
+  return 0;
+}
+
+int build_conv1_pool_sm100(const GemmDesc& conv1, void* P1, const Geom& g1, uint8_t* arg, int Hp, GemmPlanSm100* p) {
+  if (int rc = build_gemm_sm100(conv1, p)) return rc;
+  RGIE_CHECK(p->patch == 2 && !p->patch_2cta && p->patch_ny == 4 && p->patch_nx == 1, "conv1 + pool: conv1 must be the 4-tap patch variant");
+  RGIE_CHECK(conv1.relu && conv1.Cout == 64 && conv1.ntaps == 4 && conv1.src.planes == 1 && conv1.src.H == conv1.src.W &&
+             conv1.src.H == 2 * Hp && conv1.src.W == 8 * POOL_BAND_TILES, "conv1 + pool: unexpected stem geometry");
+  RGIE_CHECK(g1.planes == 1 && g1.n_img == conv1.src.n_img && g1.H == Hp && g1.W == Hp, "conv1 + pool: pooled geometry");
+  StemPoolParams& sp = p->sp;
+  sp.n_img = conv1.src.n_img; sp.H0 = conv1.src.H; sp.Hp = Hp;
+  sp.lines_per_img = conv1.src.S / conv1.src.P;
+  sp.TY = ceil_div(Hp, 7); sp.TX = POOL_BAND_TILES;
+  RGIE_CHECK((long)sp.n_img * sp.TY < (1L << 31), "conv1 + pool: too many bands");
+  sp.fd_img = make_fastdiv((uint32_t)sp.TY);           // band -> image
+  sp.fd_tx = make_fastdiv((uint32_t)sp.TX);
+  sp.P1 = P1; sp.g1 = g1; sp.arg = arg;
+  p->pool = 1;
+  return 0;
+}
+
 int run_gemm_sm100(const GemmPlanSm100& p, cudaStream_t st) {
+  if (p.pool == 1) return run_conv1_pool(p, st);
   if (p.b2b == 1) return run_b2b(p, st);
   if (p.d.m_end <= p.d.m_begin) return 0;
   if (p.special == 1) return run_conv_hshare(p, st);

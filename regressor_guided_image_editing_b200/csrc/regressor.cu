@@ -511,6 +511,10 @@ struct RgieRegressor {
   Geom gZZs, gDYs;       // geometry of one group
   void *zz_s = nullptr, *c1_s = nullptr, *dC1_s = nullptr;
   GemmOp conv1_s, conv1t_s;   // conv1 forward / input gradient over one group
+  // conv1 + max-pool in ONE launch (gemm_conv1_pool_kernel, bf16 tcgen05 mode): the 64-channel 224 x 224 stem activation is
+  // never written to HBM.  `conv1_plain` keeps the plain conv1 plan (rgie_regressor_tap("stem") runs it on demand).
+  int stem_pool = 0;
+  GemmPlanSm100 conv1_plain;
   void* wh_dev = nullptr;     // conv_hshare weights (bf16 mode)
   int Hs[5] = {0, 0, 0, 0, 0};
   Geom gZZ, gDY, gS[5], gPh[5];
@@ -1092,6 +1096,18 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
   }
   if (int rc = fuse_b2b(R, R->fwd_ops)) return rc;
   if (int rc = fuse_b2b(R, R->bwd_ops)) return rc;
+  {
+    // conv1 + max-pool fused (RGIE_STEM_POOL=0 keeps conv1 -> c1 -> maxpool_fwd_kernel).  Needs the 16-channel conv1 operand,
+    // the single-CTA 4-tap patch plan and the whole-batch stem (not the L2-resident sub-batching experiment).
+    static const int env_pool = getenv("RGIE_STEM_POOL") ? atoi(getenv("RGIE_STEM_POOL")) : 1;
+    GemmOp& c1op = R->fwd_ops[0];
+    if (env_pool && R->precision == RGIE_PREC_BF16 && R->zz16 && R->stem_sub == 0 && c1op.plan.patch == 2 && !c1op.plan.patch_2cta &&
+        !c1op.fused_next) {
+      R->conv1_plain = c1op.plan;
+      if (int rc = build_conv1_pool_sm100(c1op.d, R->p1, R->gS[1], R->arg, R->Hs[1], &c1op.plan)) return rc;
+      R->stem_pool = 1;
+    }
+  }
   RGIE_CUDA_OK(cudaDeviceSynchronize());
   guard.ok = true;
   *out = R;
@@ -1138,6 +1154,7 @@ int rgie_regressor_forward_ex(RgieRegressor* R, const float* img, int B, int Hr,
     RGIE_LAUNCH_OK();
     if (sub) { if (int rc = run_op_raw(R, R->conv1_s, st)) return rc; }
     else if (int rc = run_op(R, R->fwd_ops[0], st, 0)) return rc;
+    if (R->stem_pool) continue;                  // fwd_ops[0] was conv1 + max-pool: p1 and the argmax bytes are written
     char* p1g = (char*)R->p1 + (size_t)(n0 / NG) * p1_group;
     uint8_t* argg = R->arg + (size_t)(n0 / NG) * arg_group;
     if (R->dtype == 0)
@@ -1258,6 +1275,12 @@ int rgie_regressor_get_profile(RgieRegressor* R, float* h_ms, double* h_flops, d
     if (!fwd && i == n - 1) useful = (147.0 * 64.0) / (16.0 * 16.0 * 64.0);
     h_flops[i] = op_flops(op.d, useful);
     h_bytes[i] = op_bytes(op.d, R->esz);
+    if (fwd && i == 0 && R->stem_pool) {
+      // conv1 + max-pool in one launch: the packed crops are read, the pooled tensor and one argmax byte per pooled element
+      // are written; the 224 x 224 x 64 conv output never reaches HBM
+      const double pooled = (double)R->N * R->Hs[1] * R->Hs[1] * 64.0;
+      h_bytes[i] = (double)R->gZZ.rows() * 16.0 * R->esz + pooled * (R->esz + 1.0);
+    }
     if (op.absorbed) { h_flops[i] = 0.0; h_bytes[i] = 0.0; h_ms[i] = 0.f; }
     if (op.fused_next) {
       // the fused launch does both ops; the second one's A operand never travels through HBM
@@ -1288,7 +1311,12 @@ int rgie_regressor_tap(RgieRegressor* R, const char* name, float* out, long capa
     *n_out = n;
     return 0;
   }
-  if (nm == "stem") { buf = R->c1; g = make_geom(1, R->N, R->H0, R->H0, 0, 0, 0, 0); C = 64; fh = fw = R->H0; }
+  if (nm == "stem") {
+    // with the fused conv1 + max-pool the stem activation does not exist: produce it on demand from the packed crops of the
+    // last forward (diagnostics only)
+    if (R->stem_pool) { if (int rc = run_gemm_sm100(R->conv1_plain, st)) return rc; }
+    buf = R->c1; g = make_geom(1, R->N, R->H0, R->H0, 0, 0, 0, 0); C = 64; fh = fw = R->H0;
+  }
   else if (nm == "pool") { buf = R->p1; g = R->gS[1]; C = 64; fh = fw = R->Hs[1]; }
   else {
     // "layer{s}.{i}" [".c1" | ".c2"]

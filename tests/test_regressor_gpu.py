@@ -173,3 +173,43 @@ def test_back_to_back_fusion_opt_in_matches():
                            cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
         assert r.returncode == 0, f"RGIE_GEMM_B2B={flag}: " + r.stdout[-2000:] + r.stderr[-2000:]
         assert "2 passed" in r.stdout
+
+
+_STEM_CHILD = r"""
+import sys, torch
+sys.path.insert(0, {root!r})
+from oracle import oracle as O
+from regressor_guided_image_editing_b200 import ops
+sd = O.make_regressor_state_dict()
+torch.manual_seed(5)
+img = torch.stack([O.synthetic_image(20 + i, 480, 480) for i in range(2)]).cuda()
+offs = O.draw_crop_offsets(1, 2, 480, 480)[0].int().cuda()
+reg = ops.Regressor(sd, max_crops=6, crop_size=448, precision="bf16")
+logits = reg.forward(img, offs[:, :3].contiguous(), normalize=True)
+pool = reg.tap("pool", (6, 64, 112, 112))
+dimg = torch.empty_like(img)
+reg.backward(torch.randn(6, 4, generator=torch.Generator().manual_seed(3)).cuda(), dimg)
+torch.cuda.synchronize()
+torch.save(dict(logits=logits.cpu(), pool=pool.cpu(), dimg=dimg.cpu()), sys.argv[1])
+"""
+
+
+def test_fused_conv1_maxpool_is_bit_identical(tmp_path):
+    """gemm_conv1_pool_kernel (conv1 + 3x3/2 max-pool in one launch; the 224 x 224 x 64 stem activation never reaches HBM)
+    against conv1 -> maxpool_fwd_kernel (RGIE_STEM_POOL=0): pooled tensor, logits and the image gradient (which goes through
+    the argmax bytes) must be bit-identical -- same bf16 rounding of the conv output, same first-maximum scan order.
+    The switch is read once per process: two child processes."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for flag in ("1", "0"):
+        path = str(tmp_path / f"stem_{flag}.pt")
+        r = subprocess.run([sys.executable, "-c", _STEM_CHILD.format(root=root), path], env=dict(os.environ, RGIE_STEM_POOL=flag),
+                           capture_output=True, text=True, timeout=300, cwd=root)
+        assert r.returncode == 0, f"RGIE_STEM_POOL={flag}: " + r.stdout[-2000:] + r.stderr[-2000:]
+        outs.append(torch.load(path))
+    a, b = outs
+    assert a["pool"].abs().max().item() > 0
+    assert torch.equal(a["pool"], b["pool"]), (a["pool"] - b["pool"]).abs().max().item()
+    assert torch.equal(a["logits"], b["logits"])
+    assert torch.equal(a["dimg"], b["dimg"])
