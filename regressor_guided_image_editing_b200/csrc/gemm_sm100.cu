@@ -1532,7 +1532,7 @@ gemm_patch_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
 // tensor and the argmax bytes are produced straight from the accumulators:
 //   * a tile is still a 16 x 8 conv patch (one 19-line TMA box, 16 MMAs).  Vertically it starts at conv line 14 ty - 1 of
 //     ITS image, so its 16 lines hold 7 pooling-window rows completely (bands overlap by 2 lines: 1.14x the conv work).
-//     Horizontally the tiles of a band do NOT overlap (columns 8k .. 8k+7): a CTA walks the 28 tiles of a band left to
+//     Horizontally the tiles of a band do NOT overlap (columns 8k .. 8k+7): a CTA walks the W / 8 tiles of a band left to
 //     right, and the one column a window needs from the tile on its left (window 4k = columns 8k-1, 8k, 8k+1) travels
 //     through a 2 KB carry slot in shared memory.  (A first version with tiles overlapping both ways -- 1.5x the conv
 //     work -- was correct and SLOWER than conv1 + maxpool_fwd_kernel, 2.03 vs 1.64 ms per 320 crops: the stem's main loop
@@ -1555,7 +1555,64 @@ struct PoolSmem {
   static constexpr int END = CARRY_OFF + 4 * 2048;
 };
 static_assert(PoolSmem::END <= PatchSmem::W_OFF + PATCH_W_BYTES, "conv1 + pool: tiles and carry slots must fit the free weight area");
-constexpr int POOL_BAND_TILES = 28;     // 224 / 8
+
+// 7 x 4 pooling windows x 8 channel chunks of one tile, 128 threads.  tile_s: [128 pixels][8 chunks ^ (pixel & 7)] bf16 of the
+// 16 x 8 patch; left_s: column 7 of the tile on the left ([16 lines][8 chunks ^ (line & 7)]).  CHECK: conv positions outside
+// the image are skipped (border tiles); the scan order (dy, dx) and the strict > keep the first maximum, as maxpool_fwd_kernel.
+template <bool CHECK>
+__device__ __forceinline__ void pool_scan(const uint8_t* tile_s, const uint8_t* left_s, const int tid, const StemPoolParams& sp,
+                                          __nv_bfloat16* P1, const int n, const int ty, const int k, const int y0) {
+  for (int item = tid; item < 28 * 8; item += 128) {
+    const int ck = item & 7, pw = item >> 3;
+    const int pr = pw >> 2, pc = pw & 3;
+    const int i = 7 * ty + pr, j = 4 * k + pc;
+    if (CHECK && i >= sp.Hp) continue;
+    uint4 u[9];
+    bool ok[9];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int ly = 2 * pr + dy;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int lx = 2 * pc - 1 + dx;
+        const int t9 = dy * 3 + dx;
+        ok[t9] = !CHECK || (y0 + ly >= 0 && y0 + ly < sp.H0 && 8 * k + lx >= 0 && 8 * k + lx < sp.H0);
+        const uint8_t* src = lx < 0 ? left_s + ly * 128 + ((ck ^ (ly & 7)) << 4)
+                                    : tile_s + (ly * 8 + lx) * 128 + ((ck ^ ((ly * 8 + lx) & 7)) << 4);
+        if (ok[t9]) u[t9] = *reinterpret_cast<const uint4*>(src);
+      }
+    }
+    uint32_t best[4], code[4];
+    bool first = true;
+#pragma unroll
+    for (int t9 = 0; t9 < 9; ++t9) {
+      if (CHECK && !ok[t9]) continue;
+      const uint32_t w[4] = {u[t9].x, u[t9].y, u[t9].z, u[t9].w};
+      const uint32_t tc = (uint32_t)t9 * 0x00010001u;
+      if (first) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { best[e] = w[e]; code[e] = tc; }
+        first = false;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t m = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&w[e]), *reinterpret_cast<const __nv_bfloat162*>(&best[e]));
+          best[e] = (w[e] & m) | (best[e] & ~m);
+          code[e] = (tc & m) | (code[e] & ~m);
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(P1 + geom_row(sp.g1, 0, n, i, j) * 64 + ck * 8) = make_uint4(best[0], best[1], best[2], best[3]);
+    const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      code[e] |= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&best[e]), zero2) & 0x00100010u;
+    uint2 pkc;
+    pkc.x = __byte_perm(code[0], code[1], 0x6420);
+    pkc.y = __byte_perm(code[2], code[3], 0x6420);
+    *reinterpret_cast<uint2*>(sp.arg + (((long)n * sp.Hp + i) * sp.Hp + j) * 64 + ck * 8) = pkc;
+  }
+}
 
 __global__ void __launch_bounds__(num_threads(8), 1)
 gemm_conv1_pool_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmB, const GemmDesc d,
@@ -1623,7 +1680,7 @@ gemm_conv1_pool_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_co
         const int n = (int)sp.fd_img.div((uint32_t)band), ty = band - n * sp.TY;
         // source-grid line of conv line y of image n = n * lines_per_img + pad_t + y; the box starts dy0 lines above
         const int line = n * sp.lines_per_img + d.src.pad_t + (14 * ty - 1) + tp.dy0;
-        for (int k = 0; k < POOL_BAND_TILES; ++k) {
+        for (int k = 0; k < sp.TX; ++k) {
           mbar_wait(aempty_bar(slot), phase ^ 1);
           mbar_expect_tx(afull_bar(slot), slab_bytes);
           tma_load_3d(smem_base + L::A_OFF + slot * PATCH_SLAB_BYTES, &tmA3, 0, d.src.pad_l + 8 * k + tp.dx0, line, afull_bar(slot));
@@ -1640,7 +1697,7 @@ gemm_conv1_pool_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_co
       uint32_t phase = 0;
       int it = 0;
       for (int band = blockIdx.x; band < num_bands; band += gridDim.x) {
-        for (int k = 0; k < POOL_BAND_TILES; ++k, ++it) {
+        for (int k = 0; k < sp.TX; ++k, ++it) {
           const int acc = it % NACC;
           const uint32_t acc_phase = (it / NACC) & 1;
           mbar_wait(tempty_bar(acc), acc_phase ^ 1);
@@ -1678,7 +1735,7 @@ gemm_conv1_pool_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_co
     for (int band = blockIdx.x; band < num_bands; band += gridDim.x) {
       const int n = (int)sp.fd_img.div((uint32_t)band), ty = band - n * sp.TY;
       const int y0 = 14 * ty - 1;
-      for (int k = 0; k < POOL_BAND_TILES; ++k, ++s) {
+      for (int k = 0; k < sp.TX; ++k, ++s) {
         if ((s & 1) != grp) continue;
         const int acc = s % NACC;
         const uint32_t acc_phase = (s / NACC) & 1;
@@ -1715,51 +1772,11 @@ gemm_conv1_pool_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_co
         named_bar_sync(1 + grp, 128);
         if (tid == 0) mbar_arrive(carry_bar(grp));
         const uint8_t* left_s = carry_s + ((s - 1) & 3) * 2048;   // column 7 of the tile on the left (k > 0 only)
-        for (int item = tid; item < 28 * 8; item += 128) {
-          const int ck = item & 7, pw = item >> 3;
-          const int pr = pw >> 2, pc = pw & 3;
-          const int i = 7 * ty + pr, j = 4 * k + pc;
-          if (i >= sp.Hp) continue;
-          uint32_t best[4], code[4];
-          bool first = true;
-#pragma unroll
-          for (int dy = 0; dy < 3; ++dy) {
-            const int ly = 2 * pr + dy, y = y0 + ly;
-            if (y < 0 || y >= sp.H0) continue;
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-              const int lx = 2 * pc - 1 + dx, x = 8 * k + lx;
-              if (x < 0 || x >= sp.H0) continue;
-              const uint8_t* src = lx < 0 ? left_s + ly * 128 + ((ck ^ (ly & 7)) << 4)
-                                          : tile_s + (ly * 8 + lx) * 128 + ((ck ^ ((ly * 8 + lx) & 7)) << 4);
-              const uint4 u = *reinterpret_cast<const uint4*>(src);
-              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-              const uint32_t tc = (uint32_t)(dy * 3 + dx) * 0x00010001u;
-              if (first) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { best[e] = w[e]; code[e] = tc; }
-                first = false;
-              } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const uint32_t m = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&w[e]),
-                                                 *reinterpret_cast<const __nv_bfloat162*>(&best[e]));
-                  best[e] = (w[e] & m) | (best[e] & ~m);
-                  code[e] = (tc & m) | (code[e] & ~m);
-                }
-              }
-            }
-          }
-          *reinterpret_cast<uint4*>(P1 + geom_row(sp.g1, 0, n, i, j) * 64 + ck * 8) = make_uint4(best[0], best[1], best[2], best[3]);
-          const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            code[e] |= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&best[e]), zero2) & 0x00100010u;
-          uint2 pkc;
-          pkc.x = __byte_perm(code[0], code[1], 0x6420);
-          pkc.y = __byte_perm(code[2], code[3], 0x6420);
-          *reinterpret_cast<uint2*>(sp.arg + (((long)n * sp.Hp + i) * sp.Hp + j) * 64 + ck * 8) = pkc;
-        }
+        // interior tiles (every conv position of the patch and of the carried column lies inside the image) take the scan
+        // without bounds checks: nine independent 16-byte loads, then the compare / select chain
+        const bool interior = k > 0 && y0 >= 0 && y0 + 15 < sp.H0 && 7 * ty + 6 < sp.Hp;
+        if (interior) pool_scan<false>(tile_s, left_s, tid, sp, P1, n, ty, k, y0);
+        else pool_scan<true>(tile_s, left_s, tid, sp, P1, n, ty, k, y0);
         named_bar_sync(1 + grp, 128);                         // the tile buffer is rewritten by this group's next tile
         ++t;
       }
@@ -2092,6 +2109,224 @@ conv_hshare_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_consta
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ===============================================================================================================
+// 3x3 convolution 64 -> 64 (layer1's conv2 and its input gradient), "horizontal taps as N".
+// The patch kernels above issue 36 tcgen05.mma of N = 64 per 128 pixels, and an N = 64 instruction reads 4 KB of A and 2 KB
+// of B from shared memory for 32 cycles of math -- these layers are bound by shared-memory operand bandwidth (measured
+// ~3 650 cycles per tile against 1 152 of tensor work).  With the three HORIZONTAL taps as the N dimension
+//     D[u, (xi, co)] = sum_yi sum_ci  X[u + (yi + dy0) lines, ci] * W[co, (yi, xi), ci]         N = 3 x 64 = 192, K = 3 x 64
+// a tile (source patch of 8 lines x 16 pixels, ONE 3-D TMA box of 10 lines) needs 12 instructions of N = 192 (4 KB + 6 KB
+// per 96 cycles of math), and the epilogue finishes the horizontal sum in registers:
+//     out[(l, w), co] = sum_xi D[(l, w + xi + dx0), (xi, co)]                                  warp shuffles inside a 16-lane line
+// then bias / ReLU / sign bits / mask bits exactly as epilogue_role.  A tile yields 8 x 14 output pixels (lanes 1..14 of its
+// 16 columns); tiles step by 14 columns.  Shared-memory operand traffic per 128 source pixels: 140 KB instead of 273 KB.
+// The three partial products are summed in a different order than the 36-instruction accumulation (fp32, same terms).
+// ===============================================================================================================
+constexpr int H3_NJ = 3, H3_NY = 3, H3_CO = 64, H3_N = H3_NJ * H3_CO, H3_OUTW = 16 - (H3_NJ - 1);
+constexpr int H3_SLAB_BYTES = (8 + H3_NY - 1) * 16 * 128;      // 20480
+constexpr int H3_SLABS = 6;
+constexpr int H3_W_TAP_BYTES = H3_N * BK * 2;                   // 24576
+struct H3Smem {
+  static constexpr int A_OFF = 0;
+  static constexpr int W_OFF = H3_SLABS * H3_SLAB_BYTES;
+  static constexpr int BAR_OFF = W_OFF + H3_NY * H3_W_TAP_BYTES;   // afull[S], aempty[S], tfull[2], tempty[2], wfull
+  static constexpr int TMEM_PTR_OFF = BAR_OFF + (2 * H3_SLABS + 6) * 8;
+  static constexpr int BIAS_OFF = TMEM_PTR_OFF + 16;
+  static constexpr int TOTAL = BIAS_OFF + H3_CO * 4;
+  static constexpr int DYN_BYTES = TOTAL + 1024;
+};
+static_assert(H3Smem::DYN_BYTES <= 232448, "conv3 hshare shared memory plan exceeds 227 KB");
+
+__global__ void __launch_bounds__(num_threads(8), 1)
+conv3_hshare_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmB, const GemmDesc d,
+                    const HsParams hp, const int num_tiles) {
+  using L = H3Smem;
+  constexpr int NACC = 2;
+  constexpr int ACC_COLS = 256;                   // accumulator stride in TMEM columns (192 used)
+  constexpr uint32_t TMEM_COLS = NACC * ACC_COLS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_base + L::BAR_OFF;
+  auto afull_bar = [&](int s) { return bar_base + 8u * s; };
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (H3_SLABS + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * H3_SLABS + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * H3_SLABS + NACC + a); };
+  const uint32_t wfull_bar = bar_base + 8u * (2 * H3_SLABS + 2 * NACC);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_PTR_OFF);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA3) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+    for (int s = 0; s < H3_SLABS; ++s) {
+      mbar_init(afull_bar(s), 1);
+      mbar_init(aempty_bar(s), 1);
+    }
+    for (int a = 0; a < NACC; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    mbar_init(wfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_base + L::TMEM_PTR_OFF),
+                 "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {
+    float* sb = reinterpret_cast<float*>(smem + L::BIAS_OFF);
+    for (int i = threadIdx.x; i < H3_CO; i += num_threads(8)) sb[i] = d.bias != nullptr ? d.bias[i] : 0.f;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(wfull_bar, (uint32_t)(H3_NY * H3_W_TAP_BYTES));
+      for (int t = 0; t < H3_NY; ++t) tma_load_2d(smem_base + L::W_OFF + t * H3_W_TAP_BYTES, &tmB, t * BK, 0, wfull_bar);
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int g = (int)hp.fd_wt.div((uint32_t)tile), k = tile - g * hp.WT;
+        mbar_wait(aempty_bar(slot), phase ^ 1);
+        mbar_expect_tx(afull_bar(slot), H3_SLAB_BYTES);
+        tma_load_3d(smem_base + L::A_OFF + slot * H3_SLAB_BYTES, &tmA3, 0, hp.col0 + H3_OUTW * k, 8 * g + hp.dy0, afull_bar(slot));
+        if (++slot == H3_SLABS) { slot = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, H3_N);
+      mbar_wait(wfull_bar, 0);
+      const uint64_t wdesc0 = make_smem_desc(smem_base + L::W_OFF);
+      int slot = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it % NACC;
+        const uint32_t acc_phase = (it / NACC) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * ACC_COLS);
+        mbar_wait(afull_bar(slot), phase);
+        tcgen05_fence_after();
+        const uint64_t adesc0 = make_smem_desc(smem_base + L::A_OFF + slot * H3_SLAB_BYTES);
+#pragma unroll
+        for (int yi = 0; yi < H3_NY; ++yi) {
+          // vertical tap yi: the same box, yi lines of 16 pixels (= 2 swizzle atoms = 128 descriptor units) further down
+          const uint64_t adesc = adesc0 + (uint64_t)(yi * 128);
+          const uint64_t bdesc = wdesc0 + (uint64_t)(yi * (H3_W_TAP_BYTES >> 4));
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk)
+            umma_bf16(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (yi | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(aempty_bar(slot));
+        if (++slot == H3_SLABS) { slot = 0; phase ^= 1; }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    // ===================== epilogue: two groups of 4 warps take alternate tiles =====================
+    const float* sbias = reinterpret_cast<const float*>(smem + L::BIAS_OFF);
+    const int q4 = warp & 3;                       // TMEM lane quarter: rows 32 q4 .. 32 q4 + 31 = source lines 2 q4, 2 q4 + 1
+    const int part = (warp - 2) >> 2;
+    const int row = q4 * 32 + lane;
+    const int l = row >> 4, w = row & 15;
+    const bool w_ok = w >= -hp.dx0 && w < -hp.dx0 + H3_OUTW;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.D);
+    for (int it = part, tile = blockIdx.x + part * gridDim.x; tile < num_tiles; it += 2, tile += 2 * gridDim.x) {
+      const int g = (int)hp.fd_wt.div((uint32_t)tile), k = tile - g * hp.WT;
+      const int acc = it % NACC;
+      const uint32_t acc_phase = (it / NACC) & 1;
+      const long line = 8L * g + l;
+      const int col = hp.col0 + H3_OUTW * k + w;
+      long m = -1, dest = -1;
+      if (w_ok && line < hp.lines && col < d.src.P) { m = line * d.src.P + col; dest = map_row(d.src, d.dst_kind, d.dst, m); }
+      uint32_t mb0 = 0xFFFFFFFFu, mb1 = 0xFFFFFFFFu;
+      if (dest >= 0 && d.mask_bits != nullptr) {
+        mb0 = __ldg(d.mask_bits + bits_index(m, 0, d.ld_mb));
+        mb1 = __ldg(d.mask_bits + bits_index(m, 1, d.ld_mb));
+      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * ACC_COLS);
+      float o[H3_CO];
+#pragma unroll
+      for (int c = 0; c < H3_CO; ++c) o[c] = 0.f;
+#pragma unroll
+      for (int xi = 0; xi < H3_NJ; ++xi) {
+        uint32_t r0[32], r1[32];
+        tmem_ld<32>(taddr + (uint32_t)(xi * H3_CO), r0);
+        tmem_ld<32>(taddr + (uint32_t)(xi * H3_CO + 32), r1);
+        tmem_ld_wait();
+        if (xi == H3_NJ - 1) {                       // the accumulator is in registers: release it before the last shuffles
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        // output pixel w needs D[(l, w + xi - 1), (xi, co)]: pull it from the lane that holds that source pixel (dx0 = -1 is
+        // checked by the plan builder, so the centre tap needs no shuffle)
+        if (xi == 1) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) { o[c] += __uint_as_float(r0[c]); o[32 + c] += __uint_as_float(r1[c]); }
+        } else {
+          const int src_lane = lane + xi - 1;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            o[c] += __shfl_sync(0xffffffffu, __uint_as_float(r0[c]), src_lane);
+            o[32 + c] += __shfl_sync(0xffffffffu, __uint_as_float(r1[c]), src_lane);
+          }
+        }
+      }
+      if (dest >= 0) {
+        uint32_t bo0 = 0u, bo1 = 0u;
+#pragma unroll
+        for (int c = 0; c < H3_CO; ++c) {
+          float v = o[c] + sbias[c];
+          if (d.relu) v = fmaxf(v, 0.f);
+          const uint32_t keep = ((c < 32 ? mb0 : mb1) >> (c & 31)) & 1u;
+          v = keep ? v : 0.f;
+          if (v > 0.f) { if (c < 32) bo0 |= 1u << c; else bo1 |= 1u << (c - 32); }
+          o[c] = v;
+        }
+        uint32_t pk[H3_CO / 2];
+#pragma unroll
+        for (int c = 0; c < H3_CO / 2; ++c) pk[c] = pack_bf16x2(o[2 * c], o[2 * c + 1]);
+        __nv_bfloat16* op = out + dest * d.ldd;
+#pragma unroll
+        for (int c = 0; c < H3_CO / 16; ++c) stg256(op + 16 * c, pk + 8 * c);
+        if (d.D_bits != nullptr) {
+          d.D_bits[bits_index(dest, 0, d.ld_db)] = bo0;
+          d.D_bits[bits_index(dest, 1, d.ld_db)] = bo1;
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// Wh3[(xi * 64 + n), yi * 64 + c] = Wt[n, tap(yi, xi) * 64 + c]
+__global__ void repack_h3_weights_kernel(const __nv_bfloat16* __restrict__ wt, __nv_bfloat16* __restrict__ wh, int ntaps,
+                                         int t00, int t01, int t02, int t10, int t11, int t12, int t20, int t21, int t22) {
+  const int taps[3][3] = {{t00, t01, t02}, {t10, t11, t12}, {t20, t21, t22}};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H3_N * H3_NY * 64; i += gridDim.x * blockDim.x) {
+    const int rowi = i / (H3_NY * 64), kcol = i - rowi * (H3_NY * 64);
+    const int xi = rowi / 64, n = rowi - xi * 64, yi = kcol / 64, c = kcol - yi * 64;
+    wh[i] = wt[(long)n * ntaps * 64 + taps[yi][xi] * 64 + c];
   }
 }
 
@@ -2499,6 +2734,59 @@ static int run_conv_hshare(const GemmPlanSm100& p, cudaStream_t st) {
   return 0;
 }
 
+// Plan for conv3_hshare_kernel from the descriptor of a 3x3 64 -> 64 op (any 3 x 3 tap grid: forward or input gradient).
+// `wh_buf`: device buffer of 192 * 192 bf16 owned by the caller; it receives the re-ordered weights.
+int build_conv3_hshare_sm100(const GemmDesc& d, void* wh_buf, GemmPlanSm100* p) {
+  if (int rc = build_gemm_sm100(d, p)) return rc;
+  RGIE_CHECK(p->patch == 1 && p->patch_ny == 3 && p->patch_nx == 3, "conv3_hshare: not a 3x3 64 -> 64 patch op");
+  RGIE_CHECK(!d.d_fp32 && d.mask == nullptr && d.res == nullptr && d.A2 == nullptr && d.ldd % 16 == 0 && d.Cout == 64,
+             "conv3_hshare: unsupported epilogue operands");
+  RGIE_CHECK(p->patch_dx0 == -1 && d.src.pad_l + p->patch_dx0 >= 0, "conv3_hshare: the horizontal taps must be -1, 0, +1");
+  const int (*t)[4] = p->patch_tap;
+  repack_h3_weights_kernel<<<64, 256>>>(reinterpret_cast<const __nv_bfloat16*>(d.Wt), reinterpret_cast<__nv_bfloat16*>(wh_buf), d.ntaps,
+                                        t[0][0], t[0][1], t[0][2], t[1][0], t[1][1], t[1][2], t[2][0], t[2][1], t[2][2]);
+  RGIE_LAUNCH_OK();
+  RGIE_CUDA_OK(cudaDeviceSynchronize());
+  const int dy0 = p->patch_dy0, dx0 = p->patch_dx0;
+  p->patch = 0; p->patch_2cta = 0; p->epi = 0; p->b2b = 0; p->pool = 0;
+  p->special = 2;
+  p->bn = H3_N;
+  const int P = d.src.P;
+  const long lines = d.a_rows / P;
+  p->hs_wt = ceil_div(d.src.W, H3_OUTW);
+  p->hs_dy0 = dy0; p->hs_dx0 = dx0; p->hs_col0 = d.src.pad_l + dx0; p->hs_lines = lines;
+  p->num_m_tiles = (int)(((lines + 7) / 8) * p->hs_wt);
+  p->num_n_tiles = 1;
+  const int sms = gemm_sm100_num_sms();
+  p->grid = p->num_m_tiles < sms ? p->num_m_tiles : sms;
+  PFN_encodeTiled enc = get_encode_fn();
+  RGIE_CHECK(enc != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
+  cuuint64_t gdim[3] = {64, (cuuint64_t)P, (cuuint64_t)lines};
+  cuuint64_t gstride[2] = {64 * 2, (cuuint64_t)P * 64 * 2};
+  cuuint32_t box[3] = {64, 16, 8 + H3_NY - 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(&p->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d.A), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (conv3 hshare) failed with CUresult " + std::to_string((int)r));
+  p->tmA2 = p->tmA; p->tmD = p->tmA; p->tmR = p->tmA;
+  return make_map_2d(&p->tmB, wh_buf, (uint64_t)H3_NY * 64, (uint64_t)H3_N, BK, (uint32_t)H3_N);
+}
+
+static int run_conv3_hshare(const GemmPlanSm100& p, cudaStream_t st) {
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
+    RGIE_CUDA_OK(cudaFuncSetAttribute(conv3_hshare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H3Smem::DYN_BYTES));
+    attr_once.done();
+  }
+  HsParams hp;
+  hp.WT = p.hs_wt; hp.fd_wt = make_fastdiv((uint32_t)p.hs_wt); hp.dy0 = p.hs_dy0; hp.dx0 = p.hs_dx0; hp.col0 = p.hs_col0;
+  hp.lines = p.hs_lines;
+  conv3_hshare_kernel<<<p.grid, num_threads(8), H3Smem::DYN_BYTES, st>>>(p.tmA, p.tmB, p.d, hp, p.num_m_tiles);
+  RGIE_LAUNCH_OK();
+  return 0;
+}
+
 int run_conv1_pool(const GemmPlanSm100& p, cudaStream_t st) {
   static DeviceOnce attr_once;
   if (attr_once.needed()) {
@@ -2520,12 +2808,12 @@ int build_conv1_pool_sm100(const GemmDesc& conv1, void* P1, const Geom& g1, uint
   if (int rc = build_gemm_sm100(conv1, p)) return rc;
   RGIE_CHECK(p->patch == 2 && !p->patch_2cta && p->patch_ny == 4 && p->patch_nx == 1, "conv1 + pool: conv1 must be the 4-tap patch variant");
   RGIE_CHECK(conv1.relu && conv1.Cout == 64 && conv1.ntaps == 4 && conv1.src.planes == 1 && conv1.src.H == conv1.src.W &&
-             conv1.src.H == 2 * Hp && conv1.src.W == 8 * POOL_BAND_TILES, "conv1 + pool: unexpected stem geometry");
+             conv1.src.H == 2 * Hp && conv1.src.W % 8 == 0, "conv1 + pool: unexpected stem geometry");
   RGIE_CHECK(g1.planes == 1 && g1.n_img == conv1.src.n_img && g1.H == Hp && g1.W == Hp, "conv1 + pool: pooled geometry");
   StemPoolParams& sp = p->sp;
   sp.n_img = conv1.src.n_img; sp.H0 = conv1.src.H; sp.Hp = Hp;
   sp.lines_per_img = conv1.src.S / conv1.src.P;
-  sp.TY = ceil_div(Hp, 7); sp.TX = POOL_BAND_TILES;
+  sp.TY = ceil_div(Hp, 7); sp.TX = conv1.src.W / 8;     // tiles per band: 8 conv columns = 4 pooled columns each
   RGIE_CHECK((long)sp.n_img * sp.TY < (1L << 31), "conv1 + pool: too many bands");
   sp.fd_img = make_fastdiv((uint32_t)sp.TY);           // band -> image
   sp.fd_tx = make_fastdiv((uint32_t)sp.TX);
@@ -2539,6 +2827,7 @@ int run_gemm_sm100(const GemmPlanSm100& p, cudaStream_t st) {
   if (p.b2b == 1) return run_b2b(p, st);
   if (p.d.m_end <= p.d.m_begin) return 0;
   if (p.special == 1) return run_conv_hshare(p, st);
+  if (p.special == 2) return run_conv3_hshare(p, st);
   if (p.patch == 1) return p.patch_2cta ? run_patch_2cta<64, 3, 3>(p, st) : run_patch<64, 3, 3>(p, st);     // 3x3, 64 -> 64 (layer1)
   if (p.patch == 2) return p.patch_2cta ? run_patch_2cta<64, 4, 1>(p, st) : run_patch<64, 4, 1>(p, st);     // conv1 forward: 4 vertical taps
   if (p.patch == 3) return run_patch<16, 4, 4>(p, st);     // conv1 input gradient: 4 x 4 taps, 64 -> 16

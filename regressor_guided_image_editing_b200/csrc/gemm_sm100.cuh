@@ -24,7 +24,7 @@ struct GemmPlanSm100 {
   // patch-tile variant (gemm_sm100.cu: gemm_patch_kernel): taps on a (dy, dx) grid, 16 x 8 pixel output tiles
   int patch, patch_ny, patch_nx, patch_dy0, patch_dx0, patch_wt, patch_tap[4][4];
   int patch_2cta;                   // 1: gemm_patch_2cta_kernel (cta_group::2, a CTA pair per pair of horizontally adjacent patches)
-  // special == 1: conv_hshare_kernel (conv1 input gradient with the horizontal taps as the N dimension)
+  // special == 1: conv_hshare_kernel (conv1 input gradient with the horizontal taps as the N dimension); 2: conv3_hshare_kernel
   int special, hs_wt, hs_dy0, hs_dx0, hs_col0;
   long hs_lines;
   int num_m_tiles, num_n_tiles;
@@ -40,6 +40,8 @@ struct GemmPlanSm100 {
 
 int build_gemm_sm100(const GemmDesc& d, GemmPlanSm100* p);
 int build_conv_hshare_sm100(const GemmDesc& d, const void* Wh, int dy0, int dx0, GemmPlanSm100* p);
+// 3x3 64 -> 64 with the horizontal taps as the N dimension (conv3_hshare_kernel); wh_buf: 192 x 192 bf16 device scratch of the caller
+int build_conv3_hshare_sm100(const GemmDesc& d, void* wh_buf, GemmPlanSm100* p);
 // back-to-back fusion of two consecutive 1x1 ops (the second one reads exactly what the first one writes)
 bool gemm_b2b_eligible(const GemmDesc& d1, const GemmDesc& d2);
 int build_gemm_b2b_sm100(const GemmDesc& d1, const GemmDesc& d2, GemmPlanSm100* p);

@@ -1097,12 +1097,26 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
   if (int rc = fuse_b2b(R, R->fwd_ops)) return rc;
   if (int rc = fuse_b2b(R, R->bwd_ops)) return rc;
   {
+    // layer1's 3x3 convs and their input gradients with the horizontal taps as the N dimension (conv3_hshare_kernel: 12
+    // instructions of N = 192 per tile instead of 36 of N = 64).  RGIE_CONV3_HSHARE=0 keeps the CTA-pair patch kernel.
+    static const int env_h3 = getenv("RGIE_CONV3_HSHARE") ? atoi(getenv("RGIE_CONV3_HSHARE")) : 1;
+    if (env_h3 && R->precision == RGIE_PREC_BF16) {
+      for (std::vector<GemmOp>* ops : {&R->fwd_ops, &R->bwd_ops})
+        for (GemmOp& op : *ops) {
+          if (op.absorbed || op.fused_next || op.plan.patch != 1 || op.d.d_fp32 || op.d.mask != nullptr || op.d.res != nullptr) continue;
+          void* wh = nullptr;
+          if (int rc = dev_alloc(R, &wh, (size_t)192 * 192 * 2, false)) return rc;
+          if (int rc = build_conv3_hshare_sm100(op.d, wh, &op.plan)) return rc;
+        }
+    }
+  }
+  {
     // conv1 + max-pool fused (RGIE_STEM_POOL=0 keeps conv1 -> c1 -> maxpool_fwd_kernel).  Needs the 16-channel conv1 operand,
     // the single-CTA 4-tap patch plan and the whole-batch stem (not the L2-resident sub-batching experiment).
     static const int env_pool = getenv("RGIE_STEM_POOL") ? atoi(getenv("RGIE_STEM_POOL")) : 1;
     GemmOp& c1op = R->fwd_ops[0];
     if (env_pool && R->precision == RGIE_PREC_BF16 && R->zz16 && R->stem_sub == 0 && c1op.plan.patch == 2 && !c1op.plan.patch_2cta &&
-        !c1op.fused_next) {
+        !c1op.fused_next && R->H0 % 8 == 0 && R->Hs[1] * 2 == R->H0) {
       R->conv1_plain = c1op.plan;
       if (int rc = build_conv1_pool_sm100(c1op.d, R->p1, R->gS[1], R->arg, R->Hs[1], &c1op.plan)) return rc;
       R->stem_pool = 1;

@@ -213,3 +213,19 @@ def test_fused_conv1_maxpool_is_bit_identical(tmp_path):
     assert torch.equal(a["pool"], b["pool"]), (a["pool"] - b["pool"]).abs().max().item()
     assert torch.equal(a["logits"], b["logits"])
     assert torch.equal(a["dimg"], b["dimg"])
+
+
+def test_conv3_hshare_on_and_off_pass_the_bf16_parity_tests():
+    """RGIE_CONV3_HSHARE (conv3_hshare_kernel: layer1's 3x3 convs and their input gradients with the three horizontal taps as
+    the N dimension, horizontal sum by warp shuffles in the epilogue) against the CTA-pair patch kernel: both settings must
+    pass the bf16 parity tests (tcgen05 vs the CUDA-core bf16 GEMM and vs the fp32 oracle, reference-generated golden).
+    The switch is read once per process: child processes."""
+    import subprocess, sys
+    for flag in ("1", "0"):
+        env = dict(os.environ, RGIE_CONV3_HSHARE=flag)
+        r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", __file__, "-k",
+                            "test_bf16_tcgen05_matches_bf16_simt_and_oracle or test_regressor_golden"],
+                           env=env, capture_output=True, text=True, timeout=300,
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        assert r.returncode == 0, f"RGIE_CONV3_HSHARE={flag}: " + r.stdout[-2000:] + r.stderr[-2000:]
+        assert "2 passed" in r.stdout
