@@ -1087,79 +1087,13 @@ __global__ void __launch_bounds__(kThreads) scale_bwd_gather_kernel(const float*
 // per pixel, and the gather kernel inverts the tables by binary search -- source column u receives from the contiguous
 // destination range {x : i0x(x) in {u - 1, u}} -- instead of re-deriving candidates with divisions per pixel.
 // Same arithmetic per coordinate (sample_coord) as scale_kernel / scale_bwd_gather_kernel, which remain the reference
-// form (RGIE_SCALE_TAB=0) and the path for tables that would not fit shared memory.
+// form (RGIE_SCALE_TAB=0 or RGIE_SCALE_COL=0) and the path for tables that would not fit shared memory.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kScaleRows = 16;          // destination (or source) rows per block
 __device__ __forceinline__ void build_coord_table(int* __restrict__ ti0, float* __restrict__ tw1, int n, float inv_s, float t) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const SampleCoord c = sample_coord(i, n, inv_s, t);
     ti0[i] = c.i0; tw1[i] = c.w1;
-  }
-}
-
-// forward (BWD=false): out = clamp(bilinear(in)); backward pass A (BWD=true): gm = g * [0 <= bilinear(in) <= 1] -> out,
-// block partials of d(sx, sy, cx, cy) from four plain sums (sum ggx, sum ggx*xn, sum ggy, sum ggy*yn)
-template <bool BWD>
-__global__ void __launch_bounds__(kThreads) scale_tab_kernel(const float* __restrict__ in, const float* __restrict__ gout,
-                                                            float* __restrict__ out, const float* __restrict__ p, int stride,
-                                                            float* __restrict__ partial, int H, int W) {
-  extern __shared__ __align__(16) int s_tab[];              // [W] i0x, [W] w1x
-  int* xi0 = s_tab;
-  float* xw1 = reinterpret_cast<float*>(s_tab + W);
-  const int b = blockIdx.y;
-  const float* pb = p + (long)b * stride;
-  const WarpCoef k = warp_coef(pb, H, W);
-  build_coord_table(xi0, xw1, W, k.inv_sx, k.t02);
-  __syncthreads();
-  const long base = (long)b * 3 * H * W;
-  const int HW = H * W;
-  const int ya = blockIdx.x * kScaleRows, yb = min(ya + kScaleRows, H);
-  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-  for (int y = ya; y < yb; ++y)
-  for (int x = threadIdx.x; x < W; x += blockDim.x) {
-    const SampleCoord syc = sample_coord(y, H, k.inv_sy, k.t12);
-    const int x0 = xi0[x], y0 = syc.i0, x1 = x0 + 1, y1 = y0 + 1;
-    const float wx1 = xw1[x], wx0 = 1.0f - wx1, wy1 = syc.w1, wy0 = 1.0f - wy1;
-    const bool vx0 = x0 >= 0 && x0 < W, vx1 = x1 >= 0 && x1 < W, vy0 = y0 >= 0 && y0 < H, vy1 = y1 >= 0 && y1 < H;
-    const int i = y * W + x;
-    float gix = 0.f, giy = 0.f;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float* pl = in + base + (long)c * HW;
-      const float v00 = (vy0 && vx0) ? pl[(long)y0 * W + x0] : 0.f;
-      const float v01 = (vy0 && vx1) ? pl[(long)y0 * W + x1] : 0.f;
-      const float v10 = (vy1 && vx0) ? pl[(long)y1 * W + x0] : 0.f;
-      const float v11 = (vy1 && vx1) ? pl[(long)y1 * W + x1] : 0.f;
-      const float o = v00 * (wx0 * wy0) + v01 * (wx1 * wy0) + v10 * (wx0 * wy1) + v11 * (wx1 * wy1);
-      if (!BWD) {
-        out[base + (long)c * HW + i] = clamp01(o);
-      } else {
-        const float g = in01(o) ? gout[base + (long)c * HW + i] : 0.f;
-        out[base + (long)c * HW + i] = g;
-        gix += g * ((v01 - v00) * wy0 + (v11 - v10) * wy1);
-        giy += g * ((v10 - v00) * wx0 + (v11 - v01) * wx1);
-      }
-    }
-    if (BWD) {
-      const float ggx = gix * 0.5f * (float)(W - 1), ggy = giy * 0.5f * (float)(H - 1);   // d/d(grid x), d/d(grid y)
-      a0 += ggx; a1 = fmaf(ggx, lin_coord(x, W), a1);
-      b0 += ggy; b1 = fmaf(ggy, lin_coord(y, H), b1);
-    }
-  }
-  if (BWD) {
-    float acc[4] = {a0, a1, b0, b1};
-    __shared__ float sums[4];
-    block_reduce_store<4>(acc, sums);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const float sx = pb[0], sy = pb[1], cx = pb[2], cy = pb[3];
-      const float a = 2.0f / (float)(W - 1), bb = 2.0f / (float)(H - 1);
-      float* dst = partial + ((long)b * gridDim.x + blockIdx.x) * 4;
-      dst[0] = (-sums[1] + (a * cx - 1.0f) * sums[0]) / (sx * sx) + sums[2] * (bb * cy / sy);      // d/dsx
-      dst[1] = (-sums[3] + (bb * (1.0f - sx) * cy - 1.0f) * sums[2]) / (sy * sy);                  // d/dsy
-      dst[2] = sums[0] * (-a * (1.0f - sx) / sx);                                                 // d/dcx
-      dst[3] = sums[2] * (-bb * (1.0f - sx) / sy);                                                // d/dcy
-    }
   }
 }
 
@@ -1422,123 +1356,6 @@ __global__ void affine_param_grad_kernel(const float* __restrict__ dtheta, const
   o[5] = dA[1][2] * bb;
 }
 
-// ---- shared-memory band versions of the sharpen kernels: one block = `R` image rows of one plane at full width.  The rows a
-// band needs (1 halo row forward; 2 halo rows of `in` and 1 of `gout` backward) are staged with coalesced 16-byte loads, every
-// 3x3 neighbourhood is then read from shared memory, and backward runs both of its passes (gradient of the clamped smoothing,
-// then its transposed 3x3) on the band, so the intermediate never goes to HBM: forward 2N bytes, backward 3N.
-// Arithmetic (fmaf order, clamp masks) is that of the kernels above.
-__device__ __forceinline__ void stage_band(float* dst, const float* __restrict__ src, long n_floats) {
-  if ((n_floats & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
-    const float4* s4 = reinterpret_cast<const float4*>(src);
-    float4* d4 = reinterpret_cast<float4*>(dst);
-    for (long i = threadIdx.x; i < n_floats / 4; i += blockDim.x) d4[i] = s4[i];
-  } else {
-    for (long i = threadIdx.x; i < n_floats; i += blockDim.x) dst[i] = src[i];
-  }
-}
-// 3x3 smoothing of pixel (r, x) of a staged band (row r of `t`, width W); the caller guarantees an interior pixel
-__device__ __forceinline__ float sharp_conv_s(const float* t, int r, int x, int W) {
-  const float k1 = 1.0f / 13.0f, k5 = 5.0f / 13.0f;
-  const float* r0 = t + (r - 1) * W + x;
-  const float* r1 = r0 + W;
-  const float* r2 = r1 + W;
-  float s = 0.f;
-  s = fmaf(k1, r0[-1], s); s = fmaf(k1, r0[0], s); s = fmaf(k1, r0[1], s);
-  s = fmaf(k1, r1[-1], s); s = fmaf(k5, r1[0], s); s = fmaf(k1, r1[1], s);
-  s = fmaf(k1, r2[-1], s); s = fmaf(k1, r2[0], s); s = fmaf(k1, r2[1], s);
-  return s;
-}
-
-__global__ void __launch_bounds__(kThreads) sharp_fwd_band_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                                                 const float* __restrict__ p, int stride, int H, int W, int R) {
-  extern __shared__ __align__(16) float band[];            // rows [ya, yb) of the plane
-  const int b = blockIdx.z, c = blockIdx.y;
-  const float f = p[(long)b * stride];
-  const int mode = sharp_mode(f);
-  const long off = ((long)b * 3 + c) * H * W;
-  const int y0 = blockIdx.x * R, y1 = min(y0 + R, H);
-  const int ya = max(y0 - 1, 0), yb = min(y1 + 1, H);
-  stage_band(band, in + off + (long)ya * W, (long)(yb - ya) * W);
-  __syncthreads();
-  for (int y = y0; y < y1; ++y)
-  for (int x = threadIdx.x; x < W; x += blockDim.x) {      // row loops: no per-pixel division
-    const float xin = band[(y - ya) * W + x];
-    float result = xin;
-    if (y >= 1 && y < H - 1 && x >= 1 && x < W - 1) result = clamp01(sharp_conv_s(band, y - ya, x, W));
-    float o;
-    if (mode == 0) o = result;
-    else if (mode == 1) o = xin;
-    else {
-      o = __fadd_rn(result, __fmul_rn(xin - result, f));
-      if (mode == 3) o = clamp01(o);
-    }
-    out[off + (long)y * W + x] = clamp01(o);
-  }
-}
-
-__global__ void __launch_bounds__(kThreads) sharp_bwd_band_kernel(const float* __restrict__ in, const float* __restrict__ gout,
-                                                                 float* __restrict__ gin, const float* __restrict__ p,
-                                                                 int stride, float* __restrict__ partial, int H, int W, int R) {
-  extern __shared__ __align__(16) float smem_s[];
-  const int b = blockIdx.z, c = blockIdx.y;
-  const float f = p[(long)b * stride];
-  const int mode = sharp_mode(f);
-  const long off = ((long)b * 3 + c) * H * W;
-  const int y0 = blockIdx.x * R, y1 = min(y0 + R, H);
-  const int ga = max(y0 - 1, 0), gb = min(y1 + 1, H);      // rows whose smoothing gradient this band needs
-  const int ia = max(ga - 1, 0), ib = min(gb + 1, H);      // rows of `in` needed to recompute the smoothing there
-  float* s_in = smem_s;                                    // [(R + 4), W]
-  float* s_g = s_in + (R + 4) * W;                         // [(R + 2), W]  gout rows [ga, gb)
-  float* s_deg = s_g + (R + 2) * W;                        // [(R + 2), W]  d(clamped smoothing) rows [ga, gb)
-  float* s_gx = s_deg + (R + 2) * W;                       // [R, W]        direct d(in) term rows [y0, y1)
-  stage_band(s_in, in + off + (long)ia * W, (long)(ib - ia) * W);
-  stage_band(s_g, gout + off + (long)ga * W, (long)(gb - ga) * W);
-  __syncthreads();
-  float acc[1] = {0.f};
-  for (int y = ga; y < gb; ++y)
-  for (int x = threadIdx.x; x < W; x += blockDim.x) {
-    const int yr = y - ga;
-    const float xin = s_in[(y - ia) * W + x];
-    const bool interior = y >= 1 && y < H - 1 && x >= 1 && x < W - 1;
-    float conv = 0.f, result = xin;
-    if (interior) { conv = sharp_conv_s(s_in, y - ia, x, W); result = clamp01(conv); }
-    float g = s_g[yr * W + x];
-    float g_res = 0.f, g_x = 0.f;
-    const bool own = y >= y0 && y < y1;                    // rows of this band (the halo rows belong to the neighbours)
-    if (mode == 0) { g = in01(result) ? g : 0.f; g_res = g; }
-    else if (mode == 1) { g = in01(xin) ? g : 0.f; g_x = g; }
-    else {
-      const float o = __fadd_rn(result, __fmul_rn(xin - result, f));
-      g = in01(o) ? g : 0.f;
-      g_res = g - g * f;
-      g_x = g * f;
-      if (own) acc[0] += g * (xin - result);
-    }
-    if (interior) s_deg[yr * W + x] = in01(conv) ? g_res : 0.f;
-    else { s_deg[yr * W + x] = 0.f; g_x += g_res; }
-    if (own) s_gx[(y - y0) * W + x] = g_x;
-  }
-  __syncthreads();
-  const float k1 = 1.0f / 13.0f, k5 = 5.0f / 13.0f;
-  for (int y = y0; y < y1; ++y)
-  for (int x = threadIdx.x; x < W; x += blockDim.x) {
-    const int yr = y - y0;
-    float s = 0.f;
-#pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-      const int yy = y + dy;
-      if (yy < 0 || yy >= H) continue;
-#pragma unroll
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int xx = x + dx;
-        if (xx < 0 || xx >= W) continue;
-        s = fmaf((dy == 0 && dx == 0) ? k5 : k1, s_deg[(yy - ga) * W + xx], s);
-      }
-    }
-    gin[off + (long)y * W + x] = s_gx[yr * W + x] + s;
-  }
-  block_reduce_store<1>(acc, partial + ((long)b * 3 + c) * gridDim.x + blockIdx.x);
-}
 // ---------------------------------------------------------------------------------------------------------------
 // Marching kernels (W % 4 == 0): a thread owns FOUR adjacent columns and walks down a band of rows with the three input
 // rows it needs (6 values each: its 4 columns + one neighbour either side) rolling through registers, so every input
@@ -1546,7 +1363,9 @@ __global__ void __launch_bounds__(kThreads) sharp_bwd_band_kernel(const float* _
 // (gdeg) goes through a 4-row ring in shared memory (one __syncthreads per row), the transposed 3x3 reads it from
 // there, and the direct term of the previous row waits in registers -- in + g are read once, gin is written once (3N),
 // no intermediate in HBM.  The 9-term fmaf chains are those of sharp_conv / sharp_bwd_b_kernel, in the same order (the
-// [0 <= conv <= 1] mask of a saturated neighbourhood depends on it).
+// [0 <= conv <= 1] mask of a saturated neighbourhood depends on it).  (An earlier form that staged whole row bands of in,
+// g, gdeg and the direct term in shared memory -- 80 KB per block, scalar 3x3 reads -- measured 0.58 ms backward against 0.53
+// for the two global-memory passes and 0.19 for this one; it is no longer in the file.)
 // ---------------------------------------------------------------------------------------------------------------
 struct Row6 { float v[6]; };     // columns x0-1 .. x0+4 of one row (zero outside the image: only read for interior pixels)
 __device__ __forceinline__ Row6 load_row6(const float* __restrict__ row, int x0, int W, bool valid) {
@@ -1709,23 +1528,6 @@ SharpMarch sharp_march(int H, int W) {
   return m;
 }
 
-// rows per band and shared-memory bytes of the band kernels (0 rows = fall back to the global-memory kernels)
-// MEASURED (B200, 64 x 512^2): forward 0.156 -> 0.125 ms (default on); the fused backward is SLOWER than the two global-memory
-// passes (0.583 vs 0.529 ms: 80 KB of shared memory per block, three shared-memory passes of scalar 3x3 reads), so backward
-// keeps the two-pass kernels unless RGIE_SHARP_BAND=1.
-struct SharpBand { int R, nb; size_t smem_f, smem_b; };
-SharpBand sharp_band(int H, int W, bool backward) {
-  SharpBand s;
-  s.R = ceil_div(H, 64) < 8 ? 8 : ceil_div(H, 64);          // at most 64 bands per plane (partials per image: 3 * 64)
-  s.nb = ceil_div(H, s.R);
-  s.smem_f = (size_t)(s.R + 2) * W * sizeof(float);
-  s.smem_b = (size_t)(4 * s.R + 8) * W * sizeof(float);
-  static const int env_band = getenv("RGIE_SHARP_BAND") ? atoi(getenv("RGIE_SHARP_BAND")) : -1;   // 0 off, 1 on for both
-  const bool on = env_band == 1 || (env_band != 0 && !backward);
-  if (!on || (backward ? s.smem_b : s.smem_f) > 160 * 1024) s.R = 0;
-  return s;
-}
-
 int plane_blocks(int HW) { int n = ceil_div(HW, kThreads * 4); return n > 64 ? 64 : (n < 1 ? 1 : n); }
 
 }  // namespace
@@ -1804,18 +1606,6 @@ int rgie_filter_fwd(int kind, const float* in, float* out, const float* p, int p
         RGIE_LAUNCH_OK();
         return 0;
       }
-      const SharpBand sb = sharp_band(H, W, false);
-      if (sb.R > 0) {
-        static DeviceOnce attr_once;
-        if (attr_once.needed()) {
-          RGIE_CUDA_OK(cudaFuncSetAttribute(sharp_fwd_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-          RGIE_CUDA_OK(cudaFuncSetAttribute(sharp_bwd_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-          attr_once.done();
-        }
-        sharp_fwd_band_kernel<<<dim3(sb.nb, 3, B), kThreads, sb.smem_f, st>>>(in, out, p, p_stride, H, W, sb.R);
-        RGIE_LAUNCH_OK();
-        return 0;
-      }
       dim3 grid(plane_blocks(HW), 3, B);
       sharp_fwd_kernel<<<grid, kThreads, 0, st>>>(in, out, p, p_stride, H, W);
       RGIE_LAUNCH_OK();
@@ -1837,16 +1627,10 @@ int rgie_filter_fwd(int kind, const float* in, float* out, const float* p, int p
     }
     case RGIE_F_SCALE: {
       RGIE_CHECK(H >= 2 && W >= 2, "scale: image too small");
-      // forward keeps the direct-coordinate kernel: measured 0.135 ms vs 0.152 ms for the table-driven one (64 x 512^2);
-      // the tables pay in the backward passes (0.77 -> 0.50 ms)
+      // column-marching kernel: 0.104 ms against 0.135 ms for the direct-coordinate kernel below (64 x 512^2; a per-block
+      // coordinate table in shared memory measured 0.152 ms and is no longer in the file).  RGIE_SCALE_COL=0: kernel below
       if (scale_col_on()) {
         scale_col_kernel<false><<<dim3(ceil_div(W, kThreads), ceil_div(H, kScaleColRows), B), kThreads, 0, st>>>(in, nullptr, out, p, p_stride, nullptr, H, W);
-        RGIE_LAUNCH_OK();
-        return 0;
-      }
-      static const bool fwd_tab = getenv("RGIE_SCALE_TAB_FWD") && atoi(getenv("RGIE_SCALE_TAB_FWD")) != 0;
-      if (fwd_tab && scale_tab_ok(H, W)) {
-        scale_tab_kernel<false><<<dim3(ceil_div(H, kScaleRows), B), kThreads, 2 * W * sizeof(int), st>>>(in, nullptr, out, p, p_stride, nullptr, H, W);
         RGIE_LAUNCH_OK();
         return 0;
       }
@@ -1970,19 +1754,6 @@ int rgie_filter_bwd(int kind, const float* in, const float* gout, float* gin, co
         finalize_partials<<<B, 32, 0, st>>>(partial, 3 * sm.nb, 1, gp, gp_stride);
         break;
       }
-      const SharpBand sb = sharp_band(H, W, true);
-      if (sb.R > 0) {
-        static DeviceOnce attr_once;
-        if (attr_once.needed()) {
-          RGIE_CUDA_OK(cudaFuncSetAttribute(sharp_fwd_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-          RGIE_CUDA_OK(cudaFuncSetAttribute(sharp_bwd_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-          attr_once.done();
-        }
-        sharp_bwd_band_kernel<<<dim3(sb.nb, 3, B), kThreads, sb.smem_b, st>>>(in, gout, gin, p, p_stride, partial, H, W, sb.R);
-        RGIE_LAUNCH_OK();
-        finalize_partials<<<B, 32, 0, st>>>(partial, 3 * sb.nb, 1, gp, gp_stride);
-        break;
-      }
       const int nb = plane_blocks(HW);
       float* gdeg = ws + (long)B * kMaxBlk * 24;
       dim3 grid(nb, 3, B);
@@ -2025,17 +1796,16 @@ int rgie_filter_bwd(int kind, const float* in, const float* gout, float* gin, co
     }
     case RGIE_F_SCALE: {
       RGIE_CHECK(H >= 2 && W >= 2, "scale: image too small");
-      if (scale_tab_ok(H, W) && ceil_div(H, kScaleRows) <= kMaxBlk * 6) {
+      const dim3 gcol(ceil_div(W, kThreads), ceil_div(H, kScaleColRows), B);
+      if (scale_col_on() && scale_tab_ok(H, W) && (long)gcol.x * gcol.y <= kMaxBlk * 6) {
+        // pass A: column-marching kernel (masked gradient + four plain sums per block); pass B: table-driven gather
         const int nbt = ceil_div(H, kScaleRows);
         float* gmt = ws + (long)B * kMaxBlk * 24;
-        const dim3 gcol(ceil_div(W, kThreads), ceil_div(H, kScaleColRows), B);
-        const bool col = scale_col_on() && (long)gcol.x * gcol.y <= kMaxBlk * 6;
-        if (col) scale_col_kernel<true><<<gcol, kThreads, 0, st>>>(in, gout, gmt, p, p_stride, partial, H, W);
-        else scale_tab_kernel<true><<<dim3(nbt, B), kThreads, 2 * W * sizeof(int), st>>>(in, gout, gmt, p, p_stride, partial, H, W);
+        scale_col_kernel<true><<<gcol, kThreads, 0, st>>>(in, gout, gmt, p, p_stride, partial, H, W);
         RGIE_LAUNCH_OK();
         scale_gather_tab_kernel<<<dim3(nbt, B), kThreads, scale_gather_smem(H, W), st>>>(gmt, gin, p, p_stride, H, W);
         RGIE_LAUNCH_OK();
-        finalize_partials<<<B, 32, 0, st>>>(partial, col ? (int)(gcol.x * gcol.y) : nbt, 4, gp, gp_stride);
+        finalize_partials<<<B, 32, 0, st>>>(partial, (int)(gcol.x * gcol.y), 4, gp, gp_stride);
         break;
       }
       const int nb = plane_blocks(HW);

@@ -504,13 +504,6 @@ struct RgieRegressor {
   int H0 = 0;
   int zz16 = 0;          // conv1 operand as 16-channel pixels read through overlapped rows (pack_crops16_kernel)
   int tc32 = 0;          // fp32 mode on the tensor cores: weights are three bf16 planes, GEMMs run gemm_tc32_kernel
-  // L2-resident stem: pack -> conv1 -> max-pool (and max-pool^T -> conv1 input gradient) run per group of `stem_sub` crops
-  // through ONE small set of buffers that is overwritten group after group, so the 64-channel 224 x 224 tensors (6.4 MB per
-  // crop each way) are produced and consumed inside the 126 MB L2 instead of travelling through HBM.  0 = whole batch at once.
-  int stem_sub = 0;
-  Geom gZZs, gDYs;       // geometry of one group
-  void *zz_s = nullptr, *c1_s = nullptr, *dC1_s = nullptr;
-  GemmOp conv1_s, conv1t_s;   // conv1 forward / input gradient over one group
   // conv1 + max-pool in ONE launch (gemm_conv1_pool_kernel, bf16 tcgen05 mode): the 64-channel 224 x 224 stem activation is
   // never written to HBM.  `conv1_plain` keeps the plain conv1 plan (rgie_regressor_tap("stem") runs it on demand).
   int stem_pool = 0;
@@ -1052,48 +1045,10 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
       if (int rc = add_op(R, R->bwd_ops, d)) return rc;
     }
   }
-  // ---- L2-resident stem (see RgieRegressor::stem_sub).  RGIE_STEM_SUB = crops per group, 0 = off (default).
-  //      MEASURED (B200, 640 crops per step, same box, bit-identical results): whole batch 72.8 / 72.9 ms per step; groups of
-  //      16 crops 74.3, of 8 crops (51 MB of stem activation per group) 74.2 / 74.2, of 4 crops 75.9 ms -- the 8 GB per
-  //      micro-batch that stop travelling through HBM are paid back with interest by 40-160 small launches per pass (tails,
-  //      prologues, 390-790 more graph nodes per step).  The depth-first schedule does NOT pay even where it is cheapest
-  //      (three kernels, the largest tensors of the network); kept as an opt-in experiment.
-  {
-    static const int env_sub = getenv("RGIE_STEM_SUB") ? atoi(getenv("RGIE_STEM_SUB")) : 0;
-    if (env_sub > 0 && N % env_sub == 0 && N >= 2 * env_sub) {
-      R->stem_sub = env_sub;
-      const int NS = env_sub;
-      R->gZZs = R->zz16 ? make_geom(1, NS, H0, H0, 2, 1, 0, 4) : make_geom(1, NS, H0, H0, 2, 1, 0, 0);
-      R->gDYs = make_geom(1, NS, H0, H0, 1, 2, 1, 2);
-      if (int rc = dev_alloc(R, &R->zz_s, ((size_t)R->gZZs.rows() + R->gZZs.P) * (R->zz16 ? 16 : 64) * esz, true)) return rc;
-      if (int rc = dev_alloc(R, &R->c1_s, (size_t)NS * H0 * H0 * 64 * esz, true)) return rc;
-      if (int rc = dev_alloc(R, &R->dC1_s, (size_t)R->gDYs.rows() * 64 * esz, true)) return rc;
-      // conv1 forward over one group: the batch-wide descriptor with the group's geometry and buffers
-      GemmDesc d = R->fwd_ops[0].d;
-      d.A = R->zz_s; d.a_rows = R->gZZs.rows(); d.m_end = R->gZZs.rows();
-      d.src = R->gZZs; d.dst = R->gZZs; d.D = R->c1_s;
-      for (int a = 0; a < 4; ++a) d.row_off[a] = (long)(a - 2) * R->gZZs.P;
-      R->conv1_s.d = d;
-      if (R->precision == RGIE_PREC_BF16) { if (int rc = build_gemm_sm100(d, &R->conv1_s.plan)) return rc; }
-      else if (R->tc32) { if (int rc = build_gemm_tc32(d, &R->conv1_s.tplan)) return rc; }
-      // conv1 input gradient over one group (its destination pointer is moved group by group at run time)
-      GemmDesc t = R->bwd_ops.back().d;
-      t.A = R->dC1_s; t.a_rows = R->gDYs.rows(); t.m_end = R->gDYs.rows();
-      t.src = R->gDYs; t.dst = R->gDYs;
-      for (int a = 0; a < 4; ++a)
-        for (int j = 0; j < 4; ++j) t.row_off[a * 4 + j] = -((long)(a - 2) * R->gDYs.P + ((3 - j) - 2));
-      R->conv1t_s.d = t;
-      if (R->precision == RGIE_PREC_BF16) {
-        if (R->bwd_ops.back().plan.special == 1) {
-          if (int rc = build_conv_hshare_sm100(t, R->wh_dev, -1, -1, &R->conv1t_s.plan)) return rc;
-        } else {
-          if (int rc = build_gemm_sm100(t, &R->conv1t_s.plan)) return rc;
-        }
-      } else if (R->tc32) {
-        if (int rc = build_gemm_tc32(t, &R->conv1t_s.tplan)) return rc;
-      }
-    }
-  }
+  // (An "L2-resident stem" -- pack -> conv1 -> max-pool and the mirrored backward per group of 4-16 crops through small reused
+  //  buffers -- was measured on B200: 74.2-75.9 ms per step against 72.8 for the whole batch at once; the 8 GB per micro-batch
+  //  that stopped travelling through HBM were paid back with interest by 40-160 small launches per pass.  It is no longer in
+  //  the file; the stem activation now stays on chip through gemm_conv1_pool_kernel instead.)
   if (int rc = fuse_b2b(R, R->fwd_ops)) return rc;
   if (int rc = fuse_b2b(R, R->bwd_ops)) return rc;
   {
@@ -1112,10 +1067,10 @@ int rgie_regressor_create(const float* const* h_tensors, int n_tensors, int num_
   }
   {
     // conv1 + max-pool fused (RGIE_STEM_POOL=0 keeps conv1 -> c1 -> maxpool_fwd_kernel).  Needs the 16-channel conv1 operand,
-    // the single-CTA 4-tap patch plan and the whole-batch stem (not the L2-resident sub-batching experiment).
+    // the single-CTA 4-tap patch plan and a 224-type geometry (width a multiple of 8).
     static const int env_pool = getenv("RGIE_STEM_POOL") ? atoi(getenv("RGIE_STEM_POOL")) : 1;
     GemmOp& c1op = R->fwd_ops[0];
-    if (env_pool && R->precision == RGIE_PREC_BF16 && R->zz16 && R->stem_sub == 0 && c1op.plan.patch == 2 && !c1op.plan.patch_2cta &&
+    if (env_pool && R->precision == RGIE_PREC_BF16 && R->zz16 && c1op.plan.patch == 2 && !c1op.plan.patch_2cta &&
         !c1op.fused_next && R->H0 % 8 == 0 && R->Hs[1] * 2 == R->H0) {
       R->conv1_plain = c1op.plan;
       if (int rc = build_conv1_pool_sm100(c1op.d, R->p1, R->gS[1], R->arg, R->Hs[1], &c1op.plan)) return rc;
@@ -1142,40 +1097,30 @@ int rgie_regressor_forward_ex(RgieRegressor* R, const float* img, int B, int Hr,
   xf.mode = normalize;
   const int N = R->N, H0 = R->H0, H1 = R->Hs[1];
   const int pack_threads = (H0 * 4) % 224 == 0 ? 224 : 256;     // 4 work items per output pixel: whole iterations per line
-  // stem: pack -> conv1 -> max-pool, over the whole batch or (L2-resident) group by group through the small buffers; the
-  // per-GEMM profiling mode times the batch-wide launches
-  const bool sub = R->stem_sub > 0 && !R->profiling;
-  const int NG = sub ? R->stem_sub : N;                 // crops per group
-  const Geom& gz = sub ? R->gZZs : R->gZZ;
-  void* zz = sub ? R->zz_s : R->zz;
-  void* c1 = sub ? R->c1_s : R->c1;
-  const size_t p1_group = (size_t)NG * R->gS[1].S * 64 * R->esz;            // bytes of pooled rows per group
-  const size_t arg_group = (size_t)NG * H1 * H1 * 64;
-  for (int n0 = 0; n0 < N; n0 += NG) {
+  // stem: pack -> conv1 (+ max-pool in the same launch when fused) -> max-pool
+  {
     if (R->zz16) {
       if (R->dtype == 0)
-        pack_crops16_kernel<float><<<NG * H0, 224, 0, st>>>(img, offsets, step_ptr, off_step_stride, (float*)zz, gz, reps, Hr, Wr, xf, n0);
+        pack_crops16_kernel<float><<<N * H0, 224, 0, st>>>(img, offsets, step_ptr, off_step_stride, (float*)R->zz, R->gZZ, reps, Hr, Wr, xf, 0);
       else
-        pack_crops16_kernel<__nv_bfloat16><<<NG * H0, 224, 0, st>>>(img, offsets, step_ptr, off_step_stride, (__nv_bfloat16*)zz, gz,
-                                                                    reps, Hr, Wr, xf, n0);
+        pack_crops16_kernel<__nv_bfloat16><<<N * H0, 224, 0, st>>>(img, offsets, step_ptr, off_step_stride, (__nv_bfloat16*)R->zz, R->gZZ,
+                                                                   reps, Hr, Wr, xf, 0);
     } else if (R->dtype == 0) {
-      pack_crops_kernel<float><<<NG * H0, pack_threads, 0, st>>>(img, offsets, step_ptr, off_step_stride, (float*)zz, gz, reps, Hr, Wr,
-                                                                 xf, n0);
+      pack_crops_kernel<float><<<N * H0, pack_threads, 0, st>>>(img, offsets, step_ptr, off_step_stride, (float*)R->zz, R->gZZ, reps, Hr, Wr,
+                                                                xf, 0);
     } else {
-      pack_crops_kernel<__nv_bfloat16><<<NG * H0, pack_threads, 0, st>>>(img, offsets, step_ptr, off_step_stride, (__nv_bfloat16*)zz,
-                                                                         gz, reps, Hr, Wr, xf, n0);
+      pack_crops_kernel<__nv_bfloat16><<<N * H0, pack_threads, 0, st>>>(img, offsets, step_ptr, off_step_stride, (__nv_bfloat16*)R->zz,
+                                                                        R->gZZ, reps, Hr, Wr, xf, 0);
     }
     RGIE_LAUNCH_OK();
-    if (sub) { if (int rc = run_op_raw(R, R->conv1_s, st)) return rc; }
-    else if (int rc = run_op(R, R->fwd_ops[0], st, 0)) return rc;
-    if (R->stem_pool) continue;                  // fwd_ops[0] was conv1 + max-pool: p1 and the argmax bytes are written
-    char* p1g = (char*)R->p1 + (size_t)(n0 / NG) * p1_group;
-    uint8_t* argg = R->arg + (size_t)(n0 / NG) * arg_group;
-    if (R->dtype == 0)
-      maxpool_fwd_kernel<float><<<NG * H1, 256, 0, st>>>((const float*)c1, (float*)p1g, argg, R->gS[1], H0, 64);
-    else
-      maxpool_fwd_kernel<__nv_bfloat16><<<NG * H1, 256, 0, st>>>((const __nv_bfloat16*)c1, (__nv_bfloat16*)p1g, argg, R->gS[1], H0, 64);
-    RGIE_LAUNCH_OK();
+    if (int rc = run_op(R, R->fwd_ops[0], st, 0)) return rc;
+    if (!R->stem_pool) {             // otherwise fwd_ops[0] was conv1 + max-pool: p1 and the argmax bytes are written
+      if (R->dtype == 0)
+        maxpool_fwd_kernel<float><<<N * H1, 256, 0, st>>>((const float*)R->c1, (float*)R->p1, R->arg, R->gS[1], H0, 64);
+      else
+        maxpool_fwd_kernel<__nv_bfloat16><<<N * H1, 256, 0, st>>>((const __nv_bfloat16*)R->c1, (__nv_bfloat16*)R->p1, R->arg, R->gS[1], H0, 64);
+      RGIE_LAUNCH_OK();
+    }
   }
   for (size_t i = 1; i < R->fwd_ops.size(); ++i)
     if (int rc = run_op(R, R->fwd_ops[i], st, i)) return rc;
@@ -1218,29 +1163,13 @@ int rgie_regressor_backward(RgieRegressor* R, const float* dlogits, float* dimg,
   // d(pool out) is the destination of the last block op (layer1.0 c1 dgrad)
   const void* dP = R->bwd_ops[nb - 2].d.D;
   {
-    const bool sub = R->stem_sub > 0 && !R->profiling;
-    const int NG = sub ? R->stem_sub : N;
-    const int H0 = R->H0, H1 = R->Hs[1];
-    const Geom& gd = sub ? R->gDYs : R->gDY;
-    void* dC1 = sub ? R->dC1_s : R->dC1;
-    const size_t dp_group = (size_t)NG * R->gS[1].S * 64 * R->esz;
-    const size_t arg_group = (size_t)NG * H1 * H1 * 64;
-    const size_t dz_group = (size_t)NG * H0 * H0 * 16;                      // floats of packed input gradient per group
-    for (int n0 = 0; n0 < N; n0 += NG) {
-      const char* dPg = (const char*)dP + (size_t)(n0 / NG) * dp_group;
-      const uint8_t* argg = R->arg + (size_t)(n0 / NG) * arg_group;
-      if (R->dtype == 0)
-        maxpool_bwd_kernel<float><<<NG * H1, 256, 0, st>>>((const float*)dPg, argg, (float*)dC1, R->gS[1], gd, 64);
-      else
-        maxpool_bwd_kernel<__nv_bfloat16><<<NG * H1, 256, 0, st>>>((const __nv_bfloat16*)dPg, argg, (__nv_bfloat16*)dC1, R->gS[1], gd, 64);
-      RGIE_LAUNCH_OK();
-      if (sub) {
-        GemmOp o = R->conv1t_s;                 // same plan, destination moved to this group's rows of dZ
-        float* dzg = R->dZ + (size_t)(n0 / NG) * dz_group;
-        o.d.D = dzg; o.plan.d.D = dzg; o.tplan.d.D = dzg;
-        if (int rc = run_op_raw(R, o, st)) return rc;
-      } else if (int rc = run_op(R, R->bwd_ops[nb - 1], st, R->fwd_ops.size() + nb - 1)) return rc;
-    }
+    const int H1 = R->Hs[1];
+    if (R->dtype == 0)
+      maxpool_bwd_kernel<float><<<N * H1, 256, 0, st>>>((const float*)dP, R->arg, (float*)R->dC1, R->gS[1], R->gDY, 64);
+    else
+      maxpool_bwd_kernel<__nv_bfloat16><<<N * H1, 256, 0, st>>>((const __nv_bfloat16*)dP, R->arg, (__nv_bfloat16*)R->dC1, R->gS[1], R->gDY, 64);
+    RGIE_LAUNCH_OK();
+    if (int rc = run_op(R, R->bwd_ops[nb - 1], st, R->fwd_ops.size() + nb - 1)) return rc;
   }
   InXform xf = R->xf2;
   xf.mode = R->normalize;
