@@ -62,6 +62,26 @@ def _lib_sha():
         return None
 
 
+def _src_sha():
+    """sha256 over the sources librgie.so is built from (csrc/*.cu, *.cuh, Makefile, include/rgie.h), in name order.  nvcc's
+    output is not byte-reproducible (two clean builds of the same tree give different librgie.so hashes), so an ncu capture
+    under profiles/ is matched to the running build by this hash; tools/summarize_launches.py stamps the same value."""
+    import glob
+    import hashlib
+    csrc = os.path.join(ROOT, "regressor_guided_image_editing_b200", "csrc")
+    files = sorted(glob.glob(os.path.join(csrc, "*.cu")) + glob.glob(os.path.join(csrc, "*.cuh"))) + \
+        [os.path.join(csrc, "Makefile"), os.path.join(ROOT, "include", "rgie.h")]
+    h = hashlib.sha256()
+    try:
+        for fn in files:
+            h.update(os.path.basename(fn).encode() + b"\0")
+            with open(fn, "rb") as f:
+                h.update(f.read())
+        return h.hexdigest()[:16]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
@@ -352,7 +372,7 @@ def run_latent(args, dev, lib):
                          "frac": reg_flop / (reg_ms / 1e3) / 1e12 / peak, "traffic": None,
                          "span": "native regressor fwd+bwd of one step (resize 256->480, 160 crops, resnet50 fwd + dgrad, resize^T), "
                                  "653.9 GFLOP per image", "peak_source": which},
-            "cpu_baseline": None, "lib_sha256": _lib_sha()}
+            "cpu_baseline": None, "lib_sha256": _lib_sha(), "src_sha256": _src_sha()}
     return line
 
 
@@ -533,14 +553,15 @@ def main():
         traffic, traffic_src = None, None
         try:
             import glob
-            sha = _lib_sha()
+            sha, ssha = _lib_sha(), _src_sha()
             for cand in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_step_B32.json")), reverse=True):
                 pj = json.load(open(cand))
-                if eng.mb == 32 and sha is not None and pj.get("lib_sha256") == sha:
+                same = (sha is not None and pj.get("lib_sha256") == sha) or (ssha is not None and pj.get("src_sha256") == ssha)
+                if eng.mb == 32 and same:
                     traffic, traffic_src = pj["gemm_dram_bytes_per_launch"], os.path.relpath(cand, ROOT)
                     break
             if traffic is None:
-                traffic_src = "no ncu capture of this build (librgie.so sha256 %s) under profiles/: not reported" % sha
+                traffic_src = "no ncu capture of this build (librgie.so sha256 %s, sources %s) under profiles/: not reported" % (sha, ssha)
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
@@ -646,7 +667,7 @@ def main():
             "roofline": prof, "cpu_baseline": cpu_base,
             "regressor_fwd_bwd_ms": None if prof is None else prof["regressor_fwd_bwd_ms"],
             "gemm_ms_per_step": None if prof is None else prof["gemm_ms_per_step"],
-            "lib_sha256": _lib_sha(),
+            "lib_sha256": _lib_sha(), "src_sha256": _src_sha(),
             "final_mean_best_loss": float(res["best_loss"].mean().item())}
     print(json.dumps(line))
     if world > 1:

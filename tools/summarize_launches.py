@@ -35,7 +35,7 @@ for i in step:
     f[1] += e.get("gpu__time_duration.sum", 0.0)
     f[2] += e.get("dram__bytes_read.sum", 0.0) + e.get("dram__bytes_write.sum", 0.0)
 tot = sum(v[1] for v in fam.values())
-is_gemm = lambda k: k.startswith("gemm_") or k.startswith("conv_hshare")      # the tcgen05 row-shifted GEMM family
+is_gemm = lambda k: k.startswith("gemm_") or "hshare_kernel" in k      # the tcgen05 row-shifted GEMM family
 gemm = sum(v[1] for k, v in fam.items() if is_gemm(k))
 gemm_n = sum(v[0] for k, v in fam.items() if is_gemm(k))
 gemm_b = sum(v[2] for k, v in fam.items() if is_gemm(k))
@@ -51,6 +51,8 @@ if "--json" in sys.argv:
     sha = hashlib.sha256(open(so, "rb").read()).hexdigest()[:16] if os.path.exists(so) else None
     if "--sha" in sys.argv:          # the build that was profiled, when the in-tree library has been rebuilt since (bench.py prints lib_sha256)
         sha = sys.argv[sys.argv.index("--sha") + 1]
-    json.dump({"lib_sha256": sha, "step_launches": len(step), "step_us": tot, "gemm_launches": gemm_n, "gemm_us": gemm, "gemm_share": gemm / tot,
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench                     # the same source hash bench.py matches a capture by (nvcc output is not byte-reproducible)
+    json.dump({"lib_sha256": sha, "src_sha256": bench._src_sha(), "step_launches": len(step), "step_us": tot, "gemm_launches": gemm_n, "gemm_us": gemm, "gemm_share": gemm / tot,
                "gemm_dram_bytes": gemm_b, "gemm_dram_bytes_per_launch": gemm_b / max(gemm_n, 1),
                "families": {k: {"launches": v[0], "us": v[1], "dram_bytes": v[2]} for k, v in fam.items()}}, open(out, "w"), indent=1)
