@@ -63,19 +63,19 @@ def _lib_sha():
 
 
 def _src_sha():
-    """sha256 over the sources librgie.so is built from (csrc/*.cu, *.cuh, Makefile, include/rgie.h), in name order.  nvcc's
-    output is not byte-reproducible (two clean builds of the same tree give different librgie.so hashes), so an ncu capture
-    under profiles/ is matched to the running build by this hash; tools/summarize_launches.py stamps the same value."""
-    import glob
+    """sha256 over the sources the GEMM family of the regressor is built from (the kernels, their PTX helpers, the launch
+    plan, the Makefile with the compiler flags), in name order.  nvcc's output is not byte-reproducible (two clean builds of
+    one tree give different librgie.so hashes), so an ncu capture under profiles/ is matched to the running build by this
+    hash; tools/summarize_launches.py stamps the same value.  `roofline.traffic` is a statement about these kernels only, so
+    the filter / resize / update / MiDU sources are not part of it."""
     import hashlib
     csrc = os.path.join(ROOT, "regressor_guided_image_editing_b200", "csrc")
-    files = sorted(glob.glob(os.path.join(csrc, "*.cu")) + glob.glob(os.path.join(csrc, "*.cuh"))) + \
-        [os.path.join(csrc, "Makefile"), os.path.join(ROOT, "include", "rgie.h")]
+    names = ["Makefile", "common.cuh", "gemm_sm100.cu", "gemm_sm100.cuh", "regressor.cu", "sm100_ptx.cuh"]
     h = hashlib.sha256()
     try:
-        for fn in files:
-            h.update(os.path.basename(fn).encode() + b"\0")
-            with open(fn, "rb") as f:
+        for fn in names:
+            h.update(fn.encode() + b"\0")
+            with open(os.path.join(csrc, fn), "rb") as f:
                 h.update(f.read())
         return h.hexdigest()[:16]
     except Exception:

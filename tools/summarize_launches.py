@@ -27,13 +27,17 @@ def short(n):
     n = re.sub(r"rgie::(<unnamed>::)?", "", n)
     n = re.sub(r"\(.*$", "", n)
     return n
-fam = defaultdict(lambda: [0, 0.0, 0.0])
+TP, DT = "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"
+fam = defaultdict(lambda: [0, 0.0, 0.0, 0.0, 0.0])      # launches, us, DRAM bytes, us x tensor-pipe %, us x DRAM-throughput %
 for i in step:
     e = launch[i]
     f = fam[short(e["name"])]
+    t = e.get("gpu__time_duration.sum", 0.0)
     f[0] += 1
-    f[1] += e.get("gpu__time_duration.sum", 0.0)
+    f[1] += t
     f[2] += e.get("dram__bytes_read.sum", 0.0) + e.get("dram__bytes_write.sum", 0.0)
+    f[3] += t * e.get(TP, 0.0)
+    f[4] += t * e.get(DT, 0.0)
 tot = sum(v[1] for v in fam.values())
 is_gemm = lambda k: k.startswith("gemm_") or "hshare_kernel" in k      # the tcgen05 row-shifted GEMM family
 gemm = sum(v[1] for k, v in fam.items() if is_gemm(k))
@@ -42,8 +46,14 @@ gemm_b = sum(v[2] for k, v in fam.items() if is_gemm(k))
 print(f"# one optimisation step: {len(step)} launches, {tot:.1f} us (cold-cache, serialised under ncu: compare SHARES)")
 print(f"# GEMM family: {gemm_n} launches, {gemm:.1f} us, share {100 * gemm / tot:.1f}%, DRAM {gemm_b / 1e9:.2f} GB "
       f"({gemm_b / max(gemm_n, 1) / 1e6:.1f} MB per launch)")
+has_pipe = any(TP in launch[i] for i in step)
+if has_pipe:
+    gt = sum(v[3] for k, v in fam.items() if is_gemm(k)) / max(gemm, 1e-9)
+    gd = sum(v[4] for k, v in fam.items() if is_gemm(k)) / max(gemm, 1e-9)
+    print(f"# GEMM family, time-weighted over its launches: tensor pipe active {gt:.1f} %, DRAM throughput {gd:.1f} % of peak")
 for k, v in sorted(fam.items(), key=lambda kv: -kv[1][1]):
-    print(f"{v[1]:10.1f} us {100 * v[1] / tot:5.1f}%  x{v[0]:3d}  {v[2] / 1e9:7.3f} GB  {k}")
+    pipe = f"  tensor {v[3] / max(v[1], 1e-9):5.1f}%  dram {v[4] / max(v[1], 1e-9):5.1f}%" if has_pipe else ""
+    print(f"{v[1]:10.1f} us {100 * v[1] / tot:5.1f}%  x{v[0]:3d}  {v[2] / 1e9:7.3f} GB{pipe}  {k}")
 if "--json" in sys.argv:
     out = sys.argv[sys.argv.index("--json") + 1]
     import hashlib, os
@@ -55,4 +65,5 @@ if "--json" in sys.argv:
     import bench                     # the same source hash bench.py matches a capture by (nvcc output is not byte-reproducible)
     json.dump({"lib_sha256": sha, "src_sha256": bench._src_sha(), "step_launches": len(step), "step_us": tot, "gemm_launches": gemm_n, "gemm_us": gemm, "gemm_share": gemm / tot,
                "gemm_dram_bytes": gemm_b, "gemm_dram_bytes_per_launch": gemm_b / max(gemm_n, 1),
+               "gemm_tensor_pipe_pct_time_weighted": (gt if has_pipe else None), "gemm_dram_throughput_pct_time_weighted": (gd if has_pipe else None),
                "families": {k: {"launches": v[0], "us": v[1], "dram_bytes": v[2]} for k, v in fam.items()}}, open(out, "w"), indent=1)
