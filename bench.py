@@ -416,11 +416,14 @@ def main():
         Wc = min(W, 1)
         val, sec, K = cpu_reference_leg(K, Wc, H, H, threads, budget)
         W = Wc
-        config = dict(config, precision="fp32 (torch CPU)", micro_batch=1,
-                      parallelism=f"{threads} host threads, one image at a time (the reference's own loop)")
+        # `config` stays byte-identical to the native arm's (same workload, same keys): how the CPU arm runs it goes
+        # under its own key
+        how = {"precision": "fp32 (torch CPU)", "micro_batch": 1,
+               "parallelism": f"{threads} host threads, one image at a time (the reference's own loop)"}
         line = {"metric": "edited images/sec (100 steps, 512^2)", "value": val, "unit": "images/s", "n_gpus": args.gpus,
                 "steps": K, "warmup": W, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference", "config": config,
+                "reference_run": how,
                 "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port",
                                  "sample": f"1 image x {K} optimisation steps (of {STEPS_PER_IMAGE}; bounded to ~{budget:.0f} s "
                                            f"of CPU work) at {H}x{H}, per-step time extrapolated to 100 steps; all "

@@ -1,0 +1,64 @@
+"""CPU: the driver-facing contract of bench.py that can be checked without a GPU -- the reference arm's JSON line
+(`--impl reference`: the oracle port on the host cores, bounded sample), that its `config` is the native arm's own, that a
+non-zero rank of the reference arm exits without work, that the native arm refuses to run without CUDA, and that the
+source hash which ties an ncu capture under profiles/ to the running build is the one the newest capture carries."""
+import glob
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(args, env=None, timeout=600):
+    e = dict(os.environ, RGIE_CPU_BUDGET_S="5")
+    e.update(env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, cwd=ROOT, env=e, capture_output=True,
+                          text=True, timeout=timeout)
+
+
+def test_reference_arm_line():
+    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "1"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "edited images/sec (100 steps, 512^2)" and d["unit"] == "images/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["gpu_launches"] == 0
+    assert d["value"] > 0 and abs(d["value"] - 1.0 / (100 * d["ms_per_step"] / 1e3)) <= 1e-9 * d["value"] + 1e-12
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and "1 image x 1" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the config is the native arm's, key for key (what the CPU arm does differently sits under its own key)
+    cfg = d["config"]
+    assert cfg["workload"].startswith("configs[1]: parametric-filter edit (8 default filters), batch 64 synthetic 512x512")
+    assert cfg["precision"] == "bf16" and cfg["micro_batch"] == 32 and cfg["batch_per_gpu"] == 64
+    assert cfg["parallelism"].startswith("dp1 ")
+    assert d["reference_run"]["precision"].startswith("fp32")
+
+
+def test_reference_arm_other_ranks_exit_without_work():
+    r = _run(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"], env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"},
+             timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CUDA present")
+def test_native_arm_refuses_to_run_without_cuda():
+    r = _run(["--steps", "1", "--warmup", "1"], timeout=300)
+    assert r.returncode != 0 and "CUDA" in (r.stderr + r.stdout)
+    assert not [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+def test_newest_capture_under_profiles_matches_these_sources():
+    sys.path.insert(0, ROOT)
+    import bench
+    ssha = bench._src_sha()
+    assert ssha is not None and len(ssha) == 16
+    caps = [json.load(open(p)) for p in glob.glob(os.path.join(ROOT, "profiles", "*_step_B32.json"))]
+    assert any(c.get("src_sha256") == ssha for c in caps), \
+        "the GEMM-family sources changed since the last ncu launch list under profiles/: bench.py will report roofline.traffic = null"
