@@ -199,3 +199,25 @@ def test_fused_prefix_equals_four_passes(hw):
     for o, c in zip(offs, cnt):
         a, b = gp_fused[:, o:o + c], gp_seq[:, o:o + c]
         assert (a - b).abs().max().item() <= 2e-5 * (b.abs().max().item() + 1e-3), (o, a, b)
+
+
+def test_single_filters_vs_reference_generated_goldens(golden_dir):
+    """Each filter of the default list alone against the per-filter fixtures the REFERENCE generated (filters.pt `singles`,
+    oracle/gen_golden.py: the reference's apply_params on one filter, its autograd for d/d(param) and d/d(image))."""
+    IT = _mirror()
+    s = torch.load(os.path.join(golden_dir, "filters.pt"))["singles"]
+    im0 = O.synthetic_image(s["image_index"], s["h"], s["w"])[None]
+    gout = torch.randn(im0.shape, generator=torch.Generator().manual_seed(s["gout_seed"])).to(DEV)
+    assert len(s["cases"]) >= 18
+    for key, c in s["cases"].items():
+        im = im0.to(DEV).requires_grad_(True)
+        p = torch.tensor(float(c["value"]), device=DEV, requires_grad=True)
+        out = IT._DISPATCH[c["name"]](im, p)
+        gi, gp = torch.autograd.grad((out * gout).sum(), [im, p], allow_unused=True)
+        gp = torch.zeros(()) if gp is None else gp.cpu()
+        err = (out.detach().cpu() - c["out"]).abs().max().item()
+        assert err <= 2e-6, f"{key}: forward max-abs {err}"
+        gerr = (gi.cpu() - c["grad_im"]).abs().mean().item() / (c["grad_im"].abs().mean().item() + 1e-12)
+        assert gerr <= 1e-4, f"{key}: d(image) relative L1 {gerr}"
+        perr = abs(gp.item() - c["grad_p"].item()) / (abs(c["grad_p"].item()) + 1e-6 * gout.numel() ** 0.5)
+        assert perr <= 5e-4, f"{key}: d(param) {gp.item()} vs {c['grad_p'].item()}"
