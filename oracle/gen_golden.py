@@ -3,7 +3,7 @@
 Generates tests/golden/*.pt by running the UNMODIFIED reference Python (imported from /root/reference/src through
 oracle/ref_harness.py) on CPU.  Run in the build container only:
 
-    python -m oracle.gen_golden [--only filters|regressor|loop|loopk|loops|loop512|midu|munit]
+    python -m oracle.gen_golden [--only filters|filters_extra|regressor|loop|loopk|loops|loop512|midu|munit]
 
 The reference ships no tests/fixtures, so these vectors are the pin for the standalone oracle
 (oracle/oracle.py) and, through it, for the CUDA path.  Inputs are regenerated from seeds at test time; only outputs
@@ -104,6 +104,49 @@ def gen_filters(r):
     out["singles"] = dict(image_index=6, h=36, w=44, gout_seed=13, cases=singles)
     torch.save(out, os.path.join(GOLDEN_DIR, "filters.pt"))
     print("filters.pt:", len(out), "entries")
+
+
+def extra_filter_cases():
+    """(key, filter name, parameter tensor in the shape the reference's apply_* expects) -- the filters that filters.pt's
+    `singles` leave out: tone / colour curves, scale, and the six 'next' filters incl. bw (1-d parameter) and affine."""
+    g = torch.Generator().manual_seed(17)
+    cases = []
+    for v in (1.0, 2.2, 1.3):
+        cases.append((f"gamma_{v}", "gamma", torch.tensor(v)))
+    for v in (0.0, 0.3, 1.0):
+        cases.append((f"bright_{v}", "bright", torch.tensor(v)))
+    for v in (0.0, 0.4, 1.0):
+        cases.append((f"bw_{v}", "bw", torch.tensor([v])))                       # img_trans_torch_diff.py:67-70 indexes [:, None, None, None]
+    for v in (0.7, -2.1, 3.0):
+        cases.append((f"hue_{v}", "hue", torch.tensor(v)))
+    for v in (0.0, 0.5, 1.0):
+        cases.append((f"wb_{v}", "wb", torch.tensor(v)))
+    cases.append(("tone_random", "tone", (1.0 + 0.3 * torch.randn(8, generator=g)).view(1, 1, 8, 1)))
+    cases.append(("color_random", "color", (1.0 + 0.3 * torch.randn(24, generator=g)).view(1, 3, 8, 1)))
+    cases.append(("scale_a", "scale", torch.tensor([[1.2371, 1.1113, 9.37, 14.21]])))
+    cases.append(("scale_b", "scale", torch.tensor([[1.5311, 1.0173, 30.19, 5.23]])))
+    cases.append(("affine_a", "affine", torch.tensor([[[1.0371, 0.0513, 1.37], [-0.0431, 0.9713, -2.21]]])))
+    cases.append(("affine_b", "affine", torch.tensor([[[0.8713, -0.1211, 3.19], [0.0917, 1.1307, 1.43]]])))
+    return cases
+
+
+def gen_filters_extra(r):
+    """tests/golden/filters_extra.pt: one filter at a time through the reference's own apply_params (filter + clamp), with the
+    reference's autograd for d/d(param) and d/d(image)."""
+    h, w, image_index, gout_seed = 36, 44, 6, 19
+    im = torch.clamp(O.synthetic_image(image_index, h, w)[None] * 1.25 - 0.1, 0.0, 1.0)     # clamps / channel ties bite
+    gout = torch.randn(im.shape, generator=torch.Generator().manual_seed(gout_seed))
+    cases = {}
+    for key, name, p in extra_filter_cases():
+        pv = p.clone().requires_grad_(True)
+        imv = im.clone().requires_grad_(True)
+        out = r.image_transformations.apply_params(imv, {name: pv})[-1]
+        gp, gim = torch.autograd.grad((out * gout).sum(), [pv, imv], allow_unused=True)
+        cases[key] = dict(name=name, param=p.clone(), out=out.detach().clone(),
+                          grad_p=(gp.detach().clone() if gp is not None else torch.zeros_like(p)), grad_im=gim.detach().clone())
+    torch.save(dict(image_index=image_index, h=h, w=w, gout_seed=gout_seed, image_map="clamp(1.25 * synthetic - 0.1, 0, 1)",
+                    cases=cases), os.path.join(GOLDEN_DIR, "filters_extra.pt"))
+    print("filters_extra.pt:", len(cases), "cases")
 
 
 def gen_regressor(r):
@@ -270,6 +313,8 @@ def main():
     todo = [args.only] if args.only else ["filters", "midu", "regressor", "loop"]
     if "filters" in todo:
         gen_filters(r)
+    if "filters_extra" in todo:
+        gen_filters_extra(r)
     if "midu" in todo:
         gen_midu(r)
     if "regressor" in todo:

@@ -221,3 +221,27 @@ def test_single_filters_vs_reference_generated_goldens(golden_dir):
         assert gerr <= 1e-4, f"{key}: d(image) relative L1 {gerr}"
         perr = abs(gp.item() - c["grad_p"].item()) / (abs(c["grad_p"].item()) + 1e-6 * gout.numel() ** 0.5)
         assert perr <= 5e-4, f"{key}: d(param) {gp.item()} vs {c['grad_p'].item()}"
+
+
+def test_extra_filters_vs_reference_generated_goldens(golden_dir):
+    """filters_extra.pt (oracle/gen_golden.py --only filters_extra): tone / colour curves, scale, gamma, brightness, b&w (1-d
+    parameter), hue, white balance and the general affine warp, each alone through the REFERENCE's apply_params with its
+    autograd gradients, against the native kernels."""
+    IT = _mirror()
+    s = torch.load(os.path.join(golden_dir, "filters_extra.pt"))
+    im0 = torch.clamp(O.synthetic_image(s["image_index"], s["h"], s["w"])[None] * 1.25 - 0.1, 0.0, 1.0)
+    gout = torch.randn(im0.shape, generator=torch.Generator().manual_seed(s["gout_seed"])).to(DEV)
+    assert len(s["cases"]) == 21
+    for key, c in s["cases"].items():
+        im = im0.to(DEV).requires_grad_(True)
+        p = c["param"].to(DEV).requires_grad_(True)
+        out = IT._DISPATCH[c["name"]](im, p)
+        gi, gp = torch.autograd.grad((out * gout).sum(), [im, p], allow_unused=True)
+        gp = torch.zeros_like(c["param"]) if gp is None else gp.cpu()
+        warp = c["name"] in ("scale", "affine")
+        err = (out.detach().cpu() - c["out"]).abs().max().item()
+        assert err <= (2e-4 if warp else 2e-6), f"{key}: forward max-abs {err}"
+        gerr = (gi.cpu() - c["grad_im"]).abs().mean().item() / (c["grad_im"].abs().mean().item() + 1e-12)
+        assert gerr <= (2e-3 if warp else 1e-4), f"{key}: d(image) relative L1 {gerr}"
+        perr = (gp - c["grad_p"]).abs().max().item() / (c["grad_p"].abs().max().item() + 1e-6 * gout.numel() ** 0.5)
+        assert perr <= (5e-3 if warp else 5e-4), f"{key}: d(param) {gp.flatten()[:4]} vs {c['grad_p'].flatten()[:4]} rel {perr}"
