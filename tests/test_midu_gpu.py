@@ -39,12 +39,16 @@ def _pipe(device):
     return types.SimpleNamespace(unet=unet, scheduler=_FakeScheduler())
 
 
-def test_head_matches_reference_golden(golden_dir):
+@pytest.mark.parametrize("variant", ["sd", "sdxl"])
+def test_head_matches_reference_golden(golden_dir, variant):
+    """midu.pt: the reference's own `_create_midu_classifier` heads (SD: MiduClassifier.py:145-160, SDXL: :125-143), forward +
+    `valence_arousal_score` + autograd on CPU; the native head in fp32 mode."""
     from regressor_guided_image_editing_b200.guidance_classifier.ValenceArousalMidu import ValenceArousalMidu
     from regressor_guided_image_editing_b200.guidance_classifier.guidance_scores import valence_arousal_score
-    g = torch.load(os.path.join(golden_dir, "midu.pt"))["sd"]
-    clf = ValenceArousalMidu(_pipe(DEV), DEV, precision="fp32")
-    clf.model.load_state_dict(O.make_midu_head_state_dict(g["seed"]))
+    g = torch.load(os.path.join(golden_dir, "midu.pt"))[variant]
+    sdxl = variant == "sdxl"
+    clf = ValenceArousalMidu(_pipe(DEV), DEV, is_sdxl=sdxl, precision="fp32")
+    clf.model.load_state_dict(O.make_midu_head_state_dict(g["seed"], is_sdxl=sdxl))
     feat = torch.randn(2, 1280, g["hw"], g["hw"], generator=torch.Generator().manual_seed(g["feat_seed"]))
     f = feat.to(DEV).requires_grad_(True)
     pred = clf.head(f)
@@ -53,31 +57,14 @@ def test_head_matches_reference_golden(golden_dir):
     assert (pred.detach().cpu() - g["pred"]).abs().max().item() <= 2e-5
     assert abs(loss.item() - g["loss"].item()) <= 1e-5
     gs = gf.cpu()[:, ::64, ::2, ::2]
-    assert (gs - g["grad_slice"]).abs().max().item() <= 1e-3 * g["grad_slice"].abs().max().item() + 1e-7
+    if sdxl:
+        # four max-pools in a row: a near-tie of two window entries may route one gradient element elsewhere in another fp32
+        # summation order, so the slice is compared by direction and size (test_sdxl_head_vs_oracle bounds the same way)
+        cos = torch.nn.functional.cosine_similarity(gs.flatten(), g["grad_slice"].flatten(), dim=0).item()
+        assert cos >= 0.9999, cos
+    else:
+        assert (gs - g["grad_slice"]).abs().max().item() <= 1e-3 * g["grad_slice"].abs().max().item() + 1e-7
     assert abs(gf.abs().sum().item() - g["grad_abs_sum"].item()) <= 2e-3 * g["grad_abs_sum"].item()
-
-
-@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 2e-2)])
-def test_head_vs_oracle(precision, tol):
-    from regressor_guided_image_editing_b200.guidance_classifier.ValenceArousalMidu import ValenceArousalMidu
-    sd = O.make_midu_head_state_dict(3)
-    B = 32
-    feat = torch.randn(B, 1280, 8, 8, generator=torch.Generator().manual_seed(5))
-    fc = feat.clone().requires_grad_(True)
-    pc = O.midu_head_forward(fc, sd)
-    lc = O.valence_arousal_score(pc, True, None)
-    gc, = torch.autograd.grad(lc, fc)
-    clf = ValenceArousalMidu(_pipe(DEV), DEV, precision=precision)
-    clf.model.load_state_dict(sd)
-    f = feat.to(DEV).requires_grad_(True)
-    pn = clf.head(f)
-    ln = clf._calculate_score(f, clf.head, DEV, True, None)
-    gn, = torch.autograd.grad(ln, f)
-    scale = pc.abs().max().item()
-    assert (pn.detach().cpu() - pc.detach()).abs().max().item() <= tol * max(scale, 1.0)
-    cos = torch.nn.functional.cosine_similarity(gn.cpu().flatten(), gc.flatten(), dim=0).item()
-    assert cos >= (0.9999 if precision == "fp32" else 0.99), cos
-    assert abs(gn.norm().item() / gc.norm().item() - 1) <= (1e-3 if precision == "fp32" else 3e-2)
 
 
 @pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 2e-2)])
