@@ -3,7 +3,7 @@
 Generates tests/golden/*.pt by running the UNMODIFIED reference Python (imported from /root/reference/src through
 oracle/ref_harness.py) on CPU.  Run in the build container only:
 
-    python -m oracle.gen_golden [--only filters|filters_extra|regressor|loop|loopk|loops|loop512|midu|munit]
+    python -m oracle.gen_golden [--only filters|filters_extra|emonet|regressor|loop|loopk|loops|loop512|midu|munit]
 
 The reference ships no tests/fixtures, so these vectors are the pin for the standalone oracle
 (oracle/oracle.py) and, through it, for the CUDA path.  Inputs are regenerated from seeds at test time; only outputs
@@ -147,6 +147,27 @@ def gen_filters_extra(r):
     torch.save(dict(image_index=image_index, h=h, w=w, gout_seed=gout_seed, image_map="clamp(1.25 * synthetic - 0.1, 0, 1)",
                     cases=cases), os.path.join(GOLDEN_DIR, "filters_extra.pt"))
     print("filters_extra.pt:", len(cases), "cases")
+
+
+def gen_emonet(r):
+    """tests/golden/emonet.pt: the reference's own ValenceArousalLoss on an "EmoNet" checkpoint path (EmoNet.py:33-130: resnet50
+    with a 1-output head, Resize(256) + deterministic ten-crop of 224, denorm + ImageNet normalisation, fake arousal column),
+    forward + autograd w.r.t. the image on CPU, for a square and a non-square image."""
+    sd = O.make_regressor_state_dict(num_classes=1)
+    ck = {"state_dict": {("module.model." + k).replace("module.model.fc.", "module.model.last_linear."): v for k, v in sd.items()}}
+    path = os.path.join(tempfile.mkdtemp(), "EmoNet_valence_test.pth.tar")
+    torch.save(ck, path)
+    clf = r.ValenceArousalLoss(path, torch.device("cpu"), 1, is_minimized=True, requires_grad=True)
+    target = torch.tensor([[0.3, 0.0]])
+    out = dict(image_index=9, image_map="clamp(1.2 * synthetic - 0.1, 0, 1)", target=target, cases={})
+    for h, w in ((256, 256), (300, 340)):
+        img = torch.clamp(O.synthetic_image(9, h, w)[None] * 1.2 - 0.1, 0.0, 1.0).requires_grad_(True)
+        loss = clf(img, target=target)
+        g, = torch.autograd.grad(loss, img)
+        out["cases"][f"{h}x{w}"] = dict(h=h, w=w, pred=clf.fake_loss_metric.detach().clone(), loss=loss.detach().clone(),
+                                        grad_ds=g[0, :, ::4, ::4].clone(), grad_abs_sum=g.abs().sum())
+    torch.save(out, os.path.join(GOLDEN_DIR, "emonet.pt"))
+    print("emonet.pt written")
 
 
 def gen_regressor(r):
@@ -315,6 +336,8 @@ def main():
         gen_filters(r)
     if "filters_extra" in todo:
         gen_filters_extra(r)
+    if "emonet" in todo:
+        gen_emonet(r)
     if "midu" in todo:
         gen_midu(r)
     if "regressor" in todo:

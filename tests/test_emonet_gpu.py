@@ -52,6 +52,28 @@ def test_emonet_loss_and_gradient_match_oracle(ckpt, hw):
     assert rel <= 4e-3 and mx <= 5e-2
 
 
+def test_emonet_matches_reference_generated_golden(ckpt, golden_dir):
+    """emonet.pt: forward + d(image) of the REFERENCE's ValenceArousalLoss("...EmoNet...") on CPU (oracle/gen_golden.py --only
+    emonet) against the native fp32 path."""
+    from regressor_guided_image_editing_b200.baselines.losses.ValenceArousalLoss import ValenceArousalLoss
+    sd, path = ckpt
+    gold = torch.load(os.path.join(golden_dir, "emonet.pt"))
+    clf = ValenceArousalLoss(path, torch.device(DEV), 1, is_minimized=True, requires_grad=True, precision="fp32")
+    for key, g in gold["cases"].items():
+        img = torch.clamp(O.synthetic_image(gold["image_index"], g["h"], g["w"])[None] * 1.2 - 0.1, 0.0, 1.0)
+        x = img.to(DEV).requires_grad_(True)
+        loss = clf(x, target=gold["target"].to(DEV))
+        gi, = torch.autograd.grad(loss, x)
+        pred = clf.fake_loss_metric.detach().cpu()
+        assert (pred - g["pred"]).abs().max().item() <= 2e-5, key
+        assert abs(loss.item() - g["loss"].item()) <= 2e-5 * max(1.0, abs(g["loss"].item())), key
+        gs = gi.cpu()[0, :, ::4, ::4]
+        rel = (gs - g["grad_ds"]).abs().mean().item() / (g["grad_ds"].abs().mean().item() + 1e-20)
+        # against the oracle above the full-image figure is 1.4e-3 ... 2.6e-3 (bound 4e-3); this is a 1/16 sample of the pixels
+        assert rel <= 6e-3, f"{key}: d(image) mean-rel {rel}"
+        assert abs(gi.abs().sum().item() - g["grad_abs_sum"].item()) <= 2e-3 * g["grad_abs_sum"].item(), key
+
+
 def test_emonet_bf16_tracks_fp32(ckpt):
     from regressor_guided_image_editing_b200.baselines.models import EmoNet as E
     sd, path = ckpt
