@@ -68,6 +68,29 @@ def test_head_matches_reference_golden(golden_dir, variant):
 
 
 @pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 2e-2)])
+def test_head_vs_oracle(precision, tol):
+    from regressor_guided_image_editing_b200.guidance_classifier.ValenceArousalMidu import ValenceArousalMidu
+    sd = O.make_midu_head_state_dict(3)
+    B = 32
+    feat = torch.randn(B, 1280, 8, 8, generator=torch.Generator().manual_seed(5))
+    fc = feat.clone().requires_grad_(True)
+    pc = O.midu_head_forward(fc, sd)
+    lc = O.valence_arousal_score(pc, True, None)
+    gc, = torch.autograd.grad(lc, fc)
+    clf = ValenceArousalMidu(_pipe(DEV), DEV, precision=precision)
+    clf.model.load_state_dict(sd)
+    f = feat.to(DEV).requires_grad_(True)
+    pn = clf.head(f)
+    ln = clf._calculate_score(f, clf.head, DEV, True, None)
+    gn, = torch.autograd.grad(ln, f)
+    scale = pc.abs().max().item()
+    assert (pn.detach().cpu() - pc.detach()).abs().max().item() <= tol * max(scale, 1.0)
+    cos = torch.nn.functional.cosine_similarity(gn.cpu().flatten(), gc.flatten(), dim=0).item()
+    assert cos >= (0.9999 if precision == "fp32" else 0.99), cos
+    assert abs(gn.norm().item() / gc.norm().item() - 1) <= (1e-3 if precision == "fp32" else 3e-2)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 2e-2)])
 def test_sdxl_head_vs_oracle(precision, tol):
     """SDXL head variant (MiduClassifier.py:125-143): four conv + ReLU + max-pool stages on 32x32 mid-block features."""
     from regressor_guided_image_editing_b200.guidance_classifier.ValenceArousalMidu import ValenceArousalMidu
