@@ -10,6 +10,11 @@ best-x tracking BEFORE the update :78-81, returns best_x :97).  Two execution pa
   * generic: any other objective callable is evaluated through autograd each step; the Adam update and the best-x
     snapshot are the fused rgie_adam_step kernel (loss compared on the device, so the reference's two per-step host
     syncs disappear).
+
+`compute_clip_loss` (:151-183) is the reconstruction term of the script's default objective (weight_recon = 1.0).  Its
+image tower is OpenAI's `clip` package (third party, like diffusers' UNet: SURVEY.md 8f rank 3) -- used when importable, or
+any object with `.encode_image` assigned to `CLIP_MODEL`; everything around it (resize to 224, range mapping, feature
+normalisation, cosine of the first pair) is here, so `weight_recon > 0` runs through the generic path.
 """
 from __future__ import annotations
 
@@ -24,6 +29,42 @@ def get_condition_from_alpha(alpha, clf, img):                                  
     condition = clf.predict_loss_metric(img)
     condition = condition + torch.ones(condition.shape).to(condition.device) * alpha
     return torch.clamp(condition, min=0.0, max=1.0)
+
+
+CLIP_MODEL = None          # as in the reference (:151): loaded on first use; a caller may assign any module with .encode_image
+
+
+def _clip_image_tower(device):
+    global CLIP_MODEL
+    if CLIP_MODEL is None:
+        try:
+            import clip
+        except ImportError as e:
+            raise _lib.RgieError("weight_recon > 0 needs the CLIP image tower: install OpenAI's `clip` package (the reference "
+                                 "calls clip.load('ViT-B/32'), optimize_image.py:171-172) or assign a model with "
+                                 ".encode_image to baselines.optimize_image.CLIP_MODEL; or run with weight_recon=0") from e
+        CLIP_MODEL, _ = clip.load("ViT-B/32", device=device)
+    return CLIP_MODEL
+
+
+def _unit(features):
+    return features / features.norm(dim=-1, keepdim=True)
+
+
+def compute_clip_loss(image1, image2):                                                    # :152-183
+    """1 - cosine similarity of the CLIP image embeddings of the FIRST image pair.  Both images are resized to 224 x 224
+    (torchvision's tensor Resize: antialiased bilinear); if image1 lives in [0, 1] (decided by image1 alone, as in the
+    reference) both are mapped to [-1, 1] first."""
+    tower = _clip_image_tower(image1.device)
+    to_unit_range = bool(image1.min() >= 0)
+
+    def embed(image):
+        x = torch.nn.functional.interpolate(image, size=[224, 224], mode="bilinear", align_corners=False, antialias=True)
+        if to_unit_range:
+            x = (x - 0.5) / 0.5
+        return _unit(tower.encode_image(x))
+
+    return 1 - (embed(image1) * embed(image2)).sum(dim=-1)[0]
 
 
 def _fused_eligible(x0, params, objective_function):

@@ -1,7 +1,8 @@
 """Drop-in for the hot-path functions of src/optimize_image_param.py: `init_params` (:121-209),
 `initialize_parametric` (:212-234), `objective_function_parametric` (:237-259), `get_params_from_vector` (:262-292),
 and the caller right after the loop, `output_transform` (:295-312: evaluation + full-resolution re-render of the edit,
-SURVEY.md 8f rank 4).  Script glue (main, dataset loop, JPEG save, CLIP / discriminator terms) is out of scope (section 8).
+SURVEY.md 8f rank 4).  Script glue (main, dataset loop, JPEG save, discriminator loading) is out of scope (section 8); the CLIP term runs when its
+third-party image tower is available (baselines/optimize_image.py::compute_clip_loss).
 """
 from __future__ import annotations
 
@@ -102,9 +103,9 @@ def objective_function_parametric(x_opt, image, params, clf, weight_clf, weight_
     loss = weight_clf * clf(outputs[-1], target=target)
     if dis is not None and weight_dis > 0:
         loss = loss - weight_dis * dis(image)
-    if weight_recon > 0:
-        raise _lib.RgieError("the CLIP reconstruction term (optimize_image.py:152-183) is out of scope here "
-                             "(SURVEY.md 8f rank 3): run with weight_recon=0")
+    if weight_recon > 0:                            # CLIP reconstruction term; needs the third-party image tower (see there)
+        from .baselines.optimize_image import compute_clip_loss
+        loss = loss + weight_recon * compute_clip_loss(image, outputs[-1])
     return loss
 
 

@@ -171,3 +171,72 @@ def test_score_and_crop_mean_equal_reference():
                 assert torch.equal(sa, sb) and torch.equal(ga, gb)
     x = torch.rand(30, 4, generator=g)
     assert torch.equal(MeanReplicatedCrops(10)(x), RM(10)(x))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CLIP reconstruction term: everything AROUND the third-party image tower
+# ---------------------------------------------------------------------------------------------------------------
+class _FakeClipTower(torch.nn.Module):
+    """Seeded stand-in with CLIP's call surface (`encode_image` on a [B,3,224,224] batch -> [B,D] features)."""
+
+    def __init__(self):
+        super().__init__()
+        g = torch.Generator().manual_seed(31)
+        self.w1 = torch.nn.Parameter(0.2 * torch.randn(8, 3, 16, 16, generator=g))
+        self.w2 = torch.nn.Parameter(0.2 * torch.randn(32, 8 * 14 * 14, generator=g))
+
+    def encode_image(self, x):
+        assert x.shape[1:] == (3, 224, 224)
+        return torch.tanh(torch.nn.functional.conv2d(x, self.w1, stride=16)).flatten(1) @ self.w2.t()
+
+
+def _clip_pair(lo):
+    g = torch.Generator().manual_seed(32)
+    a = torch.rand(2, 3, 96, 130, generator=g)
+    b = (a + 0.1 * torch.randn(a.shape, generator=g)).clamp(0, 1)
+    return (a, b) if lo >= 0 else (2 * a - 1, 2 * b - 1)
+
+
+def test_clip_loss_needs_a_tower_and_says_so(monkeypatch):
+    import sys
+    from regressor_guided_image_editing_b200 import _lib
+    from regressor_guided_image_editing_b200.baselines import optimize_image as oi
+    monkeypatch.setattr(oi, "CLIP_MODEL", None)
+    monkeypatch.setitem(sys.modules, "clip", None)            # `import clip` raises ImportError
+    a, b = _clip_pair(0)
+    with pytest.raises(_lib.RgieError, match="clip"):
+        oi.compute_clip_loss(a, b)
+
+
+@pytest.mark.parametrize("lo", [0, -1])
+def test_clip_loss_properties(monkeypatch, lo):
+    from regressor_guided_image_editing_b200.baselines import optimize_image as oi
+    monkeypatch.setattr(oi, "CLIP_MODEL", _FakeClipTower())
+    a, b = _clip_pair(lo)
+    assert oi.compute_clip_loss(a, a).abs().item() <= 1e-6          # identical images: cosine 1
+    l = oi.compute_clip_loss(a, b)
+    assert l.dim() == 0 and 0 < l.item() < 2
+    # only the FIRST pair counts (the reference indexes [0] after the sum over features)
+    b2 = b.clone(); b2[1] = 0.5
+    assert oi.compute_clip_loss(a, b2).item() == l.item()
+
+
+@needs_ref
+@pytest.mark.parametrize("lo", [0, -1])
+def test_clip_loss_matches_reference(monkeypatch, lo):
+    """compute_clip_loss of the reference (baselines/optimize_image.py:152-183: torchvision Resize((224, 224)), Normalize(.5, .5)
+    when image1 >= 0, two encode_image calls, normalised features, 1 - cosine of the first pair) with the same tower."""
+    import importlib
+    ref_harness.install()
+    ref_oi = importlib.import_module("baselines.optimize_image")
+    from regressor_guided_image_editing_b200.baselines import optimize_image as oi
+    tower = _FakeClipTower()
+    monkeypatch.setattr(ref_oi, "CLIP_MODEL", tower)
+    monkeypatch.setattr(oi, "CLIP_MODEL", tower)
+    a, b = _clip_pair(lo)
+    b_r, b_m = b.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    l_r, l_m = ref_oi.compute_clip_loss(a, b_r), oi.compute_clip_loss(a, b_m)
+    assert torch.equal(l_r.detach(), l_m.detach())
+    g_r, = torch.autograd.grad(l_r, b_r)
+    g_m, = torch.autograd.grad(l_m, b_m)
+    assert torch.equal(g_r, g_m)

@@ -1,6 +1,8 @@
 """GPU: `output_transform` (optimize_image_param.py:295-312) -- the caller right after the optimisation loop: evaluation of
 the edit at the working size (two native regressor predictions + statistics) and the full-resolution re-render of the same
 parameters through the native filter kernels, against the oracle's apply_params on the same file."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -65,3 +67,58 @@ def test_output_transform_needs_configuration():
     with pytest.raises(_lib.RgieError):
         oip.output_transform(O.synthetic_image(3, 64, 64)[None].to(DEV), x0.to(DEV), {"params": params_trans, "clf": clf},
                              {"emotion_type_labels": ['Valence', 'Arousal']}, 0.1, ["x.png"])
+
+
+def test_parametric_objective_with_clip_reconstruction_term():
+    """weight_recon > 0 (the script's default objective, optimize_image_param.py:249-257): loss and d(loss)/d(x) of
+    objective_function_parametric with the native filters + native regressor + the CLIP term around a seeded stand-in tower,
+    against the CPU oracle's regressor term plus the same term evaluated on the oracle's edited image (compute_clip_loss is
+    pinned bit for bit to the reference's on CPU: tests/test_callers_cpu.py::test_clip_loss_matches_reference)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_callers_cpu import _FakeClipTower
+    from oracle import oracle as O
+    from regressor_guided_image_editing_b200 import optimize_image_param as oip
+    from regressor_guided_image_editing_b200.baselines import optimize_image as oi
+    from regressor_guided_image_editing_b200.baselines.losses.ValenceArousalLoss import ValenceArousalLoss
+    sd = O.make_regressor_state_dict()
+    h = w = 96
+    image = O.smooth_image(3, h, w)[None]
+    x = O.init_x0().clone()
+    x[0], x[1], x[34], x[35], x[36] = 0.2, 1.2, 1.1, 0.3, 0.8                      # exposure, saturation, contrast, sharp, blur
+    x[2:34] += 0.1 * torch.randn(32, generator=torch.Generator().manual_seed(41))   # tone + colour curves
+    x[37:41] = torch.tensor([1.2371, 1.1113, 9.37, 14.21])                          # scale at generic values (no kink)
+    target = torch.tensor([[0.7, 0.5]])
+    w_clf, w_rec = 0.15, 0.5
+    torch.manual_seed(2011)
+    offs = O.draw_crop_offsets(1, 1, 480, 480)
+
+    prev, tf32 = oi.CLIP_MODEL, torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False          # the stand-in tower's convolution would otherwise run in TF32 on the GPU
+    try:
+        oi.CLIP_MODEL = _FakeClipTower()
+        xc = x.clone().requires_grad_(True)
+        loss_reg, _, edited = O.objective_parametric(xc, image, sd, offs[0], target, w_clf)
+        clip_c = oi.compute_clip_loss(image, edited)
+        loss_c = loss_reg + w_rec * clip_c
+        g_c, = torch.autograd.grad(loss_c, xc)
+
+        oi.CLIP_MODEL = _FakeClipTower().to(DEV)
+        clf = ValenceArousalLoss(sd, torch.device(DEV), 1, is_minimized=True, requires_grad=True, precision="fp32")
+        _, params = oip.initialize_parametric(image.to(DEV), {"clf": clf, "dis": None, "weight_clf": w_clf, "weight_dis": 0.0,
+                                                              "weight_recon": w_rec, "target": target.to(DEV)})
+        xg = x.to(DEV).requires_grad_(True)
+        torch.manual_seed(2011)
+        loss_g = oip.objective_function_parametric(xg, **params)
+        g_g, = torch.autograd.grad(loss_g, xg)
+    finally:
+        oi.CLIP_MODEL, torch.backends.cudnn.allow_tf32 = prev, tf32
+    print("loss", loss_g.item(), loss_c.item(), "clip term", clip_c.item())
+    assert clip_c.item() > 1e-4                                                     # the term is live
+    assert abs(loss_g.item() - loss_c.item()) <= 1e-4
+    g_g = g_g.cpu()
+    for name, (o, n) in dict(exposure=(0, 1), saturation=(1, 1), tone=(2, 8), color=(10, 24), contrast=(34, 1), sharp=(35, 1),
+                             blur=(36, 1), scale=(37, 4)).items():
+        ref = g_c[o:o + n]
+        rel = (g_g[o:o + n] - ref).abs().max().item() / (ref.abs().max().item() + 1e-6)
+        assert rel <= (2e-2 if name == "scale" else 5e-3), (name, rel, g_g[o:o + n], ref)
