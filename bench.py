@@ -26,6 +26,8 @@ same, the default K=100 is exactly one full edit of the batch.
           native regressor, batch 16 at 256x256, through the reference's own call surface (initialize_imaginaire,
           objective_function_imaginaire, optimization); the generator is PyTorch (library convolutions),
           the regressor forward + input gradient and the Adam / best-x update are librgie.so.  Single GPU, extra line.
+  inputs : seeded synthetic images / regressor weights from bench_inputs.py; oracle/ is imported by the CPU
+          leg (cpu_reference_leg) only.
 --impl reference : times that same CPU implementation alone (the reference is pure Python/PyTorch; /root/reference does
           not exist on the GPU box, the oracle port is its restatement validated bit-exactly against it).
 """
@@ -161,13 +163,13 @@ def run_sweep(args, rank, world, dev, lib):
     """BASELINE.json configs[4]: --images N synthetic images, strong split over the ranks, final gather to rank 0."""
     import torch
     import torch.distributed as dist
-    from oracle import oracle as O          # seeded synthetic inputs / weights only
+    import bench_inputs as BI               # seeded synthetic inputs / weights (SURVEY.md 8(d))
     from regressor_guided_image_editing_b200 import engine, shard
 
     N, B, H, S = args.images, args.batch, args.size, args.sweep_steps
     begin, end = shard.partition(N, world, rank)
     batches = shard.micro_batches(begin, end, B)
-    sd = O.make_regressor_state_dict()
+    sd = BI.make_regressor_state_dict()
     eng = engine.ParametricEditEngine(sd, batch=B, height=H, width=H, num_steps=S, precision=args.precision,
                                       micro_batch=args.micro_batch, device=dev)
     n_local = end - begin
@@ -175,7 +177,7 @@ def run_sweep(args, rank, world, dev, lib):
     images_h = torch.empty(max(n_local, 1), 3, H, H, dtype=torch.float32).pin_memory()
     offs_h = torch.empty(1 + S, max(n_local, 1), 10, 2, dtype=torch.int32).pin_memory()
     for k, i in enumerate(range(begin, end)):
-        images_h[k] = O.synthetic_image(i, H, H)
+        images_h[k] = BI.synthetic_image(i, H, H)
         g = torch.Generator().manual_seed(2000 + i)
         offs_h[:, k] = torch.randint(0, eng.Hr - 448 + 1, (1 + S, 10, 2), generator=g, dtype=torch.int32)
     edited_d = torch.empty(max(n_local, 1), 3, H, H, dtype=torch.uint8, device=dev)
@@ -272,19 +274,19 @@ def run_sweep(args, rank, world, dev, lib):
 def run_latent(args, dev, lib):
     """BASELINE.json configs[2]: optimize_image_imaginaire.py's loop at batch 16, 256x256 (one GPU)."""
     import torch
-    from oracle import oracle as O          # seeded synthetic inputs / regressor weights only
+    import bench_inputs as BI               # seeded synthetic inputs / regressor weights (SURVEY.md 8(d))
     from regressor_guided_image_editing_b200 import optimize_image_imaginaire as oii
     from regressor_guided_image_editing_b200.baselines import optimize_image as oi
     from regressor_guided_image_editing_b200.baselines.losses.ValenceArousalLoss import ValenceArousalLoss
     from regressor_guided_image_editing_b200.external.imaginaire.generators.munit import Generator
 
     B, H, K, W = args.latent_batch, args.latent_size, max(args.steps, 1), max(args.warmup, 3)
-    sd = O.make_regressor_state_dict()
+    sd = BI.make_regressor_state_dict()
     torch.manual_seed(0)
     gen = Generator().to(dev)                                   # imagenet2imagenet.yaml, random init, training mode (:75-79)
     clf = ValenceArousalLoss(sd, dev, 1, is_minimized=True, is_input_range_0_1=False, requires_grad=True,
                              precision=args.precision)
-    images_h = torch.stack([2.0 * O.synthetic_image(300 + i, H, H) - 1.0 for i in range(B)]).pin_memory()
+    images_h = torch.stack([2.0 * BI.synthetic_image(300 + i, H, H) - 1.0 for i in range(B)]).pin_memory()
     edited_h = torch.empty(B, 3, H, H).pin_memory()
     style_h = torch.empty(B, 8, 1, 1).pin_memory()
 
@@ -436,7 +438,7 @@ def main():
     # ---------------------------------------------------------------------------------------------------------
     import torch
     import torch.distributed as dist
-    from oracle import oracle as O          # only for the seeded synthetic inputs/weights and the cpu_baseline leg
+    import bench_inputs as BI               # seeded synthetic inputs / weights; oracle/ is touched by cpu_reference_leg only
     from regressor_guided_image_editing_b200 import _lib, engine
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback of the product path)"
@@ -461,12 +463,12 @@ def main():
             dist.destroy_process_group()
         return
 
-    sd = O.make_regressor_state_dict()
+    sd = BI.make_regressor_state_dict()
     n_steps_total = W + K
     eng = engine.ParametricEditEngine(sd, batch=B, height=H, width=H, num_steps=max(n_steps_total, 1),
                                       precision=args.precision, micro_batch=args.micro_batch, device=dev)
     g = torch.Generator().manual_seed(1234 + rank)
-    images_h = torch.stack([O.synthetic_image(rank * B + i, H, H) for i in range(B)]).pin_memory()
+    images_h = torch.stack([BI.synthetic_image(rank * B + i, H, H) for i in range(B)]).pin_memory()
     offs_h = torch.randint(0, eng.Hr - 448 + 1, (1 + n_steps_total, B, 10, 2), generator=g, dtype=torch.int32).pin_memory()
 
     def barrier():

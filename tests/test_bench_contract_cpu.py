@@ -64,3 +64,33 @@ def test_capture_to_build_matching_uses_the_source_hash():
     if not any(c.get("src_sha256") == ssha for c in caps):
         pytest.skip("the GEMM-family sources changed since the last ncu launch list under profiles/: bench.py reports "
                     "roofline.traffic = null until tools/run_final.sh + tools/summarize_launches.py are re-run")
+
+
+def test_bench_inputs_are_the_oracles_inputs():
+    """bench.py's native arm draws its synthetic images / regressor weights from bench_inputs.py (not from oracle/); they must be
+    the very inputs the parity tests use."""
+    sys.path.insert(0, ROOT)
+    import bench_inputs as BI
+    from oracle import oracle as O
+    for idx, h, w in ((0, 64, 48), (63, 512, 512), (300, 256, 256)):
+        assert torch.equal(BI.synthetic_image(idx, h, w), O.synthetic_image(idx, h, w))
+    for nc in (4, 1):
+        a, b = BI.make_regressor_state_dict(nc), O.make_regressor_state_dict(num_classes=nc)
+        assert list(a.keys()) == list(b.keys())
+        assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_bench_touches_the_oracle_only_in_the_cpu_leg():
+    """Only `cpu_reference_leg` (the cpu_baseline leg and the --impl reference arm) may import oracle/."""
+    import ast
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    users = set()
+    for fn in [n for n in ast.walk(tree) if isinstance(n, (ast.FunctionDef, ast.AsyncFunctionDef))]:
+        for node in ast.walk(fn):
+            if isinstance(node, ast.ImportFrom) and (node.module or "").split(".")[0] == "oracle":
+                users.add(fn.name)
+            if isinstance(node, ast.Import) and any(a.name.split(".")[0] == "oracle" for a in node.names):
+                users.add(fn.name)
+    top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
+    assert not any("oracle" in ast.dump(n) for n in top)
+    assert users == {"cpu_reference_leg"}, users
