@@ -94,3 +94,23 @@ def test_bench_touches_the_oracle_only_in_the_cpu_leg():
     top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
     assert not any("oracle" in ast.dump(n) for n in top)
     assert users == {"cpu_reference_leg"}, users
+
+
+def test_roofline_numerator_is_an_independent_flop_count():
+    """bench.FLOP_PER_IMAGE_STEP (653.9 GFLOP = 10 crops x 65.39: the numerator of roofline.achieved) against PyTorch's own
+    FlopCounterMode over torchvision's resnet50 (fc -> 4) at one 448 x 448 crop: forward + input gradient, no weight gradients."""
+    from torch.utils.flop_counter import FlopCounterMode
+    from torchvision import models
+    sys.path.insert(0, ROOT)
+    import bench
+    net = models.resnet50()
+    net.fc = torch.nn.Linear(2048, 4)
+    net.eval()
+    for p in net.parameters():
+        p.requires_grad_(False)
+    x = torch.zeros(1, 3, 448, 448, requires_grad=True)
+    with FlopCounterMode(display=False) as fc:
+        net(x).sum().backward()
+    per_crop = fc.get_total_flops()
+    assert abs(10 * per_crop - bench.FLOP_PER_IMAGE_STEP) <= 1e-3 * bench.FLOP_PER_IMAGE_STEP, (per_crop, bench.FLOP_PER_IMAGE_STEP)
+    assert bench.STEPS_PER_IMAGE == 100
